@@ -205,6 +205,8 @@ class RefEnv:
             if self.kind == "arena":
                 actions = [b.get_action() for b in self.bots]   # bot_arena.py:51-52 (pre-tick state)
                 actions = [list(a) for a in actions]
+            if actions is None:
+                actions = []     # team config with no agent tanks (bot_team_configs)
             obs, rew, done, trunc, info = self.env.step([list(map(int, a)) for a in actions])
         return obs, rew, bool(done), info, actions
 
@@ -273,7 +275,7 @@ def record_trace(kind, seed, env_id, ticks, action_seed=None, **kw):
         rec["done"][t] = done
         rec["tanks"][t] = r.tank_state()
         rec["nbul"][t], rec["bullets"][t] = r.bullet_state(cap)
-        ua = np.asarray(used, dtype=np.int32)
+        ua = np.asarray(used if used is not None else [], dtype=np.int32).reshape(-1, 3)
         rec["actions"][t, :ua.shape[0]] = ua
         rec["rng_ctr"][t] = r.stream.ctr
         if done:
