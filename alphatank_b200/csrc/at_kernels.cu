@@ -1,0 +1,480 @@
+// at_kernels.cu - sm_100a kernels and the C ABI (include/alphatank_b200.h) of the batched alphaTank step.
+//
+// One fused kernel per tick (env_kernel<true>):
+//   phase A  one thread per env.  Tanks / bot FSMs of the block's 64 envs live in shared memory
+//            ([field][tank][thread], conflict-free), bullets stay in HBM as [slot][env] columns (every
+//            warp access is a contiguous run; the two advection passes, the dodge-reward scans and the
+//            obs reads hit L1 after the first touch).  Sequential per-env semantics (firing order, tank
+//            order) are trivially exact.  Rewards / done are written here; done envs are reset in place.
+//   phase B  each warp assembles the observation rows of its 32 envs in a shared-memory staging buffer
+//            (static wall / maze columns are written once per kernel for fixed maps) and ships every row
+//            with one bulk-async (TMA) shared->global copy, double buffered; rows whose byte length is not
+//            a multiple of 16 fall back to coalesced lane-strided stores.
+// The step is HBM-bound integer / fp64 work: no tensor cores anywhere.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/alphatank_b200.h"
+#include "at_host.h"
+#include "at_sim.h"
+
+using namespace at;
+
+// ------------------------------------------------------------------------------------------------ device
+namespace {
+
+struct SmemLayout {
+    int n, dpad;
+    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_ewlo, off_ewhi, off_tpack, off_thits,
+        off_bpack, off_tlive, off_tshot, off_ecnt, off_ezones, off_stage, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int n, int obs_dim) {
+    SmemLayout L;
+    L.n = n;
+    L.dpad = (obs_dim + 3) & ~3;
+    size_t o = 0;
+    L.off_trig = o; o += 722 * 8;
+    L.off_tx = o; o += (size_t)n * BS * 8;
+    L.off_ty = o; o += (size_t)n * BS * 8;
+    L.off_trew = o; o += (size_t)n * BS * 8;
+    L.off_bf0 = o; o += (size_t)n * BS * 8;
+    L.off_bf1 = o; o += (size_t)n * BS * 8;
+    L.off_ewlo = o; o += BS * 8;
+    L.off_ewhi = o; o += BS * 8;
+    L.off_tpack = o; o += (size_t)n * BS * 4;
+    L.off_thits = o; o += (size_t)n * BS * 4;
+    L.off_bpack = o; o += (size_t)n * BS * 4;
+    L.off_tlive = o; o += (size_t)n * BS * 4;
+    L.off_tshot = o; o += (size_t)n * BS * 4;
+    L.off_ecnt = o; o += BS * 4;
+    L.off_ezones = o; o += BS * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.off_stage = o; o += (size_t)(BS / 32) * 2 * L.dpad * 4;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void bulk_store_row(float *gdst, const float *ssrc, uint32_t bytes) {
+    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+template <bool IS_STEP>
+__global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c, const DevState st,
+                                                 const int32_t *__restrict__ actions,
+                                                 const uint8_t *__restrict__ mask, float *__restrict__ obs,
+                                                 float *__restrict__ rewards, uint8_t *__restrict__ done,
+                                                 int use_bulk) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const SmemLayout L = smem_layout(c.n_tanks, c.obs_dim);
+    BlockMem bm;
+    bm.trig = (double *)(smem + L.off_trig);
+    bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
+    bm.trew = (double *)(smem + L.off_trew);
+    bm.bf0 = (double *)(smem + L.off_bf0); bm.bf1 = (double *)(smem + L.off_bf1);
+    bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.thits = (uint32_t *)(smem + L.off_thits);
+    bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint32_t *)(smem + L.off_tlive);
+    bm.tshot = (int32_t *)(smem + L.off_tshot);
+    uint64_t *ewlo = (uint64_t *)(smem + L.off_ewlo), *ewhi = (uint64_t *)(smem + L.off_ewhi);
+    uint32_t *ecnt = (uint32_t *)(smem + L.off_ecnt), *ezones = (uint32_t *)(smem + L.off_ezones);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 722; i += BS) bm.trig[i] = st.trig[i];
+    __syncthreads();
+
+    // ---------------- phase A: one thread per env
+    const int64_t e = (int64_t)blockIdx.x * BS + tid;
+    bool emit = false;
+    if (e < st.N) {
+        Sim s(c, st, bm, e, tid);
+        if (IS_STEP) {
+            s.load();
+            float rw[MAX_TANKS];
+            const bool d = s.wrapper_step(actions ? actions + e * c.act_rows * 3 : nullptr, rw);
+            for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
+            done[e] = d ? 1 : 0;
+            if (d && c.auto_reset) s.env_reset();
+            s.store();
+            emit = obs != nullptr;
+        } else if (!mask || mask[e]) {
+            s.load();
+            s.env_reset();
+            s.store();
+            emit = obs != nullptr;
+        } else if (obs != nullptr) {
+            // not reset: nothing to write for this env
+        }
+        ecnt[tid] = s.cnt;
+        ezones[tid] = s.zones;
+        ewlo[tid] = s.wlo;
+        ewhi[tid] = s.whi;
+    }
+    __syncwarp();
+
+    // ---------------- phase B: the warp writes the observation rows of its 32 envs
+    const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
+    if (emit_mask == 0u) return;
+    float *stage = (float *)(smem + L.off_stage) + (size_t)warp * 2 * L.dpad;
+    const int D = c.obs_dim;
+    if (c.map != 2) {  // fixed map: static columns are staged once
+        for (int b = 0; b < 2; ++b) {
+            RowCtx rc{c, st, bm, stage + b * L.dpad, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
+            row_static(rc, lane);
+        }
+    }
+    __syncwarp();
+    int buf = 0;
+    for (int le = 0; le < 32; ++le) {
+        if (!((emit_mask >> le) & 1u)) continue;
+        const int q = warp * 32 + le;
+        const int64_t ee = (int64_t)blockIdx.x * BS + q;
+        for (int r = 0; r < c.rows; ++r) {
+            const int t = c.team_layout ? c.agent_tank[r] : r;
+            float *row = stage + buf * L.dpad;
+            if (use_bulk) {  // the copy issued from this buffer two rows ago must have drained
+                if (lane == 0) bulk_wait_read<1>();
+                __syncwarp();
+            }
+            RowCtx rc{c, st, bm, row, q, ee, ecnt[q], ezones[q], ewlo[q], ewhi[q]};
+            if (c.map == 2) row_static(rc, lane);
+            row_clear_bullets(rc, lane);
+            __syncwarp();
+            row_bullets(rc, lane, t);
+            row_tanks(rc, lane, t);
+            row_misc(rc, lane, t);
+            float *dst = obs + (ee * c.rows + r) * (int64_t)D;
+            if (use_bulk) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) bulk_store_row(dst, row, (uint32_t)D * 4u);
+            } else {
+                __syncwarp();
+                for (int j = lane; j < D; j += 32) dst[j] = row[j];
+                __syncwarp();
+            }
+            buf ^= 1;
+        }
+    }
+    if (use_bulk && lane == 0) bulk_wait_read<0>();
+}
+
+__global__ void gather_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
+                              PackedEnv *out) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < count) gather_env(c, st, first + q, out[q]);
+}
+__global__ void scatter_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
+                               const PackedEnv *in) {
+    int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < count) scatter_env(c, st, first + q, in[q]);
+}
+
+__global__ void info_kernel(const __grid_constant__ KCfg c, const DevState st, int32_t *winner, int32_t *hits,
+                            int32_t *be_hits, int32_t *change_time) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    int w = -1;
+    for (int i = 0; i < c.n_tanks; ++i) {
+        int64_t g = (int64_t)i * st.N + e;
+        if (w < 0 && (st.tpack[g] & TP_ALIVE)) w = i;
+        uint32_t h = st.thits[g];
+        if (hits) hits[e * c.n_tanks + i] = (int32_t)(h & 0xFFFFu);
+        if (be_hits) be_hits[e * c.n_tanks + i] = (int32_t)(h >> 16);
+        if (change_time) change_time[e * c.n_tanks + i] = st.change_time[g];
+    }
+    if (winner) winner[e] = w;
+}
+
+__global__ void synthetic_actions_kernel(uint64_t seed, int64_t env_id_base, int64_t n_envs, int rows, uint32_t tick,
+                                         int32_t *out) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_envs * rows) return;
+    int64_t e = k / rows;
+    int a = (int)(k % rows);
+    int64_t env_id = env_id_base + e;
+    uint32_t c0 = tick, c1 = 1u + (uint32_t)a, c2 = (uint32_t)((uint64_t)env_id & 0xFFFFFFFFu),
+             c3 = (uint32_t)((uint64_t)env_id >> 32);
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32));
+    out[k * 3 + 0] = (int32_t)(((uint64_t)c0 * 3u) >> 32);
+    out[k * 3 + 1] = (int32_t)(((uint64_t)c1 * 3u) >> 32);
+    out[k * 3 + 2] = (int32_t)(((uint64_t)c2 * 2u) >> 32);
+}
+
+__global__ void bfs_batch_kernel(const uint8_t *maze, const int32_t *query, int64_t n, int32_t *out) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int32_t *q = query + 5 * k;
+    const uint8_t *m = maze + (int64_t)q[0] * CELLS;
+    uint64_t lo = 0, hi = 0;
+    for (int i = 0; i < CELLS; ++i)
+        if (m[i]) { if (i < 64) lo |= 1ull << i; else hi |= 1ull << (i - 64); }
+    int nr, nc;
+    int len = bfs_first_step(lo, hi, q[1], q[2], q[3], q[4], &nr, &nc);
+    out[3 * k] = len; out[3 * k + 1] = len > 1 ? nr : -1; out[3 * k + 2] = len > 1 ? nc : -1;
+}
+__global__ void maze_kernel(uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *maze, uint32_t *ctr_out) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    uint32_t ctr = 0;
+    uint64_t lo, hi;
+    generate_maze_mask(seed, env_id_base + k, ctr, lo, hi);
+    for (int i = 0; i < CELLS; ++i) maze[k * CELLS + i] = (uint8_t)((i < 64 ? lo >> i : hi >> (i - 64)) & 1ull);
+    if (ctr_out) ctr_out[k] = ctr;
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------- host
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CUDA_TRY(x)                                                                                        \
+    do {                                                                                                   \
+        cudaError_t err__ = (x);                                                                           \
+        if (err__ != cudaSuccess)                                                                          \
+            return fail(AT_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__));                  \
+    } while (0)
+
+struct at_env {
+    at_config user_cfg;
+    KCfg k;
+    DevState st;
+    int device;
+    int64_t n_envs;
+    void *arena;  // one allocation, carved into the SoA columns (at_host.h arena_layout)
+    size_t arena_bytes;
+    int32_t *d_actions_scratch;
+    float *d_rewards_scratch;
+    uint8_t *d_done_scratch;
+    HostLuts luts;
+    size_t smem_bytes;
+    int64_t launches;
+};
+
+static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
+                             float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s) {
+    const int grid = (int)((env->n_envs + BS - 1) / BS);
+    const int use_bulk = env->k.row_bulk_ok && (((uintptr_t)d_obs & 15u) == 0) ? 1 : 0;
+    if (is_step)
+        env_kernel<true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
+                                                          d_done, use_bulk);
+    else
+        env_kernel<false><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
+                                                           d_done, use_bulk);
+    env->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+extern "C" {
+
+const char *at_last_error(void) { return g_err.c_str(); }
+const char *at_version(void) { return "alphatank_b200 0.1 (sm_100a)"; }
+
+int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_t seed, int device, at_env **out) {
+    if (!cfg || !out || n_envs <= 0) return fail(AT_ERR_ARG, "at_create: null config / handle or n_envs <= 0");
+    KCfg k;
+    std::string msg = build_kcfg(cfg, seed, env_id_base, k);
+    if (!msg.empty()) return fail(AT_ERR_ARG, "at_create: " + msg);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || device < 0 || device >= ndev) {
+        cudaGetLastError();
+        return fail(AT_ERR_NOGPU, "at_create: no usable CUDA device (the batched env has no CPU fallback)");
+    }
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(AT_ERR_NOGPU, "at_create: device is not sm_100 class; this library ships sm_100a code only");
+
+    at_env *env = new at_env();
+    env->user_cfg = *cfg;
+    env->k = k;
+    env->device = device;
+    env->n_envs = n_envs;
+    env->launches = 0;
+    build_luts(env->luts);
+    const ArenaLayout L = arena_layout(k, n_envs);
+    env->arena_bytes = L.bytes;
+    if (cudaMalloc(&env->arena, L.bytes) != cudaSuccess) {
+        std::string m = std::string("at_create: cudaMalloc of ") + std::to_string(L.bytes) + " bytes failed";
+        cudaGetLastError();
+        delete env;
+        return fail(AT_ERR_CUDA, m);
+    }
+    cudaMemset(env->arena, 0, L.bytes);
+    char *b = (char *)env->arena;
+    bind_state(env->st, b, L, n_envs);
+    env->d_actions_scratch = (int32_t *)(b + L.o_act);
+    env->d_rewards_scratch = (float *)(b + L.o_rw);
+    env->d_done_scratch = (uint8_t *)(b + L.o_dn);
+    cudaMemcpy(b + L.o_trig, env->luts.trig.data(), 722 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(b + L.o_corn, env->luts.corn.data(), 361 * 4 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(b + L.o_pend, env->luts.pend.data(), PEND_LUT * 8, cudaMemcpyHostToDevice);
+
+    env->smem_bytes = smem_layout(k.n_tanks, k.obs_dim).total;
+    cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+    cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+    // GamingENV.__init__ -> self.reset() (gaming_env.py:43): the constructor's own reset consumes draws
+    int rc = launch_env_kernel(env, false, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+    if (rc == AT_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(AT_ERR_CUDA, "at_create: reset kernel failed");
+    if (rc != AT_OK) {
+        cudaFree(env->arena);
+        delete env;
+        return rc;
+    }
+    *out = env;
+    return AT_OK;
+}
+
+int at_destroy(at_env *env) {
+    if (!env) return AT_OK;
+    cudaSetDevice(env->device);
+    cudaFree(env->arena);
+    delete env;
+    return AT_OK;
+}
+
+int at_obs_dim(const at_env *env) { return env ? env->k.obs_dim : AT_ERR_ARG; }
+int at_obs_rows(const at_env *env) { return env ? env->k.rows : AT_ERR_ARG; }
+int at_action_rows(const at_env *env) { return env ? env->k.act_rows : AT_ERR_ARG; }
+int at_num_walls(const at_env *env) { return env ? env->k.n_walls : AT_ERR_ARG; }
+int64_t at_num_envs(const at_env *env) { return env ? env->n_envs : AT_ERR_ARG; }
+int64_t at_launch_count(const at_env *env) { return env ? env->launches : AT_ERR_ARG; }
+
+int at_reset(at_env *env, const uint8_t *d_mask, float *d_obs, void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_reset: null handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    return launch_env_kernel(env, false, nullptr, d_mask, d_obs, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_rewards, uint8_t *d_done, void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_step: null handle");
+    if (env->k.act_rows > 0 && !d_actions) return fail(AT_ERR_ARG, "at_step: this mode needs an actions array");
+    if (!d_rewards || !d_done) return fail(AT_ERR_ARG, "at_step: rewards / done must not be null");
+    CUDA_TRY(cudaSetDevice(env->device));
+    return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream);
+}
+
+int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
+                 void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_step_host: null handle");
+    if (!h_rewards || !h_done) return fail(AT_ERR_ARG, "at_step_host: rewards / done must not be null");
+    cudaStream_t s = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int64_t N = env->n_envs;
+    if (env->k.act_rows > 0) {
+        if (!h_actions) return fail(AT_ERR_ARG, "at_step_host: this mode needs an actions array");
+        CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)N * env->k.act_rows * 3 * 4,
+                                 cudaMemcpyHostToDevice, s));
+    }
+    int rc = launch_env_kernel(env, true, env->d_actions_scratch, nullptr, d_obs, env->d_rewards_scratch,
+                               env->d_done_scratch, s);
+    if (rc != AT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(h_rewards, env->d_rewards_scratch, (size_t)N * env->k.rows * 4, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h_done, env->d_done_scratch, (size_t)N, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return AT_OK;
+}
+
+int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
+                void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_get_info: null handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int grid = (int)((env->n_envs + 127) / 128);
+    info_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(env->k, env->st, d_winner, d_hits, d_be_hits, d_change_time);
+    env->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_synthetic_actions(at_env *env, int64_t tick, int32_t *d_actions, void *stream) {
+    if (!env || !d_actions) return fail(AT_ERR_ARG, "at_synthetic_actions: null argument");
+    if (env->k.act_rows == 0) return AT_OK;
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int64_t total = env->n_envs * env->k.act_rows;
+    synthetic_actions_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        env->k.seed, env->k.env_id_base, env->n_envs, env->k.act_rows, (uint32_t)tick, d_actions);
+    env->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_get_state(at_env *env, int64_t first, int64_t count, at_env_state *h_out) {
+    if (!env || !h_out || first < 0 || count <= 0 || first + count > env->n_envs)
+        return fail(AT_ERR_ARG, "at_get_state: bad range");
+    CUDA_TRY(cudaSetDevice(env->device));
+    PackedEnv *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(PackedEnv) * count));
+    gather_kernel<<<(int)((count + 63) / 64), 64>>>(env->k, env->st, first, count, d);
+    env->launches += 1;
+    std::vector<PackedEnv> h((size_t)count);
+    cudaError_t err = cudaMemcpy(h.data(), d, sizeof(PackedEnv) * count, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (err != cudaSuccess) return fail(AT_ERR_CUDA, std::string("at_get_state: ") + cudaGetErrorString(err));
+    for (int64_t q = 0; q < count; ++q) unpack_env(env->k, env->luts, h[(size_t)q], h_out[q]);
+    return AT_OK;
+}
+
+int at_set_state(at_env *env, int64_t first, int64_t count, const at_env_state *h_in) {
+    if (!env || !h_in || first < 0 || count <= 0 || first + count > env->n_envs)
+        return fail(AT_ERR_ARG, "at_set_state: bad range");
+    std::vector<PackedEnv> h((size_t)count);
+    for (int64_t q = 0; q < count; ++q) {
+        std::string msg = pack_env(env->k, env->luts, h_in[q], h[(size_t)q]);
+        if (!msg.empty()) return fail(AT_ERR_ARG, msg);
+    }
+    CUDA_TRY(cudaSetDevice(env->device));
+    PackedEnv *d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, sizeof(PackedEnv) * count));
+    cudaError_t err = cudaMemcpy(d, h.data(), sizeof(PackedEnv) * count, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        scatter_kernel<<<(int)((count + 63) / 64), 64>>>(env->k, env->st, first, count, d);
+        env->launches += 1;
+        err = cudaDeviceSynchronize();
+    }
+    cudaFree(d);
+    if (err != cudaSuccess) return fail(AT_ERR_CUDA, std::string("at_set_state: ") + cudaGetErrorString(err));
+    return AT_OK;
+}
+
+int at_bfs_batch(int device, const uint8_t *d_maze, const int32_t *d_query, int64_t n, int32_t *d_out, void *stream) {
+    if (!d_maze || !d_query || !d_out || n <= 0) return fail(AT_ERR_ARG, "at_bfs_batch: bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    bfs_batch_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_maze, d_query, n, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *d_maze, uint32_t *d_ctr,
+                      void *stream) {
+    if (!d_maze || n <= 0) return fail(AT_ERR_ARG, "at_generate_mazes: bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    maze_kernel<<<(int)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(seed, env_id_base, n, d_maze, d_ctr);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_get_luts(const at_env *env, double *h_trig, double *h_corner) {
+    if (!env) return fail(AT_ERR_ARG, "at_get_luts: null handle");
+    if (h_trig) memcpy(h_trig, env->luts.trig.data(), 722 * 8);
+    if (h_corner) memcpy(h_corner, env->luts.corn.data(), 361 * 4 * 8);
+    return AT_OK;
+}
+
+}  // extern "C"

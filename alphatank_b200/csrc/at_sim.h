@@ -1,0 +1,1065 @@
+// at_sim.h - per-thread (= per-env) simulation of one alphaTank tick, and the per-lane observation row
+// builders.  Written as __host__ __device__ code: the CUDA kernels in at_kernels.cu run it with one thread
+// per env; tests/cpu_emul compiles the same header with g++ to check the formulation against the oracle in
+// a GPU-less container (test infrastructure only - the product has no CPU path).
+//
+// This is NOT a transliteration of the reference's Python: walls are a 121-bit mask probed by cell, angles
+// are integers indexing host-built libm tables, bullets carry a packed 64-bit record, BFS is a bit-parallel
+// 4-label frontier sweep, the pending "away" penalty is a counter.  Each routine cites the reference lines
+// whose results it must reproduce bit-for-bit.
+//
+// Numerics: compile with -fmad=false (nvcc) / -ffp-contract=off (g++).  The only fused multiply-adds are
+// the explicit fma_rn() calls that restate numpy/OpenBLAS 2-element dot products (see oracle/tank_oracle.c).
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#include "at_types.h"
+
+namespace at {
+
+constexpr double PI = 3.141592653589793;
+constexpr double GRID = 70.0;
+
+AT_HD double fma_rn(double a, double b, double c) {
+#ifdef __CUDA_ARCH__
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+AT_HD int d2i(double x) {  // C (int)double: truncation toward zero, as pygame.Rect does with float args
+#ifdef __CUDA_ARCH__
+    return __double2int_rz(x);
+#else
+    return (int)x;
+#endif
+}
+AT_HD int fdiv70(int v) { return v >= 0 ? v / 70 : -((69 - v) / 70); }
+AT_HD int imin(int a, int b) { return a < b ? a : b; }
+AT_HD int imax(int a, int b) { return a > b ? a : b; }
+
+// ------------------------------------------------------------------ ATRNG (oracle/atrng.py)
+AT_HD void philox4x32_10(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+}
+AT_HD uint32_t rng_word(uint64_t seed, int64_t env_id, uint32_t stream, uint32_t ctr) {
+    uint32_t c0 = ctr, c1 = stream, c2 = (uint32_t)((uint64_t)env_id & 0xFFFFFFFFu),
+             c3 = (uint32_t)((uint64_t)env_id >> 32);
+    philox4x32_10(c0, c1, c2, c3, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32));
+    return c0;
+}
+
+// ------------------------------------------------------------------ Python float helpers
+AT_HD double py_fmod360(double v) {  // CPython float_rem with divisor 360.0
+    double m = fmod(v, 360.0);
+    if (m != 0.0) {
+        if (m < 0) m += 360.0;
+    } else {
+        m = 0.0;
+    }
+    return m;
+}
+AT_HD double py_radians(double x) { return x * (PI / 180.0); }
+AT_HD double py_degrees(double x) { return x * (180.0 / PI); }
+AT_HD double np_dot2(double a0, double a1, double b0, double b1) { return fma_rn(a1, b1, a0 * b0); }
+AT_HD double np_norm2(double a0, double a1) { return sqrt(np_dot2(a0, a1, a0, a1)); }
+
+// atan2 with the lattice cases pinned to the correctly rounded doubles glibc returns (axis-aligned and
+// diagonal bearings are NOT measure-zero here: tanks spawn on cell centres).  Elsewhere the device atan2
+// (<= 2 ulp) feeds integer-degree thresholds, where a last-bit difference cannot change the decision
+// unless the bearing is within ~1e-13 deg of an integer (DESIGN.md "Transcendentals").
+AT_HD double at_atan2(double y, double x) {
+    double ax = fabs(x), ay = fabs(y);
+    if (ay == 0.0) {
+        if (x > 0.0 || (x == 0.0 && !signbit(x))) return y;
+        return copysign(3.141592653589793, y);
+    }
+    if (ax == 0.0) return copysign(1.5707963267948966, y);
+    if (ax == ay) return copysign(x > 0 ? 0.7853981633974483 : 2.356194490192345, y);
+    return atan2(y, x);
+}
+
+// ------------------------------------------------------------------ bit-parallel BFS (env/bfs.py:6-56)
+// FIFO BFS with neighbour order up, down, left, right.  Queue order within a level is the lexicographic
+// order of the direction strings from the start, so a cell's parent is the neighbour with the smallest
+// string and its first letter (the child of `start` the path goes through) is the minimum first letter
+// among its previous-level neighbours.  Four 121-bit frontier sets, one per first letter, are expanded
+// level by level; returns len(path) (0 = None) and path[1].
+struct M128 {
+    uint64_t lo, hi;
+};
+AT_HD M128 m_and(M128 a, M128 b) { return {a.lo & b.lo, a.hi & b.hi}; }
+AT_HD M128 m_or(M128 a, M128 b) { return {a.lo | b.lo, a.hi | b.hi}; }
+AT_HD M128 m_andn(M128 a, M128 b) { return {a.lo & ~b.lo, a.hi & ~b.hi}; }
+AT_HD bool m_any(M128 a) { return (a.lo | a.hi) != 0; }
+AT_HD bool m_test(M128 a, int i) { return ((i < 64 ? a.lo >> i : a.hi >> (i - 64)) & 1ull) != 0; }
+AT_HD M128 m_bit(int i) { return i < 64 ? M128{1ull << i, 0} : M128{0, 1ull << (i - 64)}; }
+AT_HD M128 m_shl(M128 a, int k) { return {a.lo << k, (a.hi << k) | (a.lo >> (64 - k))}; }
+AT_HD M128 m_shr(M128 a, int k) { return {(a.lo >> k) | (a.hi << (64 - k)), a.hi >> k}; }
+AT_HD M128 col_mask(int col) {  // bits r*11+col, r = 0..10
+    M128 m = {0, 0};
+#pragma unroll
+    for (int r = 0; r < 11; ++r) m = m_or(m, m_bit(r * 11 + col));
+    return m;
+}
+AT_HD M128 m_neighbours(M128 f, M128 notc0, M128 notc10) {
+    M128 up = m_shr(f, 11), down = m_shl(f, 11);
+    M128 left = m_shr(m_and(f, notc0), 1), right = m_shl(m_and(f, notc10), 1);
+    M128 r = m_or(m_or(up, down), m_or(left, right));
+    r.hi &= (1ull << (CELLS - 64)) - 1;
+    return r;
+}
+AT_HDN int bfs_first_step(uint64_t wall_lo, uint64_t wall_hi, int sr, int sc, int gr, int gc, int *next_r,
+                          int *next_c) {
+    *next_r = -1;
+    *next_c = -1;
+    if (sr < 0 || sr > 10 || sc < 0 || sc > 10 || gr < 0 || gr > 10 || gc < 0 || gc > 10) return 0;
+    const M128 wall = {wall_lo, wall_hi};
+    const int s = sr * 11 + sc, g = gr * 11 + gc;
+    if (m_test(wall, s) || m_test(wall, g)) return 0;
+    if (s == g) return 1;
+    const M128 all = {~0ull, (1ull << (CELLS - 64)) - 1};
+    const M128 freec = m_andn(all, wall);
+    const M128 notc0 = m_andn(all, col_mask(0)), notc10 = m_andn(all, col_mask(10));
+    M128 visited = m_bit(s);
+    M128 F[4];
+    const int dr[4] = {-1, 1, 0, 0}, dc[4] = {0, 0, -1, 1};
+#pragma unroll
+    for (int d = 0; d < 4; ++d) {
+        int r = sr + dr[d], cc = sc + dc[d];
+        F[d] = {0, 0};
+        if (r >= 0 && r <= 10 && cc >= 0 && cc <= 10) {
+            M128 b = m_bit(r * 11 + cc);
+            if (m_any(m_and(b, freec))) F[d] = b;
+        }
+        visited = m_or(visited, F[d]);
+    }
+    const M128 goal = m_bit(g);
+    for (int level = 1; level < CELLS; ++level) {
+#pragma unroll
+        for (int d = 0; d < 4; ++d)
+            if (m_any(m_and(F[d], goal))) {
+                *next_r = sr + dr[d];
+                *next_c = sc + dc[d];
+                return level + 1;
+            }
+        if (!m_any(m_or(m_or(F[0], F[1]), m_or(F[2], F[3])))) return 0;
+        M128 avail = m_andn(freec, visited);
+        M128 n0 = m_and(m_neighbours(F[0], notc0, notc10), avail);
+        M128 n1 = m_andn(m_and(m_neighbours(F[1], notc0, notc10), avail), n0);
+        M128 n01 = m_or(n0, n1);
+        M128 n2 = m_andn(m_and(m_neighbours(F[2], notc0, notc10), avail), n01);
+        M128 n012 = m_or(n01, n2);
+        M128 n3 = m_andn(m_and(m_neighbours(F[3], notc0, notc10), avail), n012);
+        F[0] = n0; F[1] = n1; F[2] = n2; F[3] = n3;
+        visited = m_or(visited, m_or(n012, n3));
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ maze generation (env/maze.py:7-33)
+// Randomized Prim with the reference's list.pop(idx) semantics; draws come from the env's ATRNG stream.
+AT_HDN void generate_maze_mask(uint64_t seed, int64_t env_id, uint32_t &ctr, uint64_t &wall_lo, uint64_t &wall_hi) {
+    M128 wall = {~0ull, (1ull << (CELLS - 64)) - 1};
+    uint16_t wl[128];  // packed (nx, ny, px, py), 4 bits each
+    int nw = 0;
+    auto below = [&](int n) { return (int)(((uint64_t)rng_word(seed, env_id, 0, ctr++) * (uint64_t)n) >> 32); };
+    int sx = 1 + 2 * below(5), sy = 1 + 2 * below(5);
+    wall = m_andn(wall, m_bit(sy * 11 + sx));
+    const int DX[4] = {0, 0, -2, 2}, DY[4] = {-2, 2, 0, 0};
+    int cx = sx, cy = sy;
+    for (;;) {
+        for (int d = 0; d < 4; ++d) {  // add_walls(cx, cy)
+            int nx = cx + DX[d], ny = cy + DY[d];
+            if (0 < nx && nx < 10 && 0 < ny && ny < 10 && m_test(wall, ny * 11 + nx) && nw < 128)
+                wl[nw++] = (uint16_t)(nx | (ny << 4) | (cx << 8) | (cy << 12));
+        }
+        bool carved = false;
+        while (nw > 0 && !carved) {
+            int idx = below(nw);  // random.randint(0, len(walls) - 1)
+            uint16_t v = wl[idx];
+            for (int i = idx; i < nw - 1; ++i) wl[i] = wl[i + 1];
+            --nw;
+            int wx = v & 15, wy = (v >> 4) & 15, px = (v >> 8) & 15, py = (v >> 12) & 15;
+            if (m_test(wall, wy * 11 + wx)) {
+                wall = m_andn(wall, m_bit(wy * 11 + wx));
+                wall = m_andn(wall, m_bit(((wy + py) / 2) * 11 + (wx + px) / 2));
+                cx = wx;
+                cy = wy;
+                carved = true;
+            }
+        }
+        if (!carved) break;
+    }
+    wall_lo = wall.lo;
+    wall_hi = wall.hi;
+}
+
+AT_HD int popc64(uint64_t v) {
+#ifdef __CUDA_ARCH__
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+// index of the k-th (0-based) set bit of a 128-bit mask
+AT_HD int select_bit(M128 m, int k) {
+    uint64_t w = m.lo;
+    int base = 0;
+    int pl = popc64(m.lo);
+    if (k >= pl) { k -= pl; w = m.hi; base = 64; }
+    for (int i = 0; i < k; ++i) w &= w - 1;  // drop k lowest set bits
+#ifdef __CUDA_ARCH__
+    return base + __ffsll((long long)w) - 1;
+#else
+    return base + __builtin_ctzll(w);
+#endif
+}
+
+// ------------------------------------------------------------------ the per-env simulator
+struct Sim {
+    const KCfg &c;
+    const DevState &st;
+    const BlockMem &bm;
+    int64_t e;  // env index into the SoA arrays
+    int tid;    // slot in the block working set
+    uint32_t cnt, rng, tick, tstep, epstep, zones;
+    uint64_t wlo, whi;
+
+    AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
+        : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
+          whi(0) {}
+
+    AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
+    AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
+    AT_HD double &TREW(int i) const { return bm.trew[i * BS + tid]; }
+    AT_HD uint32_t &TPACK(int i) const { return bm.tpack[i * BS + tid]; }
+    AT_HD uint32_t &THITS(int i) const { return bm.thits[i * BS + tid]; }
+    AT_HD uint32_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
+    AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * BS + tid]; }
+    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[i * BS + tid]; }
+    AT_HD double &BF0(int i) const { return bm.bf0[i * BS + tid]; }
+    AT_HD double &BF1(int i) const { return bm.bf1[i * BS + tid]; }
+    AT_HD int64_t G(int slot) const { return (int64_t)slot * st.N + e; }
+
+    AT_HD int t_angle(int i) const { return (int)(TPACK(i) & 511u); }
+    AT_HD int t_speed(int i) const {
+        uint32_t s = (TPACK(i) >> 9) & 3u;
+        return s == 0 ? 0 : (s == 1 ? 10 : (s == 2 ? -10 : 1));
+    }
+    AT_HD bool t_alive(int i) const { return (TPACK(i) & TP_ALIVE) != 0; }
+    AT_HD void set_speed(int i, int sp) {
+        uint32_t code = sp == 0 ? 0u : (sp == 10 ? 1u : (sp == -10 ? 2u : 3u));
+        TPACK(i) = (TPACK(i) & ~(3u << 9)) | (code << 9);
+    }
+    AT_HD double cosr(int a) const { return bm.trig[2 * a]; }
+    AT_HD double sinr(int a) const { return bm.trig[2 * a + 1]; }
+
+    AT_HD uint32_t rng_u32() { return rng_word(c.seed, c.env_id_base + e, 0, rng++); }
+    AT_HD int rng_below(int n) { return (int)(((uint64_t)rng_u32() * (uint64_t)n) >> 32); }
+    AT_HD double rng_unit53() {
+        uint32_t a = rng_u32() >> 5, b = rng_u32() >> 6;
+        return ((double)a * 67108864.0 + (double)b) / 9007199254740992.0;
+    }
+
+    AT_HD bool wall_at(int idx) const { return ((idx < 64 ? wlo >> idx : whi >> (idx - 64)) & 1ull) != 0; }
+
+    // first wall (row-major = reference list order, gaming_env.py:610-615) that a w x h pygame.Rect at
+    // integer (ix, iy) collides with; -1 if none.  Replaces `for wall in walls: colliderect` scans.
+    AT_HD int first_wall(int ix, int iy, int w, int h) const {
+        int c0 = imax(fdiv70(ix), 0), c1 = imin(fdiv70(ix + w - 1), 10);
+        int r0 = imax(fdiv70(iy), 0), r1 = imin(fdiv70(iy + h - 1), 10);
+        for (int r = r0; r <= r1; ++r)
+            for (int cc = c0; cc <= c1; ++cc)
+                if (wall_at(r * 11 + cc)) return r * 11 + cc;
+        return -1;
+    }
+    AT_HD static bool rect5_hits_cell(int ix, int iy, int cell) {  // Rect(ix,iy,5,5) vs the 70x70 wall rect
+        int X = (cell % 11) * 70, Y = (cell / 11) * 70;
+        return X < ix + 5 && Y < iy + 5 && X + 70 > ix && Y + 70 > iy;
+    }
+    AT_HD bool rect5_hits_tank(int ix, int iy, int i) const {  // vs Rect(x - 15, y - 12, 30, 24) (F11)
+        int Tx = d2i(TX(i) - 15), Ty = d2i(TY(i) - 12);
+        return ix < Tx + 30 && iy < Ty + 24 && ix + 5 > Tx && iy + 5 > Ty;
+    }
+
+    // ---------------------------------------------------------------- bullets (env/sprite.py:27-111)
+    // gaming_env.py:522-541 (1v1 incl. quirk F6) / gaming_env_multi.py:433-442 (team)
+    AT_HD void reward_by_bullets(int shooter, int victim) {
+        TREW(shooter) += 50;
+        TREW(victim) += -50;
+        if (c.mode != AT_MODE_TEAM_) {
+            bool all_same = true;
+            for (int i = 1; i < c.n_tanks; ++i) all_same = all_same && (t_alive(i) == t_alive(0));
+            if (all_same)
+                for (int i = 0; i < c.n_tanks; ++i)
+                    if (t_alive(i)) {
+                        double q = (double)(1000 - (int)epstep) / 1000.0;
+                        double time_bonus = q > 0 ? 5 * q : 0.0;
+                        TREW(i) += 200 * time_bonus;
+                    }
+        }
+    }
+
+    static constexpr int AT_MODE_AGENT_ = 0, AT_MODE_BOT_AGENT_ = 1, AT_MODE_ARENA_ = 2, AT_MODE_TEAM_ = 3;
+
+    // One Bullet.move().  Returns true when the bullet leaves the list.
+    AT_HD bool bullet_move(double &x, double &y, uint64_t &m) {
+        const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u);
+        const bool fx = (m >> BM_FLIPX) & 1u, fy = (m >> BM_FLIPY) & 1u;
+        int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
+        bool cleared = (m >> BM_CLEARED) & 1u;
+        uint32_t pcnt = (uint32_t)((m >> BM_PEND) & 0xFFFFu);
+        const double cv = cosr(ang), sv = sinr(ang);
+        double dx = fx ? -cv : cv, dy = fy ? sv : -sv;
+        const double nx = x + dx, ny = y + dy;
+        const int ix = d2i(nx), iy = d2i(ny);
+        const int oteam = c.team[owner];
+        // update_reward_logic on the pre-move position (sprite.py:27-57)
+        {
+            const double nrm = np_norm2(dx, dy);
+            const double d0 = dx / nrm, d1 = dy / nrm;
+            for (int i = 0; i < c.n_tanks; ++i) {
+                if (!t_alive(i) || c.team[i] == oteam) continue;
+                double tx = TX(i) - x, ty = TY(i) - y;
+                double dt = np_norm2(tx, ty);
+                if (dt > 300) continue;
+                double u0 = tx / dt, u1 = ty / dt;
+                double dp = np_dot2(d0, d1, u0, u1);
+                if (dp > 0.9) TREW(owner) += 0.01;
+                else if (dp < 0.1) { if (!cleared) ++pcnt; }
+                if (dt < 100) { pcnt = 0; cleared = true; }
+            }
+        }
+        bool nfx = fx, nfy = fy;
+        int cell = first_wall(ix, iy, 5, 5);
+        if (cell >= 0) {  // sprite.py:66-82 (F12)
+            bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
+            if (bxh) nfx = !nfx;
+            if (byh) nfy = !nfy;
+            ++bounces;
+        }
+        x = nx;
+        y = ny;
+        ++dist;
+        for (int i = 0; i < c.n_tanks; ++i) {  // sprite.py:88-100
+            if (t_alive(i) && c.team[i] != oteam && rect5_hits_tank(ix, iy, i)) {
+                if (c.terminate_time == 0) TPACK(i) &= ~TP_ALIVE;
+                THITS(owner) += 1u;
+                THITS(i) += 1u << 16;
+                reward_by_bullets(owner, i);
+                return true;
+            }
+        }
+        if (bounces >= 6 || dist >= 300) {  // sprite.py:102-111
+            if (!cleared && pcnt > 0) TREW(owner) -= st.pend[pcnt];
+            return true;
+        }
+        m = (uint64_t)owner | ((uint64_t)ang << BM_ANGLE) | ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) |
+            ((uint64_t)bounces << BM_BOUNCES) | ((uint64_t)cleared << BM_CLEARED) | ((uint64_t)dist << BM_DIST) |
+            ((uint64_t)pcnt << BM_PEND);
+        return false;
+    }
+
+    // `for bullet in self.bullets[:]: bullet.move()` (gaming_env.py:71-72, 378-379): firing order, stable
+    // compaction in place; also rebuilds the per-owner live counts and ranks (obs uses them).
+    AT_HDN void bullets_pass() {
+        const uint32_t n = cnt;
+        uint32_t w = 0;
+        for (int i = 0; i < c.n_tanks; ++i) TLIVE(i) = 0;
+        for (uint32_t r = 0; r < n; ++r) {
+            double x = st.bx[G(r)], y = st.by[G(r)];
+            uint64_t m = st.bmeta[G(r)];
+            if (!bullet_move(x, y, m)) {
+                uint32_t rank = TLIVE((int)(m & 15u))++;
+                m = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
+                st.bx[G(w)] = x;
+                st.by[G(w)] = y;
+                st.bmeta[G(w)] = m;
+                ++w;
+            }
+        }
+        cnt = w;
+    }
+
+    // ---------------------------------------------------------------- tanks (env/sprite.py:326-357, 528-657)
+    AT_HD void zone_xy(int k, int &zx, int &zy) const {
+        int cell = (int)((zones >> (7 * k)) & 127u);
+        zx = (cell % 11) * 70;
+        zy = (cell / 11) * 70;
+    }
+    AT_HD bool tank_in_zone(int i, int k) const {  // Rect(x-15,y-12,30,24) vs Rect(zx, zy, 245, 245)
+        int Tx = d2i(TX(i) - 15), Ty = d2i(TY(i) - 12), zx, zy;
+        zone_xy(k, zx, zy);
+        return Tx < zx + 245 && Ty < zy + 245 && Tx + 30 > zx && Ty + 24 > zy;
+    }
+    AT_HD void check_buff_debuff(int i) {  // sprite.py:613-636 (F8: effective cap is 1 or 6)
+        bool inb = c.buff_on && (tank_in_zone(i, 0) || tank_in_zone(i, 1));
+        bool ind = c.debuff_on && (tank_in_zone(i, 2) || tank_in_zone(i, 3));
+        uint32_t p = TPACK(i) & ~(TP_INBUFF | TP_INDEBUFF | TP_MAXB1);
+        if (inb) p |= TP_INBUFF;
+        if (ind) p |= TP_INDEBUFF | TP_MAXB1;
+        TPACK(i) = p;
+    }
+    AT_HD void rotate(int i, int direction) {  // sprite.py:528-549 (aiming ray-march is zero-weight, F18)
+        if (!t_alive(i)) return;
+        int a = (t_angle(i) + direction * 2) % 360;
+        if (a < 0) a += 360;
+        TPACK(i) = (TPACK(i) & ~511u) | (uint32_t)a;
+    }
+    AT_HD void shoot(int i) {  // sprite.py:579-609 on the virtual clock (F9)
+        check_buff_debuff(i);
+        if (!t_alive(i)) return;
+        const int now = (int)(((uint64_t)tick * 1000u) / 60u);
+        const uint32_t maxb = (TPACK(i) & TP_MAXB1) ? 1u : 6u;
+        if (TLIVE(i) >= maxb) return;
+        if (now - TSHOT(i) < 300) return;
+        const int a = t_angle(i);
+        const double cv = cosr(a), sv = sinr(a);
+        st.bx[G(cnt)] = TX(i) + 10 * cv;
+        st.by[G(cnt)] = TY(i) - 10 * sv;
+        uint32_t rank = TLIVE(i)++;
+        st.bmeta[G(cnt)] = (uint64_t)i | ((uint64_t)a << BM_ANGLE) | ((uint64_t)rank << BM_RANK);
+        ++cnt;
+        TSHOT(i) = now;
+    }
+    AT_HD void dodge_reward(int i) {  // sprite.py:497-525 (F17)
+        const int sp = t_speed(i);
+        if (sp == 0) return;  // projection is exactly 0: reward unchanged
+        const int a = t_angle(i);
+        const double tvx = (double)sp * cosr(a), tvy = (double)sp * sinr(a);
+        const int myteam = c.team[i];
+        double reward = 0;
+        for (uint32_t r = 0; r < cnt; ++r) {
+            const uint64_t m = st.bmeta[G(r)];
+            if (c.team[(int)(m & 15u)] == myteam) continue;
+            const double bxv = st.bx[G(r)], byv = st.by[G(r)];
+            double distance = np_norm2(TX(i) - bxv, TY(i) - byv);
+            if (distance >= 100) continue;
+            const int ba = (int)((m >> BM_ANGLE) & 511u);
+            const double cv = cosr(ba), sv = sinr(ba);
+            double dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv, dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
+            double nrm = np_norm2(dx, dy);
+            double d0 = dx / nrm, d1 = dy / nrm;
+            double proj = np_dot2(tvx, tvy, -d1, d0);
+            reward += fabs(proj) * 0.01;
+        }
+        TREW(i) += reward;
+    }
+    // obb_vs_aabb over the wall list (util.py:15-48) -> exact 4-axis SAT against the few wall cells whose
+    // AABB can reach the OBB (others are separated on the x or y axis by construction).
+    AT_HD bool obb_hits_walls(double nx, double ny, int a) const {
+        const double *co = st.corn + 4 * a;
+        const double o0x = co[0], o0y = co[1], o1x = co[2], o1y = co[3];
+        double kx[4] = {nx + o0x, nx + o1x, nx - o0x, nx - o1x};
+        double ky[4] = {ny + o0y, ny + o1y, ny - o0y, ny - o1y};
+        double mnx = kx[0], mxx = kx[0], mny = ky[0], mxy = ky[0];
+#pragma unroll
+        for (int k = 1; k < 4; ++k) {
+            mnx = kx[k] < mnx ? kx[k] : mnx; mxx = kx[k] > mxx ? kx[k] : mxx;
+            mny = ky[k] < mny ? ky[k] : mny; mxy = ky[k] > mxy ? ky[k] : mxy;
+        }
+        int c0 = imax((int)floor((mnx - 0.02) / 70.0) - 1, 0), c1 = imin((int)floor((mxx + 0.02) / 70.0), 10);
+        int r0 = imax((int)floor((mny - 0.02) / 70.0) - 1, 0), r1 = imin((int)floor((mxy + 0.02) / 70.0), 10);
+        bool any = false;
+        for (int r = r0; r <= r1; ++r)
+            for (int cc = c0; cc <= c1; ++cc) any = any || wall_at(r * 11 + cc);
+        if (!any) return false;
+        // OBB axes and projections (computed from the absolute corners, as the reference does)
+        double e0x = kx[1] - kx[0], e0y = ky[1] - ky[0], e1x = kx[3] - kx[0], e1y = ky[3] - ky[0];
+        double l0 = sqrt((0.0 + e0x * e0x) + e0y * e0y), l1 = sqrt((0.0 + e1x * e1x) + e1y * e1y);
+        double ax[2] = {e0x / l0, e1x / l1}, ay[2] = {e0y / l0, e1y / l1};
+        double omin[2], omax[2];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            double lo = 0, hi = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                double d = (0.0 + kx[k] * ax[q]) + ky[k] * ay[q];
+                lo = (k == 0 || d < lo) ? d : lo;
+                hi = (k == 0 || d > hi) ? d : hi;
+            }
+            omin[q] = lo; omax[q] = hi;
+        }
+        for (int r = r0; r <= r1; ++r)
+            for (int cc = c0; cc <= c1; ++cc) {
+                if (!wall_at(r * 11 + cc)) continue;
+                const double X0 = (double)(cc * 70), X1 = (double)(cc * 70 + 70), Y0 = (double)(r * 70),
+                             Y1 = (double)(r * 70 + 70);
+                bool sep = false;
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    double d0 = (0.0 + X0 * ax[q]) + Y0 * ay[q], d1 = (0.0 + X1 * ax[q]) + Y0 * ay[q];
+                    double d2 = (0.0 + X1 * ax[q]) + Y1 * ay[q], d3 = (0.0 + X0 * ax[q]) + Y1 * ay[q];
+                    double lo = fmin(fmin(d0, d1), fmin(d2, d3)), hi = fmax(fmax(d0, d1), fmax(d2, d3));
+                    sep = sep || (omax[q] < lo - 0.01) || (hi < omin[q] - 0.01);
+                }
+                sep = sep || (mxx < X0 - 0.01) || (X1 < mnx - 0.01);
+                sep = sep || (mxy < Y0 - 0.01) || (Y1 < mny - 0.01);
+                if (!sep) return true;
+            }
+        return false;
+    }
+    AT_HD void move(int i) {  // sprite.py:326-357
+        if (!t_alive(i)) return;
+        const int a = t_angle(i), sp = t_speed(i);
+        const double nx = TX(i) + (double)sp * cosr(a), ny = TY(i) - (double)sp * sinr(a);
+        if (!obb_hits_walls(nx, ny, a)) {
+            TX(i) = nx;
+            TY(i) = ny;
+            TPACK(i) &= ~TP_HW;
+        } else {
+            TPACK(i) |= TP_HW;
+        }
+        dodge_reward(i);
+    }
+    AT_HD void apply_action(int i, int a0, int a1, int a2, int fwd, int back, int stop_speed) {
+        if (a0 == 0) rotate(i, 3);
+        else if (a0 == 2) rotate(i, -3);
+        set_speed(i, a1 == fwd ? 10 : (a1 == back ? -10 : stop_speed));
+        if (a2 == 1) shoot(i);
+        move(i);
+    }
+
+    // ---------------------------------------------------------------- bots (env/bots/*.py)
+    AT_HD int nearest_opponent(int me, double *dist_out) const {
+        double best = INFINITY;
+        int idx = -1;
+        for (int i = 0; i < c.n_tanks; ++i)
+            if (c.team[i] != c.team[me] && t_alive(i)) {
+                double dx = TX(i) - TX(me), dy = TY(i) - TY(me);
+                double d = sqrt(dx * dx + dy * dy);
+                if (d < best) { best = d; idx = i; }
+            }
+        if (dist_out) *dist_out = best;
+        return idx;
+    }
+    AT_HD double angle_diff_to(int me, double tx, double ty) const {
+        double dx = tx - TX(me), dy = ty - TY(me);
+        double ta = py_fmod360(py_degrees(at_atan2(-dy, dx)));
+        int cur = t_angle(me) % 360;
+        return py_fmod360(ta - cur + 180) - 180;
+    }
+    AT_HD static int aim_from_diff(double d, double thr) { return fabs(d) < thr ? 0 : (d > 0 ? -1 : 1); }
+
+    // BulletTrajectory.simulate_complete_trajectory -> will_hit_target (sprite.py:131-190), used by
+    // SmartStrategyBot.check_line_of_sight (strategy_bot.py:58-73).
+    AT_HDN bool line_of_sight(int me) const {
+        const int a = t_angle(me);
+        const double cv = cosr(a), sv = sinr(a);
+        double x = TX(me) + 10 * cv, y = TY(me) - 10 * sv, dx = cv, dy = -sv;
+        int ex[MAX_TANKS], ey[MAX_TANKS], ne = 0;
+        bool reachable = false;
+        for (int i = 0; i < c.n_tanks; ++i)
+            if (c.team[i] != c.team[me] && t_alive(i)) {
+                ex[ne] = d2i(TX(i) - 15);
+                ey[ne] = d2i(TY(i) - 12);
+                ++ne;
+                // a hit needs the 5x5 rect within <= 301 advancing sub-steps of the muzzle: exact cull
+                double gx = fabs(TX(i) - x), gy = fabs(TY(i) - y);
+                reachable = reachable || (gx < 340.0 && gy < 340.0);
+            }
+        if (!reachable) return false;
+        int bounces = 0, dist = 0;
+        for (;;) {
+            const double nx = x + dx, ny = y + dy;
+            const int ix = d2i(nx), iy = d2i(ny);
+            for (int k = 0; k < ne; ++k)
+                if (ix < ex[k] + 30 && iy < ey[k] + 24 && ix + 5 > ex[k] && iy + 5 > ey[k]) return true;
+            int cell = first_wall(ix, iy, 5, 5);
+            if (cell >= 0) {
+                bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
+                if (bxh) dx = -dx;
+                if (byh) dy = -dy;
+                ++bounces;
+            } else {
+                x = nx;
+                y = ny;
+                ++dist;
+            }
+            if (bounces > 6 || dist > 300) return false;
+        }
+    }
+
+    // bpack layouts -----------------------------------------------------
+    // smart:     target+1 [0:4) aiming 4 rot_dir>0 5 stuck [6:12) has_next 12 next_r [13:17) next_c [17:21)
+    // defensive: has_tpos 0, zone index 1
+    // dodge:     timer [0:5) state [5:7) has_angle 7
+    // random:    delay [0:6) a0 [6:8) a1 [8:10) a2 10
+    AT_HD static uint32_t bot_init_pack(int type) {
+        if (type == 0) return 1u << 5;                 // rot_dir = +1
+        if (type == 1) return (1u << 6) | (1u << 8);   // current_action = [1, 1, 0]
+        return 0u;
+    }
+    AT_HD void bot_init(int i) {
+        BPACK(i) = bot_init_pack(c.bot_type[i]);
+        BF0(i) = TX(i);  // strategy_bot.py:15 last_position
+        BF1(i) = TY(i);
+        if (c.bot_type[i] != 0) { BF0(i) = 0.0; BF1(i) = 0.0; }
+    }
+
+    AT_HDN void smart_action(int me, int act[3]) {  // strategy_bot.py:75-203
+        uint32_t p = BPACK(me);
+        int target = (int)(p & 15u) - 1;
+        bool aiming = (p >> 4) & 1u, rot_pos = (p >> 5) & 1u, has_next = (p >> 12) & 1u;
+        int stuck = (int)((p >> 6) & 63u), next_r = (int)((p >> 13) & 15u), next_c = (int)((p >> 17) & 15u);
+        if (target < 0 || !t_alive(target)) {
+            aiming = false;
+            target = nearest_opponent(me, nullptr);
+        }
+        if (target >= 0) {
+            int nr, nc;
+            int len = bfs_first_step(wlo, whi, d2i(TY(me)) / 70, d2i(TX(me)) / 70, d2i(TY(target)) / 70,
+                                     d2i(TX(target)) / 70, &nr, &nc);
+            has_next = len > 1;
+            if (has_next) { next_r = nr; next_c = nc; }
+        }
+        {
+            double dx = TX(me) - BF0(me), dy = TY(me) - BF1(me);
+            stuck = (sqrt(dx * dx + dy * dy) < 1) ? stuck + 1 : 0;
+            BF0(me) = TX(me);
+            BF1(me) = TY(me);
+        }
+        act[0] = 1; act[1] = 1; act[2] = 0;
+        if (!aiming) {
+            target = nearest_opponent(me, nullptr);
+            if (target >= 0) aiming = true;
+        }
+        if (aiming && target >= 0) {
+            if (line_of_sight(me)) {
+                double tx = TX(target), ty = TY(target);
+                int rotation = aim_from_diff(angle_diff_to(me, tx, ty), 10);
+                if (rotation != 0) act[0] = rotation > 0 ? 2 : 0;
+                double dx = tx - TX(me), dy = ty - TY(me);
+                double d = sqrt(dx * dx + dy * dy);
+                if (d > 200) act[1] = 2;
+                else if (d < 20) act[1] = 0;
+                if (rotation == 0) act[2] = 1;
+            } else if (has_next) {
+                double tx = next_c * GRID + (GRID / 2), ty = next_r * GRID + (GRID / 2);
+                int rotation = aim_from_diff(angle_diff_to(me, tx, ty), 10);
+                if (rotation != 0) act[0] = rotation > 0 ? 2 : 0;
+                act[1] = rotation == 0 ? 2 : 1;
+            }
+        }
+        if (stuck > 20) {
+            act[1] = 2;
+            act[0] = rot_pos ? 0 : 2;
+            rot_pos = !rot_pos;
+            stuck = 0;
+        }
+        BPACK(me) = (uint32_t)(target + 1) | ((uint32_t)aiming << 4) | ((uint32_t)rot_pos << 5) |
+                    ((uint32_t)stuck << 6) | ((uint32_t)has_next << 12) | ((uint32_t)next_r << 13) |
+                    ((uint32_t)next_c << 17);
+    }
+    AT_HD void random_action(int me, int act[3]) {  // simple_bots.py:32-46
+        uint32_t p = BPACK(me);
+        int delay = (int)(p & 63u), a0 = (int)((p >> 6) & 3u), a1 = (int)((p >> 8) & 3u), a2 = (int)((p >> 10) & 1u);
+        if (delay <= 0) {
+            a0 = rng_below(3);
+            a1 = rng_below(3);
+            a2 = rng_below(2);
+            delay = 10 + rng_below(21);
+        }
+        delay -= 1;
+        BPACK(me) = (uint32_t)delay | ((uint32_t)a0 << 6) | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 10);
+        act[0] = a0; act[1] = a1; act[2] = a2;
+    }
+    AT_HD void aggressive_action(int me, int act[3]) const {  // simple_bots.py:86-125
+        double dist;
+        int target = nearest_opponent(me, &dist);
+        act[0] = 1; act[1] = 1; act[2] = 0;
+        if (target < 0) return;
+        double d = angle_diff_to(me, TX(target), TY(target));
+        double ad = fabs(d);
+        int rotation = aim_from_diff(d, 15);
+        act[0] = rotation > 0 ? 2 : (rotation < 0 ? 0 : 1);
+        if (ad < 15 && dist <= 70.0) act[2] = 1;
+        if (dist > 70.0) { if (ad < 45) act[1] = 2; }
+    }
+    AT_HD void defensive_action(int me, int act[3]) {  // simple_bots.py:151-292
+        act[0] = 1; act[1] = 1; act[2] = 0;
+        int target = nearest_opponent(me, nullptr);
+        if (target < 0) return;
+        const int nb = c.buff_on ? 2 : 0;
+        bool in_buff = false;
+        for (int k = 0; k < nb; ++k) in_buff = in_buff || tank_in_zone(me, k);
+        if (in_buff) {
+            double d = angle_diff_to(me, TX(target), TY(target));
+            int rot = aim_from_diff(d, 20);
+            act[0] = rot > 0 ? 2 : (rot < 0 ? 0 : 1);
+            if (fabs(d) < 20) act[2] = 1;
+            return;
+        }
+        uint32_t p = BPACK(me);
+        bool has = p & 1u;
+        int zi = (int)((p >> 1) & 1u);
+        if (!has) {
+            double best = INFINITY;
+            for (int k = 0; k < nb; ++k) {
+                double sx, sy;
+                safe_centre(k, sx, sy);
+                double dx = sx - TX(me), dy = sy - TY(me);
+                double d = sqrt(dx * dx + dy * dy);
+                if (d < best) { best = d; has = true; zi = k; }
+            }
+            BPACK(me) = (uint32_t)has | ((uint32_t)zi << 1);
+        }
+        if (has) {
+            double sx, sy;
+            safe_centre(zi, sx, sy);
+            double d = angle_diff_to(me, sx, sy);
+            int rot = aim_from_diff(d, 20);
+            act[0] = rot > 0 ? 2 : (rot < 0 ? 0 : 1);
+            if (fabs(d) < 45) act[1] = 2;
+        }
+    }
+    AT_HD void safe_centre(int k, double &sx, double &sy) const {  // simple_bots.py:151-175
+        int zx, zy;
+        zone_xy(k, zx, zy);
+        const double bw = GRID * 3.5, mx = 30 * 0.75, my = 24 * 0.75;
+        double x0 = zx + mx, x1 = zx + bw - mx, y0 = zy + my, y1 = zy + bw - my;
+        sx = (x0 + x1) / 2;
+        sy = (y0 + y1) / 2;
+    }
+    AT_HD bool dodge_hits_wall(int me, double angle) const {  // simple_bots.py:309-329
+        double rad = py_radians(angle);
+        double wcd = GRID * 1.5;
+        double fx = TX(me) + cos(rad) * wcd, fy = TY(me) - sin(rad) * wcd;
+        return first_wall(d2i(fx - 15), d2i(fy - 12), 30, 24) >= 0;
+    }
+    AT_HD double dodge_calc_angle(int me, double thx, double thy) {  // simple_bots.py:359-402
+        double v0 = thx - TX(me), v1 = thy - TY(me);
+        double n = np_norm2(v0, v1);
+        if (n > 0) {
+            v0 = v0 / n;
+            v1 = v1 / n;
+            int base[2] = {90, -90};
+            if (rng_below(2) == 0) { base[0] = -90; base[1] = 90; }  // random.shuffle of a 2-list
+            for (int bi = 0; bi < 2; ++bi)
+                for (int k = 0; k < 3; ++k) {
+                    double var = -45.0 + (-30.0 - -45.0) * rng_unit53();  // random.uniform(-45, -30)
+                    double theta = py_radians(base[bi] + var);
+                    double cs = cos(theta), sn = sin(theta);
+                    double r0 = fma_rn(cs, v0, (-sn) * v1), r1 = fma_rn(sn, v0, cs * v1);
+                    double fa = py_fmod360(py_degrees(at_atan2(-r1, r0)));
+                    if (!dodge_hits_wall(me, fa)) return fa;
+                }
+        }
+        return (double)t_angle(me);
+    }
+    AT_HDN void dodge_action(int me, int act[3]) {  // simple_bots.py:331-357, 404-455
+        act[0] = 1; act[1] = 1; act[2] = 1;
+        uint32_t p = BPACK(me);
+        int timer = (int)(p & 31u), state = (int)((p >> 5) & 3u);
+        bool has_angle = (p >> 7) & 1u;
+        const double radius = GRID * 4;
+        double best = INFINITY, px = 0, py = 0;
+        bool have = false;
+        for (int i = 0; i < c.n_tanks; ++i)
+            if (c.team[i] != c.team[me] && t_alive(i)) {
+                double dx = TX(i) - TX(me), dy = TY(i) - TY(me);
+                double d = sqrt(dx * dx + dy * dy);
+                if (d < best && d < radius) { best = d; px = TX(i); py = TY(i); have = true; }
+            }
+        for (uint32_t r = 0; r < cnt; ++r) {
+            const uint64_t m = st.bmeta[G(r)];
+            if (c.team[(int)(m & 15u)] == c.team[me]) continue;
+            double bxv = st.bx[G(r)], byv = st.by[G(r)];
+            double dx = bxv - TX(me), dy = byv - TY(me);
+            double d = sqrt(dx * dx + dy * dy);
+            if (d < best && d < radius) { best = d; px = bxv; py = byv; have = true; }
+        }
+        if (!have) {
+            BPACK(me) = 0u;  // idle, timer 0, no angle
+            return;
+        }
+        if (timer <= 0 || !has_angle) {
+            BF0(me) = dodge_calc_angle(me, px, py);
+            has_angle = true;
+            timer = 10;
+            state = 1;
+        }
+        if (state == 1) {
+            if (dodge_hits_wall(me, BF0(me))) {
+                BF0(me) = dodge_calc_angle(me, px, py);
+                state = 2;
+            }
+            int cur = t_angle(me) % 360;
+            double d = py_fmod360(BF0(me) - cur + 180) - 180;
+            int rotation = fabs(d) < 5 ? 0 : (d > 0 ? -1 : 1);
+            act[0] = rotation > 0 ? 2 : (rotation < 0 ? 0 : 1);
+            if (fabs(d) < 45) act[1] = 2;
+        }
+        timer -= 1;
+        BPACK(me) = (uint32_t)timer | ((uint32_t)state << 5) | ((uint32_t)has_angle << 7);
+    }
+    AT_HD void bot_action(int me, int act[3]) {
+        switch (c.bot_type[me]) {
+        case 0:
+            // runs for dead tanks too: take_action still sets their speed (sprite.py:646-651), which the
+            // other tanks' observation rows expose as velocity
+            smart_action(me, act);
+            break;
+        case 1: random_action(me, act); break;
+        case 2: aggressive_action(me, act); break;
+        case 3: defensive_action(me, act); break;
+        case 4: dodge_action(me, act); break;
+        default: act[0] = 1; act[1] = 1; act[2] = 0; break;
+        }
+    }
+
+    // ---------------------------------------------------------------- reset (gaming_env.py:48-66, 509-520)
+    AT_HDN void env_reset() {
+        if (c.map == 2) generate_maze_mask(c.seed, c.env_id_base + e, rng, wlo, whi);
+        const M128 all = {~0ull, (1ull << (CELLS - 64)) - 1};
+        const M128 freec = m_andn(all, M128{wlo, whi});
+        const int n_empty = CELLS - c.n_walls;
+        for (int i = 0; i < c.n_tanks; ++i) {
+            int cell = select_bit(freec, rng_below(n_empty));
+            TX(i) = (double)((cell % 11) * 70) + GRID / 2;
+            TY(i) = (double)((cell / 11) * 70) + GRID / 2;
+            int a = rng_below(361);
+            TPACK(i) = (uint32_t)a | TP_ALIVE;
+            TREW(i) = 0.0;
+            THITS(i) = 0u;
+            TLIVE(i) = 0u;
+            TSHOT(i) = 0;
+            BPACK(i) = 0u;
+            BF0(i) = 0.0;
+            BF1(i) = 0.0;
+        }
+        cnt = 0;
+        for (int i = 0; i < c.n_tanks; ++i) {
+            bool has_bot = (c.mode == AT_MODE_BOT_AGENT_ && i == 0) ||
+                           ((c.mode == AT_MODE_TEAM_ || c.mode == AT_MODE_ARENA_) && c.ctrl[i] == 1);
+            if (has_bot) bot_init(i);
+        }
+        zones = 0;
+        for (int z = 0; z < 2; ++z) {
+            if ((z == 0 && !c.buff_on) || (z == 1 && !c.debuff_on)) continue;
+            int i = rng_below(n_empty), j = rng_below(n_empty - 1);
+            if (j >= i) ++j;
+            zones |= (uint32_t)select_bit(freec, i) << (14 * z);
+            zones |= (uint32_t)select_bit(freec, j) << (14 * z + 7);
+        }
+        epstep = 0;
+        st.prev_act[e] = 0u;
+        for (int k = 0; k < c.n_tanks; ++k) st.change_time[G(k)] = 0;
+    }
+
+    // ---------------------------------------------------------------- one tick
+    // GamingENV.step (gaming_env.py:68-386) / GamingTeamENV.step (gaming_env_multi.py:65-97)
+    AT_HDN void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
+        int act[3];
+        int arena[2][3];
+        tick += 1;
+        if (c.mode == AT_MODE_ARENA_)  // bot_arena.py:51-52
+            for (int i = 0; i < 2; ++i) bot_action(i, arena[i]);
+        if (c.mode != AT_MODE_TEAM_) epstep += 1;
+        bullets_pass();
+        if (c.mode == AT_MODE_BOT_AGENT_) {  // gaming_env.py:139-199 (F14, F15)
+            bot_action(0, act);
+            if (!(rng_unit53() < c.weakness)) { act[0] = 1; act[1] = 1; act[2] = 0; }
+            apply_action(0, act[0], act[1], act[2], 2, 0, 0);
+            apply_action(1, a[3], a[4], a[5], 0, 2, 1);
+        } else if (c.mode == AT_MODE_TEAM_) {  // controller.py:81-113
+            for (int k = 0; k < c.n_agents; ++k)
+                apply_action(c.agent_tank[k], a[3 * k], a[3 * k + 1], a[3 * k + 2], 2, 0, 0);
+            for (int i = 0; i < c.n_tanks; ++i)
+                if (c.ctrl[i] == 1) {
+                    bot_action(i, act);
+                    apply_action(i, act[0], act[1], act[2], 2, 0, 0);
+                }
+        } else if (c.mode == AT_MODE_ARENA_) {
+            for (int i = 0; i < 2; ++i) apply_action(i, arena[i][0], arena[i][1], arena[i][2], 2, 0, 0);
+        } else {  // "AI only" gaming_env.py:309-374
+            for (int i = 0; i < c.n_tanks; ++i) apply_action(i, a[3 * i], a[3 * i + 1], a[3 * i + 2], 2, 0, 0);
+        }
+        bullets_pass();
+    }
+
+    // wrapper step (gym_env.py:73-103, 186-200; gym_env_multi.py:202-223, 307-326).  Returns done.
+    AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
+        tstep += 1;
+        if (!c.team_layout && a) {  // change_time, gym_env.py:77-85
+            uint32_t pv = st.prev_act[e];
+            uint32_t nv = 1u;
+            for (int k = 0; k < c.act_rows; ++k) {
+                uint32_t code = (uint32_t)(a[3 * k] * 3 + a[3 * k + 1]) & 15u;
+                if ((pv & 1u) && ((pv >> (1 + 4 * k)) & 15u) == code) st.change_time[G(k)] += 1;
+                nv |= code << (1 + 4 * k);
+            }
+            st.prev_act[e] = nv;
+        }
+        game_step(a);
+        for (int r = 0; r < c.rows; ++r)
+            rewards_row[r] = (float)TREW(c.team_layout ? c.agent_tank[r] : r);
+        bool done;
+        if (c.terminate_time != 0) {
+            done = !((int)tstep < c.terminate_time);
+            if (done) tstep = 0;
+        } else {
+            uint32_t teams = 0;
+            int winner_team = -1;
+            for (int i = 0; i < c.n_tanks; ++i)
+                if (t_alive(i)) {
+                    teams |= 1u << c.team[i];
+                    if (winner_team < 0) winner_team = c.team[i];
+                }
+            int nalive = popc64(teams);
+            done = nalive <= 1;
+            if (c.team_layout && nalive == 1)  // F5: lands after the rewards were read
+                for (int i = 0; i < c.n_tanks; ++i)
+                    if (c.team[i] == winner_team) TREW(i) += 200;
+        }
+        return done;
+    }
+
+    // ---------------------------------------------------------------- HBM <-> working set
+    AT_HD void load() {
+        cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
+        zones = st.zones[e];
+        if (c.map == 2) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; }
+        else { wlo = c.wall_lo; whi = c.wall_hi; }
+        for (int i = 0; i < c.n_tanks; ++i) {
+            TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
+            TPACK(i) = st.tpack[G(i)]; THITS(i) = st.thits[G(i)]; TSHOT(i) = st.tshot[G(i)];
+            if (c.ctrl[i] == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
+        }
+    }
+    AT_HD void load_scalars_only() {
+        cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
+        zones = st.zones[e];
+        if (c.map == 2) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; }
+        else { wlo = c.wall_lo; whi = c.wall_hi; }
+    }
+    AT_HD void store() {
+        st.cnt[e] = cnt; st.rng_ctr[e] = rng; st.tick[e] = tick; st.tstep[e] = tstep; st.epstep[e] = epstep;
+        st.zones[e] = zones;
+        if (c.map == 2) { st.wall_lo[e] = wlo; st.wall_hi[e] = whi; }
+        for (int i = 0; i < c.n_tanks; ++i) {
+            st.tx[G(i)] = TX(i); st.ty[G(i)] = TY(i); st.trew[G(i)] = TREW(i);
+            st.tpack[G(i)] = TPACK(i); st.thits[G(i)] = THITS(i); st.tshot[G(i)] = TSHOT(i);
+            if (c.ctrl[i] == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
+        }
+    }
+};
+
+// ------------------------------------------------------------------ observation rows
+// gym_env.py:105-183 (1v1 layout) / gym_env_multi.py:225-304 (team layout).  A row is assembled by the 32
+// lanes of a warp in a shared-memory staging buffer and leaves as one contiguous block.  `q` is the env's
+// slot in the block working set, `e` its SoA index, `t` the tank the row belongs to.
+struct RowCtx {
+    const KCfg &c;
+    const DevState &st;
+    const BlockMem &bm;
+    float *row;
+    int q;
+    int64_t e;
+    uint32_t cnt, zones;
+    uint64_t wlo, whi;
+};
+
+AT_HD void row_static(const RowCtx &r, int lane) {  // walls (row-major) + maze: change only with the map
+    const KCfg &c = r.c;
+    for (int cell = lane; cell < CELLS; cell += 32) {
+        bool w = ((cell < 64 ? r.wlo >> cell : r.whi >> (cell - 64)) & 1ull) != 0;
+        r.row[c.off_maze + cell] = w ? 1.0f : 0.0f;
+        if (w) {
+            uint64_t below_lo = cell < 64 ? (r.wlo & ((1ull << cell) - 1)) : r.wlo;
+            uint64_t below_hi = cell < 64 ? 0ull : (r.whi & ((1ull << (cell - 64)) - 1));
+            int idx = popc64(below_lo) + popc64(below_hi);
+            float X = (float)((cell % 11) * 70), Y = (float)((cell / 11) * 70);
+            float *p = r.row + c.off_walls + 4 * idx;
+            p[0] = X; p[1] = Y; p[2] = X + 70.0f; p[3] = Y + 70.0f;
+        }
+    }
+}
+AT_HD void row_clear_bullets(const RowCtx &r, int lane) {
+    for (int j = r.c.off_ob + lane; j < r.c.off_et; j += 32) r.row[j] = 0.0f;
+}
+AT_HD void row_bullets(const RowCtx &r, int lane, int t) {
+    const KCfg &c = r.c;
+    const double ax = r.bm.tx[t * BS + r.q], ay = r.bm.ty[t * BS + r.q];
+    for (uint32_t s = lane; s < r.cnt; s += 32) {
+        const int64_t g = (int64_t)s * r.st.N + r.e;
+        const uint64_t m = r.st.bmeta[g];
+        const double x = r.st.bx[g], y = r.st.by[g];
+        const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u), rank = (int)((m >> BM_RANK) & 7u);
+        const double cv = r.bm.trig[2 * ang], sv = r.bm.trig[2 * ang + 1];
+        const double dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv, dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
+        if (owner == t) {
+            float *p = r.row + c.off_ob + 4 * rank;
+            p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
+        } else {
+            const int oi = owner < t ? owner : owner - 1;
+            const int per = c.team_layout ? 8 : 7;
+            float *p = r.row + c.off_eb + oi * c.eb_stride + per * rank;
+            const double rx = x - ax, ry = y - ay;
+            p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
+            p[4] = (float)rx; p[5] = (float)ry; p[6] = (float)sqrt(rx * rx + ry * ry);
+            if (c.team_layout) p[7] = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
+        }
+    }
+}
+AT_HD void row_tanks(const RowCtx &r, int lane, int t) {
+    const KCfg &c = r.c;
+    if (lane < c.n_tanks) {
+        const int i = lane;
+        const double x = r.bm.tx[i * BS + r.q], y = r.bm.ty[i * BS + r.q];
+        const uint32_t pk = r.bm.tpack[i * BS + r.q];
+        const int a = (int)(pk & 511u);
+        const uint32_t sc = (pk >> 9) & 3u;
+        const double sp = sc == 0 ? 0.0 : (sc == 1 ? 10.0 : (sc == 2 ? -10.0 : 1.0));
+        const double *co = r.st.corn + 4 * a;
+        float *p;
+        if (i == t) {
+            p = r.row;
+            p[0] = (float)x; p[1] = (float)y;
+            p += 2;
+        } else {
+            const int oi = i < t ? i : i - 1;
+            p = r.row + c.off_et + oi * c.et_len;
+            const double ax = r.bm.tx[t * BS + r.q], ay = r.bm.ty[t * BS + r.q];
+            const double rx = x - ax, ry = y - ay;
+            p[0] = (float)x; p[1] = (float)y; p[2] = (float)rx; p[3] = (float)ry;
+            p[4] = (float)sqrt(rx * rx + ry * ry);
+            p += 5;
+        }
+        p[0] = (float)(x + co[0]); p[1] = (float)(y + co[1]); p[2] = (float)(x + co[2]); p[3] = (float)(y + co[3]);
+        p[4] = (float)(x - co[0]); p[5] = (float)(y - co[1]); p[6] = (float)(x - co[2]); p[7] = (float)(y - co[3]);
+        p[8] = (float)(sp * r.bm.trig[2 * a]);
+        p[9] = (float)(sp * r.bm.trig[2 * a + 1]);
+        p[10] = (pk & TP_HW) ? 1.0f : 0.0f;
+        p += 11;
+        if (c.team_layout) *p++ = (i == t) ? 1.0f : (c.team[i] == c.team[t] ? 1.0f : 0.0f);
+        *p = (pk & TP_ALIVE) ? 1.0f : 0.0f;
+    }
+}
+AT_HD void row_misc(const RowCtx &r, int lane, int t) {
+    const KCfg &c = r.c;
+    if (lane < c.n_zone_vals) {  // zone corner coordinates, buff first (gym_env.py:168-173)
+        int k = lane >> 1;
+        if (!c.buff_on) k += 2;
+        int cell = (int)((r.zones >> (7 * k)) & 127u);
+        r.row[c.off_zones + lane] = (float)(((lane & 1) ? cell / 11 : cell % 11) * 70);
+    }
+    if (lane == 30) r.row[c.off_flags] = (r.bm.tpack[t * BS + r.q] & TP_INBUFF) ? 1.0f : 0.0f;
+    if (lane == 31) r.row[c.off_flags + 1] = (r.bm.tpack[t * BS + r.q] & TP_INDEBUFF) ? 1.0f : 0.0f;
+}
+
+}  // namespace at

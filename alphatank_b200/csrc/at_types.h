@@ -1,0 +1,73 @@
+// at_types.h - shared POD types of the CUDA env step (kernel config, SoA state, packed fields).
+//
+// Data layout in HBM (DESIGN.md "State layout"): structure-of-arrays, env index
+// fastest, so that the 32 lanes of a warp (= 32 consecutive envs) touch
+// consecutive addresses.  Per-tank / per-bullet-slot arrays are [slot][N].
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define AT_HD __host__ __device__ __forceinline__
+#define AT_HDN __host__ __device__ __noinline__
+#else
+#define AT_HD inline
+#define AT_HDN
+#endif
+
+namespace at {
+
+constexpr int BS = 64;          // envs (threads) per block
+constexpr int MAX_TANKS = 8;
+constexpr int SLOTS_PER_TANK = 6;
+constexpr int CELLS = 121;
+constexpr int MAZE_W = 11;
+constexpr int PEND_LUT = 300 * 7 + 1;
+
+// tpack: angle[0:9) speed_code[9:11) alive 11 hitting_wall 12 in_buff 13 in_debuff 14 maxb1 15
+constexpr uint32_t TP_ALIVE = 1u << 11, TP_HW = 1u << 12, TP_INBUFF = 1u << 13, TP_INDEBUFF = 1u << 14,
+                   TP_MAXB1 = 1u << 15;
+// bmeta: owner[0:4) angle[4:13) flipx 13 flipy 14 bounces[15:18) cleared 18 distance[19:28) rank[28:31)
+//        pending_count[32:48)
+constexpr int BM_ANGLE = 4, BM_FLIPX = 13, BM_FLIPY = 14, BM_BOUNCES = 15, BM_CLEARED = 18, BM_DIST = 19,
+              BM_RANK = 28, BM_PEND = 32;
+
+struct KCfg {
+    int32_t mode, n_tanks, map, terminate_time, buff_on, debuff_on, auto_reset;
+    int32_t n_agents, rows, obs_dim, act_rows, n_walls, team_layout, n_zone_vals;
+    int32_t team[MAX_TANKS], ctrl[MAX_TANKS], bot_type[MAX_TANKS], agent_tank[MAX_TANKS];
+    // observation row layout (floats)
+    int32_t self_len, off_ob, off_eb, eb_stride, off_et, et_len, off_walls, off_maze, off_zones, off_flags;
+    int32_t row_bulk_ok;  // D*4 % 16 == 0: rows can leave shared memory as one bulk-async copy
+    double weakness;
+    uint64_t seed;
+    int64_t env_id_base;
+    uint64_t wall_lo, wall_hi;  // static map wall mask (bit r*11+c); per-env arrays are used when map == MAZE
+};
+
+struct DevState {
+    int64_t N;
+    uint32_t *cnt, *rng_ctr, *tick, *tstep, *epstep, *zones, *prev_act;
+    int32_t *change_time;          // [n][N]
+    uint64_t *wall_lo, *wall_hi;   // [N], only when map == MAZE
+    double *tx, *ty, *trew;        // [n][N]
+    uint32_t *tpack, *thits;       // [n][N]
+    int32_t *tshot;                // [n][N]
+    uint32_t *bpack;               // [n][N] bot FSM
+    double *bf0, *bf1;             // [n][N] bot doubles (smart: last_x,last_y; dodge: dodge_angle)
+    double *bx, *by;               // [6n][N]
+    uint64_t *bmeta;               // [6n][N]
+    const double *trig;            // [361][2] cos, sin of math.radians(a)
+    const double *corn;            // [361][4] pygame-rotated corner offsets (c0x, c0y, c1x, c1y)
+    const double *pend;            // [PEND_LUT] k-fold accumulation of BULLET_AWAY_PENALTY
+};
+
+// per-block working set of the tanks / bots (shared memory on the GPU)
+struct BlockMem {
+    double *trig;                  // [722] copy of st.trig
+    double *tx, *ty, *trew;        // [n][BS]
+    double *bf0, *bf1;             // [n][BS]
+    uint32_t *tpack, *thits, *bpack, *tlive;  // [n][BS]  (tlive: live bullets per owner)
+    int32_t *tshot;                // [n][BS]
+};
+
+}  // namespace at

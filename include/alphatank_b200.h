@@ -1,0 +1,172 @@
+/* alphatank_b200.h - C ABI of the B200-native batched alphaTank environment step.
+ *
+ * The reference (georgong/alphaTank) is pure in-process Python: one env per
+ * process, stepped by
+ *     MultiAgentEnv.reset/step          env/gym_env.py:63-103
+ *     MultiAgentTeamEnv.reset/step      env/gym_env_multi.py:192-223
+ * over GamingENV / GamingTeamENV (env/gaming_env.py:48-386,
+ * env/gaming_env_multi.py:48-97).  It has no FFI of its own; this header is
+ * the boundary a maintainer binds instead of those two classes' bodies (the
+ * ctypes stub is shown in INTEGRATION.md, the shipped one is
+ * alphatank_b200/_capi.py).  N independent envs live as structure-of-arrays
+ * state in HBM and every entry point below is one (or a few) kernel launches
+ * on the caller's stream.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary.
+ *   - d_* pointers are DEVICE pointers owned by the caller (e.g. torch tensors);
+ *     h_* pointers are HOST pointers.  The env state is owned by the handle.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream).  All
+ *     work is enqueued on it; no entry point synchronises unless it says so.
+ *   - every function returns 0 on success or a negative AT_ERR_* code and
+ *     records a thread-local message readable through at_last_error().
+ *     Nothing throws; nothing is freed across the boundary.
+ *   - a handle is single-writer (like a reference env instance).
+ */
+#ifndef ALPHATANK_B200_H
+#define ALPHATANK_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AT_MAX_TANKS 8
+#define AT_MAX_BULLETS 48 /* MAX_BULLETS(6) x tanks, configs/config_basic.py:24 */
+#define AT_CELLS 121      /* MAZEWIDTH x MAZEHEIGHT, configs/config_basic.py:4 */
+
+#define AT_OK 0
+#define AT_ERR_ARG (-1)    /* invalid argument / unsupported config (e.g. mode "human") */
+#define AT_ERR_CUDA (-2)   /* CUDA runtime error, see at_last_error() */
+#define AT_ERR_NOGPU (-3)  /* no usable sm_100 device: the product has no CPU fallback */
+
+/* which branch of GamingENV.step / GamingTeamENV.step runs */
+enum at_mode {
+    AT_MODE_AGENT = 0,     /* MultiAgentEnv(mode="agent"): "AI only" branch, gaming_env.py:309-374 */
+    AT_MODE_BOT_AGENT = 1, /* MultiAgentEnv(mode="bot_agent", type="train"): gaming_env.py:139-199 */
+    AT_MODE_ARENA = 2,     /* bot_arena.py:23-74: both tanks bot-driven, decisions on the pre-tick state */
+    AT_MODE_TEAM = 3       /* MultiAgentTeamEnv(game_configs): gaming_env_multi.py:65-97 */
+};
+enum at_ctrl { AT_CTRL_AGENT = 0, AT_CTRL_BOT = 1 }; /* config_teams.py "mode": "agent" | "bot" */
+enum at_bot {                                        /* env/bots/bot_factory.py:7-14 */
+    AT_BOT_SMART = 0, AT_BOT_RANDOM = 1, AT_BOT_AGGRESSIVE = 2, AT_BOT_DEFENSIVE = 3, AT_BOT_DODGE = 4,
+    AT_BOT_STATIONARY = 5
+};
+enum at_map {
+    AT_MAP_OCTAGON = 0,     /* USE_OCTAGON=True, gaming_env.py:576-578 (40 walls) */
+    AT_MAP_BATTLEFIELD = 1, /* USE_OCTAGON=False, gaming_env.py:579-606 (61 walls) */
+    AT_MAP_MAZE = 2         /* env/maze.py:7-33 generate_maze per env at every reset (72 walls) */
+};
+
+/* The frozen form of configs/config_basic.py + one configs/config_teams.py dict. */
+typedef struct at_config {
+    int32_t mode;           /* enum at_mode */
+    int32_t n_tanks;        /* 2 for the 1v1 modes, 2..8 for team mode */
+    int32_t map;            /* enum at_map */
+    int32_t terminate_time; /* TERMINATE_TIME, 0 = None (config_basic.py:127) */
+    int32_t buff_on;        /* BUFF_ON   (config_basic.py:123) */
+    int32_t debuff_on;      /* DEBUFF_ON (config_basic.py:124) */
+    int32_t auto_reset;     /* 1: done envs are reset inside at_step and obs holds the post-reset observation */
+    int32_t reserved;
+    int32_t team[AT_MAX_TANKS];     /* team id per tank, config order */
+    int32_t ctrl[AT_MAX_TANKS];     /* enum at_ctrl per tank */
+    int32_t bot_type[AT_MAX_TANKS]; /* enum at_bot per bot tank */
+    double weakness;                /* GamingENV(weakness=...), gaming_env.py:144 */
+} at_config;
+
+/* AoS snapshot of one env, for tests, checkpoints and state injection. */
+typedef struct at_tank_state {
+    double x, y, reward;
+    int32_t angle, speed, alive, hitting_wall, in_buff, in_debuff, max_bullets, last_shot_ms, num_hit, num_be_hit;
+} at_tank_state;
+typedef struct at_bullet_state {
+    double x, y, dx, dy, pending;
+    int32_t owner, distance, bounces, cleared;
+} at_bullet_state;
+typedef struct at_bot_state {
+    int32_t target, aiming, rot_dir, stuck_timer, has_next, next_r, next_c, pad0; /* SmartStrategyBot */
+    double last_x, last_y;
+    int32_t has_tpos, pad1; /* DefensiveBot.target_position */
+    double tpos_x, tpos_y;
+    int32_t dodge_timer, dodge_state, has_dodge_angle, pad2; /* DodgeBot */
+    double dodge_angle;
+    int32_t action_delay, cur_action[3]; /* RandomBot */
+} at_bot_state;
+typedef struct at_env_state {
+    int32_t n_bullets, tick, training_step, episode_steps;
+    uint32_t rng_ctr;
+    int32_t n_walls;
+    int32_t zones[8]; /* buff0 x,y buff1 x,y debuff0 x,y debuff1 x,y in pixels (multiples of 70) */
+    uint8_t maze[AT_CELLS + 7];
+    at_tank_state tanks[AT_MAX_TANKS];
+    at_bot_state bots[AT_MAX_TANKS];
+    at_bullet_state bullets[AT_MAX_BULLETS];
+} at_env_state;
+
+typedef struct at_env at_env; /* opaque handle: one batch of envs on one device */
+
+/* Replaces MultiAgentEnv.__init__ (gym_env.py:11-23) / MultiAgentTeamEnv.__init__ (gym_env_multi.py:13-25).
+ * Allocates SoA state for n_envs envs on `device` and runs the constructor's own reset (gaming_env.py:43).
+ * Env i draws from the ATRNG stream keyed by (seed, env_id_base + i): a batch can be cut across GPUs
+ * without changing any env's trajectory. */
+int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_t seed, int device, at_env **out);
+int at_destroy(at_env *env);
+
+/* Geometry of the arrays: obs is float[n_envs][rows*dim], rewards float[n_envs][rows], done uint8[n_envs],
+ * actions int32[n_envs][action_rows][3].  rows = n_tanks (1v1 wrapper, gym_env.py:119) or #agent tanks
+ * (team wrapper, gym_env_multi.py:239); action_rows = 2 (1v1), #agents (team), 0 (arena). */
+int at_obs_dim(const at_env *env);
+int at_obs_rows(const at_env *env);
+int at_action_rows(const at_env *env);
+int at_num_walls(const at_env *env);
+int64_t at_num_envs(const at_env *env);
+
+/* Replaces env.reset() (gym_env.py:63-71, gym_env_multi.py:192-199) for the envs whose d_mask byte is
+ * non-zero (d_mask NULL = all).  Writes the reset observation rows of those envs into d_obs (if non-NULL). */
+int at_reset(at_env *env, const uint8_t *d_mask, float *d_obs, void *stream);
+
+/* Replaces env.step(actions) (gym_env.py:73-103, gym_env_multi.py:202-223): one fused kernel does bullets
+ * pass 1, controllers (agents from d_actions, bots on device), bullets pass 2, rewards (cumulative, F1),
+ * done / TERMINATE_TIME bookkeeping, optional auto-reset and the observation rows. */
+int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_rewards, uint8_t *d_done, void *stream);
+
+/* Same call with HOST action / reward / done buffers (pinned memory recommended): copies actions in,
+ * steps, copies rewards+done out and synchronises the stream.  Observations stay in HBM (d_obs). */
+int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
+                 void *stream);
+
+/* info dict of step(): winner int32[n_envs] (gym_env.py:97, -1 = nobody alive), hits / be_hits
+ * int32[n_envs][n_tanks] (gym_env_multi.py:220-222), change_time int32[n_envs][n_tanks] (gym_env.py:77-83).
+ * Any pointer may be NULL. */
+int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
+                void *stream);
+
+/* Snapshot / inject `count` envs starting at `first` (host AoS records).  Synchronous. */
+int at_get_state(at_env *env, int64_t first, int64_t count, at_env_state *h_out);
+int at_set_state(at_env *env, int64_t first, int64_t count, const at_env_state *h_in);
+
+/* Synthetic uniform action stream used by bench / tests: ATRNG stream 1+a, counter = tick
+ * (same function as oracle/atrng.py synthetic_actions).  d_actions int32[n_envs][action_rows][3]. */
+int at_synthetic_actions(at_env *env, int64_t tick, int32_t *d_actions, void *stream);
+
+/* Stand-alone primitives (parity tests of env/bfs.py:6-56 and env/maze.py:7-33).
+ * at_bfs_batch: d_maze uint8[n_mazes][121]; d_query int32[n][5] = (maze index, start r, c, goal r, c);
+ *               d_out int32[n][3] = (len(path) or 0 for None, path[1] row, col or -1).
+ * at_generate_mazes: maze i is generated from ATRNG stream (seed, env_id_base + i) starting at counter 0;
+ *               d_maze uint8[n][121], d_ctr uint32[n] = draws consumed. */
+int at_bfs_batch(int device, const uint8_t *d_maze, const int32_t *d_query, int64_t n, int32_t *d_out, void *stream);
+int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *d_maze, uint32_t *d_ctr,
+                      void *stream);
+
+/* Host copies of the device lookup tables (tests): cos/sin of math.radians(a), a = 0..360 -> double[361][2];
+ * pygame Vector2.rotate corner offsets -> double[361][4]. */
+int at_get_luts(const at_env *env, double *h_trig, double *h_corner);
+
+int64_t at_launch_count(const at_env *env); /* kernels launched through this handle so far */
+const char *at_last_error(void);
+const char *at_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,165 @@
+// emul.cpp - TEST-ONLY host emulation of the CUDA env kernel (alphatank_b200/csrc/at_kernels.cu).
+//
+// This GPU-less build container cannot run the kernels, so this file compiles the kernels' own per-thread
+// code (at_sim.h, __host__ __device__) with g++ and drives it the way env_kernel does: blocks of 64 envs,
+// phase A one "thread" per env over a block working set, phase B 32 "lanes" per observation row through a
+// staging buffer.  It lets the CPU test-suite compare the CUDA-side FORMULATION (cell bitmasks, integer-angle
+// tables, packed bullets, bit-parallel BFS, counter penalties, row builders) with the oracle before any GPU
+// time is spent.  It is not part of the product, is never loaded by alphatank_b200/, and is not a fallback:
+// the product fails loudly without a GPU.  What it cannot cover (warp sync, bulk-async stores, HBM layout
+// races) is covered by the -m gpu tests.
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../alphatank_b200/csrc/at_host.h"
+#include "../../alphatank_b200/csrc/at_sim.h"
+
+using namespace at;
+
+struct em_env {
+    KCfg k;
+    DevState st;
+    HostLuts luts;
+    int64_t n_envs;
+    std::vector<char> arena;
+    std::vector<char> block;  // one block's working set
+    std::vector<float> stage;
+    BlockMem bm;
+    std::vector<uint32_t> ecnt, ezones;
+    std::vector<uint64_t> ewlo, ewhi;
+};
+static thread_local std::string g_err;
+
+static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
+                uint8_t *done) {
+    const KCfg &c = env->k;
+    const DevState &st = env->st;
+    const int D = c.obs_dim;
+    for (int64_t b0 = 0; b0 < env->n_envs; b0 += BS) {
+        bool emit[BS] = {false};
+        for (int tid = 0; tid < BS; ++tid) {  // phase A
+            const int64_t e = b0 + tid;
+            if (e >= st.N) continue;
+            Sim s(c, st, env->bm, e, tid);
+            if (is_step) {
+                s.load();
+                float rw[MAX_TANKS];
+                const bool d = s.wrapper_step(actions ? actions + e * c.act_rows * 3 : nullptr, rw);
+                for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
+                done[e] = d ? 1 : 0;
+                if (d && c.auto_reset) s.env_reset();
+                s.store();
+                emit[tid] = obs != nullptr;
+            } else if (!mask || mask[e]) {
+                s.load();
+                s.env_reset();
+                s.store();
+                emit[tid] = obs != nullptr;
+            }
+            env->ecnt[tid] = s.cnt; env->ezones[tid] = s.zones; env->ewlo[tid] = s.wlo; env->ewhi[tid] = s.whi;
+        }
+        float *row = env->stage.data();  // phase B
+        if (c.map != 2) {
+            RowCtx rc{c, st, env->bm, row, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
+            for (int lane = 0; lane < 32; ++lane) row_static(rc, lane);
+        }
+        for (int q = 0; q < BS; ++q) {
+            if (!emit[q]) continue;
+            const int64_t ee = b0 + q;
+            for (int r = 0; r < c.rows; ++r) {
+                const int t = c.team_layout ? c.agent_tank[r] : r;
+                RowCtx rc{c, st, env->bm, row, q, ee, env->ecnt[q], env->ezones[q], env->ewlo[q], env->ewhi[q]};
+                if (c.map == 2) for (int lane = 0; lane < 32; ++lane) row_static(rc, lane);
+                for (int lane = 0; lane < 32; ++lane) row_clear_bullets(rc, lane);
+                for (int lane = 0; lane < 32; ++lane) row_bullets(rc, lane, t);
+                for (int lane = 0; lane < 32; ++lane) row_tanks(rc, lane, t);
+                for (int lane = 0; lane < 32; ++lane) row_misc(rc, lane, t);
+                memcpy(obs + (ee * c.rows + r) * (int64_t)D, row, sizeof(float) * D);
+            }
+        }
+    }
+}
+
+extern "C" {
+const char *em_last_error(void) { return g_err.c_str(); }
+
+int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_t seed, em_env **out) {
+    em_env *env = new em_env();
+    std::string msg = build_kcfg(cfg, seed, env_id_base, env->k);
+    if (!msg.empty()) { g_err = msg; delete env; return AT_ERR_ARG; }
+    env->n_envs = n_envs;
+    build_luts(env->luts);
+    const ArenaLayout L = arena_layout(env->k, n_envs);
+    env->arena.assign(L.bytes, 0);
+    bind_state(env->st, env->arena.data(), L, n_envs);
+    memcpy(env->arena.data() + L.o_trig, env->luts.trig.data(), 722 * 8);
+    memcpy(env->arena.data() + L.o_corn, env->luts.corn.data(), 361 * 4 * 8);
+    memcpy(env->arena.data() + L.o_pend, env->luts.pend.data(), PEND_LUT * 8);
+    const int n = env->k.n_tanks;
+    env->block.assign((size_t)n * BS * (5 * 8 + 5 * 4) + 722 * 8, 0);
+    char *p = env->block.data();
+    BlockMem &bm = env->bm;
+    bm.trig = (double *)p; p += 722 * 8;
+    memcpy(bm.trig, env->luts.trig.data(), 722 * 8);
+    bm.tx = (double *)p; p += n * BS * 8; bm.ty = (double *)p; p += n * BS * 8; bm.trew = (double *)p; p += n * BS * 8;
+    bm.bf0 = (double *)p; p += n * BS * 8; bm.bf1 = (double *)p; p += n * BS * 8;
+    bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.thits = (uint32_t *)p; p += n * BS * 4;
+    bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint32_t *)p; p += n * BS * 4;
+    bm.tshot = (int32_t *)p; p += n * BS * 4;
+    env->stage.assign(env->k.obs_dim + 8, 0.f);
+    env->ecnt.assign(BS, 0); env->ezones.assign(BS, 0); env->ewlo.assign(BS, 0); env->ewhi.assign(BS, 0);
+    run(env, false, nullptr, nullptr, nullptr, nullptr, nullptr);  // the constructor's own reset
+    *out = env;
+    return AT_OK;
+}
+void em_destroy(em_env *env) { delete env; }
+int em_obs_dim(em_env *env) { return env->k.obs_dim; }
+int em_obs_rows(em_env *env) { return env->k.rows; }
+int em_action_rows(em_env *env) { return env->k.act_rows; }
+void em_reset(em_env *env, const uint8_t *mask, float *obs) { run(env, false, nullptr, mask, obs, nullptr, nullptr); }
+void em_step(em_env *env, const int32_t *actions, float *obs, float *rewards, uint8_t *done) {
+    run(env, true, actions, nullptr, obs, rewards, done);
+}
+void em_get_state(em_env *env, int64_t e, at_env_state *out) {
+    PackedEnv p;
+    memset(&p, 0, sizeof p);
+    gather_env(env->k, env->st, e, p);
+    unpack_env(env->k, env->luts, p, *out);
+}
+int em_set_state(em_env *env, int64_t e, const at_env_state *in) {
+    PackedEnv p;
+    std::string msg = pack_env(env->k, env->luts, *in, p);
+    if (!msg.empty()) { g_err = msg; return AT_ERR_ARG; }
+    scatter_env(env->k, env->st, e, p);
+    return AT_OK;
+}
+void em_get_info(em_env *env, int32_t *winner, int32_t *hits, int32_t *be_hits, int32_t *change_time) {
+    const KCfg &c = env->k;
+    const DevState &st = env->st;
+    for (int64_t e = 0; e < st.N; ++e) {
+        int w = -1;
+        for (int i = 0; i < c.n_tanks; ++i) {
+            int64_t g = (int64_t)i * st.N + e;
+            if (w < 0 && (st.tpack[g] & TP_ALIVE)) w = i;
+            if (hits) hits[e * c.n_tanks + i] = (int32_t)(st.thits[g] & 0xFFFFu);
+            if (be_hits) be_hits[e * c.n_tanks + i] = (int32_t)(st.thits[g] >> 16);
+            if (change_time) change_time[e * c.n_tanks + i] = st.change_time[g];
+        }
+        if (winner) winner[e] = w;
+    }
+}
+int em_bfs(const uint8_t *maze121, int sr, int sc, int gr, int gc, int *next_r, int *next_c) {
+    uint64_t lo = 0, hi = 0;
+    for (int i = 0; i < CELLS; ++i)
+        if (maze121[i]) { if (i < 64) lo |= 1ull << i; else hi |= 1ull << (i - 64); }
+    return bfs_first_step(lo, hi, sr, sc, gr, gc, next_r, next_c);
+}
+void em_generate_maze(uint64_t seed, int64_t env_id, uint32_t *ctr, uint8_t *maze121) {
+    uint64_t lo, hi;
+    generate_maze_mask(seed, env_id, *ctr, lo, hi);
+    for (int i = 0; i < CELLS; ++i) maze121[i] = (uint8_t)((i < 64 ? lo >> i : hi >> (i - 64)) & 1ull);
+}
+}

@@ -1,0 +1,132 @@
+"""CPU: the CUDA kernel's per-thread code (alphatank_b200/csrc/at_sim.h), compiled with g++ into the
+test-only emulator (tests/cpu_emul), against the reference traces and against the oracle.
+
+This checks the kernel FORMULATION (bitmask walls, LUT trig, packed bullets, bit-parallel BFS, row builders)
+in the GPU-less build container; the real kernels are checked by the -m gpu tests."""
+import os
+
+import numpy as np
+import pytest
+
+import emul_env
+import parity
+from oracle import oracle as O
+from oracle.atrng import synthetic_actions
+
+
+@pytest.mark.parametrize("name", parity.fixture_names())
+def test_kernel_logic_replays_reference_trace(name):
+    rec = parity.load_fixture(name)
+    meta = rec["meta"]
+    env = emul_env.make_emul_env(parity.env_spec(meta), 1, meta["seed"], meta["env_id"])
+    assert env.D * env.R == rec["obs"].shape[1]
+    parity.replay_fixture(env, rec, where=name, max_ticks=700, check_state_every=3)
+
+
+def _spec(mode, layout, map_="octagon", tt=None, weakness=1.0, buff=True, debuff=True):
+    ids = {}
+    return dict(mode=mode, teams=[ids.setdefault(t, len(ids)) for t, _, _ in layout], ctrl=[c for _, c, _ in layout],
+                bots=[b for _, _, b in layout], map=map_, terminate_time=tt, buff_on=buff, debuff_on=debuff,
+                weakness=weakness)
+
+
+T = parity.TEAM_DICTS
+SWEEP = {
+    "agent_maze": _spec("agent", [("A", "agent", None), ("B", "agent", None)], "maze"),
+    "agent_t96": _spec("agent", [("A", "agent", None), ("B", "agent", None)], tt=96),
+    "botagent_smart_maze": _spec("bot_agent", [("A", "bot", "smart"), ("B", "agent", None)], "maze"),
+    "botagent_dodge_weak": _spec("bot_agent", [("A", "bot", "dodge"), ("B", "agent", None)], weakness=0.6),
+    "arena_def_dodge_t200": _spec("arena", [("A", "bot", "defensive"), ("B", "bot", "dodge")], tt=200),
+    "arena_random_aggr_maze": _spec("arena", [("A", "bot", "random"), ("B", "bot", "aggressive")], "maze"),
+    "team_vs_bot": _spec("team", T["team_vs_bot_configs"]),
+    "team_vs_bot_maze": _spec("team", T["team_vs_bot_configs"], "maze"),
+    "team_harder_battlefield": _spec("team", T["team_vs_bot_harder_configs"], "battlefield"),
+    "team_three_teams_nodebuff": _spec("team", T["bot_team_configs"], debuff=False),
+    "team_8_mixed": _spec("team", [("A", "agent", None), ("A", "bot", "dodge"), ("B", "bot", "smart"), ("B", "agent", None),
+                                   ("C", "bot", "random"), ("C", "bot", "defensive"), ("D", "bot", "aggressive"),
+                                   ("D", "agent", None)], tt=150),
+}
+
+
+@pytest.mark.parametrize("name", sorted(SWEEP))
+def test_kernel_logic_matches_oracle_on_batches(name):
+    spec = SWEEP[name]
+    N, ticks, seed, base = 96, 260, 2024, 1000   # 96 envs: one full and one partial block of 64
+    a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
+    b = emul_env.make_emul_env(spec, N, seed, base, auto_reset=True)
+    assert (a.D, a.R, a.A) == (b.D, b.R, b.A)
+    assert np.array_equal(a.reset(), b.reset())
+    ids = np.arange(base, base + N)
+    dones = 0
+    for t in range(ticks):
+        acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
+        oa, ra, da = a.step(acts, threads=4)
+        ob, rb, db = b.step(acts)
+        assert np.array_equal(da, db), "%s tick %d done" % (name, t)
+        assert np.array_equal(ra, rb), "%s tick %d rewards" % (name, t)
+        if not np.array_equal(oa, ob):
+            bad = np.argwhere(oa != ob)
+            raise AssertionError("%s tick %d obs differ at (env, col) %s" % (name, t, bad[:8].tolist()))
+        dones += int(da.sum())
+    sa, sb = a.get_state(), b.get_state()
+    for f in ("n_bullets", "tick", "training_step", "episode_steps", "rng_ctr", "zones", "maze"):
+        assert np.array_equal(sa[f], sb[f]), f
+    n = a.n_tanks
+    for f in ("x", "y", "reward", "angle", "speed", "alive", "hitting_wall", "in_buff", "in_debuff", "max_bullets",
+              "last_shot_ms", "num_hit", "num_be_hit"):
+        assert np.array_equal(sa["tanks"][f][:, :n], sb["tanks"][f][:, :n]), f
+    for i in range(N):
+        nb = sa["n_bullets"][i]
+        for f in ("x", "y", "dx", "dy", "pending", "owner", "distance", "bounces", "cleared"):
+            assert np.array_equal(sa["bullets"][f][i, :nb], sb["bullets"][f][i, :nb]), f
+    ia, ib = a.info(), b.info()
+    for f in ia:
+        assert np.array_equal(ia[f], ib[f]), f
+    assert dones > 0 or spec["mode"] == "agent"
+
+
+def test_bfs_bitparallel_matches_reference_pairs():
+    z = np.load(os.path.join(parity.GOLDEN, "bfs.npz"))
+    grids, cases = z["grids"], z["cases"]
+    L = emul_env.lib()
+    import ctypes as C
+    nr, nc = C.c_int(), C.c_int()
+    flat = [np.ascontiguousarray(g.reshape(-1)) for g in grids]
+    for gi, sr, sc, gr, gc, ln, er, ec in cases[::3].tolist():
+        n = L.em_bfs(flat[gi].ctypes.data, sr, sc, gr, gc, C.byref(nr), C.byref(nc))
+        assert n == ln
+        if ln > 1:
+            assert (nr.value, nc.value) == (er, ec)
+
+
+def test_maze_kernel_logic_matches_reference():
+    z = np.load(os.path.join(parity.GOLDEN, "mazes.npz"))
+    import ctypes as C
+    L = emul_env.lib()
+    for i, (m, c) in enumerate(zip(z["mazes"], z["ctrs"])):
+        out = np.zeros(121, np.uint8)
+        ctr = C.c_uint32(0)
+        L.em_generate_maze(int(z["seed"]), i, C.byref(ctr), out.ctypes.data)
+        assert np.array_equal(out.reshape(11, 11), m) and ctr.value == c
+
+
+def test_state_roundtrip_through_packed_layout():
+    spec = SWEEP["team_8_mixed"]
+    a = parity.make_oracle_env(spec, 4, 5, 0)
+    b = emul_env.make_emul_env(spec, 4, 5, 0)
+    ids = np.arange(4)
+    for t in range(150):
+        a.step(synthetic_actions(5, ids, t, a.A))
+    for i in range(4):                      # inject oracle state into the packed SoA layout and read it back
+        b.set_state(i, a.get_state(i))
+        sa, sb = a.get_state(i), b.get_state(i)
+        n, nb = a.n_tanks, sa["n_bullets"]
+        for f in ("x", "y", "reward", "angle", "speed", "alive", "num_hit", "num_be_hit", "last_shot_ms"):
+            assert np.array_equal(sa["tanks"][f][:n], sb["tanks"][f][:n]), f
+        for f in ("x", "y", "dx", "dy", "pending", "owner", "distance", "bounces", "cleared"):
+            assert np.array_equal(sa["bullets"][f][:nb], sb["bullets"][f][:nb]), f
+    for t in range(150, 260):               # and keep stepping in lock-step
+        acts = synthetic_actions(5, ids, t, a.A)
+        oa, ra, da = a.step(acts)
+        ob, rb, db = b.step(acts)
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db)
