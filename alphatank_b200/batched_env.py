@@ -1,0 +1,191 @@
+"""BatchedTankEnv - owner of one at_env handle (include/alphatank_b200.h) plus the torch-visible
+buffers the kernels write into.  The reference-facing classes in gym_env.py / gym_env_multi.py are
+thin shape adapters over this class.  PyTorch is used for device memory and streams only."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _capi
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class LazyInfo(dict):
+    """``info`` dict of step(): the device tensors are produced (one small kernel) on first access."""
+
+    def __init__(self, env, keys):
+        super().__init__()
+        self._env, self._keys, self._done = env, keys, False
+
+    def _fill(self):
+        if not self._done:
+            self._done = True
+            full = self._env.get_info()
+            for k in self._keys:
+                dict.__setitem__(self, k, full[k])
+
+    def __getitem__(self, k):
+        self._fill()
+        return dict.__getitem__(self, k)
+
+    def __contains__(self, k):
+        return k in self._keys
+
+    def keys(self):
+        self._fill()
+        return dict.keys(self)
+
+    def items(self):
+        self._fill()
+        return dict.items(self)
+
+    def get(self, k, default=None):
+        self._fill()
+        return dict.get(self, k, default)
+
+    def __repr__(self):
+        self._fill()
+        return dict.__repr__(self)
+
+
+class BatchedTankEnv:
+    def __init__(self, cfg, num_envs, device="cuda:0", seed=0, env_id_base=0):
+        self.L = _capi.lib()                      # raises NativeLibraryMissing when not built
+        if not torch.cuda.is_available():
+            raise RuntimeError("alphatank_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("alphatank_b200 envs live in GPU memory; device must be a cuda device, got %r" % (device,))
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.cfg, self.num_envs, self.seed, self.env_id_base = cfg, int(num_envs), int(seed), int(env_id_base)
+        h = C.c_void_p()
+        _capi.check(self.L.at_create(C.byref(cfg), self.num_envs, self.env_id_base, self.seed, self.dev_index,
+                                     C.byref(h)), "at_create")
+        self.h = h
+        self.D = self.L.at_obs_dim(h)
+        self.R = self.L.at_obs_rows(h)
+        self.A = self.L.at_action_rows(h)
+        self.n_tanks = cfg.n_tanks
+        self.num_walls = self.L.at_num_walls(h)
+        N, dev = self.num_envs, self.device
+        self.obs = torch.zeros((N, self.R * self.D), dtype=torch.float32, device=dev)
+        self.rewards = torch.zeros((N, self.R), dtype=torch.float32, device=dev)
+        self.done = torch.zeros((N,), dtype=torch.uint8, device=dev)
+        self._actions = torch.zeros((N, max(self.A, 1), 3), dtype=torch.int32, device=dev)
+        self._h_rewards = self._h_done = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.at_destroy(self.h)
+            self.h = None
+
+    __del__ = close
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ------------------------------------------------------------------ core calls
+    def reset(self, mask=None, obs_out=None):
+        obs = self.obs if obs_out is None else obs_out
+        m = None
+        if mask is not None:
+            m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        _capi.check(self.L.at_reset(self.h, _ptr(m), _ptr(obs), self._stream()), "at_reset")
+        return obs
+
+    def _device_actions(self, actions):
+        if self.A == 0:
+            return None
+        if isinstance(actions, torch.Tensor):
+            a = actions
+        else:
+            a = torch.as_tensor(np.asarray(actions))
+        a = a.reshape(self.num_envs, self.A, 3)
+        if a.device != self.device or a.dtype != torch.int32 or not a.is_contiguous():
+            self._actions.copy_(a, non_blocking=True)
+            a = self._actions
+        return a
+
+    def step(self, actions=None, obs_out=None, rewards_out=None, done_out=None):
+        """actions: int tensor/array [N, A, 3] (any int dtype, any device).  Outputs default to the env's own
+        persistent buffers (self.obs / self.rewards / self.done) and may be redirected, e.g. into rollout storage."""
+        a = self._device_actions(actions)
+        obs = self.obs if obs_out is None else obs_out
+        rew = self.rewards if rewards_out is None else rewards_out
+        dn = self.done if done_out is None else done_out
+        _capi.check(self.L.at_step(self.h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(dn), self._stream()), "at_step")
+        return obs, rew, dn
+
+    def step_host(self, h_actions):
+        """End-to-end variant: actions come from (pinned) HOST memory, rewards and done are returned in pinned
+        host memory, observations stay in HBM.  Synchronises the current stream."""
+        if self._h_rewards is None:
+            self._h_rewards = torch.zeros((self.num_envs, self.R), dtype=torch.float32).pin_memory()
+            self._h_done = torch.zeros((self.num_envs,), dtype=torch.uint8).pin_memory()
+        ap = None
+        if self.A:
+            if not (isinstance(h_actions, torch.Tensor) and h_actions.dtype == torch.int32 and h_actions.is_contiguous()
+                    and h_actions.device.type == "cpu"):
+                h_actions = torch.as_tensor(np.asarray(h_actions), dtype=torch.int32).contiguous()
+            ap = C.c_void_p(h_actions.data_ptr())
+        _capi.check(self.L.at_step_host(self.h, ap, _ptr(self.obs), C.c_void_p(self._h_rewards.data_ptr()),
+                                        C.c_void_p(self._h_done.data_ptr()), self._stream()), "at_step_host")
+        return self.obs, self._h_rewards, self._h_done
+
+    def synthetic_actions(self, tick, out=None):
+        out = self._actions if out is None else out
+        _capi.check(self.L.at_synthetic_actions(self.h, int(tick), _ptr(out), self._stream()), "at_synthetic_actions")
+        return out
+
+    def get_info(self):
+        N, n, dev = self.num_envs, self.n_tanks, self.device
+        winner = torch.empty((N,), dtype=torch.int32, device=dev)
+        hits = torch.empty((N, n), dtype=torch.int32, device=dev)
+        be_hits = torch.empty((N, n), dtype=torch.int32, device=dev)
+        change = torch.empty((N, n), dtype=torch.int32, device=dev)
+        _capi.check(self.L.at_get_info(self.h, _ptr(winner), _ptr(hits), _ptr(be_hits), _ptr(change), self._stream()),
+                    "at_get_info")
+        return {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change}
+
+    def get_state(self, first=0, count=None):
+        count = self.num_envs - first if count is None else count
+        out = np.zeros(count, _capi.ENV_STATE_DT)
+        torch.cuda.synchronize(self.device)
+        _capi.check(self.L.at_get_state(self.h, int(first), int(count), out.ctypes.data), "at_get_state")
+        return out
+
+    def set_state(self, first, states):
+        st = np.ascontiguousarray(np.asarray(states, dtype=_capi.ENV_STATE_DT).reshape(-1))
+        torch.cuda.synchronize(self.device)
+        _capi.check(self.L.at_set_state(self.h, int(first), int(st.shape[0]), st.ctypes.data), "at_set_state")
+
+    def launch_count(self):
+        return int(self.L.at_launch_count(self.h))
+
+    def luts(self):
+        trig, corn = np.zeros((361, 2)), np.zeros((361, 4))
+        _capi.check(self.L.at_get_luts(self.h, trig.ctypes.data, corn.ctypes.data), "at_get_luts")
+        return trig, corn
+
+
+class TankView:
+    """``env.game_env.tanks[i]`` stand-in: per-tank state columns as torch tensors over the batch
+    (the reference's callers read ``tanks[i].alive``, inference.py:115-116)."""
+
+    def __init__(self, owner, index):
+        self._o, self._i = owner, index
+
+    def _col(self, name):
+        st = self._o.core.get_state()
+        return torch.as_tensor(st["tanks"][name][:, self._i].copy())
+
+    alive = property(lambda s: s._col("alive").bool())
+    x = property(lambda s: s._col("x"))
+    y = property(lambda s: s._col("y"))
+    angle = property(lambda s: s._col("angle"))
+    reward = property(lambda s: s._col("reward"))
+    num_hit = property(lambda s: s._col("num_hit"))
+    num_be_hit = property(lambda s: s._col("num_be_hit"))

@@ -1,0 +1,251 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI (ctypes -> libalphatank_b200.so), against
+ (a) the golden traces recorded from the unmodified reference,
+ (b) the CPU oracle on seeded batches, and
+ (c) size-independent properties at BASELINE.json's full batch sizes.
+Bar: bit-exact events / integer state / f64 positions / f32 obs; rewards bit-exact as well (the kernels
+restate the reference's fp64 operation order, including numpy's FMA-contracted 2-vector dots)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import parity
+from oracle.atrng import synthetic_actions
+from test_kernel_logic_cpu import SWEEP
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu(*a, **k):
+    from gpu_env import GpuEnv
+    return GpuEnv(*a, **k)
+
+
+def test_native_library_is_the_cuda_one():
+    from alphatank_b200 import _capi
+    L = _capi.lib()
+    assert b"sm_100a" in L.at_version()
+    assert torch.cuda.get_device_capability(0)[0] >= 10
+
+
+@pytest.mark.parametrize("name", parity.fixture_names())
+def test_cuda_replays_reference_trace(name):
+    rec = parity.load_fixture(name)
+    meta = rec["meta"]
+    env = _gpu(parity.env_spec(meta), 1, meta["seed"], meta["env_id"])
+    assert env.D * env.R == rec["obs"].shape[1]
+    parity.replay_fixture(env, rec, where=name, check_state_every=2)
+
+
+@pytest.mark.parametrize("name", sorted(SWEEP))
+def test_cuda_matches_oracle_on_batches(name):
+    spec = SWEEP[name]
+    N, ticks, seed, base = 1000, 220, 77, 5000          # 1000: last block partially filled
+    a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
+    b = _gpu(spec, N, seed, base, auto_reset=True)
+    assert (a.D, a.R, a.A) == (b.D, b.R, b.A)
+    assert np.array_equal(a.reset(), b.reset())
+    ids = np.arange(base, base + N)
+    thr = os.cpu_count() or 1
+    dones = 0
+    for t in range(ticks):
+        acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
+        oa, ra, da = a.step(acts, threads=thr)
+        ob, rb, db = b.step(acts)
+        assert np.array_equal(da, db), "%s tick %d done differs for envs %s" % (name, t, np.nonzero(da != db)[0][:8])
+        assert np.array_equal(ra, rb), "%s tick %d rewards differ for envs %s" % (
+            name, t, np.unique(np.nonzero(ra != rb)[0])[:8])
+        if not np.array_equal(oa, ob):
+            raise AssertionError("%s tick %d obs differ at (env, col) %s" % (name, t, np.argwhere(oa != ob)[:8].tolist()))
+        dones += int(da.sum())
+    sa, sb = a.get_state(), b.get_state()
+    n = a.n_tanks
+    for f in ("n_bullets", "tick", "training_step", "episode_steps", "rng_ctr", "zones", "maze"):
+        assert np.array_equal(sa[f], sb[f]), f
+    for f in ("x", "y", "reward", "angle", "speed", "alive", "hitting_wall", "in_buff", "in_debuff", "max_bullets",
+              "last_shot_ms", "num_hit", "num_be_hit"):
+        assert np.array_equal(sa["tanks"][f][:, :n], sb["tanks"][f][:, :n]), f
+    ia, ib = a.info(), b.info()
+    for f in ia:
+        assert np.array_equal(ia[f], ib[f]), f
+    assert dones > 0 or spec["mode"] == "agent"
+
+
+def test_device_action_stream_is_atrng():
+    b = _gpu(SWEEP["team_vs_bot"], 300, 9, 123)
+    for tick in (0, 1, 77, 2**20):
+        got = b.core.synthetic_actions(tick).cpu().numpy()
+        assert np.array_equal(got, synthetic_actions(9, np.arange(123, 423), tick, b.A))
+
+
+def test_bfs_kernel_matches_reference_pairs():
+    from alphatank_b200 import _capi
+    import ctypes as C
+    z = np.load(os.path.join(parity.GOLDEN, "bfs.npz"))
+    grids = torch.as_tensor(z["grids"].reshape(len(z["grids"]), -1).astype(np.uint8)).cuda()
+    cases = z["cases"].astype(np.int32)
+    q = torch.as_tensor(np.ascontiguousarray(cases[:, :5])).cuda()
+    out = torch.zeros((len(cases), 3), dtype=torch.int32, device="cuda")
+    _capi.check(_capi.lib().at_bfs_batch(0, C.c_void_p(grids.data_ptr()), C.c_void_p(q.data_ptr()), len(cases),
+                                         C.c_void_p(out.data_ptr()), None), "at_bfs_batch")
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[:, 0], cases[:, 5])                       # len(path): BFS distances bit-exact
+    moving = cases[:, 5] > 1
+    assert np.array_equal(o[moving, 1:], cases[moving, 6:8])          # path[1], incl. the FIFO tie-break
+
+
+def test_maze_kernel_matches_reference():
+    from alphatank_b200 import _capi
+    import ctypes as C
+    z = np.load(os.path.join(parity.GOLDEN, "mazes.npz"))
+    n = len(z["mazes"])
+    m = torch.zeros((n, 121), dtype=torch.uint8, device="cuda")
+    c = torch.zeros((n,), dtype=torch.int32, device="cuda")
+    _capi.check(_capi.lib().at_generate_mazes(0, int(z["seed"]), 0, n, C.c_void_p(m.data_ptr()),
+                                              C.c_void_p(c.data_ptr()), None), "at_generate_mazes")
+    torch.cuda.synchronize()
+    assert np.array_equal(m.cpu().numpy().reshape(n, 11, 11), z["mazes"])
+    assert np.array_equal(c.cpu().numpy(), z["ctrs"])
+
+
+def test_lookup_tables_are_libm():
+    import math
+    b = _gpu(SWEEP["agent_t96"], 1, 0)
+    trig, corn = b.core.luts()
+    for a in range(361):
+        assert trig[a, 0] == math.cos(math.radians(a)) and trig[a, 1] == math.sin(math.radians(a))
+    from oracle import oracle as O
+    out = np.zeros(8)
+    for a in range(361):
+        O.lib().ato_corners(0.0, 0.0, a, out.ctypes.data)
+        assert np.array_equal(corn[a], out[:4])
+
+
+# ----------------------------------------------------------------- BASELINE.json sizes: properties
+def _full(name, N, seed=3, base=0, **kw):
+    return _gpu(SWEEP[name], N, seed, base, auto_reset=True, **kw)
+
+
+def test_full_size_2v2_shard_invariance_determinism_and_oracle_slices():
+    """config 3 (65536 envs, 2 agents vs 2 smart bots): (i) two identical runs are bitwise equal, (ii) env i of the
+    big batch equals the same env id stepped in a small batch (how the 8-GPU sharding cuts the id space),
+    (iii) the first / last envs equal the CPU oracle, (iv) invariants on the whole batch."""
+    N, ticks, seed = 65536, 160, 3
+    big = _full("team_vs_bot", N, seed)
+    big2 = _full("team_vs_bot", N, seed)
+    lo = _full("team_vs_bot", 96, seed, 0)
+    hi = _full("team_vs_bot", 96, seed, N - 96)
+    ora = parity.make_oracle_env(SWEEP["team_vs_bot"], 96, seed, N - 96, auto_reset=True)
+    for e in (big, big2, lo, hi, ora):
+        e.reset()
+    dones = np.zeros(N, np.int64)
+    acts = torch.zeros((N, big.A, 3), dtype=torch.int32, device="cuda")
+    for t in range(ticks):
+        big.core.synthetic_actions(t, acts)
+        o1, r1, d1 = big.core.step(acts)
+        o1, r1, d1 = o1.clone(), r1.clone(), d1.clone()
+        o2, r2, d2 = big2.core.step(acts)
+        assert torch.equal(o1, o2) and torch.equal(r1, r2) and torch.equal(d1, d2), "run-to-run determinism, tick %d" % t
+        a = acts.cpu().numpy()
+        ol, rl, dl = lo.step(a[:96])
+        oh, rh, dh = hi.step(a[-96:])
+        oo, ro, do = ora.step(a[-96:], threads=4)
+        o1n, r1n, d1n = o1.cpu().numpy(), r1.cpu().numpy(), d1.cpu().numpy()
+        assert np.array_equal(o1n[:96], ol) and np.array_equal(r1n[:96], rl) and np.array_equal(d1n[:96], dl)
+        assert np.array_equal(o1n[-96:], oh) and np.array_equal(r1n[-96:], rh) and np.array_equal(d1n[-96:], dh)
+        assert np.array_equal(oh, oo) and np.array_equal(rh, ro) and np.array_equal(dh, do), "oracle slice, tick %d" % t
+        assert np.isfinite(o1n).all() and o1n.min() >= -1.0 - 770.0 and o1n.max() <= 771.0
+        dones += d1n
+    st = big.get_state()
+    assert (st["n_bullets"] <= 24).all() and (st["n_bullets"] >= 0).all()
+    assert (st["tick"] == ticks).all()
+    tk = st["tanks"]
+    assert ((tk["x"][:, :4] > 70) & (tk["x"][:, :4] < 700) & (tk["y"][:, :4] > 70) & (tk["y"][:, :4] < 700)).all()
+    assert ((tk["angle"][:, :4] >= 0) & (tk["angle"][:, :4] <= 360)).all()
+    assert dones.sum() > N // 4                                      # episodes do end (about 190 ticks each)
+    assert (tk["num_hit"][:, :4].sum(1) == tk["num_be_hit"][:, :4].sum(1)).all()   # every hit has a victim
+
+
+def test_full_size_arena_stress_bullet_saturation():
+    """config 4 (262144 envs, defensive vs dodge, TERMINATE_TIME=4096 -> immortal tanks, bullets saturate)."""
+    N = 262144
+    spec = dict(SWEEP["arena_def_dodge_t200"], terminate_time=4096)
+    env = _gpu(spec, N, 11, 0, auto_reset=True)
+    env.core.reset()
+    for t in range(120):
+        env.core.step(None)
+    st = env.get_state(0, 4096) if False else env.core.get_state(0, 4096)
+    assert st["n_bullets"].max() == 12 or st["n_bullets"].max() >= 10
+    assert (st["tanks"]["alive"][:, :2] == 1).all()                  # nobody dies with TERMINATE_TIME set
+    d = env.core.done.cpu().numpy()
+    assert d.sum() == 0                                              # 120 < 4096
+    ora = parity.make_oracle_env(spec, 64, 11, 0, auto_reset=True)
+    ora.reset()
+    for t in range(120):
+        ora.step(None)
+    so = ora.get_state()
+    assert np.array_equal(so["tanks"]["reward"][:, :2], st["tanks"]["reward"][:64, :2])
+    assert np.array_equal(so["n_bullets"], st["n_bullets"][:64])
+
+
+def test_step_host_equals_step_and_non_default_stream():
+    spec = SWEEP["team_vs_bot"]
+    a = _gpu(spec, 512, 5, 0, auto_reset=True)
+    b = _gpu(spec, 512, 5, 0, auto_reset=True)
+    a.reset(); b.reset()
+    s = torch.cuda.Stream()
+    h = torch.zeros((512, a.A, 3), dtype=torch.int32).pin_memory()
+    for t in range(60):
+        acts = synthetic_actions(5, np.arange(512), t, a.A)
+        h.copy_(torch.as_tensor(acts))
+        with torch.cuda.stream(s):
+            ob, rb, db = b.core.step_host(h)
+        oa, ra, da = a.step(acts)
+        assert np.array_equal(oa, ob.cpu().numpy()) and np.array_equal(ra, rb.numpy()) and np.array_equal(da, db.numpy())
+
+
+def test_masked_reset_only_touches_masked_envs():
+    spec = SWEEP["agent_t96"]
+    env = _gpu(spec, 200, 8, 0)
+    env.reset()
+    for t in range(10):
+        env.step(synthetic_actions(8, np.arange(200), t, env.A))
+    before = env.get_state()
+    obs_before = env.core.obs.cpu().numpy().copy()
+    mask = np.zeros(200, np.uint8)
+    mask[[3, 64, 199]] = 1
+    obs = env.reset(mask)
+    after = env.get_state()
+    keep = mask == 0
+    assert np.array_equal(before[keep], after[keep])
+    assert np.array_equal(obs[keep], obs_before[keep])
+    assert (after["tanks"]["reward"][mask == 1][:, :2] == 0).all() and (after["n_bullets"][mask == 1] == 0).all()
+    assert (after["rng_ctr"][mask == 1] > before["rng_ctr"][mask == 1]).all()
+
+
+def test_reference_facing_classes_and_errors():
+    from alphatank_b200 import MultiAgentEnv, MultiAgentTeamEnv
+    from alphatank_b200.configs import config_teams
+    env = MultiAgentEnv(mode="bot_agent", type="train", bot_type="smart", weakness=1.0, num_envs=8, seed=1)
+    obs, info = env.reset()
+    assert tuple(obs.shape) == (8, 2, 388) and env.observation_space.shape[0] == 776          # F2, H11
+    assert list(env.action_space.nvec[:3]) == [3, 3, 2] and env.num_tanks == 2
+    acts = torch.zeros((8, 2, 3), dtype=torch.int64, device="cuda")                              # Categorical samples are int64
+    obs, rew, done, trunc, info = env.step(acts)
+    assert tuple(obs.shape) == (8, 776) and tuple(rew.shape) == (8, 2) and trunc is False
+    assert set(info.keys()) == {"change_time", "winner"}
+    env.render(); env.set_bot_type("aggressive")
+    assert env.game_env.bot_type == "aggressive" and env.game_env.tanks[0].alive.shape == (8,)
+    tenv = MultiAgentTeamEnv(config_teams.team_vs_bot_configs, num_envs=4)
+    o, _ = tenv.reset()
+    assert tuple(o.shape) == (4, 1056) and tenv.num_agents == 2 and tenv.get_observation_order() == ["Tank1", "Tank2"]
+    o, r, d, _, info = tenv.step(np.zeros((4, 2, 3), np.int64))
+    assert tuple(info["hits"].shape) == (4, 4)
+    with pytest.raises(ValueError):
+        MultiAgentEnv(mode="human_play", num_envs=2)
+    with pytest.raises(ValueError):
+        MultiAgentEnv(mode="bot_agent", bot_type="nonsense", num_envs=2)                          # bot_factory.py:29-31
+    with pytest.raises(ValueError):
+        MultiAgentTeamEnv(config_teams.mixed_team_configs, num_envs=2)                            # human tanks
