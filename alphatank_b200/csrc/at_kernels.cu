@@ -367,7 +367,7 @@ int at_reset(at_env *env, const uint8_t *d_mask, float *d_obs, void *stream) {
 int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_rewards, uint8_t *d_done, void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_step: null handle");
     if (env->k.act_rows > 0 && !d_actions) return fail(AT_ERR_ARG, "at_step: this mode needs an actions array");
-    if (!d_rewards || !d_done) return fail(AT_ERR_ARG, "at_step: rewards / done must not be null");
+    if ((env->k.rows > 0 && !d_rewards) || !d_done) return fail(AT_ERR_ARG, "at_step: rewards / done must not be null");
     CUDA_TRY(cudaSetDevice(env->device));
     return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream);
 }
@@ -375,7 +375,7 @@ int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_reward
 int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
                  void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_step_host: null handle");
-    if (!h_rewards || !h_done) return fail(AT_ERR_ARG, "at_step_host: rewards / done must not be null");
+    if ((env->k.rows > 0 && !h_rewards) || !h_done) return fail(AT_ERR_ARG, "at_step_host: rewards / done must not be null");
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(env->device));
     const int64_t N = env->n_envs;
@@ -387,7 +387,8 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
     int rc = launch_env_kernel(env, true, env->d_actions_scratch, nullptr, d_obs, env->d_rewards_scratch,
                                env->d_done_scratch, s);
     if (rc != AT_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(h_rewards, env->d_rewards_scratch, (size_t)N * env->k.rows * 4, cudaMemcpyDeviceToHost, s));
+    if (env->k.rows > 0)
+        CUDA_TRY(cudaMemcpyAsync(h_rewards, env->d_rewards_scratch, (size_t)N * env->k.rows * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(h_done, env->d_done_scratch, (size_t)N, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return AT_OK;

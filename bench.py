@@ -106,7 +106,7 @@ class ClockSampler:
                             self.reasons.add(nm)
             except Exception:  # noqa: BLE001
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.01)
 
     def __enter__(self):
         self._t.start()
@@ -246,9 +246,8 @@ def run_ours(args):
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": E, "total_envs": total_envs, "agents_per_env": N_AGENTS,
                    "tanks_per_env": 4, "obs_dim": core.D, "parallelism": "env-id sharding x%d, no step-path collective"
-                   % world, "timing": "per-step working set (state ~%d MB + obs %d MB written) exceeds the 126 MB L2; "
-                   "no flush needed" % (ALG_BYTES_PER_ENV_STEP * E // 2**20 - core.D * 8 * E // 2**20,
-                                        core.D * 8 * E // 2**20),
+                   % world, "timing": "per-step footprint (SoA state ~%d MB + %d MB of observations written) exceeds the "
+                   "126 MB L2; no flush between steps needed" % (804 * E // 2**20, core.D * 4 * N_AGENTS * E // 2**20),
                    "env_steps_per_sec": value / N_AGENTS},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
