@@ -280,8 +280,14 @@ struct Sim {
     // first wall (row-major = reference list order, gaming_env.py:610-615) that a w x h pygame.Rect at
     // integer (ix, iy) collides with; -1 if none.  Replaces `for wall in walls: colliderect` scans.
     AT_HD int first_wall(int ix, int iy, int w, int h) const {
-        int c0 = imax(fdiv70(ix), 0), c1 = imin(fdiv70(ix + w - 1), 10);
-        int r0 = imax(fdiv70(iy), 0), r1 = imin(fdiv70(iy + h - 1), 10);
+        int c0, c1, r0, r1;
+        if ((ix | iy) >= 0) {  // one division per axis; the far edge is at most one cell further (w, h <= 70)
+            c0 = ix / 70; c1 = imin(c0 + ((ix - 70 * c0 + w - 1) >= 70 ? 1 : 0), 10);
+            r0 = iy / 70; r1 = imin(r0 + ((iy - 70 * r0 + h - 1) >= 70 ? 1 : 0), 10);
+        } else {               // look-ahead rects of the dodge bot may leave the arena (App. H note)
+            c0 = imax(fdiv70(ix), 0); c1 = imin(fdiv70(ix + w - 1), 10);
+            r0 = imax(fdiv70(iy), 0); r1 = imin(fdiv70(iy + h - 1), 10);
+        }
         for (int r = r0; r <= r1; ++r)
             for (int cc = c0; cc <= c1; ++cc)
                 if (wall_at(r * 11 + cc)) return r * 11 + cc;
@@ -575,6 +581,45 @@ struct Sim {
         if (!reachable) return false;
         int bounces = 0, dist = 0;
         for (;;) {
+            // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every time.
+            // When the 5x5 rect is provably clear of every enemy rect for the next m sub-steps (each axis moves
+            // <= 1 px per sub-step) and the bounding box of the m-step sweep touches only free cells, those m
+            // iterations can only be "advance": do the same m sequential additions (bit-identical positions)
+            // and skip the tests.  m is capped so that `dist > 300` cannot fire inside the jump.
+            int m = 300 - dist;
+            if (m >= 4) {
+                double g = 1.0e9;
+                for (int k = 0; k < ne; ++k) {
+                    double gx = fmax((double)ex[k] - (x + 5.0), x - (double)(ex[k] + 31));
+                    double gy = fmax((double)ey[k] - (y + 5.0), y - (double)(ey[k] + 25));
+                    g = fmin(g, fmax(gx, gy));
+                }
+                m = imin(imin(m, 64), g > 2.0 ? d2i(g) - 2 : 0);
+                while (m >= 4) {
+                    const double x1 = x + (double)m * dx, y1 = y + (double)m * dy;
+                    const double xlo = fmin(x, x1) - 1.0, xhi = fmax(x, x1) + 6.0;
+                    const double ylo = fmin(y, y1) - 1.0, yhi = fmax(y, y1) + 6.0;
+                    const int ca = xlo < 0.0 ? 0 : d2i(xlo) / 70, cb = imin(d2i(xhi) / 70, 10);
+                    const int ra = ylo < 0.0 ? 0 : d2i(ylo) / 70, rb = imin(d2i(yhi) / 70, 10);
+                    const uint32_t colmask = ((1u << (cb - ca + 1)) - 1u) << ca;
+                    bool blocked = false;
+                    for (int r = ra; r <= rb; ++r) {
+                        const int sh = r * 11;
+                        const uint64_t rowbits = sh < 64 ? ((wlo >> sh) | (sh > 0 ? whi << (64 - sh) : 0ull))
+                                                         : (whi >> (sh - 64));
+                        blocked = blocked || (((uint32_t)rowbits & 0x7FFu) & colmask) != 0u;
+                    }
+                    if (!blocked) break;
+                    m >>= 1;
+                }
+                if (m >= 4) {
+                    for (int j = 0; j < m; ++j) {
+                        x = x + dx;
+                        y = y + dy;
+                    }
+                    dist += m;
+                }
+            }
             const double nx = x + dx, ny = y + dy;
             const int ix = d2i(nx), iy = d2i(ny);
             for (int k = 0; k < ne; ++k)
