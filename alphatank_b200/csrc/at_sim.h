@@ -13,6 +13,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "at_types.h"
 
@@ -34,6 +35,46 @@ AT_HD int d2i(double x) {  // C (int)double: truncation toward zero, as pygame.R
 #else
     return (int)x;
 #endif
+}
+
+// --- exact multi-step accumulation --------------------------------------------------------------------------
+// The reference advances a (hypothetical) bullet by x = x + d once per sub-step.  While x stays inside one
+// binade [2^e, 2^(e+1)) every representable x is a multiple of u = 2^(e-52); writing d = Q + r with Q the
+// multiple of u that fl(x + d) - x yields, the sum x + d rounds to x + Q for EVERY x of the binade as long
+// as |r| < u/2 (no tie), so m sequential additions give exactly x + m*Q, which one fma computes without
+// rounding (the result is a multiple of u inside the binade).  jump_axis() applies that and falls back to
+// the literal loop whenever a precondition fails, so it is bit-identical to m sequential additions.
+AT_HD uint64_t d_bits(double v) {
+#ifdef __CUDA_ARCH__
+    return (uint64_t)__double_as_longlong(v);
+#else
+    uint64_t b;
+    memcpy(&b, &v, 8);
+    return b;
+#endif
+}
+AT_HD double bits_d(uint64_t b) {
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double v;
+    memcpy(&v, &b, 8);
+    return v;
+#endif
+}
+AT_HD int d_expo(double v) { return (int)((d_bits(v) >> 52) & 0x7FFu); }
+AT_HD double jump_axis(double x, double d, int m) {
+    const double x1 = x + d;
+    const double Q = x1 - x;
+    const double r = d - Q;
+    const int e = d_expo(x);
+    const double xm = fma_rn((double)m, Q, x);
+    const bool same_sign = (((d_bits(x) ^ d_bits(x1)) | (d_bits(x) ^ d_bits(xm))) >> 63) == 0;
+    const bool ok = same_sign && e > 53 && e < 0x7FF && d_expo(x1) == e && d_expo(xm) == e &&
+                    fabs(r) < bits_d((uint64_t)(e - 53) << 52);
+    if (ok) return xm;
+    for (int j = 0; j < m; ++j) x = x + d;
+    return x;
 }
 AT_HD int fdiv70(int v) { return v >= 0 ? v / 70 : -((69 - v) / 70); }
 AT_HD int imin(int a, int b) { return a < b ? a : b; }
@@ -579,46 +620,56 @@ struct Sim {
                 reachable = reachable || (gx < 340.0 && gy < 340.0);
             }
         if (!reachable) return false;
-        int bounces = 0, dist = 0;
+        // |dx|, |dy| never change (reflections only negate).  cos/sin of an integer angle are either
+        // >= 0.017 or < 2e-16 in magnitude; the latter is absorbed by every addition (x >= 2): static axis.
+        const bool stat_x = fabs(dx) < 1e-15, stat_y = fabs(dy) < 1e-15;
+        const double inv_dx = stat_x ? 0.0 : 1.0 / fabs(dx), inv_dy = stat_y ? 0.0 : 1.0 / fabs(dy);
+        int bounces = 0, dist = 0, plan_in = 0;
         for (;;) {
-            // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every time.
-            // When the 5x5 rect is provably clear of every enemy rect for the next m sub-steps (each axis moves
-            // <= 1 px per sub-step) and the bounding box of the m-step sweep touches only free cells, those m
-            // iterations can only be "advance": do the same m sequential additions (bit-identical positions)
-            // and skip the tests.  m is capped so that `dist > 300` cannot fire inside the jump.
-            int m = 300 - dist;
-            if (m >= 4) {
-                double g = 1.0e9;
-                for (int k = 0; k < ne; ++k) {
-                    double gx = fmax((double)ex[k] - (x + 5.0), x - (double)(ex[k] + 31));
-                    double gy = fmax((double)ey[k] - (y + 5.0), y - (double)(ey[k] + 25));
-                    g = fmin(g, fmax(gx, gy));
-                }
-                m = imin(imin(m, 64), g > 2.0 ? d2i(g) - 2 : 0);
-                while (m >= 4) {
-                    const double x1 = x + (double)m * dx, y1 = y + (double)m * dy;
-                    const double xlo = fmin(x, x1) - 1.0, xhi = fmax(x, x1) + 6.0;
-                    const double ylo = fmin(y, y1) - 1.0, yhi = fmax(y, y1) + 6.0;
-                    const int ca = xlo < 0.0 ? 0 : d2i(xlo) / 70, cb = imin(d2i(xhi) / 70, 10);
-                    const int ra = ylo < 0.0 ? 0 : d2i(ylo) / 70, rb = imin(d2i(yhi) / 70, 10);
-                    const uint32_t colmask = ((1u << (cb - ca + 1)) - 1u) << ca;
-                    bool blocked = false;
-                    for (int r = ra; r <= rb; ++r) {
-                        const int sh = r * 11;
-                        const uint64_t rowbits = sh < 64 ? ((wlo >> sh) | (sh > 0 ? whi << (64 - sh) : 0ull))
-                                                         : (whi >> (sh - 64));
-                        blocked = blocked || (((uint32_t)rowbits & 0x7FFu) & colmask) != 0u;
+            // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every
+            // time.  From an accepted (wall-free) position the set of cells under the 5x5 rect can only
+            // shrink until a LEADING edge crosses a cell boundary, and the rect cannot overlap an enemy rect
+            // before both axes have entered its span; both events are linear in the step count.  For
+            // m <= (first event) - 2 those iterations can only be "advance": take them in one exact jump.
+            if (plan_in == 0) {
+                int m = 0;
+                const int room = 300 - dist;  // `dist > 300` must not fire inside the jump
+                const int jx = d2i(x), jy = d2i(y);
+                if (room >= 6 && jx >= 0 && jy >= 0 && first_wall(jx, jy, 5, 5) < 0) {
+                    double lim = (double)room;
+                    if (!stat_x) {
+                        const double gap = dx > 0 ? (double)(70 * ((jx + 4) / 70 + 1) - 4) - x : x - (double)(70 * (jx / 70));
+                        const int e = d_expo(x);
+                        const double gb = dx > 0 ? bits_d((uint64_t)(e + 1) << 52) - x : x - bits_d((uint64_t)e << 52);
+                        lim = fmin(lim, fmin(gap, gb) * inv_dx);
                     }
-                    if (!blocked) break;
-                    m >>= 1;
+                    if (!stat_y) {
+                        const double gap = dy > 0 ? (double)(70 * ((jy + 4) / 70 + 1) - 4) - y : y - (double)(70 * (jy / 70));
+                        const int e = d_expo(y);
+                        const double gb = dy > 0 ? bits_d((uint64_t)(e + 1) << 52) - y : y - bits_d((uint64_t)e << 52);
+                        lim = fmin(lim, fmin(gap, gb) * inv_dy);
+                    }
+                    for (int k = 0; k < ne; ++k) {  // overlap needs x in [ex-4, ex+30) and y in [ey-4, ey+24)
+                        const double lx = (double)(ex[k] - 4), hx = (double)(ex[k] + 30);
+                        const double ly = (double)(ey[k] - 4), hy = (double)(ey[k] + 24);
+                        const double sx = x < lx ? ((dx > 0 && !stat_x) ? (lx - x) * inv_dx : 1.0e9)
+                                                 : (x >= hx ? ((dx < 0 && !stat_x) ? (x - hx) * inv_dx : 1.0e9) : 0.0);
+                        const double sy = y < ly ? ((dy > 0 && !stat_y) ? (ly - y) * inv_dy : 1.0e9)
+                                                 : (y >= hy ? ((dy < 0 && !stat_y) ? (y - hy) * inv_dy : 1.0e9) : 0.0);
+                        lim = fmin(lim, fmax(sx, sy));
+                    }
+                    m = imax(d2i(lim) - 2, 0);
                 }
                 if (m >= 4) {
-                    for (int j = 0; j < m; ++j) {
-                        x = x + dx;
-                        y = y + dy;
-                    }
+                    if (!stat_x) x = jump_axis(x, dx, m);
+                    if (!stat_y) y = jump_axis(y, dy, m);
                     dist += m;
+                    plan_in = 3;  // the event is 2..3 sub-steps ahead: walk through it before planning again
+                } else {
+                    plan_in = m + 3;
                 }
+            } else {
+                --plan_in;
             }
             const double nx = x + dx, ny = y + dy;
             const int ix = d2i(nx), iy = d2i(ny);
@@ -630,6 +681,7 @@ struct Sim {
                 if (bxh) dx = -dx;
                 if (byh) dy = -dy;
                 ++bounces;
+                plan_in = 0;
             } else {
                 x = nx;
                 y = ny;

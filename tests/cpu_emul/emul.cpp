@@ -157,6 +157,7 @@ int em_bfs(const uint8_t *maze121, int sr, int sc, int gr, int gc, int *next_r, 
         if (maze121[i]) { if (i < 64) lo |= 1ull << i; else hi |= 1ull << (i - 64); }
     return bfs_first_step(lo, hi, sr, sc, gr, gc, next_r, next_c);
 }
+double em_jump_axis(double x, double d, int m) { return jump_axis(x, d, m); }
 void em_generate_maze(uint64_t seed, int64_t env_id, uint32_t *ctr, uint8_t *maze121) {
     uint64_t lo, hi;
     generate_maze_mask(seed, env_id, *ctr, lo, hi);

@@ -41,6 +41,8 @@ def lib():
         L.em_get_info.argtypes = [vp, vp, vp, vp, vp]
         L.em_bfs.argtypes = [vp, i32, i32, i32, i32, vp, vp]
         L.em_generate_maze.argtypes = [C.c_uint64, i64, vp, vp]
+        L.em_jump_axis.restype = C.c_double
+        L.em_jump_axis.argtypes = [C.c_double, C.c_double, i32]
         L.em_last_error.restype = C.c_char_p
         _lib = L
     return _lib

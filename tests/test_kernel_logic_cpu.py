@@ -130,3 +130,31 @@ def test_state_roundtrip_through_packed_layout():
         oa, ra, da = a.step(acts)
         ob, rb, db = b.step(acts)
         assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db)
+
+
+def test_exact_multi_step_jump_equals_sequential_additions():
+    """jump_axis (one fma inside a binade) must be bit-identical to m sequential `x = x + d` additions - the
+    line-of-sight skip-ahead relies on it.  Covers all LUT directions, binade crossings (64, 128, 256, 512),
+    tiny / absorbed steps and constructed rounding ties."""
+    import math
+    L = emul_env.lib()
+    rng = np.random.RandomState(0)
+    dirs = [s * f(math.radians(a)) for a in range(361) for f in (math.cos, math.sin) for s in (1.0, -1.0)]
+    cases = []
+    for _ in range(6000):
+        cases.append((rng.uniform(60.0, 710.0), dirs[rng.randint(len(dirs))], int(rng.randint(1, 301))))
+    for b in (64.0, 128.0, 256.0, 512.0):                      # straddle every binade boundary of the arena
+        for _ in range(300):
+            cases.append((b + rng.uniform(-40, 40), dirs[rng.randint(len(dirs))], int(rng.randint(4, 120))))
+    for e in (6, 7, 8, 9):                                     # exact ties: d = q*u + u/2
+        u = 2.0 ** (e - 52)
+        for q in (3, 1000, 2 ** 30 + 1):
+            for sgn in (1.0, -1.0):
+                cases.append((2.0 ** e * 1.37, sgn * (q * u + u / 2), 50))
+                cases.append((2.0 ** e * 1.37 + u, sgn * (q * u + u / 2), 50))
+    for x, d, m in cases:
+        want = x
+        for _ in range(m):
+            want = want + d
+        got = L.em_jump_axis(x, d, m)
+        assert got == want, (x, d, m, got, want)
