@@ -33,7 +33,7 @@ namespace {
 struct SmemLayout {
     int n, dpad;
     size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_ewlo, off_ewhi, off_tpack, off_thits,
-        off_bpack, off_tlive, off_tshot, off_ecnt, off_ezones, off_stage, total;
+        off_bpack, off_tlive, off_tshot, off_ecnt, off_ezones, off_trec, off_stage, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int n, int obs_dim) {
     SmemLayout L;
@@ -55,6 +55,8 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int obs_dim) {
     L.off_tshot = o; o += (size_t)n * BS * 4;
     L.off_ecnt = o; o += BS * 4;
     L.off_ezones = o; o += BS * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.off_trec = o; o += (size_t)(BS / 32) * TREC_FLOATS * 4;
     o = (o + 15) & ~(size_t)15;
     L.off_stage = o; o += (size_t)(BS / 32) * 2 * L.dpad * 4;
     L.total = o;
@@ -129,10 +131,11 @@ __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c,
     const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
     if (emit_mask == 0u) return;
     float *stage = (float *)(smem + L.off_stage) + (size_t)warp * 2 * L.dpad;
+    float *trec = (float *)(smem + L.off_trec) + (size_t)warp * TREC_FLOATS;
     const int D = c.obs_dim;
     if (c.map != 2) {  // fixed map: static columns are staged once
         for (int b = 0; b < 2; ++b) {
-            RowCtx rc{c, st, bm, stage + b * L.dpad, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
+            RowCtx rc{c, st, bm, stage + b * L.dpad, trec, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
             row_static(rc, lane);
         }
     }
@@ -142,18 +145,22 @@ __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c,
         if (!((emit_mask >> le) & 1u)) continue;
         const int q = warp * 32 + le;
         const int64_t ee = (int64_t)blockIdx.x * BS + q;
+        RowCtx rc{c, st, bm, nullptr, trec, q, ee, ecnt[q], ezones[q], ewlo[q], ewhi[q]};
+        __syncwarp();  // the previous env's rows have consumed trec
+        env_records(rc, lane);
+        const LaneBullet lb = row_preload_bullet(rc, lane);
         for (int r = 0; r < c.rows; ++r) {
             const int t = c.team_layout ? c.agent_tank[r] : r;
             float *row = stage + buf * L.dpad;
             if (use_bulk) {  // the copy issued from this buffer two rows ago must have drained
                 if (lane == 0) bulk_wait_read<1>();
-                __syncwarp();
             }
-            RowCtx rc{c, st, bm, row, q, ee, ecnt[q], ezones[q], ewlo[q], ewhi[q]};
+            __syncwarp();
+            rc.row = row;
             if (c.map == 2) row_static(rc, lane);
             row_clear_bullets(rc, lane);
             __syncwarp();
-            row_bullets(rc, lane, t);
+            row_bullets(rc, lane, t, lb);
             row_tanks(rc, lane, t);
             row_misc(rc, lane, t);
             float *dst = obs + (ee * c.rows + r) * (int64_t)D;
@@ -164,7 +171,6 @@ __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c,
             } else {
                 __syncwarp();
                 for (int j = lane; j < D; j += 32) dst[j] = row[j];
-                __syncwarp();
             }
             buf ^= 1;
         }
@@ -303,6 +309,11 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     if (prop.major < 10)
         return fail(AT_ERR_NOGPU, "at_create: device is not sm_100 class; this library ships sm_100a code only");
 
+    {
+        const M128 nm = near_wall_mask(k.wall_lo, k.wall_hi);
+        k.near_lo = nm.lo;
+        k.near_hi = nm.hi;
+    }
     at_env *env = new at_env();
     env->user_cfg = *cfg;
     env->k = k;
@@ -327,6 +338,12 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaMemcpy(b + L.o_trig, env->luts.trig.data(), 722 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(b + L.o_corn, env->luts.corn.data(), 361 * 4 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(b + L.o_pend, env->luts.pend.data(), PEND_LUT * 8, cudaMemcpyHostToDevice);
+    if (k.map != AT_MAP_MAZE) {  // fixed map: path-finding becomes one table lookup
+        std::vector<uint16_t> tab((size_t)CELLS * CELLS);
+        fill_bfs_table(k.wall_lo, k.wall_hi, tab.data());
+        cudaMemcpy(b + L.o_bfs, tab.data(), tab.size() * 2, cudaMemcpyHostToDevice);
+        env->st.bfs_tab = (const uint16_t *)(b + L.o_bfs);
+    }
 
     env->smem_bytes = smem_layout(k.n_tanks, k.obs_dim).total;
     cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);

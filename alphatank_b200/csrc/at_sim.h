@@ -249,6 +249,30 @@ AT_HDN void generate_maze_mask(uint64_t seed, int64_t env_id, uint32_t &ctr, uin
     wall_hi = wall.hi;
 }
 
+// cells that are a wall or have one in their 8-neighbourhood: a tank whose centre lies in any other cell cannot
+// touch a wall (its OBB stays within 19.3 px of the centre, the nearest wall is >= 70 px from the cell)
+AT_HD M128 near_wall_mask(uint64_t wall_lo, uint64_t wall_hi) {
+    const M128 all = {~0ull, (1ull << (CELLS - 64)) - 1};
+    const M128 w = {wall_lo, wall_hi};
+    const M128 notc0 = m_andn(all, col_mask(0)), notc10 = m_andn(all, col_mask(10));
+    M128 h = m_or(w, m_or(m_shr(m_and(w, notc0), 1), m_shl(m_and(w, notc10), 1)));
+    M128 v = m_or(h, m_or(m_shr(h, 11), m_shl(h, 11)));
+    v.hi &= (1ull << (CELLS - 64)) - 1;
+    return v;
+}
+// all-pairs table of bfs_first_step for a fixed map (built once on the host): len | dir << 8
+AT_HD void fill_bfs_table(uint64_t wall_lo, uint64_t wall_hi, uint16_t *tab) {
+    for (int s = 0; s < CELLS; ++s)
+        for (int g = 0; g < CELLS; ++g) {
+            int nr, nc;
+            const int sr = s / 11, sc = s % 11;
+            const int len = bfs_first_step(wall_lo, wall_hi, sr, sc, g / 11, g % 11, &nr, &nc);
+            int dir = 0;
+            if (len > 1) dir = nr < sr ? 0 : (nr > sr ? 1 : (nc < sc ? 2 : 3));
+            tab[s * CELLS + g] = (uint16_t)(len | (dir << 8));
+        }
+}
+
 AT_HD int popc64(uint64_t v) {
 #ifdef __CUDA_ARCH__
     return __popcll(v);
@@ -278,11 +302,11 @@ struct Sim {
     int64_t e;  // env index into the SoA arrays
     int tid;    // slot in the block working set
     uint32_t cnt, rng, tick, tstep, epstep, zones;
-    uint64_t wlo, whi;
+    uint64_t wlo, whi, nlo, nhi;
 
     AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0) {}
+          whi(0), nlo(0), nhi(0) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
     AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
@@ -317,6 +341,7 @@ struct Sim {
     }
 
     AT_HD bool wall_at(int idx) const { return ((idx < 64 ? wlo >> idx : whi >> (idx - 64)) & 1ull) != 0; }
+    AT_HD bool near_at(int idx) const { return ((idx < 64 ? nlo >> idx : nhi >> (idx - 64)) & 1ull) != 0; }
 
     // first wall (row-major = reference list order, gaming_env.py:610-615) that a w x h pygame.Rect at
     // integer (ix, iy) collides with; -1 if none.  Replaces `for wall in walls: colliderect` scans.
@@ -509,6 +534,10 @@ struct Sim {
     // obb_vs_aabb over the wall list (util.py:15-48) -> exact 4-axis SAT against the few wall cells whose
     // AABB can reach the OBB (others are separated on the x or y axis by construction).
     AT_HD bool obb_hits_walls(double nx, double ny, int a) const {
+        {   // quick reject: centre in a cell with no wall in its 3x3 neighbourhood
+            const int cx = d2i(nx), cy = d2i(ny);
+            if (cx >= 0 && cy >= 0 && cx < 770 && cy < 770 && !near_at((cy / 70) * 11 + cx / 70)) return false;
+        }
         const double *co = st.corn + 4 * a;
         const double o0x = co[0], o0y = co[1], o1x = co[2], o1y = co[3];
         double kx[4] = {nx + o0x, nx + o1x, nx - o0x, nx - o1x};
@@ -609,11 +638,13 @@ struct Sim {
         const double cv = cosr(a), sv = sinr(a);
         double x = TX(me) + 10 * cv, y = TY(me) - 10 * sv, dx = cv, dy = -sv;
         int ex[MAX_TANKS], ey[MAX_TANKS], ne = 0;
+        int bx0 = 1 << 20, bx1 = -(1 << 20), by0 = 1 << 20, by1 = -(1 << 20);  // union of the enemy rect origins
         bool reachable = false;
         for (int i = 0; i < c.n_tanks; ++i)
             if (c.team[i] != c.team[me] && t_alive(i)) {
                 ex[ne] = d2i(TX(i) - 15);
                 ey[ne] = d2i(TY(i) - 12);
+                bx0 = imin(bx0, ex[ne]); bx1 = imax(bx1, ex[ne]); by0 = imin(by0, ey[ne]); by1 = imax(by1, ey[ne]);
                 ++ne;
                 // a hit needs the 5x5 rect within <= 301 advancing sub-steps of the muzzle: exact cull
                 double gx = fabs(TX(i) - x), gy = fabs(TY(i) - y);
@@ -625,30 +656,21 @@ struct Sim {
         const bool stat_x = fabs(dx) < 1e-15, stat_y = fabs(dy) < 1e-15;
         const double inv_dx = stat_x ? 0.0 : 1.0 / fabs(dx), inv_dy = stat_y ? 0.0 : 1.0 / fabs(dy);
         int bounces = 0, dist = 0, plan_in = 0;
+        // the muzzle position itself is never tested by the reference; the skip-ahead needs a wall-free rect
+        bool accepted = first_wall(d2i(x), d2i(y), 5, 5) < 0;
         for (;;) {
             // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every
-            // time.  From an accepted (wall-free) position the set of cells under the 5x5 rect can only
-            // shrink until a LEADING edge crosses a cell boundary, and the rect cannot overlap an enemy rect
-            // before both axes have entered its span; both events are linear in the step count.  For
-            // m <= (first event) - 2 those iterations can only be "advance": take them in one exact jump.
+            // time.  From an accepted (wall-free) position the 5x5 rect can only START overlapping a wall
+            // when one of its LEADING edges crosses a cell boundary (trailing edges only uncover cells), and
+            // it cannot overlap an enemy rect before both axes have entered that rect's span.  Both kinds of
+            // event are linear in the step count, so a DDA over the leading-edge crossings finds the first
+            // crossing that uncovers a wall cell; all sub-steps more than 2 before it (and before the tank
+            // bound, the next binade boundary and `dist > 300`) can only be "advance": one exact jump.
             if (plan_in == 0) {
                 int m = 0;
-                const int room = 300 - dist;  // `dist > 300` must not fire inside the jump
-                const int jx = d2i(x), jy = d2i(y);
-                if (room >= 6 && jx >= 0 && jy >= 0 && first_wall(jx, jy, 5, 5) < 0) {
+                const int room = 300 - dist;
+                if (room >= 6 && accepted) {
                     double lim = (double)room;
-                    if (!stat_x) {
-                        const double gap = dx > 0 ? (double)(70 * ((jx + 4) / 70 + 1) - 4) - x : x - (double)(70 * (jx / 70));
-                        const int e = d_expo(x);
-                        const double gb = dx > 0 ? bits_d((uint64_t)(e + 1) << 52) - x : x - bits_d((uint64_t)e << 52);
-                        lim = fmin(lim, fmin(gap, gb) * inv_dx);
-                    }
-                    if (!stat_y) {
-                        const double gap = dy > 0 ? (double)(70 * ((jy + 4) / 70 + 1) - 4) - y : y - (double)(70 * (jy / 70));
-                        const int e = d_expo(y);
-                        const double gb = dy > 0 ? bits_d((uint64_t)(e + 1) << 52) - y : y - bits_d((uint64_t)e << 52);
-                        lim = fmin(lim, fmin(gap, gb) * inv_dy);
-                    }
                     for (int k = 0; k < ne; ++k) {  // overlap needs x in [ex-4, ex+30) and y in [ey-4, ey+24)
                         const double lx = (double)(ex[k] - 4), hx = (double)(ex[k] + 30);
                         const double ly = (double)(ey[k] - 4), hy = (double)(ey[k] + 24);
@@ -657,6 +679,43 @@ struct Sim {
                         const double sy = y < ly ? ((dy > 0 && !stat_y) ? (ly - y) * inv_dy : 1.0e9)
                                                  : (y >= hy ? ((dy < 0 && !stat_y) ? (y - hy) * inv_dy : 1.0e9) : 0.0);
                         lim = fmin(lim, fmax(sx, sy));
+                    }
+                    const int jx = d2i(x), jy = d2i(y);
+                    double tx = 1.0e9, ty = 1.0e9;  // step count of the next leading-edge crossing per axis
+                    int lcx = 0, lcy = 0;           // leading column / row
+                    const int sgx = dx > 0 ? 1 : -1, sgy = dy > 0 ? 1 : -1;
+                    if (!stat_x) {
+                        lcx = dx > 0 ? (jx + 4) / 70 : jx / 70;
+                        tx = (dx > 0 ? (double)(70 * (lcx + 1) - 4) - x : x - (double)(70 * lcx)) * inv_dx;
+                        const int e = d_expo(x);  // jumps stay inside one binade (jump_axis)
+                        lim = fmin(lim, (dx > 0 ? bits_d((uint64_t)(e + 1) << 52) - x : x - bits_d((uint64_t)e << 52)) * inv_dx);
+                    }
+                    if (!stat_y) {
+                        lcy = dy > 0 ? (jy + 4) / 70 : jy / 70;
+                        ty = (dy > 0 ? (double)(70 * (lcy + 1) - 4) - y : y - (double)(70 * lcy)) * inv_dy;
+                        const int e = d_expo(y);
+                        lim = fmin(lim, (dy > 0 ? bits_d((uint64_t)(e + 1) << 52) - y : y - bits_d((uint64_t)e << 52)) * inv_dy);
+                    }
+                    const double step_x = 70.0 * inv_dx, step_y = 70.0 * inv_dy;
+                    for (;;) {
+                        const bool xev = tx <= ty;
+                        const double t = xev ? tx : ty;
+                        if (t >= lim) break;
+                        bool hit = false;
+                        if (xev) {  // column lcx + sgx becomes covered; rows around the predicted y (+-3 px slack)
+                            lcx += sgx;
+                            const double yt = y + t * dy;
+                            const int ra = imax(d2i(yt - 3.0) / 70, 0), rb = imin(d2i(yt + 8.0) / 70, 10);
+                            for (int r = ra; r <= rb; ++r) hit = hit || lcx < 0 || lcx > 10 || wall_at(r * 11 + lcx);
+                            tx += step_x;
+                        } else {
+                            lcy += sgy;
+                            const double xt = x + t * dx;
+                            const int ca = imax(d2i(xt - 3.0) / 70, 0), cb = imin(d2i(xt + 8.0) / 70, 10);
+                            for (int cc = ca; cc <= cb; ++cc) hit = hit || lcy < 0 || lcy > 10 || wall_at(lcy * 11 + cc);
+                            ty += step_y;
+                        }
+                        if (hit) { lim = t; break; }
                     }
                     m = imax(d2i(lim) - 2, 0);
                 }
@@ -673,8 +732,9 @@ struct Sim {
             }
             const double nx = x + dx, ny = y + dy;
             const int ix = d2i(nx), iy = d2i(ny);
-            for (int k = 0; k < ne; ++k)
-                if (ix < ex[k] + 30 && iy < ey[k] + 24 && ix + 5 > ex[k] && iy + 5 > ey[k]) return true;
+            if (ix < bx1 + 30 && iy < by1 + 24 && ix + 5 > bx0 && iy + 5 > by0)  // inside the union box: test each
+                for (int k = 0; k < ne; ++k)
+                    if (ix < ex[k] + 30 && iy < ey[k] + 24 && ix + 5 > ex[k] && iy + 5 > ey[k]) return true;
             int cell = first_wall(ix, iy, 5, 5);
             if (cell >= 0) {
                 bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
@@ -686,6 +746,7 @@ struct Sim {
                 x = nx;
                 y = ny;
                 ++dist;
+                accepted = true;
             }
             if (bounces > 6 || dist > 300) return false;
         }
@@ -718,9 +779,17 @@ struct Sim {
             target = nearest_opponent(me, nullptr);
         }
         if (target >= 0) {
-            int nr, nc;
-            int len = bfs_first_step(wlo, whi, d2i(TY(me)) / 70, d2i(TX(me)) / 70, d2i(TY(target)) / 70,
-                                     d2i(TX(target)) / 70, &nr, &nc);
+            int nr, nc, len;
+            const int sr = d2i(TY(me)) / 70, sc = d2i(TX(me)) / 70, gr = d2i(TY(target)) / 70, gc = d2i(TX(target)) / 70;
+            if (st.bfs_tab != nullptr && (unsigned)sr < 11u && (unsigned)sc < 11u && (unsigned)gr < 11u && (unsigned)gc < 11u) {
+                const uint32_t ent = st.bfs_tab[(sr * 11 + sc) * CELLS + gr * 11 + gc];  // fixed map: all-pairs table
+                const int dir = (int)(ent >> 8);
+                len = (int)(ent & 255u);
+                nr = sr + (dir == 0 ? -1 : (dir == 1 ? 1 : 0));
+                nc = sc + (dir == 2 ? -1 : (dir == 3 ? 1 : 0));
+            } else {
+                len = bfs_first_step(wlo, whi, sr, sc, gr, gc, &nr, &nc);
+            }
             has_next = len > 1;
             if (has_next) { next_r = nr; next_c = nc; }
         }
@@ -921,7 +990,7 @@ struct Sim {
 
     // ---------------------------------------------------------------- reset (gaming_env.py:48-66, 509-520)
     AT_HDN void env_reset() {
-        if (c.map == 2) generate_maze_mask(c.seed, c.env_id_base + e, rng, wlo, whi);
+        if (c.map == 2) { generate_maze_mask(c.seed, c.env_id_base + e, rng, wlo, whi); set_near(); }
         const M128 all = {~0ull, (1ull << (CELLS - 64)) - 1};
         const M128 freec = m_andn(all, M128{wlo, whi});
         const int n_empty = CELLS - c.n_walls;
@@ -1030,14 +1099,15 @@ struct Sim {
     AT_HD void load() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
         zones = st.zones[e];
-        if (c.map == 2) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; }
-        else { wlo = c.wall_lo; whi = c.wall_hi; }
+        if (c.map == 2) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; set_near(); }
+        else { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
         for (int i = 0; i < c.n_tanks; ++i) {
             TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
             TPACK(i) = st.tpack[G(i)]; THITS(i) = st.thits[G(i)]; TSHOT(i) = st.tshot[G(i)];
             if (c.ctrl[i] == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
         }
     }
+    AT_HD void set_near() { M128 nm = near_wall_mask(wlo, whi); nlo = nm.lo; nhi = nm.hi; }
     AT_HD void load_scalars_only() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
         zones = st.zones[e];
@@ -1059,16 +1129,24 @@ struct Sim {
 // ------------------------------------------------------------------ observation rows
 // gym_env.py:105-183 (1v1 layout) / gym_env_multi.py:225-304 (team layout).  A row is assembled by the 32
 // lanes of a warp in a shared-memory staging buffer and leaves as one contiguous block.  `q` is the env's
-// slot in the block working set, `e` its SoA index, `t` the tank the row belongs to.
+// slot in the block working set, `e` its SoA index, `t` the tank the row belongs to.  Everything that does
+// not depend on the viewer (each tank's position / corners / velocity / flags, the zone corners, the env's
+// bullets) is produced once per env: `trec` is a per-warp scratch of TREC_FLOATS floats.
+constexpr int TREC_STRIDE = 16, TREC_ZONES = MAX_TANKS * TREC_STRIDE, TREC_FLOATS = TREC_ZONES + 8;
 struct RowCtx {
     const KCfg &c;
     const DevState &st;
     const BlockMem &bm;
     float *row;
+    float *trec;
     int q;
     int64_t e;
     uint32_t cnt, zones;
     uint64_t wlo, whi;
+};
+struct LaneBullet {
+    double x, y;
+    uint64_t m;
 };
 
 AT_HD void row_static(const RowCtx &r, int lane) {  // walls (row-major) + maze: change only with the map
@@ -1086,34 +1164,9 @@ AT_HD void row_static(const RowCtx &r, int lane) {  // walls (row-major) + maze:
         }
     }
 }
-AT_HD void row_clear_bullets(const RowCtx &r, int lane) {
-    for (int j = r.c.off_ob + lane; j < r.c.off_et; j += 32) r.row[j] = 0.0f;
-}
-AT_HD void row_bullets(const RowCtx &r, int lane, int t) {
-    const KCfg &c = r.c;
-    const double ax = r.bm.tx[t * BS + r.q], ay = r.bm.ty[t * BS + r.q];
-    for (uint32_t s = lane; s < r.cnt; s += 32) {
-        const int64_t g = (int64_t)s * r.st.N + r.e;
-        const uint64_t m = r.st.bmeta[g];
-        const double x = r.st.bx[g], y = r.st.by[g];
-        const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u), rank = (int)((m >> BM_RANK) & 7u);
-        const double cv = r.bm.trig[2 * ang], sv = r.bm.trig[2 * ang + 1];
-        const double dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv, dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
-        if (owner == t) {
-            float *p = r.row + c.off_ob + 4 * rank;
-            p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
-        } else {
-            const int oi = owner < t ? owner : owner - 1;
-            const int per = c.team_layout ? 8 : 7;
-            float *p = r.row + c.off_eb + oi * c.eb_stride + per * rank;
-            const double rx = x - ax, ry = y - ay;
-            p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
-            p[4] = (float)rx; p[5] = (float)ry; p[6] = (float)sqrt(rx * rx + ry * ry);
-            if (c.team_layout) p[7] = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
-        }
-    }
-}
-AT_HD void row_tanks(const RowCtx &r, int lane, int t) {
+// once per env: lane i < n writes tank i's viewer-independent record (x, y, 4 corners, velocity, hittingWall,
+// alive); lanes < n_zone_vals write the zone corner coordinates (buff first, gym_env.py:168-173)
+AT_HD void env_records(const RowCtx &r, int lane) {
     const KCfg &c = r.c;
     if (lane < c.n_tanks) {
         const int i = lane;
@@ -1123,38 +1176,101 @@ AT_HD void row_tanks(const RowCtx &r, int lane, int t) {
         const uint32_t sc = (pk >> 9) & 3u;
         const double sp = sc == 0 ? 0.0 : (sc == 1 ? 10.0 : (sc == 2 ? -10.0 : 1.0));
         const double *co = r.st.corn + 4 * a;
-        float *p;
+        float *p = r.trec + i * TREC_STRIDE;
+        p[0] = (float)x; p[1] = (float)y;
+        p[2] = (float)(x + co[0]); p[3] = (float)(y + co[1]); p[4] = (float)(x + co[2]); p[5] = (float)(y + co[3]);
+        p[6] = (float)(x - co[0]); p[7] = (float)(y - co[1]); p[8] = (float)(x - co[2]); p[9] = (float)(y - co[3]);
+        p[10] = (float)(sp * r.bm.trig[2 * a]);
+        p[11] = (float)(sp * r.bm.trig[2 * a + 1]);
+        p[12] = (pk & TP_HW) ? 1.0f : 0.0f;
+        p[13] = (pk & TP_ALIVE) ? 1.0f : 0.0f;
+    }
+    if (lane >= 16 && lane - 16 < c.n_zone_vals) {
+        const int v = lane - 16;
+        int k = v >> 1;
+        if (!c.buff_on) k += 2;
+        const int cell = (int)((r.zones >> (7 * k)) & 127u);
+        r.trec[TREC_ZONES + v] = (float)(((v & 1) ? cell / 11 : cell % 11) * 70);
+    }
+}
+AT_HD LaneBullet row_preload_bullet(const RowCtx &r, int lane) {
+    LaneBullet lb = {0.0, 0.0, 0ull};
+    if ((uint32_t)lane < r.cnt) {
+        const int64_t g = (int64_t)lane * r.st.N + r.e;
+        lb.m = r.st.bmeta[g];
+        lb.x = r.st.bx[g];
+        lb.y = r.st.by[g];
+    }
+    return lb;
+}
+AT_HD void row_clear_bullets(const RowCtx &r, int lane) {  // 16-byte stores; the spill-over into the
+    const int j0 = r.c.off_ob & ~3, j1 = (r.c.off_et + 3) & ~3;  // neighbouring tank fields is rewritten after
+    for (int j = j0 + 4 * lane; j < j1; j += 128) {
+        float *p = r.row + j;
+#ifdef __CUDA_ARCH__
+        *reinterpret_cast<float4 *>(p) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+#else
+        p[0] = 0.0f; p[1] = 0.0f; p[2] = 0.0f; p[3] = 0.0f;
+#endif
+    }
+}
+AT_HD void row_put_bullet(const RowCtx &r, int t, double ax, double ay, double x, double y, uint64_t m) {
+    const KCfg &c = r.c;
+    const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u), rank = (int)((m >> BM_RANK) & 7u);
+    const double cv = r.bm.trig[2 * ang], sv = r.bm.trig[2 * ang + 1];
+    const double dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv, dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
+    if (owner == t) {
+        float *p = r.row + c.off_ob + 4 * rank;
+        p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
+    } else {
+        const int oi = owner < t ? owner : owner - 1;
+        const int per = c.team_layout ? 8 : 7;
+        float *p = r.row + c.off_eb + oi * c.eb_stride + per * rank;
+        const double rx = x - ax, ry = y - ay;
+        p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
+        p[4] = (float)rx; p[5] = (float)ry; p[6] = (float)sqrt(rx * rx + ry * ry);
+        if (c.team_layout) p[7] = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
+    }
+}
+AT_HD void row_bullets(const RowCtx &r, int lane, int t, const LaneBullet &lb) {
+    const double ax = r.bm.tx[t * BS + r.q], ay = r.bm.ty[t * BS + r.q];
+    if ((uint32_t)lane < r.cnt) row_put_bullet(r, t, ax, ay, lb.x, lb.y, lb.m);
+    for (uint32_t s = lane + 32; s < r.cnt; s += 32) {  // more than 32 live bullets only with >= 6 tanks
+        const int64_t g = (int64_t)s * r.st.N + r.e;
+        row_put_bullet(r, t, ax, ay, r.st.bx[g], r.st.by[g], r.st.bmeta[g]);
+    }
+}
+AT_HD void row_tanks(const RowCtx &r, int lane, int t) {
+    const KCfg &c = r.c;
+    const int total = c.n_tanks * 14;
+    for (int j = lane; j < total; j += 32) {  // copy the per-env records into this viewer's layout
+        const int i = j / 14, f = j - 14 * i;
+        const float v = r.trec[i * TREC_STRIDE + f];
+        int dst;
         if (i == t) {
-            p = r.row;
-            p[0] = (float)x; p[1] = (float)y;
-            p += 2;
+            dst = f < 13 ? f : c.self_len - 1;
         } else {
-            const int oi = i < t ? i : i - 1;
-            p = r.row + c.off_et + oi * c.et_len;
-            const double ax = r.bm.tx[t * BS + r.q], ay = r.bm.ty[t * BS + r.q];
-            const double rx = x - ax, ry = y - ay;
-            p[0] = (float)x; p[1] = (float)y; p[2] = (float)rx; p[3] = (float)ry;
-            p[4] = (float)sqrt(rx * rx + ry * ry);
-            p += 5;
+            const int base = c.off_et + (i < t ? i : i - 1) * c.et_len;
+            dst = base + (f < 2 ? f : (f < 13 ? f + 3 : c.et_len - 1));
         }
-        p[0] = (float)(x + co[0]); p[1] = (float)(y + co[1]); p[2] = (float)(x + co[2]); p[3] = (float)(y + co[3]);
-        p[4] = (float)(x - co[0]); p[5] = (float)(y - co[1]); p[6] = (float)(x - co[2]); p[7] = (float)(y - co[3]);
-        p[8] = (float)(sp * r.bm.trig[2 * a]);
-        p[9] = (float)(sp * r.bm.trig[2 * a + 1]);
-        p[10] = (pk & TP_HW) ? 1.0f : 0.0f;
-        p += 11;
-        if (c.team_layout) *p++ = (i == t) ? 1.0f : (c.team[i] == c.team[t] ? 1.0f : 0.0f);
-        *p = (pk & TP_ALIVE) ? 1.0f : 0.0f;
+        r.row[dst] = v;
+    }
+    if (lane < c.n_tanks) {  // viewer-dependent fields of tank `lane`
+        const int i = lane;
+        if (i == t) {
+            if (c.team_layout) r.row[13] = 1.0f;
+        } else {
+            float *p = r.row + c.off_et + (i < t ? i : i - 1) * c.et_len;
+            const double rx = r.bm.tx[i * BS + r.q] - r.bm.tx[t * BS + r.q];
+            const double ry = r.bm.ty[i * BS + r.q] - r.bm.ty[t * BS + r.q];
+            p[2] = (float)rx; p[3] = (float)ry; p[4] = (float)sqrt(rx * rx + ry * ry);
+            if (c.team_layout) p[16] = c.team[i] == c.team[t] ? 1.0f : 0.0f;
+        }
     }
 }
 AT_HD void row_misc(const RowCtx &r, int lane, int t) {
     const KCfg &c = r.c;
-    if (lane < c.n_zone_vals) {  // zone corner coordinates, buff first (gym_env.py:168-173)
-        int k = lane >> 1;
-        if (!c.buff_on) k += 2;
-        int cell = (int)((r.zones >> (7 * k)) & 127u);
-        r.row[c.off_zones + lane] = (float)(((lane & 1) ? cell / 11 : cell % 11) * 70);
-    }
+    if (lane < c.n_zone_vals) r.row[c.off_zones + lane] = r.trec[TREC_ZONES + lane];
     if (lane == 30) r.row[c.off_flags] = (r.bm.tpack[t * BS + r.q] & TP_INBUFF) ? 1.0f : 0.0f;
     if (lane == 31) r.row[c.off_flags + 1] = (r.bm.tpack[t * BS + r.q] & TP_INDEBUFF) ? 1.0f : 0.0f;
 }

@@ -42,6 +42,7 @@ struct KCfg {
     uint64_t seed;
     int64_t env_id_base;
     uint64_t wall_lo, wall_hi;  // static map wall mask (bit r*11+c); per-env arrays are used when map == MAZE
+    uint64_t near_lo, near_hi;  // static map: cells that are a wall or touch one (8-neighbourhood)
 };
 
 struct DevState {
@@ -59,6 +60,7 @@ struct DevState {
     const double *trig;            // [361][2] cos, sin of math.radians(a)
     const double *corn;            // [361][4] pygame-rotated corner offsets (c0x, c0y, c1x, c1y)
     const double *pend;            // [PEND_LUT] k-fold accumulation of BULLET_AWAY_PENALTY
+    const uint16_t *bfs_tab;       // [121*121] all-pairs bfs_first_step of a FIXED map: len | dir << 8 (null for mazes)
 };
 
 // per-block working set of the tanks / bots (shared memory on the GPU)

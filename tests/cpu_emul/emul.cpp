@@ -62,19 +62,23 @@ static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t
             env->ecnt[tid] = s.cnt; env->ezones[tid] = s.zones; env->ewlo[tid] = s.wlo; env->ewhi[tid] = s.whi;
         }
         float *row = env->stage.data();  // phase B
+        float trec[TREC_FLOATS];
         if (c.map != 2) {
-            RowCtx rc{c, st, env->bm, row, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
+            RowCtx rc{c, st, env->bm, row, trec, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
             for (int lane = 0; lane < 32; ++lane) row_static(rc, lane);
         }
         for (int q = 0; q < BS; ++q) {
             if (!emit[q]) continue;
             const int64_t ee = b0 + q;
+            RowCtx rc{c, st, env->bm, row, trec, q, ee, env->ecnt[q], env->ezones[q], env->ewlo[q], env->ewhi[q]};
+            LaneBullet lb[32];
+            for (int lane = 0; lane < 32; ++lane) env_records(rc, lane);
+            for (int lane = 0; lane < 32; ++lane) lb[lane] = row_preload_bullet(rc, lane);
             for (int r = 0; r < c.rows; ++r) {
                 const int t = c.team_layout ? c.agent_tank[r] : r;
-                RowCtx rc{c, st, env->bm, row, q, ee, env->ecnt[q], env->ezones[q], env->ewlo[q], env->ewhi[q]};
                 if (c.map == 2) for (int lane = 0; lane < 32; ++lane) row_static(rc, lane);
                 for (int lane = 0; lane < 32; ++lane) row_clear_bullets(rc, lane);
-                for (int lane = 0; lane < 32; ++lane) row_bullets(rc, lane, t);
+                for (int lane = 0; lane < 32; ++lane) row_bullets(rc, lane, t, lb[lane]);
                 for (int lane = 0; lane < 32; ++lane) row_tanks(rc, lane, t);
                 for (int lane = 0; lane < 32; ++lane) row_misc(rc, lane, t);
                 memcpy(obs + (ee * c.rows + r) * (int64_t)D, row, sizeof(float) * D);
@@ -91,6 +95,11 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     std::string msg = build_kcfg(cfg, seed, env_id_base, env->k);
     if (!msg.empty()) { g_err = msg; delete env; return AT_ERR_ARG; }
     env->n_envs = n_envs;
+    {
+        const M128 nm = near_wall_mask(env->k.wall_lo, env->k.wall_hi);
+        env->k.near_lo = nm.lo;
+        env->k.near_hi = nm.hi;
+    }
     build_luts(env->luts);
     const ArenaLayout L = arena_layout(env->k, n_envs);
     env->arena.assign(L.bytes, 0);
@@ -98,6 +107,10 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     memcpy(env->arena.data() + L.o_trig, env->luts.trig.data(), 722 * 8);
     memcpy(env->arena.data() + L.o_corn, env->luts.corn.data(), 361 * 4 * 8);
     memcpy(env->arena.data() + L.o_pend, env->luts.pend.data(), PEND_LUT * 8);
+    if (env->k.map != AT_MAP_MAZE) {
+        fill_bfs_table(env->k.wall_lo, env->k.wall_hi, (uint16_t *)(env->arena.data() + L.o_bfs));
+        env->st.bfs_tab = (const uint16_t *)(env->arena.data() + L.o_bfs);
+    }
     const int n = env->k.n_tanks;
     env->block.assign((size_t)n * BS * (5 * 8 + 5 * 4) + 722 * 8, 0);
     char *p = env->block.data();
@@ -109,7 +122,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.thits = (uint32_t *)p; p += n * BS * 4;
     bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint32_t *)p; p += n * BS * 4;
     bm.tshot = (int32_t *)p; p += n * BS * 4;
-    env->stage.assign(env->k.obs_dim + 8, 0.f);
+    env->stage.assign(env->k.obs_dim + 16, 0.f);
     env->ecnt.assign(BS, 0); env->ezones.assign(BS, 0); env->ewlo.assign(BS, 0); env->ewhi.assign(BS, 0);
     run(env, false, nullptr, nullptr, nullptr, nullptr, nullptr);  // the constructor's own reset
     *out = env;
