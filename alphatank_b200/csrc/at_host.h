@@ -134,7 +134,7 @@ inline std::string build_kcfg(const at_config *cfg, uint64_t seed, int64_t env_i
 // One arena for every SoA column (HBM on the GPU, malloc in the emulator).
 struct ArenaLayout {
     size_t o_cnt, o_rng, o_tick, o_tstep, o_ep, o_zones, o_prev, o_change, o_wlo, o_whi, o_tx, o_ty, o_trew, o_tpack,
-        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_bfs, o_act, o_rw, o_dn, bytes;
+        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_bfs, o_tmpl, o_act, o_rw, o_dn, bytes;
 };
 inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     ArenaLayout L;
@@ -148,6 +148,7 @@ inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     L.o_bf0 = take(8 * N * n); L.o_bf1 = take(8 * N * n); L.o_bx = take(8 * N * slots); L.o_by = take(8 * N * slots);
     L.o_bm = take(8 * N * slots); L.o_trig = take(722 * 8); L.o_corn = take(361 * 4 * 8); L.o_pend = take(PEND_LUT * 8);
     L.o_bfs = take(CELLS * CELLS * 2);
+    L.o_tmpl = take((4 * 72 + CELLS) * 4);
     L.o_act = take(4 * N * 3 * (k.act_rows ? k.act_rows : 1)); L.o_rw = take(4 * N * (k.rows ? k.rows : 1));
     L.o_dn = take(N);
     L.bytes = bytes;

@@ -31,14 +31,14 @@ using namespace at;
 namespace {
 
 struct SmemLayout {
-    int n, dpad;
-    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_ewlo, off_ewhi, off_tpack, off_thits,
-        off_bpack, off_tlive, off_tshot, off_ecnt, off_ezones, off_trec, off_stage, total;
+    int n;
+    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_thits, off_bpack, off_tlive,
+        off_tshot, off_tmpl, off_tile, off_slot, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n, int obs_dim) {
+constexpr int TILE_FLOATS = 32 * 32;  // per warp: 32 envs x 32 observation columns
+__host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
     SmemLayout L;
     L.n = n;
-    L.dpad = (obs_dim + 3) & ~3;
     size_t o = 0;
     L.off_trig = o; o += 722 * 8;
     L.off_tx = o; o += (size_t)n * BS * 8;
@@ -46,43 +46,70 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int obs_dim) {
     L.off_trew = o; o += (size_t)n * BS * 8;
     L.off_bf0 = o; o += (size_t)n * BS * 8;
     L.off_bf1 = o; o += (size_t)n * BS * 8;
-    L.off_ewlo = o; o += BS * 8;
-    L.off_ewhi = o; o += BS * 8;
     L.off_tpack = o; o += (size_t)n * BS * 4;
     L.off_thits = o; o += (size_t)n * BS * 4;
     L.off_bpack = o; o += (size_t)n * BS * 4;
     L.off_tlive = o; o += (size_t)n * BS * 4;
     L.off_tshot = o; o += (size_t)n * BS * 4;
-    L.off_ecnt = o; o += BS * 4;
-    L.off_ezones = o; o += BS * 4;
+    L.off_tmpl = o; o += (size_t)(4 * n_walls + CELLS) * 4;
     o = (o + 15) & ~(size_t)15;
-    L.off_trec = o; o += (size_t)(BS / 32) * TREC_FLOATS * 4;
-    o = (o + 15) & ~(size_t)15;
-    L.off_stage = o; o += (size_t)(BS / 32) * 2 * L.dpad * 4;
-    L.total = o;
+    L.off_tile = o; o += (size_t)(BS / 32) * TILE_FLOATS * 4;
+    L.off_slot = o; o += (size_t)n * SLOTS_PER_TANK * BS;
+    L.total = (o + 15) & ~(size_t)15;
     return L;
 }
 
-__device__ __forceinline__ void bulk_store_row(float *gdst, const float *ssrc, uint32_t bytes) {
-    uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes)
-                 : "memory");
-    asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
-}
-template <int N>
-__device__ __forceinline__ void bulk_wait_read() {
-    asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// Observation sink of one warp.  Every lane (= env) emits the same column j at the same time; the value goes
+// to tile[lane][(j + lane) & 31] (rotation => the 32 lanes hit 32 different banks).  After 32 columns the warp
+// flushes the 32 x 32 tile: lane L takes row 4i + L/8 and the four columns 4*(L%8)..+3 (again conflict-free)
+// and writes them with one 16-byte store, so a warp store instruction covers four complete 128-byte row
+// chunks - full-sector, fully coalesced HBM writes from thread-per-env code.
+struct TileSink {
+    float *tile;
+    float *gbase;       // obs row of the warp's lane 0
+    int64_t row_len;    // R * D floats per env
+    unsigned emit_mask; // lanes whose env gets an observation
+    int lane, j;
+    bool vec_ok;        // row_len % 4 == 0 and 16-byte aligned base
+    __device__ __forceinline__ void put(float v) {
+        tile[lane * 32 + ((j + lane) & 31)] = v;
+        if (((++j) & 31) == 0) flush(32);
+    }
+    __device__ __forceinline__ void finish() {
+        if (j & 31) flush(j & 31);
+    }
+    __device__ __noinline__ void flush(int ncols) {
+        __syncwarp();
+        const int j0 = (j - 1) & ~31;  // first column of this tile
+        if (vec_ok) {
+            const int c4 = (lane & 7) * 4;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = 4 * i + (lane >> 3);
+                const float *src = tile + r * 32;
+                float4 v;
+                v.x = src[(c4 + 0 + r) & 31]; v.y = src[(c4 + 1 + r) & 31];
+                v.z = src[(c4 + 2 + r) & 31]; v.w = src[(c4 + 3 + r) & 31];
+                if (((emit_mask >> r) & 1u) && c4 < ncols)
+                    *reinterpret_cast<float4 *>(gbase + (int64_t)r * row_len + j0 + c4) = v;
+            }
+        } else {
+            for (int r = 0; r < 32; ++r)
+                if (((emit_mask >> r) & 1u) && lane < ncols)
+                    gbase[(int64_t)r * row_len + j0 + lane] = tile[r * 32 + ((lane + r) & 31)];
+        }
+        __syncwarp();
+    }
+};
 
 template <bool IS_STEP>
 __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                  const int32_t *__restrict__ actions,
                                                  const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                  float *__restrict__ rewards, uint8_t *__restrict__ done,
-                                                 int use_bulk) {
+                                                 const float *__restrict__ g_tmpl) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(c.n_tanks, c.obs_dim);
+    const SmemLayout L = smem_layout(c.n_tanks, c.n_walls);
     BlockMem bm;
     bm.trig = (double *)(smem + L.off_trig);
     bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
@@ -91,18 +118,28 @@ __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c,
     bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.thits = (uint32_t *)(smem + L.off_thits);
     bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint32_t *)(smem + L.off_tlive);
     bm.tshot = (int32_t *)(smem + L.off_tshot);
-    uint64_t *ewlo = (uint64_t *)(smem + L.off_ewlo), *ewhi = (uint64_t *)(smem + L.off_ewhi);
-    uint32_t *ecnt = (uint32_t *)(smem + L.off_ecnt), *ezones = (uint32_t *)(smem + L.off_ezones);
+    bm.slot_of = (uint8_t *)(smem + L.off_slot);
+    float *tmpl = (float *)(smem + L.off_tmpl);
+    bm.tmpl = tmpl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 722; i += BS) bm.trig[i] = st.trig[i];
+    if (c.map != 2)
+        for (int i = tid; i < 4 * c.n_walls + CELLS; i += BS) tmpl[i] = g_tmpl[i];
+    for (int i = 0; i < c.n_tanks; ++i) {  // lanes without an env still walk the emitter: give them inert data
+        bm.tlive[i * BS + tid] = 0u;
+        bm.tpack[i * BS + tid] = 0u;
+        bm.tx[i * BS + tid] = 0.0;
+        bm.ty[i * BS + tid] = 0.0;
+    }
     __syncthreads();
 
     // ---------------- phase A: one thread per env
     const int64_t e = (int64_t)blockIdx.x * BS + tid;
+    const bool valid = e < st.N;
+    Sim s(c, st, bm, valid ? e : 0, tid);
     bool emit = false;
-    if (e < st.N) {
-        Sim s(c, st, bm, e, tid);
+    if (valid) {
         if (IS_STEP) {
             s.load();
             float rw[MAX_TANKS];
@@ -117,65 +154,23 @@ __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c,
             s.env_reset();
             s.store();
             emit = obs != nullptr;
-        } else if (obs != nullptr) {
-            // not reset: nothing to write for this env
         }
-        ecnt[tid] = s.cnt;
-        ezones[tid] = s.zones;
-        ewlo[tid] = s.wlo;
-        ewhi[tid] = s.whi;
     }
-    __syncwarp();
 
-    // ---------------- phase B: the warp writes the observation rows of its 32 envs
+    // ---------------- phase B: still one thread per env; the warp transposes through its tile
     const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-    if (emit_mask == 0u) return;
-    float *stage = (float *)(smem + L.off_stage) + (size_t)warp * 2 * L.dpad;
-    float *trec = (float *)(smem + L.off_trec) + (size_t)warp * TREC_FLOATS;
-    const int D = c.obs_dim;
-    if (c.map != 2) {  // fixed map: static columns are staged once
-        for (int b = 0; b < 2; ++b) {
-            RowCtx rc{c, st, bm, stage + b * L.dpad, trec, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
-            row_static(rc, lane);
-        }
-    }
-    __syncwarp();
-    int buf = 0;
-    for (int le = 0; le < 32; ++le) {
-        if (!((emit_mask >> le) & 1u)) continue;
-        const int q = warp * 32 + le;
-        const int64_t ee = (int64_t)blockIdx.x * BS + q;
-        RowCtx rc{c, st, bm, nullptr, trec, q, ee, ecnt[q], ezones[q], ewlo[q], ewhi[q]};
-        __syncwarp();  // the previous env's rows have consumed trec
-        env_records(rc, lane);
-        const LaneBullet lb = row_preload_bullet(rc, lane);
-        for (int r = 0; r < c.rows; ++r) {
-            const int t = c.team_layout ? c.agent_tank[r] : r;
-            float *row = stage + buf * L.dpad;
-            if (use_bulk) {  // the copy issued from this buffer two rows ago must have drained
-                if (lane == 0) bulk_wait_read<1>();
-            }
-            __syncwarp();
-            rc.row = row;
-            if (c.map == 2) row_static(rc, lane);
-            row_clear_bullets(rc, lane);
-            __syncwarp();
-            row_bullets(rc, lane, t, lb);
-            row_tanks(rc, lane, t);
-            row_misc(rc, lane, t);
-            float *dst = obs + (ee * c.rows + r) * (int64_t)D;
-            if (use_bulk) {
-                fence_async_smem();
-                __syncwarp();
-                if (lane == 0) bulk_store_row(dst, row, (uint32_t)D * 4u);
-            } else {
-                __syncwarp();
-                for (int j = lane; j < D; j += 32) dst[j] = row[j];
-            }
-            buf ^= 1;
-        }
-    }
-    if (use_bulk && lane == 0) bulk_wait_read<0>();
+    if (emit_mask == 0u || c.rows == 0) return;
+    const int64_t row_len = (int64_t)c.rows * c.obs_dim;
+    TileSink out;
+    out.tile = (float *)(smem + L.off_tile) + (size_t)warp * TILE_FLOATS;
+    out.gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
+    out.row_len = row_len;
+    out.emit_mask = emit_mask;
+    out.lane = lane;
+    out.j = 0;
+    out.vec_ok = (row_len % 4 == 0) && ((((uintptr_t)obs) & 15u) == 0);
+    s.emit_rows(out);
+    out.finish();
 }
 
 __global__ void gather_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
@@ -269,6 +264,7 @@ struct at_env {
     float *d_rewards_scratch;
     uint8_t *d_done_scratch;
     HostLuts luts;
+    const float *d_tmpl;
     size_t smem_bytes;
     int64_t launches;
 };
@@ -276,13 +272,12 @@ struct at_env {
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s) {
     const int grid = (int)((env->n_envs + BS - 1) / BS);
-    const int use_bulk = env->k.row_bulk_ok && (((uintptr_t)d_obs & 15u) == 0) ? 1 : 0;
     if (is_step)
         env_kernel<true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                          d_done, use_bulk);
+                                                          d_done, env->d_tmpl);
     else
         env_kernel<false><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                           d_done, use_bulk);
+                                                           d_done, env->d_tmpl);
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
@@ -345,7 +340,13 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->st.bfs_tab = (const uint16_t *)(b + L.o_bfs);
     }
 
-    env->smem_bytes = smem_layout(k.n_tanks, k.obs_dim).total;
+    env->d_tmpl = (const float *)(b + L.o_tmpl);
+    if (k.map != AT_MAP_MAZE) {
+        std::vector<float> tm((size_t)4 * k.n_walls + CELLS);
+        fill_static_template(k.wall_lo, k.wall_hi, tm.data());
+        cudaMemcpy(b + L.o_tmpl, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice);
+    }
+    env->smem_bytes = smem_layout(k.n_tanks, k.n_walls).total;
     cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     // GamingENV.__init__ -> self.reset() (gaming_env.py:43): the constructor's own reset consumes draws

@@ -456,7 +456,9 @@ struct Sim {
             double x = st.bx[G(r)], y = st.by[G(r)];
             uint64_t m = st.bmeta[G(r)];
             if (!bullet_move(x, y, m)) {
-                uint32_t rank = TLIVE((int)(m & 15u))++;
+                const int ow = (int)(m & 15u);
+                uint32_t rank = TLIVE(ow)++;
+                bm.slot_of[(ow * SLOTS_PER_TANK + (int)rank) * BS + tid] = (uint8_t)w;
                 m = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
                 st.bx[G(w)] = x;
                 st.by[G(w)] = y;
@@ -1095,6 +1097,92 @@ struct Sim {
         return done;
     }
 
+    // ---------------------------------------------------------------- observation rows
+    // gym_env.py:105-183 (1v1 layout) / gym_env_multi.py:225-304 (team layout), one value after the other in
+    // layout order, exactly like the reference builds its list.  Runs one thread per env: control flow is
+    // uniform across the warp (slot loops run to 6 with a predicate), so all 32 lanes emit column j together and
+    // the sink can transpose 32 envs x 32 columns through shared memory into coalesced row-chunk stores.
+    template <class Sink>
+    AT_HD void emit_tank_common(Sink &out, int i) const {
+        const double x = TX(i), y = TY(i);
+        const int a = t_angle(i);
+        const double sp = (double)t_speed(i);
+        const double *co = st.corn + 4 * a;
+        out.put((float)(x + co[0])); out.put((float)(y + co[1])); out.put((float)(x + co[2])); out.put((float)(y + co[3]));
+        out.put((float)(x - co[0])); out.put((float)(y - co[1])); out.put((float)(x - co[2])); out.put((float)(y - co[3]));
+        out.put((float)(sp * cosr(a)));
+        out.put((float)(sp * sinr(a)));
+        out.put((TPACK(i) & TP_HW) ? 1.0f : 0.0f);
+    }
+    template <class Sink>
+    AT_HD void emit_rows(Sink &out) const {
+        const bool team = c.team_layout != 0;
+        for (int r = 0; r < c.rows; ++r) {
+            const int t = team ? c.agent_tank[r] : r;
+            const double ax = TX(t), ay = TY(t);
+            out.put((float)ax); out.put((float)ay);
+            emit_tank_common(out, t);
+            if (team) out.put(1.0f);
+            out.put(t_alive(t) ? 1.0f : 0.0f);
+            for (int o = 0; o < c.n_tanks; ++o) {  // own bullets first, then every other tank's, in tank order
+                const int owner = o == 0 ? t : (o <= t ? o - 1 : o);
+                const uint32_t live = TLIVE(owner);
+                const float same = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
+                for (int k = 0; k < SLOTS_PER_TANK; ++k) {
+                    const bool has = (uint32_t)k < live;
+                    double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
+                    if (has) {
+                        const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
+                        const uint64_t m = st.bmeta[G(slot)];
+                        x = st.bx[G(slot)];
+                        y = st.by[G(slot)];
+                        const int ang = (int)((m >> BM_ANGLE) & 511u);
+                        const double cv = cosr(ang), sv = sinr(ang);
+                        dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv;
+                        dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
+                    }
+                    out.put((float)x); out.put((float)y); out.put((float)dx); out.put((float)dy);
+                    if (o != 0) {
+                        const double rx = x - ax, ry = y - ay;
+                        out.put(has ? (float)rx : 0.0f);
+                        out.put(has ? (float)ry : 0.0f);
+                        out.put(has ? (float)sqrt(rx * rx + ry * ry) : 0.0f);
+                        if (team) out.put(has ? same : 0.0f);
+                    }
+                }
+            }
+            for (int i = 0; i < c.n_tanks; ++i) {
+                if (i == t) continue;
+                const double x = TX(i), y = TY(i);
+                const double rx = x - ax, ry = y - ay;
+                out.put((float)x); out.put((float)y); out.put((float)rx); out.put((float)ry);
+                out.put((float)sqrt(rx * rx + ry * ry));
+                emit_tank_common(out, i);
+                if (team) out.put(c.team[i] == c.team[t] ? 1.0f : 0.0f);
+                out.put(t_alive(i) ? 1.0f : 0.0f);
+            }
+            if (c.map != 2) {  // fixed map: wall rectangles + maze grid from the block's template
+                const int ns = 4 * c.n_walls + CELLS;
+                for (int k = 0; k < ns; ++k) out.put(bm.tmpl[k]);
+            } else {
+                const M128 wm = {wlo, whi};
+                for (int k = 0; k < c.n_walls; ++k) {  // k-th wall in row-major order (uniform trip count)
+                    const int cell = select_bit(wm, k);
+                    const float X = (float)((cell % 11) * 70), Y = (float)((cell / 11) * 70);
+                    out.put(X); out.put(Y); out.put(X + 70.0f); out.put(Y + 70.0f);
+                }
+                for (int cell = 0; cell < CELLS; ++cell) out.put(wall_at(cell) ? 1.0f : 0.0f);
+            }
+            for (int v = 0; v < c.n_zone_vals; ++v) {  // zone corners, buff first (gym_env.py:168-173)
+                const int k = (v >> 1) + (c.buff_on ? 0 : 2);
+                const int cell = (int)((zones >> (7 * k)) & 127u);
+                out.put((float)(((v & 1) ? cell / 11 : cell % 11) * 70));
+            }
+            out.put((TPACK(t) & TP_INBUFF) ? 1.0f : 0.0f);
+            out.put((TPACK(t) & TP_INDEBUFF) ? 1.0f : 0.0f);
+        }
+    }
+
     // ---------------------------------------------------------------- HBM <-> working set
     AT_HD void load() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
@@ -1126,153 +1214,17 @@ struct Sim {
     }
 };
 
-// ------------------------------------------------------------------ observation rows
-// gym_env.py:105-183 (1v1 layout) / gym_env_multi.py:225-304 (team layout).  A row is assembled by the 32
-// lanes of a warp in a shared-memory staging buffer and leaves as one contiguous block.  `q` is the env's
-// slot in the block working set, `e` its SoA index, `t` the tank the row belongs to.  Everything that does
-// not depend on the viewer (each tank's position / corners / velocity / flags, the zone corners, the env's
-// bullets) is produced once per env: `trec` is a per-warp scratch of TREC_FLOATS floats.
-constexpr int TREC_STRIDE = 16, TREC_ZONES = MAX_TANKS * TREC_STRIDE, TREC_FLOATS = TREC_ZONES + 8;
-struct RowCtx {
-    const KCfg &c;
-    const DevState &st;
-    const BlockMem &bm;
-    float *row;
-    float *trec;
-    int q;
-    int64_t e;
-    uint32_t cnt, zones;
-    uint64_t wlo, whi;
-};
-struct LaneBullet {
-    double x, y;
-    uint64_t m;
-};
-
-AT_HD void row_static(const RowCtx &r, int lane) {  // walls (row-major) + maze: change only with the map
-    const KCfg &c = r.c;
-    for (int cell = lane; cell < CELLS; cell += 32) {
-        bool w = ((cell < 64 ? r.wlo >> cell : r.whi >> (cell - 64)) & 1ull) != 0;
-        r.row[c.off_maze + cell] = w ? 1.0f : 0.0f;
-        if (w) {
-            uint64_t below_lo = cell < 64 ? (r.wlo & ((1ull << cell) - 1)) : r.wlo;
-            uint64_t below_hi = cell < 64 ? 0ull : (r.whi & ((1ull << (cell - 64)) - 1));
-            int idx = popc64(below_lo) + popc64(below_hi);
-            float X = (float)((cell % 11) * 70), Y = (float)((cell / 11) * 70);
-            float *p = r.row + c.off_walls + 4 * idx;
-            p[0] = X; p[1] = Y; p[2] = X + 70.0f; p[3] = Y + 70.0f;
+// wall rectangles (row-major = reference list order) + maze grid columns of a fixed map
+AT_HD void fill_static_template(uint64_t wall_lo, uint64_t wall_hi, float *tmpl) {
+    int w = 0;
+    for (int cell = 0; cell < CELLS; ++cell)
+        if ((cell < 64 ? wall_lo >> cell : wall_hi >> (cell - 64)) & 1ull) {
+            const float X = (float)((cell % 11) * 70), Y = (float)((cell / 11) * 70);
+            tmpl[4 * w] = X; tmpl[4 * w + 1] = Y; tmpl[4 * w + 2] = X + 70.0f; tmpl[4 * w + 3] = Y + 70.0f;
+            ++w;
         }
-    }
-}
-// once per env: lane i < n writes tank i's viewer-independent record (x, y, 4 corners, velocity, hittingWall,
-// alive); lanes < n_zone_vals write the zone corner coordinates (buff first, gym_env.py:168-173)
-AT_HD void env_records(const RowCtx &r, int lane) {
-    const KCfg &c = r.c;
-    if (lane < c.n_tanks) {
-        const int i = lane;
-        const double x = r.bm.tx[i * BS + r.q], y = r.bm.ty[i * BS + r.q];
-        const uint32_t pk = r.bm.tpack[i * BS + r.q];
-        const int a = (int)(pk & 511u);
-        const uint32_t sc = (pk >> 9) & 3u;
-        const double sp = sc == 0 ? 0.0 : (sc == 1 ? 10.0 : (sc == 2 ? -10.0 : 1.0));
-        const double *co = r.st.corn + 4 * a;
-        float *p = r.trec + i * TREC_STRIDE;
-        p[0] = (float)x; p[1] = (float)y;
-        p[2] = (float)(x + co[0]); p[3] = (float)(y + co[1]); p[4] = (float)(x + co[2]); p[5] = (float)(y + co[3]);
-        p[6] = (float)(x - co[0]); p[7] = (float)(y - co[1]); p[8] = (float)(x - co[2]); p[9] = (float)(y - co[3]);
-        p[10] = (float)(sp * r.bm.trig[2 * a]);
-        p[11] = (float)(sp * r.bm.trig[2 * a + 1]);
-        p[12] = (pk & TP_HW) ? 1.0f : 0.0f;
-        p[13] = (pk & TP_ALIVE) ? 1.0f : 0.0f;
-    }
-    if (lane >= 16 && lane - 16 < c.n_zone_vals) {
-        const int v = lane - 16;
-        int k = v >> 1;
-        if (!c.buff_on) k += 2;
-        const int cell = (int)((r.zones >> (7 * k)) & 127u);
-        r.trec[TREC_ZONES + v] = (float)(((v & 1) ? cell / 11 : cell % 11) * 70);
-    }
-}
-AT_HD LaneBullet row_preload_bullet(const RowCtx &r, int lane) {
-    LaneBullet lb = {0.0, 0.0, 0ull};
-    if ((uint32_t)lane < r.cnt) {
-        const int64_t g = (int64_t)lane * r.st.N + r.e;
-        lb.m = r.st.bmeta[g];
-        lb.x = r.st.bx[g];
-        lb.y = r.st.by[g];
-    }
-    return lb;
-}
-AT_HD void row_clear_bullets(const RowCtx &r, int lane) {  // 16-byte stores; the spill-over into the
-    const int j0 = r.c.off_ob & ~3, j1 = (r.c.off_et + 3) & ~3;  // neighbouring tank fields is rewritten after
-    for (int j = j0 + 4 * lane; j < j1; j += 128) {
-        float *p = r.row + j;
-#ifdef __CUDA_ARCH__
-        *reinterpret_cast<float4 *>(p) = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-#else
-        p[0] = 0.0f; p[1] = 0.0f; p[2] = 0.0f; p[3] = 0.0f;
-#endif
-    }
-}
-AT_HD void row_put_bullet(const RowCtx &r, int t, double ax, double ay, double x, double y, uint64_t m) {
-    const KCfg &c = r.c;
-    const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u), rank = (int)((m >> BM_RANK) & 7u);
-    const double cv = r.bm.trig[2 * ang], sv = r.bm.trig[2 * ang + 1];
-    const double dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv, dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
-    if (owner == t) {
-        float *p = r.row + c.off_ob + 4 * rank;
-        p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
-    } else {
-        const int oi = owner < t ? owner : owner - 1;
-        const int per = c.team_layout ? 8 : 7;
-        float *p = r.row + c.off_eb + oi * c.eb_stride + per * rank;
-        const double rx = x - ax, ry = y - ay;
-        p[0] = (float)x; p[1] = (float)y; p[2] = (float)dx; p[3] = (float)dy;
-        p[4] = (float)rx; p[5] = (float)ry; p[6] = (float)sqrt(rx * rx + ry * ry);
-        if (c.team_layout) p[7] = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
-    }
-}
-AT_HD void row_bullets(const RowCtx &r, int lane, int t, const LaneBullet &lb) {
-    const double ax = r.bm.tx[t * BS + r.q], ay = r.bm.ty[t * BS + r.q];
-    if ((uint32_t)lane < r.cnt) row_put_bullet(r, t, ax, ay, lb.x, lb.y, lb.m);
-    for (uint32_t s = lane + 32; s < r.cnt; s += 32) {  // more than 32 live bullets only with >= 6 tanks
-        const int64_t g = (int64_t)s * r.st.N + r.e;
-        row_put_bullet(r, t, ax, ay, r.st.bx[g], r.st.by[g], r.st.bmeta[g]);
-    }
-}
-AT_HD void row_tanks(const RowCtx &r, int lane, int t) {
-    const KCfg &c = r.c;
-    const int total = c.n_tanks * 14;
-    for (int j = lane; j < total; j += 32) {  // copy the per-env records into this viewer's layout
-        const int i = j / 14, f = j - 14 * i;
-        const float v = r.trec[i * TREC_STRIDE + f];
-        int dst;
-        if (i == t) {
-            dst = f < 13 ? f : c.self_len - 1;
-        } else {
-            const int base = c.off_et + (i < t ? i : i - 1) * c.et_len;
-            dst = base + (f < 2 ? f : (f < 13 ? f + 3 : c.et_len - 1));
-        }
-        r.row[dst] = v;
-    }
-    if (lane < c.n_tanks) {  // viewer-dependent fields of tank `lane`
-        const int i = lane;
-        if (i == t) {
-            if (c.team_layout) r.row[13] = 1.0f;
-        } else {
-            float *p = r.row + c.off_et + (i < t ? i : i - 1) * c.et_len;
-            const double rx = r.bm.tx[i * BS + r.q] - r.bm.tx[t * BS + r.q];
-            const double ry = r.bm.ty[i * BS + r.q] - r.bm.ty[t * BS + r.q];
-            p[2] = (float)rx; p[3] = (float)ry; p[4] = (float)sqrt(rx * rx + ry * ry);
-            if (c.team_layout) p[16] = c.team[i] == c.team[t] ? 1.0f : 0.0f;
-        }
-    }
-}
-AT_HD void row_misc(const RowCtx &r, int lane, int t) {
-    const KCfg &c = r.c;
-    if (lane < c.n_zone_vals) r.row[c.off_zones + lane] = r.trec[TREC_ZONES + lane];
-    if (lane == 30) r.row[c.off_flags] = (r.bm.tpack[t * BS + r.q] & TP_INBUFF) ? 1.0f : 0.0f;
-    if (lane == 31) r.row[c.off_flags + 1] = (r.bm.tpack[t * BS + r.q] & TP_INDEBUFF) ? 1.0f : 0.0f;
+    for (int cell = 0; cell < CELLS; ++cell)
+        tmpl[4 * w + cell] = ((cell < 64 ? wall_lo >> cell : wall_hi >> (cell - 64)) & 1ull) ? 1.0f : 0.0f;
 }
 
 }  // namespace at

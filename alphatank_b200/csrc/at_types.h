@@ -70,6 +70,8 @@ struct BlockMem {
     double *bf0, *bf1;             // [n][BS]
     uint32_t *tpack, *thits, *bpack, *tlive;  // [n][BS]  (tlive: live bullets per owner)
     int32_t *tshot;                // [n][BS]
+    uint8_t *slot_of;              // [n*6][BS] bullet slot of (owner, per-owner rank), valid for rank < tlive
+    const float *tmpl;             // [4W + 121] wall + maze observation columns of a fixed map
 };
 
 }  // namespace at

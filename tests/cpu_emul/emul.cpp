@@ -26,24 +26,29 @@ struct em_env {
     int64_t n_envs;
     std::vector<char> arena;
     std::vector<char> block;  // one block's working set
-    std::vector<float> stage;
+    std::vector<float> tmpl;
+    std::vector<uint8_t> slot_of;
     BlockMem bm;
-    std::vector<uint32_t> ecnt, ezones;
-    std::vector<uint64_t> ewlo, ewhi;
 };
 static thread_local std::string g_err;
+
+struct DirectSink {  // the emulator writes column j of the env's observation row directly
+    float *row;
+    int j;
+    void put(float v) { row[j++] = v; }
+};
 
 static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
                 uint8_t *done) {
     const KCfg &c = env->k;
     const DevState &st = env->st;
-    const int D = c.obs_dim;
+    const int64_t row_len = (int64_t)c.rows * c.obs_dim;
     for (int64_t b0 = 0; b0 < env->n_envs; b0 += BS) {
-        bool emit[BS] = {false};
-        for (int tid = 0; tid < BS; ++tid) {  // phase A
+        for (int tid = 0; tid < BS; ++tid) {
             const int64_t e = b0 + tid;
             if (e >= st.N) continue;
             Sim s(c, st, env->bm, e, tid);
+            bool emit = false;
             if (is_step) {
                 s.load();
                 float rw[MAX_TANKS];
@@ -52,36 +57,16 @@ static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t
                 done[e] = d ? 1 : 0;
                 if (d && c.auto_reset) s.env_reset();
                 s.store();
-                emit[tid] = obs != nullptr;
+                emit = obs != nullptr;
             } else if (!mask || mask[e]) {
                 s.load();
                 s.env_reset();
                 s.store();
-                emit[tid] = obs != nullptr;
+                emit = obs != nullptr;
             }
-            env->ecnt[tid] = s.cnt; env->ezones[tid] = s.zones; env->ewlo[tid] = s.wlo; env->ewhi[tid] = s.whi;
-        }
-        float *row = env->stage.data();  // phase B
-        float trec[TREC_FLOATS];
-        if (c.map != 2) {
-            RowCtx rc{c, st, env->bm, row, trec, 0, 0, 0u, 0u, c.wall_lo, c.wall_hi};
-            for (int lane = 0; lane < 32; ++lane) row_static(rc, lane);
-        }
-        for (int q = 0; q < BS; ++q) {
-            if (!emit[q]) continue;
-            const int64_t ee = b0 + q;
-            RowCtx rc{c, st, env->bm, row, trec, q, ee, env->ecnt[q], env->ezones[q], env->ewlo[q], env->ewhi[q]};
-            LaneBullet lb[32];
-            for (int lane = 0; lane < 32; ++lane) env_records(rc, lane);
-            for (int lane = 0; lane < 32; ++lane) lb[lane] = row_preload_bullet(rc, lane);
-            for (int r = 0; r < c.rows; ++r) {
-                const int t = c.team_layout ? c.agent_tank[r] : r;
-                if (c.map == 2) for (int lane = 0; lane < 32; ++lane) row_static(rc, lane);
-                for (int lane = 0; lane < 32; ++lane) row_clear_bullets(rc, lane);
-                for (int lane = 0; lane < 32; ++lane) row_bullets(rc, lane, t, lb[lane]);
-                for (int lane = 0; lane < 32; ++lane) row_tanks(rc, lane, t);
-                for (int lane = 0; lane < 32; ++lane) row_misc(rc, lane, t);
-                memcpy(obs + (ee * c.rows + r) * (int64_t)D, row, sizeof(float) * D);
+            if (emit && c.rows > 0) {
+                DirectSink out{obs + e * row_len, 0};
+                s.emit_rows(out);
             }
         }
     }
@@ -122,8 +107,11 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.thits = (uint32_t *)p; p += n * BS * 4;
     bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint32_t *)p; p += n * BS * 4;
     bm.tshot = (int32_t *)p; p += n * BS * 4;
-    env->stage.assign(env->k.obs_dim + 16, 0.f);
-    env->ecnt.assign(BS, 0); env->ezones.assign(BS, 0); env->ewlo.assign(BS, 0); env->ewhi.assign(BS, 0);
+    env->tmpl.assign(4 * 72 + CELLS, 0.f);
+    if (env->k.map != AT_MAP_MAZE) fill_static_template(env->k.wall_lo, env->k.wall_hi, env->tmpl.data());
+    env->slot_of.assign((size_t)n * SLOTS_PER_TANK * BS, 0);
+    bm.tmpl = env->tmpl.data();
+    bm.slot_of = env->slot_of.data();
     run(env, false, nullptr, nullptr, nullptr, nullptr, nullptr);  // the constructor's own reset
     *out = env;
     return AT_OK;
