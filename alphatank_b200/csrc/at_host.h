@@ -69,17 +69,22 @@ inline void build_map(int map, uint64_t *lo, uint64_t *hi, int *n_walls) {
 
 
 struct HostLuts {
-    std::vector<double> trig, corn, pend;
+    std::vector<double> trig, corn, pend, udir;
 };
 // built with the host libm exactly as CPython's math module / pygame would
 inline void build_luts(HostLuts &l) {
-    l.trig.resize(722); l.corn.resize(361 * 4); l.pend.resize(PEND_LUT);
+    l.trig.resize(722); l.corn.resize(361 * 4); l.pend.resize(PEND_LUT); l.udir.resize(722);
     for (int a = 0; a <= 360; ++a) {
         double rad = (double)a * (M_PI / 180.0);  // math.radians
         l.trig[2 * a] = cos(rad);
         l.trig[2 * a + 1] = sin(rad);
         pg_rotate(-15.0, -12.0, (double)a, &l.corn[4 * a], &l.corn[4 * a + 1]);
         pg_rotate(15.0, -12.0, (double)a, &l.corn[4 * a + 2], &l.corn[4 * a + 3]);
+        // bullet_dir / np.linalg.norm(bullet_dir) (sprite.py:32, 516): norm = sqrt(fma(dy, dy, dx*dx)), see oracle
+        const double dx = l.trig[2 * a], dy = -l.trig[2 * a + 1];
+        const double nrm = sqrt(fma(dy, dy, dx * dx));
+        l.udir[2 * a] = dx / nrm;
+        l.udir[2 * a + 1] = dy / nrm;
     }
     double acc = 0.0;
     for (int i = 0; i < PEND_LUT; ++i) { l.pend[i] = acc; acc = acc + 0.02; }  // pending += BULLET_AWAY_PENALTY
@@ -134,7 +139,7 @@ inline std::string build_kcfg(const at_config *cfg, uint64_t seed, int64_t env_i
 // One arena for every SoA column (HBM on the GPU, malloc in the emulator).
 struct ArenaLayout {
     size_t o_cnt, o_rng, o_tick, o_tstep, o_ep, o_zones, o_prev, o_change, o_wlo, o_whi, o_tx, o_ty, o_trew, o_tpack,
-        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_bfs, o_tmpl, o_act, o_rw, o_dn, bytes;
+        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_udir, o_bfs, o_tmpl, o_act, o_rw, o_dn, bytes;
 };
 inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     ArenaLayout L;
@@ -147,6 +152,7 @@ inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     L.o_tpack = take(4 * N * n); L.o_thits = take(4 * N * n); L.o_tshot = take(4 * N * n); L.o_bpack = take(4 * N * n);
     L.o_bf0 = take(8 * N * n); L.o_bf1 = take(8 * N * n); L.o_bx = take(8 * N * slots); L.o_by = take(8 * N * slots);
     L.o_bm = take(8 * N * slots); L.o_trig = take(722 * 8); L.o_corn = take(361 * 4 * 8); L.o_pend = take(PEND_LUT * 8);
+    L.o_udir = take(722 * 8);
     L.o_bfs = take(CELLS * CELLS * 2);
     L.o_tmpl = take((4 * 72 + CELLS) * 4);
     L.o_act = take(4 * N * 3 * (k.act_rows ? k.act_rows : 1)); L.o_rw = take(4 * N * (k.rows ? k.rows : 1));
@@ -166,6 +172,7 @@ inline void bind_state(DevState &st, char *b, const ArenaLayout &L, int64_t N) {
     st.bx = (double *)(b + L.o_bx); st.by = (double *)(b + L.o_by); st.bmeta = (uint64_t *)(b + L.o_bm);
     st.trig = (const double *)(b + L.o_trig); st.corn = (const double *)(b + L.o_corn);
     st.pend = (const double *)(b + L.o_pend);
+    st.udir = (const double *)(b + L.o_udir);
     st.bfs_tab = nullptr;  // set by the owner for fixed maps (at_sim.h fill_bfs_table)
 }
 

@@ -64,7 +64,29 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
 // flushes the 32 x 32 tile: lane L takes row 4i + L/8 and the four columns 4*(L%8)..+3 (again conflict-free)
 // and writes them with one 16-byte store, so a warp store instruction covers four complete 128-byte row
 // chunks - full-sector, fully coalesced HBM writes from thread-per-env code.
-struct TileSink {
+__device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t row_len, unsigned emit_mask, int lane,
+                                        int j0, int ncols, bool vec_ok) {
+    __syncwarp();
+    if (vec_ok) {
+        const int c4 = (lane & 7) * 4;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = 4 * i + (lane >> 3);
+            const float *src = tile + r * 32;
+            float4 v;
+            v.x = src[(c4 + 0 + r) & 31]; v.y = src[(c4 + 1 + r) & 31];
+            v.z = src[(c4 + 2 + r) & 31]; v.w = src[(c4 + 3 + r) & 31];
+            if (((emit_mask >> r) & 1u) && c4 < ncols)
+                *reinterpret_cast<float4 *>(gbase + (int64_t)r * row_len + j0 + c4) = v;
+        }
+    } else {
+        for (int r = 0; r < 32; ++r)
+            if (((emit_mask >> r) & 1u) && lane < ncols)
+                gbase[(int64_t)r * row_len + j0 + lane] = tile[r * 32 + ((lane + r) & 31)];
+    }
+    __syncwarp();
+}
+struct TileSink {  // kept in registers: flush takes everything by value
     float *tile;
     float *gbase;       // obs row of the warp's lane 0
     int64_t row_len;    // R * D floats per env
@@ -73,32 +95,11 @@ struct TileSink {
     bool vec_ok;        // row_len % 4 == 0 and 16-byte aligned base
     __device__ __forceinline__ void put(float v) {
         tile[lane * 32 + ((j + lane) & 31)] = v;
-        if (((++j) & 31) == 0) flush(32);
+        ++j;
+        if ((j & 31) == 0) tile_flush(tile, gbase, row_len, emit_mask, lane, j - 32, 32, vec_ok);
     }
     __device__ __forceinline__ void finish() {
-        if (j & 31) flush(j & 31);
-    }
-    __device__ __noinline__ void flush(int ncols) {
-        __syncwarp();
-        const int j0 = (j - 1) & ~31;  // first column of this tile
-        if (vec_ok) {
-            const int c4 = (lane & 7) * 4;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = 4 * i + (lane >> 3);
-                const float *src = tile + r * 32;
-                float4 v;
-                v.x = src[(c4 + 0 + r) & 31]; v.y = src[(c4 + 1 + r) & 31];
-                v.z = src[(c4 + 2 + r) & 31]; v.w = src[(c4 + 3 + r) & 31];
-                if (((emit_mask >> r) & 1u) && c4 < ncols)
-                    *reinterpret_cast<float4 *>(gbase + (int64_t)r * row_len + j0 + c4) = v;
-            }
-        } else {
-            for (int r = 0; r < 32; ++r)
-                if (((emit_mask >> r) & 1u) && lane < ncols)
-                    gbase[(int64_t)r * row_len + j0 + lane] = tile[r * 32 + ((lane + r) & 31)];
-        }
-        __syncwarp();
+        if (j & 31) tile_flush(tile, gbase, row_len, emit_mask, lane, j & ~31, j & 31, vec_ok);
     }
 };
 
@@ -333,6 +334,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaMemcpy(b + L.o_trig, env->luts.trig.data(), 722 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(b + L.o_corn, env->luts.corn.data(), 361 * 4 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(b + L.o_pend, env->luts.pend.data(), PEND_LUT * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(b + L.o_udir, env->luts.udir.data(), 722 * 8, cudaMemcpyHostToDevice);
     if (k.map != AT_MAP_MAZE) {  // fixed map: path-finding becomes one table lookup
         std::vector<uint16_t> tab((size_t)CELLS * CELLS);
         fill_bfs_table(k.wall_lo, k.wall_hi, tab.data());

@@ -117,6 +117,18 @@ AT_HD double py_radians(double x) { return x * (PI / 180.0); }
 AT_HD double py_degrees(double x) { return x * (180.0 / PI); }
 AT_HD double np_dot2(double a0, double a1, double b0, double b1) { return fma_rn(a1, b1, a0 * b0); }
 AT_HD double np_norm2(double a0, double a1) { return sqrt(np_dot2(a0, a1, a0, a1)); }
+// Exact squared-distance forms of the reference's distance compares (sqrt is correctly rounded and monotonic):
+//   sqrt(s) > 300  <=>  s > S300   (S300 = largest double whose root rounds to <= 300)
+//   sqrt(s) < 100  <=>  s < 10000  (the double just below 10000 already roots to < 100)
+constexpr double S300 = 0x1.5f90000000001p+16;
+constexpr double S100 = 10000.0;
+AT_HD double fast_rsqrt(double s) {
+#ifdef __CUDA_ARCH__
+    return rsqrt(s);
+#else
+    return 1.0 / sqrt(s);
+#endif
+}
 
 // atan2 with the lattice cases pinned to the correctly rounded doubles glibc returns (axis-aligned and
 // diagonal bearings are NOT measure-zero here: tanks spawn on cell centres).  Elsewhere the device atan2
@@ -400,20 +412,33 @@ struct Sim {
         const double nx = x + dx, ny = y + dy;
         const int ix = d2i(nx), iy = d2i(ny);
         const int oteam = c.team[owner];
-        // update_reward_logic on the pre-move position (sprite.py:27-57)
+        // update_reward_logic on the pre-move position (sprite.py:27-57).  Same decisions as the reference's
+        // norm / divide / dot sequence, reached cheaply: the unit direction comes from a table, distances are
+        // compared through their squares (exact, see S300 / S100), and the cosine is first evaluated with fast
+        // arithmetic - only when it lands within 1e-9 of a threshold is the reference's exact sequence run.
         {
-            const double nrm = np_norm2(dx, dy);
-            const double d0 = dx / nrm, d1 = dy / nrm;
+            const double u0 = st.udir[2 * ang], u1 = st.udir[2 * ang + 1];
+            const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
             for (int i = 0; i < c.n_tanks; ++i) {
                 if (!t_alive(i) || c.team[i] == oteam) continue;
-                double tx = TX(i) - x, ty = TY(i) - y;
-                double dt = np_norm2(tx, ty);
-                if (dt > 300) continue;
-                double u0 = tx / dt, u1 = ty / dt;
-                double dp = np_dot2(d0, d1, u0, u1);
-                if (dp > 0.9) TREW(owner) += 0.01;
-                else if (dp < 0.1) { if (!cleared) ++pcnt; }
-                if (dt < 100) { pcnt = 0; cleared = true; }
+                const double tx = TX(i) - x, ty = TY(i) - y;
+                if (fabs(tx) > 301.0 || fabs(ty) > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
+                const double s2 = np_dot2(tx, ty, tx, ty);
+                if (s2 > S300) continue;                              // dist > BULLET_MAX_DISTANCE
+                const double dpa = (d0 * tx + d1 * ty) * fast_rsqrt(s2);
+                bool hi, lo;
+                if (fabs(dpa - 0.9) > 1e-9 && fabs(dpa - 0.1) > 1e-9) {
+                    hi = dpa > 0.9;
+                    lo = dpa < 0.1;
+                } else {  // also taken for dist == 0 (NaN): the reference's comparisons are then both false
+                    const double dt = sqrt(s2);
+                    const double dp = np_dot2(d0, d1, tx / dt, ty / dt);
+                    hi = dp > 0.9;
+                    lo = dp < 0.1;
+                }
+                if (hi) TREW(owner) += 0.01;
+                else if (lo) { if (!cleared) ++pcnt; }
+                if (s2 < S100) { pcnt = 0; cleared = true; }          // dist < DISTANCE_CANCEL_THRESHOLD
             }
         }
         bool nfx = fx, nfy = fy;
@@ -517,17 +542,17 @@ struct Sim {
         const double tvx = (double)sp * cosr(a), tvy = (double)sp * sinr(a);
         const int myteam = c.team[i];
         double reward = 0;
+        const double mx = TX(i), my = TY(i);
         for (uint32_t r = 0; r < cnt; ++r) {
             const uint64_t m = st.bmeta[G(r)];
             if (c.team[(int)(m & 15u)] == myteam) continue;
-            const double bxv = st.bx[G(r)], byv = st.by[G(r)];
-            double distance = np_norm2(TX(i) - bxv, TY(i) - byv);
-            if (distance >= 100) continue;
+            const double ex_ = mx - st.bx[G(r)];
+            if (fabs(ex_) >= 101.0) continue;                          // distance >= 100 for sure
+            const double ey_ = my - st.by[G(r)];
+            if (!(np_dot2(ex_, ey_, ex_, ey_) < S100)) continue;       // `distance >= 100: continue` (sprite.py:508)
             const int ba = (int)((m >> BM_ANGLE) & 511u);
-            const double cv = cosr(ba), sv = sinr(ba);
-            double dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv, dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
-            double nrm = np_norm2(dx, dy);
-            double d0 = dx / nrm, d1 = dy / nrm;
+            const double u0 = st.udir[2 * ba], u1 = st.udir[2 * ba + 1];
+            const double d0 = ((m >> BM_FLIPX) & 1u) ? -u0 : u0, d1 = ((m >> BM_FLIPY) & 1u) ? -u1 : u1;
             double proj = np_dot2(tvx, tvy, -d1, d0);
             reward += fabs(proj) * 0.01;
         }

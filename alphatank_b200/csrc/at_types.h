@@ -60,6 +60,7 @@ struct DevState {
     const double *trig;            // [361][2] cos, sin of math.radians(a)
     const double *corn;            // [361][4] pygame-rotated corner offsets (c0x, c0y, c1x, c1y)
     const double *pend;            // [PEND_LUT] k-fold accumulation of BULLET_AWAY_PENALTY
+    const double *udir;            // [361][2] (cos a, -sin a) / |(cos a, -sin a)| as numpy computes it
     const uint16_t *bfs_tab;       // [121*121] all-pairs bfs_first_step of a FIXED map: len | dir << 8 (null for mazes)
 };
 

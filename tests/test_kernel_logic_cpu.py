@@ -158,3 +158,23 @@ def test_exact_multi_step_jump_equals_sequential_additions():
             want = want + d
         got = L.em_jump_axis(x, d, m)
         assert got == want, (x, d, m, got, want)
+
+
+def test_squared_distance_thresholds_are_exact():
+    """sqrt(s) > 300 <=> s > S300 and sqrt(s) < 100 <=> s < S100 for every double s (checked on the +-300
+    neighbours of each boundary; sqrt is monotonic and correctly rounded)."""
+    import math
+    import re
+    src = open(os.path.join(os.path.dirname(parity.GOLDEN), "..", "alphatank_b200", "csrc", "at_sim.h")).read()
+    s300 = float.fromhex(re.search(r"S300 = (0x[0-9a-fp.+]+);", src).group(1))
+    s100 = float(re.search(r"S100 = ([0-9.]+);", src).group(1))
+    for thr, s0, gt in ((300.0, s300, True), (100.0, s100, False)):
+        s = s0
+        for _ in range(300):
+            s = math.nextafter(s, -math.inf)
+        for _ in range(600):
+            if gt:
+                assert (math.sqrt(s) > thr) == (s > s0), s.hex()
+            else:
+                assert (math.sqrt(s) < thr) == (s < s0), s.hex()
+            s = math.nextafter(s, math.inf)
