@@ -113,6 +113,9 @@ inline std::string build_kcfg(const at_config *cfg, uint64_t seed, int64_t env_i
     if (cfg->mode == AT_MODE_AGENT) { k.ctrl[0] = k.ctrl[1] = AT_CTRL_AGENT; }
     if (cfg->mode == AT_MODE_BOT_AGENT) { k.ctrl[0] = AT_CTRL_BOT; k.ctrl[1] = AT_CTRL_AGENT; }
     if (cfg->mode == AT_MODE_ARENA) { k.ctrl[0] = k.ctrl[1] = AT_CTRL_BOT; }
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j < n; ++j)
+            if (k.team[i] == k.team[j]) k.team_members[i] |= 1u << j;
     k.team_layout = cfg->mode == AT_MODE_TEAM;
     for (int i = 0; i < n; ++i)
         if (k.ctrl[i] == AT_CTRL_AGENT) k.agent_tank[k.n_agents++] = i;

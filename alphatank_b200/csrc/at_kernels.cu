@@ -64,47 +64,52 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
 // flushes the 32 x 32 tile: lane L takes row 4i + L/8 and the four columns 4*(L%8)..+3 (again conflict-free)
 // and writes them with one 16-byte store, so a warp store instruction covers four complete 128-byte row
 // chunks - full-sector, fully coalesced HBM writes from thread-per-env code.
+// Observation sink of one warp.  Every lane (= env) emits the same (virtual) column at the same time; the value
+// goes to tile[lane][(j + lane) & 31] (rotation => the 32 lanes hit 32 different banks).  After 32 columns the warp
+// flushes the 32 x 32 tile: for each env row, lane L stores column j0 + L (again conflict-free in shared
+// memory), i.e. one coalesced 128-byte run per store instruction.  For fixed maps the static wall / maze columns
+// are not emitted by the threads at all: virtual columns skip them (remap) and the warp copies them from the
+// block's template once per kernel.
 __device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t row_len, unsigned emit_mask, int lane,
-                                        int j0, int ncols, bool vec_ok) {
+                                        int j0, int ncols, int dyn_len, int head_len, int static_len, int obs_dim) {
     __syncwarp();
-    if (vec_ok) {
-        const int c4 = (lane & 7) * 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = 4 * i + (lane >> 3);
-            const float *src = tile + r * 32;
-            float4 v;
-            v.x = src[(c4 + 0 + r) & 31]; v.y = src[(c4 + 1 + r) & 31];
-            v.z = src[(c4 + 2 + r) & 31]; v.w = src[(c4 + 3 + r) & 31];
-            if (((emit_mask >> r) & 1u) && c4 < ncols)
-                *reinterpret_cast<float4 *>(gbase + (int64_t)r * row_len + j0 + c4) = v;
+    const int jv = j0 + lane;               // virtual column handled by this lane
+    const int r = jv / dyn_len, kk = jv - r * dyn_len;
+    const int gcol = r * obs_dim + (kk < head_len ? kk : kk + static_len);
+    if (lane < ncols) {
+        float *dst = gbase + gcol;
+        const float *src = tile;
+#pragma unroll 8
+        for (int rr = 0; rr < 32; ++rr) {
+            const float v = src[(lane + rr) & 31];
+            if ((emit_mask >> rr) & 1u) *dst = v;
+            dst += row_len;
+            src += 32;
         }
-    } else {
-        for (int r = 0; r < 32; ++r)
-            if (((emit_mask >> r) & 1u) && lane < ncols)
-                gbase[(int64_t)r * row_len + j0 + lane] = tile[r * 32 + ((lane + r) & 31)];
     }
     __syncwarp();
 }
 struct TileSink {  // kept in registers: flush takes everything by value
+    float *my;          // tile + lane * 32
     float *tile;
     float *gbase;       // obs row of the warp's lane 0
     int64_t row_len;    // R * D floats per env
     unsigned emit_mask; // lanes whose env gets an observation
     int lane, j;
-    bool vec_ok;        // row_len % 4 == 0 and 16-byte aligned base
+    int dyn_len, head_len, static_len, obs_dim;
     __device__ __forceinline__ void put(float v) {
-        tile[lane * 32 + ((j + lane) & 31)] = v;
+        my[(j + lane) & 31] = v;
         ++j;
-        if ((j & 31) == 0) tile_flush(tile, gbase, row_len, emit_mask, lane, j - 32, 32, vec_ok);
+        if ((j & 31) == 0) tile_flush(tile, gbase, row_len, emit_mask, lane, j - 32, 32, dyn_len, head_len, static_len, obs_dim);
     }
+    __device__ __forceinline__ void skip_static(const float *, int) {}  // written by the warp from the template
     __device__ __forceinline__ void finish() {
-        if (j & 31) tile_flush(tile, gbase, row_len, emit_mask, lane, j & ~31, j & 31, vec_ok);
+        if (j & 31) tile_flush(tile, gbase, row_len, emit_mask, lane, j & ~31, j & 31, dyn_len, head_len, static_len, obs_dim);
     }
 };
 
 template <bool IS_STEP>
-__global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c, const DevState st,
+__global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                  const int32_t *__restrict__ actions,
                                                  const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                  float *__restrict__ rewards, uint8_t *__restrict__ done,
@@ -162,14 +167,29 @@ __global__ void __launch_bounds__(BS) env_kernel(const __grid_constant__ KCfg c,
     const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
     if (emit_mask == 0u || c.rows == 0) return;
     const int64_t row_len = (int64_t)c.rows * c.obs_dim;
+    float *gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
+    const int static_len = c.map != 2 ? 4 * c.n_walls + CELLS : 0;
+    if (static_len) {  // fixed map: wall rectangles + maze grid straight from the template, coalesced
+        for (int rr = 0; rr < 32; ++rr) {
+            if (!((emit_mask >> rr) & 1u)) continue;
+            for (int r = 0; r < c.rows; ++r) {
+                float *dst = gbase + rr * row_len + (int64_t)r * c.obs_dim + c.off_walls;
+                for (int q = lane; q < static_len; q += 32) dst[q] = tmpl[q];
+            }
+        }
+    }
     TileSink out;
     out.tile = (float *)(smem + L.off_tile) + (size_t)warp * TILE_FLOATS;
-    out.gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
+    out.my = out.tile + lane * 32;
+    out.gbase = gbase;
     out.row_len = row_len;
     out.emit_mask = emit_mask;
     out.lane = lane;
     out.j = 0;
-    out.vec_ok = (row_len % 4 == 0) && ((((uintptr_t)obs) & 15u) == 0);
+    out.static_len = static_len;
+    out.head_len = c.off_walls;
+    out.dyn_len = c.obs_dim - static_len;
+    out.obs_dim = c.obs_dim;
     s.emit_rows(out);
     out.finish();
 }
@@ -231,9 +251,9 @@ __global__ void bfs_batch_kernel(const uint8_t *maze, const int32_t *query, int6
 __global__ void maze_kernel(uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *maze, uint32_t *ctr_out) {
     int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    uint32_t ctr = 0;
-    uint64_t lo, hi;
-    generate_maze_mask(seed, env_id_base + k, ctr, lo, hi);
+    const MazeOut mz = generate_maze_mask(seed, env_id_base + k, 0u);
+    const uint64_t lo = mz.lo, hi = mz.hi;
+    const uint32_t ctr = mz.ctr;
     for (int i = 0; i < CELLS; ++i) maze[k * CELLS + i] = (uint8_t)((i < 64 ? lo >> i : hi >> (i - 64)) & 1ull);
     if (ctr_out) ctr_out[k] = ctr;
 }

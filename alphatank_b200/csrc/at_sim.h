@@ -225,7 +225,11 @@ AT_HDN int bfs_first_step(uint64_t wall_lo, uint64_t wall_hi, int sr, int sc, in
 
 // ------------------------------------------------------------------ maze generation (env/maze.py:7-33)
 // Randomized Prim with the reference's list.pop(idx) semantics; draws come from the env's ATRNG stream.
-AT_HDN void generate_maze_mask(uint64_t seed, int64_t env_id, uint32_t &ctr, uint64_t &wall_lo, uint64_t &wall_hi) {
+struct MazeOut {
+    uint64_t lo, hi;
+    uint32_t ctr;
+};
+AT_HDN MazeOut generate_maze_mask(uint64_t seed, int64_t env_id, uint32_t ctr) {
     M128 wall = {~0ull, (1ull << (CELLS - 64)) - 1};
     uint16_t wl[128];  // packed (nx, ny, px, py), 4 bits each
     int nw = 0;
@@ -257,8 +261,7 @@ AT_HDN void generate_maze_mask(uint64_t seed, int64_t env_id, uint32_t &ctr, uin
         }
         if (!carved) break;
     }
-    wall_lo = wall.lo;
-    wall_hi = wall.hi;
+    return MazeOut{wall.lo, wall.hi, ctr};
 }
 
 // cells that are a wall or have one in their 8-neighbourhood: a tank whose centre lies in any other cell cannot
@@ -292,6 +295,13 @@ AT_HD int popc64(uint64_t v) {
     return __builtin_popcountll(v);
 #endif
 }
+AT_HD int ffs32(uint32_t v) {  // index of the lowest set bit (v != 0)
+#ifdef __CUDA_ARCH__
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
 // index of the k-th (0-based) set bit of a 128-bit mask
 AT_HD int select_bit(M128 m, int k) {
     uint64_t w = m.lo;
@@ -315,10 +325,12 @@ struct Sim {
     int tid;    // slot in the block working set
     uint32_t cnt, rng, tick, tstep, epstep, zones;
     uint64_t wlo, whi, nlo, nhi;
+    uint64_t tclo, tchi;   // cells under any alive tank's 30x24 rect (rebuilt per bullet pass; superset after kills)
+    uint32_t alive_bits;   // bit i: tank i alive (mirror of TPACK)
 
     AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0), nlo(0), nhi(0) {}
+          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), alive_bits(0) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
     AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
@@ -353,6 +365,7 @@ struct Sim {
     }
 
     AT_HD bool wall_at(int idx) const { return ((idx < 64 ? wlo >> idx : whi >> (idx - 64)) & 1ull) != 0; }
+    AT_HD bool tank_cell_at(int idx) const { return ((idx < 64 ? tclo >> idx : tchi >> (idx - 64)) & 1ull) != 0; }
     AT_HD bool near_at(int idx) const { return ((idx < 64 ? nlo >> idx : nhi >> (idx - 64)) & 1ull) != 0; }
 
     // first wall (row-major = reference list order, gaming_env.py:610-615) that a w x h pygame.Rect at
@@ -419,18 +432,19 @@ struct Sim {
         {
             const double u0 = st.udir[2 * ang], u1 = st.udir[2 * ang + 1];
             const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
-            for (int i = 0; i < c.n_tanks; ++i) {
-                if (!t_alive(i) || c.team[i] == oteam) continue;
+            for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // alive enemies
+                const int i = ffs32(bits);
                 const double tx = TX(i) - x, ty = TY(i) - y;
                 if (fabs(tx) > 301.0 || fabs(ty) > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
                 const double s2 = np_dot2(tx, ty, tx, ty);
                 if (s2 > S300) continue;                              // dist > BULLET_MAX_DISTANCE
-                const double dpa = (d0 * tx + d1 * ty) * fast_rsqrt(s2);
+                // cos > 0.9 <=> q > 0 and q^2 > 0.81 s2 ; cos < 0.1 <=> q <= 0 or q^2 < 0.01 s2   (q = d . t)
+                const double q = d0 * tx + d1 * ty, q2 = q * q, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
                 bool hi, lo;
-                if (fabs(dpa - 0.9) > 1e-9 && fabs(dpa - 0.1) > 1e-9) {
-                    hi = dpa > 0.9;
-                    lo = dpa < 0.1;
-                } else {  // also taken for dist == 0 (NaN): the reference's comparisons are then both false
+                if (s2 > 0.0 && !(q > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps))) {
+                    hi = q > 0.0 && q2 > a81;
+                    lo = !(q > 0.0 && q2 >= b01);
+                } else {  // within 1e-9 of a threshold, or dist == 0 (NaN: both comparisons false): reference sequence
                     const double dt = sqrt(s2);
                     const double dp = np_dot2(d0, d1, tx / dt, ty / dt);
                     hi = dp > 0.9;
@@ -442,7 +456,25 @@ struct Sim {
             }
         }
         bool nfx = fx, nfy = fy;
-        int cell = first_wall(ix, iy, 5, 5);
+        // one pass over the <= 4 cells under the 5x5 rect: first wall in list order + "is any tank rect here?"
+        int cell = -1;
+        bool near_tank = false;
+        {
+            int c0, c1, r0, r1;
+            if ((ix | iy) >= 0) {
+                c0 = ix / 70; c1 = imin(c0 + ((ix - 70 * c0 + 4) >= 70 ? 1 : 0), 10);
+                r0 = iy / 70; r1 = imin(r0 + ((iy - 70 * r0 + 4) >= 70 ? 1 : 0), 10);
+            } else {
+                c0 = imax(fdiv70(ix), 0); c1 = imin(fdiv70(ix + 4), 10);
+                r0 = imax(fdiv70(iy), 0); r1 = imin(fdiv70(iy + 4), 10);
+            }
+            for (int r = r1; r >= r0; --r)
+                for (int cc = c1; cc >= c0; --cc) {
+                    const int idx = r * 11 + cc;
+                    if (wall_at(idx)) cell = idx;  // descending scan: the last hit kept is the row-major first
+                    near_tank = near_tank || tank_cell_at(idx);
+                }
+        }
         if (cell >= 0) {  // sprite.py:66-82 (F12)
             bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
             if (bxh) nfx = !nfx;
@@ -452,15 +484,17 @@ struct Sim {
         x = nx;
         y = ny;
         ++dist;
-        for (int i = 0; i < c.n_tanks; ++i) {  // sprite.py:88-100
-            if (t_alive(i) && c.team[i] != oteam && rect5_hits_tank(ix, iy, i)) {
-                if (c.terminate_time == 0) TPACK(i) &= ~TP_ALIVE;
-                THITS(owner) += 1u;
-                THITS(i) += 1u << 16;
-                reward_by_bullets(owner, i);
-                return true;
+        if (near_tank)
+            for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // sprite.py:88-100
+                const int i = ffs32(bits);
+                if (rect5_hits_tank(ix, iy, i)) {
+                    if (c.terminate_time == 0) { TPACK(i) &= ~TP_ALIVE; alive_bits &= ~(1u << i); }
+                    THITS(owner) += 1u;
+                    THITS(i) += 1u << 16;
+                    reward_by_bullets(owner, i);
+                    return true;
+                }
             }
-        }
         if (bounces >= 6 || dist >= 300) {  // sprite.py:102-111
             if (!cleared && pcnt > 0) TREW(owner) -= st.pend[pcnt];
             return true;
@@ -473,10 +507,23 @@ struct Sim {
 
     // `for bullet in self.bullets[:]: bullet.move()` (gaming_env.py:71-72, 378-379): firing order, stable
     // compaction in place; also rebuilds the per-owner live counts and ranks (obs uses them).
-    AT_HDN void bullets_pass() {
+    AT_HD void bullets_pass() {
         const uint32_t n = cnt;
         uint32_t w = 0;
         for (int i = 0; i < c.n_tanks; ++i) TLIVE(i) = 0;
+        tclo = 0; tchi = 0;
+        if (n > 0)
+            for (uint32_t bits = alive_bits; bits; bits &= bits - 1) {  // cells under Rect(x-15, y-12, 30, 24)
+                const int i = ffs32(bits);
+                const int Tx = d2i(TX(i) - 15), Ty = d2i(TY(i) - 12);
+                const int c0 = imax(fdiv70(Tx), 0), c1 = imin(fdiv70(Tx + 29), 10);
+                const int r0 = imax(fdiv70(Ty), 0), r1 = imin(fdiv70(Ty + 23), 10);
+                for (int r = r0; r <= r1; ++r)
+                    for (int cc = c0; cc <= c1; ++cc) {
+                        const int idx = r * 11 + cc;
+                        if (idx < 64) tclo |= 1ull << idx; else tchi |= 1ull << (idx - 64);
+                    }
+            }
         for (uint32_t r = 0; r < n; ++r) {
             double x = st.bx[G(r)], y = st.by[G(r)];
             uint64_t m = st.bmeta[G(r)];
@@ -660,7 +707,7 @@ struct Sim {
 
     // BulletTrajectory.simulate_complete_trajectory -> will_hit_target (sprite.py:131-190), used by
     // SmartStrategyBot.check_line_of_sight (strategy_bot.py:58-73).
-    AT_HDN bool line_of_sight(int me) const {
+    AT_HD bool line_of_sight(int me) const {
         const int a = t_angle(me);
         const double cv = cosr(a), sv = sinr(a);
         double x = TX(me) + 10 * cv, y = TY(me) - 10 * sv, dx = cv, dy = -sv;
@@ -796,7 +843,7 @@ struct Sim {
         if (c.bot_type[i] != 0) { BF0(i) = 0.0; BF1(i) = 0.0; }
     }
 
-    AT_HDN void smart_action(int me, int act[3]) {  // strategy_bot.py:75-203
+    AT_HD void smart_action(int me, int act[3]) {  // strategy_bot.py:75-203
         uint32_t p = BPACK(me);
         int target = (int)(p & 15u) - 1;
         bool aiming = (p >> 4) & 1u, rot_pos = (p >> 5) & 1u, has_next = (p >> 12) & 1u;
@@ -954,7 +1001,7 @@ struct Sim {
         }
         return (double)t_angle(me);
     }
-    AT_HDN void dodge_action(int me, int act[3]) {  // simple_bots.py:331-357, 404-455
+    AT_HD void dodge_action(int me, int act[3]) {  // simple_bots.py:331-357, 404-455
         act[0] = 1; act[1] = 1; act[2] = 1;
         uint32_t p = BPACK(me);
         int timer = (int)(p & 31u), state = (int)((p >> 5) & 3u);
@@ -1016,8 +1063,12 @@ struct Sim {
     }
 
     // ---------------------------------------------------------------- reset (gaming_env.py:48-66, 509-520)
-    AT_HDN void env_reset() {
-        if (c.map == 2) { generate_maze_mask(c.seed, c.env_id_base + e, rng, wlo, whi); set_near(); }
+    AT_HD void env_reset() {
+        if (c.map == 2) {
+            const MazeOut mz = generate_maze_mask(c.seed, c.env_id_base + e, rng);
+            wlo = mz.lo; whi = mz.hi; rng = mz.ctr;
+            set_near();
+        }
         const M128 all = {~0ull, (1ull << (CELLS - 64)) - 1};
         const M128 freec = m_andn(all, M128{wlo, whi});
         const int n_empty = CELLS - c.n_walls;
@@ -1036,6 +1087,7 @@ struct Sim {
             BF1(i) = 0.0;
         }
         cnt = 0;
+        alive_bits = (1u << c.n_tanks) - 1u;
         for (int i = 0; i < c.n_tanks; ++i) {
             bool has_bot = (c.mode == AT_MODE_BOT_AGENT_ && i == 0) ||
                            ((c.mode == AT_MODE_TEAM_ || c.mode == AT_MODE_ARENA_) && c.ctrl[i] == 1);
@@ -1056,7 +1108,7 @@ struct Sim {
 
     // ---------------------------------------------------------------- one tick
     // GamingENV.step (gaming_env.py:68-386) / GamingTeamENV.step (gaming_env_multi.py:65-97)
-    AT_HDN void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
+    AT_HD void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
         int act[3];
         int arena[2][3];
         tick += 1;
@@ -1186,9 +1238,8 @@ struct Sim {
                 if (team) out.put(c.team[i] == c.team[t] ? 1.0f : 0.0f);
                 out.put(t_alive(i) ? 1.0f : 0.0f);
             }
-            if (c.map != 2) {  // fixed map: wall rectangles + maze grid from the block's template
-                const int ns = 4 * c.n_walls + CELLS;
-                for (int k = 0; k < ns; ++k) out.put(bm.tmpl[k]);
+            if (c.map != 2) {  // fixed map: the sink fills these columns from the block's template
+                out.skip_static(bm.tmpl, 4 * c.n_walls + CELLS);
             } else {
                 const M128 wm = {wlo, whi};
                 for (int k = 0; k < c.n_walls; ++k) {  // k-th wall in row-major order (uniform trip count)
@@ -1218,6 +1269,7 @@ struct Sim {
             TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
             TPACK(i) = st.tpack[G(i)]; THITS(i) = st.thits[G(i)]; TSHOT(i) = st.tshot[G(i)];
             if (c.ctrl[i] == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
+            if (TPACK(i) & TP_ALIVE) alive_bits |= 1u << i;
         }
     }
     AT_HD void set_near() { M128 nm = near_wall_mask(wlo, whi); nlo = nm.lo; nhi = nm.hi; }

@@ -35,6 +35,7 @@ struct KCfg {
     int32_t mode, n_tanks, map, terminate_time, buff_on, debuff_on, auto_reset;
     int32_t n_agents, rows, obs_dim, act_rows, n_walls, team_layout, n_zone_vals;
     int32_t team[MAX_TANKS], ctrl[MAX_TANKS], bot_type[MAX_TANKS], agent_tank[MAX_TANKS];
+    uint32_t team_members[MAX_TANKS];  // bit j set: tank j is on tank i's team (incl. i)
     // observation row layout (floats)
     int32_t self_len, off_ob, off_eb, eb_stride, off_et, et_len, off_walls, off_maze, off_zones, off_flags;
     int32_t row_bulk_ok;  // D*4 % 16 == 0: rows can leave shared memory as one bulk-async copy

@@ -36,6 +36,7 @@ struct DirectSink {  // the emulator writes column j of the env's observation ro
     float *row;
     int j;
     void put(float v) { row[j++] = v; }
+    void skip_static(const float *tmpl, int n) { for (int k = 0; k < n; ++k) row[j++] = tmpl[k]; }
 };
 
 static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
@@ -161,8 +162,9 @@ int em_bfs(const uint8_t *maze121, int sr, int sc, int gr, int gc, int *next_r, 
 }
 double em_jump_axis(double x, double d, int m) { return jump_axis(x, d, m); }
 void em_generate_maze(uint64_t seed, int64_t env_id, uint32_t *ctr, uint8_t *maze121) {
-    uint64_t lo, hi;
-    generate_maze_mask(seed, env_id, *ctr, lo, hi);
+    const MazeOut mz = generate_maze_mask(seed, env_id, *ctr);
+    const uint64_t lo = mz.lo, hi = mz.hi;
+    *ctr = mz.ctr;
     for (int i = 0; i < CELLS; ++i) maze121[i] = (uint8_t)((i < 64 ? lo >> i : hi >> (i - 64)) & 1ull);
 }
 }
