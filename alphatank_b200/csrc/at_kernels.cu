@@ -51,7 +51,8 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
     L.off_bpack = o; o += (size_t)n * BS * 4;
     L.off_tlive = o; o += (size_t)n * BS * 4;
     L.off_tshot = o; o += (size_t)n * BS * 4;
-    L.off_tmpl = o; o += (size_t)(4 * n_walls + CELLS) * 4;
+    o = (o + 15) & ~(size_t)15;
+    L.off_tmpl = o; o += (size_t)(4 * n_walls + CELLS + 4) * 4;  // +4: shifted so that it shares the rows' 16-byte phase
     o = (o + 15) & ~(size_t)15;
     L.off_tile = o; o += (size_t)(BS / 32) * TILE_FLOATS * 4;
     L.off_slot = o; o += (size_t)n * SLOTS_PER_TANK * BS;
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint32_t *)(smem + L.off_tlive);
     bm.tshot = (int32_t *)(smem + L.off_tshot);
     bm.slot_of = (uint8_t *)(smem + L.off_slot);
-    float *tmpl = (float *)(smem + L.off_tmpl);
+    float *tmpl = (float *)(smem + L.off_tmpl) + (c.off_walls & 3);  // tmpl[q] and obs column off_walls + q: same phase
     bm.tmpl = tmpl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -170,11 +171,23 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     float *gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
     const int static_len = c.map != 2 ? 4 * c.n_walls + CELLS : 0;
     if (static_len) {  // fixed map: wall rectangles + maze grid straight from the template, coalesced
+        const bool vec = (c.obs_dim % 4 == 0) && ((((uintptr_t)obs) & 15u) == 0);
+        const int head = vec ? ((4 - (c.off_walls & 3)) & 3) : static_len;  // scalars up to the first 16-byte boundary
+        const int nvec = vec ? (static_len - head) >> 2 : 0;
+        const int tail0 = head + 4 * nvec;
         for (int rr = 0; rr < 32; ++rr) {
             if (!((emit_mask >> rr) & 1u)) continue;
             for (int r = 0; r < c.rows; ++r) {
                 float *dst = gbase + rr * row_len + (int64_t)r * c.obs_dim + c.off_walls;
-                for (int q = lane; q < static_len; q += 32) dst[q] = tmpl[q];
+                if (vec) {
+                    if (lane < head) dst[lane] = tmpl[lane];
+                    const float4 *s4 = reinterpret_cast<const float4 *>(tmpl + head);
+                    float4 *d4 = reinterpret_cast<float4 *>(dst + head);
+                    for (int q = lane; q < nvec; q += 32) d4[q] = s4[q];
+                    if (tail0 + lane < static_len) dst[tail0 + lane] = tmpl[tail0 + lane];
+                } else {
+                    for (int q = lane; q < static_len; q += 32) dst[q] = tmpl[q];
+                }
             }
         }
     }

@@ -326,11 +326,12 @@ struct Sim {
     uint32_t cnt, rng, tick, tstep, epstep, zones;
     uint64_t wlo, whi, nlo, nhi;
     uint64_t tclo, tchi;   // cells under any alive tank's 30x24 rect (rebuilt per bullet pass; superset after kills)
+    uint64_t iclo, ichi;   // wall | tank cells: a 5x5 rect inside one uninteresting cell needs no further test
     uint32_t alive_bits;   // bit i: tank i alive (mirror of TPACK)
 
     AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), alive_bits(0) {}
+          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
     AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
@@ -424,7 +425,6 @@ struct Sim {
         double dx = fx ? -cv : cv, dy = fy ? sv : -sv;
         const double nx = x + dx, ny = y + dy;
         const int ix = d2i(nx), iy = d2i(ny);
-        const int oteam = c.team[owner];
         // update_reward_logic on the pre-move position (sprite.py:27-57).  Same decisions as the reference's
         // norm / divide / dot sequence, reached cheaply: the unit direction comes from a table, distances are
         // compared through their squares (exact, see S300 / S100), and the cosine is first evaluated with fast
@@ -468,12 +468,15 @@ struct Sim {
                 c0 = imax(fdiv70(ix), 0); c1 = imin(fdiv70(ix + 4), 10);
                 r0 = imax(fdiv70(iy), 0); r1 = imin(fdiv70(iy + 4), 10);
             }
-            for (int r = r1; r >= r0; --r)
-                for (int cc = c1; cc >= c0; --cc) {
-                    const int idx = r * 11 + cc;
-                    if (wall_at(idx)) cell = idx;  // descending scan: the last hit kept is the row-major first
-                    near_tank = near_tank || tank_cell_at(idx);
-                }
+            const int idx0 = r0 * 11 + c0;
+            const bool quiet = c0 == c1 && r0 == r1 && !(((idx0 < 64 ? iclo >> idx0 : ichi >> (idx0 - 64)) & 1ull) != 0);
+            if (!quiet)
+                for (int r = r1; r >= r0; --r)
+                    for (int cc = c1; cc >= c0; --cc) {
+                        const int idx = r * 11 + cc;
+                        if (wall_at(idx)) cell = idx;  // descending scan: the last hit kept is the row-major first
+                        near_tank = near_tank || tank_cell_at(idx);
+                    }
         }
         if (cell >= 0) {  // sprite.py:66-82 (F12)
             bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
@@ -524,6 +527,7 @@ struct Sim {
                         if (idx < 64) tclo |= 1ull << idx; else tchi |= 1ull << (idx - 64);
                     }
             }
+        iclo = tclo | wlo; ichi = tchi | whi;
         for (uint32_t r = 0; r < n; ++r) {
             double x = st.bx[G(r)], y = st.by[G(r)];
             uint64_t m = st.bmeta[G(r)];
@@ -879,20 +883,23 @@ struct Sim {
             if (target >= 0) aiming = true;
         }
         if (aiming && target >= 0) {
-            if (line_of_sight(me)) {
-                double tx = TX(target), ty = TY(target);
-                int rotation = aim_from_diff(angle_diff_to(me, tx, ty), 10);
+            // one aim computation for both branches (strategy_bot.py:141-175): at the target when there is a line
+            // of sight, else at the centre of the next BFS cell
+            const bool los = line_of_sight(me);
+            if (los || has_next) {
+                const double px = los ? TX(target) : next_c * GRID + (GRID / 2);
+                const double py = los ? TY(target) : next_r * GRID + (GRID / 2);
+                const int rotation = aim_from_diff(angle_diff_to(me, px, py), 10);
                 if (rotation != 0) act[0] = rotation > 0 ? 2 : 0;
-                double dx = tx - TX(me), dy = ty - TY(me);
-                double d = sqrt(dx * dx + dy * dy);
-                if (d > 200) act[1] = 2;
-                else if (d < 20) act[1] = 0;
-                if (rotation == 0) act[2] = 1;
-            } else if (has_next) {
-                double tx = next_c * GRID + (GRID / 2), ty = next_r * GRID + (GRID / 2);
-                int rotation = aim_from_diff(angle_diff_to(me, tx, ty), 10);
-                if (rotation != 0) act[0] = rotation > 0 ? 2 : 0;
-                act[1] = rotation == 0 ? 2 : 1;
+                if (los) {
+                    const double dx = px - TX(me), dy = py - TY(me);
+                    const double d = sqrt(dx * dx + dy * dy);
+                    if (d > 200) act[1] = 2;
+                    else if (d < 20) act[1] = 0;
+                    if (rotation == 0) act[2] = 1;
+                } else {
+                    act[1] = rotation == 0 ? 2 : 1;
+                }
             }
         }
         if (stuck > 20) {
