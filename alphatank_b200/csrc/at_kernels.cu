@@ -1,15 +1,16 @@
 // at_kernels.cu - sm_100a kernels and the C ABI (include/alphatank_b200.h) of the batched alphaTank step.
 //
-// One fused kernel per tick (env_kernel<true>):
-//   phase A  one thread per env.  Tanks / bot FSMs of the block's 64 envs live in shared memory
-//            ([field][tank][thread], conflict-free), bullets stay in HBM as [slot][env] columns (every
-//            warp access is a contiguous run; the two advection passes, the dodge-reward scans and the
-//            obs reads hit L1 after the first touch).  Sequential per-env semantics (firing order, tank
-//            order) are trivially exact.  Rewards / done are written here; done envs are reset in place.
-//   phase B  each warp assembles the observation rows of its 32 envs in a shared-memory staging buffer
-//            (static wall / maze columns are written once per kernel for fixed maps) and ships every row
-//            with one bulk-async (TMA) shared->global copy, double buffered; rows whose byte length is not
-//            a multiple of 16 fall back to coalesced lane-strided stores.
+// One fused kernel per tick (env_kernel<true>), one thread per env in both phases:
+//   phase A  simulation.  Tanks / bot FSMs of the block's 64 envs live in shared memory ([field][tank][thread],
+//            conflict-free); bullets stay in HBM as [slot][env] columns (every warp access is a contiguous run; the
+//            two advection passes, the dodge-reward scans and the obs reads hit L1/L2 after the first touch).
+//            Sequential per-env semantics (firing order, tank order) are trivially exact.  Rewards / done are
+//            written here; done envs are reset in place.
+//   phase B  observation rows.  Each thread emits its env's row values in layout order (uniform control flow, all
+//            lanes busy); the warp transposes 32 envs x 32 columns through a rotated, bank-conflict-free
+//            shared-memory tile into coalesced 128-byte row-chunk stores.  For fixed maps the 281 static wall / maze
+//            columns of every row are not recomputed: they sit once per block in shared memory and each thread
+//            ships them into its rows with one bulk-async (TMA, SASS UBLKCP) copy per row.
 // The step is HBM-bound integer / fp64 work: no tensor cores anywhere.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -59,6 +60,14 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
+
+__device__ __forceinline__ void bulk_store(float *gdst, const float *ssrc, uint32_t bytes) {  // TMA 1-D bulk copy
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;\n" ::"l"(gdst), "r"(s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
 // Observation sink of one warp.  Every lane (= env) emits the same column j at the same time; the value goes
 // to tile[lane][(j + lane) & 31] (rotation => the 32 lanes hit 32 different banks).  After 32 columns the warp
@@ -131,8 +140,10 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 722; i += BS) bm.trig[i] = st.trig[i];
-    if (c.map != 2)
+    if (c.map != 2) {
         for (int i = tid; i < 4 * c.n_walls + CELLS; i += BS) tmpl[i] = g_tmpl[i];
+        fence_async_smem();  // the template is later read by bulk-async copies
+    }
     for (int i = 0; i < c.n_tanks; ++i) {  // lanes without an env still walk the emitter: give them inert data
         bm.tlive[i * BS + tid] = 0u;
         bm.tpack[i * BS + tid] = 0u;
@@ -170,22 +181,30 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     const int64_t row_len = (int64_t)c.rows * c.obs_dim;
     float *gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
     const int static_len = c.map != 2 ? 4 * c.n_walls + CELLS : 0;
-    if (static_len) {  // fixed map: wall rectangles + maze grid straight from the template, coalesced
+    bool bulk_pending = false;
+    if (static_len) {
+        // Fixed map: the wall rectangles + maze grid of every row are the block's shared-memory template.  When rows
+        // are 16-byte phased, each env's thread ships the aligned body of its rows with ONE bulk-async (TMA) copy per
+        // row and the few unaligned edge floats with plain stores; otherwise the warp copies them cooperatively.
         const bool vec = (c.obs_dim % 4 == 0) && ((((uintptr_t)obs) & 15u) == 0);
-        const int head = vec ? ((4 - (c.off_walls & 3)) & 3) : static_len;  // scalars up to the first 16-byte boundary
-        const int nvec = vec ? (static_len - head) >> 2 : 0;
-        const int tail0 = head + 4 * nvec;
-        for (int rr = 0; rr < 32; ++rr) {
-            if (!((emit_mask >> rr) & 1u)) continue;
-            for (int r = 0; r < c.rows; ++r) {
-                float *dst = gbase + rr * row_len + (int64_t)r * c.obs_dim + c.off_walls;
-                if (vec) {
-                    if (lane < head) dst[lane] = tmpl[lane];
-                    const float4 *s4 = reinterpret_cast<const float4 *>(tmpl + head);
-                    float4 *d4 = reinterpret_cast<float4 *>(dst + head);
-                    for (int q = lane; q < nvec; q += 32) d4[q] = s4[q];
-                    if (tail0 + lane < static_len) dst[tail0 + lane] = tmpl[tail0 + lane];
-                } else {
+        if (vec) {
+            const int head = (4 - (c.off_walls & 3)) & 3;
+            const int nbody = (static_len - head) & ~3;
+            if (emit) {
+                for (int r = 0; r < c.rows; ++r) {
+                    float *dst = gbase + lane * row_len + (int64_t)r * c.obs_dim + c.off_walls;
+                    bulk_store(dst + head, tmpl + head, (uint32_t)nbody * 4u);
+                    for (int q = 0; q < head; ++q) dst[q] = tmpl[q];
+                    for (int q = head + nbody; q < static_len; ++q) dst[q] = tmpl[q];
+                }
+                bulk_commit();
+                bulk_pending = true;
+            }
+        } else {
+            for (int rr = 0; rr < 32; ++rr) {
+                if (!((emit_mask >> rr) & 1u)) continue;
+                for (int r = 0; r < c.rows; ++r) {
+                    float *dst = gbase + rr * row_len + (int64_t)r * c.obs_dim + c.off_walls;
                     for (int q = lane; q < static_len; q += 32) dst[q] = tmpl[q];
                 }
             }
@@ -205,6 +224,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     out.obs_dim = c.obs_dim;
     s.emit_rows(out);
     out.finish();
+    if (bulk_pending) bulk_wait_read_all();  // shared memory must outlive the copies' reads
 }
 
 __global__ void gather_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
