@@ -70,10 +70,12 @@ inline void build_map(int map, uint64_t *lo, uint64_t *hi, int *n_walls) {
 
 struct HostLuts {
     std::vector<double> trig, corn, pend, udir;
+    std::vector<uint8_t> udelta;
+    bool udelta_ok = true;
 };
 // built with the host libm exactly as CPython's math module / pygame would
 inline void build_luts(HostLuts &l) {
-    l.trig.resize(722); l.corn.resize(361 * 4); l.pend.resize(PEND_LUT); l.udir.resize(722);
+    l.trig.resize(722); l.corn.resize(361 * 4); l.pend.resize(PEND_LUT); l.udir.resize(722); l.udelta.resize(364);
     for (int a = 0; a <= 360; ++a) {
         double rad = (double)a * (M_PI / 180.0);  // math.radians
         l.trig[2 * a] = cos(rad);
@@ -85,6 +87,13 @@ inline void build_luts(HostLuts &l) {
         const double nrm = sqrt(fma(dy, dy, dx * dx));
         l.udir[2 * a] = dx / nrm;
         l.udir[2 * a + 1] = dy / nrm;
+        // the normalised direction is within one ulp of (dx, dy): keep only the two ulp offsets (-1, 0, +1)
+        int64_t b0, b1, v0, v1;
+        memcpy(&b0, &l.udir[2 * a], 8); memcpy(&b1, &l.udir[2 * a + 1], 8);
+        memcpy(&v0, &dx, 8); memcpy(&v1, &dy, 8);
+        const int64_t d0 = b0 - v0, d1 = b1 - v1;
+        l.udelta_ok = l.udelta_ok && d0 >= -1 && d0 <= 1 && d1 >= -1 && d1 <= 1;
+        l.udelta[a] = (uint8_t)((d0 + 1) | ((d1 + 1) << 2));
     }
     double acc = 0.0;
     for (int i = 0; i < PEND_LUT; ++i) { l.pend[i] = acc; acc = acc + 0.02; }  // pending += BULLET_AWAY_PENALTY
@@ -117,8 +126,12 @@ inline std::string build_kcfg(const at_config *cfg, uint64_t seed, int64_t env_i
         for (int j = 0; j < n; ++j)
             if (k.team[i] == k.team[j]) k.team_members[i] |= 1u << j;
     k.team_layout = cfg->mode == AT_MODE_TEAM;
-    for (int i = 0; i < n; ++i)
+    int nb = 0;
+    for (int i = 0; i < n; ++i) {
         if (k.ctrl[i] == AT_CTRL_AGENT) k.agent_tank[k.n_agents++] = i;
+        else { k.bot_ord[i] = nb; k.bot_tank[nb++] = i; }
+    }
+    k.n_bots = nb;
     k.rows = k.team_layout ? k.n_agents : n;
     k.act_rows = k.team_layout ? k.n_agents : (cfg->mode == AT_MODE_ARENA ? 0 : n);
     build_map(cfg->map, &k.wall_lo, &k.wall_hi, &k.n_walls);
@@ -155,7 +168,7 @@ inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     L.o_tpack = take(4 * N * n); L.o_thits = take(4 * N * n); L.o_tshot = take(4 * N * n); L.o_bpack = take(4 * N * n);
     L.o_bf0 = take(8 * N * n); L.o_bf1 = take(8 * N * n); L.o_bx = take(8 * N * slots); L.o_by = take(8 * N * slots);
     L.o_bm = take(8 * N * slots); L.o_trig = take(722 * 8); L.o_corn = take(361 * 4 * 8); L.o_pend = take(PEND_LUT * 8);
-    L.o_udir = take(722 * 8);
+    L.o_udir = take(364);
     L.o_bfs = take(CELLS * CELLS * 2);
     L.o_tmpl = take((4 * 72 + CELLS) * 4);
     L.o_act = take(4 * N * 3 * (k.act_rows ? k.act_rows : 1)); L.o_rw = take(4 * N * (k.rows ? k.rows : 1));
@@ -175,7 +188,7 @@ inline void bind_state(DevState &st, char *b, const ArenaLayout &L, int64_t N) {
     st.bx = (double *)(b + L.o_bx); st.by = (double *)(b + L.o_by); st.bmeta = (uint64_t *)(b + L.o_bm);
     st.trig = (const double *)(b + L.o_trig); st.corn = (const double *)(b + L.o_corn);
     st.pend = (const double *)(b + L.o_pend);
-    st.udir = (const double *)(b + L.o_udir);
+    st.udelta = (const uint8_t *)(b + L.o_udir);
     st.bfs_tab = nullptr;  // set by the owner for fixed maps (at_sim.h fill_bfs_table)
 }
 

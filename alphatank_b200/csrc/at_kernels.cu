@@ -34,10 +34,11 @@ namespace {
 struct SmemLayout {
     int n;
     size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_thits, off_bpack, off_tlive,
-        off_tshot, off_tmpl, off_tile, off_slot, total;
+        off_tshot, off_tmpl, off_tile, off_slot, off_udelta, total;
 };
 constexpr int TILE_FLOATS = 32 * 32;  // per warp: 32 envs x 32 observation columns
-__host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
+__host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots) {
+    const int nb = n_bots > 0 ? n_bots : 1;
     SmemLayout L;
     L.n = n;
     size_t o = 0;
@@ -45,11 +46,11 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
     L.off_tx = o; o += (size_t)n * BS * 8;
     L.off_ty = o; o += (size_t)n * BS * 8;
     L.off_trew = o; o += (size_t)n * BS * 8;
-    L.off_bf0 = o; o += (size_t)n * BS * 8;
-    L.off_bf1 = o; o += (size_t)n * BS * 8;
+    L.off_bf0 = o; o += (size_t)nb * BS * 8;
+    L.off_bf1 = o; o += (size_t)nb * BS * 8;
     L.off_tpack = o; o += (size_t)n * BS * 4;
     L.off_thits = o; o += (size_t)n * BS * 4;
-    L.off_bpack = o; o += (size_t)n * BS * 4;
+    L.off_bpack = o; o += (size_t)nb * BS * 4;
     L.off_tlive = o; o += (size_t)n * BS * 4;
     L.off_tshot = o; o += (size_t)n * BS * 4;
     o = (o + 15) & ~(size_t)15;
@@ -57,6 +58,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls) {
     o = (o + 15) & ~(size_t)15;
     L.off_tile = o; o += (size_t)(BS / 32) * TILE_FLOATS * 4;
     L.off_slot = o; o += (size_t)n * SLOTS_PER_TANK * BS;
+    L.off_udelta = o; o += 368;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -125,7 +127,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
                                                  float *__restrict__ rewards, uint8_t *__restrict__ done,
                                                  const float *__restrict__ g_tmpl) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(c.n_tanks, c.n_walls);
+    const SmemLayout L = smem_layout(c.n_tanks, c.n_walls, c.n_bots);
     BlockMem bm;
     bm.trig = (double *)(smem + L.off_trig);
     bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
@@ -135,11 +137,14 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint32_t *)(smem + L.off_tlive);
     bm.tshot = (int32_t *)(smem + L.off_tshot);
     bm.slot_of = (uint8_t *)(smem + L.off_slot);
+    uint8_t *udl = (uint8_t *)(smem + L.off_udelta);
+    bm.udelta = udl;
     float *tmpl = (float *)(smem + L.off_tmpl) + (c.off_walls & 3);  // tmpl[q] and obs column off_walls + q: same phase
     bm.tmpl = tmpl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < 722; i += BS) bm.trig[i] = st.trig[i];
+    for (int i = tid; i < 361; i += BS) udl[i] = st.udelta[i];
     if (c.map != 2) {
         for (int i = tid; i < 4 * c.n_walls + CELLS; i += BS) tmpl[i] = g_tmpl[i];
         fence_async_smem();  // the template is later read by bulk-async copies
@@ -370,6 +375,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     env->n_envs = n_envs;
     env->launches = 0;
     build_luts(env->luts);
+    if (!env->luts.udelta_ok) { delete env; return fail(AT_ERR_CUDA, "at_create: host libm gives a normalised direction more than 1 ulp from (cos, -sin)"); }
     const ArenaLayout L = arena_layout(k, n_envs);
     env->arena_bytes = L.bytes;
     if (cudaMalloc(&env->arena, L.bytes) != cudaSuccess) {
@@ -387,7 +393,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaMemcpy(b + L.o_trig, env->luts.trig.data(), 722 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(b + L.o_corn, env->luts.corn.data(), 361 * 4 * 8, cudaMemcpyHostToDevice);
     cudaMemcpy(b + L.o_pend, env->luts.pend.data(), PEND_LUT * 8, cudaMemcpyHostToDevice);
-    cudaMemcpy(b + L.o_udir, env->luts.udir.data(), 722 * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(b + L.o_udir, env->luts.udelta.data(), 364, cudaMemcpyHostToDevice);
     if (k.map != AT_MAP_MAZE) {  // fixed map: path-finding becomes one table lookup
         std::vector<uint16_t> tab((size_t)CELLS * CELLS);
         fill_bfs_table(k.wall_lo, k.wall_hi, tab.data());
@@ -401,7 +407,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         fill_static_template(k.wall_lo, k.wall_hi, tm.data());
         cudaMemcpy(b + L.o_tmpl, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice);
     }
-    env->smem_bytes = smem_layout(k.n_tanks, k.n_walls).total;
+    env->smem_bytes = smem_layout(k.n_tanks, k.n_walls, k.n_bots).total;
     cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     // GamingENV.__init__ -> self.reset() (gaming_env.py:43): the constructor's own reset consumes draws

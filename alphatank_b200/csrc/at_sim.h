@@ -76,6 +76,14 @@ AT_HD double jump_axis(double x, double d, int m) {
     for (int j = 0; j < m; ++j) x = x + d;
     return x;
 }
+template <class T>
+AT_HD T ldg(const T *p) {  // read-only tables: lets the compiler hoist / batch the loads
+#ifdef __CUDA_ARCH__
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
 AT_HD int fdiv70(int v) { return v >= 0 ? v / 70 : -((69 - v) / 70); }
 AT_HD int imin(int a, int b) { return a < b ? a : b; }
 AT_HD int imax(int a, int b) { return a > b ? a : b; }
@@ -340,9 +348,10 @@ struct Sim {
     AT_HD uint32_t &THITS(int i) const { return bm.thits[i * BS + tid]; }
     AT_HD uint32_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
     AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * BS + tid]; }
-    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[i * BS + tid]; }
-    AT_HD double &BF0(int i) const { return bm.bf0[i * BS + tid]; }
-    AT_HD double &BF1(int i) const { return bm.bf1[i * BS + tid]; }
+    // bot FSM columns exist only for bot tanks (bot_ord: ordinal among the bots)
+    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[c.bot_ord[i] * BS + tid]; }
+    AT_HD double &BF0(int i) const { return bm.bf0[c.bot_ord[i] * BS + tid]; }
+    AT_HD double &BF1(int i) const { return bm.bf1[c.bot_ord[i] * BS + tid]; }
     AT_HD int64_t G(int slot) const { return (int64_t)slot * st.N + e; }
 
     AT_HD int t_angle(int i) const { return (int)(TPACK(i) & 511u); }
@@ -354,6 +363,12 @@ struct Sim {
     AT_HD void set_speed(int i, int sp) {
         uint32_t code = sp == 0 ? 0u : (sp == 10 ? 1u : (sp == -10 ? 2u : 3u));
         TPACK(i) = (TPACK(i) & ~(3u << 9)) | (code << 9);
+    }
+    // bullet_dir / np.linalg.norm(bullet_dir) of the firing direction (cos a, -sin a): one ulp offset per component
+    AT_HD void unit_dir(int a, double &u0, double &u1) const {
+        const uint32_t dl = bm.udelta[a];
+        u0 = bits_d(d_bits(bm.trig[2 * a]) + (uint64_t)(int64_t)((int)(dl & 3u) - 1));
+        u1 = bits_d(d_bits(-bm.trig[2 * a + 1]) + (uint64_t)(int64_t)((int)((dl >> 2) & 3u) - 1));
     }
     AT_HD double cosr(int a) const { return bm.trig[2 * a]; }
     AT_HD double sinr(int a) const { return bm.trig[2 * a + 1]; }
@@ -430,7 +445,8 @@ struct Sim {
         // compared through their squares (exact, see S300 / S100), and the cosine is first evaluated with fast
         // arithmetic - only when it lands within 1e-9 of a threshold is the reference's exact sequence run.
         {
-            const double u0 = st.udir[2 * ang], u1 = st.udir[2 * ang + 1];
+            double u0, u1;
+            unit_dir(ang, u0, u1);
             const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
             for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // alive enemies
                 const int i = ffs32(bits);
@@ -499,7 +515,7 @@ struct Sim {
                 }
             }
         if (bounces >= 6 || dist >= 300) {  // sprite.py:102-111
-            if (!cleared && pcnt > 0) TREW(owner) -= st.pend[pcnt];
+            if (!cleared && pcnt > 0) TREW(owner) -= ldg(st.pend + pcnt);
             return true;
         }
         m = (uint64_t)owner | ((uint64_t)ang << BM_ANGLE) | ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) |
@@ -528,9 +544,15 @@ struct Sim {
                     }
             }
         iclo = tclo | wlo; ichi = tchi | whi;
+        // software pipelining: the next bullet's record is requested before the current one is processed (the
+        // columns come from L2/HBM - shared memory leaves the SM almost no L1 - and a move is ~300 instructions)
+        double nx_ = 0.0, ny_ = 0.0;
+        uint64_t nm_ = 0;
+        if (n > 0) { nx_ = st.bx[G(0)]; ny_ = st.by[G(0)]; nm_ = st.bmeta[G(0)]; }
         for (uint32_t r = 0; r < n; ++r) {
-            double x = st.bx[G(r)], y = st.by[G(r)];
-            uint64_t m = st.bmeta[G(r)];
+            double x = nx_, y = ny_;
+            uint64_t m = nm_;
+            if (r + 1 < n) { nx_ = st.bx[G(r + 1)]; ny_ = st.by[G(r + 1)]; nm_ = st.bmeta[G(r + 1)]; }
             if (!bullet_move(x, y, m)) {
                 const int ow = (int)(m & 15u);
                 uint32_t rank = TLIVE(ow)++;
@@ -602,7 +624,8 @@ struct Sim {
             const double ey_ = my - st.by[G(r)];
             if (!(np_dot2(ex_, ey_, ex_, ey_) < S100)) continue;       // `distance >= 100: continue` (sprite.py:508)
             const int ba = (int)((m >> BM_ANGLE) & 511u);
-            const double u0 = st.udir[2 * ba], u1 = st.udir[2 * ba + 1];
+            double u0, u1;
+            unit_dir(ba, u0, u1);
             const double d0 = ((m >> BM_FLIPX) & 1u) ? -u0 : u0, d1 = ((m >> BM_FLIPY) & 1u) ? -u1 : u1;
             double proj = np_dot2(tvx, tvy, -d1, d0);
             reward += fabs(proj) * 0.01;
@@ -617,7 +640,7 @@ struct Sim {
             if (cx >= 0 && cy >= 0 && cx < 770 && cy < 770 && !near_at((cy / 70) * 11 + cx / 70)) return false;
         }
         const double *co = st.corn + 4 * a;
-        const double o0x = co[0], o0y = co[1], o1x = co[2], o1y = co[3];
+        const double o0x = ldg(co), o0y = ldg(co + 1), o1x = ldg(co + 2), o1y = ldg(co + 3);
         double kx[4] = {nx + o0x, nx + o1x, nx - o0x, nx - o1x};
         double ky[4] = {ny + o0y, ny + o1y, ny - o0y, ny - o1y};
         double mnx = kx[0], mxx = kx[0], mny = ky[0], mxy = ky[0];
@@ -860,7 +883,7 @@ struct Sim {
             int nr, nc, len;
             const int sr = d2i(TY(me)) / 70, sc = d2i(TX(me)) / 70, gr = d2i(TY(target)) / 70, gc = d2i(TX(target)) / 70;
             if (st.bfs_tab != nullptr && (unsigned)sr < 11u && (unsigned)sc < 11u && (unsigned)gr < 11u && (unsigned)gc < 11u) {
-                const uint32_t ent = st.bfs_tab[(sr * 11 + sc) * CELLS + gr * 11 + gc];  // fixed map: all-pairs table
+                const uint32_t ent = ldg(st.bfs_tab + (sr * 11 + sc) * CELLS + gr * 11 + gc);  // fixed map: all-pairs table
                 const int dir = (int)(ent >> 8);
                 len = (int)(ent & 255u);
                 nr = sr + (dir == 0 ? -1 : (dir == 1 ? 1 : 0));
@@ -1089,9 +1112,7 @@ struct Sim {
             THITS(i) = 0u;
             TLIVE(i) = 0u;
             TSHOT(i) = 0;
-            BPACK(i) = 0u;
-            BF0(i) = 0.0;
-            BF1(i) = 0.0;
+            if (c.ctrl[i] == 1) { BPACK(i) = 0u; BF0(i) = 0.0; BF1(i) = 0.0; }
         }
         cnt = 0;
         alive_bits = (1u << c.n_tanks) - 1u;
@@ -1114,34 +1135,41 @@ struct Sim {
     }
 
     // ---------------------------------------------------------------- one tick
-    // GamingENV.step (gaming_env.py:68-386) / GamingTeamENV.step (gaming_env_multi.py:65-97)
+    // GamingENV.step (gaming_env.py:68-386) / GamingTeamENV.step (gaming_env_multi.py:65-97).
+    // Written as a 4-stage loop so that bullets_pass, bot_action and apply_action each have exactly ONE call
+    // site (they are force-inlined; duplicating them made the kernel 700 KB of SASS and instruction-fetch bound):
+    //   stage 0  arena only: both bots decide on the pre-tick state (bot_arena.py:51-52)
+    //   stage 1  bullets pass 1      stage 2  controllers in the reference's order      stage 3  bullets pass 2
     AT_HD void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
-        int act[3];
-        int arena[2][3];
+        int acts[MAX_TANKS][3];
         tick += 1;
-        if (c.mode == AT_MODE_ARENA_)  // bot_arena.py:51-52
-            for (int i = 0; i < 2; ++i) bot_action(i, arena[i]);
         if (c.mode != AT_MODE_TEAM_) epstep += 1;
-        bullets_pass();
-        if (c.mode == AT_MODE_BOT_AGENT_) {  // gaming_env.py:139-199 (F14, F15)
-            bot_action(0, act);
-            if (!(rng_unit53() < c.weakness)) { act[0] = 1; act[1] = 1; act[2] = 0; }
-            apply_action(0, act[0], act[1], act[2], 2, 0, 0);
-            apply_action(1, a[3], a[4], a[5], 0, 2, 1);
-        } else if (c.mode == AT_MODE_TEAM_) {  // controller.py:81-113
-            for (int k = 0; k < c.n_agents; ++k)
-                apply_action(c.agent_tank[k], a[3 * k], a[3 * k + 1], a[3 * k + 2], 2, 0, 0);
-            for (int i = 0; i < c.n_tanks; ++i)
-                if (c.ctrl[i] == 1) {
-                    bot_action(i, act);
-                    apply_action(i, act[0], act[1], act[2], 2, 0, 0);
+        const bool arena = c.mode == AT_MODE_ARENA_, team = c.mode == AT_MODE_TEAM_, botagent = c.mode == AT_MODE_BOT_AGENT_;
+        for (int stage = arena ? 0 : 1; stage < 4; ++stage) {
+            if (stage & 1) {
+                bullets_pass();
+                continue;
+            }
+            // acting order: team mode = agent tanks in config order, then bot tanks in config order
+            // (controller.py:81-113); every 1v1 mode = tank 0, tank 1
+            for (int k = 0; k < c.n_tanks; ++k) {
+                int i = k;
+                if (team) i = k < c.n_agents ? c.agent_tank[k] : c.bot_tank[k - c.n_agents];
+                const bool is_bot = c.ctrl[i] == 1;
+                if (is_bot && (stage == 0 || !arena)) {
+                    bot_action(i, acts[i]);
+                    if (botagent && !(rng_unit53() < c.weakness)) { acts[i][0] = 1; acts[i][1] = 1; acts[i][2] = 0; }
                 }
-        } else if (c.mode == AT_MODE_ARENA_) {
-            for (int i = 0; i < 2; ++i) apply_action(i, arena[i][0], arena[i][1], arena[i][2], 2, 0, 0);
-        } else {  // "AI only" gaming_env.py:309-374
-            for (int i = 0; i < c.n_tanks; ++i) apply_action(i, a[3 * i], a[3 * i + 1], a[3 * i + 2], 2, 0, 0);
+                if (stage == 0) continue;
+                if (!is_bot) {
+                    const int row = team ? k : i;
+                    acts[i][0] = a[3 * row]; acts[i][1] = a[3 * row + 1]; acts[i][2] = a[3 * row + 2];
+                }
+                // bot_agent's agent tank uses the swapped movement table and creeps on "stop" (F14)
+                const bool swapped = botagent && i == 1;
+                apply_action(i, acts[i][0], acts[i][1], acts[i][2], swapped ? 0 : 2, swapped ? 2 : 0, swapped ? 1 : 0);
+            }
         }
-        bullets_pass();
     }
 
     // wrapper step (gym_env.py:73-103, 186-200; gym_env_multi.py:202-223, 307-326).  Returns done.
@@ -1192,8 +1220,9 @@ struct Sim {
         const int a = t_angle(i);
         const double sp = (double)t_speed(i);
         const double *co = st.corn + 4 * a;
-        out.put((float)(x + co[0])); out.put((float)(y + co[1])); out.put((float)(x + co[2])); out.put((float)(y + co[3]));
-        out.put((float)(x - co[0])); out.put((float)(y - co[1])); out.put((float)(x - co[2])); out.put((float)(y - co[3]));
+        const double c0 = ldg(co), c1 = ldg(co + 1), c2 = ldg(co + 2), c3 = ldg(co + 3);
+        out.put((float)(x + c0)); out.put((float)(y + c1)); out.put((float)(x + c2)); out.put((float)(y + c3));
+        out.put((float)(x - c0)); out.put((float)(y - c1)); out.put((float)(x - c2)); out.put((float)(y - c3));
         out.put((float)(sp * cosr(a)));
         out.put((float)(sp * sinr(a)));
         out.put((TPACK(i) & TP_HW) ? 1.0f : 0.0f);

@@ -35,6 +35,9 @@ struct KCfg {
     int32_t mode, n_tanks, map, terminate_time, buff_on, debuff_on, auto_reset;
     int32_t n_agents, rows, obs_dim, act_rows, n_walls, team_layout, n_zone_vals;
     int32_t team[MAX_TANKS], ctrl[MAX_TANKS], bot_type[MAX_TANKS], agent_tank[MAX_TANKS];
+    int32_t bot_tank[MAX_TANKS];       // bot-controlled tanks in config order
+    int32_t bot_ord[MAX_TANKS];        // tank -> its ordinal among the bots (0 for agents)
+    int32_t n_bots;
     uint32_t team_members[MAX_TANKS];  // bit j set: tank j is on tank i's team (incl. i)
     // observation row layout (floats)
     int32_t self_len, off_ob, off_eb, eb_stride, off_et, et_len, off_walls, off_maze, off_zones, off_flags;
@@ -61,7 +64,7 @@ struct DevState {
     const double *trig;            // [361][2] cos, sin of math.radians(a)
     const double *corn;            // [361][4] pygame-rotated corner offsets (c0x, c0y, c1x, c1y)
     const double *pend;            // [PEND_LUT] k-fold accumulation of BULLET_AWAY_PENALTY
-    const double *udir;            // [361][2] (cos a, -sin a) / |(cos a, -sin a)| as numpy computes it
+    const uint8_t *udelta;         // [361] ulp offsets of the numpy-normalised bullet direction from (cos a, -sin a)
     const uint16_t *bfs_tab;       // [121*121] all-pairs bfs_first_step of a FIXED map: len | dir << 8 (null for mazes)
 };
 
@@ -74,6 +77,7 @@ struct BlockMem {
     int32_t *tshot;                // [n][BS]
     uint8_t *slot_of;              // [n*6][BS] bullet slot of (owner, per-owner rank), valid for rank < tlive
     const float *tmpl;             // [4W + 121] wall + maze observation columns of a fixed map
+    const uint8_t *udelta;         // [361] copy of st.udelta
 };
 
 }  // namespace at

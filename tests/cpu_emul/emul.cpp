@@ -93,7 +93,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     memcpy(env->arena.data() + L.o_trig, env->luts.trig.data(), 722 * 8);
     memcpy(env->arena.data() + L.o_corn, env->luts.corn.data(), 361 * 4 * 8);
     memcpy(env->arena.data() + L.o_pend, env->luts.pend.data(), PEND_LUT * 8);
-    memcpy(env->arena.data() + L.o_udir, env->luts.udir.data(), 722 * 8);
+    memcpy(env->arena.data() + L.o_udir, env->luts.udelta.data(), 364);
     if (env->k.map != AT_MAP_MAZE) {
         fill_bfs_table(env->k.wall_lo, env->k.wall_hi, (uint16_t *)(env->arena.data() + L.o_bfs));
         env->st.bfs_tab = (const uint16_t *)(env->arena.data() + L.o_bfs);
@@ -114,6 +114,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     env->slot_of.assign((size_t)n * SLOTS_PER_TANK * BS, 0);
     bm.tmpl = env->tmpl.data();
     bm.slot_of = env->slot_of.data();
+    bm.udelta = env->luts.udelta.data();
     run(env, false, nullptr, nullptr, nullptr, nullptr, nullptr);  // the constructor's own reset
     *out = env;
     return AT_OK;
