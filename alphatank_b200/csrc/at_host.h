@@ -132,6 +132,19 @@ inline std::string build_kcfg(const at_config *cfg, uint64_t seed, int64_t env_i
         else { k.bot_ord[i] = nb; k.bot_tank[nb++] = i; }
     }
     k.n_bots = nb;
+    // pooled line-of-sight: a smart bot's query may run when the first bot decides if no enemy BOT acts before it
+    // (agents have all acted by then in team mode; in the arena both bots decide before anybody acts)
+    k.first_bot_k = k.team_layout ? k.n_agents : 0;
+    k.los_hoist = 0;
+    if (cfg->map != AT_MAP_MAZE)
+        for (int b = 0; b < nb; ++b) {
+            const int j = k.bot_tank[b];
+            if (k.bot_type[j] != AT_BOT_SMART) continue;
+            bool ok = true;
+            if (cfg->mode != AT_MODE_ARENA)
+                for (int b2 = 0; b2 < b; ++b2) ok = ok && k.team[k.bot_tank[b2]] == k.team[j];
+            if (ok) k.los_hoist |= 1u << j;
+        }
     k.rows = k.team_layout ? k.n_agents : n;
     k.act_rows = k.team_layout ? k.n_agents : (cfg->mode == AT_MODE_ARENA ? 0 : n);
     build_map(cfg->map, &k.wall_lo, &k.wall_hi, &k.n_walls);

@@ -34,9 +34,9 @@ namespace {
 struct SmemLayout {
     int n;
     size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_thits, off_bpack, off_tlive,
-        off_tshot, off_tmpl, off_tile, off_slot, off_udelta, total;
+        off_tshot, off_tmpl, off_tile, off_slot, off_udelta, off_losq, total;
 };
-constexpr int TILE_FLOATS = 32 * 32;  // per warp: 32 envs x 32 observation columns
+constexpr int TILE_FLOATS = 32 * 33;  // per warp: 32 envs x 32 observation columns, row stride 33
 __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots) {
     const int nb = n_bots > 0 ? n_bots : 1;
     SmemLayout L;
@@ -59,6 +59,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots
     L.off_tile = o; o += (size_t)(BS / 32) * TILE_FLOATS * 4;
     L.off_slot = o; o += (size_t)n * SLOTS_PER_TANK * BS;
     L.off_udelta = o; o += 368;
+    L.off_losq = o; o += (size_t)(BS / 32) * 512;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
@@ -71,17 +72,13 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// Observation sink of one warp.  Every lane (= env) emits the same column j at the same time; the value goes
-// to tile[lane][(j + lane) & 31] (rotation => the 32 lanes hit 32 different banks).  After 32 columns the warp
-// flushes the 32 x 32 tile: lane L takes row 4i + L/8 and the four columns 4*(L%8)..+3 (again conflict-free)
-// and writes them with one 16-byte store, so a warp store instruction covers four complete 128-byte row
-// chunks - full-sector, fully coalesced HBM writes from thread-per-env code.
-// Observation sink of one warp.  Every lane (= env) emits the same (virtual) column at the same time; the value
-// goes to tile[lane][(j + lane) & 31] (rotation => the 32 lanes hit 32 different banks).  After 32 columns the warp
-// flushes the 32 x 32 tile: for each env row, lane L stores column j0 + L (again conflict-free in shared
-// memory), i.e. one coalesced 128-byte run per store instruction.  For fixed maps the static wall / maze columns
-// are not emitted by the threads at all: virtual columns skip them (remap) and the warp copies them from the
-// block's template once per kernel.
+// Observation sink of one warp.  Every lane (= env) emits the same (virtual) column at the same time into its own
+// row of a 32 x 33-float shared-memory tile (odd row stride => the 32 lanes hit 32 different banks, and so does a
+// warp reading one tile row).  After 32 columns the warp flushes the tile: for each env row, lane L stores column
+// j0 + L - one coalesced 128-byte run per store instruction, addresses are immediates off two per-lane bases.
+// For fixed maps the static wall / maze columns are not emitted by the threads at all: virtual columns skip them
+// (remap) and each thread ships them with a bulk-async copy from the block's template.
+constexpr int TILE_STRIDE = 33;
 __device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t row_len, unsigned emit_mask, int lane,
                                         int j0, int ncols, int dyn_len, int head_len, int static_len, int obs_dim) {
     __syncwarp();
@@ -90,33 +87,32 @@ __device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t
     const int gcol = r * obs_dim + (kk < head_len ? kk : kk + static_len);
     if (lane < ncols) {
         float *dst = gbase + gcol;
-        const float *src = tile;
-#pragma unroll 8
-        for (int rr = 0; rr < 32; ++rr) {
-            const float v = src[(lane + rr) & 31];
-            if ((emit_mask >> rr) & 1u) *dst = v;
-            dst += row_len;
-            src += 32;
-        }
+        const float *src = tile + lane;
+#pragma unroll
+        for (int rr = 0; rr < 32; ++rr)
+            if ((emit_mask >> rr) & 1u) dst[(int64_t)rr * row_len] = src[rr * TILE_STRIDE];
     }
     __syncwarp();
 }
 struct TileSink {  // kept in registers: flush takes everything by value
-    float *my;          // tile + lane * 32
+    float *my;          // tile + lane * TILE_STRIDE
     float *tile;
     float *gbase;       // obs row of the warp's lane 0
     int64_t row_len;    // R * D floats per env
     unsigned emit_mask; // lanes whose env gets an observation
-    int lane, j;
+    int lane, j0, jj;   // columns [j0, j0 + jj) are in the tile
     int dyn_len, head_len, static_len, obs_dim;
     __device__ __forceinline__ void put(float v) {
-        my[(j + lane) & 31] = v;
-        ++j;
-        if ((j & 31) == 0) tile_flush(tile, gbase, row_len, emit_mask, lane, j - 32, 32, dyn_len, head_len, static_len, obs_dim);
+        my[jj] = v;
+        if (++jj == 32) {
+            tile_flush(tile, gbase, row_len, emit_mask, lane, j0, 32, dyn_len, head_len, static_len, obs_dim);
+            j0 += 32;
+            jj = 0;
+        }
     }
-    __device__ __forceinline__ void skip_static(const float *, int) {}  // written by the warp from the template
+    __device__ __forceinline__ void skip_static(const float *, int) {}  // shipped by bulk copies from the template
     __device__ __forceinline__ void finish() {
-        if (j & 31) tile_flush(tile, gbase, row_len, emit_mask, lane, j & ~31, j & 31, dyn_len, head_len, static_len, obs_dim);
+        if (jj) tile_flush(tile, gbase, row_len, emit_mask, lane, j0, jj, dyn_len, head_len, static_len, obs_dim);
     }
 };
 
@@ -139,6 +135,8 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bm.slot_of = (uint8_t *)(smem + L.off_slot);
     uint8_t *udl = (uint8_t *)(smem + L.off_udelta);
     bm.udelta = udl;
+    bm.los_q = (uint8_t *)(smem + L.off_losq);
+    bm.los_r = bm.los_q + (BS / 32) * 256;
     float *tmpl = (float *)(smem + L.off_tmpl) + (c.off_walls & 3);  // tmpl[q] and obs column off_walls + q: same phase
     bm.tmpl = tmpl;
 
@@ -161,6 +159,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     const int64_t e = (int64_t)blockIdx.x * BS + tid;
     const bool valid = e < st.N;
     Sim s(c, st, bm, valid ? e : 0, tid);
+    s.warp_mask = __ballot_sync(0xffffffffu, valid);
     bool emit = false;
     if (valid) {
         if (IS_STEP) {
@@ -217,12 +216,13 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     }
     TileSink out;
     out.tile = (float *)(smem + L.off_tile) + (size_t)warp * TILE_FLOATS;
-    out.my = out.tile + lane * 32;
+    out.my = out.tile + lane * TILE_STRIDE;
     out.gbase = gbase;
     out.row_len = row_len;
     out.emit_mask = emit_mask;
     out.lane = lane;
-    out.j = 0;
+    out.j0 = 0;
+    out.jj = 0;
     out.static_len = static_len;
     out.head_len = c.off_walls;
     out.dyn_len = c.obs_dim - static_len;

@@ -336,10 +336,11 @@ struct Sim {
     uint64_t tclo, tchi;   // cells under any alive tank's 30x24 rect (rebuilt per bullet pass; superset after kills)
     uint64_t iclo, ichi;   // wall | tank cells: a 5x5 rect inside one uninteresting cell needs no further test
     uint32_t alive_bits;   // bit i: tank i alive (mirror of TPACK)
+    uint32_t warp_mask;    // lanes of this warp that run the simulation (device: for the pooled stages)
 
     AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0) {}
+          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0), warp_mask(0xffffffffu) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
     AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
@@ -655,27 +656,33 @@ struct Sim {
         for (int r = r0; r <= r1; ++r)
             for (int cc = c0; cc <= c1; ++cc) any = any || wall_at(r * 11 + cc);
         if (!any) return false;
-        // OBB axes and projections (computed from the absolute corners, as the reference does)
-        double e0x = kx[1] - kx[0], e0y = ky[1] - ky[0], e1x = kx[3] - kx[0], e1y = ky[3] - ky[0];
-        double l0 = sqrt((0.0 + e0x * e0x) + e0y * e0y), l1 = sqrt((0.0 + e1x * e1x) + e1y * e1y);
-        double ax[2] = {e0x / l0, e1x / l1}, ay[2] = {e0y / l0, e1y / l1};
-        double omin[2], omax[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            double lo = 0, hi = 0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                double d = (0.0 + kx[k] * ax[q]) + ky[k] * ay[q];
-                lo = (k == 0 || d < lo) ? d : lo;
-                hi = (k == 0 || d > hi) ? d : hi;
-            }
-            omin[q] = lo; omax[q] = hi;
-        }
+        // the reference tests 4 axes per wall (2 OBB axes, x, y) and needs all of them to overlap: test the cheap
+        // x / y axes first and build the OBB axes (2 sqrt, 4 divisions) only for a wall that survives them
+        bool have_axes = false;
+        double ax[2] = {0, 0}, ay[2] = {0, 0}, omin[2] = {0, 0}, omax[2] = {0, 0};
         for (int r = r0; r <= r1; ++r)
             for (int cc = c0; cc <= c1; ++cc) {
                 if (!wall_at(r * 11 + cc)) continue;
                 const double X0 = (double)(cc * 70), X1 = (double)(cc * 70 + 70), Y0 = (double)(r * 70),
                              Y1 = (double)(r * 70 + 70);
+                if ((mxx < X0 - 0.01) || (X1 < mnx - 0.01) || (mxy < Y0 - 0.01) || (Y1 < mny - 0.01)) continue;
+                if (!have_axes) {  // computed from the absolute corners, as the reference does
+                    have_axes = true;
+                    double e0x = kx[1] - kx[0], e0y = ky[1] - ky[0], e1x = kx[3] - kx[0], e1y = ky[3] - ky[0];
+                    double l0 = sqrt((0.0 + e0x * e0x) + e0y * e0y), l1 = sqrt((0.0 + e1x * e1x) + e1y * e1y);
+                    ax[0] = e0x / l0; ax[1] = e1x / l1; ay[0] = e0y / l0; ay[1] = e1y / l1;
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        double lo = 0, hi = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            double d = (0.0 + kx[k] * ax[q]) + ky[k] * ay[q];
+                            lo = (k == 0 || d < lo) ? d : lo;
+                            hi = (k == 0 || d > hi) ? d : hi;
+                        }
+                        omin[q] = lo; omax[q] = hi;
+                    }
+                }
                 bool sep = false;
 #pragma unroll
                 for (int q = 0; q < 2; ++q) {
@@ -684,8 +691,6 @@ struct Sim {
                     double lo = fmin(fmin(d0, d1), fmin(d2, d3)), hi = fmax(fmax(d0, d1), fmax(d2, d3));
                     sep = sep || (omax[q] < lo - 0.01) || (hi < omin[q] - 0.01);
                 }
-                sep = sep || (mxx < X0 - 0.01) || (X1 < mnx - 0.01);
-                sep = sep || (mxy < Y0 - 0.01) || (Y1 < mny - 0.01);
                 if (!sep) return true;
             }
         return false;
@@ -733,124 +738,158 @@ struct Sim {
     AT_HD static int aim_from_diff(double d, double thr) { return fabs(d) < thr ? 0 : (d > 0 ? -1 : 1); }
 
     // BulletTrajectory.simulate_complete_trajectory -> will_hit_target (sprite.py:131-190), used by
-    // SmartStrategyBot.check_line_of_sight (strategy_bot.py:58-73).
-    AT_HD bool line_of_sight(int me) const {
-        const int a = t_angle(me);
+    // SmartStrategyBot.check_line_of_sight (strategy_bot.py:58-73).  Written as a resumable state machine so that
+    // the same iteration runs inline (one env per thread) or pooled across the lanes of a warp (`q` = block slot
+    // of the env the job belongs to; wall masks are this thread's, which is the same map for fixed-map handles).
+    struct Los {
+        double x, y, dx, dy, inv_dx, inv_dy;
+        uint32_t enemies;  // alive tanks of other teams
+        int q, bx0, bx1, by0, by1, bounces, dist, plan_in, result;  // result: -1 running, 0 / 1 finished
+        bool stat_x, stat_y, accepted;
+    };
+    AT_HD int los_ex(const Los &L, int i) const { return d2i(bm.tx[i * BS + L.q] - 15); }
+    AT_HD int los_ey(const Los &L, int i) const { return d2i(bm.ty[i * BS + L.q] - 12); }
+    AT_HD void los_init(Los &L, int q, int me) const {
+        const uint32_t pk = bm.tpack[me * BS + q];
+        const int a = (int)(pk & 511u);
         const double cv = cosr(a), sv = sinr(a);
-        double x = TX(me) + 10 * cv, y = TY(me) - 10 * sv, dx = cv, dy = -sv;
-        int ex[MAX_TANKS], ey[MAX_TANKS], ne = 0;
-        int bx0 = 1 << 20, bx1 = -(1 << 20), by0 = 1 << 20, by1 = -(1 << 20);  // union of the enemy rect origins
+        L.q = q;
+        L.x = bm.tx[me * BS + q] + 10 * cv;
+        L.y = bm.ty[me * BS + q] - 10 * sv;
+        L.dx = cv;
+        L.dy = -sv;
+        L.enemies = 0;
+        L.bx0 = 1 << 20; L.bx1 = -(1 << 20); L.by0 = 1 << 20; L.by1 = -(1 << 20);  // union of the enemy rect origins
         bool reachable = false;
         for (int i = 0; i < c.n_tanks; ++i)
-            if (c.team[i] != c.team[me] && t_alive(i)) {
-                ex[ne] = d2i(TX(i) - 15);
-                ey[ne] = d2i(TY(i) - 12);
-                bx0 = imin(bx0, ex[ne]); bx1 = imax(bx1, ex[ne]); by0 = imin(by0, ey[ne]); by1 = imax(by1, ey[ne]);
-                ++ne;
+            if (c.team[i] != c.team[me] && (bm.tpack[i * BS + q] & TP_ALIVE)) {
+                L.enemies |= 1u << i;
+                const int exi = los_ex(L, i), eyi = los_ey(L, i);
+                L.bx0 = imin(L.bx0, exi); L.bx1 = imax(L.bx1, exi); L.by0 = imin(L.by0, eyi); L.by1 = imax(L.by1, eyi);
                 // a hit needs the 5x5 rect within <= 301 advancing sub-steps of the muzzle: exact cull
-                double gx = fabs(TX(i) - x), gy = fabs(TY(i) - y);
+                const double gx = fabs(bm.tx[i * BS + q] - L.x), gy = fabs(bm.ty[i * BS + q] - L.y);
                 reachable = reachable || (gx < 340.0 && gy < 340.0);
             }
-        if (!reachable) return false;
+        L.result = reachable ? -1 : 0;
         // |dx|, |dy| never change (reflections only negate).  cos/sin of an integer angle are either
         // >= 0.017 or < 2e-16 in magnitude; the latter is absorbed by every addition (x >= 2): static axis.
-        const bool stat_x = fabs(dx) < 1e-15, stat_y = fabs(dy) < 1e-15;
-        const double inv_dx = stat_x ? 0.0 : 1.0 / fabs(dx), inv_dy = stat_y ? 0.0 : 1.0 / fabs(dy);
-        int bounces = 0, dist = 0, plan_in = 0;
+        L.stat_x = fabs(L.dx) < 1e-15;
+        L.stat_y = fabs(L.dy) < 1e-15;
+        L.inv_dx = L.stat_x ? 0.0 : 1.0 / fabs(L.dx);
+        L.inv_dy = L.stat_y ? 0.0 : 1.0 / fabs(L.dy);
+        L.bounces = 0; L.dist = 0; L.plan_in = 0;
         // the muzzle position itself is never tested by the reference; the skip-ahead needs a wall-free rect
-        bool accepted = first_wall(d2i(x), d2i(y), 5, 5) < 0;
-        for (;;) {
-            // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every
-            // time.  From an accepted (wall-free) position the 5x5 rect can only START overlapping a wall
-            // when one of its LEADING edges crosses a cell boundary (trailing edges only uncover cells), and
-            // it cannot overlap an enemy rect before both axes have entered that rect's span.  Both kinds of
-            // event are linear in the step count, so a DDA over the leading-edge crossings finds the first
-            // crossing that uncovers a wall cell; all sub-steps more than 2 before it (and before the tank
-            // bound, the next binade boundary and `dist > 300`) can only be "advance": one exact jump.
-            if (plan_in == 0) {
-                int m = 0;
-                const int room = 300 - dist;
-                if (room >= 6 && accepted) {
-                    double lim = (double)room;
-                    for (int k = 0; k < ne; ++k) {  // overlap needs x in [ex-4, ex+30) and y in [ey-4, ey+24)
-                        const double lx = (double)(ex[k] - 4), hx = (double)(ex[k] + 30);
-                        const double ly = (double)(ey[k] - 4), hy = (double)(ey[k] + 24);
-                        const double sx = x < lx ? ((dx > 0 && !stat_x) ? (lx - x) * inv_dx : 1.0e9)
-                                                 : (x >= hx ? ((dx < 0 && !stat_x) ? (x - hx) * inv_dx : 1.0e9) : 0.0);
-                        const double sy = y < ly ? ((dy > 0 && !stat_y) ? (ly - y) * inv_dy : 1.0e9)
-                                                 : (y >= hy ? ((dy < 0 && !stat_y) ? (y - hy) * inv_dy : 1.0e9) : 0.0);
-                        lim = fmin(lim, fmax(sx, sy));
-                    }
-                    const int jx = d2i(x), jy = d2i(y);
-                    double tx = 1.0e9, ty = 1.0e9;  // step count of the next leading-edge crossing per axis
-                    int lcx = 0, lcy = 0;           // leading column / row
-                    const int sgx = dx > 0 ? 1 : -1, sgy = dy > 0 ? 1 : -1;
-                    if (!stat_x) {
-                        lcx = dx > 0 ? (jx + 4) / 70 : jx / 70;
-                        tx = (dx > 0 ? (double)(70 * (lcx + 1) - 4) - x : x - (double)(70 * lcx)) * inv_dx;
-                        const int e = d_expo(x);  // jumps stay inside one binade (jump_axis)
-                        lim = fmin(lim, (dx > 0 ? bits_d((uint64_t)(e + 1) << 52) - x : x - bits_d((uint64_t)e << 52)) * inv_dx);
-                    }
-                    if (!stat_y) {
-                        lcy = dy > 0 ? (jy + 4) / 70 : jy / 70;
-                        ty = (dy > 0 ? (double)(70 * (lcy + 1) - 4) - y : y - (double)(70 * lcy)) * inv_dy;
-                        const int e = d_expo(y);
-                        lim = fmin(lim, (dy > 0 ? bits_d((uint64_t)(e + 1) << 52) - y : y - bits_d((uint64_t)e << 52)) * inv_dy);
-                    }
-                    const double step_x = 70.0 * inv_dx, step_y = 70.0 * inv_dy;
-                    for (;;) {
-                        const bool xev = tx <= ty;
-                        const double t = xev ? tx : ty;
-                        if (t >= lim) break;
-                        bool hit = false;
-                        if (xev) {  // column lcx + sgx becomes covered; rows around the predicted y (+-3 px slack)
-                            lcx += sgx;
-                            const double yt = y + t * dy;
-                            const int ra = imax(d2i(yt - 3.0) / 70, 0), rb = imin(d2i(yt + 8.0) / 70, 10);
-                            for (int r = ra; r <= rb; ++r) hit = hit || lcx < 0 || lcx > 10 || wall_at(r * 11 + lcx);
-                            tx += step_x;
-                        } else {
-                            lcy += sgy;
-                            const double xt = x + t * dx;
-                            const int ca = imax(d2i(xt - 3.0) / 70, 0), cb = imin(d2i(xt + 8.0) / 70, 10);
-                            for (int cc = ca; cc <= cb; ++cc) hit = hit || lcy < 0 || lcy > 10 || wall_at(lcy * 11 + cc);
-                            ty += step_y;
-                        }
-                        if (hit) { lim = t; break; }
-                    }
-                    m = imax(d2i(lim) - 2, 0);
+        L.accepted = first_wall(d2i(L.x), d2i(L.y), 5, 5) < 0;
+    }
+    // One iteration: an optional exact skip-ahead followed by one reference sub-step.  Returns true when done.
+    AT_HD bool los_iter(Los &L) const {
+        if (L.result >= 0) return true;
+        double x = L.x, y = L.y, dx = L.dx, dy = L.dy;
+        const bool stat_x = L.stat_x, stat_y = L.stat_y;
+        const double inv_dx = L.inv_dx, inv_dy = L.inv_dy;
+        // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every
+        // time.  From an accepted (wall-free) position the 5x5 rect can only START overlapping a wall
+        // when one of its LEADING edges crosses a cell boundary (trailing edges only uncover cells), and
+        // it cannot overlap an enemy rect before both axes have entered that rect's span.  Both kinds of
+        // event are linear in the step count, so a DDA over the leading-edge crossings finds the first
+        // crossing that uncovers a wall cell; all sub-steps more than 2 before it (and before the tank
+        // bound, the next binade boundary and `dist > 300`) can only be "advance": one exact jump.
+        if (L.plan_in == 0) {
+            int m = 0;
+            const int room = 300 - L.dist;
+            if (room >= 6 && L.accepted) {
+                double lim = (double)room;
+                for (uint32_t bits = L.enemies; bits; bits &= bits - 1) {  // overlap needs x in [ex-4, ex+30), y in [ey-4, ey+24)
+                    const int i = ffs32(bits);
+                    const int exi = los_ex(L, i), eyi = los_ey(L, i);
+                    const double lx = (double)(exi - 4), hx = (double)(exi + 30);
+                    const double ly = (double)(eyi - 4), hy = (double)(eyi + 24);
+                    const double sx = x < lx ? ((dx > 0 && !stat_x) ? (lx - x) * inv_dx : 1.0e9)
+                                             : (x >= hx ? ((dx < 0 && !stat_x) ? (x - hx) * inv_dx : 1.0e9) : 0.0);
+                    const double sy = y < ly ? ((dy > 0 && !stat_y) ? (ly - y) * inv_dy : 1.0e9)
+                                             : (y >= hy ? ((dy < 0 && !stat_y) ? (y - hy) * inv_dy : 1.0e9) : 0.0);
+                    lim = fmin(lim, fmax(sx, sy));
                 }
-                if (m >= 4) {
-                    if (!stat_x) x = jump_axis(x, dx, m);
-                    if (!stat_y) y = jump_axis(y, dy, m);
-                    dist += m;
-                    plan_in = 3;  // the event is 2..3 sub-steps ahead: walk through it before planning again
-                } else {
-                    plan_in = m + 3;
+                const int jx = d2i(x), jy = d2i(y);
+                double tx = 1.0e9, ty = 1.0e9;  // step count of the next leading-edge crossing per axis
+                int lcx = 0, lcy = 0;           // leading column / row
+                const int sgx = dx > 0 ? 1 : -1, sgy = dy > 0 ? 1 : -1;
+                if (!stat_x) {
+                    lcx = dx > 0 ? (jx + 4) / 70 : jx / 70;
+                    tx = (dx > 0 ? (double)(70 * (lcx + 1) - 4) - x : x - (double)(70 * lcx)) * inv_dx;
+                    const int e = d_expo(x);  // jumps stay inside one binade (jump_axis)
+                    lim = fmin(lim, (dx > 0 ? bits_d((uint64_t)(e + 1) << 52) - x : x - bits_d((uint64_t)e << 52)) * inv_dx);
                 }
-            } else {
-                --plan_in;
+                if (!stat_y) {
+                    lcy = dy > 0 ? (jy + 4) / 70 : jy / 70;
+                    ty = (dy > 0 ? (double)(70 * (lcy + 1) - 4) - y : y - (double)(70 * lcy)) * inv_dy;
+                    const int e = d_expo(y);
+                    lim = fmin(lim, (dy > 0 ? bits_d((uint64_t)(e + 1) << 52) - y : y - bits_d((uint64_t)e << 52)) * inv_dy);
+                }
+                const double step_x = 70.0 * inv_dx, step_y = 70.0 * inv_dy;
+                for (;;) {
+                    const bool xev = tx <= ty;
+                    const double t = xev ? tx : ty;
+                    if (t >= lim) break;
+                    bool hit = false;
+                    if (xev) {  // column lcx + sgx becomes covered; rows around the predicted y (+-3 px slack)
+                        lcx += sgx;
+                        const double yt = y + t * dy;
+                        const int ra = imax(d2i(yt - 3.0) / 70, 0), rb = imin(d2i(yt + 8.0) / 70, 10);
+                        for (int r = ra; r <= rb; ++r) hit = hit || lcx < 0 || lcx > 10 || wall_at(r * 11 + lcx);
+                        tx += step_x;
+                    } else {
+                        lcy += sgy;
+                        const double xt = x + t * dx;
+                        const int ca = imax(d2i(xt - 3.0) / 70, 0), cb = imin(d2i(xt + 8.0) / 70, 10);
+                        for (int cc = ca; cc <= cb; ++cc) hit = hit || lcy < 0 || lcy > 10 || wall_at(lcy * 11 + cc);
+                        ty += step_y;
+                    }
+                    if (hit) { lim = t; break; }
+                }
+                m = imax(d2i(lim) - 2, 0);
             }
-            const double nx = x + dx, ny = y + dy;
-            const int ix = d2i(nx), iy = d2i(ny);
-            if (ix < bx1 + 30 && iy < by1 + 24 && ix + 5 > bx0 && iy + 5 > by0)  // inside the union box: test each
-                for (int k = 0; k < ne; ++k)
-                    if (ix < ex[k] + 30 && iy < ey[k] + 24 && ix + 5 > ex[k] && iy + 5 > ey[k]) return true;
-            int cell = first_wall(ix, iy, 5, 5);
-            if (cell >= 0) {
-                bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
-                if (bxh) dx = -dx;
-                if (byh) dy = -dy;
-                ++bounces;
-                plan_in = 0;
+            if (m >= 4) {
+                if (!stat_x) x = jump_axis(x, dx, m);
+                if (!stat_y) y = jump_axis(y, dy, m);
+                L.dist += m;
+                L.plan_in = 3;  // the event is 2..3 sub-steps ahead: walk through it before planning again
             } else {
-                x = nx;
-                y = ny;
-                ++dist;
-                accepted = true;
+                L.plan_in = m + 3;
             }
-            if (bounces > 6 || dist > 300) return false;
+        } else {
+            --L.plan_in;
         }
+        const double nx = x + dx, ny = y + dy;
+        const int ix = d2i(nx), iy = d2i(ny);
+        if (ix < L.bx1 + 30 && iy < L.by1 + 24 && ix + 5 > L.bx0 && iy + 5 > L.by0)  // inside the union box: test each
+            for (uint32_t bits = L.enemies; bits; bits &= bits - 1) {
+                const int i = ffs32(bits);
+                const int exi = los_ex(L, i), eyi = los_ey(L, i);
+                if (ix < exi + 30 && iy < eyi + 24 && ix + 5 > exi && iy + 5 > eyi) { L.result = 1; return true; }
+            }
+        const int cell = first_wall(ix, iy, 5, 5);
+        if (cell >= 0) {
+            const bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
+            if (bxh) dx = -dx;
+            if (byh) dy = -dy;
+            ++L.bounces;
+            L.plan_in = 0;
+        } else {
+            x = nx;
+            y = ny;
+            ++L.dist;
+            L.accepted = true;
+        }
+        L.x = x; L.y = y; L.dx = dx; L.dy = dy;
+        if (L.bounces > 6 || L.dist > 300) { L.result = 0; return true; }
+        return false;
+    }
+    AT_HD bool line_of_sight(int me) const {
+        Los L;
+        los_init(L, tid, me);
+        while (!los_iter(L)) {}
+        return L.result != 0;
     }
 
     // bpack layouts -----------------------------------------------------
@@ -870,10 +909,13 @@ struct Sim {
         if (c.bot_type[i] != 0) { BF0(i) = 0.0; BF1(i) = 0.0; }
     }
 
-    AT_HD void smart_action(int me, int act[3]) {  // strategy_bot.py:75-203
+    // SmartStrategyBot.get_action (strategy_bot.py:75-203) split around its line-of-sight query so that the
+    // ray-marches of a warp's envs can be pooled: smart_pre = update_state + target bookkeeping (returns whether
+    // a line-of-sight query is needed), smart_post = the decision given the answer.
+    AT_HD bool smart_pre(int me) {
         uint32_t p = BPACK(me);
         int target = (int)(p & 15u) - 1;
-        bool aiming = (p >> 4) & 1u, rot_pos = (p >> 5) & 1u, has_next = (p >> 12) & 1u;
+        bool aiming = (p >> 4) & 1u, has_next = (p >> 12) & 1u;
         int stuck = (int)((p >> 6) & 63u), next_r = (int)((p >> 13) & 15u), next_c = (int)((p >> 17) & 15u);
         if (target < 0 || !t_alive(target)) {
             aiming = false;
@@ -900,15 +942,25 @@ struct Sim {
             BF0(me) = TX(me);
             BF1(me) = TY(me);
         }
-        act[0] = 1; act[1] = 1; act[2] = 0;
         if (!aiming) {
             target = nearest_opponent(me, nullptr);
             if (target >= 0) aiming = true;
         }
+        BPACK(me) = (uint32_t)(target + 1) | ((uint32_t)aiming << 4) | (p & (1u << 5)) | ((uint32_t)stuck << 6) |
+                    ((uint32_t)has_next << 12) | ((uint32_t)next_r << 13) | ((uint32_t)next_c << 17);
+        return aiming && target >= 0;
+    }
+    AT_HD void smart_post(int me, bool los, int act[3]) {
+        const uint32_t p = BPACK(me);
+        const int target = (int)(p & 15u) - 1;
+        const bool aiming = (p >> 4) & 1u, has_next = (p >> 12) & 1u;
+        bool rot_pos = (p >> 5) & 1u;
+        int stuck = (int)((p >> 6) & 63u);
+        const int next_r = (int)((p >> 13) & 15u), next_c = (int)((p >> 17) & 15u);
+        act[0] = 1; act[1] = 1; act[2] = 0;
         if (aiming && target >= 0) {
             // one aim computation for both branches (strategy_bot.py:141-175): at the target when there is a line
             // of sight, else at the centre of the next BFS cell
-            const bool los = line_of_sight(me);
             if (los || has_next) {
                 const double px = los ? TX(target) : next_c * GRID + (GRID / 2);
                 const double py = los ? TY(target) : next_r * GRID + (GRID / 2);
@@ -931,9 +983,65 @@ struct Sim {
             rot_pos = !rot_pos;
             stuck = 0;
         }
-        BPACK(me) = (uint32_t)(target + 1) | ((uint32_t)aiming << 4) | ((uint32_t)rot_pos << 5) |
-                    ((uint32_t)stuck << 6) | ((uint32_t)has_next << 12) | ((uint32_t)next_r << 13) |
-                    ((uint32_t)next_c << 17);
+        BPACK(me) = (p & ~((1u << 5) | (63u << 6))) | ((uint32_t)rot_pos << 5) | ((uint32_t)stuck << 6);
+    }
+    // Line-of-sight queries of the warp's envs, pooled: the ray-march lengths differ wildly between envs (0 to ~40
+    // iterations), so instead of every thread marching its own bots while its neighbours idle, the (env, bot) jobs
+    // of the 32 envs go into a shared-memory queue and idle lanes keep dequeuing - one los_iter per lockstep round.
+    // `need` has bit j set when bot tank j of this env needs an answer; returns the answers in the same bits.
+    AT_HD uint32_t pool_los(uint32_t need) {
+#ifdef __CUDA_ARCH__
+        const int lane = tid & 31, wbase = tid & ~31;
+        const unsigned wm = warp_mask;
+        uint8_t *queue = bm.los_q + (tid >> 5) * 256;
+        uint8_t *res = bm.los_r + (tid >> 5) * 256;
+        int total = 0;
+        for (uint32_t hb = c.los_hoist; hb; hb &= hb - 1) {
+            const int j = ffs32(hb);
+            const bool mine = (need >> j) & 1u;
+            const unsigned m = __ballot_sync(wm, mine);
+            if (mine) queue[total + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane | (j << 5));
+            total += __popc(m);
+        }
+        __syncwarp(wm);  // queue and the other envs' tank columns (shared memory) are visible
+        int next = 0, myjob = 0;
+        bool active = false;
+        Los L;
+        L.result = 0;
+        for (;;) {
+            const unsigned idle = __ballot_sync(wm, !active);
+            const int pos = next + __popc(idle & ((1u << lane) - 1u));
+            if (!active && pos < total) {
+                myjob = queue[pos];
+                los_init(L, wbase + (myjob & 31), myjob >> 5);
+                active = true;
+            }
+            next = imin(next + __popc(idle), total);
+            if (__ballot_sync(wm, active) == 0u) break;
+            if (active) {
+                bool fin = false;
+                for (int it = 0; it < 4 && !fin; ++it) fin = los_iter(L);
+                if (fin) {
+                    res[myjob] = (uint8_t)(L.result != 0);
+                    active = false;
+                }
+            }
+        }
+        __syncwarp(wm);
+        uint32_t out = 0;
+        for (uint32_t hb = need; hb; hb &= hb - 1) {
+            const int j = ffs32(hb);
+            out |= (uint32_t)res[lane | (j << 5)] << j;
+        }
+        return out;
+#else
+        uint32_t out = 0;
+        for (uint32_t hb = need; hb; hb &= hb - 1) {
+            const int j = ffs32(hb);
+            if (line_of_sight(j)) out |= 1u << j;
+        }
+        return out;
+#endif
     }
     AT_HD void random_action(int me, int act[3]) {  // simple_bots.py:32-46
         uint32_t p = BPACK(me);
@@ -1077,13 +1185,16 @@ struct Sim {
         timer -= 1;
         BPACK(me) = (uint32_t)timer | ((uint32_t)state << 5) | ((uint32_t)has_angle << 7);
     }
-    AT_HD void bot_action(int me, int act[3]) {
+    AT_HD void bot_action(int me, int act[3], bool pre_done, bool los_hoisted) {
         switch (c.bot_type[me]) {
-        case 0:
+        case 0: {
             // runs for dead tanks too: take_action still sets their speed (sprite.py:646-651), which the
             // other tanks' observation rows expose as velocity
-            smart_action(me, act);
+            bool los = los_hoisted;
+            if (!pre_done) los = smart_pre(me) && line_of_sight(me);
+            smart_post(me, los, act);
             break;
+        }
         case 1: random_action(me, act); break;
         case 2: aggressive_action(me, act); break;
         case 3: defensive_action(me, act); break;
@@ -1145,6 +1256,7 @@ struct Sim {
         tick += 1;
         if (c.mode != AT_MODE_TEAM_) epstep += 1;
         const bool arena = c.mode == AT_MODE_ARENA_, team = c.mode == AT_MODE_TEAM_, botagent = c.mode == AT_MODE_BOT_AGENT_;
+        uint32_t pre_done = 0, los_bits = 0;
         for (int stage = arena ? 0 : 1; stage < 4; ++stage) {
             if (stage & 1) {
                 bullets_pass();
@@ -1157,7 +1269,17 @@ struct Sim {
                 if (team) i = k < c.n_agents ? c.agent_tank[k] : c.bot_tank[k - c.n_agents];
                 const bool is_bot = c.ctrl[i] == 1;
                 if (is_bot && (stage == 0 || !arena)) {
-                    bot_action(i, acts[i]);
+                    if (k == c.first_bot_k && c.los_hoist != 0u) {
+                        // every smart bot whose line of sight cannot change before it acts: query them together
+                        uint32_t need = 0;
+                        for (uint32_t hb = c.los_hoist; hb; hb &= hb - 1) {
+                            const int j = ffs32(hb);
+                            if (smart_pre(j)) need |= 1u << j;
+                        }
+                        pre_done = c.los_hoist;
+                        los_bits = pool_los(need);
+                    }
+                    bot_action(i, acts[i], (pre_done >> i) & 1u, (los_bits >> i) & 1u);
                     if (botagent && !(rng_unit53() < c.weakness)) { acts[i][0] = 1; acts[i][1] = 1; acts[i][2] = 0; }
                 }
                 if (stage == 0) continue;

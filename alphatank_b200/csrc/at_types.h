@@ -38,6 +38,8 @@ struct KCfg {
     int32_t bot_tank[MAX_TANKS];       // bot-controlled tanks in config order
     int32_t bot_ord[MAX_TANKS];        // tank -> its ordinal among the bots (0 for agents)
     int32_t n_bots;
+    int32_t first_bot_k;               // position in the acting order of the first deciding bot
+    uint32_t los_hoist;                // smart bots whose line-of-sight query can run at that point (pooled)
     uint32_t team_members[MAX_TANKS];  // bit j set: tank j is on tank i's team (incl. i)
     // observation row layout (floats)
     int32_t self_len, off_ob, off_eb, eb_stride, off_et, et_len, off_walls, off_maze, off_zones, off_flags;
@@ -78,6 +80,7 @@ struct BlockMem {
     uint8_t *slot_of;              // [n*6][BS] bullet slot of (owner, per-owner rank), valid for rank < tlive
     const float *tmpl;             // [4W + 121] wall + maze observation columns of a fixed map
     const uint8_t *udelta;         // [361] copy of st.udelta
+    uint8_t *los_q, *los_r;        // [warps][256] pooled line-of-sight job queue / answers
 };
 
 }  // namespace at
