@@ -781,10 +781,11 @@ struct Sim {
         // the muzzle position itself is never tested by the reference; the skip-ahead needs a wall-free rect
         L.accepted = first_wall(d2i(L.x), d2i(L.y), 5, 5) < 0;
     }
-    // One iteration: an optional exact skip-ahead followed by one reference sub-step.  Returns true when done.
-    AT_HD bool los_iter(Los &L) const {
-        if (L.result >= 0) return true;
-        double x = L.x, y = L.y, dx = L.dx, dy = L.dy;
+    // los_plan: the exact skip-ahead (an accelerator: it may run at any time, or never).
+    AT_HD void los_plan(Los &L) const {
+        if (L.result >= 0) return;
+        double x = L.x, y = L.y;
+        const double dx = L.dx, dy = L.dy;
         const bool stat_x = L.stat_x, stat_y = L.stat_y;
         const double inv_dx = L.inv_dx, inv_dy = L.inv_dy;
         // Exact skip-ahead.  The reference advances 1 px per sub-step and tests tanks and walls every
@@ -794,7 +795,7 @@ struct Sim {
         // event are linear in the step count, so a DDA over the leading-edge crossings finds the first
         // crossing that uncovers a wall cell; all sub-steps more than 2 before it (and before the tank
         // bound, the next binade boundary and `dist > 300`) can only be "advance": one exact jump.
-        if (L.plan_in == 0) {
+        {
             int m = 0;
             const int room = 300 - L.dist;
             if (room >= 6 && L.accepted) {
@@ -857,9 +858,15 @@ struct Sim {
             } else {
                 L.plan_in = m + 3;
             }
-        } else {
-            --L.plan_in;
         }
+        L.x = x;
+        L.y = y;
+    }
+    // los_step: one reference sub-step (tank test, wall test / bounce, advance).  Returns true when done.
+    AT_HD bool los_step(Los &L) const {
+        if (L.result >= 0) return true;
+        double x = L.x, y = L.y, dx = L.dx, dy = L.dy;
+        --L.plan_in;
         const double nx = x + dx, ny = y + dy;
         const int ix = d2i(nx), iy = d2i(ny);
         if (ix < L.bx1 + 30 && iy < L.by1 + 24 && ix + 5 > L.bx0 && iy + 5 > L.by0)  // inside the union box: test each
@@ -888,7 +895,10 @@ struct Sim {
     AT_HD bool line_of_sight(int me) const {
         Los L;
         los_init(L, tid, me);
-        while (!los_iter(L)) {}
+        for (;;) {
+            if (L.plan_in <= 0) los_plan(L);
+            if (los_step(L)) break;
+        }
         return L.result != 0;
     }
 
@@ -1018,9 +1028,11 @@ struct Sim {
             }
             next = imin(next + __popc(idle), total);
             if (__ballot_sync(wm, active) == 0u) break;
-            if (active) {
+            if (active) {  // phase-aligned: everybody plans now, then everybody takes plain sub-steps
+                if (L.plan_in <= 0) los_plan(L);
                 bool fin = false;
-                for (int it = 0; it < 4 && !fin; ++it) fin = los_iter(L);
+#pragma unroll 1
+                for (int it = 0; it < 4 && !fin; ++it) fin = los_step(L);
                 if (fin) {
                     res[myjob] = (uint8_t)(L.result != 0);
                     active = false;
