@@ -33,7 +33,7 @@ namespace {
 
 struct SmemLayout {
     int n;
-    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_thits, off_bpack, off_tlive,
+    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_nearlo, off_nearhi, off_bpack, off_tlive,
         off_tshot, off_tmpl, off_tile, off_slot, off_udelta, off_losq, total;
 };
 constexpr int TILE_FLOATS = 32 * 33;  // per warp: 32 envs x 32 observation columns, row stride 33
@@ -49,7 +49,8 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots
     L.off_bf0 = o; o += (size_t)nb * BS * 8;
     L.off_bf1 = o; o += (size_t)nb * BS * 8;
     L.off_tpack = o; o += (size_t)n * BS * 4;
-    L.off_thits = o; o += (size_t)n * BS * 4;
+    L.off_nearlo = o; o += (size_t)n * BS * 4;
+    L.off_nearhi = o; o += n * SLOTS_PER_TANK > 32 ? (size_t)n * BS * 4 : 0;
     L.off_bpack = o; o += (size_t)nb * BS * 4;
     L.off_tlive = o; o += (size_t)n * BS * 4;
     L.off_tshot = o; o += (size_t)n * BS * 4;
@@ -79,6 +80,11 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 // For fixed maps the static wall / maze columns are not emitted by the threads at all: virtual columns skip them
 // (remap) and each thread ships them with a bulk-async copy from the block's template.
 constexpr int TILE_STRIDE = 33;
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(saddr));
+    return v;
+}
 __device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t row_len, unsigned emit_mask, int lane,
                                         int j0, int ncols, int dyn_len, int head_len, int static_len, int obs_dim) {
     __syncwarp();
@@ -87,10 +93,23 @@ __device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t
     const int gcol = r * obs_dim + (kk < head_len ? kk : kk + static_len);
     if (lane < ncols) {
         float *dst = gbase + gcol;
-        const float *src = tile + lane;
+        const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + lane);
+        if (emit_mask == 0xffffffffu) {      // the usual case: 8 tile reads in flight, then 8 row-chunk stores
 #pragma unroll
-        for (int rr = 0; rr < 32; ++rr)
-            if ((emit_mask >> rr) & 1u) dst[(int64_t)rr * row_len] = src[rr * TILE_STRIDE];
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] = lds_f32(src + (uint32_t)((r0 + q) * TILE_STRIDE * 4));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { *dst = v[q]; dst += row_len; }
+            }
+        } else {
+#pragma unroll 4
+            for (int rr = 0; rr < 32; ++rr) {
+                if ((emit_mask >> rr) & 1u) *dst = lds_f32(src + (uint32_t)(rr * TILE_STRIDE * 4));
+                dst += row_len;
+            }
+        }
     }
     __syncwarp();
 }
@@ -129,7 +148,8 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
     bm.trew = (double *)(smem + L.off_trew);
     bm.bf0 = (double *)(smem + L.off_bf0); bm.bf1 = (double *)(smem + L.off_bf1);
-    bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.thits = (uint32_t *)(smem + L.off_thits);
+    bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.nearlo = (uint32_t *)(smem + L.off_nearlo);
+    bm.nearhi = (uint32_t *)(smem + L.off_nearhi);
     bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint32_t *)(smem + L.off_tlive);
     bm.tshot = (int32_t *)(smem + L.off_tshot);
     bm.slot_of = (uint8_t *)(smem + L.off_slot);
@@ -141,10 +161,23 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bm.tmpl = tmpl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 722; i += BS) bm.trig[i] = st.trig[i];
-    for (int i = tid; i < 361; i += BS) udl[i] = st.udelta[i];
+    {   // table copies: every load is issued before the first store (one round trip instead of a dozen)
+        constexpr int TRIG_IT = (722 + BS - 1) / BS, UDL_IT = (361 + BS - 1) / BS;
+        double tv[TRIG_IT];
+        uint8_t uv[UDL_IT];
+#pragma unroll
+        for (int k = 0; k < TRIG_IT; ++k) tv[k] = tid + k * BS < 722 ? __ldg(st.trig + tid + k * BS) : 0.0;
+#pragma unroll
+        for (int k = 0; k < UDL_IT; ++k) uv[k] = tid + k * BS < 361 ? __ldg(st.udelta + tid + k * BS) : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < TRIG_IT; ++k) if (tid + k * BS < 722) bm.trig[tid + k * BS] = tv[k];
+#pragma unroll
+        for (int k = 0; k < UDL_IT; ++k) if (tid + k * BS < 361) udl[tid + k * BS] = uv[k];
+    }
     if (c.map != 2) {
-        for (int i = tid; i < 4 * c.n_walls + CELLS; i += BS) tmpl[i] = g_tmpl[i];
+        const int nt = 4 * c.n_walls + CELLS;
+#pragma unroll 8
+        for (int i = tid; i < nt; i += BS) tmpl[i] = __ldg(g_tmpl + i);
         fence_async_smem();  // the template is later read by bulk-async copies
     }
     for (int i = 0; i < c.n_tanks; ++i) {  // lanes without an env still walk the emitter: give them inert data

@@ -303,6 +303,13 @@ AT_HD int popc64(uint64_t v) {
     return __builtin_popcountll(v);
 #endif
 }
+AT_HD int ctz64(uint64_t v) {  // index of the lowest set bit (v != 0)
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long)v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
 AT_HD int ffs32(uint32_t v) {  // index of the lowest set bit (v != 0)
 #ifdef __CUDA_ARCH__
     return __ffs((int)v) - 1;
@@ -346,7 +353,21 @@ struct Sim {
     AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
     AT_HD double &TREW(int i) const { return bm.trew[i * BS + tid]; }
     AT_HD uint32_t &TPACK(int i) const { return bm.tpack[i * BS + tid]; }
-    AT_HD uint32_t &THITS(int i) const { return bm.thits[i * BS + tid]; }
+    AT_HD uint32_t &THITS(int i) const { return st.thits[G(i)]; }  // touched on hits / resets only: stays in HBM
+    // bullets (slot indices) that may lie within 100 px of tank i when it acts this tick (dodge_reward candidates)
+    AT_HD void near_clear(int i) const {
+        bm.nearlo[i * BS + tid] = 0u;
+        if (c.n_tanks * SLOTS_PER_TANK > 32) bm.nearhi[i * BS + tid] = 0u;
+    }
+    AT_HD void near_set(int i, int slot) const {
+        if (slot < 32) bm.nearlo[i * BS + tid] |= 1u << slot;
+        else bm.nearhi[i * BS + tid] |= 1u << (slot - 32);
+    }
+    AT_HD uint64_t near_get(int i) const {
+        uint64_t v = bm.nearlo[i * BS + tid];
+        if (c.n_tanks * SLOTS_PER_TANK > 32) v |= (uint64_t)bm.nearhi[i * BS + tid] << 32;
+        return v;
+    }
     AT_HD uint32_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
     AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * BS + tid]; }
     // bot FSM columns exist only for bot tanks (bot_ord: ordinal among the bots)
@@ -431,7 +452,7 @@ struct Sim {
     static constexpr int AT_MODE_AGENT_ = 0, AT_MODE_BOT_AGENT_ = 1, AT_MODE_ARENA_ = 2, AT_MODE_TEAM_ = 3;
 
     // One Bullet.move().  Returns true when the bullet leaves the list.
-    AT_HD bool bullet_move(double &x, double &y, uint64_t &m) {
+    AT_HD bool bullet_move(double &x, double &y, uint64_t &m, uint32_t &near_tanks) {
         const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u);
         const bool fx = (m >> BM_FLIPX) & 1u, fy = (m >> BM_FLIPY) & 1u;
         int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
@@ -452,6 +473,8 @@ struct Sim {
             for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // alive enemies
                 const int i = ffs32(bits);
                 const double tx = TX(i) - x, ty = TY(i) - y;
+                // dodge_reward candidate: the tank moves <= 10 px and this bullet <= 1 px per axis before that test
+                if (fabs(tx) < 113.0 && fabs(ty) < 113.0) near_tanks |= 1u << i;
                 if (fabs(tx) > 301.0 || fabs(ty) > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
                 const double s2 = np_dot2(tx, ty, tx, ty);
                 if (s2 > S300) continue;                              // dist > BULLET_MAX_DISTANCE
@@ -530,7 +553,7 @@ struct Sim {
     AT_HD void bullets_pass() {
         const uint32_t n = cnt;
         uint32_t w = 0;
-        for (int i = 0; i < c.n_tanks; ++i) TLIVE(i) = 0;
+        for (int i = 0; i < c.n_tanks; ++i) { TLIVE(i) = 0; near_clear(i); }
         tclo = 0; tchi = 0;
         if (n > 0)
             for (uint32_t bits = alive_bits; bits; bits &= bits - 1) {  // cells under Rect(x-15, y-12, 30, 24)
@@ -554,8 +577,10 @@ struct Sim {
             double x = nx_, y = ny_;
             uint64_t m = nm_;
             if (r + 1 < n) { nx_ = st.bx[G(r + 1)]; ny_ = st.by[G(r + 1)]; nm_ = st.bmeta[G(r + 1)]; }
-            if (!bullet_move(x, y, m)) {
+            uint32_t near_tanks = 0;
+            if (!bullet_move(x, y, m, near_tanks)) {
                 const int ow = (int)(m & 15u);
+                for (; near_tanks; near_tanks &= near_tanks - 1) near_set(ffs32(near_tanks), (int)w);
                 uint32_t rank = TLIVE(ow)++;
                 bm.slot_of[(ow * SLOTS_PER_TANK + (int)rank) * BS + tid] = (uint8_t)w;
                 m = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
@@ -606,6 +631,8 @@ struct Sim {
         st.by[G(cnt)] = TY(i) - 10 * sv;
         uint32_t rank = TLIVE(i)++;
         st.bmeta[G(cnt)] = (uint64_t)i | ((uint64_t)a << BM_ANGLE) | ((uint64_t)rank << BM_RANK);
+        for (uint32_t bits = ((1u << c.n_tanks) - 1u) & ~c.team_members[i]; bits; bits &= bits - 1)
+            near_set(ffs32(bits), (int)cnt);  // a fresh bullet is a candidate for every enemy that acts later
         ++cnt;
         TSHOT(i) = now;
     }
@@ -617,12 +644,16 @@ struct Sim {
         const int myteam = c.team[i];
         double reward = 0;
         const double mx = TX(i), my = TY(i);
-        for (uint32_t r = 0; r < cnt; ++r) {
+        // only the candidates flagged by the bullet pass / shoot() are visited, in slot order (= list order);
+        // every other enemy bullet is provably >= 100 px away and would hit `continue` (sprite.py:508)
+        for (uint64_t cand = near_get(i); cand; cand &= cand - 1) {
+            const int r = ctz64(cand);
             const uint64_t m = st.bmeta[G(r)];
+            const double bxv = st.bx[G(r)], byv = st.by[G(r)];
             if (c.team[(int)(m & 15u)] == myteam) continue;
-            const double ex_ = mx - st.bx[G(r)];
+            const double ex_ = mx - bxv;
             if (fabs(ex_) >= 101.0) continue;                          // distance >= 100 for sure
-            const double ey_ = my - st.by[G(r)];
+            const double ey_ = my - byv;
             if (!(np_dot2(ex_, ey_, ex_, ey_) < S100)) continue;       // `distance >= 100: continue` (sprite.py:508)
             const int ba = (int)((m >> BM_ANGLE) & 511u);
             double u0, u1;
@@ -1375,14 +1406,28 @@ struct Sim {
                 const int owner = o == 0 ? t : (o <= t ? o - 1 : o);
                 const uint32_t live = TLIVE(owner);
                 const float same = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
+                // all of the owner's live records are requested before the first one is used: one L2 round trip
+                // per owner instead of one per slot (the emitter is otherwise a chain of dependent loads)
+                double bxv[SLOTS_PER_TANK], byv[SLOTS_PER_TANK];
+                uint64_t bmv[SLOTS_PER_TANK];
+#pragma unroll
+                for (int k = 0; k < SLOTS_PER_TANK; ++k) {
+                    bxv[k] = 0.0; byv[k] = 0.0; bmv[k] = 0;
+                    if ((uint32_t)k < live) {
+                        const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
+                        bmv[k] = st.bmeta[G(slot)];
+                        bxv[k] = st.bx[G(slot)];
+                        byv[k] = st.by[G(slot)];
+                    }
+                }
+#pragma unroll
                 for (int k = 0; k < SLOTS_PER_TANK; ++k) {
                     const bool has = (uint32_t)k < live;
                     double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
                     if (has) {
-                        const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
-                        const uint64_t m = st.bmeta[G(slot)];
-                        x = st.bx[G(slot)];
-                        y = st.by[G(slot)];
+                        const uint64_t m = bmv[k];
+                        x = bxv[k];
+                        y = byv[k];
                         const int ang = (int)((m >> BM_ANGLE) & 511u);
                         const double cv = cosr(ang), sv = sinr(ang);
                         dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv;
@@ -1437,7 +1482,7 @@ struct Sim {
         else { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
         for (int i = 0; i < c.n_tanks; ++i) {
             TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
-            TPACK(i) = st.tpack[G(i)]; THITS(i) = st.thits[G(i)]; TSHOT(i) = st.tshot[G(i)];
+            TPACK(i) = st.tpack[G(i)]; TSHOT(i) = st.tshot[G(i)];
             if (c.ctrl[i] == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
             if (TPACK(i) & TP_ALIVE) alive_bits |= 1u << i;
         }
@@ -1455,7 +1500,7 @@ struct Sim {
         if (c.map == 2) { st.wall_lo[e] = wlo; st.wall_hi[e] = whi; }
         for (int i = 0; i < c.n_tanks; ++i) {
             st.tx[G(i)] = TX(i); st.ty[G(i)] = TY(i); st.trew[G(i)] = TREW(i);
-            st.tpack[G(i)] = TPACK(i); st.thits[G(i)] = THITS(i); st.tshot[G(i)] = TSHOT(i);
+            st.tpack[G(i)] = TPACK(i); st.tshot[G(i)] = TSHOT(i);
             if (c.ctrl[i] == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
         }
     }

@@ -99,16 +99,17 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->st.bfs_tab = (const uint16_t *)(env->arena.data() + L.o_bfs);
     }
     const int n = env->k.n_tanks;
-    env->block.assign((size_t)n * BS * (5 * 8 + 5 * 4) + 722 * 8, 0);
+    env->block.assign((size_t)n * BS * (5 * 8 + 6 * 4) + 722 * 8, 0);
     char *p = env->block.data();
     BlockMem &bm = env->bm;
     bm.trig = (double *)p; p += 722 * 8;
     memcpy(bm.trig, env->luts.trig.data(), 722 * 8);
     bm.tx = (double *)p; p += n * BS * 8; bm.ty = (double *)p; p += n * BS * 8; bm.trew = (double *)p; p += n * BS * 8;
     bm.bf0 = (double *)p; p += n * BS * 8; bm.bf1 = (double *)p; p += n * BS * 8;
-    bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.thits = (uint32_t *)p; p += n * BS * 4;
+    bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.nearlo = (uint32_t *)p; p += n * BS * 4;
     bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint32_t *)p; p += n * BS * 4;
     bm.tshot = (int32_t *)p; p += n * BS * 4;
+    bm.nearhi = (uint32_t *)p; p += n * BS * 4;
     env->tmpl.assign(4 * 72 + CELLS, 0.f);
     if (env->k.map != AT_MAP_MAZE) fill_static_template(env->k.wall_lo, env->k.wall_hi, env->tmpl.data());
     env->slot_of.assign((size_t)n * SLOTS_PER_TANK * BS, 0);
