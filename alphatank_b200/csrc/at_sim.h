@@ -406,21 +406,37 @@ struct Sim {
     AT_HD bool tank_cell_at(int idx) const { return ((idx < 64 ? tclo >> idx : tchi >> (idx - 64)) & 1ull) != 0; }
     AT_HD bool near_at(int idx) const { return ((idx < 64 ? nlo >> idx : nhi >> (idx - 64)) & 1ull) != 0; }
 
-    // first wall (row-major = reference list order, gaming_env.py:610-615) that a w x h pygame.Rect at
-    // integer (ix, iy) collides with; -1 if none.  Replaces `for wall in walls: colliderect` scans.
-    AT_HD int first_wall(int ix, int iy, int w, int h) const {
+    // The <= 2 x 2 cells under a w x h rect (w, h <= 70) at integer (ix, iy): index of the top-left cell and a
+    // 13-bit selector with bit 0 / 1 / 11 / 12 = that cell / right / below / below-right (ascending bit order is
+    // row-major order = the reference's wall list order, gaming_env.py:610-615).  sel == 0: outside the grid.
+    AT_HD static void rect_cells(int ix, int iy, int w, int h, int &idx00, uint32_t &sel) {
         int c0, c1, r0, r1;
-        if ((ix | iy) >= 0) {  // one division per axis; the far edge is at most one cell further (w, h <= 70)
+        if ((ix | iy) >= 0) {  // one division per axis; the far edge is at most one cell further
             c0 = ix / 70; c1 = imin(c0 + ((ix - 70 * c0 + w - 1) >= 70 ? 1 : 0), 10);
             r0 = iy / 70; r1 = imin(r0 + ((iy - 70 * r0 + h - 1) >= 70 ? 1 : 0), 10);
         } else {               // look-ahead rects of the dodge bot may leave the arena (App. H note)
             c0 = imax(fdiv70(ix), 0); c1 = imin(fdiv70(ix + w - 1), 10);
             r0 = imax(fdiv70(iy), 0); r1 = imin(fdiv70(iy + h - 1), 10);
         }
-        for (int r = r0; r <= r1; ++r)
-            for (int cc = c0; cc <= c1; ++cc)
-                if (wall_at(r * 11 + cc)) return r * 11 + cc;
-        return -1;
+        const bool ok = c0 <= c1 && r0 <= r1 && c0 <= 10 && r0 <= 10;
+        const uint32_t dc = c1 > c0 ? 1u : 0u, dr = r1 > r0 ? 1u : 0u;
+        idx00 = ok ? r0 * 11 + c0 : 0;
+        sel = ok ? (1u | (dc << 1) | (dr << 11) | ((dc & dr) << 12)) : 0u;
+    }
+    AT_HD static uint32_t window13(uint64_t lo, uint64_t hi, int idx) {  // bits [idx, idx + 13) of a 128-bit mask
+        const uint64_t a = idx < 64 ? lo : hi, b = idx < 64 ? hi : 0ull;
+        const int sh = idx & 63;
+        const uint64_t v = (a >> sh) | ((b << 1) << (63 - sh));
+        return (uint32_t)v & 0x1FFFu;
+    }
+    // first wall in list order that a w x h pygame.Rect at integer (ix, iy) collides with; -1 if none.
+    // Replaces `for wall in walls: colliderect` scans.
+    AT_HD int first_wall(int ix, int iy, int w, int h) const {
+        int idx00;
+        uint32_t sel;
+        rect_cells(ix, iy, w, h, idx00, sel);
+        const uint32_t ww = window13(wlo, whi, idx00) & sel;
+        return ww ? idx00 + ffs32(ww) : -1;
     }
     AT_HD static bool rect5_hits_cell(int ix, int iy, int cell) {  // Rect(ix,iy,5,5) vs the 70x70 wall rect
         int X = (cell % 11) * 70, Y = (cell / 11) * 70;
@@ -496,27 +512,18 @@ struct Sim {
             }
         }
         bool nfx = fx, nfy = fy;
-        // one pass over the <= 4 cells under the 5x5 rect: first wall in list order + "is any tank rect here?"
+        // the <= 4 cells under the 5x5 rect, branch-free: first wall in list order + "is any tank rect here?"
         int cell = -1;
         bool near_tank = false;
         {
-            int c0, c1, r0, r1;
-            if ((ix | iy) >= 0) {
-                c0 = ix / 70; c1 = imin(c0 + ((ix - 70 * c0 + 4) >= 70 ? 1 : 0), 10);
-                r0 = iy / 70; r1 = imin(r0 + ((iy - 70 * r0 + 4) >= 70 ? 1 : 0), 10);
-            } else {
-                c0 = imax(fdiv70(ix), 0); c1 = imin(fdiv70(ix + 4), 10);
-                r0 = imax(fdiv70(iy), 0); r1 = imin(fdiv70(iy + 4), 10);
+            int idx00;
+            uint32_t sel;
+            rect_cells(ix, iy, 5, 5, idx00, sel);
+            if (window13(iclo, ichi, idx00) & sel) {  // some cell holds a wall or lies under a tank rect
+                const uint32_t ww = window13(wlo, whi, idx00) & sel;
+                cell = ww ? idx00 + ffs32(ww) : -1;
+                near_tank = (window13(tclo, tchi, idx00) & sel) != 0u;
             }
-            const int idx0 = r0 * 11 + c0;
-            const bool quiet = c0 == c1 && r0 == r1 && !(((idx0 < 64 ? iclo >> idx0 : ichi >> (idx0 - 64)) & 1ull) != 0);
-            if (!quiet)
-                for (int r = r1; r >= r0; --r)
-                    for (int cc = c1; cc >= c0; --cc) {
-                        const int idx = r * 11 + cc;
-                        if (wall_at(idx)) cell = idx;  // descending scan: the last hit kept is the row-major first
-                        near_tank = near_tank || tank_cell_at(idx);
-                    }
         }
         if (cell >= 0) {  // sprite.py:66-82 (F12)
             bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
@@ -527,25 +534,28 @@ struct Sim {
         x = nx;
         y = ny;
         ++dist;
+        // single exit: the warp reconverges before the record is packed / stored by the caller
+        int victim = -1;
         if (near_tank)
             for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // sprite.py:88-100
                 const int i = ffs32(bits);
-                if (rect5_hits_tank(ix, iy, i)) {
-                    if (c.terminate_time == 0) { TPACK(i) &= ~TP_ALIVE; alive_bits &= ~(1u << i); }
-                    THITS(owner) += 1u;
-                    THITS(i) += 1u << 16;
-                    reward_by_bullets(owner, i);
-                    return true;
-                }
+                if (rect5_hits_tank(ix, iy, i)) { victim = i; break; }
             }
-        if (bounces >= 6 || dist >= 300) {  // sprite.py:102-111
+        bool gone = false;
+        if (victim >= 0) {
+            if (c.terminate_time == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
+            THITS(owner) += 1u;
+            THITS(victim) += 1u << 16;
+            reward_by_bullets(owner, victim);
+            gone = true;
+        } else if (bounces >= 6 || dist >= 300) {  // sprite.py:102-111
             if (!cleared && pcnt > 0) TREW(owner) -= ldg(st.pend + pcnt);
-            return true;
+            gone = true;
         }
         m = (uint64_t)owner | ((uint64_t)ang << BM_ANGLE) | ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) |
             ((uint64_t)bounces << BM_BOUNCES) | ((uint64_t)cleared << BM_CLEARED) | ((uint64_t)dist << BM_DIST) |
             ((uint64_t)pcnt << BM_PEND);
-        return false;
+        return gone;
     }
 
     // `for bullet in self.bullets[:]: bullet.move()` (gaming_env.py:71-72, 378-379): firing order, stable
@@ -1379,6 +1389,20 @@ struct Sim {
     // layout order, exactly like the reference builds its list.  Runs one thread per env: control flow is
     // uniform across the warp (slot loops run to 6 with a predicate), so all 32 lanes emit column j together and
     // the sink can transpose 32 envs x 32 columns through shared memory into coalesced row-chunk stores.
+    // record of observation slot f of agent tank t's row (f / 6 = position in the owner order: t first, then the
+    // other tanks); bit 63 of m marks "slot holds a live bullet"
+    AT_HD void fetch_slot(int t, int f, int nslots, uint64_t &m, double &x, double &y) const {
+        m = 0; x = 0.0; y = 0.0;
+        if (f >= nslots) return;
+        const int o = f / SLOTS_PER_TANK, k = f - o * SLOTS_PER_TANK;
+        const int owner = o == 0 ? t : (o <= t ? o - 1 : o);
+        if ((uint32_t)k < TLIVE(owner)) {
+            const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
+            m = st.bmeta[G(slot)] | (1ull << 63);
+            x = st.bx[G(slot)];
+            y = st.by[G(slot)];
+        }
+    }
     template <class Sink>
     AT_HD void emit_tank_common(Sink &out, int i) const {
         const double x = TX(i), y = TY(i);
@@ -1402,44 +1426,38 @@ struct Sim {
             emit_tank_common(out, t);
             if (team) out.put(1.0f);
             out.put(t_alive(t) ? 1.0f : 0.0f);
-            for (int o = 0; o < c.n_tanks; ++o) {  // own bullets first, then every other tank's, in tank order
-                const int owner = o == 0 ? t : (o <= t ? o - 1 : o);
-                const uint32_t live = TLIVE(owner);
-                const float same = c.team[owner] == c.team[t] ? 1.0f : 0.0f;
-                // all of the owner's live records are requested before the first one is used: one L2 round trip
-                // per owner instead of one per slot (the emitter is otherwise a chain of dependent loads)
-                double bxv[SLOTS_PER_TANK], byv[SLOTS_PER_TANK];
-                uint64_t bmv[SLOTS_PER_TANK];
-#pragma unroll
-                for (int k = 0; k < SLOTS_PER_TANK; ++k) {
-                    bxv[k] = 0.0; byv[k] = 0.0; bmv[k] = 0;
-                    if ((uint32_t)k < live) {
-                        const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
-                        bmv[k] = st.bmeta[G(slot)];
-                        bxv[k] = st.bx[G(slot)];
-                        byv[k] = st.by[G(slot)];
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < SLOTS_PER_TANK; ++k) {
-                    const bool has = (uint32_t)k < live;
+            // bullet slots: own 6 first, then every other tank's in tank order (zeros beyond an owner's live
+            // ones).  One rolled loop over the n*6 slots (small code: the kernel is instruction-cache bound) with
+            // the records requested two iterations ahead, so their L2 latency overlaps the emission.
+            {
+                const int nslots = c.n_tanks * SLOTS_PER_TANK;
+                uint64_t m0, m1;
+                double x0, y0, x1, y1;
+                fetch_slot(t, 0, nslots, m0, x0, y0);
+                fetch_slot(t, 1, nslots, m1, x1, y1);
+#pragma unroll 1
+                for (int f = 0; f < nslots; ++f) {
+                    const uint64_t m = m0;
+                    const double bxv = x0, byv = y0;
+                    m0 = m1; x0 = x1; y0 = y1;
+                    fetch_slot(t, f + 2, nslots, m1, x1, y1);
+                    const bool has = (m >> 63) != 0;
                     double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
                     if (has) {
-                        const uint64_t m = bmv[k];
-                        x = bxv[k];
-                        y = byv[k];
+                        x = bxv;
+                        y = byv;
                         const int ang = (int)((m >> BM_ANGLE) & 511u);
                         const double cv = cosr(ang), sv = sinr(ang);
                         dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv;
                         dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
                     }
                     out.put((float)x); out.put((float)y); out.put((float)dx); out.put((float)dy);
-                    if (o != 0) {
+                    if (f >= SLOTS_PER_TANK) {
                         const double rx = x - ax, ry = y - ay;
                         out.put(has ? (float)rx : 0.0f);
                         out.put(has ? (float)ry : 0.0f);
                         out.put(has ? (float)sqrt(rx * rx + ry * ry) : 0.0f);
-                        if (team) out.put(has ? same : 0.0f);
+                        if (team) out.put(has && c.team[(int)(m & 15u)] == c.team[t] ? 1.0f : 0.0f);
                     }
                 }
             }
