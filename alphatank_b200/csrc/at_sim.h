@@ -646,7 +646,9 @@ struct Sim {
         ++cnt;
         TSHOT(i) = now;
     }
-    AT_HD void dodge_reward(int i) {  // sprite.py:497-525 (F17)
+    // `cand` = near_get(i); (pm, px, py) = the record of its lowest slot, requested by the caller before the wall
+    // test so that the L2 round trip overlaps it
+    AT_HD void dodge_reward(int i, uint64_t cand, uint64_t pm, double px, double py) {  // sprite.py:497-525 (F17)
         const int sp = t_speed(i);
         if (sp == 0) return;  // projection is exactly 0: reward unchanged
         const int a = t_angle(i);
@@ -656,10 +658,11 @@ struct Sim {
         const double mx = TX(i), my = TY(i);
         // only the candidates flagged by the bullet pass / shoot() are visited, in slot order (= list order);
         // every other enemy bullet is provably >= 100 px away and would hit `continue` (sprite.py:508)
-        for (uint64_t cand = near_get(i); cand; cand &= cand - 1) {
+        for (bool first = true; cand; cand &= cand - 1, first = false) {
             const int r = ctz64(cand);
-            const uint64_t m = st.bmeta[G(r)];
-            const double bxv = st.bx[G(r)], byv = st.by[G(r)];
+            uint64_t m = pm;
+            double bxv = px, byv = py;
+            if (!first) { m = st.bmeta[G(r)]; bxv = st.bx[G(r)]; byv = st.by[G(r)]; }
             if (c.team[(int)(m & 15u)] == myteam) continue;
             const double ex_ = mx - bxv;
             if (fabs(ex_) >= 101.0) continue;                          // distance >= 100 for sure
@@ -691,17 +694,26 @@ struct Sim {
             mnx = kx[k] < mnx ? kx[k] : mnx; mxx = kx[k] > mxx ? kx[k] : mxx;
             mny = ky[k] < mny ? ky[k] : mny; mxy = ky[k] > mxy ? ky[k] : mxy;
         }
-        int c0 = imax((int)floor((mnx - 0.02) / 70.0) - 1, 0), c1 = imin((int)floor((mxx + 0.02) / 70.0), 10);
-        int r0 = imax((int)floor((mny - 0.02) / 70.0) - 1, 0), r1 = imin((int)floor((mxy + 0.02) / 70.0), 10);
-        bool any = false;
-        for (int r = r0; r <= r1; ++r)
-            for (int cc = c0; cc <= c1; ++cc) any = any || wall_at(r * 11 + cc);
-        if (!any) return false;
+        // candidate cells: a conservative superset is enough (every candidate gets the exact test below), so the
+        // bounds use a reciprocal multiply; the 0.02 vs 0.01 slack absorbs its last-bit difference from a division
+        constexpr double INV70 = 1.0 / 70.0;
+        const int c0 = imax((int)floor((mnx - 0.02) * INV70) - 1, 0), c1 = imin((int)floor((mxx + 0.02) * INV70), 10);
+        const int r0 = imax((int)floor((mny - 0.02) * INV70) - 1, 0), r1 = imin((int)floor((mxy + 0.02) * INV70), 10);
+        if (c0 > c1 || r0 > r1) return false;
+        {
+            const uint32_t colmask = ((2u << (c1 - c0)) - 1u) << c0;
+            uint32_t any = 0u;
+#pragma unroll 1
+            for (int r = r0; r <= r1; ++r) any |= window13(wlo, whi, r * 11) & colmask;
+            if (!any) return false;
+        }
         // the reference tests 4 axes per wall (2 OBB axes, x, y) and needs all of them to overlap: test the cheap
         // x / y axes first and build the OBB axes (2 sqrt, 4 divisions) only for a wall that survives them
         bool have_axes = false;
         double ax[2] = {0, 0}, ay[2] = {0, 0}, omin[2] = {0, 0}, omax[2] = {0, 0};
+#pragma unroll 1
         for (int r = r0; r <= r1; ++r)
+#pragma unroll 1
             for (int cc = c0; cc <= c1; ++cc) {
                 if (!wall_at(r * 11 + cc)) continue;
                 const double X0 = (double)(cc * 70), X1 = (double)(cc * 70 + 70), Y0 = (double)(r * 70),
@@ -740,6 +752,10 @@ struct Sim {
         if (!t_alive(i)) return;
         const int a = t_angle(i), sp = t_speed(i);
         const double nx = TX(i) + (double)sp * cosr(a), ny = TY(i) - (double)sp * sinr(a);
+        const uint64_t cand = sp != 0 ? near_get(i) : 0ull;
+        uint64_t pm = 0;
+        double px = 0.0, py = 0.0;
+        if (cand) { const int r = ctz64(cand); pm = st.bmeta[G(r)]; px = st.bx[G(r)]; py = st.by[G(r)]; }
         if (!obb_hits_walls(nx, ny, a)) {
             TX(i) = nx;
             TY(i) = ny;
@@ -747,7 +763,7 @@ struct Sim {
         } else {
             TPACK(i) |= TP_HW;
         }
-        dodge_reward(i);
+        dodge_reward(i, cand, pm, px, py);
     }
     AT_HD void apply_action(int i, int a0, int a1, int a2, int fwd, int back, int stop_speed) {
         if (a0 == 0) rotate(i, 3);
@@ -1390,15 +1406,16 @@ struct Sim {
     // uniform across the warp (slot loops run to 6 with a predicate), so all 32 lanes emit column j together and
     // the sink can transpose 32 envs x 32 columns through shared memory into coalesced row-chunk stores.
     // record of observation slot f of agent tank t's row (f / 6 = position in the owner order: t first, then the
-    // other tanks); bit 63 of m marks "slot holds a live bullet"
-    AT_HD void fetch_slot(int t, int f, int nslots, uint64_t &m, double &x, double &y) const {
-        m = 0; x = 0.0; y = 0.0;
+    // other tanks).  The loaded values are not touched here, so the loads stay in flight until they are used.
+    AT_HD void fetch_slot(int t, int f, int nslots, bool &has, uint64_t &m, double &x, double &y) const {
+        has = false; m = 0; x = 0.0; y = 0.0;
         if (f >= nslots) return;
         const int o = f / SLOTS_PER_TANK, k = f - o * SLOTS_PER_TANK;
         const int owner = o == 0 ? t : (o <= t ? o - 1 : o);
         if ((uint32_t)k < TLIVE(owner)) {
             const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
-            m = st.bmeta[G(slot)] | (1ull << 63);
+            has = true;
+            m = st.bmeta[G(slot)];
             x = st.bx[G(slot)];
             y = st.by[G(slot)];
         }
@@ -1419,6 +1436,10 @@ struct Sim {
     template <class Sink>
     AT_HD void emit_rows(Sink &out) const {
         const bool team = c.team_layout != 0;
+#ifdef __CUDA_ARCH__
+        for (int i = 0; i < c.n_tanks; ++i)  // corner-offset LUT entries (one 32-byte sector each) -> L1
+            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(st.corn + 4 * t_angle(i)));
+#endif
         for (int r = 0; r < c.rows; ++r) {
             const int t = team ? c.agent_tank[r] : r;
             const double ax = TX(t), ay = TY(t);
@@ -1430,18 +1451,11 @@ struct Sim {
             // ones).  One rolled loop over the n*6 slots (small code: the kernel is instruction-cache bound) with
             // the records requested two iterations ahead, so their L2 latency overlaps the emission.
             {
-                const int nslots = c.n_tanks * SLOTS_PER_TANK;
+                const int nslots = c.n_tanks * SLOTS_PER_TANK;  // even
                 uint64_t m0, m1;
                 double x0, y0, x1, y1;
-                fetch_slot(t, 0, nslots, m0, x0, y0);
-                fetch_slot(t, 1, nslots, m1, x1, y1);
-#pragma unroll 1
-                for (int f = 0; f < nslots; ++f) {
-                    const uint64_t m = m0;
-                    const double bxv = x0, byv = y0;
-                    m0 = m1; x0 = x1; y0 = y1;
-                    fetch_slot(t, f + 2, nslots, m1, x1, y1);
-                    const bool has = (m >> 63) != 0;
+                bool h0, h1;
+                auto emit_slot = [&](int f, bool has, uint64_t m, double bxv, double byv) {
                     double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
                     if (has) {
                         x = bxv;
@@ -1459,6 +1473,16 @@ struct Sim {
                         out.put(has ? (float)sqrt(rx * rx + ry * ry) : 0.0f);
                         if (team) out.put(has && c.team[(int)(m & 15u)] == c.team[t] ? 1.0f : 0.0f);
                     }
+                };
+                // two register sets used alternately (a register move of an in-flight load would wait for it)
+                fetch_slot(t, 0, nslots, h0, m0, x0, y0);
+                fetch_slot(t, 1, nslots, h1, m1, x1, y1);
+#pragma unroll 1
+                for (int f = 0; f < nslots; f += 2) {
+                    emit_slot(f, h0, m0, x0, y0);
+                    fetch_slot(t, f + 2, nslots, h0, m0, x0, y0);
+                    emit_slot(f + 1, h1, m1, x1, y1);
+                    fetch_slot(t, f + 3, nslots, h1, m1, x1, y1);
                 }
             }
             for (int i = 0; i < c.n_tanks; ++i) {
