@@ -31,12 +31,12 @@ using namespace at;
 // ------------------------------------------------------------------------------------------------ device
 namespace {
 
+constexpr int TILE_FLOATS = 32 * 33;  // per warp: 32 envs x 32 observation columns, row stride 33
 struct SmemLayout {
     int n;
     size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_nearlo, off_nearhi, off_bpack, off_tlive,
         off_tshot, off_tmpl, off_tile, off_slot, off_udelta, off_losq, total;
 };
-constexpr int TILE_FLOATS = 32 * 33;  // per warp: 32 envs x 32 observation columns, row stride 33
 __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots) {
     const int nb = n_bots > 0 ? n_bots : 1;
     SmemLayout L;
@@ -75,31 +75,34 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 // Observation sink of one warp.  Every lane (= env) emits the same (virtual) column at the same time into its own
 // row of a 32 x 33-float shared-memory tile (odd row stride => the 32 lanes hit 32 different banks, and so does a
-// warp reading one tile row).  After 32 columns the warp flushes the tile: for each env row, lane L stores column
-// j0 + L - one coalesced 128-byte run per store instruction, addresses are immediates off two per-lane bases.
-// For fixed maps the static wall / maze columns are not emitted by the threads at all: virtual columns skip them
-// (remap) and each thread ships them with a bulk-async copy from the block's template.
+// warp reading one tile column).  The emitter announces groups of values with reserve(n); when a group does not
+// fit, the warp flushes the tile: for each env row, lane L stores column j0 + L - one coalesced <= 128-byte run per
+// store instruction.  (A per-thread staging row drained with 16-byte stores was tried: fewer instructions, but the
+// 16-byte row alignment it needs makes every scalar put a 4-way bank conflict and it was slower.)
+// For fixed maps the static wall / maze columns are not emitted at all: virtual columns skip them and each thread
+// ships them with a bulk-async copy from the block's template.
 constexpr int TILE_STRIDE = 33;
 __device__ __forceinline__ float lds_f32(uint32_t saddr) {
     float v;
     asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(saddr));
     return v;
 }
+// columns [0, ncols) of the tile are virtual columns k0 .. of observation row r0 (and continue into row r0 + 1)
 __device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t row_len, unsigned emit_mask, int lane,
-                                        int j0, int ncols, int dyn_len, int head_len, int static_len, int obs_dim) {
+                                        int r0, int k0, int ncols, int dyn_len, int head_len, int static_len, int obs_dim) {
     __syncwarp();
-    const int jv = j0 + lane;               // virtual column handled by this lane
-    const int r = jv / dyn_len, kk = jv - r * dyn_len;
+    int kk = k0 + lane, r = r0;
+    if (kk >= dyn_len) { kk -= dyn_len; ++r; }
     const int gcol = r * obs_dim + (kk < head_len ? kk : kk + static_len);
     if (lane < ncols) {
         float *dst = gbase + gcol;
         const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + lane);
         if (emit_mask == 0xffffffffu) {      // the usual case: 8 tile reads in flight, then 8 row-chunk stores
 #pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 8) {
+            for (int q0 = 0; q0 < 32; q0 += 8) {
                 float v[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = lds_f32(src + (uint32_t)((r0 + q) * TILE_STRIDE * 4));
+                for (int q = 0; q < 8; ++q) v[q] = lds_f32(src + (uint32_t)((q0 + q) * TILE_STRIDE * 4));
 #pragma unroll
                 for (int q = 0; q < 8; ++q) { *dst = v[q]; dst += row_len; }
             }
@@ -119,19 +122,22 @@ struct TileSink {  // kept in registers: flush takes everything by value
     float *gbase;       // obs row of the warp's lane 0
     int64_t row_len;    // R * D floats per env
     unsigned emit_mask; // lanes whose env gets an observation
-    int lane, j0, jj;   // columns [j0, j0 + jj) are in the tile
+    int lane, jj;       // tile columns [0, jj) are filled
+    int r0, k0;         // ... with virtual columns k0.. of observation row r0
     int dyn_len, head_len, static_len, obs_dim;
-    __device__ __forceinline__ void put(float v) {
-        my[jj] = v;
-        if (++jj == 32) {
-            tile_flush(tile, gbase, row_len, emit_mask, lane, j0, 32, dyn_len, head_len, static_len, obs_dim);
-            j0 += 32;
-            jj = 0;
-        }
+    __device__ __forceinline__ void put(float v) { my[jj++] = v; }
+    __device__ __forceinline__ void flush() {
+        tile_flush(tile, gbase, row_len, emit_mask, lane, r0, k0, jj, dyn_len, head_len, static_len, obs_dim);
+        k0 += jj;
+        if (k0 >= dyn_len) { k0 -= dyn_len; ++r0; }
+        jj = 0;
+    }
+    __device__ __forceinline__ void reserve(int n) {   // n <= 32
+        if (jj + n > 32) flush();
     }
     __device__ __forceinline__ void skip_static(const float *, int) {}  // shipped by bulk copies from the template
     __device__ __forceinline__ void finish() {
-        if (jj) tile_flush(tile, gbase, row_len, emit_mask, lane, j0, jj, dyn_len, head_len, static_len, obs_dim);
+        if (jj) flush();
     }
 };
 
@@ -254,8 +260,9 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     out.row_len = row_len;
     out.emit_mask = emit_mask;
     out.lane = lane;
-    out.j0 = 0;
     out.jj = 0;
+    out.r0 = 0;
+    out.k0 = 0;
     out.static_len = static_len;
     out.head_len = c.off_walls;
     out.dyn_len = c.obs_dim - static_len;

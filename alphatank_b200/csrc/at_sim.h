@@ -1402,9 +1402,10 @@ struct Sim {
 
     // ---------------------------------------------------------------- observation rows
     // gym_env.py:105-183 (1v1 layout) / gym_env_multi.py:225-304 (team layout), one value after the other in
-    // layout order, exactly like the reference builds its list.  Runs one thread per env: control flow is
-    // uniform across the warp (slot loops run to 6 with a predicate), so all 32 lanes emit column j together and
-    // the sink can transpose 32 envs x 32 columns through shared memory into coalesced row-chunk stores.
+    // layout order, exactly like the reference builds its list.  Runs one thread per env; values go to a sink
+    // (`reserve(n)` announces a group of <= n puts, `skip_static` jumps over the template columns).  Control flow
+    // is uniform across the warp (slot loops run over all 6 n slots with a predicate), so all 32 lanes emit column j
+    // together and the GPU sink can transpose 32 envs x 32 columns through shared memory (at_kernels.cu: TileSink).
     // record of observation slot f of agent tank t's row (f / 6 = position in the owner order: t first, then the
     // other tanks).  The loaded values are not touched here, so the loads stay in flight until they are used.
     AT_HD void fetch_slot(int t, int f, int nslots, bool &has, uint64_t &m, double &x, double &y) const {
@@ -1443,6 +1444,7 @@ struct Sim {
         for (int r = 0; r < c.rows; ++r) {
             const int t = team ? c.agent_tank[r] : r;
             const double ax = TX(t), ay = TY(t);
+            out.reserve(15);
             out.put((float)ax); out.put((float)ay);
             emit_tank_common(out, t);
             if (team) out.put(1.0f);
@@ -1451,7 +1453,7 @@ struct Sim {
             // ones).  One rolled loop over the n*6 slots (small code: the kernel is instruction-cache bound) with
             // the records requested two iterations ahead, so their L2 latency overlaps the emission.
             {
-                const int nslots = c.n_tanks * SLOTS_PER_TANK;  // even
+                const int nslots = c.n_tanks * SLOTS_PER_TANK;
                 uint64_t m0, m1;
                 double x0, y0, x1, y1;
                 bool h0, h1;
@@ -1465,6 +1467,7 @@ struct Sim {
                         dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv;
                         dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
                     }
+                    out.reserve(8);
                     out.put((float)x); out.put((float)y); out.put((float)dx); out.put((float)dy);
                     if (f >= SLOTS_PER_TANK) {
                         const double rx = x - ax, ry = y - ay;
@@ -1489,6 +1492,7 @@ struct Sim {
                 if (i == t) continue;
                 const double x = TX(i), y = TY(i);
                 const double rx = x - ax, ry = y - ay;
+                out.reserve(18);
                 out.put((float)x); out.put((float)y); out.put((float)rx); out.put((float)ry);
                 out.put((float)sqrt(rx * rx + ry * ry));
                 emit_tank_common(out, i);
@@ -1502,15 +1506,18 @@ struct Sim {
                 for (int k = 0; k < c.n_walls; ++k) {  // k-th wall in row-major order (uniform trip count)
                     const int cell = select_bit(wm, k);
                     const float X = (float)((cell % 11) * 70), Y = (float)((cell / 11) * 70);
+                    out.reserve(4);
                     out.put(X); out.put(Y); out.put(X + 70.0f); out.put(Y + 70.0f);
                 }
-                for (int cell = 0; cell < CELLS; ++cell) out.put(wall_at(cell) ? 1.0f : 0.0f);
+                for (int cell = 0; cell < CELLS; ++cell) { out.reserve(1); out.put(wall_at(cell) ? 1.0f : 0.0f); }
             }
             for (int v = 0; v < c.n_zone_vals; ++v) {  // zone corners, buff first (gym_env.py:168-173)
                 const int k = (v >> 1) + (c.buff_on ? 0 : 2);
                 const int cell = (int)((zones >> (7 * k)) & 127u);
+                out.reserve(1);
                 out.put((float)(((v & 1) ? cell / 11 : cell % 11) * 70));
             }
+            out.reserve(2);
             out.put((TPACK(t) & TP_INBUFF) ? 1.0f : 0.0f);
             out.put((TPACK(t) & TP_INDEBUFF) ? 1.0f : 0.0f);
         }

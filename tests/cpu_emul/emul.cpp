@@ -35,6 +35,7 @@ static thread_local std::string g_err;
 struct DirectSink {  // the emulator writes column j of the env's observation row directly
     float *row;
     int j;
+    void reserve(int) {}
     void put(float v) { row[j++] = v; }
     void skip_static(const float *tmpl, int n) { for (int k = 0; k < n; ++k) row[j++] = tmpl[k]; }
 };
