@@ -20,6 +20,7 @@
 #include <string.h>
 
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/alphatank_b200.h"
@@ -269,14 +270,47 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
 #endif
 
     // ---------------- phase A: one thread per env
+    // This env's action rows are staged in the (still unused) observation tile by asynchronous copies: the first
+    // read comes after the first bullet pass, so the copy latency - PCIe latency when at_step_host hands the kernel
+    // a mapped host buffer - is off the critical path.  Each thread copies and later reads only its own rows.
+    const int32_t *my_actions = nullptr;
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+    bool acts_shared = false;   // true: the warp's rows were copied cooperatively (needs a warp barrier before use)
+    if (IS_STEP && actions && valid_mask) {
+        // (inside this warp's own tile: the other warp of the block may already be flushing its tile)
+        int32_t *wstage = (int32_t *)(smem + L.off_tile) + (size_t)warp * TILE_FLOATS;
+        const int row_ints = c.act_rows * 3;
+        const int32_t *wsrc = actions + ((int64_t)blockIdx.x * BS + warp * 32) * row_ints;
+#ifndef COOP_ACTS
+#define COOP_ACTS 0   // measured slower (kernel +2 %, host-buffer step +10 %) than per-thread copies (r01t)
+#endif
+        if (COOP_ACTS && valid_mask == 0xffffffffu && ((((uintptr_t)wsrc) & 15u) == 0)) {
+            // full warp: its 32 envs' rows are one contiguous run - 16-byte chunks, lane-strided (full-line requests;
+            // this matters when `actions` is mapped host memory and every request crosses PCIe)
+            const int chunks = 32 * row_ints / 4;   // 32 * 3 * act_rows ints: a multiple of 4
+            for (int q = lane; q < chunks; q += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(wstage + 4 * q)),
+                             "l"(wsrc + 4 * q)
+                             : "memory");
+            acts_shared = true;
+        } else if (valid) {   // partial warp: every thread copies (and later reads) only its own rows
+            for (int q = 0; q < row_ints; ++q)
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(wstage + lane * row_ints + q)),
+                             "l"(wsrc + lane * row_ints + q)
+                             : "memory");
+        }
+        my_actions = wstage + lane * row_ints;
+    }
     Sim s(c, st, bm, valid ? e : 0, tid);
-    s.warp_mask = __ballot_sync(0xffffffffu, valid);
+    s.warp_mask = valid_mask;
+    s.acts_shared = acts_shared;
     if (valid) {
         if (IS_STEP) {
             s.load();
             float rw[MAX_TANKS];
-            const bool d = s.wrapper_step(actions ? actions + e * c.act_rows * 3 : nullptr, rw);
-            for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
+            const bool d = s.wrapper_step(my_actions, rw);
+            if (c.rows == 2) *reinterpret_cast<float2 *>(rewards + e * 2) = make_float2(rw[0], rw[1]);  // one 8-byte store
+            else for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
             done[e] = d ? 1 : 0;
             if (d && c.auto_reset) s.env_reset();
             s.store();
@@ -405,6 +439,7 @@ struct at_env {
     const float *d_tmpl;
     size_t smem_bytes;
     int64_t launches;
+    std::vector<std::pair<const void *, void *>> mapped;  // host buffers seen by at_step_host -> device alias (null: not mapped)
 };
 
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
@@ -530,18 +565,52 @@ int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_reward
     return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream);
 }
 
+// device-visible alias of a host buffer (pinned + mapped memory under unified addressing), or nullptr
+static void *mapped_alias(const void *h) {
+    if (!h) return nullptr;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) return at.devicePointer;
+    return nullptr;
+}
+
 int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
                  void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_step_host: null handle");
     if ((env->k.rows > 0 && !h_rewards) || !h_done) return fail(AT_ERR_ARG, "at_step_host: rewards / done must not be null");
+    if (env->k.act_rows > 0 && !h_actions) return fail(AT_ERR_ARG, "at_step_host: this mode needs an actions array");
     cudaStream_t s = (cudaStream_t)stream;
     CUDA_TRY(cudaSetDevice(env->device));
     const int64_t N = env->n_envs;
-    if (env->k.act_rows > 0) {
-        if (!h_actions) return fail(AT_ERR_ARG, "at_step_host: this mode needs an actions array");
+    // Pinned (mapped) host buffers are handed to the kernel as they are: it fetches each env's 24 bytes of actions
+    // with asynchronous copies that are hidden behind the first bullet pass and posts rewards / done straight into
+    // host memory, so the step costs one launch + one synchronisation instead of three DMA copies around the
+    // kernel.  (Cutting the batch into pipelined slices was tried and is slower: the kernel is latency-bound, a
+    // slice takes as long as the whole batch.)  Pageable buffers take the copy path.
+    void *dev[3];
+    const void *host[3] = {h_actions, h_rewards, h_done};
+    for (int q = 0; q < 3; ++q) {   // the attribute query is a driver call: remember the buffers already seen
+        dev[q] = nullptr;
+        bool hit = false;
+        for (const auto &m : env->mapped)
+            if (m.first == host[q]) { dev[q] = m.second; hit = true; break; }
+        if (!hit) {
+            dev[q] = mapped_alias(host[q]);
+            if (env->mapped.size() >= 256) env->mapped.clear();
+            env->mapped.emplace_back(host[q], dev[q]);
+        }
+    }
+    static const bool allow_direct = !getenv("AT_STEP_HOST_COPY");  // diagnostic switch: force the copy path
+    const bool direct = allow_direct && (env->k.act_rows == 0 || dev[0]) && (env->k.rows == 0 || dev[1]) && dev[2];
+    if (direct) {
+        int rc = launch_env_kernel(env, true, (const int32_t *)dev[0], nullptr, d_obs, (float *)dev[1], (uint8_t *)dev[2], s);
+        if (rc != AT_OK) return rc;
+        CUDA_TRY(cudaStreamSynchronize(s));
+        return AT_OK;
+    }
+    if (env->k.act_rows > 0)
         CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)N * env->k.act_rows * 3 * 4,
                                  cudaMemcpyHostToDevice, s));
-    }
     int rc = launch_env_kernel(env, true, env->d_actions_scratch, nullptr, d_obs, env->d_rewards_scratch,
                                env->d_done_scratch, s);
     if (rc != AT_OK) return rc;

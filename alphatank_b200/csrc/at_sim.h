@@ -344,10 +344,11 @@ struct Sim {
     uint64_t iclo, ichi;   // wall | tank cells: a 5x5 rect inside one uninteresting cell needs no further test
     uint32_t alive_bits;   // bit i: tank i alive (mirror of TPACK)
     uint32_t warp_mask;    // lanes of this warp that run the simulation (device: for the pooled stages)
+    bool acts_shared;      // device: action rows staged cooperatively by the whole (full) warp
 
     AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0), warp_mask(0xffffffffu) {}
+          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0), warp_mask(0xffffffffu), acts_shared(false) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
     AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
@@ -395,6 +396,15 @@ struct Sim {
     AT_HD double cosr(int a) const { return bm.trig[2 * a]; }
     AT_HD double sinr(int a) const { return bm.trig[2 * a + 1]; }
 
+    // the kernel stages the action rows with asynchronous copies at launch; they must have landed before the
+    // first read.  Full warps copy their rows cooperatively (acts_shared): wait, then a warp barrier - control flow
+    // is uniform up to both call sites.  Partial warps copy thread by thread.
+    AT_HD void acts_ready() const {
+#ifdef __CUDA_ARCH__
+        asm volatile("cp.async.wait_all;\n" ::: "memory");
+        if (acts_shared) __syncwarp();
+#endif
+    }
     AT_HD uint32_t rng_u32() { return rng_word(c.seed, c.env_id_base + e, 0, rng++); }
     AT_HD int rng_below(int n) { return (int)(((uint64_t)rng_u32() * (uint64_t)n) >> 32); }
     AT_HD double rng_unit53() {
@@ -1354,6 +1364,7 @@ struct Sim {
                 if (stage == 0) continue;
                 if (!is_bot) {
                     const int row = team ? k : i;
+                    acts_ready();
                     acts[i][0] = a[3 * row]; acts[i][1] = a[3 * row + 1]; acts[i][2] = a[3 * row + 2];
                 }
                 // bot_agent's agent tank uses the swapped movement table and creeps on "stop" (F14)
@@ -1367,6 +1378,7 @@ struct Sim {
     AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
         tstep += 1;
         if (!c.team_layout && a) {  // change_time, gym_env.py:77-85
+            acts_ready();
             uint32_t pv = st.prev_act[e];
             uint32_t nv = 1u;
             for (int k = 0; k < c.act_rows; ++k) {
