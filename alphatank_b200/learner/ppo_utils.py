@@ -1,0 +1,81 @@
+"""Policy / value networks and observation normalisation of the reference's PPO (models/ppo_utils.py).
+
+Module and parameter names are the reference's (``critic.{0,2,4}``, ``actor.{h}.{0,2,4}``), so a ``state_dict`` saved
+here loads into the reference's ``PPOAgentPPO`` / ``PPOAgentBot`` (inference.py:10-41, inference_multi.py:13-21) and
+vice versa - tests/test_learner_cpu.py pins the key / shape list recorded from the reference classes."""
+import torch
+import torch.nn as nn
+
+
+class RunningMeanStd:
+    """models/ppo_utils.py:6-29 - Welford-style running mean / variance over the leading (batch) dimension."""
+
+    def __init__(self, shape, epsilon=1e-4, device="cpu"):
+        self.mean = torch.zeros(shape, dtype=torch.float32, device=device)
+        self.var = torch.ones(shape, dtype=torch.float32, device=device)
+        self.count = torch.tensor(epsilon, dtype=torch.float32, device=device)
+
+    def update(self, x):
+        x = x.to(self.mean.device)
+        batch_mean = x.mean(dim=0)
+        batch_var = x.var(dim=0, unbiased=False)
+        batch_count = x.shape[0]
+        delta = batch_mean - self.mean
+        total = self.count + batch_count
+        self.mean = self.mean + delta * batch_count / total
+        self.var = self.var + (batch_var * batch_count + delta ** 2 * self.count * batch_count / total) / total
+        self.count = total
+
+    def normalize(self, x):
+        x = x.to(self.mean.device)
+        return (x - self.mean) / (torch.sqrt(self.var) + 1e-8)
+
+
+def tick_normalize(obs, epsilon=1e-4):
+    """What train_multi_ppo.py:89-91 / train_ppo_bot.py do every tick, batched over envs.
+
+    The reference builds a FRESH ``RunningMeanStd(shape=(A, D))`` per tick, updates it with the current ``[A, D]``
+    observation block and normalises that block with it; the statistics therefore run over the env's own A agent rows
+    (dim 0), not over time.  ``obs`` is ``[N, A, D]``; returns the normalised ``[N, A, D]`` (same arithmetic, one env per
+    batch row)."""
+    a = obs.shape[1]
+    bm = obs.mean(dim=1, keepdim=True)
+    bv = obs.var(dim=1, unbiased=False, keepdim=True)
+    total = epsilon + a
+    mean = bm * a / total                                             # 0 + delta * n / total
+    var = 1.0 + (bv * a + bm ** 2 * epsilon * a / total) / total
+    return (obs - mean) / (torch.sqrt(var) + 1e-8)
+
+
+def _mlp(obs_dim, out):
+    return nn.Sequential(nn.Linear(obs_dim, 128), nn.Tanh(), nn.Linear(128, 128), nn.Tanh(), nn.Linear(128, out))
+
+
+class PPOAgentPPO(nn.Module):
+    """models/ppo_utils.py:31-62: one critic MLP and one actor MLP per action head ([3, 3, 2] -> rot, move, shoot)."""
+
+    def __init__(self, obs_dim, act_dim=(3, 3, 2)):
+        super().__init__()
+        self.critic = _mlp(obs_dim, 1)
+        self.actor = nn.ModuleList([_mlp(obs_dim, int(a)) for a in act_dim])
+
+    def get_value(self, x):
+        return self.critic(x)
+
+    def get_action_and_value(self, x, action=None):
+        logits = [head(x) for head in self.actor]
+        logp_all = [torch.log_softmax(l, dim=-1) for l in logits]
+        if action is None:
+            # Gumbel-max sampling == Categorical(logits).sample(), without the host sync of torch.multinomial's checks
+            action = torch.stack([(lp - torch.log(-torch.log(torch.rand_like(lp).clamp_min(1e-20)))).argmax(dim=-1)
+                                  for lp in logp_all], dim=-1)
+        elif isinstance(action, (list, tuple)):
+            action = torch.stack(list(action), dim=-1)
+        idx = action.long()
+        logprobs = torch.stack([lp.gather(-1, idx[..., h:h + 1]).squeeze(-1) for h, lp in enumerate(logp_all)], dim=-1)
+        entropy = torch.stack([-(lp.exp() * lp).sum(dim=-1) for lp in logp_all], dim=-1)
+        return action, logprobs, entropy, self.critic(x)
+
+
+class PPOAgentBot(PPOAgentPPO):
+    """models/ppo_utils.py:64-94 (identical architecture; the 1v1-vs-bot trainers use this name)."""
