@@ -1,0 +1,268 @@
+"""Batched PPO on the CUDA env step: the reference's train_multi_ppo.py (one PPOAgentPPO + Adam per agent tank,
+GAE, clipped surrogate) re-laid for tens of thousands of envs per GPU.
+
+* The rollout never leaves the device: ``at_step`` writes observations, cumulative rewards and done flags straight
+  into the rollout storage (``obs_out`` / ``rewards_out`` / ``done_out`` of ``BatchedTankEnv.step``), actions are
+  sampled on the device (Gumbel-max) and handed over as an int32 tensor.  The reference's per-tick
+  tensor -> cuda -> cpu -> list hop (train_multi_ppo.py:96-116) does not exist.
+* Data parallel: every rank owns a contiguous env-id range (sharding.py) and its own replicas of the A policies;
+  the only collective is one all-reduce of the flattened gradient per optimiser step (NCCL on GPUs, gloo in the
+  CPU tests), plus one for the advantage statistics so that every rank normalises with the global mean / std.
+* Reference quirks kept behind switches (defaults are the reference's): ``reward_mode="cumulative"`` feeds the env's
+  cumulative per-episode reward as the per-step reward (train_multi_ppo.py:118), ``obs_norm="tick"`` re-creates the
+  observation normaliser every tick (train_multi_ppo.py:89-91).  ``"delta"`` / ``"running"`` are the conventional
+  alternatives.  The reference's reset-the-env-when-any-reward-is-negative rule (:123-131) is off by default.
+"""
+import dataclasses
+import os
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .ppo_utils import PPOAgentPPO, RunningMeanStd, tick_normalize
+
+
+@dataclasses.dataclass
+class PPOConfig:                       # defaults: train_multi_ppo.py:25-38
+    learning_rate: float = 3e-4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_coef: float = 0.2
+    ent_coef: float = 0.01
+    vf_coef: float = 0.3
+    max_grad_norm: float = 0.3
+    num_steps: int = 32                # ticks per rollout (the reference uses 512 with ONE env)
+    num_epochs: int = 4                # (the reference uses 60 full-batch epochs on 512 samples)
+    num_minibatches: int = 8
+    reward_mode: str = "cumulative"    # "cumulative" (reference) | "delta"
+    obs_norm: str = "tick"             # "tick" (reference) | "running" | "none"
+    adam_eps: float = 1e-5
+
+
+class RolloutBuffer:
+    """[T(+1), N, A, ...] storage on the env's device; the env kernel writes obs / rewards / done into it directly."""
+
+    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device):
+        T, N, A, D = num_steps, num_envs, num_agents, obs_dim
+        self.T, self.N, self.A, self.D = T, N, A, D
+        self.raw_obs = torch.zeros((T + 1, N, A * D), dtype=torch.float32, device=device)   # env output, un-normalised
+        self.obs = torch.zeros((T, N, A, D), dtype=torch.float32, device=device)            # what the policy saw
+        self.actions = torch.zeros((T, N, A, 3), dtype=torch.int32, device=device)
+        self.logprobs = torch.zeros((T, N, A, 3), dtype=torch.float32, device=device)
+        self.env_rewards = torch.zeros((T, N, A), dtype=torch.float32, device=device)       # cumulative, as returned
+        self.rewards = torch.zeros((T, N, A), dtype=torch.float32, device=device)           # what GAE consumes
+        self.dones = torch.zeros((T + 1, N), dtype=torch.uint8, device=device)              # dones[t]: obs[t] starts an episode
+        self.values = torch.zeros((T + 1, N, A), dtype=torch.float32, device=device)
+
+
+def compute_gae(rewards, values, dones, gamma, gae_lambda):
+    """train_multi_ppo.py:135-146, batched: rewards [T, ...], values [T+1, ...], dones [T+1, ...] (broadcastable).
+    delta_t = r_t + gamma (1 - d_{t+1}) V_{t+1} - V_t ;  A_t = delta_t + gamma lambda (1 - d_{t+1}) A_{t+1}."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(rewards[0])
+    for t in reversed(range(T)):
+        nonterminal = 1.0 - dones[t + 1].to(rewards.dtype)
+        delta = rewards[t] + gamma * values[t + 1] * nonterminal - values[t]
+        last = delta + gamma * gae_lambda * nonterminal * last
+        adv[t] = last
+    return adv
+
+
+def _world():
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def allreduce_mean_(flat):
+    """In-place mean over ranks of a flat tensor (the PPO gradient all-reduce; no-op for a single process)."""
+    w = _world()
+    if w > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat.div_(w)
+    return flat
+
+
+class PPOLearner:
+    """A policies (one per agent tank, like the reference) + optimisers; device-agnostic (tested on CPU with gloo)."""
+
+    def __init__(self, num_agents, obs_dim, act_dim=(3, 3, 2), cfg=None, device="cpu", seed=0):
+        self.cfg = cfg or PPOConfig()
+        self.device = torch.device(device)
+        self.A, self.D = num_agents, obs_dim
+        g = torch.Generator().manual_seed(seed)       # identical initial replicas on every rank
+        state = torch.random.get_rng_state()
+        torch.random.set_rng_state(g.get_state())
+        self.agents = [PPOAgentPPO(obs_dim, act_dim).to(self.device) for _ in range(num_agents)]
+        torch.random.set_rng_state(state)
+        self.optimizers = [torch.optim.Adam(a.parameters(), lr=self.cfg.learning_rate, eps=self.cfg.adam_eps)
+                           for a in self.agents]
+        self.running = [RunningMeanStd((obs_dim,), device=self.device) for _ in range(num_agents)]
+
+    # ---- acting
+    def normalize(self, raw_obs, update=True):
+        """raw_obs [N, A*D] (env layout) -> [N, A, D] as the policies see it."""
+        x = raw_obs.view(raw_obs.shape[0], self.A, self.D)
+        mode = self.cfg.obs_norm
+        if mode == "tick":
+            return tick_normalize(x)
+        if mode == "running":
+            out = torch.empty_like(x)
+            for i in range(self.A):
+                if update:
+                    self.running[i].update(x[:, i])
+                out[:, i] = self.running[i].normalize(x[:, i])
+            return out
+        return x
+
+    @torch.no_grad()
+    def act(self, obs_nad):
+        """obs [N, A, D] -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]."""
+        acts, lps, vals = [], [], []
+        for i, agent in enumerate(self.agents):
+            a, lp, v = agent.sample(obs_nad[:, i])
+            acts.append(a)
+            lps.append(lp)
+            vals.append(v.squeeze(-1))
+        return (torch.stack(acts, dim=1).to(torch.int32), torch.stack(lps, dim=1), torch.stack(vals, dim=1))
+
+    @torch.no_grad()
+    def values(self, obs_nad):
+        return torch.stack([agent.get_value(obs_nad[:, i]).squeeze(-1) for i, agent in enumerate(self.agents)], dim=1)
+
+    # ---- learning
+    def update(self, buf, generator=None):
+        """One PPO update from a filled RolloutBuffer (train_multi_ppo.py:133-182).  Returns per-agent stats."""
+        c = self.cfg
+        dones = buf.dones.to(torch.float32).unsqueeze(-1)                     # [T+1, N, 1]
+        adv = compute_gae(buf.rewards, buf.values, dones, c.gamma, c.gae_lambda)
+        # advantage normalisation over everything (:148), with global statistics when data parallel
+        s = torch.stack([adv.sum(), (adv * adv).sum(), torch.tensor(float(adv.numel()), device=adv.device)]).double()
+        if _world() > 1:
+            dist.all_reduce(s, op=dist.ReduceOp.SUM)
+        mean = s[0] / s[2]
+        var = (s[1] / s[2] - mean * mean).clamp_min(0.0) * (s[2] / (s[2] - 1.0).clamp_min(1.0))   # unbiased, like .std()
+        adv = ((adv - mean) / (var.sqrt() + 1e-8)).to(torch.float32)
+        returns = adv + buf.values[:-1]
+        T, N = buf.T, buf.N
+        B = T * N
+        mb = max(B // max(c.num_minibatches, 1), 1)
+        stats = []
+        for i, (agent, opt) in enumerate(zip(self.agents, self.optimizers)):
+            b_obs = buf.obs[:, :, i].reshape(B, self.D)
+            b_act = buf.actions[:, :, i].reshape(B, 3)
+            b_lp = buf.logprobs[:, :, i].reshape(B, 3)
+            b_adv = adv[:, :, i].reshape(B, 1)
+            b_ret = returns[:, :, i].reshape(B)
+            params = [p for p in agent.parameters()]
+            last = {}
+            for _ in range(c.num_epochs):
+                perm = torch.randperm(B, device=b_obs.device, generator=generator) if c.num_minibatches > 1 else None
+                for k in range(0, B, mb):
+                    idx = perm[k:k + mb] if perm is not None else slice(None)
+                    _, new_lp, entropy, new_v = agent.get_action_and_value(b_obs[idx], b_act[idx])
+                    ratio = torch.exp((new_lp - b_lp[idx]).clamp(-10, 10))
+                    pg = torch.max(-b_adv[idx] * ratio, -b_adv[idx] * torch.clamp(ratio, 1 - c.clip_coef, 1 + c.clip_coef)).mean()
+                    v_loss = 0.5 * ((new_v.squeeze(-1) - b_ret[idx]) ** 2).mean()
+                    ent = entropy.mean()
+                    loss = pg - c.ent_coef * ent + c.vf_coef * v_loss
+                    opt.zero_grad(set_to_none=True)
+                    loss.backward()
+                    if _world() > 1:                                          # the step path's only collective
+                        flat = torch.cat([p.grad.reshape(-1) for p in params])
+                        allreduce_mean_(flat)
+                        o = 0
+                        for p in params:
+                            n = p.numel()
+                            p.grad.copy_(flat[o:o + n].view_as(p))
+                            o += n
+                    nn.utils.clip_grad_norm_(params, c.max_grad_norm)
+                    opt.step()
+                    last = {"policy_loss": pg.detach(), "value_loss": v_loss.detach(), "entropy": ent.detach()}
+            stats.append({k: float(v) for k, v in last.items()})
+        return stats
+
+
+@torch.no_grad()
+def collect_rollout(env, learner, buf, first=False):
+    """Fill ``buf`` with ``buf.T`` ticks of ``env`` (a batched MultiAgentTeamEnv / MultiAgentEnv) under the learner's
+    policies.  Everything stays on the device; the env kernel writes into the buffer.  ``first``: start from reset()."""
+    core = env.core
+    T = buf.T
+    if first:
+        core.reset(obs_out=buf.raw_obs[0])
+        buf.dones[0].zero_()
+    else:                                     # continue: the previous rollout's last observation / done flag
+        buf.raw_obs[0].copy_(buf.raw_obs[T])
+        buf.dones[0].copy_(buf.dones[T])
+    prev_cum = getattr(buf, "_prev_cum", None)
+    if prev_cum is None or first:
+        prev_cum = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.raw_obs.device)
+    for t in range(T):
+        x = learner.normalize(buf.raw_obs[t])
+        buf.obs[t].copy_(x)
+        a, lp, v = learner.act(x)
+        buf.actions[t].copy_(a)
+        buf.logprobs[t].copy_(lp)
+        buf.values[t].copy_(v)
+        core.step(buf.actions[t], obs_out=buf.raw_obs[t + 1], rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
+        if learner.cfg.reward_mode == "delta":
+            buf.rewards[t].copy_(buf.env_rewards[t] - prev_cum)
+            prev_cum = buf.env_rewards[t] * (1.0 - buf.dones[t + 1].to(torch.float32)).unsqueeze(-1)  # reset -> 0
+        else:
+            buf.rewards[t].copy_(buf.env_rewards[t])
+    buf._prev_cum = prev_cum
+    buf._prev_live = prev_cum
+    buf.values[T].copy_(learner.values(learner.normalize(buf.raw_obs[T], update=False)))
+    return buf
+
+
+class RolloutRunner:
+    """collect_rollout() captured once as a CUDA graph and replayed: a tick is ~60 small kernels (normalise, three
+    batched GEMMs per policy, sampling, the env step), and issued one by one the rollout is bound by launch overhead
+    on the host, not by the GPU.  The env step takes part in the capture like any other kernel (at_step launches on
+    torch's current stream).  Only for stateless observation normalisers ("tick" / "none")."""
+
+    def __init__(self, env, learner, buf, use_graph=True):
+        self.env, self.learner, self.buf = env, learner, buf
+        self.use_graph = use_graph and learner.cfg.obs_norm in ("tick", "none") and buf.raw_obs.is_cuda
+        self.graph = None
+        self._prev = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.raw_obs.device)
+
+    def run(self, first=False):
+        buf = self.buf
+        if first or not self.use_graph:
+            return collect_rollout(self.env, self.learner, buf, first=first)
+        if self.graph is None:
+            buf._prev_cum = self._prev                      # a static tensor the captured code reads and rewrites
+            self._prev.copy_(getattr(buf, "_prev_live", self._prev))
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                collect_rollout(self.env, self.learner, buf, first=False)
+                self._prev.copy_(buf._prev_cum)
+            self.graph = g                                  # (capture does not execute: replay below)
+        self.graph.replay()
+        return buf
+
+
+# ---------------------------------------------------------------------------- checkpoints (train_multi_ppo.py:202-211)
+def save_team_checkpoint(path, game_configs, tank_names, agents):
+    """``{'team_config': game_configs, '<TankName>': state_dict, ...}`` - the file inference_multi.py:75-98 loads."""
+    d = {"team_config": game_configs}
+    for name, agent in zip(tank_names, agents):
+        d[name] = {k: v.detach().cpu() for k, v in agent.state_dict().items()}
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    torch.save(d, path)
+    return path
+
+
+def load_team_checkpoint(path, obs_dim, act_dim=(3, 3, 2), device="cpu"):
+    ck = torch.load(path, map_location=device, weights_only=False)
+    agents = {}
+    for name, sd in ck.items():
+        if name == "team_config":
+            continue
+        a = PPOAgentPPO(obs_dim, act_dim).to(device)
+        a.load_state_dict(sd)
+        agents[name] = a
+    return ck["team_config"], agents

@@ -62,6 +62,33 @@ class PPOAgentPPO(nn.Module):
     def get_value(self, x):
         return self.critic(x)
 
+    @torch.no_grad()
+    def fused_logits_and_value(self, x):
+        """Inference-only forward of all four MLPs as three batched GEMMs: the first layers share the input, so their
+        weights are concatenated into one [4*128, D] matrix (one pass over the [N, D] observations instead of four);
+        layers two and three are batched over the four networks.  Same arithmetic per network as the module path."""
+        nets = [self.critic] + list(self.actor)
+        w1 = torch.cat([n[0].weight for n in nets], dim=0)                      # [512, D]
+        b1 = torch.cat([n[0].bias for n in nets], dim=0)
+        h = torch.tanh(torch.addmm(b1, x, w1.t())).view(x.shape[0], len(nets), 128).transpose(0, 1)   # [4, N, 128]
+        w2 = torch.stack([n[2].weight.t() for n in nets])                       # [4, 128, 128]
+        b2 = torch.stack([n[2].bias for n in nets]).unsqueeze(1)
+        h = torch.tanh(torch.baddbmm(b2, h, w2))
+        outs = [torch.addmm(n[4].bias, h[k], n[4].weight.t()) for k, n in enumerate(nets)]
+        return outs[1:], outs[0]
+
+    @torch.no_grad()
+    def sample(self, x):
+        """(action int64 [N, 3], logprob [N, 3], value [N, 1]) through the fused forward."""
+        logits, value = self.fused_logits_and_value(x)
+        acts, lps = [], []
+        for l in logits:
+            lp = torch.log_softmax(l, dim=-1)
+            a = (lp - torch.log(-torch.log(torch.rand_like(lp).clamp_min(1e-20)))).argmax(dim=-1)
+            acts.append(a)
+            lps.append(lp.gather(-1, a.unsqueeze(-1)).squeeze(-1))
+        return torch.stack(acts, dim=-1), torch.stack(lps, dim=-1), value
+
     def get_action_and_value(self, x, action=None):
         logits = [head(x) for head in self.actor]
         logp_all = [torch.log_softmax(l, dim=-1) for l in logits]

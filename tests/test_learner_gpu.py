@@ -1,0 +1,100 @@
+"""GPU (-m gpu): the PPO rollout / update loop on the CUDA env step and the checkpoint file
+(row 2).  The rollout writes env outputs straight into the rollout storage; replaying its recorded actions through
+a second env handle must reproduce every stored observation / reward / done bit for bit."""
+import os
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+pytestmark = pytest.mark.gpu
+
+
+def test_rollout_update_checkpoint_and_replay(tmp_path):
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import (PPOAgentPPO, PPOConfig, PPOLearner, RolloutBuffer, collect_rollout,
+                                        load_team_checkpoint, save_team_checkpoint)
+    N, T, seed = 2048, 12, 9
+    dev = torch.device("cuda:0")
+    env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=seed)
+    names = env.get_observation_order()
+    A, D = len(names), env.observation_space.shape[0] // len(names)
+    assert (A, D) == (2, 528)
+    cfg = PPOConfig(num_steps=T, num_epochs=2, num_minibatches=4, reward_mode="delta")
+    L = PPOLearner(A, D, (3, 3, 2), cfg, dev, seed=1)
+    buf = RolloutBuffer(T, N, A, D, dev)
+    before = [p.detach().clone() for p in L.agents[0].parameters()]
+    for it in range(3):
+        collect_rollout(env, L, buf, first=(it == 0))
+        if it == 0:
+            first_roll = {k: getattr(buf, k).clone() for k in ("raw_obs", "actions", "env_rewards", "dones")}
+        stats = L.update(buf)
+        assert all(all(torch.isfinite(torch.tensor(v)) for v in s.values()) for s in stats)
+    assert any(not torch.equal(a, b) for a, b in zip(before, L.agents[0].parameters()))
+    assert torch.isfinite(buf.obs).all() and torch.isfinite(buf.values).all()
+    assert int(buf.actions.min()) >= 0 and int(buf.actions[..., :2].max()) <= 2 and int(buf.actions[..., 2].max()) <= 1
+    # replay the first rollout's actions through a fresh handle with the same seed: identical stream
+    env2 = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=seed)
+    obs, _ = env2.reset()
+    assert torch.equal(obs, first_roll["raw_obs"][0])
+    for t in range(T):
+        o, r, d, _, _ = env2.step(first_roll["actions"][t])
+        assert torch.equal(o, first_roll["raw_obs"][t + 1]), "obs differ at tick %d" % t
+        assert torch.equal(r, first_roll["env_rewards"][t]) and torch.equal(d, first_roll["dones"][t + 1])
+    # checkpoint in the reference's layout
+    path = save_team_checkpoint(str(tmp_path / "team_ppo" / "2a_vs_2b.pth"), team_vs_bot_configs, names, L.agents)
+    raw = torch.load(path, map_location="cpu", weights_only=False)
+    assert set(raw) == {"team_config", "Tank1", "Tank2"} and raw["team_config"] == team_vs_bot_configs
+    assert list(raw["Tank1"]) == list(PPOAgentPPO(D).state_dict())
+    tc, agents = load_team_checkpoint(path, D, device=dev)
+    x = buf.obs[0, :64, 0]
+    with torch.no_grad():
+        assert torch.equal(agents["Tank1"].get_value(x), L.agents[0].get_value(x))
+
+
+def test_delta_rewards_telescope_to_cumulative():
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, collect_rollout
+    N, T = 512, 40
+    dev = torch.device("cuda:0")
+    env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=4)
+    L = PPOLearner(2, 528, (3, 3, 2), PPOConfig(num_steps=T, reward_mode="delta"), dev)
+    buf = RolloutBuffer(T, N, 2, 528, dev)
+    collect_rollout(env, L, buf, first=True)
+    run = torch.zeros((N, 2), device=dev, dtype=torch.float64)
+    for t in range(T):
+        run = run + buf.rewards[t].double()
+        assert torch.allclose(run.float(), buf.env_rewards[t], atol=2e-3), "tick %d" % t
+        run = run * (1.0 - buf.dones[t + 1].double()).unsqueeze(-1)           # a finished episode restarts at 0
+
+
+def test_graph_captured_rollout_replays_bit_exactly():
+    """RolloutRunner: the whole T-tick rollout (policies + env step) as one CUDA graph.  A second env handle fed the
+    recorded actions must reproduce what the graph wrote, rollout after rollout."""
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
+    N, T, seed = 1024, 10, 21
+    dev = torch.device("cuda:0")
+    env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=seed)
+    env2 = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=seed)
+    L = PPOLearner(2, 528, (3, 3, 2), PPOConfig(num_steps=T, reward_mode="delta"), dev)
+    buf = RolloutBuffer(T, N, 2, 528, dev)
+    runner = RolloutRunner(env, L, buf)
+    obs2, _ = env2.reset()
+    for it in range(4):                                   # 0: eager (reset), 1: capture + first replay, 2-3: replays
+        runner.run(first=(it == 0))
+        torch.cuda.synchronize()
+        assert torch.equal(buf.raw_obs[0], obs2), "rollout %d does not start where the previous one ended" % it
+        run = None
+        for t in range(T):
+            obs2, r, d, _, _ = env2.step(buf.actions[t])
+            assert torch.equal(obs2, buf.raw_obs[t + 1]), "rollout %d tick %d" % (it, t)
+            assert torch.equal(r, buf.env_rewards[t]) and torch.equal(d, buf.dones[t + 1])
+        obs2 = obs2.clone()
+    assert runner.graph is not None
+    assert len({int(x) for x in buf.actions[..., 0].flatten()[:4096].tolist()}) == 3      # sampling is alive in replays
