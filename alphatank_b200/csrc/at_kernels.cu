@@ -698,6 +698,13 @@ int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n,
     return AT_OK;
 }
 
+int at_set_weakness(at_env *env, double weakness) {
+    if (!env || !(weakness >= 0.0 && weakness <= 1.0)) return fail(AT_ERR_ARG, "at_set_weakness: null handle or weakness outside [0, 1]");
+    env->user_cfg.weakness = weakness;
+    env->k.weakness = weakness;   // the kernel config travels by value with every launch
+    return AT_OK;
+}
+
 int at_get_luts(const at_env *env, double *h_trig, double *h_corner) {
     if (!env) return fail(AT_ERR_ARG, "at_get_luts: null handle");
     if (h_trig) memcpy(h_trig, env->luts.trig.data(), 722 * 8);

@@ -88,6 +88,13 @@ class MultiAgentEnv:
         self._build()
         return self.reset()
 
+    def set_weakness(self, weakness):
+        """Curriculum hook (train_ppo_cycle.py:82-92, 296): probability that the scripted opponent acts on a tick,
+        changed in place (no reset, no rebuild)."""
+        from . import _capi
+        _capi.check(self.core.L.at_set_weakness(self.core.h, float(weakness)), "at_set_weakness")
+        self.weakness = float(weakness)
+
     def reset(self, mask=None):
         obs = self.core.reset(mask)
         info = {"Tank:%d-%s" % (i, t): 0 for i, t in enumerate(("TeamA", "TeamB"))}   # gym_env.py:70

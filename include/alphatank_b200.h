@@ -162,6 +162,11 @@ int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n,
  * pygame Vector2.rotate corner offsets -> double[361][4]. */
 int at_get_luts(const at_env *env, double *h_trig, double *h_corner);
 
+/* Curriculum hook of the 1v1 bot_agent trainers (train_ppo_cycle.py:82-92, 296, 332-333; GamingENV(weakness=...),
+ * gaming_env.py:144): probability that the scripted opponent's decision is applied on a tick.  Takes effect from the
+ * next at_step; 0 <= weakness <= 1. */
+int at_set_weakness(at_env *env, double weakness);
+
 int64_t at_launch_count(const at_env *env); /* kernels launched through this handle so far */
 const char *at_last_error(void);
 const char *at_version(void);

@@ -25,7 +25,7 @@ BULLET_COLS = (("owner", 0), ("x", 1), ("y", 2), ("dx", 3), ("dy", 4), ("distanc
 
 
 def fixture_names():
-    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("mazes.npz", "bfs.npz"))
+    return sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and f not in ("mazes.npz", "bfs.npz", "learner.npz"))
 
 
 def load_fixture(name):

@@ -249,3 +249,27 @@ def test_reference_facing_classes_and_errors():
         MultiAgentEnv(mode="bot_agent", bot_type="nonsense", num_envs=2)                          # bot_factory.py:29-31
     with pytest.raises(ValueError):
         MultiAgentTeamEnv(config_teams.mixed_team_configs, num_envs=2)                            # human tanks
+
+
+def test_set_weakness_hot_swap_equals_construction_and_oracle():
+    """train_ppo_cycle.py's curriculum changes the opponent's act probability while training: at_set_weakness on a
+    live handle gives the stream of a handle constructed with that value (and of the oracle)."""
+    from alphatank_b200 import _capi
+    spec = dict(SWEEP["botagent_dodge_weak"])
+    N, seed = 300, 17
+    a = _gpu(dict(spec, weakness=0.35), N, seed, 0, auto_reset=True)
+    b = _gpu(dict(spec, weakness=1.0), N, seed, 0, auto_reset=True)
+    _capi.check(b.core.L.at_set_weakness(b.core.h, 0.35), "at_set_weakness")
+    ora = parity.make_oracle_env(dict(spec, weakness=0.35), N, seed, 0, auto_reset=True)
+    r0 = a.reset()
+    assert np.array_equal(r0, b.reset()) and np.array_equal(r0, ora.reset())
+    ids = np.arange(N)
+    for t in range(60):
+        acts = synthetic_actions(seed, ids, t, a.A)
+        oa, ra, da = a.step(acts)
+        ob, rb, db = b.step(acts)
+        oo, ro, do = ora.step(acts, threads=4)
+        assert np.array_equal(oa, ob) and np.array_equal(ra, rb) and np.array_equal(da, db), "tick %d" % t
+        assert np.array_equal(oa, oo) and np.array_equal(ra, ro) and np.array_equal(da, do), "oracle, tick %d" % t
+    with pytest.raises(ValueError):
+        _capi.check(b.core.L.at_set_weakness(b.core.h, 1.5), "at_set_weakness")
