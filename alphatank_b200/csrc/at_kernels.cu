@@ -409,6 +409,61 @@ __global__ void maze_kernel(uint64_t seed, int64_t env_id_base, int64_t n, uint8
     if (ctr_out) ctr_out[k] = ctr;
 }
 
+
+// Per-tick observation normaliser of the reference's trainers (train_multi_ppo.py:89-91 with models/ppo_utils.py:
+// 13-29): a FRESH RunningMeanStd(shape=(A, D), epsilon) is updated with the env's own [A, D] block and applied to
+// it, i.e. per env and column  bm = mean_a x, bv = mean_a (x - bm)^2, total = eps + A,
+//   mean = bm A / total,  var = 1 + (bv A + bm^2 eps A / total) / total,  y = (x - mean) / (sqrt(var) + 1e-8).
+// One pass: each thread owns 4 consecutive columns of one env and its A rows (16-byte loads / stores) - the torch
+// formulation costs ~10 elementwise / reduction passes over the 277 MB observation tensor per tick.
+template <int VEC>
+__global__ void tick_normalize_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t n_envs, int rows,
+                                      int dim, float eps) {
+    const int per_env = dim / VEC;
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_envs * per_env) return;
+    const int64_t e = k / per_env;
+    const int c0 = (int)(k - e * per_env) * VEC;
+    const float *src = x + (e * rows) * dim + c0;
+    float *dst = y + (e * rows) * dim + c0;
+    float v[AT_MAX_TANKS][VEC];
+    float sum[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) sum[q] = 0.f;
+    for (int a = 0; a < rows; ++a) {
+        if (VEC == 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(src + (int64_t)a * dim);
+            v[a][0] = t.x; v[a][1 % VEC] = t.y; v[a][2 % VEC] = t.z; v[a][3 % VEC] = t.w;
+        } else {
+            v[a][0] = src[(int64_t)a * dim];
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) sum[q] += v[a][q];
+    }
+    const float fa = (float)rows, total = eps + fa;
+    float mean[VEC], inv[VEC];
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+        const float bm = sum[q] / fa;
+        float ss = 0.f;
+        for (int a = 0; a < rows; ++a) { const float d = v[a][q] - bm; ss += d * d; }
+        const float bv = ss / fa;
+        mean[q] = bm * fa / total;
+        const float var = 1.0f + (bv * fa + bm * bm * eps * fa / total) / total;
+        inv[q] = 1.0f / (sqrtf(var) + 1e-8f);
+    }
+    for (int a = 0; a < rows; ++a) {
+        if (VEC == 4) {
+            float4 t;
+            t.x = (v[a][0] - mean[0]) * inv[0]; t.y = (v[a][1 % VEC] - mean[1 % VEC]) * inv[1 % VEC];
+            t.z = (v[a][2 % VEC] - mean[2 % VEC]) * inv[2 % VEC]; t.w = (v[a][3 % VEC] - mean[3 % VEC]) * inv[3 % VEC];
+            *reinterpret_cast<float4 *>(dst + (int64_t)a * dim) = t;
+        } else {
+            dst[(int64_t)a * dim] = (v[a][0] - mean[0]) * inv[0];
+        }
+    }
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------- host
@@ -702,6 +757,20 @@ int at_set_weakness(at_env *env, double weakness) {
     if (!env || !(weakness >= 0.0 && weakness <= 1.0)) return fail(AT_ERR_ARG, "at_set_weakness: null handle or weakness outside [0, 1]");
     env->user_cfg.weakness = weakness;
     env->k.weakness = weakness;   // the kernel config travels by value with every launch
+    return AT_OK;
+}
+
+int at_tick_normalize(int device, const float *d_obs, int64_t n_envs, int rows, int dim, float epsilon, float *d_out,
+                      void *stream) {
+    if (!d_obs || !d_out || n_envs <= 0 || rows <= 0 || rows > AT_MAX_TANKS || dim <= 0)
+        return fail(AT_ERR_ARG, "at_tick_normalize: bad argument");
+    CUDA_TRY(cudaSetDevice(device));
+    const bool vec = dim % 4 == 0 && ((((uintptr_t)d_obs) | ((uintptr_t)d_out)) & 15u) == 0;
+    const int64_t threads = n_envs * (vec ? dim / 4 : dim);
+    const int grid = (int)((threads + 255) / 256);
+    if (vec) tick_normalize_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    else tick_normalize_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    CUDA_TRY(cudaGetLastError());
     return AT_OK;
 }
 

@@ -100,18 +100,21 @@ class PPOLearner:
         self.running = [RunningMeanStd((obs_dim,), device=self.device) for _ in range(num_agents)]
 
     # ---- acting
-    def normalize(self, raw_obs, update=True):
-        """raw_obs [N, A*D] (env layout) -> [N, A, D] as the policies see it."""
+    def normalize(self, raw_obs, update=True, out=None):
+        """raw_obs [N, A*D] (env layout) -> [N, A, D] as the policies see it (written into ``out`` when given)."""
         x = raw_obs.view(raw_obs.shape[0], self.A, self.D)
         mode = self.cfg.obs_norm
         if mode == "tick":
-            return tick_normalize(x)
+            return tick_normalize(x, out=out)
         if mode == "running":
-            out = torch.empty_like(x)
+            out = torch.empty_like(x) if out is None else out
             for i in range(self.A):
                 if update:
                     self.running[i].update(x[:, i])
                 out[:, i] = self.running[i].normalize(x[:, i])
+            return out
+        if out is not None:
+            out.copy_(x)
             return out
         return x
 
@@ -199,8 +202,7 @@ def collect_rollout(env, learner, buf, first=False):
     if prev_cum is None or first:
         prev_cum = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.raw_obs.device)
     for t in range(T):
-        x = learner.normalize(buf.raw_obs[t])
-        buf.obs[t].copy_(x)
+        x = learner.normalize(buf.raw_obs[t], out=buf.obs[t])     # straight into the rollout storage
         a, lp, v = learner.act(x)
         buf.actions[t].copy_(a)
         buf.logprobs[t].copy_(lp)

@@ -158,6 +158,12 @@ int at_bfs_batch(int device, const uint8_t *d_maze, const int32_t *d_query, int6
 int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *d_maze, uint32_t *d_ctr,
                       void *stream);
 
+/* The trainers' per-tick observation normaliser (train_multi_ppo.py:89-91: a fresh RunningMeanStd((A, D)) from
+ * models/ppo_utils.py:6-29 is updated with, and applied to, each env's own [rows][dim] block) in one pass over
+ * d_obs float[n_envs][rows][dim] -> d_out (may alias d_obs).  epsilon = RunningMeanStd's 1e-4. */
+int at_tick_normalize(int device, const float *d_obs, int64_t n_envs, int rows, int dim, float epsilon, float *d_out,
+                      void *stream);
+
 /* Host copies of the device lookup tables (tests): cos/sin of math.radians(a), a = 0..360 -> double[361][2];
  * pygame Vector2.rotate corner offsets -> double[361][4]. */
 int at_get_luts(const at_env *env, double *h_trig, double *h_corner);

@@ -98,3 +98,23 @@ def test_graph_captured_rollout_replays_bit_exactly():
         obs2 = obs2.clone()
     assert runner.graph is not None
     assert len({int(x) for x in buf.actions[..., 0].flatten()[:4096].tolist()}) == 3      # sampling is alive in replays
+
+
+def test_tick_normalize_kernel_matches_reference_formula():
+    import numpy as np
+    from alphatank_b200.learner.ppo_utils import tick_normalize
+    G = np.load(os.path.join(HERE, "golden", "learner.npz"))
+    x = torch.from_numpy(G["tick_in"]).cuda()                      # [5, 2, 24]: recorded from the reference class
+    np.testing.assert_allclose(tick_normalize(x).cpu().numpy(), G["tick_out"], rtol=2e-5, atol=2e-5)
+    torch.manual_seed(1)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for shape in ((4096, 2, 528), (100, 4, 388), (77, 3, 17), (64, 1, 528)):   # vector path, odd dims, single row
+        x = torch.randn(shape, device="cuda", generator=g) * 250 + 300
+        got = tick_normalize(x)
+        want = tick_normalize(x.cpu()).cuda()
+        # one row: x - x * A / (eps + A) cancels to ~1e-4 x, so fp32 op-order differences show up at 1e-5 absolute
+        tol = 2e-4 if shape[1] == 1 else 2e-5
+        assert torch.allclose(got, want, rtol=tol, atol=tol), (shape, float((got - want).abs().max()))
+    x = torch.randn((512, 2, 528), device="cuda")
+    want = tick_normalize(x.clone())
+    assert tick_normalize(x, out=x) is x and torch.equal(x, want)          # in place
