@@ -4,4 +4,4 @@ models/ppo_utils.py, models/sac_utils.py and train_multi_ppo.py on top of the CU
 "PyTorch for the PPO/SAC side", NCCL only for the gradient all-reduce)."""
 from .ppo_utils import PPOAgentBot, PPOAgentPPO, RunningMeanStd, tick_normalize  # noqa: F401
 from .ppo import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner, collect_rollout, load_team_checkpoint, save_team_checkpoint  # noqa: F401
-from .sac_utils import ContinuousToDiscrete, DeviceReplayBuffer  # noqa: F401
+from .sac_utils import ContinuousToDiscrete, DeviceReplayBuffer, PolicyNetwork, QNetwork, SACAgent  # noqa: F401

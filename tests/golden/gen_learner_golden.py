@@ -20,7 +20,7 @@ sys.path.insert(0, REF)
 os.chdir(REF)
 
 from models.ppo_utils import PPOAgentPPO, RunningMeanStd  # noqa: E402
-from models.sac_utils import ContinuousToDiscreteWrapper  # noqa: E402
+from models.sac_utils import ContinuousToDiscreteWrapper, SACAgent  # noqa: E402
 
 
 def main():
@@ -66,6 +66,25 @@ def main():
                      for b in (0.25, 0.75) for c in (0.0, 0.49, 0.5, 0.51, 1.0)], dtype=np.float32)
     out["c2d_in"] = grid
     out["c2d_out"] = np.array(w.action(grid), dtype=np.int32)
+    # SAC: schema of SACAgent(388, 6).state_dict(), and a small seeded agent's deterministic + seeded-sample outputs
+    big = SACAgent(388, 6).state_dict()
+    out["sac_keys"] = json.dumps({k: ([[n, list(v.shape)] for n, v in big[k].items()] if k != "log_alpha" else list(big[k].shape))
+                                  for k in big})
+    torch.manual_seed(11)
+    ag = SACAgent(10, 3, hidden_dim=16)
+    sd = ag.state_dict()
+    for net in ("actor", "critic1"):
+        out["sac_names/" + net] = json.dumps(list(sd[net].keys()))
+        for k, v in sd[net].items():
+            out["sac/%s/%s" % (net, k)] = v.numpy()
+    st, ac = torch.randn(7, 10), torch.rand(7, 3)
+    with torch.no_grad():
+        mean, std = ag.actor(st)
+        q = ag.critic1(st, ac)
+        torch.manual_seed(5)
+        a, lp = ag.actor.sample(st)
+    out["sac_state"], out["sac_action"], out["sac_mean"], out["sac_std"], out["sac_q"] = st.numpy(), ac.numpy(), mean.numpy(), std.numpy(), q.numpy()
+    out["sac_sample_a"], out["sac_sample_lp"] = a.numpy(), lp.numpy()
     np.savez_compressed(os.path.join(HERE, "learner.npz"), **out)
     print("wrote learner.npz:", len(out), "arrays")
 

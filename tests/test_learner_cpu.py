@@ -168,3 +168,41 @@ def test_two_rank_update_equals_single_process_full_batch(tmp_path):
         for k in ref:
             assert torch.equal(a0[k], a1[k]), "replicas diverged: " + k               # same all-reduced gradient
             assert torch.allclose(a0[k], ref[k], rtol=1e-4, atol=1e-5), k              # == the full-batch update
+
+
+def test_sac_networks_match_reference():
+    from alphatank_b200.learner import SACAgent
+    want = json.loads(str(G["sac_keys"]))
+    sd = SACAgent(388, 6).state_dict()
+    got = {k: ([[n, list(v.shape)] for n, v in sd[k].items()] if k != "log_alpha" else list(sd[k].shape)) for k in sd}
+    assert got == want                                               # checkpoint layout of models/sac_utils.py:222-231
+    ag = SACAgent(10, 3, hidden_dim=16)
+    for net in ("actor", "critic1"):
+        names = json.loads(str(G["sac_names/" + net]))
+        getattr(ag, net).load_state_dict({k: torch.from_numpy(G["sac/%s/%s" % (net, k)]) for k in names})
+    st, ac = torch.from_numpy(G["sac_state"]), torch.from_numpy(G["sac_action"])
+    with torch.no_grad():
+        mean, std = ag.actor(st)
+        q = ag.critic1(st, ac)
+        torch.manual_seed(5)
+        a, lp = ag.actor.sample(st)
+    for got_, key in ((mean, "sac_mean"), (std, "sac_std"), (q, "sac_q"), (a, "sac_sample_a"), (lp, "sac_sample_lp")):
+        np.testing.assert_allclose(got_.numpy(), G[key], rtol=1e-5, atol=1e-6)
+
+
+def test_sac_update_runs_and_moves_targets():
+    from alphatank_b200.learner import SACAgent
+    torch.manual_seed(0)
+    ag = SACAgent(10, 3, hidden_dim=16)
+    rb = DeviceReplayBuffer(256, 10, 3, "cpu")
+    rb.push(torch.randn(200, 10), torch.rand(200, 3), torch.randn(200), torch.randn(200, 10), (torch.rand(200) < 0.1).float())
+    before = [p.clone() for p in ag.critic1_target.parameters()]
+    losses = [ag.update(rb, 64) for _ in range(3)]
+    assert all(np.isfinite(v) for l in losses for v in l)
+    assert any(not torch.equal(a, b) for a, b in zip(before, ag.critic1_target.parameters()))
+    sd = ag.state_dict()
+    ag2 = SACAgent(10, 3, hidden_dim=16)
+    ag2.load_state_dict(sd)
+    x = torch.randn(4, 10)
+    with torch.no_grad():
+        assert torch.equal(ag.actor(x)[0], ag2.actor(x)[0])
