@@ -26,6 +26,7 @@
 #include "../../include/alphatank_b200.h"
 #include "at_host.h"
 #include "at_sim.h"
+#include "at_rows.h"
 
 using namespace at;
 
@@ -38,7 +39,7 @@ struct SmemLayout {
     size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_nearlo, off_nearhi, off_bpack, off_tlive,
         off_tshot, off_tmpl, off_tile, off_slot, off_udelta, off_losq, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots) {
+__host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots, bool fused = true, int act_rows = 0) {
     const int nb = n_bots > 0 ? n_bots : 1;
     SmemLayout L;
     L.n = n;
@@ -56,9 +57,10 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots
     L.off_tlive = o; o += (size_t)n * BS * 4;
     L.off_tshot = o; o += (size_t)n * BS * 4;
     o = (o + 15) & ~(size_t)15;
-    L.off_tmpl = o; o += (size_t)(4 * n_walls + CELLS + 4) * 4;  // +4: shifted so that it shares the rows' 16-byte phase
+    L.off_tmpl = o; o += fused ? (size_t)(4 * n_walls + CELLS + 4) * 4 : 0;  // +4: shifted so that it shares the rows' 16-byte phase
     o = (o + 15) & ~(size_t)15;
-    L.off_tile = o; o += (size_t)(BS / 32) * TILE_FLOATS * 4;
+    // fused: the observation tile (the action rows are staged in it before phase B needs it); split: only the staging area
+    L.off_tile = o; o += fused ? (size_t)(BS / 32) * TILE_FLOATS * 4 : (size_t)BS * act_rows * 3 * 4;
     L.off_slot = o; o += (size_t)n * SLOTS_PER_TANK * BS;
     L.off_udelta = o; o += 368;
     L.off_losq = o; o += (size_t)(BS / 32) * 512;
@@ -169,14 +171,17 @@ struct TileSink {  // kept in registers: flush takes everything by value
     }
 };
 
-template <bool IS_STEP>
+// FUSED = true: simulation + observation rows in one launch (phase B below).  FUSED = false: simulation only; the rows
+// are built from the stored state by rows_kernel, launched behind this kernel as a programmatic dependent.
+template <bool IS_STEP, bool FUSED>
 __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                  const int32_t *__restrict__ actions,
                                                  const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                  float *__restrict__ rewards, uint8_t *__restrict__ done,
                                                  const float *__restrict__ g_tmpl) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(c.n_tanks, c.n_walls, c.n_bots);
+    const SmemLayout L = smem_layout(c.n_tanks, c.n_walls, c.n_bots, FUSED, c.act_rows);
+    if (!FUSED) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // rows_kernel may take freed SM slots
     BlockMem bm;
     bm.trig = (double *)(smem + L.off_trig);
     bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
@@ -208,7 +213,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
 #pragma unroll
         for (int k = 0; k < UDL_IT; ++k) if (tid + k * BS < 361) udl[tid + k * BS] = uv[k];
     }
-    if (c.map != 2) {
+    if (FUSED && c.map != 2) {
         const int nt = 4 * c.n_walls + CELLS;
 #pragma unroll 8
         for (int i = tid; i < nt; i += BS) tmpl[i] = __ldg(g_tmpl + i);
@@ -225,7 +230,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     const int64_t e = (int64_t)blockIdx.x * BS + tid;
     const bool valid = e < st.N;
     // which envs get an observation is known up front (every stepped env; the masked ones of a reset)
-    const bool emit = valid && obs != nullptr && c.rows > 0 && (IS_STEP || !mask || mask[e]);
+    const bool emit = FUSED && valid && obs != nullptr && c.rows > 0 && (IS_STEP || !mask || mask[e]);
     const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
     const int64_t row_len = (int64_t)c.rows * c.obs_dim;
     float *gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
@@ -278,8 +283,8 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bool acts_shared = false;   // true: the warp's rows were copied cooperatively (needs a warp barrier before use)
     if (IS_STEP && actions && valid_mask) {
         // (inside this warp's own tile: the other warp of the block may already be flushing its tile)
-        int32_t *wstage = (int32_t *)(smem + L.off_tile) + (size_t)warp * TILE_FLOATS;
         const int row_ints = c.act_rows * 3;
+        int32_t *wstage = (int32_t *)(smem + L.off_tile) + (size_t)warp * (FUSED ? TILE_FLOATS : 32 * row_ints);
         const int32_t *wsrc = actions + ((int64_t)blockIdx.x * BS + warp * 32) * row_ints;
 #ifndef COOP_ACTS
 #define COOP_ACTS 0   // measured slower (kernel +2 %, host-buffer step +10 %) than per-thread copies (r01t)
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     }
 
     // ---------------- phase B: still one thread per env; the warp transposes through its tile
-    if (emit_mask == 0u) return;   // (no bulk copy is pending either)
+    if (!FUSED || emit_mask == 0u) return;   // (no bulk copy is pending either)
 #if !EARLY_TMA
     ship_static();
 #endif
@@ -344,6 +349,227 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     out.finish();
     if (bulk_pending) bulk_wait_read_all();  // shared memory must outlive the copies' reads
 }
+
+// ------------------------------------------------------------------------------------------------ rows_kernel
+// Observation rows from the stored state (split path, the default): persistent blocks of 256 threads, each looping
+// over groups of G consecutive envs.  A group's R x D rows are ONE contiguous run of the observation buffer, so the
+// block assembles them as an image in shared memory - the static wall / maze columns are written once per block,
+// the ~45 % dynamic columns are scattered by independent jobs (at_rows.h), one job per thread - and hands the whole
+// image (33 KB for 8 envs of the 2v2 layout) to the bulk-async engine: one TMA copy per group, with an L2
+// evict-first hint, no per-column stores and no transposition.  Images are double-buffered (the engine drains one
+// while the block fills the other) and the next groups' state columns are requested two / one iterations ahead
+// (bullet counts, then the live records), so the loop is bounded by the drain, i.e. by the HBM write stream.
+// Launched as a programmatic dependent of env_kernel<.., false>: the prologue (tables, static columns) overlaps
+// the simulation's tail; griddepcontrol.wait orders everything else behind the simulation's stores.
+constexpr int RK_THREADS = 256;
+struct RowsSmem {
+    size_t off_img, off_rx, off_ry, off_rm, off_tx, off_ty, off_tp, off_zn, off_wlo, off_whi, off_emit, off_trig, off_occ, total;
+};
+__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats) {
+    RowsSmem L;
+    size_t o = 0;
+    const size_t S = (size_t)n * SLOTS_PER_TANK;
+    L.off_img = o; o += (((size_t)G * row_floats * 4 + 127) & ~(size_t)127) * 2;
+    L.off_rx = o; o += (size_t)G * S * 8;
+    L.off_ry = o; o += (size_t)G * S * 8;
+    L.off_rm = o; o += (size_t)G * S * 8;
+    L.off_tx = o; o += (size_t)G * n * 8;
+    L.off_ty = o; o += (size_t)G * n * 8;
+    L.off_wlo = o; o += (size_t)G * 8;
+    L.off_whi = o; o += (size_t)G * 8;
+    L.off_trig = o; o += 722 * 8;
+    L.off_tp = o; o += (size_t)G * n * 4;
+    L.off_zn = o; o += (size_t)G * 4;
+    L.off_emit = o; o += (size_t)G * 4 * 2;   // two parities
+    L.off_occ = o; o += (size_t)G * S * 2;     // per image: which bullet positions hold a bullet
+    L.total = (o + 15) & ~(size_t)15;
+    return L;
+}
+
+// NT / NR / TEAM: compile-time shape (0 / 0 / -1: from the config); MAZE: per-env maps; PP: (env, slot) pairs a thread
+// prefetches per group (G * 6n <= PP * RK_THREADS)
+template <int NT, int NR, int TEAM, bool MAZE, int PP>
+__global__ void __launch_bounds__(RK_THREADS, 3) rows_kernel(const __grid_constant__ KCfg c, const DevState st,
+                                                          const uint8_t *__restrict__ mask, float *__restrict__ obs,
+                                                          const float *__restrict__ g_tmpl, int lgG, int n_groups) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    typedef RowsShape<NT, NR, TEAM> SH;
+    const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, RD = SH::rows(c) * c.obs_dim;
+    const RowsSmem L = rows_smem_layout(G, n, RD);
+    const int img_stride = (int)((((size_t)G * RD * 4 + 127) & ~(size_t)127) / 4);  // floats between the two images
+    float *img0 = (float *)(smem + L.off_img);
+    double *rx = (double *)(smem + L.off_rx), *ry = (double *)(smem + L.off_ry);
+    uint64_t *rm = (uint64_t *)(smem + L.off_rm);
+    double *tx = (double *)(smem + L.off_tx), *ty = (double *)(smem + L.off_ty);
+    uint32_t *tp = (uint32_t *)(smem + L.off_tp), *zn = (uint32_t *)(smem + L.off_zn);
+    uint64_t *wl = (uint64_t *)(smem + L.off_wlo), *wh = (uint64_t *)(smem + L.off_whi);
+    int *em_s = (int *)(smem + L.off_emit);
+    uint8_t *occ = (uint8_t *)(smem + L.off_occ);
+    double *trig = (double *)(smem + L.off_trig);
+    const int tid = threadIdx.x;
+    const int N = (int)st.N;   // (at_create guarantees 6 n N < 2^31: 32-bit column indices)
+
+    // ---- prologue: nothing here depends on the simulation kernel's stores
+    for (int i = tid; i < 722; i += RK_THREADS) trig[i] = __ldg(st.trig + i);
+    for (int p = tid; p < G * S; p += RK_THREADS) { rm[p] = ROWS_EMPTY; occ[p] = 0; occ[G * S + p] = 0; }
+    for (int i = tid; i < 2 * img_stride / 4; i += RK_THREADS) reinterpret_cast<float4 *>(img0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (!MAZE) {
+        const int sl = 4 * c.n_walls + CELLS;
+        for (int gr = 0; gr < G * SH::rows(c); ++gr)   // gr = env * rows + row
+            for (int q = tid; q < sl; q += RK_THREADS) {
+                const float v = __ldg(g_tmpl + q);
+                img0[gr * c.obs_dim + c.off_walls + q] = v;
+                img0[img_stride + gr * c.obs_dim + c.off_walls + q] = v;
+            }
+    }
+    const bool bulk_ok = (((size_t)RD * 4) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0);
+    const uint64_t pol = make_evict_first_policy();
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+
+    // ---- prefetch registers.  Stage A: bullet count + emit flag of the thread's (env, slot) pairs (two groups
+    // ahead, two register sets used alternately - a register move of an in-flight load would wait for it); stage B:
+    // the live records of those pairs, this thread's (env, tank) pair and env scalars (one group ahead).
+    uint32_t x_cnt[PP], x_em[PP], y_cnt[PP], y_em[PP];
+    uint64_t r_m[PP];
+    double r_x[PP], r_y[PP];
+    double t_x = 0.0, t_y = 0.0;
+    uint32_t t_p = 0, e_zn = 0, e_em = 0;
+    uint64_t e_wl = 0, e_wh = 0;
+    const int my_g = tid & (G - 1);
+    auto load_a = [&](int grp, uint32_t *cn, uint32_t *em) {
+        const int e = grp * G + my_g;
+        const bool in = grp < n_groups && e < N;
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            cn[pp] = 0; em[pp] = 0;
+            if (in && tid + pp * RK_THREADS < G * S) {   // (RK_THREADS is a multiple of G: same env for every pp)
+                cn[pp] = st.cnt[e];
+                em[pp] = mask ? (uint32_t)mask[e] : 1u;
+            }
+        }
+    };
+    auto load_b = [&](int grp, const uint32_t *cn, const uint32_t *em) {
+        const int e = grp * G + my_g;
+        const bool in = grp < n_groups && e < N;
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            r_m[pp] = ROWS_EMPTY; r_x[pp] = 0.0; r_y[pp] = 0.0;
+            const uint32_t s = (uint32_t)((tid + pp * RK_THREADS) >> lgG);
+            if (em[pp] && s < cn[pp]) {   // (cn == 0 outside the batch)
+                const int g = (int)s * N + e;
+                r_m[pp] = st.bmeta[g]; r_x[pp] = st.bx[g]; r_y[pp] = st.by[g];
+            }
+        }
+        t_x = 0.0; t_y = 0.0; t_p = 0;
+        if (in && tid < G * n) {
+            const int g = (tid >> lgG) * N + e;
+            t_x = st.tx[g]; t_y = st.ty[g]; t_p = st.tpack[g];
+        }
+        e_zn = 0; e_em = 0; e_wl = 0; e_wh = 0;
+        if (in && tid >= RK_THREADS - G) {   // env scalars: the block's last G threads (RK_THREADS - G + g has my_g == g)
+            e_zn = st.zones[e];
+            e_em = mask ? (uint32_t)mask[e] : 1u;
+            if (MAZE) { e_wl = st.wall_lo[e]; e_wh = st.wall_hi[e]; }
+        }
+    };
+    const int g0 = blockIdx.x, gs = gridDim.x;
+    const int nrows = SH::rows(c);
+    const int jobs_pos = G * S, jobs_tank = G * nrows * n, jobs = jobs_pos + jobs_tank + (MAZE ? G * CELLS : 0);
+
+    // one group: `use` = counts of group grp + 1 (loaded one iteration ago), `fill` = receives those of grp + 2
+    auto group = [&](int grp, int it, const uint32_t *use_cnt, const uint32_t *use_em, uint32_t *fill_cnt,
+                     uint32_t *fill_em) {
+        float *img = img0 + (it & 1) * img_stride;
+        int *em_it = em_s + (it & 1) * G;
+        uint8_t *occ_it = occ + (it & 1) * G * S;
+        // ---- phase 1: this group's prefetched columns -> the block's tables
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) {
+            const uint64_t m = r_m[pp];
+            if (m != ROWS_EMPTY) {
+                const int q = ((int)(m & 15u) * SLOTS_PER_TANK + (int)((m >> BM_RANK) & 7u)) * G + my_g;
+                rm[q] = m; rx[q] = r_x[pp]; ry[q] = r_y[pp];
+            }
+        }
+        if (tid < G * n) { tx[tid] = t_x; ty[tid] = t_y; tp[tid] = t_p; }   // [tank][env]
+        int my_em = 1;
+        if (tid >= RK_THREADS - G) {
+            zn[my_g] = e_zn; em_it[my_g] = (int)e_em;
+            if (MAZE) { wl[my_g] = e_wl; wh[my_g] = e_wh; }
+            my_em = (int)e_em;
+        }
+        // ---- prefetch: records of the next group, counts of the one after
+        load_b(grp + gs, use_cnt, use_em);
+        load_a(grp + 2 * gs, fill_cnt, fill_em);
+        // the copy that last read this image (two groups ago) must be done with shared memory
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
+        const int all_emit = __syncthreads_and(my_em);
+        // ---- phase 2: one job per thread (2v2, 8 envs: 192 position jobs + 64 tank jobs).  Position jobs are
+        // rank-major - a warp holds ONE rank of every owner - and a position that holds no bullet now and held none
+        // when this image was last filled is skipped (it is still zero): the warps of ranks 3..5 mostly have no work.
+        for (int j = tid; j < jobs; j += RK_THREADS) {
+            const int g = j & (G - 1);
+            if (j < jobs_pos) {
+                const int jp = j >> lgG;
+                const int k = jp / n, o = jp - k * n;
+                const int q = (o * SLOTS_PER_TANK + k) * G + g;
+                const uint64_t m = rm[q];
+                const bool has = m != ROWS_EMPTY;
+                if (!has && !occ_it[q]) continue;
+                occ_it[q] = has ? 1 : 0;
+                rows_position_job<NT, NR, TEAM>(c, trig, o, k, m, rx[q], ry[q], tx + g, ty + g, G, img + g * RD, g);
+                if (has) rm[q] = ROWS_EMPTY;   // the table is empty again for the next group
+            } else if (j < jobs_pos + jobs_tank) {   // the rows' own blocks first, then the other-tank blocks
+                const int j2 = (j - jobs_pos) >> lgG;
+                int r, i;
+                if (j2 < nrows) {
+                    r = j2;
+                    i = SH::team(c) ? c.agent_tank[r] : r;
+                } else {
+                    const int ro = j2 - nrows;
+                    r = ro / (n - 1);
+                    const int oi = ro - r * (n - 1), t = SH::team(c) ? c.agent_tank[r] : r;
+                    i = oi < t ? oi : oi + 1;
+                }
+                rows_tank_job<NT, NR, TEAM>(c, trig, st.corn, r, i, tx + g, ty + g, tp + g, G, zn[g], img + g * RD);
+            } else {
+                rows_maze_job(c, wl[g], wh[g], (j - jobs_pos - jobs_tank) >> lgG, img + g * RD);
+            }
+        }
+        fence_async_smem();   // the image is read by the async proxy
+        __syncthreads();
+        // ---- phase 3: ship the image
+        float *dst = obs + (int64_t)grp * G * RD;
+        if (all_emit && bulk_ok) {
+            if (tid == 0) {
+                bulk_store(dst, img, (uint32_t)(G * RD * 4), pol);
+                bulk_commit();
+            }
+        } else {   // masked reset / ragged tail / rows that are not 16-byte multiples: coalesced plain stores
+            if (tid == 0) bulk_commit();   // (an empty group keeps the wait_group arithmetic uniform)
+            for (int g = 0; g < G; ++g) {
+                if (!em_it[g]) continue;
+                for (int q = tid; q < RD; q += RK_THREADS) stg_stream(dst + g * RD + q, img[g * RD + q], pol);
+            }
+        }
+    };
+
+    load_a(g0, x_cnt, x_em);
+    load_a(g0 + gs, y_cnt, y_em);
+    load_b(g0, x_cnt, x_em);
+    int it = 0;
+    for (int grp = g0;;) {   // x / y alternate between "counts of the next group" and "being filled"
+        if (grp >= n_groups) break;
+        group(grp, it, y_cnt, y_em, x_cnt, x_em);
+        grp += gs; ++it;
+        if (grp >= n_groups) break;
+        group(grp, it, x_cnt, x_em, y_cnt, y_em);
+        grp += gs; ++it;
+    }
+    if (tid == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
+}
+typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int);
 
 __global__ void gather_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
                               PackedEnv *out) {
@@ -492,7 +718,13 @@ struct at_env {
     uint8_t *d_done_scratch;
     HostLuts luts;
     const float *d_tmpl;
-    size_t smem_bytes;
+    size_t smem_bytes;        // env_kernel<.., true>  (fused rows)
+    size_t smem_bytes_sim;    // env_kernel<.., false> (simulation only)
+    bool split_rows;          // rows by rows_kernel behind the simulation (default); AT_FUSED_ROWS=1: one fused kernel
+    bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
+    int rows_lgG, rows_grid;  // rows_kernel: log2(envs per group), persistent grid
+    rows_kernel_fn rows_fn;   // the instantiation for this config's shape
+    size_t rows_smem;
     int64_t launches;
     std::vector<std::pair<const void *, void *>> mapped;  // host buffers seen by at_step_host -> device alias (null: not mapped)
 };
@@ -500,14 +732,42 @@ struct at_env {
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s) {
     const int grid = (int)((env->n_envs + BS - 1) / BS);
+    const bool rows = d_obs != nullptr && env->k.rows > 0;
+    if (!env->split_rows) {
+        if (is_step)
+            env_kernel<true, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
+                                                                    d_done, env->d_tmpl);
+        else
+            env_kernel<false, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
+                                                                     d_done, env->d_tmpl);
+        env->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        return AT_OK;
+    }
     if (is_step)
-        env_kernel<true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                          d_done, env->d_tmpl);
+        env_kernel<true, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
+                                                                     d_done, env->d_tmpl);
     else
-        env_kernel<false><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                           d_done, env->d_tmpl);
+        env_kernel<false, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
+                                                                      d_done, env->d_tmpl);
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
+    if (!rows) return AT_OK;
+    const int G = 1 << env->rows_lgG;
+    const int n_groups = (int)((env->n_envs + G - 1) / G);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(n_groups < env->rows_grid ? n_groups : env->rows_grid));
+    cfg.blockDim = dim3(RK_THREADS);
+    cfg.dynamicSmemBytes = env->rows_smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = env->pdl ? 1 : 0;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups));
+    env->launches += 1;
     return AT_OK;
 }
 
@@ -518,6 +778,8 @@ const char *at_version(void) { return "alphatank_b200 0.1 (sm_100a)"; }
 
 int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_t seed, int device, at_env **out) {
     if (!cfg || !out || n_envs <= 0) return fail(AT_ERR_ARG, "at_create: null config / handle or n_envs <= 0");
+    if (n_envs * AT_MAX_TANKS * SLOTS_PER_TANK >= ((int64_t)1 << 31))
+        return fail(AT_ERR_ARG, "at_create: more than 2^31 / 48 envs per handle (32-bit column indices); shard the batch");
     KCfg k;
     std::string msg = build_kcfg(cfg, seed, env_id_base, k);
     if (!msg.empty()) return fail(AT_ERR_ARG, "at_create: " + msg);
@@ -577,8 +839,48 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         cudaMemcpy(b + L.o_tmpl, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice);
     }
     env->smem_bytes = smem_layout(k.n_tanks, k.n_walls, k.n_bots).total;
-    cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
-    cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+    env->smem_bytes_sim = smem_layout(k.n_tanks, k.n_walls, k.n_bots, false, k.act_rows).total;
+    cudaFuncSetAttribute(env_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+    cudaFuncSetAttribute(env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
+    cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
+    cudaFuncSetAttribute(env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
+    {   // rows_kernel: the largest group (power of two, <= 8 envs) whose two images leave room for 3 blocks per SM,
+        // else whatever fits at all; G * 6n pairs must fit the prefetch registers
+        const char *fz = getenv("AT_FUSED_ROWS"), *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");
+        env->split_rows = !(fz && fz[0] == '1') && k.rows > 0;
+        env->pdl = !(np && np[0] == '1');
+        const int RD = k.rows * k.obs_dim;
+        int lg = gg ? atoi(gg) : 3;
+        if (lg < 0) lg = 0;
+        if (lg > 4) lg = 4;
+        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD).total > (size_t)72 * 1024 ||
+                          (1 << lg) * k.n_tanks * SLOTS_PER_TANK > 2 * RK_THREADS))
+            --lg;
+        const bool pp1 = (1 << lg) * k.n_tanks * SLOTS_PER_TANK <= RK_THREADS;
+        if (k.map == AT_MAP_MAZE) env->rows_fn = rows_kernel<0, 0, -1, true, 2>;
+        else if (pp1 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) env->rows_fn = rows_kernel<4, 2, 1, false, 1>;
+        else if (pp1 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) env->rows_fn = rows_kernel<2, 2, 0, false, 1>;
+        else env->rows_fn = rows_kernel<0, 0, -1, false, 2>;
+        env->rows_lgG = lg;
+        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD).total;
+        env->rows_grid = prop.multiProcessorCount;
+        if (env->split_rows) {
+            if (env->rows_smem > (size_t)prop.sharedMemPerBlockOptin) {
+                cudaFree(env->arena);
+                delete env;
+                return fail(AT_ERR_ARG, "at_create: an observation image does not fit shared memory");
+            }
+            cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->rows_smem);
+            int bps = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)env->rows_fn, RK_THREADS, env->rows_smem) != cudaSuccess || bps < 1) {
+                cudaGetLastError();
+                bps = 1;
+            }
+            const char *bp = getenv("AT_ROWS_BPS");
+            if (bp && atoi(bp) > 0 && atoi(bp) < bps) bps = atoi(bp);
+            env->rows_grid = prop.multiProcessorCount * bps;
+        }
+    }
     // GamingENV.__init__ -> self.reset() (gaming_env.py:43): the constructor's own reset consumes draws
     int rc = launch_env_kernel(env, false, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
     if (rc == AT_OK && cudaDeviceSynchronize() != cudaSuccess) rc = fail(AT_ERR_CUDA, "at_create: reset kernel failed");

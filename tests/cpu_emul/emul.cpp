@@ -16,6 +16,7 @@
 
 #include "../../alphatank_b200/csrc/at_host.h"
 #include "../../alphatank_b200/csrc/at_sim.h"
+#include "../../alphatank_b200/csrc/at_rows.h"
 
 using namespace at;
 
@@ -39,6 +40,44 @@ struct DirectSink {  // the emulator writes column j of the env's observation ro
     void put(float v) { row[j++] = v; }
     void skip_static(const float *tmpl, int n) { for (int k = 0; k < n; ++k) row[j++] = tmpl[k]; }
 };
+
+template <int A, int B, int C>
+struct ShapeTag { static constexpr int nt = A, nr = B, tm = C; };
+// rows_kernel's formulation (at_rows.h): the rows of env e rebuilt from the STORED state by independent jobs
+static int g_rows_mode = 0;  // 0: Sim::emit_rows (the fused kernel's phase B), 1: the jobs of rows_kernel
+static void rows_from_state(em_env *env, int64_t e, float *img) {
+    const KCfg &c = env->k;
+    const DevState &st = env->st;
+    const int n = c.n_tanks, S = n * SLOTS_PER_TANK;
+    double tx[MAX_TANKS], ty[MAX_TANKS];
+    uint32_t tp[MAX_TANKS];
+    for (int i = 0; i < n; ++i) { tx[i] = st.tx[i * st.N + e]; ty[i] = st.ty[i * st.N + e]; tp[i] = st.tpack[i * st.N + e]; }
+    std::vector<uint64_t> rm(S, ROWS_EMPTY);
+    std::vector<double> rx(S, 0.0), ry(S, 0.0);
+    for (uint32_t s = 0; s < st.cnt[e]; ++s) {   // phase 1 of the kernel: scatter the live records by (owner, rank)
+        const uint64_t m = st.bmeta[(int64_t)s * st.N + e];
+        const int p = (int)(m & 15u) * SLOTS_PER_TANK + (int)((m >> BM_RANK) & 7u);
+        rm[p] = m; rx[p] = st.bx[(int64_t)s * st.N + e]; ry[p] = st.by[(int64_t)s * st.N + e];
+    }
+    if (c.map != AT_MAP_MAZE) {
+        for (int r = 0; r < c.rows; ++r)
+            memcpy(img + (int64_t)r * c.obs_dim + c.off_walls, env->tmpl.data(), (4 * c.n_walls + CELLS) * sizeof(float));
+    } else {
+        for (int cell = 0; cell < CELLS; ++cell) rows_maze_job(c, st.wall_lo[e], st.wall_hi[e], cell, img);
+    }
+    // the kernel's compile-time shapes (2v2 team, 1v1) and the generic build
+    auto jobs = [&](auto shape) {
+        constexpr int NT = decltype(shape)::nt, NR = decltype(shape)::nr, TM = decltype(shape)::tm;
+        for (int p = 0; p < S; ++p)
+            rows_position_job<NT, NR, TM>(c, st.trig, p / SLOTS_PER_TANK, p % SLOTS_PER_TANK, rm[p], rx[p], ry[p], tx, ty, 1,
+                                          img, (int)((e + p) & 7));
+        for (int r = 0; r < c.rows; ++r)
+            for (int i = 0; i < n; ++i) rows_tank_job<NT, NR, TM>(c, st.trig, st.corn, r, i, tx, ty, tp, 1, st.zones[e], img);
+    };
+    if (n == 4 && c.rows == 2 && c.team_layout) jobs(ShapeTag<4, 2, 1>{});
+    else if (n == 2 && c.rows == 2 && !c.team_layout) jobs(ShapeTag<2, 2, 0>{});
+    else jobs(ShapeTag<0, 0, -1>{});
+}
 
 static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
                 uint8_t *done) {
@@ -67,8 +106,13 @@ static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t
                 emit = obs != nullptr;
             }
             if (emit && c.rows > 0) {
-                DirectSink out{obs + e * row_len, 0};
-                s.emit_rows(out);
+                if (g_rows_mode) {
+                    for (int64_t q = 0; q < row_len; ++q) obs[e * row_len + q] = -12345.0f;  // every column must be written
+                    rows_from_state(env, e, obs + e * row_len);
+                } else {
+                    DirectSink out{obs + e * row_len, 0};
+                    s.emit_rows(out);
+                }
             }
         }
     }
@@ -122,6 +166,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     return AT_OK;
 }
 void em_destroy(em_env *env) { delete env; }
+void em_set_rows_mode(int m) { g_rows_mode = m; }
 int em_obs_dim(em_env *env) { return env->k.obs_dim; }
 int em_obs_rows(em_env *env) { return env->k.rows; }
 int em_action_rows(em_env *env) { return env->k.act_rows; }

@@ -15,7 +15,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "alphatank_b200", "csrc")
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("at_sim.h", "at_host.h", "at_types.h")]
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("at_sim.h", "at_host.h", "at_types.h", "at_rows.h")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-ffp-contract=off", "-mfma", "-std=c++17", "-shared", "-o", LIB,
                                SRC, "-lm"])
@@ -35,6 +35,7 @@ def lib():
         for f in ("em_obs_dim", "em_obs_rows", "em_action_rows"):
             getattr(L, f).argtypes = [vp]
         L.em_reset.argtypes = [vp, vp, vp]
+        L.em_set_rows_mode.argtypes = [i32]
         L.em_step.argtypes = [vp, vp, vp, vp, vp]
         L.em_get_state.argtypes = [vp, i64, vp]
         L.em_set_state.argtypes = [vp, i64, vp]

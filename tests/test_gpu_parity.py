@@ -273,3 +273,41 @@ def test_set_weakness_hot_swap_equals_construction_and_oracle():
         assert np.array_equal(oa, oo) and np.array_equal(ra, ro) and np.array_equal(da, do), "oracle, tick %d" % t
     with pytest.raises(ValueError):
         _capi.check(b.core.L.at_set_weakness(b.core.h, 1.5), "at_set_weakness")
+
+
+@pytest.mark.parametrize("name,knobs", [
+    ("team_vs_bot", {}), ("team_vs_bot", {"AT_ROWS_LGG": "0"}), ("team_vs_bot", {"AT_ROWS_LGG": "4", "AT_NO_PDL": "1"}),
+    ("team_vs_bot", {"AT_ROWS_BPS": "1"}), ("agent_t96", {}), ("team_vs_bot_maze", {"AT_ROWS_LGG": "2"}),
+    ("team_8_mixed", {}), ("team_three_teams_nodebuff", {}), ("botagent_smart_maze", {}), ("agent_nobuff_battlefield", {}),
+])
+def test_split_rows_kernel_equals_fused_rows(name, knobs):
+    """Default path = simulation kernel + rows_kernel (rows rebuilt from the stored state, one bulk copy per group of
+    envs); AT_FUSED_ROWS=1 = the single fused kernel.  Same bits in every observation column on a ragged batch
+    (1003 envs: the last group is partial), through auto-resets, and after a masked reset."""
+    spec = SWEEP[name]
+    N, seed, base = 1003, 31, 900
+    old = {k: os.environ.get(k) for k in ("AT_FUSED_ROWS", "AT_ROWS_LGG", "AT_NO_PDL", "AT_ROWS_BPS")}
+    try:
+        os.environ["AT_FUSED_ROWS"] = "1"
+        a = _gpu(spec, N, seed, base, auto_reset=True)
+        os.environ["AT_FUSED_ROWS"] = "0"
+        os.environ.update(knobs)
+        b = _gpu(spec, N, seed, base, auto_reset=True)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    assert np.array_equal(a.reset(), b.reset())
+    ids = np.arange(base, base + N)
+    for t in range(120):
+        acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
+        oa, ra, da = a.step(acts)
+        ob, rb, db = b.step(acts)
+        assert np.array_equal(da, db) and np.array_equal(ra, rb)
+        if not np.array_equal(oa, ob):
+            raise AssertionError("%s tick %d obs differ at (env, col) %s" % (name, t, np.argwhere(oa != ob)[:8].tolist()))
+    mask = (np.arange(N) % 5 == 0).astype(np.uint8)
+    mask[-1] = 1
+    assert np.array_equal(a.reset(mask), b.reset(mask))

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("csv")
     ap.add_argument("--top", type=int, default=40)
     ap.add_argument("--envs", type=int, default=65536)
+    ap.add_argument("--by", default="samples", choices=["samples", "inst"], help="order of the per-line list")
     a = ap.parse_args()
     rows = list(csv.reader(open(a.csv)))
     cur_file, hdr = None, None
@@ -117,8 +118,8 @@ def main():
             nm, 100 * b["inst"] / tot_inst, b["inst"] / warps, b["tinst"] / max(b["inst"], 1),
             100 * b["samples"] / max(tot_s, 1),
             " ".join("%s:%.0f%%" % (k, 100 * x / max(b["samples"], 1)) for k, x in ts)))
-    print("\ntop lines by stall samples")
-    for (f, ln), v in sorted(per_line.items(), key=lambda kv: -kv[1]["samples"])[:a.top]:
+    print("\ntop lines by " + ("stall samples" if a.by == "samples" else "warp instructions"))
+    for (f, ln), v in sorted(per_line.items(), key=lambda kv: -kv[1][a.by])[:a.top]:
         ts = sorted(v["stalls"].items(), key=lambda kv: -kv[1])[:3]
         print("%5.2f%% inst %5.2f%% lanes %4.1f %s:%d  %s  [%s]" % (
             100 * v["samples"] / max(tot_s, 1), 100 * v["inst"] / tot_inst, v["tinst"] / max(v["inst"], 1),
