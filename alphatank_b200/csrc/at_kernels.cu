@@ -351,25 +351,26 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
 }
 
 // ------------------------------------------------------------------------------------------------ rows_kernel
-// Observation rows from the stored state (split path, the default): persistent blocks of 256 threads, each looping
-// over groups of G consecutive envs.  A group's R x D rows are ONE contiguous run of the observation buffer, so the
-// block assembles them as an image in shared memory - the static wall / maze columns are written once per block,
-// the ~45 % dynamic columns are scattered by independent jobs (at_rows.h), one job per thread - and hands the whole
-// image (33 KB for 8 envs of the 2v2 layout) to the bulk-async engine: one TMA copy per group, with an L2
-// evict-first hint, no per-column stores and no transposition.  Images are double-buffered (the engine drains one
-// while the block fills the other) and the next groups' state columns are requested two / one iterations ahead
-// (bullet counts, then the live records), so the loop is bounded by the drain, i.e. by the HBM write stream.
+// Observation rows from the stored state (split path, the default).  Every WARP works on its own: it loops over
+// groups of G consecutive envs (4 for the 2v2 layout), whose R x D rows are ONE contiguous run of the observation
+// buffer, assembles them as an image in its own slice of shared memory - the static wall / maze columns are written
+// once per warp, the ~45 % dynamic columns are scattered by independent jobs (at_rows.h), 32 jobs per pass, every
+// pass of one kind - and hands the whole image (17 KB) to the bulk-async engine: one TMA copy per group, with an L2
+// evict-first hint, no per-column stores, no transposition, and no block-wide barrier anywhere (warps only meet
+// their own copy).  The next groups' state columns are requested two / one iterations ahead (bullet counts, then the
+// live records), and 12 warps per SM keep the copy engine busy while each waits for its image to drain, so the
+// loop is bounded by the HBM write stream.
 // Launched as a programmatic dependent of env_kernel<.., false>: the prologue (tables, static columns) overlaps
 // the simulation's tail; griddepcontrol.wait orders everything else behind the simulation's stores.
-constexpr int RK_THREADS = 256;
-struct RowsSmem {
-    size_t off_img, off_rx, off_ry, off_rm, off_tx, off_ty, off_tp, off_zn, off_wlo, off_whi, off_emit, off_trig, off_occ, total;
+constexpr int RK_MAX_WARPS = 16;   // warps per block: a launch parameter (blockDim.x / 32)
+struct RowsSmem {   // per warp, after the block's trig table
+    size_t off_img, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, per_warp, total;
 };
-__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats) {
+__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats, int warps) {
     RowsSmem L;
     size_t o = 0;
     const size_t S = (size_t)n * SLOTS_PER_TANK;
-    L.off_img = o; o += (((size_t)G * row_floats * 4 + 127) & ~(size_t)127) * 2;
+    L.off_img = o; o += ((size_t)G * row_floats * 4 + 127) & ~(size_t)127;
     L.off_rx = o; o += (size_t)G * S * 8;
     L.off_ry = o; o += (size_t)G * S * 8;
     L.off_rm = o; o += (size_t)G * S * 8;
@@ -377,73 +378,73 @@ __host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_float
     L.off_ty = o; o += (size_t)G * n * 8;
     L.off_wlo = o; o += (size_t)G * 8;
     L.off_whi = o; o += (size_t)G * 8;
-    L.off_trig = o; o += 722 * 8;
     L.off_tp = o; o += (size_t)G * n * 4;
     L.off_zn = o; o += (size_t)G * 4;
-    L.off_emit = o; o += (size_t)G * 4 * 2;   // two parities
-    L.off_occ = o; o += (size_t)G * S * 2;     // per image: which bullet positions hold a bullet
-    L.total = (o + 15) & ~(size_t)15;
+    L.off_emit = o; o += (size_t)G * 4;
+    L.off_occ = o; o += (size_t)G * S;     // which bullet positions of the image hold a bullet
+    L.per_warp = (o + 127) & ~(size_t)127;
+    L.total = 722 * 8 + 64 + L.per_warp * warps;   // (722 * 8 + 64 is a multiple of 128)
     return L;
 }
 
-// NT / NR / TEAM: compile-time shape (0 / 0 / -1: from the config); MAZE: per-env maps; PP: (env, slot) pairs a thread
-// prefetches per group (G * 6n <= PP * RK_THREADS)
+// NT / NR / TEAM: compile-time shape (0 / 0 / -1: from the config); MAZE: per-env maps; PP: (env, slot) pairs a lane
+// prefetches per group (G * 6n <= 32 PP)
 template <int NT, int NR, int TEAM, bool MAZE, int PP>
-__global__ void __launch_bounds__(RK_THREADS, 3) rows_kernel(const __grid_constant__ KCfg c, const DevState st,
+__global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                           const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                           const float *__restrict__ g_tmpl, int lgG, int n_groups) {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef RowsShape<NT, NR, TEAM> SH;
-    const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, RD = SH::rows(c) * c.obs_dim;
-    const RowsSmem L = rows_smem_layout(G, n, RD);
-    const int img_stride = (int)((((size_t)G * RD * 4 + 127) & ~(size_t)127) / 4);  // floats between the two images
-    float *img0 = (float *)(smem + L.off_img);
-    double *rx = (double *)(smem + L.off_rx), *ry = (double *)(smem + L.off_ry);
-    uint64_t *rm = (uint64_t *)(smem + L.off_rm);
-    double *tx = (double *)(smem + L.off_tx), *ty = (double *)(smem + L.off_ty);
-    uint32_t *tp = (uint32_t *)(smem + L.off_tp), *zn = (uint32_t *)(smem + L.off_zn);
-    uint64_t *wl = (uint64_t *)(smem + L.off_wlo), *wh = (uint64_t *)(smem + L.off_whi);
-    int *em_s = (int *)(smem + L.off_emit);
-    uint8_t *occ = (uint8_t *)(smem + L.off_occ);
-    double *trig = (double *)(smem + L.off_trig);
-    const int tid = threadIdx.x;
+    const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, nrows = SH::rows(c), RD = nrows * c.obs_dim;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const RowsSmem L = rows_smem_layout(G, n, RD, nwarps);
+    double *trig = (double *)smem;
+    unsigned char *ws = smem + 722 * 8 + 64 + (size_t)warp * L.per_warp;
+    float *img = (float *)(ws + L.off_img);
+    double *rx = (double *)(ws + L.off_rx), *ry = (double *)(ws + L.off_ry);
+    uint64_t *rm = (uint64_t *)(ws + L.off_rm);
+    double *tx = (double *)(ws + L.off_tx), *ty = (double *)(ws + L.off_ty);
+    uint32_t *tp = (uint32_t *)(ws + L.off_tp), *zn = (uint32_t *)(ws + L.off_zn);
+    uint64_t *wl = (uint64_t *)(ws + L.off_wlo), *wh = (uint64_t *)(ws + L.off_whi);
+    int *em_s = (int *)(ws + L.off_emit);
+    uint8_t *occ = (uint8_t *)(ws + L.off_occ);
     const int N = (int)st.N;   // (at_create guarantees 6 n N < 2^31: 32-bit column indices)
 
     // ---- prologue: nothing here depends on the simulation kernel's stores
-    for (int i = tid; i < 722; i += RK_THREADS) trig[i] = __ldg(st.trig + i);
-    for (int p = tid; p < G * S; p += RK_THREADS) { rm[p] = ROWS_EMPTY; occ[p] = 0; occ[G * S + p] = 0; }
-    for (int i = tid; i < 2 * img_stride / 4; i += RK_THREADS) reinterpret_cast<float4 *>(img0)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
+    for (int i = tid; i < 722; i += (int)blockDim.x) trig[i] = __ldg(st.trig + i);
+    for (int p = lane; p < G * S; p += 32) { rm[p] = ROWS_EMPTY; occ[p] = 0; }
+    for (int i = lane; i < G * RD / 4; i += 32) reinterpret_cast<float4 *>(img)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = ((G * RD) & ~3) + lane; i < G * RD; i += 32) img[i] = 0.f;
+    __syncwarp();
     if (!MAZE) {
         const int sl = 4 * c.n_walls + CELLS;
-        for (int gr = 0; gr < G * SH::rows(c); ++gr)   // gr = env * rows + row
-            for (int q = tid; q < sl; q += RK_THREADS) {
-                const float v = __ldg(g_tmpl + q);
-                img0[gr * c.obs_dim + c.off_walls + q] = v;
-                img0[img_stride + gr * c.obs_dim + c.off_walls + q] = v;
-            }
+        for (int q = lane; q < sl; q += 32) {
+            const float v = __ldg(g_tmpl + q);
+            for (int gr = 0; gr < G * nrows; ++gr) img[gr * c.obs_dim + c.off_walls + q] = v;   // gr = env * rows + row
+        }
     }
     const bool bulk_ok = (((size_t)RD * 4) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0);
     const uint64_t pol = make_evict_first_policy();
+    __syncthreads();   // the trig table (the only block-wide barrier)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
-    // ---- prefetch registers.  Stage A: bullet count + emit flag of the thread's (env, slot) pairs (two groups
+    // ---- prefetch registers.  Stage A: bullet count + emit flag of the lane's (env, slot) pairs (two groups
     // ahead, two register sets used alternately - a register move of an in-flight load would wait for it); stage B:
-    // the live records of those pairs, this thread's (env, tank) pair and env scalars (one group ahead).
+    // the live records of those pairs, the lane's (env, tank) pair and env scalars (one group ahead).
     uint32_t x_cnt[PP], x_em[PP], y_cnt[PP], y_em[PP];
     uint64_t r_m[PP];
     double r_x[PP], r_y[PP];
     double t_x = 0.0, t_y = 0.0;
     uint32_t t_p = 0, e_zn = 0, e_em = 0;
     uint64_t e_wl = 0, e_wh = 0;
-    const int my_g = tid & (G - 1);
+    const int my_g = lane & (G - 1);   // (32 is a multiple of G: a lane's pairs, tank pair and env scalars share the env)
     auto load_a = [&](int grp, uint32_t *cn, uint32_t *em) {
         const int e = grp * G + my_g;
         const bool in = grp < n_groups && e < N;
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
             cn[pp] = 0; em[pp] = 0;
-            if (in && tid + pp * RK_THREADS < G * S) {   // (RK_THREADS is a multiple of G: same env for every pp)
+            if (in && lane + pp * 32 < G * S) {
                 cn[pp] = st.cnt[e];
                 em[pp] = mask ? (uint32_t)mask[e] : 1u;
             }
@@ -455,35 +456,30 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rows_kernel(const __grid_consta
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
             r_m[pp] = ROWS_EMPTY; r_x[pp] = 0.0; r_y[pp] = 0.0;
-            const uint32_t s = (uint32_t)((tid + pp * RK_THREADS) >> lgG);
+            const uint32_t s = (uint32_t)((lane + pp * 32) >> lgG);
             if (em[pp] && s < cn[pp]) {   // (cn == 0 outside the batch)
                 const int g = (int)s * N + e;
                 r_m[pp] = st.bmeta[g]; r_x[pp] = st.bx[g]; r_y[pp] = st.by[g];
             }
         }
         t_x = 0.0; t_y = 0.0; t_p = 0;
-        if (in && tid < G * n) {
-            const int g = (tid >> lgG) * N + e;
+        if (in && lane < G * n) {
+            const int g = (lane >> lgG) * N + e;
             t_x = st.tx[g]; t_y = st.ty[g]; t_p = st.tpack[g];
         }
         e_zn = 0; e_em = 0; e_wl = 0; e_wh = 0;
-        if (in && tid >= RK_THREADS - G) {   // env scalars: the block's last G threads (RK_THREADS - G + g has my_g == g)
+        if (in && lane >= 32 - G) {   // env scalars: the warp's last G lanes (lane 32 - G + g has my_g == g)
             e_zn = st.zones[e];
             e_em = mask ? (uint32_t)mask[e] : 1u;
             if (MAZE) { e_wl = st.wall_lo[e]; e_wh = st.wall_hi[e]; }
         }
     };
-    const int g0 = blockIdx.x, gs = gridDim.x;
-    const int nrows = SH::rows(c);
+    const int gs = gridDim.x * nwarps, g0 = blockIdx.x * nwarps + warp;
     const int jobs_pos = G * S, jobs_tank = G * nrows * n, jobs = jobs_pos + jobs_tank + (MAZE ? G * CELLS : 0);
 
     // one group: `use` = counts of group grp + 1 (loaded one iteration ago), `fill` = receives those of grp + 2
-    auto group = [&](int grp, int it, const uint32_t *use_cnt, const uint32_t *use_em, uint32_t *fill_cnt,
-                     uint32_t *fill_em) {
-        float *img = img0 + (it & 1) * img_stride;
-        int *em_it = em_s + (it & 1) * G;
-        uint8_t *occ_it = occ + (it & 1) * G * S;
-        // ---- phase 1: this group's prefetched columns -> the block's tables
+    auto group = [&](int grp, const uint32_t *use_cnt, const uint32_t *use_em, uint32_t *fill_cnt, uint32_t *fill_em) {
+        // ---- phase 1: this group's prefetched columns -> the warp's tables
 #pragma unroll
         for (int pp = 0; pp < PP; ++pp) {
             const uint64_t m = r_m[pp];
@@ -492,23 +488,23 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rows_kernel(const __grid_consta
                 rm[q] = m; rx[q] = r_x[pp]; ry[q] = r_y[pp];
             }
         }
-        if (tid < G * n) { tx[tid] = t_x; ty[tid] = t_y; tp[tid] = t_p; }   // [tank][env]
-        int my_em = 1;
-        if (tid >= RK_THREADS - G) {
-            zn[my_g] = e_zn; em_it[my_g] = (int)e_em;
+        if (lane < G * n) { tx[lane] = t_x; ty[lane] = t_y; tp[lane] = t_p; }   // [tank][env]
+        bool my_em = true;
+        if (lane >= 32 - G) {
+            zn[my_g] = e_zn; em_s[my_g] = (int)e_em;
             if (MAZE) { wl[my_g] = e_wl; wh[my_g] = e_wh; }
-            my_em = (int)e_em;
+            my_em = e_em != 0;
         }
         // ---- prefetch: records of the next group, counts of the one after
         load_b(grp + gs, use_cnt, use_em);
         load_a(grp + 2 * gs, fill_cnt, fill_em);
-        // the copy that last read this image (two groups ago) must be done with shared memory
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 1;\n" ::: "memory");
-        const int all_emit = __syncthreads_and(my_em);
-        // ---- phase 2: one job per thread (2v2, 8 envs: 192 position jobs + 64 tank jobs).  Position jobs are
-        // rank-major - a warp holds ONE rank of every owner - and a position that holds no bullet now and held none
-        // when this image was last filled is skipped (it is still zero): the warps of ranks 3..5 mostly have no work.
-        for (int j = tid; j < jobs; j += RK_THREADS) {
+        // the previous copy must be done reading the image
+        if (lane == 0) bulk_wait_read_all();
+        const bool all_emit = __all_sync(0xffffffffu, my_em);   // (also the warp barrier between phase 1 and 2)
+        // ---- phase 2: 32 jobs per pass (2v2, 4 envs: three passes of position jobs, one of tank jobs).  Position jobs
+        // are rank-major - a pass holds two ranks of every owner - and a position that holds no bullet now and held
+        // none when the image was last filled is skipped (it is still zero): the pass of ranks 4, 5 mostly has no work.
+        for (int j = lane; j < jobs; j += 32) {
             const int g = j & (G - 1);
             if (j < jobs_pos) {
                 const int jp = j >> lgG;
@@ -516,9 +512,9 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rows_kernel(const __grid_consta
                 const int q = (o * SLOTS_PER_TANK + k) * G + g;
                 const uint64_t m = rm[q];
                 const bool has = m != ROWS_EMPTY;
-                if (!has && !occ_it[q]) continue;
-                occ_it[q] = has ? 1 : 0;
-                rows_position_job<NT, NR, TEAM>(c, trig, o, k, m, rx[q], ry[q], tx + g, ty + g, G, img + g * RD, g);
+                if (!has && !occ[q]) continue;
+                occ[q] = has ? 1 : 0;
+                rows_position_job<NT, NR, TEAM>(c, trig, o, k, m, rx[q], ry[q], tx + g, ty + g, G, img + g * RD, g + 4 * (o >> 1));
                 if (has) rm[q] = ROWS_EMPTY;   // the table is empty again for the next group
             } else if (j < jobs_pos + jobs_tank) {   // the rows' own blocks first, then the other-tank blocks
                 const int j2 = (j - jobs_pos) >> lgG;
@@ -538,36 +534,35 @@ __global__ void __launch_bounds__(RK_THREADS, 3) rows_kernel(const __grid_consta
             }
         }
         fence_async_smem();   // the image is read by the async proxy
-        __syncthreads();
+        __syncwarp();
         // ---- phase 3: ship the image
         float *dst = obs + (int64_t)grp * G * RD;
         if (all_emit && bulk_ok) {
-            if (tid == 0) {
+            if (lane == 0) {
                 bulk_store(dst, img, (uint32_t)(G * RD * 4), pol);
                 bulk_commit();
             }
         } else {   // masked reset / ragged tail / rows that are not 16-byte multiples: coalesced plain stores
-            if (tid == 0) bulk_commit();   // (an empty group keeps the wait_group arithmetic uniform)
             for (int g = 0; g < G; ++g) {
-                if (!em_it[g]) continue;
-                for (int q = tid; q < RD; q += RK_THREADS) stg_stream(dst + g * RD + q, img[g * RD + q], pol);
+                if (!em_s[g]) continue;
+                for (int q = lane; q < RD; q += 32) stg_stream(dst + g * RD + q, img[g * RD + q], pol);
             }
+            __syncwarp();   // the tables (em_s) are rewritten by the next group's phase 1
         }
     };
 
     load_a(g0, x_cnt, x_em);
     load_a(g0 + gs, y_cnt, y_em);
     load_b(g0, x_cnt, x_em);
-    int it = 0;
     for (int grp = g0;;) {   // x / y alternate between "counts of the next group" and "being filled"
         if (grp >= n_groups) break;
-        group(grp, it, y_cnt, y_em, x_cnt, x_em);
-        grp += gs; ++it;
+        group(grp, y_cnt, y_em, x_cnt, x_em);
+        grp += gs;
         if (grp >= n_groups) break;
-        group(grp, it, x_cnt, x_em, y_cnt, y_em);
-        grp += gs; ++it;
+        group(grp, x_cnt, x_em, y_cnt, y_em);
+        grp += gs;
     }
-    if (tid == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
+    if (lane == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
 }
 typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int);
 
@@ -722,7 +717,7 @@ struct at_env {
     size_t smem_bytes_sim;    // env_kernel<.., false> (simulation only)
     bool split_rows;          // rows by rows_kernel behind the simulation (default); AT_FUSED_ROWS=1: one fused kernel
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
-    int rows_lgG, rows_grid;  // rows_kernel: log2(envs per group), persistent grid
+    int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
     rows_kernel_fn rows_fn;   // the instantiation for this config's shape
     size_t rows_smem;
     int64_t launches;
@@ -757,8 +752,9 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     const int n_groups = (int)((env->n_envs + G - 1) / G);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3((unsigned)(n_groups < env->rows_grid ? n_groups : env->rows_grid));
-    cfg.blockDim = dim3(RK_THREADS);
+    const int want = (n_groups + env->rows_warps - 1) / env->rows_warps;
+    cfg.gridDim = dim3((unsigned)(want < env->rows_grid ? want : env->rows_grid));
+    cfg.blockDim = dim3(env->rows_warps * 32);
     cfg.dynamicSmemBytes = env->rows_smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
@@ -844,25 +840,31 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaFuncSetAttribute(env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
-    {   // rows_kernel: the largest group (power of two, <= 8 envs) whose two images leave room for 3 blocks per SM,
-        // else whatever fits at all; G * 6n pairs must fit the prefetch registers
+    {   // rows_kernel: the largest group (power of two, <= 4 envs) whose image keeps 12 warps on an SM, else whatever
+        // fits at all; the G * 6n (env, slot) pairs must fit the lanes' prefetch registers (<= 3 per lane)
         const char *fz = getenv("AT_FUSED_ROWS"), *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");
         env->split_rows = !(fz && fz[0] == '1') && k.rows > 0;
         env->pdl = !(np && np[0] == '1');
         const int RD = k.rows * k.obs_dim;
-        int lg = gg ? atoi(gg) : 3;
+        const char *ww = getenv("AT_ROWS_WARPS");
+        int W = ww ? atoi(ww) : 8;
+        if (W < 1) W = 1;
+        if (W > RK_MAX_WARPS) W = RK_MAX_WARPS;
+        env->rows_warps = W;
+        int lg = gg ? atoi(gg) : 1;
         if (lg < 0) lg = 0;
-        if (lg > 4) lg = 4;
-        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD).total > (size_t)72 * 1024 ||
-                          (1 << lg) * k.n_tanks * SLOTS_PER_TANK > 2 * RK_THREADS))
+        if (lg > 3) lg = 3;
+        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD, W).total > (size_t)prop.sharedMemPerBlockOptin ||
+                          (1 << lg) * k.n_tanks * SLOTS_PER_TANK > 96 || (1 << lg) * k.n_tanks > 32))
             --lg;
-        const bool pp1 = (1 << lg) * k.n_tanks * SLOTS_PER_TANK <= RK_THREADS;
-        if (k.map == AT_MAP_MAZE) env->rows_fn = rows_kernel<0, 0, -1, true, 2>;
-        else if (pp1 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) env->rows_fn = rows_kernel<4, 2, 1, false, 1>;
-        else if (pp1 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) env->rows_fn = rows_kernel<2, 2, 0, false, 1>;
-        else env->rows_fn = rows_kernel<0, 0, -1, false, 2>;
+        const int pairs = (1 << lg) * k.n_tanks * SLOTS_PER_TANK;
+        if (k.map == AT_MAP_MAZE) env->rows_fn = rows_kernel<0, 0, -1, true, 3>;
+        else if (pairs <= 64 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) env->rows_fn = rows_kernel<4, 2, 1, false, 2>;
+        else if (pairs <= 96 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) env->rows_fn = rows_kernel<4, 2, 1, false, 3>;
+        else if (pairs <= 64 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) env->rows_fn = rows_kernel<2, 2, 0, false, 2>;
+        else env->rows_fn = rows_kernel<0, 0, -1, false, 3>;
         env->rows_lgG = lg;
-        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD).total;
+        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD, W).total;
         env->rows_grid = prop.multiProcessorCount;
         if (env->split_rows) {
             if (env->rows_smem > (size_t)prop.sharedMemPerBlockOptin) {
@@ -872,7 +874,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
             }
             cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->rows_smem);
             int bps = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)env->rows_fn, RK_THREADS, env->rows_smem) != cudaSuccess || bps < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)env->rows_fn, W * 32, env->rows_smem) != cudaSuccess || bps < 1) {
                 cudaGetLastError();
                 bps = 1;
             }

@@ -38,6 +38,9 @@ def parse():
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--ref-envs", type=int, default=8192, help="envs per step of the CPU reference arm (bounded sample)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--burn-in", type=int, default=600,
+                   help="untimed ticks before the warm-up steps: episodes (mean ~190 ticks) desynchronise, so the timed "
+                        "steps see the steady-state mix of episode phases instead of 65536 freshly reset battles")
     return p.parse_args()
 
 
@@ -120,6 +123,23 @@ class ClockSampler:
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
                 "samples": len(s)}
+
+
+def kernel_split(E, D, step_ms, sim_ms, peak):
+    """Per-kernel view of the step.  SURVEY 8d's 7039 B/env-step = 2 S_state + 3 A + 4 R + 1 (simulation kernel: state
+    in and out, actions, rewards, done) + 4 R D (rows kernel: the observation rows)."""
+    sim_b = (ALG_BYTES_PER_ENV_STEP - 4 * N_AGENTS * D) * E
+    rows_b = 4 * N_AGENTS * D * E
+    rows_ms = max(step_ms - sim_ms, 1e-6)
+    return {
+        "env_kernel<true,false>": {"ms": sim_ms, "alg_bytes": sim_b, "achieved_gbs": sim_b / sim_ms / 1e6,
+                                   "frac": sim_b / sim_ms / 1e6 / peak, "share_of_step": sim_ms / step_ms,
+                                   "note": "timed alone (at_step without an observation buffer); latency-bound "
+                                           "fp64 / integer simulation, see DESIGN.md"},
+        "rows_kernel": {"ms": rows_ms, "alg_bytes": rows_b, "achieved_gbs": rows_b / rows_ms / 1e6,
+                        "frac": rows_b / rows_ms / 1e6 / peak, "share_of_step": rows_ms / step_ms,
+                        "note": "step minus simulation (the two overlap slightly: programmatic dependent launch)"},
+    }
 
 
 def cpu_arm(n_envs, steps, warmup, seed, threads):
@@ -214,13 +234,28 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for t in range(warmup):
+    for t in range(args.burn_in):              # state preparation (like generating the synthetic inputs): not a step
         core.step(acts[t % ring])
+    for t in range(warmup):
+        core.step(acts[(args.burn_in + t) % ring])
     l0 = core.launch_count()
     with ClockSampler(local) as clk:
-        ms = timed(lambda i: core.step(acts[(warmup + i) % ring]), steps)
+        ms = timed(lambda i: core.step(acts[(args.burn_in + warmup + i) % ring]), steps)
     launches = core.launch_count() - l0
     total_envs = E * world
+
+    # per-kernel split of the step: the simulation kernel alone (at_step without an observation buffer launches only
+    # env_kernel<true, false>); the rest of the step is rows_kernel
+    import ctypes as C
+    from alphatank_b200 import _capi
+    sim_steps = max(min(steps, 100), 10)
+
+    def sim_only(i):
+        a = acts[(warmup + i) % ring]
+        _capi.check(core.L.at_step(core.h, C.c_void_p(a.data_ptr()), None, C.c_void_p(core.rewards.data_ptr()),
+                                   C.c_void_p(core.done.data_ptr()),
+                                   C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "at_step")
+    ms_sim = timed(sim_only, sim_steps) / sim_steps
     value = total_envs * N_AGENTS * steps / (ms * 1e-3)
 
     # end to end through the reference-facing API with HOST action / reward / done buffers
@@ -245,15 +280,17 @@ def run_ours(args):
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": WORKLOAD, "envs_per_gpu": E, "total_envs": total_envs, "agents_per_env": N_AGENTS,
-                   "tanks_per_env": 4, "obs_dim": core.D, "parallelism": "env-id sharding x%d, no step-path collective"
+                   "burn_in_ticks": args.burn_in, "tanks_per_env": 4, "obs_dim": core.D, "parallelism": "env-id sharding x%d, no step-path collective"
                    % world, "timing": "per-step footprint (SoA state ~%d MB + %d MB of observations written) exceeds the "
                    "126 MB L2; no flush between steps needed" % (804 * E // 2**20, core.D * 4 * N_AGENTS * E // 2**20),
                    "env_steps_per_sec": value / N_AGENTS},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                     "kernel": "env_kernel<true>", "alg_bytes_per_launch": alg_bytes,
+                     "kernel": "one step = env_kernel<true,false> (simulation) + rows_kernel (observation rows)",
+                     "alg_bytes_per_launch": alg_bytes,
                      "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "peak_source": peak_src,
-                     "kernel_ms": kernel_s * 1e3},
+                     "kernel_ms": kernel_s * 1e3,
+                     "kernels": kernel_split(E, core.D, kernel_s * 1e3, ms_sim, peak)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N_AGENTS * 3 * 4,
                 "d2h_bytes_per_step": E * N_AGENTS * 4 + E, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 "note": "MultiAgentTeamEnv.step_host: pinned host actions in, rewards+done out, stream sync every step; "

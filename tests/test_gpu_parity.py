@@ -276,8 +276,9 @@ def test_set_weakness_hot_swap_equals_construction_and_oracle():
 
 
 @pytest.mark.parametrize("name,knobs", [
-    ("team_vs_bot", {}), ("team_vs_bot", {"AT_ROWS_LGG": "0"}), ("team_vs_bot", {"AT_ROWS_LGG": "4", "AT_NO_PDL": "1"}),
-    ("team_vs_bot", {"AT_ROWS_BPS": "1"}), ("agent_t96", {}), ("team_vs_bot_maze", {"AT_ROWS_LGG": "2"}),
+    ("team_vs_bot", {}), ("team_vs_bot", {"AT_ROWS_LGG": "0"}), ("team_vs_bot", {"AT_ROWS_LGG": "2", "AT_NO_PDL": "1"}),
+    ("team_vs_bot", {"AT_ROWS_BPS": "1", "AT_ROWS_WARPS": "7"}), ("agent_t96", {}), ("agent_t96", {"AT_ROWS_LGG": "3"}),
+    ("team_vs_bot_maze", {"AT_ROWS_LGG": "2"}),
     ("team_8_mixed", {}), ("team_three_teams_nodebuff", {}), ("botagent_smart_maze", {}), ("agent_nobuff_battlefield", {}),
 ])
 def test_split_rows_kernel_equals_fused_rows(name, knobs):
@@ -286,7 +287,7 @@ def test_split_rows_kernel_equals_fused_rows(name, knobs):
     (1003 envs: the last group is partial), through auto-resets, and after a masked reset."""
     spec = SWEEP[name]
     N, seed, base = 1003, 31, 900
-    old = {k: os.environ.get(k) for k in ("AT_FUSED_ROWS", "AT_ROWS_LGG", "AT_NO_PDL", "AT_ROWS_BPS")}
+    old = {k: os.environ.get(k) for k in ("AT_FUSED_ROWS", "AT_ROWS_LGG", "AT_NO_PDL", "AT_ROWS_BPS", "AT_ROWS_WARPS")}
     try:
         os.environ["AT_FUSED_ROWS"] = "1"
         a = _gpu(spec, N, seed, base, auto_reset=True)
