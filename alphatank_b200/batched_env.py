@@ -119,6 +119,18 @@ class BatchedTankEnv:
         _capi.check(self.L.at_step(self.h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(dn), self._stream()), "at_step")
         return obs, rew, dn
 
+    def step_norm(self, actions, obs_norm_out, obs_out=None, rewards_out=None, done_out=None, epsilon=1e-4):
+        """``step`` that returns the rows tick-normalised (the reference trainers' fresh-RunningMeanStd-per-tick quirk,
+        train_multi_ppo.py:89-91) into ``obs_norm_out`` - normalised while still in shared memory - and the raw rows
+        only when ``obs_out`` is given.  Bit-identical to step() + learner.tick_normalize()."""
+        a = self._device_actions(actions)
+        rew = self.rewards if rewards_out is None else rewards_out
+        dn = self.done if done_out is None else done_out
+        assert obs_norm_out.is_contiguous() and obs_norm_out.numel() == self.num_envs * self.R * self.D
+        _capi.check(self.L.at_step_norm(self.h, _ptr(a), _ptr(obs_out), _ptr(obs_norm_out), float(epsilon), _ptr(rew),
+                                        _ptr(dn), self._stream()), "at_step_norm")
+        return obs_norm_out, rew, dn
+
     def step_host(self, h_actions):
         """End-to-end variant: actions come from (pinned) HOST memory, rewards and done are returned in pinned
         host memory, observations stay in HBM.  Synchronises the current stream."""

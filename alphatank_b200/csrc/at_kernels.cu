@@ -350,6 +350,36 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     if (bulk_pending) bulk_wait_read_all();  // shared memory must outlive the copies' reads
 }
 
+// The trainers' per-tick observation normaliser on ONE column of an env's [rows][dim] block (train_multi_ppo.py:89-91
+// with models/ppo_utils.py:13-29: a FRESH RunningMeanStd(shape=(A, D), epsilon) is updated with the block and applied
+// to it):  bm = mean_a x, bv = mean_a (x - bm)^2, total = eps + A,
+//   mean = bm A / total,  var = 1 + (bv A + bm^2 eps A / total) / total,  y = (x - mean) / (sqrt(var) + 1e-8).
+// Shared by tick_normalize_kernel and the normalised-rows mode of rows_kernel (same float operations, same order).
+// Float arithmetic: bm and mean with IEEE divisions in the reference's order (x - mean cancels to ~1e-4 x on
+// static columns, so mean must be as accurate as torch's); the variance path folds bv A = ss and uses a reciprocal
+// and rsqrt (var >= 1, and the 1e-8 is absorbed: sqrt(var) + 1e-8 == sqrt(var) in fp32) - a 2e-7 relative change of y.
+struct TickNormK {   // per-launch constants
+    float fa, total, k_var, inv_total;
+    __device__ __forceinline__ TickNormK(int rows, float eps) {
+        fa = (float)rows; total = eps + fa; k_var = eps * fa / total; inv_total = 1.0f / total;
+    }
+};
+template <int RMAX>
+__device__ __forceinline__ void tick_norm_column(const float (&v)[RMAX], int rows, const TickNormK &k, float &mean, float &inv) {
+    float sum = 0.f;
+#pragma unroll
+    for (int a = 0; a < RMAX; ++a)
+        if (a < rows) sum += v[a];
+    const float bm = sum / k.fa;
+    float ss = 0.f;
+#pragma unroll
+    for (int a = 0; a < RMAX; ++a)
+        if (a < rows) { const float d = v[a] - bm; ss += d * d; }
+    mean = bm * k.fa / k.total;
+    const float var = 1.0f + (ss + bm * bm * k.k_var) * k.inv_total;
+    inv = rsqrtf(var);
+}
+
 // ------------------------------------------------------------------------------------------------ rows_kernel
 // Observation rows from the stored state (split path, the default).  Every WARP works on its own: it loops over
 // groups of G consecutive envs (4 for the 2v2 layout), whose R x D rows are ONE contiguous run of the observation
@@ -364,13 +394,14 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
 // the simulation's tail; griddepcontrol.wait orders everything else behind the simulation's stores.
 constexpr int RK_MAX_WARPS = 16;   // warps per block: a launch parameter (blockDim.x / 32)
 struct RowsSmem {   // per warp, after the block's trig table
-    size_t off_img, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, per_warp, total;
+    size_t off_img, off_nimg, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, per_warp, total;
 };
-__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats, int warps) {
+__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats, int warps, bool norm) {
     RowsSmem L;
     size_t o = 0;
     const size_t S = (size_t)n * SLOTS_PER_TANK;
     L.off_img = o; o += ((size_t)G * row_floats * 4 + 127) & ~(size_t)127;
+    L.off_nimg = o; o += norm ? (((size_t)G * row_floats * 4 + 127) & ~(size_t)127) : 0;   // the normalised copy of the image
     L.off_rx = o; o += (size_t)G * S * 8;
     L.off_ry = o; o += (size_t)G * S * 8;
     L.off_rm = o; o += (size_t)G * S * 8;
@@ -392,15 +423,20 @@ __host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_float
 template <int NT, int NR, int TEAM, bool MAZE, int PP>
 __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                           const uint8_t *__restrict__ mask, float *__restrict__ obs,
-                                                          const float *__restrict__ g_tmpl, int lgG, int n_groups) {
+                                                          const float *__restrict__ g_tmpl, int lgG, int n_groups,
+                                                          float *__restrict__ obs_norm, float norm_eps) {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef RowsShape<NT, NR, TEAM> SH;
+    // obs_norm: also emit (norm2: a second, normalised image) or only emit (inplace: obs == nullptr; the image is built
+    // in full every group and normalised in place) the tick-normalised rows
+    const bool norm = obs_norm != nullptr, norm2 = norm && obs != nullptr, inplace = norm && obs == nullptr;
+    const TickNormK nk(SH::rows(c), norm_eps);
     const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, nrows = SH::rows(c), RD = nrows * c.obs_dim;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const RowsSmem L = rows_smem_layout(G, n, RD, nwarps);
+    const RowsSmem L = rows_smem_layout(G, n, RD, nwarps, norm2);
     double *trig = (double *)smem;
     unsigned char *ws = smem + 722 * 8 + 64 + (size_t)warp * L.per_warp;
-    float *img = (float *)(ws + L.off_img);
+    float *img = (float *)(ws + L.off_img), *nimg = norm2 ? (float *)(ws + L.off_nimg) : img;
     double *rx = (double *)(ws + L.off_rx), *ry = (double *)(ws + L.off_ry);
     uint64_t *rm = (uint64_t *)(ws + L.off_rm);
     double *tx = (double *)(ws + L.off_tx), *ty = (double *)(ws + L.off_ty);
@@ -416,14 +452,28 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     for (int i = lane; i < G * RD / 4; i += 32) reinterpret_cast<float4 *>(img)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = ((G * RD) & ~3) + lane; i < G * RD; i += 32) img[i] = 0.f;
     __syncwarp();
+    constexpr int RMAX = NR ? NR : MAX_TANKS;
     if (!MAZE) {
         const int sl = 4 * c.n_walls + CELLS;
         for (int q = lane; q < sl; q += 32) {
             const float v = __ldg(g_tmpl + q);
-            for (int gr = 0; gr < G * nrows; ++gr) img[gr * c.obs_dim + c.off_walls + q] = v;   // gr = env * rows + row
+            float vn = 0.f;
+            if (norm) {   // a static column holds the same value in every row: its normalised value is static too
+                float vv[RMAX], mean, inv;
+#pragma unroll
+                for (int a = 0; a < RMAX; ++a) vv[a] = v;
+                tick_norm_column<RMAX>(vv, nrows, nk, mean, inv);
+                vn = (v - mean) * inv;
+            }
+            for (int gr = 0; gr < G * nrows; ++gr) {   // gr = env * rows + row
+                if (!inplace) img[gr * c.obs_dim + c.off_walls + q] = v;
+                if (norm) nimg[gr * c.obs_dim + c.off_walls + q] = vn;
+            }
         }
     }
-    const bool bulk_ok = (((size_t)RD * 4) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0);
+    // columns the normaliser visits per group: [0, off_walls) and [dyn2, D) (everything for per-env maps)
+    const int dyn2 = MAZE ? c.off_walls : c.off_zones, ndyn = c.off_walls + (c.obs_dim - dyn2);
+    const bool bulk_ok = (((size_t)RD * 4) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0) && ((((uintptr_t)obs_norm) & 15u) == 0);
     const uint64_t pol = make_evict_first_policy();
     __syncthreads();   // the trig table (the only block-wide barrier)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -512,8 +562,10 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
                 const int q = (o * SLOTS_PER_TANK + k) * G + g;
                 const uint64_t m = rm[q];
                 const bool has = m != ROWS_EMPTY;
-                if (!has && !occ[q]) continue;
-                occ[q] = has ? 1 : 0;
+                if (!inplace) {   // (an image that is normalised in place is rebuilt in full)
+                    if (!has && !occ[q]) continue;
+                    occ[q] = has ? 1 : 0;
+                }
                 rows_position_job<NT, NR, TEAM>(c, trig, o, k, m, rx[q], ry[q], tx + g, ty + g, G, img + g * RD, g + 4 * (o >> 1));
                 if (has) rm[q] = ROWS_EMPTY;   // the table is empty again for the next group
             } else if (j < jobs_pos + jobs_tank) {   // the rows' own blocks first, then the other-tank blocks
@@ -533,19 +585,51 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
                 rows_maze_job(c, wl[g], wh[g], (j - jobs_pos - jobs_tank) >> lgG, img + g * RD);
             }
         }
-        fence_async_smem();   // the image is read by the async proxy
+        if (norm) {   // the tick normaliser over the dynamic columns: raw image -> normalised image (or in place)
+            __syncwarp();
+            for (int g = 0; g < G; ++g)
+                for (int j0 = 0; j0 < ndyn; j0 += 32) {
+                    const int j = j0 + lane;
+                    const bool in = j < ndyn;
+                    const int col = j < c.off_walls ? j : j - c.off_walls + dyn2;
+                    const float *src = img + g * RD + col;
+                    float *dn = nimg + g * RD + col;
+                    float vv[RMAX];
+                    bool zero = true;
+#pragma unroll
+                    for (int a = 0; a < RMAX; ++a) {
+                        vv[a] = in && a < nrows ? src[a * c.obs_dim] : 0.f;
+                        zero = zero && vv[a] == 0.f;
+                    }
+                    if (__all_sync(0xffffffffu, zero)) {   // 32 all-zero columns (empty bullet positions) normalise to zero
+                        if (norm2 && in)
+                            for (int a = 0; a < nrows; ++a) dn[a * c.obs_dim] = 0.f;
+                        continue;
+                    }
+                    float mean, inv;
+                    tick_norm_column<RMAX>(vv, nrows, nk, mean, inv);
+                    if (in) {
+#pragma unroll
+                        for (int a = 0; a < RMAX; ++a)
+                            if (a < nrows) dn[a * c.obs_dim] = (vv[a] - mean) * inv;
+                    }
+                }
+        }
+        fence_async_smem();   // the images are read by the async proxy
         __syncwarp();
-        // ---- phase 3: ship the image
-        float *dst = obs + (int64_t)grp * G * RD;
+        // ---- phase 3: ship the image(s)
+        float *dst = obs + (int64_t)grp * G * RD, *dstn = obs_norm + (int64_t)grp * G * RD;
         if (all_emit && bulk_ok) {
             if (lane == 0) {
-                bulk_store(dst, img, (uint32_t)(G * RD * 4), pol);
+                if (obs) bulk_store(dst, img, (uint32_t)(G * RD * 4), pol);
+                if (norm) bulk_store(dstn, nimg, (uint32_t)(G * RD * 4), pol);   // (nimg == img when in place)
                 bulk_commit();
             }
         } else {   // masked reset / ragged tail / rows that are not 16-byte multiples: coalesced plain stores
             for (int g = 0; g < G; ++g) {
                 if (!em_s[g]) continue;
-                for (int q = lane; q < RD; q += 32) stg_stream(dst + g * RD + q, img[g * RD + q], pol);
+                if (obs) for (int q = lane; q < RD; q += 32) stg_stream(dst + g * RD + q, img[g * RD + q], pol);
+                if (norm) for (int q = lane; q < RD; q += 32) stg_stream(dstn + g * RD + q, nimg[g * RD + q], pol);
             }
             __syncwarp();   // the tables (em_s) are rewritten by the next group's phase 1
         }
@@ -564,7 +648,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     }
     if (lane == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
 }
-typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int);
+typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int, float *, float);
 
 __global__ void gather_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
                               PackedEnv *out) {
@@ -637,51 +721,125 @@ __global__ void maze_kernel(uint64_t seed, int64_t env_id_base, int64_t n, uint8
 //   mean = bm A / total,  var = 1 + (bv A + bm^2 eps A / total) / total,  y = (x - mean) / (sqrt(var) + 1e-8).
 // One pass: each thread owns 4 consecutive columns of one env and its A rows (16-byte loads / stores) - the torch
 // formulation costs ~10 elementwise / reduction passes over the 277 MB observation tensor per tick.
-template <int VEC>
-__global__ void tick_normalize_kernel(const float *__restrict__ x, float *__restrict__ y, int64_t n_envs, int rows,
-                                      int dim, float eps) {
+// ROWS > 0: compile-time row count (the env's rows stay in registers; a runtime-indexed array lives in local memory
+// and the kernel then runs at a quarter of the HBM rate); ROWS == 0: any row count up to AT_MAX_TANKS.
+template <int VEC, int ROWS>
+__global__ void __launch_bounds__(256) tick_normalize_kernel(const float *__restrict__ x, float *__restrict__ y,
+                                                             int64_t n_envs, int rows_rt, int dim, float eps) {
+    const int rows = ROWS ? ROWS : rows_rt;
+    constexpr int RMAX = ROWS ? ROWS : AT_MAX_TANKS;
+    constexpr int UN = ROWS ? (ROWS <= 2 ? 4 : 2) : 1;   // column chunks per thread: all their loads are issued first
     const int per_env = dim / VEC;
-    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_envs * per_env) return;
-    const int64_t e = k / per_env;
-    const int c0 = (int)(k - e * per_env) * VEC;
-    const float *src = x + (e * rows) * dim + c0;
-    float *dst = y + (e * rows) * dim + c0;
-    float v[AT_MAX_TANKS][VEC];
-    float sum[VEC];
+    const int64_t total_k = n_envs * per_env;
+    const int64_t k0 = (int64_t)blockIdx.x * (blockDim.x * UN) + threadIdx.x;
+    float v[UN][RMAX][VEC];
+    const float *src[UN];
+    bool ok[UN];
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) sum[q] = 0.f;
-    for (int a = 0; a < rows; ++a) {
-        if (VEC == 4) {
-            const float4 t = *reinterpret_cast<const float4 *>(src + (int64_t)a * dim);
-            v[a][0] = t.x; v[a][1 % VEC] = t.y; v[a][2 % VEC] = t.z; v[a][3 % VEC] = t.w;
-        } else {
-            v[a][0] = src[(int64_t)a * dim];
+    for (int u = 0; u < UN; ++u) {
+        const int64_t k = k0 + (int64_t)u * blockDim.x;
+        ok[u] = k < total_k;
+        const int64_t e = ok[u] ? k / per_env : 0;
+        const int c0 = ok[u] ? (int)(k - e * per_env) * VEC : 0;
+        src[u] = x + (e * rows) * dim + c0;
+#pragma unroll
+        for (int a = 0; a < RMAX; ++a) {
+#pragma unroll
+            for (int q = 0; q < VEC; ++q) v[u][a][q] = 0.f;
+            if (ok[u] && a < rows) {
+                if (VEC == 4) {
+                    const float4 t = *reinterpret_cast<const float4 *>(src[u] + (int64_t)a * dim);
+                    v[u][a][0] = t.x; v[u][a][1 % VEC] = t.y; v[u][a][2 % VEC] = t.z; v[u][a][3 % VEC] = t.w;
+                } else {
+                    v[u][a][0] = src[u][(int64_t)a * dim];
+                }
+            }
+        }
+    }
+    const TickNormK nk(rows, eps);
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+        if (!ok[u]) continue;
+        float *dst = y + (src[u] - x);
+        float mean[VEC], inv[VEC];
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) {
+            float col[RMAX];
+#pragma unroll
+            for (int a = 0; a < RMAX; ++a) col[a] = v[u][a][q];
+            tick_norm_column<RMAX>(col, rows, nk, mean[q], inv[q]);
         }
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) sum[q] += v[a][q];
-    }
-    const float fa = (float)rows, total = eps + fa;
-    float mean[VEC], inv[VEC];
-#pragma unroll
-    for (int q = 0; q < VEC; ++q) {
-        const float bm = sum[q] / fa;
-        float ss = 0.f;
-        for (int a = 0; a < rows; ++a) { const float d = v[a][q] - bm; ss += d * d; }
-        const float bv = ss / fa;
-        mean[q] = bm * fa / total;
-        const float var = 1.0f + (bv * fa + bm * bm * eps * fa / total) / total;
-        inv[q] = 1.0f / (sqrtf(var) + 1e-8f);
-    }
-    for (int a = 0; a < rows; ++a) {
-        if (VEC == 4) {
-            float4 t;
-            t.x = (v[a][0] - mean[0]) * inv[0]; t.y = (v[a][1 % VEC] - mean[1 % VEC]) * inv[1 % VEC];
-            t.z = (v[a][2 % VEC] - mean[2 % VEC]) * inv[2 % VEC]; t.w = (v[a][3 % VEC] - mean[3 % VEC]) * inv[3 % VEC];
-            *reinterpret_cast<float4 *>(dst + (int64_t)a * dim) = t;
-        } else {
-            dst[(int64_t)a * dim] = (v[a][0] - mean[0]) * inv[0];
+        for (int a = 0; a < RMAX; ++a) {
+            if (a < rows) {
+                if (VEC == 4) {
+                    float4 t;
+                    t.x = (v[u][a][0] - mean[0]) * inv[0]; t.y = (v[u][a][1 % VEC] - mean[1 % VEC]) * inv[1 % VEC];
+                    t.z = (v[u][a][2 % VEC] - mean[2 % VEC]) * inv[2 % VEC]; t.w = (v[u][a][3 % VEC] - mean[3 % VEC]) * inv[3 % VEC];
+                    *reinterpret_cast<float4 *>(dst + (int64_t)a * dim) = t;
+                } else {
+                    dst[(int64_t)a * dim] = (v[u][a][0] - mean[0]) * inv[0];
+                }
+            }
         }
+    }
+}
+
+// Categorical sampling of the policies' action heads (models/ppo_utils.py:53-61: Categorical(logits=..).sample()
+// per head + log_prob) as ONE pass: log-softmax, Gumbel-max draw and the chosen log-probability of up to 4 heads per
+// row.  The torch formulation is ~15 small kernels per policy and tick.  Uniforms come from Philox4x32-10 keyed by
+// `seed`, counter = (row, draw block, *d_counter, stream) - the caller bumps *d_counter once per tick on the device,
+// so a CUDA-graph replay draws fresh numbers.
+struct SampleHeads {
+    const float *logits[4];
+    int dims[4];
+    int n_heads;
+};
+__global__ void __launch_bounds__(256) sample_heads_kernel(const SampleHeads h, int64_t n_rows, uint64_t seed,
+                                                           const int64_t *__restrict__ d_counter, uint32_t stream_id,
+                                                           int32_t *__restrict__ actions, int64_t act_stride,
+                                                           float *__restrict__ logprobs, int64_t lp_stride) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t ctr = d_counter ? (uint64_t)*d_counter : 0ull;
+    uint32_t u[8];
+    for (int b = 0; b < 2; ++b) {
+        uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)b << 31), c2 = (uint32_t)ctr,
+                 c3 = (uint32_t)(ctr >> 32) ^ (stream_id * 0x9E3779B9u);
+        philox4x32_10(c0, c1, c2, c3, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32));
+        u[4 * b] = c0; u[4 * b + 1] = c1; u[4 * b + 2] = c2; u[4 * b + 3] = c3;
+    }
+    int draw = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (k >= h.n_heads) break;
+        const int d = h.dims[k];
+        const float *l = h.logits[k] + row * d;
+        float v[4];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            v[j] = j < d ? l[j] : -INFINITY;
+            mx = fmaxf(mx, v[j]);
+        }
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) se += j < d ? expf(v[j] - mx) : 0.f;
+        const float lse = mx + logf(se);
+        int best = 0;
+        float best_s = -INFINITY, best_lp = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < d) {
+                const float lp = v[j] - lse;
+                const float un = ((float)u[(draw + j) & 7] + 0.5f) * 2.3283064365386963e-10f;   // (0, 1]
+                const float g = -logf(fmaxf(-logf(fminf(un, 0.99999994f)), 1e-20f));           // Gumbel(0, 1)
+                if (lp + g > best_s) { best_s = lp + g; best = j; best_lp = lp; }
+            }
+        }
+        draw += d;
+        actions[row * act_stride + k] = best;
+        logprobs[row * lp_stride + k] = best_lp;
     }
 }
 
@@ -719,15 +877,18 @@ struct at_env {
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
     int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
     rows_kernel_fn rows_fn;   // the instantiation for this config's shape
-    size_t rows_smem;
+    size_t rows_smem, rows_smem_norm;   // (norm: with the second, normalised image)
+    int rows_grid_norm;
     int64_t launches;
     std::vector<std::pair<const void *, void *>> mapped;  // host buffers seen by at_step_host -> device alias (null: not mapped)
 };
 
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
-                             float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s) {
+                             float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
+                             float norm_eps = 0.f) {
     const int grid = (int)((env->n_envs + BS - 1) / BS);
-    const bool rows = d_obs != nullptr && env->k.rows > 0;
+    const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
+    if (d_obs_norm && !env->split_rows) return fail(AT_ERR_ARG, "normalised rows are built by rows_kernel: unset AT_FUSED_ROWS");
     if (!env->split_rows) {
         if (is_step)
             env_kernel<true, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
@@ -753,16 +914,18 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     const int want = (n_groups + env->rows_warps - 1) / env->rows_warps;
-    cfg.gridDim = dim3((unsigned)(want < env->rows_grid ? want : env->rows_grid));
+    const int rgrid = (d_obs_norm && d_obs) ? env->rows_grid_norm : env->rows_grid;
+    cfg.gridDim = dim3((unsigned)(want < rgrid ? want : rgrid));
     cfg.blockDim = dim3(env->rows_warps * 32);
-    cfg.dynamicSmemBytes = env->rows_smem;
+    cfg.dynamicSmemBytes = (d_obs_norm && d_obs) ? env->rows_smem_norm : env->rows_smem;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = env->pdl ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups));
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups,
+                                (float *)d_obs_norm, norm_eps));
     env->launches += 1;
     return AT_OK;
 }
@@ -854,7 +1017,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         int lg = gg ? atoi(gg) : 1;
         if (lg < 0) lg = 0;
         if (lg > 3) lg = 3;
-        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD, W).total > (size_t)prop.sharedMemPerBlockOptin ||
+        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD, W, true).total > (size_t)prop.sharedMemPerBlockOptin ||
                           (1 << lg) * k.n_tanks * SLOTS_PER_TANK > 96 || (1 << lg) * k.n_tanks > 32))
             --lg;
         const int pairs = (1 << lg) * k.n_tanks * SLOTS_PER_TANK;
@@ -864,15 +1027,17 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         else if (pairs <= 64 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) env->rows_fn = rows_kernel<2, 2, 0, false, 2>;
         else env->rows_fn = rows_kernel<0, 0, -1, false, 3>;
         env->rows_lgG = lg;
-        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD, W).total;
+        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD, W, false).total;
+        env->rows_smem_norm = rows_smem_layout(1 << lg, k.n_tanks, RD, W, true).total;
+        env->rows_grid_norm = prop.multiProcessorCount;
         env->rows_grid = prop.multiProcessorCount;
         if (env->split_rows) {
-            if (env->rows_smem > (size_t)prop.sharedMemPerBlockOptin) {
+            if (env->rows_smem_norm > (size_t)prop.sharedMemPerBlockOptin) {
                 cudaFree(env->arena);
                 delete env;
                 return fail(AT_ERR_ARG, "at_create: an observation image does not fit shared memory");
             }
-            cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->rows_smem);
+            cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->rows_smem_norm);
             int bps = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)env->rows_fn, W * 32, env->rows_smem) != cudaSuccess || bps < 1) {
                 cudaGetLastError();
@@ -881,6 +1046,12 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
             const char *bp = getenv("AT_ROWS_BPS");
             if (bp && atoi(bp) > 0 && atoi(bp) < bps) bps = atoi(bp);
             env->rows_grid = prop.multiProcessorCount * bps;
+            int bpn = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpn, (const void *)env->rows_fn, W * 32, env->rows_smem_norm) != cudaSuccess || bpn < 1) {
+                cudaGetLastError();
+                bpn = 1;
+            }
+            env->rows_grid_norm = prop.multiProcessorCount * bpn;
         }
     }
     // GamingENV.__init__ -> self.reset() (gaming_env.py:43): the constructor's own reset consumes draws
@@ -922,6 +1093,16 @@ int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_reward
     if ((env->k.rows > 0 && !d_rewards) || !d_done) return fail(AT_ERR_ARG, "at_step: rewards / done must not be null");
     CUDA_TRY(cudaSetDevice(env->device));
     return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream);
+}
+
+int at_step_norm(at_env *env, const int32_t *d_actions, float *d_obs, float *d_obs_norm, float epsilon, float *d_rewards,
+                 uint8_t *d_done, void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_step_norm: null handle");
+    if (env->k.act_rows > 0 && !d_actions) return fail(AT_ERR_ARG, "at_step_norm: this mode needs an actions array");
+    if ((env->k.rows > 0 && !d_rewards) || !d_done) return fail(AT_ERR_ARG, "at_step_norm: rewards / done must not be null");
+    if (!d_obs_norm) return fail(AT_ERR_ARG, "at_step_norm: the normalised observation buffer must not be null");
+    CUDA_TRY(cudaSetDevice(env->device));
+    return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream, d_obs_norm, epsilon);
 }
 
 // device-visible alias of a host buffer (pinned + mapped memory under unified addressing), or nullptr
@@ -1071,9 +1252,38 @@ int at_tick_normalize(int device, const float *d_obs, int64_t n_envs, int rows, 
     CUDA_TRY(cudaSetDevice(device));
     const bool vec = dim % 4 == 0 && ((((uintptr_t)d_obs) | ((uintptr_t)d_out)) & 15u) == 0;
     const int64_t threads = n_envs * (vec ? dim / 4 : dim);
-    const int grid = (int)((threads + 255) / 256);
-    if (vec) tick_normalize_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
-    else tick_normalize_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    const int un = !vec || rows > 4 ? 1 : (rows <= 2 ? 4 : 2);   // tick_normalize_kernel: UN chunks per thread
+    const int grid = (int)((threads + 256 * un - 1) / (256 * un));
+    cudaStream_t s = (cudaStream_t)stream;
+    if (vec && rows == 2) tick_normalize_kernel<4, 2><<<grid, 256, 0, s>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    else if (vec && rows == 1) tick_normalize_kernel<4, 1><<<grid, 256, 0, s>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    else if (vec && rows == 3) tick_normalize_kernel<4, 3><<<grid, 256, 0, s>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    else if (vec && rows == 4) tick_normalize_kernel<4, 4><<<grid, 256, 0, s>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    else if (vec) tick_normalize_kernel<4, 0><<<grid, 256, 0, s>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    else tick_normalize_kernel<1, 0><<<grid, 256, 0, s>>>(d_obs, d_out, n_envs, rows, dim, epsilon);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_sample_heads(int device, const float *const *d_logits, const int *dims, int n_heads, int64_t n_rows, uint64_t seed,
+                    const int64_t *d_counter, uint32_t stream_id, int32_t *d_actions, int64_t act_stride,
+                    float *d_logprobs, int64_t lp_stride, void *stream) {
+    if (!d_logits || !dims || n_heads < 1 || n_heads > 4 || n_rows <= 0 || !d_actions || !d_logprobs)
+        return fail(AT_ERR_ARG, "at_sample_heads: bad argument");
+    SampleHeads h;
+    memset(&h, 0, sizeof h);
+    h.n_heads = n_heads;
+    int total = 0;
+    for (int k = 0; k < n_heads; ++k) {
+        if (!d_logits[k] || dims[k] < 1 || dims[k] > 4) return fail(AT_ERR_ARG, "at_sample_heads: a head needs 1..4 logits");
+        h.logits[k] = d_logits[k];
+        h.dims[k] = dims[k];
+        total += dims[k];
+    }
+    if (total > 8) return fail(AT_ERR_ARG, "at_sample_heads: more than 8 logits per row");
+    CUDA_TRY(cudaSetDevice(device));
+    sample_heads_kernel<<<(int)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, n_rows, seed, d_counter, stream_id,
+                                                                                   d_actions, act_stride, d_logprobs, lp_stride);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
 }

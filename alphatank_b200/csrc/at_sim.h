@@ -833,9 +833,12 @@ struct Sim {
                 L.enemies |= 1u << i;
                 const int exi = los_ex(L, i), eyi = los_ey(L, i);
                 L.bx0 = imin(L.bx0, exi); L.bx1 = imax(L.bx1, exi); L.by0 = imin(L.by0, eyi); L.by1 = imax(L.by1, eyi);
-                // a hit needs the 5x5 rect within <= 301 advancing sub-steps of the muzzle: exact cull
+                // Exact cull.  Every tested position lies within 301 unit sub-steps (a polyline, so <= 301 px) of the
+                // muzzle, and its 5x5 rect can only overlap the enemy's Rect(x-15, y-12, 30, 24) when it is less than
+                // 20 px / 17 px from the enemy's centre: the muzzle must be within 301 px of that box (1 px of slack).
                 const double gx = fabs(bm.tx[i * BS + q] - L.x), gy = fabs(bm.ty[i * BS + q] - L.y);
-                reachable = reachable || (gx < 340.0 && gy < 340.0);
+                const double ux = fmax(gx - 21.0, 0.0), uy = fmax(gy - 18.0, 0.0);
+                reachable = reachable || (ux * ux + uy * uy < 303.0 * 303.0);
             }
         L.result = reachable ? -1 : 0;
         // |dx|, |dy| never change (reflections only negate).  cos/sin of an integer angle are either

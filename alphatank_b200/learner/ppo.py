@@ -43,11 +43,14 @@ class PPOConfig:                       # defaults: train_multi_ppo.py:25-38
 class RolloutBuffer:
     """[T(+1), N, A, ...] storage on the env's device; the env kernel writes obs / rewards / done into it directly."""
 
-    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device):
+    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device, keep_raw=True):
         T, N, A, D = num_steps, num_envs, num_agents, obs_dim
         self.T, self.N, self.A, self.D = T, N, A, D
-        self.raw_obs = torch.zeros((T + 1, N, A * D), dtype=torch.float32, device=device)   # env output, un-normalised
-        self.obs = torch.zeros((T, N, A, D), dtype=torch.float32, device=device)            # what the policy saw
+        # env output, un-normalised.  keep_raw=False: only slot 0 exists (the reset observation) - with the "tick"
+        # normaliser on a GPU the env step hands over normalised rows and the raw ones are never written
+        self.keep_raw = keep_raw
+        self.raw_obs = torch.zeros(((T + 1) if keep_raw else 1, N, A * D), dtype=torch.float32, device=device)
+        self.obs = torch.zeros((T + 1, N, A, D), dtype=torch.float32, device=device)        # what the policy saw (+ the bootstrap obs)
         self.actions = torch.zeros((T, N, A, 3), dtype=torch.int32, device=device)
         self.logprobs = torch.zeros((T, N, A, 3), dtype=torch.float32, device=device)
         self.env_rewards = torch.zeros((T, N, A), dtype=torch.float32, device=device)       # cumulative, as returned
@@ -74,6 +77,10 @@ def _world():
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 
 
+def _rank():
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
 def allreduce_mean_(flat):
     """In-place mean over ranks of a flat tensor (the PPO gradient all-reduce; no-op for a single process)."""
     w = _world()
@@ -89,7 +96,7 @@ class PPOLearner:
     def __init__(self, num_agents, obs_dim, act_dim=(3, 3, 2), cfg=None, device="cpu", seed=0):
         self.cfg = cfg or PPOConfig()
         self.device = torch.device(device)
-        self.A, self.D = num_agents, obs_dim
+        self.A, self.D, self.seed = num_agents, obs_dim, int(seed)
         g = torch.Generator().manual_seed(seed)       # identical initial replicas on every rank
         state = torch.random.get_rng_state()
         torch.random.set_rng_state(g.get_state())
@@ -121,6 +128,16 @@ class PPOLearner:
     @torch.no_grad()
     def act(self, obs_nad):
         """obs [N, A, D] -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]."""
+        if obs_nad.is_cuda:   # one sampling kernel per policy, written in place (at_sample_heads)
+            n, heads = obs_nad.shape[0], len(self.agents[0].actor)
+            acts = torch.empty((n, self.A, heads), dtype=torch.int32, device=obs_nad.device)
+            lps = torch.empty((n, self.A, heads), dtype=torch.float32, device=obs_nad.device)
+            if getattr(self, "_sample_ctr", None) is None:
+                self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
+            self._sample_ctr.add_(1)
+            vals = [agent.sample_cuda(obs_nad[:, i], acts[:, i], lps[:, i], self._sample_ctr, self.seed, i + self.A * _rank()).squeeze(-1)
+                    for i, agent in enumerate(self.agents)]
+            return acts, lps, torch.stack(vals, dim=1)
         acts, lps, vals = [], [], []
         for i, agent in enumerate(self.agents):
             a, lp, v = agent.sample(obs_nad[:, i])
@@ -152,7 +169,7 @@ class PPOLearner:
         mb = max(B // max(c.num_minibatches, 1), 1)
         stats = []
         for i, (agent, opt) in enumerate(zip(self.agents, self.optimizers)):
-            b_obs = buf.obs[:, :, i].reshape(B, self.D)
+            b_obs = buf.obs[:T, :, i].reshape(B, self.D)
             b_act = buf.actions[:, :, i].reshape(B, 3)
             b_lp = buf.logprobs[:, :, i].reshape(B, 3)
             b_adv = adv[:, :, i].reshape(B, 1)
@@ -192,22 +209,36 @@ def collect_rollout(env, learner, buf, first=False):
     policies.  Everything stays on the device; the env kernel writes into the buffer.  ``first``: start from reset()."""
     core = env.core
     T = buf.T
+    # GPU + "tick" normaliser: the env step returns the normalised rows itself (at_step_norm: normalised in shared
+    # memory by rows_kernel), so the 277 MB of raw rows per tick are neither written nor read back
+    fused = learner.cfg.obs_norm == "tick" and buf.obs.is_cuda
+    assert fused or buf.keep_raw, "keep_raw=False needs the fused normalised step (cuda + obs_norm='tick')"
     if first:
         core.reset(obs_out=buf.raw_obs[0])
+        learner.normalize(buf.raw_obs[0], out=buf.obs[0])
         buf.dones[0].zero_()
     else:                                     # continue: the previous rollout's last observation / done flag
-        buf.raw_obs[0].copy_(buf.raw_obs[T])
+        if buf.keep_raw:
+            buf.raw_obs[0].copy_(buf.raw_obs[T])
+        if fused:
+            buf.obs[0].copy_(buf.obs[T])
+        else:
+            learner.normalize(buf.raw_obs[0], out=buf.obs[0])
         buf.dones[0].copy_(buf.dones[T])
     prev_cum = getattr(buf, "_prev_cum", None)
     if prev_cum is None or first:
-        prev_cum = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.raw_obs.device)
+        prev_cum = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.obs.device)
     for t in range(T):
-        x = learner.normalize(buf.raw_obs[t], out=buf.obs[t])     # straight into the rollout storage
-        a, lp, v = learner.act(x)
+        a, lp, v = learner.act(buf.obs[t])
         buf.actions[t].copy_(a)
         buf.logprobs[t].copy_(lp)
         buf.values[t].copy_(v)
-        core.step(buf.actions[t], obs_out=buf.raw_obs[t + 1], rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
+        if fused:
+            core.step_norm(buf.actions[t], buf.obs[t + 1], obs_out=buf.raw_obs[t + 1] if buf.keep_raw else None,
+                           rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
+        else:
+            core.step(buf.actions[t], obs_out=buf.raw_obs[t + 1], rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
+            learner.normalize(buf.raw_obs[t + 1], update=t + 1 < T, out=buf.obs[t + 1])   # straight into the rollout storage
         if learner.cfg.reward_mode == "delta":
             buf.rewards[t].copy_(buf.env_rewards[t] - prev_cum)
             prev_cum = buf.env_rewards[t] * (1.0 - buf.dones[t + 1].to(torch.float32)).unsqueeze(-1)  # reset -> 0
@@ -215,7 +246,7 @@ def collect_rollout(env, learner, buf, first=False):
             buf.rewards[t].copy_(buf.env_rewards[t])
     buf._prev_cum = prev_cum
     buf._prev_live = prev_cum
-    buf.values[T].copy_(learner.values(learner.normalize(buf.raw_obs[T], update=False)))
+    buf.values[T].copy_(learner.values(buf.obs[T]))
     return buf
 
 
@@ -227,9 +258,9 @@ class RolloutRunner:
 
     def __init__(self, env, learner, buf, use_graph=True):
         self.env, self.learner, self.buf = env, learner, buf
-        self.use_graph = use_graph and learner.cfg.obs_norm in ("tick", "none") and buf.raw_obs.is_cuda
+        self.use_graph = use_graph and learner.cfg.obs_norm in ("tick", "none") and buf.obs.is_cuda
         self.graph = None
-        self._prev = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.raw_obs.device)
+        self._prev = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.obs.device)
 
     def run(self, first=False):
         buf = self.buf

@@ -87,15 +87,16 @@ class PPOAgentPPO(nn.Module):
     def fused_logits_and_value(self, x):
         """Inference-only forward of all four MLPs as three batched GEMMs: the first layers share the input, so their
         weights are concatenated into one [4*128, D] matrix (one pass over the [N, D] observations instead of four);
-        layers two and three are batched over the four networks.  Same arithmetic per network as the module path."""
+        layers two and three run per network on column slices of that result (no transposed copy).  Same arithmetic per
+        network as the module path."""
         nets = [self.critic] + list(self.actor)
         w1 = torch.cat([n[0].weight for n in nets], dim=0)                      # [512, D]
         b1 = torch.cat([n[0].bias for n in nets], dim=0)
-        h = torch.tanh(torch.addmm(b1, x, w1.t())).view(x.shape[0], len(nets), 128).transpose(0, 1)   # [4, N, 128]
-        w2 = torch.stack([n[2].weight.t() for n in nets])                       # [4, 128, 128]
-        b2 = torch.stack([n[2].bias for n in nets]).unsqueeze(1)
-        h = torch.tanh(torch.baddbmm(b2, h, w2))
-        outs = [torch.addmm(n[4].bias, h[k], n[4].weight.t()) for k, n in enumerate(nets)]
+        h1 = torch.addmm(b1, x, w1.t()).tanh_()                                 # [N, 512]: the four first layers side by side
+        outs = []
+        for k, n in enumerate(nets):    # layers two and three read their 128-column slice in place (row stride 512)
+            h2 = torch.addmm(n[2].bias, h1[:, 128 * k:128 * (k + 1)], n[2].weight.t()).tanh_()
+            outs.append(torch.addmm(n[4].bias, h2, n[4].weight.t()))
         return outs[1:], outs[0]
 
     @torch.no_grad()
@@ -109,6 +110,29 @@ class PPOAgentPPO(nn.Module):
             acts.append(a)
             lps.append(lp.gather(-1, a.unsqueeze(-1)).squeeze(-1))
         return torch.stack(acts, dim=-1), torch.stack(lps, dim=-1), value
+
+    @torch.no_grad()
+    def sample_cuda(self, x, actions_out, logprobs_out, counter, seed=0, stream_id=0):
+        """CUDA path of ``sample``: the fused forward, then ONE kernel (csrc: sample_heads_kernel through at_sample_heads)
+        for log-softmax + Gumbel-max draw + chosen log-probability of all heads, written straight into
+        ``actions_out`` int32 [N, heads] / ``logprobs_out`` float32 [N, heads] (may be column slices of [N, A, heads]
+        tensors).  ``counter``: device int64 tensor [1] the caller advances once per tick.  Returns the value [N, 1]."""
+        import ctypes as C
+
+        from .. import _capi
+        logits, value = self.fused_logits_and_value(x)
+        logits = [l.contiguous() for l in logits]
+        nh = len(logits)
+        assert actions_out.dtype == torch.int32 and logprobs_out.dtype == torch.float32
+        assert actions_out.stride(-1) == 1 and logprobs_out.stride(-1) == 1
+        ptrs = (C.c_void_p * nh)(*[l.data_ptr() for l in logits])
+        dims = (C.c_int32 * nh)(*[int(l.shape[-1]) for l in logits])
+        _capi.check(_capi.lib().at_sample_heads(
+            x.device.index, C.cast(ptrs, C.c_void_p), C.cast(dims, C.c_void_p), nh, x.shape[0], int(seed),
+            C.c_void_p(counter.data_ptr()), int(stream_id), C.c_void_p(actions_out.data_ptr()), actions_out.stride(0),
+            C.c_void_p(logprobs_out.data_ptr()), logprobs_out.stride(0),
+            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "at_sample_heads")
+        return value
 
     def get_action_and_value(self, x, action=None):
         logits = [head(x) for head in self.actor]

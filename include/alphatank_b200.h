@@ -158,11 +158,27 @@ int at_bfs_batch(int device, const uint8_t *d_maze, const int32_t *d_query, int6
 int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *d_maze, uint32_t *d_ctr,
                       void *stream);
 
+/* at_step that also (d_obs != NULL) or only (d_obs == NULL) returns the observation rows as the reference's trainers
+ * feed them to the policies: tick-normalised (see at_tick_normalize) - the normaliser runs on the rows while they are
+ * still in shared memory, so the raw rows need not be written to, and read back from, HBM.  d_obs_norm has the layout
+ * of d_obs.  Bit-identical to at_step followed by at_tick_normalize. */
+int at_step_norm(at_env *env, const int32_t *d_actions, float *d_obs, float *d_obs_norm, float epsilon, float *d_rewards,
+                 uint8_t *d_done, void *stream);
+
 /* The trainers' per-tick observation normaliser (train_multi_ppo.py:89-91: a fresh RunningMeanStd((A, D)) from
  * models/ppo_utils.py:6-29 is updated with, and applied to, each env's own [rows][dim] block) in one pass over
  * d_obs float[n_envs][rows][dim] -> d_out (may alias d_obs).  epsilon = RunningMeanStd's 1e-4. */
 int at_tick_normalize(int device, const float *d_obs, int64_t n_envs, int rows, int dim, float epsilon, float *d_out,
                       void *stream);
+
+/* Categorical sampling of a policy's action heads (models/ppo_utils.py:53-61: Categorical(logits=...).sample() and
+ * log_prob per head) in one pass: d_logits[k] is float[n_rows][dims[k]] (n_heads <= 4, dims <= 4, sum <= 8).  Writes
+ * d_actions[row * act_stride + k] and d_logprobs[row * lp_stride + k] (strides in elements, so the outputs may be
+ * columns of a [n_rows][agents][heads] tensor).  Gumbel-max draw from Philox4x32-10 keyed by seed with counter
+ * (row, *d_counter, stream_id); d_counter is a device int64 the caller advances once per tick (nullable: 0). */
+int at_sample_heads(int device, const float *const *d_logits, const int *dims, int n_heads, int64_t n_rows, uint64_t seed,
+                    const int64_t *d_counter, uint32_t stream_id, int32_t *d_actions, int64_t act_stride,
+                    float *d_logprobs, int64_t lp_stride, void *stream);
 
 /* Host copies of the device lookup tables (tests): cos/sin of math.radians(a), a = 0..360 -> double[361][2];
  * pygame Vector2.rotate corner offsets -> double[361][4]. */

@@ -57,7 +57,7 @@ def main():
     cfg = PPOConfig(num_steps=a.num_steps, num_epochs=a.num_epochs, num_minibatches=a.num_minibatches,
                     reward_mode=a.reward_mode, obs_norm=a.obs_norm)
     learner = PPOLearner(A, D, tuple(int(x) for x in env.action_space.nvec[:3]), cfg, dev, seed=a.seed)
-    buf = RolloutBuffer(a.num_steps, a.num_envs, A, D, dev)
+    buf = RolloutBuffer(a.num_steps, a.num_envs, A, D, dev, keep_raw=a.obs_norm != "tick")
     runner = RolloutRunner(env, learner, buf, use_graph=not a.no_graph)
     for it in range(a.iterations):
         torch.cuda.synchronize(dev)

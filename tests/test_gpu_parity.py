@@ -312,3 +312,33 @@ def test_split_rows_kernel_equals_fused_rows(name, knobs):
     mask = (np.arange(N) % 5 == 0).astype(np.uint8)
     mask[-1] = 1
     assert np.array_equal(a.reset(mask), b.reset(mask))
+
+
+@pytest.mark.parametrize("name", ["team_vs_bot", "agent_t96", "team_vs_bot_maze", "team_8_mixed", "team_harder_battlefield"])
+def test_step_norm_equals_step_then_tick_normalize(name):
+    """at_step_norm (rows tick-normalised by rows_kernel while still in shared memory) against at_step followed by
+    at_tick_normalize: bit-identical, with and without the raw rows, on a ragged batch and through auto-resets."""
+    import torch
+    from alphatank_b200.learner.ppo_utils import tick_normalize_cuda
+    spec = SWEEP[name]
+    N, seed, base = 1003, 12, 40
+    a, b, c = (_gpu(spec, N, seed, base, auto_reset=True) for _ in range(3))
+    for e in (a, b, c):
+        e.reset()
+    ids = np.arange(base, base + N)
+    R, D = a.R, a.D
+    norm_b = torch.full((N, R * D), -7.0, device="cuda:0")
+    norm_c = torch.full((N, R * D), -7.0, device="cuda:0")
+    raw_b = torch.full((N, R * D), -7.0, device="cuda:0")
+    for t in range(100):
+        acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
+        ta = None if acts is None else torch.as_tensor(np.ascontiguousarray(acts, dtype=np.int32))
+        oa, ra, da = a.core.step(ta)
+        want = tick_normalize_cuda(oa.view(N, R, D)).view(N, R * D)
+        _, rb, db = b.core.step_norm(ta, norm_b, obs_out=raw_b)
+        _, rc, dc = c.core.step_norm(ta, norm_c)
+        assert torch.equal(raw_b, oa) and torch.equal(ra, rb) and torch.equal(da, db) and torch.equal(ra, rc)
+        for got in (norm_b, norm_c):
+            if not torch.equal(got, want):
+                bad = (got != want).nonzero()[:6].tolist()
+                raise AssertionError("%s tick %d normalised rows differ at (env, col) %s" % (name, t, bad))

@@ -121,7 +121,7 @@ def test_checkpoint_file_is_the_reference_layout(tmp_path):
 def _fake_rollout(T, N, A, D, seed):
     g = torch.Generator().manual_seed(seed)
     b = RolloutBuffer(T, N, A, D, "cpu")
-    b.obs.copy_(torch.randn(T, N, A, D, generator=g))
+    b.obs[:T].copy_(torch.randn(T, N, A, D, generator=g))
     b.actions.copy_(torch.stack([torch.randint(0, 3, (T, N, A), generator=g), torch.randint(0, 3, (T, N, A), generator=g),
                                  torch.randint(0, 2, (T, N, A), generator=g)], dim=-1).to(torch.int32))
     b.logprobs.copy_(-torch.rand(T, N, A, 3, generator=g) - 0.3)

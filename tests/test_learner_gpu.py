@@ -118,3 +118,42 @@ def test_tick_normalize_kernel_matches_reference_formula():
     x = torch.randn((512, 2, 528), device="cuda")
     want = tick_normalize(x.clone())
     assert tick_normalize(x, out=x) is x and torch.equal(x, want)          # in place
+
+
+def test_sample_heads_kernel_is_a_categorical_sampler():
+    """at_sample_heads (one kernel for log-softmax + Gumbel-max draw + chosen log-probability of all heads) against
+    torch: exact argmax bookkeeping (the returned log-probability is log_softmax(logits)[action], 1e-5), the empirical
+    distribution over 400k rows matches softmax (3 sigma of the binomial error), draws change with the counter and
+    repeat for the same counter."""
+    from alphatank_b200.learner import PPOAgentPPO
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    N = 400_000
+    agent = PPOAgentPPO(24).to(dev)
+    x = torch.randn(1, 24, device=dev).expand(N, 24).contiguous()          # the same observation in every row
+    acts = torch.full((N, 2, 3), -1, dtype=torch.int32, device=dev)
+    lps = torch.zeros((N, 2, 3), dtype=torch.float32, device=dev)
+    ctr = torch.ones(1, dtype=torch.int64, device=dev)
+    v = agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)
+    assert (acts[:, 0] == -1).all() and v.shape == (N, 1)                  # strided output: the other agent's columns untouched
+    logits, value = agent.fused_logits_and_value(x)
+    assert torch.allclose(v, value)
+    for h, l in enumerate(logits):
+        lp = torch.log_softmax(l, dim=-1)
+        a = acts[:, 1, h].long()
+        assert int(a.min()) >= 0 and int(a.max()) < l.shape[1]
+        assert torch.allclose(lps[:, 1, h], lp.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=1e-5)
+        p = torch.softmax(l[0], dim=-1).double().cpu()
+        freq = torch.bincount(a, minlength=l.shape[1]).double().cpu() / N
+        assert ((freq - p).abs() < 4 * (p * (1 - p) / N).sqrt() + 1e-4).all(), (freq, p)
+    again = torch.empty_like(acts)
+    agent.sample_cuda(x, again[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)
+    assert torch.equal(again[:, 1], acts[:, 1])
+    ctr.add_(1)
+    agent.sample_cuda(x, again[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)
+    assert (again[:, 1] != acts[:, 1]).float().mean() > 0.2
+    # heads are drawn independently: the joint frequency of (rot, move) factorises
+    a0, a1 = acts[:, 1, 0].long(), acts[:, 1, 1].long()
+    joint = torch.bincount(a0 * 3 + a1, minlength=9).double().cpu().view(3, 3) / N
+    outer = joint.sum(1, keepdim=True) * joint.sum(0, keepdim=True)
+    assert (joint - outer).abs().max() < 5e-3
