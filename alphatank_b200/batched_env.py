@@ -133,7 +133,9 @@ class BatchedTankEnv:
 
     def step_host(self, h_actions):
         """End-to-end variant: actions come from (pinned) HOST memory, rewards and done are returned in pinned
-        host memory, observations stay in HBM.  Synchronises the current stream."""
+        host memory, observations stay in HBM.  Returns as soon as rewards / done have landed in host memory (the simulation
+        kernel posts a completion word the call spins on); the observations are complete in stream order, i.e. for
+        anything enqueued on the current stream afterwards, without a stream synchronisation."""
         if self._h_rewards is None:
             self._h_rewards = torch.zeros((self.num_envs, self.R), dtype=torch.float32).pin_memory()
             self._h_done = torch.zeros((self.num_envs,), dtype=torch.uint8).pin_memory()

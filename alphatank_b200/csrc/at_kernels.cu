@@ -171,6 +171,14 @@ struct TileSink {  // kept in registers: flush takes everything by value
     }
 };
 
+// at_step_host: how the host learns that rewards / done have landed in its memory without synchronising the stream
+// (the rows kernel is still running then): the last block to finish posts `epoch` into a mapped host word.
+struct HostSignal {
+    unsigned int *counter;          // device: blocks that have finished (reset by the last one)
+    volatile uint32_t *host_flag;   // mapped host memory; nullptr: no signalling
+    uint32_t epoch;
+};
+
 // FUSED = true: simulation + observation rows in one launch (phase B below).  FUSED = false: simulation only; the rows
 // are built from the stored state by rows_kernel, launched behind this kernel as a programmatic dependent.
 template <bool IS_STEP, bool FUSED>
@@ -178,7 +186,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
                                                  const int32_t *__restrict__ actions,
                                                  const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                  float *__restrict__ rewards, uint8_t *__restrict__ done,
-                                                 const float *__restrict__ g_tmpl) {
+                                                 const float *__restrict__ g_tmpl, HostSignal sig) {
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(c.n_tanks, c.n_walls, c.n_bots, FUSED, c.act_rows);
     if (!FUSED) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // rows_kernel may take freed SM slots
@@ -323,6 +331,19 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
             s.load();
             s.env_reset();
             s.store();
+        }
+    }
+
+    if (sig.host_flag != nullptr) {   // (block-uniform)  rewards / done of this block are in host memory before it counts
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            const unsigned int prev = atomicAdd(sig.counter, 1u);
+            if (prev == gridDim.x - 1) {
+                *sig.counter = 0u;
+                __threadfence_system();
+                *sig.host_flag = sig.epoch;
+            }
         }
     }
 
@@ -880,32 +901,40 @@ struct at_env {
     size_t rows_smem, rows_smem_norm;   // (norm: with the second, normalised image)
     int rows_grid_norm;
     int64_t launches;
+    unsigned int *d_sig_counter;          // at_step_host: finished-block counter of the simulation kernel
+    volatile uint32_t *h_sig_flag;        // ... and the mapped host word its last block posts the epoch to
+    volatile uint32_t *h_sig_flag_dev;    // (device alias of h_sig_flag)
+    uint32_t sig_epoch;
+    cudaStream_t copy_stream;             // at_step_host: the actions' DMA runs beside the previous step's rows kernel
+    cudaEvent_t ev_actions;
     std::vector<std::pair<const void *, void *>> mapped;  // host buffers seen by at_step_host -> device alias (null: not mapped)
 };
 
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
-                             float norm_eps = 0.f) {
+                             float norm_eps = 0.f, bool signal_host = false) {
     const int grid = (int)((env->n_envs + BS - 1) / BS);
+    HostSignal sig = {nullptr, nullptr, 0u};
+    if (signal_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
     const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
     if (d_obs_norm && !env->split_rows) return fail(AT_ERR_ARG, "normalised rows are built by rows_kernel: unset AT_FUSED_ROWS");
     if (!env->split_rows) {
         if (is_step)
             env_kernel<true, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                                    d_done, env->d_tmpl);
+                                                                    d_done, env->d_tmpl, sig);
         else
             env_kernel<false, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                                     d_done, env->d_tmpl);
+                                                                     d_done, env->d_tmpl, sig);
         env->launches += 1;
         CUDA_TRY(cudaGetLastError());
         return AT_OK;
     }
     if (is_step)
         env_kernel<true, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                     d_done, env->d_tmpl);
+                                                                     d_done, env->d_tmpl, sig);
     else
         env_kernel<false, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                      d_done, env->d_tmpl);
+                                                                      d_done, env->d_tmpl, sig);
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     if (!rows) return AT_OK;
@@ -991,6 +1020,25 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->st.bfs_tab = (const uint16_t *)(b + L.o_bfs);
     }
 
+    env->d_sig_counter = nullptr; env->h_sig_flag = nullptr; env->h_sig_flag_dev = nullptr; env->sig_epoch = 0;
+    {
+        void *hp = nullptr, *dp = nullptr;
+        if (cudaMalloc(&dp, 64) == cudaSuccess) { cudaMemset(dp, 0, 64); env->d_sig_counter = (unsigned int *)dp; }
+        if (cudaHostAlloc(&hp, 64, cudaHostAllocMapped) == cudaSuccess) {
+            memset(hp, 0, 64);
+            void *alias = nullptr;
+            if (cudaHostGetDevicePointer(&alias, hp, 0) == cudaSuccess) {
+                env->h_sig_flag = (volatile uint32_t *)hp;
+                env->h_sig_flag_dev = (volatile uint32_t *)alias;
+            } else {
+                cudaFreeHost(hp);
+            }
+        }
+        env->copy_stream = nullptr; env->ev_actions = nullptr;
+        if (cudaStreamCreateWithFlags(&env->copy_stream, cudaStreamNonBlocking) != cudaSuccess) env->copy_stream = nullptr;
+        if (cudaEventCreateWithFlags(&env->ev_actions, cudaEventDisableTiming) != cudaSuccess) env->ev_actions = nullptr;
+        cudaGetLastError();
+    }
     env->d_tmpl = (const float *)(b + L.o_tmpl);
     if (k.map != AT_MAP_MAZE) {
         std::vector<float> tm((size_t)4 * k.n_walls + CELLS);
@@ -1069,7 +1117,12 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
 int at_destroy(at_env *env) {
     if (!env) return AT_OK;
     cudaSetDevice(env->device);
+    cudaDeviceSynchronize();
     cudaFree(env->arena);
+    if (env->d_sig_counter) cudaFree(env->d_sig_counter);
+    if (env->h_sig_flag) cudaFreeHost((void *)env->h_sig_flag);
+    if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
+    if (env->ev_actions) cudaEventDestroy(env->ev_actions);
     delete env;
     return AT_OK;
 }
@@ -1143,9 +1196,45 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
     static const bool allow_direct = !getenv("AT_STEP_HOST_COPY");  // diagnostic switch: force the copy path
     const bool direct = allow_direct && (env->k.act_rows == 0 || dev[0]) && (env->k.rows == 0 || dev[1]) && dev[2];
     if (direct) {
-        int rc = launch_env_kernel(env, true, (const int32_t *)dev[0], nullptr, d_obs, (float *)dev[1], (uint8_t *)dev[2], s);
+        // The call returns as soon as rewards / done are in host memory: the simulation kernel's last block posts the
+        // step's epoch into a mapped host word and the host spins on it - no driver synchronisation, and the rows
+        // kernel (whose output stays in HBM, valid in stream order) overlaps the host's work for the next step.
+        static const bool spin = !getenv("AT_STEP_HOST_SYNC");   // diagnostic switch: synchronise the stream instead
+        const bool sigok = spin && env->d_sig_counter && env->h_sig_flag_dev;
+        // Actions: a DMA copy on the handle's copy stream - the host calls in as soon as the previous step's simulation
+        // is done, so the copy runs beside that step's rows kernel and the simulation reads HBM (letting the kernel fetch
+        // the rows from mapped host memory itself costs it 65 us: 24-byte reads across PCIe are latency-bound).
+        // Rewards / done: posted writes from the kernel straight into the mapped host buffers.
+        static const bool dma = !getenv("AT_STEP_HOST_MAPPED_ACTIONS");   // diagnostic switch: the kernel fetches them
+        const int32_t *acts = (const int32_t *)dev[0];
+        if (dma && env->k.act_rows > 0 && env->copy_stream && env->ev_actions) {
+            CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)N * env->k.act_rows * 3 * 4,
+                                     cudaMemcpyHostToDevice, env->copy_stream));
+            CUDA_TRY(cudaEventRecord(env->ev_actions, env->copy_stream));
+            CUDA_TRY(cudaStreamWaitEvent(s, env->ev_actions, 0));
+            acts = env->d_actions_scratch;
+        }
+        int rc = launch_env_kernel(env, true, acts, nullptr, d_obs, (float *)dev[1], (uint8_t *)dev[2], s,
+                                   nullptr, 0.f, sigok);
         if (rc != AT_OK) return rc;
-        CUDA_TRY(cudaStreamSynchronize(s));
+        if (!sigok) {
+            CUDA_TRY(cudaStreamSynchronize(s));
+            return AT_OK;
+        }
+        const uint32_t want = env->sig_epoch;
+        for (uint64_t spins = 0; *env->h_sig_flag != want; ++spins) {
+            if ((spins & 0xFFFFu) == 0xFFFFu) {   // every ~65 k polls: has the stream died?
+                const cudaError_t q = cudaStreamQuery(s);
+                if (q != cudaSuccess && q != cudaErrorNotReady)
+                    return fail(AT_ERR_CUDA, std::string("at_step_host: ") + cudaGetErrorString(q));
+                if (q == cudaSuccess && *env->h_sig_flag != want)
+                    return fail(AT_ERR_CUDA, "at_step_host: the stream drained without the completion signal");
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        __sync_synchronize();
         return AT_OK;
     }
     if (env->k.act_rows > 0)

@@ -293,8 +293,9 @@ def run_ours(args):
                      "kernels": kernel_split(E, core.D, kernel_s * 1e3, ms_sim, peak)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N_AGENTS * 3 * 4,
                 "d2h_bytes_per_step": E * N_AGENTS * 4 + E, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "note": "MultiAgentTeamEnv.step_host: pinned host actions in, rewards+done out, stream sync every step; "
-                        "observations stay in HBM for the policy"},
+                "note": "MultiAgentTeamEnv.step_host: pinned host actions in (DMA copy beside the previous step's rows "
+                        "kernel), rewards+done posted into pinned host memory and read by the host every step (the "
+                        "call returns when they have landed); observations stay in HBM for the policy"},
         "gpu_launches": launches * world,
         "clocks": clk.summary(),
     }
