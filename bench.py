@@ -142,7 +142,7 @@ def kernel_split(E, D, step_ms, sim_ms, peak):
     }
 
 
-def cpu_arm(n_envs, steps, warmup, seed, threads):
+def cpu_arm(n_envs, steps, warmup, seed, threads, burn_in=0):
     """Times the oracle port (oracle/tank_oracle.c) on host threads: the reference's algorithm on the CPU."""
     import numpy as np
     from oracle import oracle as O
@@ -152,7 +152,9 @@ def cpu_arm(n_envs, steps, warmup, seed, threads):
     env = O.OracleEnv(cfg, n_envs, seed)
     env.reset()
     ids = np.arange(n_envs)
-    acts = [synthetic_actions(seed, ids, t, N_AGENTS) for t in range(warmup + steps)]
+    for t in range(burn_in):                   # same steady-state protocol as the GPU arm (untimed)
+        env.step(synthetic_actions(seed, ids, t, N_AGENTS), threads=threads)
+    acts = [synthetic_actions(seed, ids, burn_in + t, N_AGENTS) for t in range(warmup + steps)]
     for t in range(warmup):
         env.step(acts[t], threads=threads)
     t0 = time.perf_counter()
@@ -169,9 +171,9 @@ def run_reference(args):
     steps = args.steps if args.steps is not None else 20
     warmup = args.warmup if args.warmup is not None else 3
     threads = os.cpu_count() or 1
-    value, dt = cpu_arm(args.ref_envs, steps, warmup, args.seed, threads)
-    sample = "%d envs x %d ticks per run (oracle C port of the reference env step, pthreads over envs)" % (
-        args.ref_envs, steps)
+    value, dt = cpu_arm(args.ref_envs, steps, warmup, args.seed, threads, burn_in=args.burn_in)
+    sample = "%d envs x %d ticks per run after %d untimed burn-in ticks (oracle C port of the reference env step, pthreads over envs)" % (
+        args.ref_envs, steps, args.burn_in)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
