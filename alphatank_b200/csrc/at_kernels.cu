@@ -181,7 +181,7 @@ struct HostSignal {
 
 // FUSED = true: simulation + observation rows in one launch (phase B below).  FUSED = false: simulation only; the rows
 // are built from the stored state by rows_kernel, launched behind this kernel as a programmatic dependent.
-template <bool IS_STEP, bool FUSED>
+template <bool IS_STEP, bool FUSED, int SPEC = 0>
 __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                  const int32_t *__restrict__ actions,
                                                  const uint8_t *__restrict__ mask, float *__restrict__ obs,
@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
         }
         my_actions = wstage + lane * row_ints;
     }
-    Sim s(c, st, bm, valid ? e : 0, tid);
+    SimT<SPEC> s(c, st, bm, valid ? e : 0, tid);
     s.warp_mask = valid_mask;
     s.acts_shared = acts_shared;
     if (valid) {
@@ -895,6 +895,7 @@ struct at_env {
     size_t smem_bytes;        // env_kernel<.., true>  (fused rows)
     size_t smem_bytes_sim;    // env_kernel<.., false> (simulation only)
     bool split_rows;          // rows by rows_kernel behind the simulation (default); AT_FUSED_ROWS=1: one fused kernel
+    int sim_spec;             // SimT<SPEC> specialisation of the step's simulation kernel (0: generic; AT_NO_SPEC=1 forces it)
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
     int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
     rows_kernel_fn rows_fn;   // the instantiation for this config's shape
@@ -929,7 +930,13 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
         CUDA_TRY(cudaGetLastError());
         return AT_OK;
     }
-    if (is_step)
+    if (is_step && env->sim_spec == 2)
+        env_kernel<true, false, 2><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
+                                                                        d_done, env->d_tmpl, sig);
+    else if (is_step && env->sim_spec == 1)
+        env_kernel<true, false, 1><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
+                                                                        d_done, env->d_tmpl, sig);
+    else if (is_step)
         env_kernel<true, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
                                                                      d_done, env->d_tmpl, sig);
     else
@@ -1050,12 +1057,22 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaFuncSetAttribute(env_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     cudaFuncSetAttribute(env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
     cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
+    cudaFuncSetAttribute(env_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
+    cudaFuncSetAttribute(env_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     {   // rows_kernel: the largest group (power of two, <= 4 envs) whose image keeps 12 warps on an SM, else whatever
         // fits at all; the G * 6n (env, slot) pairs must fit the lanes' prefetch registers (<= 3 per lane)
         const char *fz = getenv("AT_FUSED_ROWS"), *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");
         env->split_rows = !(fz && fz[0] == '1') && k.rows > 0;
         env->pdl = !(np && np[0] == '1');
+        {   // SPEC 1: team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME
+            const char *ns = getenv("AT_NO_SPEC");
+            bool smart_only = true;
+            for (int i = 0; i < k.n_tanks; ++i) smart_only = smart_only && (k.ctrl[i] != AT_CTRL_BOT || k.bot_type[i] == AT_BOT_SMART);
+            env->sim_spec = (!(ns && ns[0] == '1') && k.mode == AT_MODE_TEAM && smart_only && k.map != AT_MAP_MAZE &&
+                             k.terminate_time == 0) ? (k.n_tanks == 4 ? 2 : 1) : 0;
+            if (env->sim_spec && ns && ns[0] == '2') env->sim_spec = 1;   // (AT_NO_SPEC=2: no tank-count specialisation)
+        }
         const int RD = k.rows * k.obs_dim;
         const char *ww = getenv("AT_ROWS_WARPS");
         int W = ww ? atoi(ww) : 8;

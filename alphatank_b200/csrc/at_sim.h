@@ -332,7 +332,17 @@ AT_HD int select_bit(M128 m, int k) {
 }
 
 // ------------------------------------------------------------------ the per-env simulator
-struct Sim {
+// SPEC selects a compile-time specialisation of the config-dependent branches (0: everything is read from the
+// config; 2 = 1 + exactly four tanks).  SPEC 1 = team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME - the 2v2 / NvM
+// team_vs_bot workloads: the other bots, the 1v1 modes, the maze generator and the arena ordering drop out of the
+// kernel (the generic build is 630 KB of SASS and stalls on instruction fetch).
+template <int SPEC>
+struct SimT {
+    AT_HD int cfg_mode() const { return SPEC >= 1 ? 3 : c.mode; }
+    AT_HD int cfg_bot_type(int i) const { return SPEC >= 1 ? 0 : c.bot_type[i]; }
+    AT_HD bool cfg_maze() const { return SPEC >= 1 ? false : c.map == 2; }
+    AT_HD int cfg_terminate() const { return SPEC >= 1 ? 0 : c.terminate_time; }
+    AT_HD int cfg_n() const { return SPEC == 2 ? 4 : c.n_tanks; }   // SPEC 2 = SPEC 1 with exactly four tanks
     const KCfg &c;
     const DevState &st;
     const BlockMem &bm;
@@ -346,7 +356,7 @@ struct Sim {
     uint32_t warp_mask;    // lanes of this warp that run the simulation (device: for the pooled stages)
     bool acts_shared;      // device: action rows staged cooperatively by the whole (full) warp
 
-    AT_HD Sim(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
+    AT_HD SimT(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
           whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0), warp_mask(0xffffffffu), acts_shared(false) {}
 
@@ -358,7 +368,7 @@ struct Sim {
     // bullets (slot indices) that may lie within 100 px of tank i when it acts this tick (dodge_reward candidates)
     AT_HD void near_clear(int i) const {
         bm.nearlo[i * BS + tid] = 0u;
-        if (c.n_tanks * SLOTS_PER_TANK > 32) bm.nearhi[i * BS + tid] = 0u;
+        if (cfg_n() * SLOTS_PER_TANK > 32) bm.nearhi[i * BS + tid] = 0u;
     }
     AT_HD void near_set(int i, int slot) const {
         if (slot < 32) bm.nearlo[i * BS + tid] |= 1u << slot;
@@ -366,7 +376,7 @@ struct Sim {
     }
     AT_HD uint64_t near_get(int i) const {
         uint64_t v = bm.nearlo[i * BS + tid];
-        if (c.n_tanks * SLOTS_PER_TANK > 32) v |= (uint64_t)bm.nearhi[i * BS + tid] << 32;
+        if (cfg_n() * SLOTS_PER_TANK > 32) v |= (uint64_t)bm.nearhi[i * BS + tid] << 32;
         return v;
     }
     AT_HD uint32_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
@@ -462,11 +472,11 @@ struct Sim {
     AT_HD void reward_by_bullets(int shooter, int victim) {
         TREW(shooter) += 50;
         TREW(victim) += -50;
-        if (c.mode != AT_MODE_TEAM_) {
+        if (cfg_mode() != AT_MODE_TEAM_) {
             bool all_same = true;
-            for (int i = 1; i < c.n_tanks; ++i) all_same = all_same && (t_alive(i) == t_alive(0));
+            for (int i = 1; i < cfg_n(); ++i) all_same = all_same && (t_alive(i) == t_alive(0));
             if (all_same)
-                for (int i = 0; i < c.n_tanks; ++i)
+                for (int i = 0; i < cfg_n(); ++i)
                     if (t_alive(i)) {
                         double q = (double)(1000 - (int)epstep) / 1000.0;
                         double time_bonus = q > 0 ? 5 * q : 0.0;
@@ -553,7 +563,7 @@ struct Sim {
             }
         bool gone = false;
         if (victim >= 0) {
-            if (c.terminate_time == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
+            if (cfg_terminate() == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
             THITS(owner) += 1u;
             THITS(victim) += 1u << 16;
             reward_by_bullets(owner, victim);
@@ -573,7 +583,7 @@ struct Sim {
     AT_HD void bullets_pass() {
         const uint32_t n = cnt;
         uint32_t w = 0;
-        for (int i = 0; i < c.n_tanks; ++i) { TLIVE(i) = 0; near_clear(i); }
+        for (int i = 0; i < cfg_n(); ++i) { TLIVE(i) = 0; near_clear(i); }
         tclo = 0; tchi = 0;
         if (n > 0)
             for (uint32_t bits = alive_bits; bits; bits &= bits - 1) {  // cells under Rect(x-15, y-12, 30, 24)
@@ -651,7 +661,7 @@ struct Sim {
         st.by[G(cnt)] = TY(i) - 10 * sv;
         uint32_t rank = TLIVE(i)++;
         st.bmeta[G(cnt)] = (uint64_t)i | ((uint64_t)a << BM_ANGLE) | ((uint64_t)rank << BM_RANK);
-        for (uint32_t bits = ((1u << c.n_tanks) - 1u) & ~c.team_members[i]; bits; bits &= bits - 1)
+        for (uint32_t bits = ((1u << cfg_n()) - 1u) & ~c.team_members[i]; bits; bits &= bits - 1)
             near_set(ffs32(bits), (int)cnt);  // a fresh bullet is a candidate for every enemy that acts later
         ++cnt;
         TSHOT(i) = now;
@@ -787,7 +797,7 @@ struct Sim {
     AT_HD int nearest_opponent(int me, double *dist_out) const {
         double best = INFINITY;
         int idx = -1;
-        for (int i = 0; i < c.n_tanks; ++i)
+        for (int i = 0; i < cfg_n(); ++i)
             if (c.team[i] != c.team[me] && t_alive(i)) {
                 double dx = TX(i) - TX(me), dy = TY(i) - TY(me);
                 double d = sqrt(dx * dx + dy * dy);
@@ -828,7 +838,7 @@ struct Sim {
         L.enemies = 0;
         L.bx0 = 1 << 20; L.bx1 = -(1 << 20); L.by0 = 1 << 20; L.by1 = -(1 << 20);  // union of the enemy rect origins
         bool reachable = false;
-        for (int i = 0; i < c.n_tanks; ++i)
+        for (int i = 0; i < cfg_n(); ++i)
             if (c.team[i] != c.team[me] && (bm.tpack[i * BS + q] & TP_ALIVE)) {
                 L.enemies |= 1u << i;
                 const int exi = los_ex(L, i), eyi = los_ey(L, i);
@@ -983,10 +993,10 @@ struct Sim {
         return 0u;
     }
     AT_HD void bot_init(int i) {
-        BPACK(i) = bot_init_pack(c.bot_type[i]);
+        BPACK(i) = bot_init_pack(cfg_bot_type(i));
         BF0(i) = TX(i);  // strategy_bot.py:15 last_position
         BF1(i) = TY(i);
-        if (c.bot_type[i] != 0) { BF0(i) = 0.0; BF1(i) = 0.0; }
+        if (cfg_bot_type(i) != 0) { BF0(i) = 0.0; BF1(i) = 0.0; }
     }
 
     // SmartStrategyBot.get_action (strategy_bot.py:75-203) split around its line-of-sight query so that the
@@ -1229,7 +1239,7 @@ struct Sim {
         const double radius = GRID * 4;
         double best = INFINITY, px = 0, py = 0;
         bool have = false;
-        for (int i = 0; i < c.n_tanks; ++i)
+        for (int i = 0; i < cfg_n(); ++i)
             if (c.team[i] != c.team[me] && t_alive(i)) {
                 double dx = TX(i) - TX(me), dy = TY(i) - TY(me);
                 double d = sqrt(dx * dx + dy * dy);
@@ -1268,7 +1278,7 @@ struct Sim {
         BPACK(me) = (uint32_t)timer | ((uint32_t)state << 5) | ((uint32_t)has_angle << 7);
     }
     AT_HD void bot_action(int me, int act[3], bool pre_done, bool los_hoisted) {
-        switch (c.bot_type[me]) {
+        switch (cfg_bot_type(me)) {
         case 0: {
             // runs for dead tanks too: take_action still sets their speed (sprite.py:646-651), which the
             // other tanks' observation rows expose as velocity
@@ -1287,7 +1297,7 @@ struct Sim {
 
     // ---------------------------------------------------------------- reset (gaming_env.py:48-66, 509-520)
     AT_HD void env_reset() {
-        if (c.map == 2) {
+        if (cfg_maze()) {
             const MazeOut mz = generate_maze_mask(c.seed, c.env_id_base + e, rng);
             wlo = mz.lo; whi = mz.hi; rng = mz.ctr;
             set_near();
@@ -1295,7 +1305,7 @@ struct Sim {
         const M128 all = {~0ull, (1ull << (CELLS - 64)) - 1};
         const M128 freec = m_andn(all, M128{wlo, whi});
         const int n_empty = CELLS - c.n_walls;
-        for (int i = 0; i < c.n_tanks; ++i) {
+        for (int i = 0; i < cfg_n(); ++i) {
             int cell = select_bit(freec, rng_below(n_empty));
             TX(i) = (double)((cell % 11) * 70) + GRID / 2;
             TY(i) = (double)((cell / 11) * 70) + GRID / 2;
@@ -1308,10 +1318,10 @@ struct Sim {
             if (c.ctrl[i] == 1) { BPACK(i) = 0u; BF0(i) = 0.0; BF1(i) = 0.0; }
         }
         cnt = 0;
-        alive_bits = (1u << c.n_tanks) - 1u;
-        for (int i = 0; i < c.n_tanks; ++i) {
-            bool has_bot = (c.mode == AT_MODE_BOT_AGENT_ && i == 0) ||
-                           ((c.mode == AT_MODE_TEAM_ || c.mode == AT_MODE_ARENA_) && c.ctrl[i] == 1);
+        alive_bits = (1u << cfg_n()) - 1u;
+        for (int i = 0; i < cfg_n(); ++i) {
+            bool has_bot = (cfg_mode() == AT_MODE_BOT_AGENT_ && i == 0) ||
+                           ((cfg_mode() == AT_MODE_TEAM_ || cfg_mode() == AT_MODE_ARENA_) && c.ctrl[i] == 1);
             if (has_bot) bot_init(i);
         }
         zones = 0;
@@ -1324,7 +1334,7 @@ struct Sim {
         }
         epstep = 0;
         st.prev_act[e] = 0u;
-        for (int k = 0; k < c.n_tanks; ++k) st.change_time[G(k)] = 0;
+        for (int k = 0; k < cfg_n(); ++k) st.change_time[G(k)] = 0;
     }
 
     // ---------------------------------------------------------------- one tick
@@ -1333,47 +1343,58 @@ struct Sim {
     // site (they are force-inlined; duplicating them made the kernel 700 KB of SASS and instruction-fetch bound):
     //   stage 0  arena only: both bots decide on the pre-tick state (bot_arena.py:51-52)
     //   stage 1  bullets pass 1      stage 2  controllers in the reference's order      stage 3  bullets pass 2
+    // stage 0 (arena: bots decide on the pre-tick state) or stage 2 (controllers in the reference's order)
+    AT_HD void controllers(int stage, const int32_t *a, int (&acts)[MAX_TANKS][3], uint32_t &pre_done, uint32_t &los_bits) {
+        const bool arena = cfg_mode() == AT_MODE_ARENA_, team = cfg_mode() == AT_MODE_TEAM_, botagent = cfg_mode() == AT_MODE_BOT_AGENT_;
+        // acting order: team mode = agent tanks in config order, then bot tanks in config order
+        // (controller.py:81-113); every 1v1 mode = tank 0, tank 1
+        for (int k = 0; k < cfg_n(); ++k) {
+            int i = k;
+            if (team) i = k < c.n_agents ? c.agent_tank[k] : c.bot_tank[k - c.n_agents];
+            const bool is_bot = c.ctrl[i] == 1;
+            if (is_bot && (stage == 0 || !arena)) {
+                if (k == c.first_bot_k && c.los_hoist != 0u) {
+                    // every smart bot whose line of sight cannot change before it acts: query them together
+                    uint32_t need = 0;
+                    for (uint32_t hb = c.los_hoist; hb; hb &= hb - 1) {
+                        const int j = ffs32(hb);
+                        if (smart_pre(j)) need |= 1u << j;
+                    }
+                    pre_done = c.los_hoist;
+                    los_bits = pool_los(need);
+                }
+                bot_action(i, acts[i], (pre_done >> i) & 1u, (los_bits >> i) & 1u);
+                if (botagent && !(rng_unit53() < c.weakness)) { acts[i][0] = 1; acts[i][1] = 1; acts[i][2] = 0; }
+            }
+            if (stage == 0) continue;
+            if (!is_bot) {
+                const int row = team ? k : i;
+                acts_ready();
+                acts[i][0] = a[3 * row]; acts[i][1] = a[3 * row + 1]; acts[i][2] = a[3 * row + 2];
+            }
+            // bot_agent's agent tank uses the swapped movement table and creeps on "stop" (F14)
+            const bool swapped = botagent && i == 1;
+            apply_action(i, acts[i][0], acts[i][1], acts[i][2], swapped ? 0 : 2, swapped ? 2 : 0, swapped ? 1 : 0);
+        }
+    }
     AT_HD void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
         int acts[MAX_TANKS][3];
         tick += 1;
-        if (c.mode != AT_MODE_TEAM_) epstep += 1;
-        const bool arena = c.mode == AT_MODE_ARENA_, team = c.mode == AT_MODE_TEAM_, botagent = c.mode == AT_MODE_BOT_AGENT_;
+        if (cfg_mode() != AT_MODE_TEAM_) epstep += 1;
         uint32_t pre_done = 0, los_bits = 0;
+        if (SPEC >= 1) {   // straight-line: pass, controllers, pass (measured: the rolled stage loop costs 10 %)
+            bullets_pass();
+            controllers(2, a, acts, pre_done, los_bits);
+            bullets_pass();
+            return;
+        }
+        const bool arena = cfg_mode() == AT_MODE_ARENA_;
         for (int stage = arena ? 0 : 1; stage < 4; ++stage) {
             if (stage & 1) {
                 bullets_pass();
                 continue;
             }
-            // acting order: team mode = agent tanks in config order, then bot tanks in config order
-            // (controller.py:81-113); every 1v1 mode = tank 0, tank 1
-            for (int k = 0; k < c.n_tanks; ++k) {
-                int i = k;
-                if (team) i = k < c.n_agents ? c.agent_tank[k] : c.bot_tank[k - c.n_agents];
-                const bool is_bot = c.ctrl[i] == 1;
-                if (is_bot && (stage == 0 || !arena)) {
-                    if (k == c.first_bot_k && c.los_hoist != 0u) {
-                        // every smart bot whose line of sight cannot change before it acts: query them together
-                        uint32_t need = 0;
-                        for (uint32_t hb = c.los_hoist; hb; hb &= hb - 1) {
-                            const int j = ffs32(hb);
-                            if (smart_pre(j)) need |= 1u << j;
-                        }
-                        pre_done = c.los_hoist;
-                        los_bits = pool_los(need);
-                    }
-                    bot_action(i, acts[i], (pre_done >> i) & 1u, (los_bits >> i) & 1u);
-                    if (botagent && !(rng_unit53() < c.weakness)) { acts[i][0] = 1; acts[i][1] = 1; acts[i][2] = 0; }
-                }
-                if (stage == 0) continue;
-                if (!is_bot) {
-                    const int row = team ? k : i;
-                    acts_ready();
-                    acts[i][0] = a[3 * row]; acts[i][1] = a[3 * row + 1]; acts[i][2] = a[3 * row + 2];
-                }
-                // bot_agent's agent tank uses the swapped movement table and creeps on "stop" (F14)
-                const bool swapped = botagent && i == 1;
-                apply_action(i, acts[i][0], acts[i][1], acts[i][2], swapped ? 0 : 2, swapped ? 2 : 0, swapped ? 1 : 0);
-            }
+            controllers(stage, a, acts, pre_done, los_bits);
         }
     }
 
@@ -1395,13 +1416,13 @@ struct Sim {
         for (int r = 0; r < c.rows; ++r)
             rewards_row[r] = (float)TREW(c.team_layout ? c.agent_tank[r] : r);
         bool done;
-        if (c.terminate_time != 0) {
-            done = !((int)tstep < c.terminate_time);
+        if (cfg_terminate() != 0) {
+            done = !((int)tstep < cfg_terminate());
             if (done) tstep = 0;
         } else {
             uint32_t teams = 0;
             int winner_team = -1;
-            for (int i = 0; i < c.n_tanks; ++i)
+            for (int i = 0; i < cfg_n(); ++i)
                 if (t_alive(i)) {
                     teams |= 1u << c.team[i];
                     if (winner_team < 0) winner_team = c.team[i];
@@ -1409,7 +1430,7 @@ struct Sim {
             int nalive = popc64(teams);
             done = nalive <= 1;
             if (c.team_layout && nalive == 1)  // F5: lands after the rewards were read
-                for (int i = 0; i < c.n_tanks; ++i)
+                for (int i = 0; i < cfg_n(); ++i)
                     if (c.team[i] == winner_team) TREW(i) += 200;
         }
         return done;
@@ -1453,7 +1474,7 @@ struct Sim {
     AT_HD void emit_rows(Sink &out) const {
         const bool team = c.team_layout != 0;
 #ifdef __CUDA_ARCH__
-        for (int i = 0; i < c.n_tanks; ++i)  // corner-offset LUT entries (one 32-byte sector each) -> L1
+        for (int i = 0; i < cfg_n(); ++i)  // corner-offset LUT entries (one 32-byte sector each) -> L1
             asm volatile("prefetch.global.L1 [%0];\n" ::"l"(st.corn + 4 * t_angle(i)));
 #endif
         for (int r = 0; r < c.rows; ++r) {
@@ -1468,7 +1489,7 @@ struct Sim {
             // ones).  One rolled loop over the n*6 slots (small code: the kernel is instruction-cache bound) with
             // the records requested two iterations ahead, so their L2 latency overlaps the emission.
             {
-                const int nslots = c.n_tanks * SLOTS_PER_TANK;
+                const int nslots = cfg_n() * SLOTS_PER_TANK;
                 uint64_t m0, m1;
                 double x0, y0, x1, y1;
                 bool h0, h1;
@@ -1503,7 +1524,7 @@ struct Sim {
                     fetch_slot(t, f + 3, nslots, h1, m1, x1, y1);
                 }
             }
-            for (int i = 0; i < c.n_tanks; ++i) {
+            for (int i = 0; i < cfg_n(); ++i) {
                 if (i == t) continue;
                 const double x = TX(i), y = TY(i);
                 const double rx = x - ax, ry = y - ay;
@@ -1514,7 +1535,7 @@ struct Sim {
                 if (team) out.put(c.team[i] == c.team[t] ? 1.0f : 0.0f);
                 out.put(t_alive(i) ? 1.0f : 0.0f);
             }
-            if (c.map != 2) {  // fixed map: the sink fills these columns from the block's template
+            if (!cfg_maze()) {  // fixed map: the sink fills these columns from the block's template
                 out.skip_static(bm.tmpl, 4 * c.n_walls + CELLS);
             } else {
                 const M128 wm = {wlo, whi};
@@ -1542,9 +1563,9 @@ struct Sim {
     AT_HD void load() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
         zones = st.zones[e];
-        if (c.map == 2) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; set_near(); }
+        if (cfg_maze()) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; set_near(); }
         else { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
-        for (int i = 0; i < c.n_tanks; ++i) {
+        for (int i = 0; i < cfg_n(); ++i) {
             TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
             TPACK(i) = st.tpack[G(i)]; TSHOT(i) = st.tshot[G(i)];
             if (c.ctrl[i] == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
@@ -1555,20 +1576,21 @@ struct Sim {
     AT_HD void load_scalars_only() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
         zones = st.zones[e];
-        if (c.map == 2) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; }
+        if (cfg_maze()) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; }
         else { wlo = c.wall_lo; whi = c.wall_hi; }
     }
     AT_HD void store() {
         st.cnt[e] = cnt; st.rng_ctr[e] = rng; st.tick[e] = tick; st.tstep[e] = tstep; st.epstep[e] = epstep;
         st.zones[e] = zones;
-        if (c.map == 2) { st.wall_lo[e] = wlo; st.wall_hi[e] = whi; }
-        for (int i = 0; i < c.n_tanks; ++i) {
+        if (cfg_maze()) { st.wall_lo[e] = wlo; st.wall_hi[e] = whi; }
+        for (int i = 0; i < cfg_n(); ++i) {
             st.tx[G(i)] = TX(i); st.ty[G(i)] = TY(i); st.trew[G(i)] = TREW(i);
             st.tpack[G(i)] = TPACK(i); st.tshot[G(i)] = TSHOT(i);
             if (c.ctrl[i] == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
         }
     }
 };
+typedef SimT<0> Sim;   // the generic build (emulator, reset kernel, every config without a specialisation)
 
 // wall rectangles (row-major = reference list order) + maze grid columns of a fixed map
 AT_HD void fill_static_template(uint64_t wall_lo, uint64_t wall_hi, float *tmpl) {
