@@ -165,6 +165,20 @@ inline std::string build_kcfg(const at_config *cfg, uint64_t seed, int64_t env_i
     return "";
 }
 
+// Which SimT<SPEC> specialisation (at_sim.h) a frozen config can run on.  1: team mode, every scripted tank a smart bot,
+// fixed map, no TERMINATE_TIME; 2: 1 with exactly four tanks; 3: 2 with the 2a_vs_2b layout (tanks 0, 1 = one team's
+// agents, tanks 2, 3 = the other team's bots).  `cap` limits the level (diagnostics: AT_NO_SPEC).
+inline int sim_spec_for(const KCfg &k, int cap = 3) {
+    bool smart_only = true;
+    for (int i = 0; i < k.n_tanks; ++i) smart_only = smart_only && (k.ctrl[i] != AT_CTRL_BOT || k.bot_type[i] == AT_BOT_SMART);
+    int spec = (k.mode == AT_MODE_TEAM && smart_only && k.map != AT_MAP_MAZE && k.terminate_time == 0) ? 1 : 0;
+    if (spec == 1 && k.n_tanks == 4) spec = 2;
+    if (spec == 2 && k.ctrl[0] == AT_CTRL_AGENT && k.ctrl[1] == AT_CTRL_AGENT && k.ctrl[2] == AT_CTRL_BOT &&
+        k.ctrl[3] == AT_CTRL_BOT && k.team[0] == k.team[1] && k.team[2] == k.team[3] && k.team[0] != k.team[2])
+        spec = 3;
+    return spec < cap ? spec : cap;
+}
+
 // One arena for every SoA column (HBM on the GPU, malloc in the emulator).
 struct ArenaLayout {
     size_t o_cnt, o_rng, o_tick, o_tstep, o_ep, o_zones, o_prev, o_change, o_wlo, o_whi, o_tx, o_ty, o_trew, o_tpack,

@@ -930,7 +930,10 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
         CUDA_TRY(cudaGetLastError());
         return AT_OK;
     }
-    if (is_step && env->sim_spec == 2)
+    if (is_step && env->sim_spec == 3)
+        env_kernel<true, false, 3><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
+                                                                        d_done, env->d_tmpl, sig);
+    else if (is_step && env->sim_spec == 2)
         env_kernel<true, false, 2><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
                                                                         d_done, env->d_tmpl, sig);
     else if (is_step && env->sim_spec == 1)
@@ -1059,19 +1062,16 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
+    cudaFuncSetAttribute(env_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     {   // rows_kernel: the largest group (power of two, <= 4 envs) whose image keeps 12 warps on an SM, else whatever
         // fits at all; the G * 6n (env, slot) pairs must fit the lanes' prefetch registers (<= 3 per lane)
         const char *fz = getenv("AT_FUSED_ROWS"), *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");
         env->split_rows = !(fz && fz[0] == '1') && k.rows > 0;
         env->pdl = !(np && np[0] == '1');
-        {   // SPEC 1: team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME
+        {   // AT_NO_SPEC=1: generic kernel; 2 / 3: stop below that specialisation level
             const char *ns = getenv("AT_NO_SPEC");
-            bool smart_only = true;
-            for (int i = 0; i < k.n_tanks; ++i) smart_only = smart_only && (k.ctrl[i] != AT_CTRL_BOT || k.bot_type[i] == AT_BOT_SMART);
-            env->sim_spec = (!(ns && ns[0] == '1') && k.mode == AT_MODE_TEAM && smart_only && k.map != AT_MAP_MAZE &&
-                             k.terminate_time == 0) ? (k.n_tanks == 4 ? 2 : 1) : 0;
-            if (env->sim_spec && ns && ns[0] == '2') env->sim_spec = 1;   // (AT_NO_SPEC=2: no tank-count specialisation)
+            env->sim_spec = sim_spec_for(k, ns && ns[0] >= '1' && ns[0] <= '3' ? ns[0] - '1' : 3);
         }
         const int RD = k.rows * k.obs_dim;
         const char *ww = getenv("AT_ROWS_WARPS");

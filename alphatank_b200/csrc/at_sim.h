@@ -333,7 +333,7 @@ AT_HD int select_bit(M128 m, int k) {
 
 // ------------------------------------------------------------------ the per-env simulator
 // SPEC selects a compile-time specialisation of the config-dependent branches (0: everything is read from the
-// config; 2 = 1 + exactly four tanks).  SPEC 1 = team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME - the 2v2 / NvM
+// config; 2 = 1 + exactly four tanks; 3 = 2 + the 2a_vs_2b tank layout).  SPEC 1 = team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME - the 2v2 / NvM
 // team_vs_bot workloads: the other bots, the 1v1 modes, the maze generator and the arena ordering drop out of the
 // kernel (the generic build is 630 KB of SASS and stalls on instruction fetch).
 template <int SPEC>
@@ -341,8 +341,21 @@ struct SimT {
     AT_HD int cfg_mode() const { return SPEC >= 1 ? 3 : c.mode; }
     AT_HD int cfg_bot_type(int i) const { return SPEC >= 1 ? 0 : c.bot_type[i]; }
     AT_HD bool cfg_maze() const { return SPEC >= 1 ? false : c.map == 2; }
+    AT_HD bool cfg_team_layout() const { return SPEC >= 1 ? true : c.team_layout != 0; }
     AT_HD int cfg_terminate() const { return SPEC >= 1 ? 0 : c.terminate_time; }
-    AT_HD int cfg_n() const { return SPEC == 2 ? 4 : c.n_tanks; }   // SPEC 2 = SPEC 1 with exactly four tanks
+    AT_HD int cfg_n() const { return SPEC >= 2 ? 4 : c.n_tanks; }   // SPEC 2 = SPEC 1 with exactly four tanks
+    // SPEC 3 = SPEC 2 with the 2a_vs_2b layout: tanks 0, 1 = one team's agents, tanks 2, 3 = the other team's smart bots
+    AT_HD int cfg_team(int i) const { return SPEC == 3 ? (i >> 1) : c.team[i]; }
+    AT_HD uint32_t cfg_team_members(int i) const { return SPEC == 3 ? (i < 2 ? 3u : 12u) : c.team_members[i]; }
+    AT_HD int cfg_ctrl(int i) const { return SPEC == 3 ? (i >> 1) : c.ctrl[i]; }
+    AT_HD int cfg_agent_tank(int k) const { return SPEC == 3 ? k : c.agent_tank[k]; }
+    AT_HD int cfg_bot_tank(int k) const { return SPEC == 3 ? 2 + k : c.bot_tank[k]; }
+    AT_HD int cfg_bot_ord(int i) const { return SPEC == 3 ? (i >= 2 ? i - 2 : 0) : c.bot_ord[i]; }
+    AT_HD uint32_t cfg_los_hoist() const { return SPEC == 3 ? 12u : c.los_hoist; }
+    AT_HD int cfg_first_bot_k() const { return SPEC == 3 ? 2 : c.first_bot_k; }
+    AT_HD int cfg_n_agents() const { return SPEC == 3 ? 2 : c.n_agents; }
+    AT_HD int cfg_rows() const { return SPEC == 3 ? 2 : c.rows; }
+    AT_HD int cfg_act_rows() const { return SPEC == 3 ? 2 : c.act_rows; }
     const KCfg &c;
     const DevState &st;
     const BlockMem &bm;
@@ -382,9 +395,9 @@ struct SimT {
     AT_HD uint32_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
     AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * BS + tid]; }
     // bot FSM columns exist only for bot tanks (bot_ord: ordinal among the bots)
-    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[c.bot_ord[i] * BS + tid]; }
-    AT_HD double &BF0(int i) const { return bm.bf0[c.bot_ord[i] * BS + tid]; }
-    AT_HD double &BF1(int i) const { return bm.bf1[c.bot_ord[i] * BS + tid]; }
+    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[cfg_bot_ord(i) * BS + tid]; }
+    AT_HD double &BF0(int i) const { return bm.bf0[cfg_bot_ord(i) * BS + tid]; }
+    AT_HD double &BF1(int i) const { return bm.bf1[cfg_bot_ord(i) * BS + tid]; }
     AT_HD int64_t G(int slot) const { return (int64_t)slot * st.N + e; }
 
     AT_HD int t_angle(int i) const { return (int)(TPACK(i) & 511u); }
@@ -506,7 +519,7 @@ struct SimT {
             double u0, u1;
             unit_dir(ang, u0, u1);
             const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
-            for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // alive enemies
+            for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies
                 const int i = ffs32(bits);
                 const double tx = TX(i) - x, ty = TY(i) - y;
                 // dodge_reward candidate: the tank moves <= 10 px and this bullet <= 1 px per axis before that test
@@ -557,7 +570,7 @@ struct SimT {
         // single exit: the warp reconverges before the record is packed / stored by the caller
         int victim = -1;
         if (near_tank)
-            for (uint32_t bits = alive_bits & ~c.team_members[owner]; bits; bits &= bits - 1) {  // sprite.py:88-100
+            for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // sprite.py:88-100
                 const int i = ffs32(bits);
                 if (rect5_hits_tank(ix, iy, i)) { victim = i; break; }
             }
@@ -661,7 +674,7 @@ struct SimT {
         st.by[G(cnt)] = TY(i) - 10 * sv;
         uint32_t rank = TLIVE(i)++;
         st.bmeta[G(cnt)] = (uint64_t)i | ((uint64_t)a << BM_ANGLE) | ((uint64_t)rank << BM_RANK);
-        for (uint32_t bits = ((1u << cfg_n()) - 1u) & ~c.team_members[i]; bits; bits &= bits - 1)
+        for (uint32_t bits = ((1u << cfg_n()) - 1u) & ~cfg_team_members(i); bits; bits &= bits - 1)
             near_set(ffs32(bits), (int)cnt);  // a fresh bullet is a candidate for every enemy that acts later
         ++cnt;
         TSHOT(i) = now;
@@ -673,7 +686,7 @@ struct SimT {
         if (sp == 0) return;  // projection is exactly 0: reward unchanged
         const int a = t_angle(i);
         const double tvx = (double)sp * cosr(a), tvy = (double)sp * sinr(a);
-        const int myteam = c.team[i];
+        const int myteam = cfg_team(i);
         double reward = 0;
         const double mx = TX(i), my = TY(i);
         // only the candidates flagged by the bullet pass / shoot() are visited, in slot order (= list order);
@@ -683,7 +696,7 @@ struct SimT {
             uint64_t m = pm;
             double bxv = px, byv = py;
             if (!first) { m = st.bmeta[G(r)]; bxv = st.bx[G(r)]; byv = st.by[G(r)]; }
-            if (c.team[(int)(m & 15u)] == myteam) continue;
+            if (cfg_team((int)(m & 15u)) == myteam) continue;
             const double ex_ = mx - bxv;
             if (fabs(ex_) >= 101.0) continue;                          // distance >= 100 for sure
             const double ey_ = my - byv;
@@ -798,7 +811,7 @@ struct SimT {
         double best = INFINITY;
         int idx = -1;
         for (int i = 0; i < cfg_n(); ++i)
-            if (c.team[i] != c.team[me] && t_alive(i)) {
+            if (cfg_team(i) != cfg_team(me) && t_alive(i)) {
                 double dx = TX(i) - TX(me), dy = TY(i) - TY(me);
                 double d = sqrt(dx * dx + dy * dy);
                 if (d < best) { best = d; idx = i; }
@@ -839,7 +852,7 @@ struct SimT {
         L.bx0 = 1 << 20; L.bx1 = -(1 << 20); L.by0 = 1 << 20; L.by1 = -(1 << 20);  // union of the enemy rect origins
         bool reachable = false;
         for (int i = 0; i < cfg_n(); ++i)
-            if (c.team[i] != c.team[me] && (bm.tpack[i * BS + q] & TP_ALIVE)) {
+            if (cfg_team(i) != cfg_team(me) && (bm.tpack[i * BS + q] & TP_ALIVE)) {
                 L.enemies |= 1u << i;
                 const int exi = los_ex(L, i), eyi = los_ey(L, i);
                 L.bx0 = imin(L.bx0, exi); L.bx1 = imax(L.bx1, exi); L.by0 = imin(L.by0, eyi); L.by1 = imax(L.by1, eyi);
@@ -1086,7 +1099,7 @@ struct SimT {
         uint8_t *queue = bm.los_q + (tid >> 5) * 256;
         uint8_t *res = bm.los_r + (tid >> 5) * 256;
         int total = 0;
-        for (uint32_t hb = c.los_hoist; hb; hb &= hb - 1) {
+        for (uint32_t hb = cfg_los_hoist(); hb; hb &= hb - 1) {
             const int j = ffs32(hb);
             const bool mine = (need >> j) & 1u;
             const unsigned m = __ballot_sync(wm, mine);
@@ -1240,14 +1253,14 @@ struct SimT {
         double best = INFINITY, px = 0, py = 0;
         bool have = false;
         for (int i = 0; i < cfg_n(); ++i)
-            if (c.team[i] != c.team[me] && t_alive(i)) {
+            if (cfg_team(i) != cfg_team(me) && t_alive(i)) {
                 double dx = TX(i) - TX(me), dy = TY(i) - TY(me);
                 double d = sqrt(dx * dx + dy * dy);
                 if (d < best && d < radius) { best = d; px = TX(i); py = TY(i); have = true; }
             }
         for (uint32_t r = 0; r < cnt; ++r) {
             const uint64_t m = st.bmeta[G(r)];
-            if (c.team[(int)(m & 15u)] == c.team[me]) continue;
+            if (cfg_team((int)(m & 15u)) == cfg_team(me)) continue;
             double bxv = st.bx[G(r)], byv = st.by[G(r)];
             double dx = bxv - TX(me), dy = byv - TY(me);
             double d = sqrt(dx * dx + dy * dy);
@@ -1315,13 +1328,13 @@ struct SimT {
             THITS(i) = 0u;
             TLIVE(i) = 0u;
             TSHOT(i) = 0;
-            if (c.ctrl[i] == 1) { BPACK(i) = 0u; BF0(i) = 0.0; BF1(i) = 0.0; }
+            if (cfg_ctrl(i) == 1) { BPACK(i) = 0u; BF0(i) = 0.0; BF1(i) = 0.0; }
         }
         cnt = 0;
         alive_bits = (1u << cfg_n()) - 1u;
         for (int i = 0; i < cfg_n(); ++i) {
             bool has_bot = (cfg_mode() == AT_MODE_BOT_AGENT_ && i == 0) ||
-                           ((cfg_mode() == AT_MODE_TEAM_ || cfg_mode() == AT_MODE_ARENA_) && c.ctrl[i] == 1);
+                           ((cfg_mode() == AT_MODE_TEAM_ || cfg_mode() == AT_MODE_ARENA_) && cfg_ctrl(i) == 1);
             if (has_bot) bot_init(i);
         }
         zones = 0;
@@ -1350,17 +1363,17 @@ struct SimT {
         // (controller.py:81-113); every 1v1 mode = tank 0, tank 1
         for (int k = 0; k < cfg_n(); ++k) {
             int i = k;
-            if (team) i = k < c.n_agents ? c.agent_tank[k] : c.bot_tank[k - c.n_agents];
-            const bool is_bot = c.ctrl[i] == 1;
+            if (team) i = k < cfg_n_agents() ? cfg_agent_tank(k) : cfg_bot_tank(k - cfg_n_agents());
+            const bool is_bot = cfg_ctrl(i) == 1;
             if (is_bot && (stage == 0 || !arena)) {
-                if (k == c.first_bot_k && c.los_hoist != 0u) {
+                if (k == cfg_first_bot_k() && cfg_los_hoist() != 0u) {
                     // every smart bot whose line of sight cannot change before it acts: query them together
                     uint32_t need = 0;
-                    for (uint32_t hb = c.los_hoist; hb; hb &= hb - 1) {
+                    for (uint32_t hb = cfg_los_hoist(); hb; hb &= hb - 1) {
                         const int j = ffs32(hb);
                         if (smart_pre(j)) need |= 1u << j;
                     }
-                    pre_done = c.los_hoist;
+                    pre_done = cfg_los_hoist();
                     los_bits = pool_los(need);
                 }
                 bot_action(i, acts[i], (pre_done >> i) & 1u, (los_bits >> i) & 1u);
@@ -1401,11 +1414,11 @@ struct SimT {
     // wrapper step (gym_env.py:73-103, 186-200; gym_env_multi.py:202-223, 307-326).  Returns done.
     AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
         tstep += 1;
-        if (!c.team_layout && a) {  // change_time, gym_env.py:77-85
+        if (!cfg_team_layout() && a) {  // change_time, gym_env.py:77-85
             acts_ready();
             uint32_t pv = st.prev_act[e];
             uint32_t nv = 1u;
-            for (int k = 0; k < c.act_rows; ++k) {
+            for (int k = 0; k < cfg_act_rows(); ++k) {
                 uint32_t code = (uint32_t)(a[3 * k] * 3 + a[3 * k + 1]) & 15u;
                 if ((pv & 1u) && ((pv >> (1 + 4 * k)) & 15u) == code) st.change_time[G(k)] += 1;
                 nv |= code << (1 + 4 * k);
@@ -1413,8 +1426,8 @@ struct SimT {
             st.prev_act[e] = nv;
         }
         game_step(a);
-        for (int r = 0; r < c.rows; ++r)
-            rewards_row[r] = (float)TREW(c.team_layout ? c.agent_tank[r] : r);
+        for (int r = 0; r < cfg_rows(); ++r)
+            rewards_row[r] = (float)TREW(cfg_team_layout() ? cfg_agent_tank(r) : r);
         bool done;
         if (cfg_terminate() != 0) {
             done = !((int)tstep < cfg_terminate());
@@ -1424,14 +1437,14 @@ struct SimT {
             int winner_team = -1;
             for (int i = 0; i < cfg_n(); ++i)
                 if (t_alive(i)) {
-                    teams |= 1u << c.team[i];
-                    if (winner_team < 0) winner_team = c.team[i];
+                    teams |= 1u << cfg_team(i);
+                    if (winner_team < 0) winner_team = cfg_team(i);
                 }
             int nalive = popc64(teams);
             done = nalive <= 1;
-            if (c.team_layout && nalive == 1)  // F5: lands after the rewards were read
+            if (cfg_team_layout() && nalive == 1)  // F5: lands after the rewards were read
                 for (int i = 0; i < cfg_n(); ++i)
-                    if (c.team[i] == winner_team) TREW(i) += 200;
+                    if (cfg_team(i) == winner_team) TREW(i) += 200;
         }
         return done;
     }
@@ -1472,13 +1485,13 @@ struct SimT {
     }
     template <class Sink>
     AT_HD void emit_rows(Sink &out) const {
-        const bool team = c.team_layout != 0;
+        const bool team = cfg_team_layout();
 #ifdef __CUDA_ARCH__
         for (int i = 0; i < cfg_n(); ++i)  // corner-offset LUT entries (one 32-byte sector each) -> L1
             asm volatile("prefetch.global.L1 [%0];\n" ::"l"(st.corn + 4 * t_angle(i)));
 #endif
-        for (int r = 0; r < c.rows; ++r) {
-            const int t = team ? c.agent_tank[r] : r;
+        for (int r = 0; r < cfg_rows(); ++r) {
+            const int t = team ? cfg_agent_tank(r) : r;
             const double ax = TX(t), ay = TY(t);
             out.reserve(15);
             out.put((float)ax); out.put((float)ay);
@@ -1510,7 +1523,7 @@ struct SimT {
                         out.put(has ? (float)rx : 0.0f);
                         out.put(has ? (float)ry : 0.0f);
                         out.put(has ? (float)sqrt(rx * rx + ry * ry) : 0.0f);
-                        if (team) out.put(has && c.team[(int)(m & 15u)] == c.team[t] ? 1.0f : 0.0f);
+                        if (team) out.put(has && cfg_team((int)(m & 15u)) == cfg_team(t) ? 1.0f : 0.0f);
                     }
                 };
                 // two register sets used alternately (a register move of an in-flight load would wait for it)
@@ -1532,7 +1545,7 @@ struct SimT {
                 out.put((float)x); out.put((float)y); out.put((float)rx); out.put((float)ry);
                 out.put((float)sqrt(rx * rx + ry * ry));
                 emit_tank_common(out, i);
-                if (team) out.put(c.team[i] == c.team[t] ? 1.0f : 0.0f);
+                if (team) out.put(cfg_team(i) == cfg_team(t) ? 1.0f : 0.0f);
                 out.put(t_alive(i) ? 1.0f : 0.0f);
             }
             if (!cfg_maze()) {  // fixed map: the sink fills these columns from the block's template
@@ -1568,7 +1581,7 @@ struct SimT {
         for (int i = 0; i < cfg_n(); ++i) {
             TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
             TPACK(i) = st.tpack[G(i)]; TSHOT(i) = st.tshot[G(i)];
-            if (c.ctrl[i] == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
+            if (cfg_ctrl(i) == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
             if (TPACK(i) & TP_ALIVE) alive_bits |= 1u << i;
         }
     }
@@ -1586,7 +1599,7 @@ struct SimT {
         for (int i = 0; i < cfg_n(); ++i) {
             st.tx[G(i)] = TX(i); st.ty[G(i)] = TY(i); st.trew[G(i)] = TREW(i);
             st.tpack[G(i)] = TPACK(i); st.tshot[G(i)] = TSHOT(i);
-            if (c.ctrl[i] == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
+            if (cfg_ctrl(i) == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
         }
     }
 };

@@ -79,7 +79,8 @@ static void rows_from_state(em_env *env, int64_t e, float *img) {
     else jobs(ShapeTag<0, 0, -1>{});
 }
 
-static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
+template <int SPEC>
+static void run_t(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
                 uint8_t *done) {
     const KCfg &c = env->k;
     const DevState &st = env->st;
@@ -88,7 +89,7 @@ static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t
         for (int tid = 0; tid < BS; ++tid) {
             const int64_t e = b0 + tid;
             if (e >= st.N) continue;
-            Sim s(c, st, env->bm, e, tid);
+            SimT<SPEC> s(c, st, env->bm, e, tid);
             bool emit = false;
             if (is_step) {
                 s.load();
@@ -116,6 +117,17 @@ static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t
             }
         }
     }
+}
+
+// steps run on the same SimT<SPEC> specialisation the library would pick for the config (resets: the generic build)
+static int g_spec_cap = 3;
+static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
+                uint8_t *done) {
+    const int spec = is_step ? sim_spec_for(env->k, g_spec_cap) : 0;
+    if (spec == 3) run_t<3>(env, is_step, actions, mask, obs, rewards, done);
+    else if (spec == 2) run_t<2>(env, is_step, actions, mask, obs, rewards, done);
+    else if (spec == 1) run_t<1>(env, is_step, actions, mask, obs, rewards, done);
+    else run_t<0>(env, is_step, actions, mask, obs, rewards, done);
 }
 
 extern "C" {
@@ -167,6 +179,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
 }
 void em_destroy(em_env *env) { delete env; }
 void em_set_rows_mode(int m) { g_rows_mode = m; }
+void em_set_spec_cap(int cap) { g_spec_cap = cap; }
 int em_obs_dim(em_env *env) { return env->k.obs_dim; }
 int em_obs_rows(em_env *env) { return env->k.rows; }
 int em_action_rows(em_env *env) { return env->k.act_rows; }

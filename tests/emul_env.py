@@ -36,6 +36,7 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.em_reset.argtypes = [vp, vp, vp]
         L.em_set_rows_mode.argtypes = [i32]
+        L.em_set_spec_cap.argtypes = [i32]
         L.em_step.argtypes = [vp, vp, vp, vp, vp]
         L.em_get_state.argtypes = [vp, i64, vp]
         L.em_set_state.argtypes = [vp, i64, vp]

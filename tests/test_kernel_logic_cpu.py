@@ -203,3 +203,28 @@ def test_squared_distance_thresholds_are_exact():
             else:
                 assert (math.sqrt(s) < thr) == (s < s0), s.hex()
             s = math.nextafter(s, math.inf)
+
+
+@pytest.mark.parametrize("cap", [0, 1, 2, 3])
+def test_simulation_specialisations_agree(cap):
+    """SimT<SPEC> (csrc/at_sim.h): the compile-time specialisations of the simulation kernel (team mode + smart bots +
+    fixed map; + four tanks; + the 2a_vs_2b layout) against the oracle on the configs that select them - capped at
+    every level, so each specialisation and the generic build run the same 2a_vs_2b batch."""
+    specs = [SWEEP["team_vs_bot"],
+             _spec("team", [("A", "agent", None), ("B", "bot", "smart"), ("B", "bot", "smart"), ("A", "agent", None)]),   # SPEC 2
+             _spec("team", [("A", "agent", None), ("B", "bot", "smart"), ("C", "bot", "smart")], "battlefield")]        # SPEC 1
+    emul_env.lib().em_set_spec_cap(cap)
+    try:
+        for spec in specs:
+            N, seed, base = 70, 5, 300
+            a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
+            b = emul_env.make_emul_env(spec, N, seed, base, auto_reset=True)
+            assert np.array_equal(a.reset(), b.reset())
+            ids = np.arange(base, base + N)
+            for t in range(260):
+                acts = synthetic_actions(seed, ids, t, a.A)
+                oa, ra, da = a.step(acts, threads=4)
+                ob, rb, db = b.step(acts)
+                assert np.array_equal(da, db) and np.array_equal(ra, rb) and np.array_equal(oa, ob), (cap, t)
+    finally:
+        emul_env.lib().em_set_spec_cap(3)
