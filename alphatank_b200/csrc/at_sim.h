@@ -359,7 +359,8 @@ struct SimT {
     const KCfg &c;
     const DevState &st;
     const BlockMem &bm;
-    int64_t e;  // env index into the SoA arrays
+    int e;      // env index into the SoA arrays (32-bit column indices: at_create caps the handle at 2^31 / 48 envs)
+    int n32;    // st.N
     int tid;    // slot in the block working set
     uint32_t cnt, rng, tick, tstep, epstep, zones;
     uint64_t wlo, whi, nlo, nhi;
@@ -370,7 +371,7 @@ struct SimT {
     bool acts_shared;      // device: action rows staged cooperatively by the whole (full) warp
 
     AT_HD SimT(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
-        : c(c_), st(st_), bm(bm_), e(e_), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
+        : c(c_), st(st_), bm(bm_), e((int)e_), n32((int)st_.N), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
           whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0), warp_mask(0xffffffffu), acts_shared(false) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
@@ -398,7 +399,7 @@ struct SimT {
     AT_HD uint32_t &BPACK(int i) const { return bm.bpack[cfg_bot_ord(i) * BS + tid]; }
     AT_HD double &BF0(int i) const { return bm.bf0[cfg_bot_ord(i) * BS + tid]; }
     AT_HD double &BF1(int i) const { return bm.bf1[cfg_bot_ord(i) * BS + tid]; }
-    AT_HD int64_t G(int slot) const { return (int64_t)slot * st.N + e; }
+    AT_HD int G(int slot) const { return slot * n32 + e; }
 
     AT_HD int t_angle(int i) const { return (int)(TPACK(i) & 511u); }
     AT_HD int t_speed(int i) const {
