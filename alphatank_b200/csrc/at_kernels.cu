@@ -864,6 +864,107 @@ __global__ void __launch_bounds__(256) sample_heads_kernel(const SampleHeads h, 
     }
 }
 
+// The tail of a policy's inference pass (models/ppo_utils.py:31-62: per network Linear(128, 128) -> Tanh -> Linear(128,
+// out), then Categorical(logits).sample() / log_prob per head and the critic's value) as ONE pass over the second
+// layers' pre-activations: tanh, the 4 small output layers (128 x {1, 3, 3, 2}), log-softmax, Gumbel-max draw, chosen
+// log-probability.  Half a warp per row, the 9 dot products reduced with shuffles.  Replaces 8 tanh kernels, 8 skinny GEMMs / GEMVs and the
+// sampling kernel per policy and tick.
+struct PolicyTail {
+    const float *z2[4];     // [n_rows][128] pre-activations of layer two: critic, head 0, head 1, head 2
+    const float *w3;        // [9][128] output-layer rows in that order (critic; 3 + 3 + 2 logits)
+    const float *b3;        // [9]
+};
+// tanh(x) = 1 - 2 / (exp(2x) + 1) with the hardware exponential and reciprocal: ~1e-6 absolute error (the GEMMs in
+// front of it run in TF32, ~1e-3 relative), a quarter of the instructions of tanhf
+__device__ __forceinline__ float fast_tanh(float x) {
+    const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+    return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+__global__ void __launch_bounds__(256) policy_tail_kernel(const PolicyTail p, int64_t n_rows, uint64_t seed,
+                                                          const int64_t *__restrict__ d_counter, uint32_t stream_id,
+                                                          int32_t *__restrict__ actions, int64_t act_stride,
+                                                          float *__restrict__ logprobs, int64_t lp_stride,
+                                                          float *__restrict__ values, int64_t val_stride) {
+    // half a warp per row: lane h (0..15) holds elements 8h .. 8h+7 of each network's 128-vector (two 16-byte loads
+    // per network, eight in flight); the 9 dot products of both rows are reduced together with 4 shuffle levels
+    __shared__ float4 w_s[9][32];
+    __shared__ float b_s[9];
+    for (int i = threadIdx.x; i < 9 * 32; i += blockDim.x) w_s[i / 32][i % 32] = reinterpret_cast<const float4 *>(p.w3)[i];
+    if (threadIdx.x < 9) b_s[threadIdx.x] = p.b3[threadIdx.x];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, h = lane & 15;
+    const int64_t hw0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4, nhw = ((int64_t)gridDim.x * blockDim.x) >> 4;
+    const uint64_t ctr = d_counter ? (uint64_t)*d_counter : 0ull;
+    constexpr int first[4] = {0, 1, 4, 7}, dims[4] = {1, 3, 3, 2};
+    const int64_t rounds = (n_rows + nhw - 1) / nhw;   // (uniform trip count: the shuffles need the whole warp)
+    for (int64_t it = 0; it < rounds; ++it) {
+        const int64_t row = hw0 + it * nhw;
+        const bool in = row < n_rows;
+        float4 v[4][2];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+                v[k][q] = in ? __ldcs(reinterpret_cast<const float4 *>(p.z2[k] + row * 128) + 2 * h + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float out[9];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float t[8] = {fast_tanh(v[k][0].x), fast_tanh(v[k][0].y), fast_tanh(v[k][0].z), fast_tanh(v[k][0].w),
+                          fast_tanh(v[k][1].x), fast_tanh(v[k][1].y), fast_tanh(v[k][1].z), fast_tanh(v[k][1].w)};
+#pragma unroll
+            for (int j = 0; j < dims[k]; ++j) {
+                const float4 w0 = w_s[first[k] + j][2 * h], w1 = w_s[first[k] + j][2 * h + 1];
+                out[first[k] + j] = ((t[0] * w0.x + t[1] * w0.y) + (t[2] * w0.z + t[3] * w0.w)) +
+                                    ((t[4] * w1.x + t[5] * w1.y) + (t[6] * w1.z + t[7] * w1.w));
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 9; ++j) {
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) out[j] += __shfl_xor_sync(0xffffffffu, out[j], d);
+            out[j] += b_s[j];
+        }
+        if (h == 0 && in) {
+            values[row * val_stride] = out[0];
+            uint32_t u[8];
+            for (int b = 0; b < 2; ++b) {
+                uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)b << 31), cc = (uint32_t)ctr,
+                         c3 = (uint32_t)(ctr >> 32) ^ (stream_id * 0x9E3779B9u);
+                philox4x32_10(c0, c1, cc, c3, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32));
+                u[4 * b] = c0; u[4 * b + 1] = c1; u[4 * b + 2] = cc; u[4 * b + 3] = c3;
+            }
+            int draw = 0;
+#pragma unroll
+            for (int k = 1; k < 4; ++k) {
+                const int d = dims[k];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < d) mx = fmaxf(mx, out[first[k] + j]);
+                float se = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    if (j < d) se += expf(out[first[k] + j] - mx);
+                const float lse = mx + logf(se);
+                int best = 0;
+                float best_s = -INFINITY, best_lp = 0.f;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (j < d) {
+                        const float lp = out[first[k] + j] - lse;
+                        const float un = ((float)u[(draw + j) & 7] + 0.5f) * 2.3283064365386963e-10f;
+                        const float g = -logf(fmaxf(-logf(fminf(un, 0.99999994f)), 1e-20f));
+                        if (lp + g > best_s) { best_s = lp + g; best = j; best_lp = lp; }
+                    }
+                }
+                draw += d;
+                actions[row * act_stride + (k - 1)] = best;
+                logprobs[row * lp_stride + (k - 1)] = best_lp;
+            }
+        }
+    }
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------- host
@@ -1390,6 +1491,28 @@ int at_sample_heads(int device, const float *const *d_logits, const int *dims, i
     CUDA_TRY(cudaSetDevice(device));
     sample_heads_kernel<<<(int)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, n_rows, seed, d_counter, stream_id,
                                                                                    d_actions, act_stride, d_logprobs, lp_stride);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_policy_tail(int device, const float *const *d_z2, const float *d_w3, const float *d_b3, int64_t n_rows, uint64_t seed,
+                   const int64_t *d_counter, uint32_t stream_id, int32_t *d_actions, int64_t act_stride, float *d_logprobs,
+                   int64_t lp_stride, float *d_values, int64_t val_stride, void *stream) {
+    if (!d_z2 || !d_w3 || !d_b3 || n_rows <= 0 || !d_actions || !d_logprobs || !d_values)
+        return fail(AT_ERR_ARG, "at_policy_tail: bad argument");
+    PolicyTail p;
+    for (int k = 0; k < 4; ++k) {
+        if (!d_z2[k] || (((uintptr_t)d_z2[k]) & 15u)) return fail(AT_ERR_ARG, "at_policy_tail: layer-two buffers must be 16-byte aligned");
+        p.z2[k] = d_z2[k];
+    }
+    if (((uintptr_t)d_w3) & 15u) return fail(AT_ERR_ARG, "at_policy_tail: the output-layer matrix must be 16-byte aligned");
+    p.w3 = d_w3;
+    p.b3 = d_b3;
+    CUDA_TRY(cudaSetDevice(device));
+    int64_t blocks = (n_rows * 16 + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    policy_tail_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
+                                                                   d_logprobs, lp_stride, d_values, val_stride);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
 }

@@ -135,9 +135,11 @@ class PPOLearner:
             if getattr(self, "_sample_ctr", None) is None:
                 self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
             self._sample_ctr.add_(1)
-            vals = [agent.sample_cuda(obs_nad[:, i], acts[:, i], lps[:, i], self._sample_ctr, self.seed, i + self.A * _rank()).squeeze(-1)
-                    for i, agent in enumerate(self.agents)]
-            return acts, lps, torch.stack(vals, dim=1)
+            vals = torch.empty((n, self.A), dtype=torch.float32, device=obs_nad.device)
+            for i, agent in enumerate(self.agents):
+                agent.sample_cuda(obs_nad[:, i], acts[:, i], lps[:, i], self._sample_ctr, self.seed, i + self.A * _rank(),
+                                  values_out=vals[:, i])
+            return acts, lps, vals
         acts, lps, vals = [], [], []
         for i, agent in enumerate(self.agents):
             a, lp, v = agent.sample(obs_nad[:, i])

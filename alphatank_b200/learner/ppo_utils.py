@@ -112,26 +112,50 @@ class PPOAgentPPO(nn.Module):
         return torch.stack(acts, dim=-1), torch.stack(lps, dim=-1), value
 
     @torch.no_grad()
-    def sample_cuda(self, x, actions_out, logprobs_out, counter, seed=0, stream_id=0):
-        """CUDA path of ``sample``: the fused forward, then ONE kernel (csrc: sample_heads_kernel through at_sample_heads)
-        for log-softmax + Gumbel-max draw + chosen log-probability of all heads, written straight into
-        ``actions_out`` int32 [N, heads] / ``logprobs_out`` float32 [N, heads] (may be column slices of [N, A, heads]
-        tensors).  ``counter``: device int64 tensor [1] the caller advances once per tick.  Returns the value [N, 1]."""
+    def sample_cuda(self, x, actions_out, logprobs_out, counter, seed=0, stream_id=0, values_out=None):
+        """CUDA path of ``sample``, written straight into ``actions_out`` int32 [N, heads] / ``logprobs_out`` float32
+        [N, heads] / ``values_out`` float32 [N] (may be column slices of [N, A, ...] tensors).  ``counter``: device int64
+        tensor [1] the caller advances once per tick.  Returns the value [N, 1].
+
+        Reference architecture (act_dim (3, 3, 2), 128 hidden units): the first layers as one GEMM, the second layers'
+        pre-activations as four GEMMs on column slices, then ONE kernel (csrc: policy_tail_kernel through
+        at_policy_tail) for tanh + the four output layers + log-softmax + Gumbel-max draw + chosen log-probability.
+        Anything else: the fused forward, then at_sample_heads."""
         import ctypes as C
 
         from .. import _capi
+        n = x.shape[0]
+        nets = [self.critic] + list(self.actor)
+        stream = C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+        assert actions_out.dtype == torch.int32 and logprobs_out.dtype == torch.float32
+        assert actions_out.stride(-1) == 1 and logprobs_out.stride(-1) == 1
+        if [int(m[4].out_features) for m in nets] == [1, 3, 3, 2] and all(m[2].out_features == 128 for m in nets):
+            w1 = torch.cat([m[0].weight for m in nets], dim=0)                      # [512, D]
+            b1 = torch.cat([m[0].bias for m in nets], dim=0)
+            h1 = torch.addmm(b1, x, w1.t()).tanh_()                                 # [N, 512]
+            z2 = [torch.addmm(m[2].bias, h1[:, 128 * k:128 * (k + 1)], m[2].weight.t()) for k, m in enumerate(nets)]
+            w3 = torch.cat([m[4].weight for m in nets], dim=0).contiguous()         # [9, 128]
+            b3 = torch.cat([m[4].bias for m in nets], dim=0).contiguous()
+            value = torch.empty((n, 1), dtype=torch.float32, device=x.device) if values_out is None else values_out
+            ptrs = (C.c_void_p * 4)(*[z.data_ptr() for z in z2])
+            _capi.check(_capi.lib().at_policy_tail(
+                x.device.index, C.cast(ptrs, C.c_void_p), C.c_void_p(w3.data_ptr()), C.c_void_p(b3.data_ptr()), n, int(seed),
+                C.c_void_p(counter.data_ptr()), int(stream_id), C.c_void_p(actions_out.data_ptr()), actions_out.stride(0),
+                C.c_void_p(logprobs_out.data_ptr()), logprobs_out.stride(0), C.c_void_p(value.data_ptr()), value.stride(0),
+                stream), "at_policy_tail")
+            return value.view(n, 1) if values_out is None else value
         logits, value = self.fused_logits_and_value(x)
         logits = [l.contiguous() for l in logits]
         nh = len(logits)
-        assert actions_out.dtype == torch.int32 and logprobs_out.dtype == torch.float32
-        assert actions_out.stride(-1) == 1 and logprobs_out.stride(-1) == 1
         ptrs = (C.c_void_p * nh)(*[l.data_ptr() for l in logits])
         dims = (C.c_int32 * nh)(*[int(l.shape[-1]) for l in logits])
         _capi.check(_capi.lib().at_sample_heads(
-            x.device.index, C.cast(ptrs, C.c_void_p), C.cast(dims, C.c_void_p), nh, x.shape[0], int(seed),
+            x.device.index, C.cast(ptrs, C.c_void_p), C.cast(dims, C.c_void_p), nh, n, int(seed),
             C.c_void_p(counter.data_ptr()), int(stream_id), C.c_void_p(actions_out.data_ptr()), actions_out.stride(0),
-            C.c_void_p(logprobs_out.data_ptr()), logprobs_out.stride(0),
-            C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)), "at_sample_heads")
+            C.c_void_p(logprobs_out.data_ptr()), logprobs_out.stride(0), stream), "at_sample_heads")
+        if values_out is not None:
+            values_out.copy_(value.view(values_out.shape))
+            return values_out
         return value
 
     def get_action_and_value(self, x, action=None):

@@ -180,6 +180,15 @@ int at_sample_heads(int device, const float *const *d_logits, const int *dims, i
                     const int64_t *d_counter, uint32_t stream_id, int32_t *d_actions, int64_t act_stride,
                     float *d_logprobs, int64_t lp_stride, void *stream);
 
+/* The tail of one policy's inference pass (models/ppo_utils.py:31-62, act_dim [3, 3, 2]) in one kernel: d_z2[k] =
+ * float[n_rows][128] pre-activations of the second Linear of the critic (k = 0) and of the three actor heads; d_w3 =
+ * float[9][128] / d_b3 = float[9] the output layers' rows (critic, 3 + 3 + 2 logits).  tanh, output layers, then as
+ * at_sample_heads: actions -> d_actions[row * act_stride + head], log-probabilities -> d_logprobs[row * lp_stride +
+ * head], and the critic's value -> d_values[row * val_stride]. */
+int at_policy_tail(int device, const float *const *d_z2, const float *d_w3, const float *d_b3, int64_t n_rows, uint64_t seed,
+                   const int64_t *d_counter, uint32_t stream_id, int32_t *d_actions, int64_t act_stride, float *d_logprobs,
+                   int64_t lp_stride, float *d_values, int64_t val_stride, void *stream);
+
 /* Host copies of the device lookup tables (tests): cos/sin of math.radians(a), a = 0..360 -> double[361][2];
  * pygame Vector2.rotate corner offsets -> double[361][4]. */
 int at_get_luts(const at_env *env, double *h_trig, double *h_corner);

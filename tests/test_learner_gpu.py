@@ -134,15 +134,25 @@ def test_sample_heads_kernel_is_a_categorical_sampler():
     acts = torch.full((N, 2, 3), -1, dtype=torch.int32, device=dev)
     lps = torch.zeros((N, 2, 3), dtype=torch.float32, device=dev)
     ctr = torch.ones(1, dtype=torch.int64, device=dev)
-    v = agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)
+    v = agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)       # reference shape: at_policy_tail
     assert (acts[:, 0] == -1).all() and v.shape == (N, 1)                  # strided output: the other agent's columns untouched
     logits, value = agent.fused_logits_and_value(x)
-    assert torch.allclose(v, value)
+    assert torch.allclose(v, value, rtol=1e-4, atol=1e-5)
+    vals = torch.zeros((N, 2), device=dev)
+    agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0, values_out=vals[:, 1])
+    assert torch.allclose(vals[:, 1:2], value, rtol=1e-4, atol=1e-5) and (vals[:, 0] == 0).all()
+    other = PPOAgentPPO(24, act_dim=(2, 4)).to(dev)                        # any other shape: at_sample_heads
+    a2 = torch.full((1000, 2), -1, dtype=torch.int32, device=dev)
+    l2 = torch.zeros((1000, 2), device=dev)
+    other.sample_cuda(x[:1000], a2, l2, ctr, seed=5)
+    lg2, _ = other.fused_logits_and_value(x[:1000])
+    for h, l in enumerate(lg2):
+        assert torch.allclose(l2[:, h], torch.log_softmax(l, -1).gather(-1, a2[:, h].long().unsqueeze(-1)).squeeze(-1), atol=1e-5)
     for h, l in enumerate(logits):
         lp = torch.log_softmax(l, dim=-1)
         a = acts[:, 1, h].long()
         assert int(a.min()) >= 0 and int(a.max()) < l.shape[1]
-        assert torch.allclose(lps[:, 1, h], lp.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=1e-5)
+        assert torch.allclose(lps[:, 1, h], lp.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=2e-5)
         p = torch.softmax(l[0], dim=-1).double().cpu()
         freq = torch.bincount(a, minlength=l.shape[1]).double().cpu() / N
         assert ((freq - p).abs() < 4 * (p * (1 - p) / N).sqrt() + 1e-4).all(), (freq, p)
