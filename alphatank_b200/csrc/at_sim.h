@@ -520,16 +520,10 @@ struct SimT {
             double u0, u1;
             unit_dir(ang, u0, u1);
             const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
-            for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies
-                const int i = ffs32(bits);
-                const double tx = TX(i) - x, ty = TY(i) - y;
-                // dodge_reward candidate: the tank moves <= 10 px and this bullet <= 1 px per axis before that test
-                if (fabs(tx) < 113.0 && fabs(ty) < 113.0) near_tanks |= 1u << i;
-                if (fabs(tx) > 301.0 || fabs(ty) > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
-                const double s2 = np_dot2(tx, ty, tx, ty);
-                if (s2 > S300) continue;                              // dist > BULLET_MAX_DISTANCE
+            // one enemy: s2 = |t|^2 and q = d . t are taken by reference so that the caller decides when they are computed
+            auto enemy = [&](int i, double tx, double ty, double s2, double q) {
                 // cos > 0.9 <=> q > 0 and q^2 > 0.81 s2 ; cos < 0.1 <=> q <= 0 or q^2 < 0.01 s2   (q = d . t)
-                const double q = d0 * tx + d1 * ty, q2 = q * q, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
+                const double q2 = q * q, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
                 bool hi, lo;
                 if (s2 > 0.0 && !(q > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps))) {
                     hi = q > 0.0 && q2 > a81;
@@ -543,6 +537,35 @@ struct SimT {
                 if (hi) TREW(owner) += 0.01;
                 else if (lo) { if (!cleared) ++pcnt; }
                 if (s2 < S100) { pcnt = 0; cleared = true; }          // dist < DISTANCE_CANCEL_THRESHOLD
+            };
+            if (SPEC == 3) {   // exactly two enemies (tanks 2, 3 or 0, 1): their geometry is computed side by side
+                const int e0 = (owner & 2) ^ 2;
+                double txv[2], tyv[2], s2v[2], qv[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    txv[j] = TX(e0 + j) - x; tyv[j] = TY(e0 + j) - y;
+                    s2v[j] = np_dot2(txv[j], tyv[j], txv[j], tyv[j]);
+                    qv[j] = d0 * txv[j] + d1 * tyv[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const int i = e0 + j;
+                    if (!((alive_bits >> i) & 1u)) continue;
+                    if (fabs(txv[j]) < 113.0 && fabs(tyv[j]) < 113.0) near_tanks |= 1u << i;
+                    if (fabs(txv[j]) > 301.0 || fabs(tyv[j]) > 301.0 || s2v[j] > S300) continue;
+                    enemy(i, txv[j], tyv[j], s2v[j], qv[j]);
+                }
+            } else {
+                for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies
+                    const int i = ffs32(bits);
+                    const double tx = TX(i) - x, ty = TY(i) - y;
+                    // dodge_reward candidate: the tank moves <= 10 px and this bullet <= 1 px per axis before that test
+                    if (fabs(tx) < 113.0 && fabs(ty) < 113.0) near_tanks |= 1u << i;
+                    if (fabs(tx) > 301.0 || fabs(ty) > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
+                    const double s2 = np_dot2(tx, ty, tx, ty);
+                    if (s2 > S300) continue;                              // dist > BULLET_MAX_DISTANCE
+                    enemy(i, tx, ty, s2, d0 * tx + d1 * ty);
+                }
             }
         }
         bool nfx = fx, nfy = fy;
