@@ -342,3 +342,35 @@ def test_step_norm_equals_step_then_tick_normalize(name):
             if not torch.equal(got, want):
                 bad = (got != want).nonzero()[:6].tolist()
                 raise AssertionError("%s tick %d normalised rows differ at (env, col) %s" % (name, t, bad))
+
+
+@pytest.mark.parametrize("cap", ["1", "2", "3"])
+def test_simulation_specialisations_equal_the_generic_kernel(cap):
+    """env_kernel<true, false, SPEC>: the simulation kernel compiled for a config class (SimT<SPEC>: team mode + smart
+    bots + fixed map; + four tanks; + the 2a_vs_2b layout) against lower levels selected with AT_NO_SPEC (1: the
+    generic kernel, 2: SPEC 1, 3: SPEC 2) - same state, rewards, done flags and rows, through auto-resets."""
+    spec = SWEEP["team_vs_bot"]
+    N, seed, base = 1500, 17, 64
+    old = os.environ.get("AT_NO_SPEC")
+    try:
+        os.environ.pop("AT_NO_SPEC", None)
+        a = _gpu(spec, N, seed, base, auto_reset=True)           # SPEC 3
+        os.environ["AT_NO_SPEC"] = cap
+        b = _gpu(spec, N, seed, base, auto_reset=True)
+    finally:
+        if old is None:
+            os.environ.pop("AT_NO_SPEC", None)
+        else:
+            os.environ["AT_NO_SPEC"] = old
+    assert np.array_equal(a.reset(), b.reset())
+    ids = np.arange(base, base + N)
+    for t in range(300):
+        acts = synthetic_actions(seed, ids, t, a.A)
+        oa, ra, da = a.step(acts)
+        ob, rb, db = b.step(acts)
+        assert np.array_equal(da, db) and np.array_equal(ra, rb) and np.array_equal(oa, ob), "tick %d" % t
+    sa, sb = a.get_state(), b.get_state()
+    for f in ("n_bullets", "tick", "training_step", "episode_steps", "rng_ctr", "zones"):
+        assert np.array_equal(sa[f], sb[f]), f
+    for f in ("x", "y", "reward", "angle", "alive", "num_hit", "num_be_hit"):
+        assert np.array_equal(sa["tanks"][f][:, :4], sb["tanks"][f][:, :4]), f
