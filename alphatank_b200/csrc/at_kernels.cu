@@ -965,6 +965,179 @@ __global__ void __launch_bounds__(256) policy_tail_kernel(const PolicyTail p, in
     }
 }
 
+// The middle of a policy's inference pass on the tensor cores: for network k (blockIdx.y: critic, three actor heads)
+//   out9[row][first_k ..] = W3_k . tanh(W2_k . tanh(z1[row][128 k .. 128 k + 128)) + b2_k) + b3_k
+// i.e. tanh of the first layers' pre-activations, the second layers (4 x 128 x 128, TF32 mma.sync m16n8k8 with fp32
+// accumulation - the precision of the cuBLAS TF32 GEMMs it replaces), their tanh and the tiny output layers, without
+// the [N, 512] activations ever going back to HBM.  A block keeps W2_k in shared memory (padded: conflict-free
+// fragment loads) and streams 64-row tiles of z1 through it; warp w owns rows 16 w .. 16 w + 15 of the tile.
+constexpr int PM_ROWS = 64, PM_LD = 132;
+struct PolicyMid {
+    const float *z1;   // [n_rows][512] pre-activations of the four first layers (bias included)
+    const float *w2;   // [4][128 out][128 in]
+    const float *b2;   // [4][128]
+    const float *w3;   // [9][128] (critic; 3 + 3 + 2 logits)
+    const float *b3;   // [9]
+    float *out9;       // [n_rows][9]
+};
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
+    return r;
+}
+__global__ void __launch_bounds__(128, 2) policy_mid_kernel(const PolicyMid p, int64_t n_rows) {
+    extern __shared__ __align__(16) unsigned char pm_smem[];
+    uint32_t *Ws = (uint32_t *)pm_smem;                 // [128 n][PM_LD]  tf32 bits of W2_k[n][k]
+    uint32_t *As = Ws + 128 * PM_LD;                    // [64 rows][PM_LD] tf32 bits of tanh(z1)
+    float *b2s = (float *)(As + PM_ROWS * PM_LD);       // [128]
+    float *w3s = b2s + 128;                             // [3][128]
+    const int k = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
+    const int first = k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 4 : 7)), nout = k == 0 ? 1 : (k == 3 ? 2 : 3);
+    for (int i = tid; i < 128 * 32; i += 128) {         // W2_k, 16 bytes at a time
+        const int n = i >> 5, c4 = (i & 31) * 4;
+        const float4 w = __ldg(reinterpret_cast<const float4 *>(p.w2 + ((int64_t)k * 128 + n) * 128 + c4));
+        uint32_t *d = Ws + n * PM_LD + c4;
+        d[0] = to_tf32(w.x); d[1] = to_tf32(w.y); d[2] = to_tf32(w.z); d[3] = to_tf32(w.w);
+    }
+    b2s[tid] = __ldg(p.b2 + k * 128 + tid);
+    for (int j = 0; j < 3; ++j) w3s[j * 128 + tid] = j < nout ? __ldg(p.w3 + (first + j) * 128 + tid) : 0.f;
+    const float b3v[3] = {__ldg(p.b3 + first), nout > 1 ? __ldg(p.b3 + first + 1) : 0.f, nout > 2 ? __ldg(p.b3 + first + 2) : 0.f};
+    const int64_t n_tiles = (n_rows + PM_ROWS - 1) / PM_ROWS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t row0 = tile * PM_ROWS;
+        __syncthreads();                                 // (first pass: the tables; later: everybody is done with As)
+        {   // the tile's slice of z1 -> tanh -> tf32: all 16 loads of a thread are in flight before the first is used
+            float4 v[PM_ROWS * 32 / 128];
+#pragma unroll
+            for (int q = 0; q < PM_ROWS * 32 / 128; ++q) {
+                const int i = tid + q * 128, r = i >> 5, c4 = (i & 31) * 4;
+                v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (row0 + r < n_rows) v[q] = __ldcs(reinterpret_cast<const float4 *>(p.z1 + (row0 + r) * 512 + k * 128 + c4));
+            }
+            const int64_t next0 = row0 + (int64_t)gridDim.x * PM_ROWS;   // the block's next tile -> L2
+#pragma unroll
+            for (int q = 0; q < PM_ROWS * 32 / 128; q += 2) {            // (one prefetch per 32-byte sector pair is plenty)
+                const int i = tid + q * 128, r = i >> 5, c4 = (i & 31) * 4;
+                if (next0 + r < n_rows) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.z1 + (next0 + r) * 512 + k * 128 + c4));
+            }
+#pragma unroll
+            for (int q = 0; q < PM_ROWS * 32 / 128; ++q) {
+                const int i = tid + q * 128, r = i >> 5, c4 = (i & 31) * 4;
+                uint4 t;
+                t.x = to_tf32(fast_tanh(v[q].x)); t.y = to_tf32(fast_tanh(v[q].y)); t.z = to_tf32(fast_tanh(v[q].z)); t.w = to_tf32(fast_tanh(v[q].w));
+                *reinterpret_cast<uint4 *>(As + r * PM_LD + c4) = t;
+            }
+        }
+        __syncthreads();
+        float acc[16][4];
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+        // fragments by ldmatrix: a tf32 8 x 4 block is an 8 x 8 b16 matrix (row = 16 bytes), and thread (gid, tig) of
+        // an ldmatrix result holds row gid, 32-bit column tig - exactly the m16n8k8 A (row, k) / B (n, k) fragment order.
+        // lane l supplies the row address of matrix l / 8: A = {rows 0-7 | 8-15} x {k 0-3 | 4-7}, B = two n-tiles x {k 0-3 | 4-7}
+        const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(As + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PM_LD + (lane >> 4) * 4);
+        const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(Ws + ((lane & 7) + (lane >> 4) * 8) * PM_LD + ((lane >> 3) & 1) * 4);
+#pragma unroll 2
+        for (int ks = 0; ks < 16; ++ks) {
+            uint32_t a0, a1, a2, a3;
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_addr + ks * 32));
+#pragma unroll
+            for (int np = 0; np < 8; ++np) {   // two n-tiles per ldmatrix
+                uint32_t b0, b1, b2, b3;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+                             : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(b_addr + (np * 16 * PM_LD + ks * 8) * 4));
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                             : "+f"(acc[2 * np][0]), "+f"(acc[2 * np][1]), "+f"(acc[2 * np][2]), "+f"(acc[2 * np][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                             : "+f"(acc[2 * np + 1][0]), "+f"(acc[2 * np + 1][1]), "+f"(acc[2 * np + 1][2]), "+f"(acc[2 * np + 1][3])
+                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b2), "r"(b3));
+            }
+        }
+        // epilogue: this thread holds columns nt * 8 + 2 tig (+1) of rows gid (acc[.][0..1]) and gid + 8 (acc[.][2..3])
+        float o_lo[3] = {0.f, 0.f, 0.f}, o_hi[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < 16; ++nt) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const int col = nt * 8 + 2 * tig + q;
+                const float bb = b2s[col];
+                const float h_lo = fast_tanh(acc[nt][q] + bb), h_hi = fast_tanh(acc[nt][2 + q] + bb);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float w = w3s[j * 128 + col];
+                    o_lo[j] += h_lo * w;
+                    o_hi[j] += h_hi * w;
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            o_lo[j] += __shfl_xor_sync(0xffffffffu, o_lo[j], 1); o_lo[j] += __shfl_xor_sync(0xffffffffu, o_lo[j], 2);
+            o_hi[j] += __shfl_xor_sync(0xffffffffu, o_hi[j], 1); o_hi[j] += __shfl_xor_sync(0xffffffffu, o_hi[j], 2);
+        }
+        if (tig == 0) {
+            const int64_t r_lo = row0 + warp * 16 + gid, r_hi = r_lo + 8;
+            for (int j = 0; j < nout; ++j) {
+                if (r_lo < n_rows) p.out9[r_lo * 9 + first + j] = o_lo[j] + b3v[j];
+                if (r_hi < n_rows) p.out9[r_hi * 9 + first + j] = o_hi[j] + b3v[j];
+            }
+        }
+    }
+}
+
+// sampling from the [n_rows][9] outputs of policy_mid_kernel (value, 3 + 3 + 2 logits): as sample_heads_kernel
+__global__ void __launch_bounds__(256) sample_out9_kernel(const float *__restrict__ out9, int64_t n_rows, uint64_t seed,
+                                                          const int64_t *__restrict__ d_counter, uint32_t stream_id,
+                                                          int32_t *__restrict__ actions, int64_t act_stride,
+                                                          float *__restrict__ logprobs, int64_t lp_stride,
+                                                          float *__restrict__ values, int64_t val_stride) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const uint64_t ctr = d_counter ? (uint64_t)*d_counter : 0ull;
+    float out[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) out[j] = out9[row * 9 + j];
+    values[row * val_stride] = out[0];
+    uint32_t u[8];
+    for (int b = 0; b < 2; ++b) {
+        uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)b << 31), cc = (uint32_t)ctr,
+                 c3 = (uint32_t)(ctr >> 32) ^ (stream_id * 0x9E3779B9u);
+        philox4x32_10(c0, c1, cc, c3, (uint32_t)(seed & 0xFFFFFFFFu), (uint32_t)(seed >> 32));
+        u[4 * b] = c0; u[4 * b + 1] = c1; u[4 * b + 2] = cc; u[4 * b + 3] = c3;
+    }
+    constexpr int first[4] = {0, 1, 4, 7}, dims[4] = {1, 3, 3, 2};
+    int draw = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k) {
+        const int d = dims[k];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (j < d) mx = fmaxf(mx, out[first[k] + j]);
+        float se = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+            if (j < d) se += expf(out[first[k] + j] - mx);
+        const float lse = mx + logf(se);
+        int best = 0;
+        float best_s = -INFINITY, best_lp = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (j < d) {
+                const float lp = out[first[k] + j] - lse;
+                const float un = ((float)u[(draw + j) & 7] + 0.5f) * 2.3283064365386963e-10f;
+                const float g = -logf(fmaxf(-logf(fminf(un, 0.99999994f)), 1e-20f));
+                if (lp + g > best_s) { best_s = lp + g; best = j; best_lp = lp; }
+            }
+        }
+        draw += d;
+        actions[row * act_stride + (k - 1)] = best;
+        logprobs[row * lp_stride + (k - 1)] = best_lp;
+    }
+}
+
 }  // namespace
 
 // -------------------------------------------------------------------------------------------------- host
@@ -1513,6 +1686,33 @@ int at_policy_tail(int device, const float *const *d_z2, const float *d_w3, cons
     if (blocks > 148 * 16) blocks = 148 * 16;
     policy_tail_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
                                                                    d_logprobs, lp_stride, d_values, val_stride);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const float *d_b2, const float *d_w3, const float *d_b3,
+                       float *d_out9, int64_t n_rows, uint64_t seed, const int64_t *d_counter, uint32_t stream_id,
+                       int32_t *d_actions, int64_t act_stride, float *d_logprobs, int64_t lp_stride, float *d_values,
+                       int64_t val_stride, void *stream) {
+    if (!d_z1 || !d_w2 || !d_b2 || !d_w3 || !d_b3 || !d_out9 || n_rows <= 0 || !d_actions || !d_logprobs || !d_values)
+        return fail(AT_ERR_ARG, "at_policy_mid_tail: bad argument");
+    if ((((uintptr_t)d_z1) | ((uintptr_t)d_w2)) & 15u) return fail(AT_ERR_ARG, "at_policy_mid_tail: z1 / w2 must be 16-byte aligned");
+    CUDA_TRY(cudaSetDevice(device));
+    static bool attr_set[64] = {false};
+    const size_t smem = (size_t)(128 + PM_ROWS) * PM_LD * 4 + (128 + 3 * 128) * 4;
+    if (device < 64 && !attr_set[device]) {
+        CUDA_TRY(cudaFuncSetAttribute(policy_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[device] = true;
+    }
+    PolicyMid p = {d_z1, d_w2, d_b2, d_w3, d_b3, d_out9};
+    const int64_t n_tiles = (n_rows + PM_ROWS - 1) / PM_ROWS;
+    int gx = 74;                       // 74 x 4 networks = 296 blocks = 2 per SM
+    if (n_tiles < gx) gx = (int)n_tiles;
+    cudaStream_t s = (cudaStream_t)stream;
+    policy_mid_kernel<<<dim3(gx, 4), 128, smem, s>>>(p, n_rows);
+    CUDA_TRY(cudaGetLastError());
+    sample_out9_kernel<<<(int)((n_rows + 255) / 256), 256, 0, s>>>(d_out9, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
+                                                                  d_logprobs, lp_stride, d_values, val_stride);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
 }

@@ -3,6 +3,8 @@
 Module and parameter names are the reference's (``critic.{0,2,4}``, ``actor.{h}.{0,2,4}``), so a ``state_dict`` saved
 here loads into the reference's ``PPOAgentPPO`` / ``PPOAgentBot`` (inference.py:10-41, inference_multi.py:13-21) and
 vice versa - tests/test_learner_cpu.py pins the key / shape list recorded from the reference classes."""
+import os
+
 import torch
 import torch.nn as nn
 
@@ -132,11 +134,25 @@ class PPOAgentPPO(nn.Module):
         if [int(m[4].out_features) for m in nets] == [1, 3, 3, 2] and all(m[2].out_features == 128 for m in nets):
             w1 = torch.cat([m[0].weight for m in nets], dim=0)                      # [512, D]
             b1 = torch.cat([m[0].bias for m in nets], dim=0)
-            h1 = torch.addmm(b1, x, w1.t()).tanh_()                                 # [N, 512]
-            z2 = [torch.addmm(m[2].bias, h1[:, 128 * k:128 * (k + 1)], m[2].weight.t()) for k, m in enumerate(nets)]
             w3 = torch.cat([m[4].weight for m in nets], dim=0).contiguous()         # [9, 128]
             b3 = torch.cat([m[4].bias for m in nets], dim=0).contiguous()
             value = torch.empty((n, 1), dtype=torch.float32, device=x.device) if values_out is None else values_out
+            if all(m[0].out_features == 128 for m in nets) and not os.environ.get("AT_NO_POLICY_MID"):
+                # first layers by cuBLAS, everything behind them in two kernels (csrc: policy_mid_kernel - tanh, the
+                # second layers on the tensor cores, tanh, output layers - and sample_out9_kernel)
+                z1 = torch.addmm(b1, x, w1.t())                                     # [N, 512] pre-activations
+                w2 = torch.stack([m[2].weight for m in nets]).contiguous()          # [4, 128 out, 128 in]
+                b2 = torch.stack([m[2].bias for m in nets]).contiguous()
+                out9 = torch.empty((n, 9), dtype=torch.float32, device=x.device)
+                _capi.check(_capi.lib().at_policy_mid_tail(
+                    x.device.index, C.c_void_p(z1.data_ptr()), C.c_void_p(w2.data_ptr()), C.c_void_p(b2.data_ptr()),
+                    C.c_void_p(w3.data_ptr()), C.c_void_p(b3.data_ptr()), C.c_void_p(out9.data_ptr()), n, int(seed),
+                    C.c_void_p(counter.data_ptr()), int(stream_id), C.c_void_p(actions_out.data_ptr()), actions_out.stride(0),
+                    C.c_void_p(logprobs_out.data_ptr()), logprobs_out.stride(0), C.c_void_p(value.data_ptr()), value.stride(0),
+                    stream), "at_policy_mid_tail")
+                return value.view(n, 1) if values_out is None else value
+            h1 = torch.addmm(b1, x, w1.t()).tanh_()                                 # [N, 512]
+            z2 = [torch.addmm(m[2].bias, h1[:, 128 * k:128 * (k + 1)], m[2].weight.t()) for k, m in enumerate(nets)]
             ptrs = (C.c_void_p * 4)(*[z.data_ptr() for z in z2])
             _capi.check(_capi.lib().at_policy_tail(
                 x.device.index, C.cast(ptrs, C.c_void_p), C.c_void_p(w3.data_ptr()), C.c_void_p(b3.data_ptr()), n, int(seed),

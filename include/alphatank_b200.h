@@ -189,6 +189,16 @@ int at_policy_tail(int device, const float *const *d_z2, const float *d_w3, cons
                    const int64_t *d_counter, uint32_t stream_id, int32_t *d_actions, int64_t act_stride, float *d_logprobs,
                    int64_t lp_stride, float *d_values, int64_t val_stride, void *stream);
 
+/* Everything of one policy's inference pass behind its first layers (models/ppo_utils.py:31-62, act_dim [3, 3, 2], 128
+ * hidden units) in two kernels: d_z1 = float[n_rows][512] pre-activations of the four first layers (critic, three
+ * heads; bias included), d_w2 = float[4][128][128] / d_b2 = float[4][128] the second layers, d_w3 / d_b3 as in
+ * at_policy_tail, d_out9 = float[n_rows][9] scratch (value and logits on return).  tanh, the second layers on the
+ * tensor cores (TF32, fp32 accumulation), tanh, the output layers, then sampling as at_sample_heads. */
+int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const float *d_b2, const float *d_w3, const float *d_b3,
+                       float *d_out9, int64_t n_rows, uint64_t seed, const int64_t *d_counter, uint32_t stream_id,
+                       int32_t *d_actions, int64_t act_stride, float *d_logprobs, int64_t lp_stride, float *d_values,
+                       int64_t val_stride, void *stream);
+
 /* Host copies of the device lookup tables (tests): cos/sin of math.radians(a), a = 0..360 -> double[361][2];
  * pygame Vector2.rotate corner offsets -> double[361][4]. */
 int at_get_luts(const at_env *env, double *h_trig, double *h_corner);

@@ -137,10 +137,10 @@ def test_sample_heads_kernel_is_a_categorical_sampler():
     v = agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)       # reference shape: at_policy_tail
     assert (acts[:, 0] == -1).all() and v.shape == (N, 1)                  # strided output: the other agent's columns untouched
     logits, value = agent.fused_logits_and_value(x)
-    assert torch.allclose(v, value, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(v, value, rtol=2e-3, atol=2e-3)                   # (TF32 second layers in policy_mid_kernel)
     vals = torch.zeros((N, 2), device=dev)
     agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0, values_out=vals[:, 1])
-    assert torch.allclose(vals[:, 1:2], value, rtol=1e-4, atol=1e-5) and (vals[:, 0] == 0).all()
+    assert torch.allclose(vals[:, 1:2], value, rtol=2e-3, atol=2e-3) and (vals[:, 0] == 0).all()
     other = PPOAgentPPO(24, act_dim=(2, 4)).to(dev)                        # any other shape: at_sample_heads
     a2 = torch.full((1000, 2), -1, dtype=torch.int32, device=dev)
     l2 = torch.zeros((1000, 2), device=dev)
@@ -152,10 +152,10 @@ def test_sample_heads_kernel_is_a_categorical_sampler():
         lp = torch.log_softmax(l, dim=-1)
         a = acts[:, 1, h].long()
         assert int(a.min()) >= 0 and int(a.max()) < l.shape[1]
-        assert torch.allclose(lps[:, 1, h], lp.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=2e-5)
+        assert torch.allclose(lps[:, 1, h], lp.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=3e-3)
         p = torch.softmax(l[0], dim=-1).double().cpu()
         freq = torch.bincount(a, minlength=l.shape[1]).double().cpu() / N
-        assert ((freq - p).abs() < 4 * (p * (1 - p) / N).sqrt() + 1e-4).all(), (freq, p)
+        assert ((freq - p).abs() < 4 * (p * (1 - p) / N).sqrt() + 2e-3).all(), (freq, p)
     again = torch.empty_like(acts)
     agent.sample_cuda(x, again[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)
     assert torch.equal(again[:, 1], acts[:, 1])
@@ -167,3 +167,36 @@ def test_sample_heads_kernel_is_a_categorical_sampler():
     joint = torch.bincount(a0 * 3 + a1, minlength=9).double().cpu().view(3, 3) / N
     outer = joint.sum(1, keepdim=True) * joint.sum(0, keepdim=True)
     assert (joint - outer).abs().max() < 5e-3
+
+
+def test_policy_mid_tail_matches_the_module_forward():
+    """at_policy_mid_tail (tanh -> second layers on the tensor cores (TF32) -> tanh -> output layers) against the fp32
+    module path on distinct rows, a ragged row count, and against the fp32 at_policy_tail path."""
+    from alphatank_b200.learner import PPOAgentPPO
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    agent = PPOAgentPPO(528).to(dev)
+    for n in (1, 63, 64, 65, 5000):
+        x = torch.randn(n, 528, device=dev)
+        acts = torch.zeros((n, 3), dtype=torch.int32, device=dev)
+        lps = torch.zeros((n, 3), device=dev)
+        ctr = torch.full((1,), 7, dtype=torch.int64, device=dev)
+        v = agent.sample_cuda(x, acts, lps, ctr, seed=3)
+        with torch.no_grad():
+            want_v = agent.get_value(x)
+            logits = [head(x) for head in agent.actor]
+        assert torch.allclose(v, want_v, rtol=3e-3, atol=3e-3), float((v - want_v).abs().max())
+        for h, l in enumerate(logits):
+            lp = torch.log_softmax(l, dim=-1)
+            a = acts[:, h].long()
+            assert int(a.min()) >= 0 and int(a.max()) < l.shape[1]
+            assert torch.allclose(lps[:, h], lp.gather(-1, a.unsqueeze(-1)).squeeze(-1), atol=3e-3)
+        os.environ["AT_NO_POLICY_MID"] = "1"
+        try:
+            acts2, lps2 = torch.zeros_like(acts), torch.zeros_like(lps)
+            v2 = agent.sample_cuda(x, acts2, lps2, ctr, seed=3)
+        finally:
+            os.environ.pop("AT_NO_POLICY_MID", None)
+        assert torch.allclose(v, v2, rtol=3e-3, atol=3e-3)
+        assert (acts2 == acts).float().mean() > 0.97                       # same uniforms: only near-ties may flip
