@@ -177,6 +177,7 @@ struct HostSignal {
     unsigned int *counter;          // device: blocks that have finished (reset by the last one)
     volatile uint32_t *host_flag;   // mapped host memory; nullptr: no signalling
     uint32_t epoch;
+    unsigned long long *dbg_times;  // diagnostics (at_debug_block_times): [2 * grid] globaltimer at block start / end
 };
 
 // FUSED = true: simulation + observation rows in one launch (phase B below).  FUSED = false: simulation only; the rows
@@ -190,6 +191,11 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     extern __shared__ __align__(16) unsigned char smem[];
     const SmemLayout L = smem_layout(c.n_tanks, c.n_walls, c.n_bots, FUSED, c.act_rows);
     if (!FUSED) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // rows_kernel may take freed SM slots
+    if (sig.dbg_times != nullptr && threadIdx.x == 0) {
+        unsigned long long t0;
+        asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t0));
+        sig.dbg_times[2 * blockIdx.x] = t0;
+    }
     BlockMem bm;
     bm.trig = (double *)(smem + L.off_trig);
     bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
@@ -334,6 +340,11 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
         }
     }
 
+    if (sig.dbg_times != nullptr && tid == 0) {
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t1));
+        sig.dbg_times[2 * blockIdx.x + 1] = t1;
+    }
     if (sig.host_flag != nullptr) {   // (block-uniform)  rewards / done of this block are in host memory before it counts
         __threadfence_system();
         __syncthreads();
@@ -1180,6 +1191,7 @@ struct at_env {
     volatile uint32_t *h_sig_flag;        // ... and the mapped host word its last block posts the epoch to
     volatile uint32_t *h_sig_flag_dev;    // (device alias of h_sig_flag)
     uint32_t sig_epoch;
+    unsigned long long *dbg_times;        // diagnostics: see at_debug_block_times
     cudaStream_t copy_stream;             // at_step_host: the actions' DMA runs beside the previous step's rows kernel
     cudaEvent_t ev_actions;
     std::vector<std::pair<const void *, void *>> mapped;  // host buffers seen by at_step_host -> device alias (null: not mapped)
@@ -1189,7 +1201,7 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
                              float norm_eps = 0.f, bool signal_host = false) {
     const int grid = (int)((env->n_envs + BS - 1) / BS);
-    HostSignal sig = {nullptr, nullptr, 0u};
+    HostSignal sig = {nullptr, nullptr, 0u, env->dbg_times};
     if (signal_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
     const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
     if (d_obs_norm && !env->split_rows) return fail(AT_ERR_ARG, "normalised rows are built by rows_kernel: unset AT_FUSED_ROWS");
@@ -1304,6 +1316,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->st.bfs_tab = (const uint16_t *)(b + L.o_bfs);
     }
 
+    env->dbg_times = nullptr;
     env->d_sig_counter = nullptr; env->h_sig_flag = nullptr; env->h_sig_flag_dev = nullptr; env->sig_epoch = 0;
     {
         void *hp = nullptr, *dp = nullptr;
@@ -1714,6 +1727,12 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
     sample_out9_kernel<<<(int)((n_rows + 255) / 256), 256, 0, s>>>(d_out9, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
                                                                   d_logprobs, lp_stride, d_values, val_stride);
     CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_debug_block_times(at_env *env, unsigned long long *d_times) {
+    if (!env) return fail(AT_ERR_ARG, "at_debug_block_times: null handle");
+    env->dbg_times = d_times;   // [2 * ceil(n_envs / 64)] device words, or NULL to switch the stamps off
     return AT_OK;
 }
 

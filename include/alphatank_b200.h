@@ -199,6 +199,11 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
                        int32_t *d_actions, int64_t act_stride, float *d_logprobs, int64_t lp_stride, float *d_values,
                        int64_t val_stride, void *stream);
 
+/* Diagnostics: while d_times (device, uint64[2 * ceil(n_envs / 64)]) is set, every block of the simulation kernel
+ * stamps %globaltimer (ns) at its start and end into it; NULL switches the stamps off.  Used to study how the blocks'
+ * finishing times spread (profiles/). */
+int at_debug_block_times(at_env *env, unsigned long long *d_times);
+
 /* Host copies of the device lookup tables (tests): cos/sin of math.radians(a), a = 0..360 -> double[361][2];
  * pygame Vector2.rotate corner offsets -> double[361][4]. */
 int at_get_luts(const at_env *env, double *h_trig, double *h_corner);
