@@ -981,8 +981,8 @@ __global__ void __launch_bounds__(256) policy_tail_kernel(const PolicyTail p, in
 // i.e. tanh of the first layers' pre-activations, the second layers (4 x 128 x 128, TF32 mma.sync m16n8k8 with fp32
 // accumulation - the precision of the cuBLAS TF32 GEMMs it replaces), their tanh and the tiny output layers, without
 // the [N, 512] activations ever going back to HBM.  A block keeps W2_k in shared memory (padded: conflict-free
-// fragment loads) and streams 64-row tiles of z1 through it; warp w owns rows 16 w .. 16 w + 15 of the tile.
-constexpr int PM_ROWS = 64, PM_LD = 132;
+// fragment loads) and streams 128-row tiles of z1 through it; compute warp w owns rows 16 w .. 16 w + 15 of the tile.
+constexpr int PM_ROWS = 128, PM_LD = 132, PM_CWARPS = 8, PM_LWARPS = 4, PM_THREADS = (PM_CWARPS + PM_LWARPS) * 32;
 struct PolicyMid {
     const float *z1;   // [n_rows][512] pre-activations of the four first layers (bias included)
     const float *w2;   // [4][128 out][128 in]
@@ -996,105 +996,119 @@ __device__ __forceinline__ uint32_t to_tf32(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
     return r;
 }
-__global__ void __launch_bounds__(128, 2) policy_mid_kernel(const PolicyMid p, int64_t n_rows) {
+// One block per SM: 8 compute warps (16 rows of a 128-row tile each) and 4 loader warps that fill the other of two
+// A buffers with the next tile (z1 -> tanh -> tf32) meanwhile; the roles meet once per tile at a block barrier.
+__global__ void __launch_bounds__(PM_THREADS, 1) policy_mid_kernel(const PolicyMid p, int64_t n_rows) {
     extern __shared__ __align__(16) unsigned char pm_smem[];
     uint32_t *Ws = (uint32_t *)pm_smem;                 // [128 n][PM_LD]  tf32 bits of W2_k[n][k]
-    uint32_t *As = Ws + 128 * PM_LD;                    // [64 rows][PM_LD] tf32 bits of tanh(z1)
-    float *b2s = (float *)(As + PM_ROWS * PM_LD);       // [128]
+    uint32_t *As0 = Ws + 128 * PM_LD;                   // 2 x [128 rows][PM_LD] tf32 bits of tanh(z1)
+    float *b2s = (float *)(As0 + 2 * PM_ROWS * PM_LD);  // [128]
     float *w3s = b2s + 128;                             // [3][128]
     const int k = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gid = lane >> 2, tig = lane & 3;
     const int first = k == 0 ? 0 : (k == 1 ? 1 : (k == 2 ? 4 : 7)), nout = k == 0 ? 1 : (k == 3 ? 2 : 3);
-    for (int i = tid; i < 128 * 32; i += 128) {         // W2_k, 16 bytes at a time
+    for (int i = tid; i < 128 * 32; i += PM_THREADS) {  // W2_k, 16 bytes at a time
         const int n = i >> 5, c4 = (i & 31) * 4;
         const float4 w = __ldg(reinterpret_cast<const float4 *>(p.w2 + ((int64_t)k * 128 + n) * 128 + c4));
-        uint32_t *d = Ws + n * PM_LD + c4;
-        d[0] = to_tf32(w.x); d[1] = to_tf32(w.y); d[2] = to_tf32(w.z); d[3] = to_tf32(w.w);
+        uint4 t;
+        t.x = to_tf32(w.x); t.y = to_tf32(w.y); t.z = to_tf32(w.z); t.w = to_tf32(w.w);
+        *reinterpret_cast<uint4 *>(Ws + n * PM_LD + c4) = t;
     }
-    b2s[tid] = __ldg(p.b2 + k * 128 + tid);
-    for (int j = 0; j < 3; ++j) w3s[j * 128 + tid] = j < nout ? __ldg(p.w3 + (first + j) * 128 + tid) : 0.f;
+    if (tid < 128) {
+        b2s[tid] = __ldg(p.b2 + k * 128 + tid);
+        for (int j = 0; j < 3; ++j) w3s[j * 128 + tid] = j < nout ? __ldg(p.w3 + (first + j) * 128 + tid) : 0.f;
+    }
     const float b3v[3] = {__ldg(p.b3 + first), nout > 1 ? __ldg(p.b3 + first + 1) : 0.f, nout > 2 ? __ldg(p.b3 + first + 2) : 0.f};
     const int64_t n_tiles = (n_rows + PM_ROWS - 1) / PM_ROWS;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const bool loader = warp >= PM_CWARPS;
+    const int ltid = tid - PM_CWARPS * 32;              // 0 .. 127 among the loader threads
+    // a tile's slice of z1 -> tanh -> tf32 (loader warps): 16 loads of a thread in flight at a time
+    auto fill = [&](int64_t tile, uint32_t *As) {
         const int64_t row0 = tile * PM_ROWS;
-        __syncthreads();                                 // (first pass: the tables; later: everybody is done with As)
-        {   // the tile's slice of z1 -> tanh -> tf32: all 16 loads of a thread are in flight before the first is used
-            float4 v[PM_ROWS * 32 / 128];
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+            float4 v[16];
 #pragma unroll
-            for (int q = 0; q < PM_ROWS * 32 / 128; ++q) {
-                const int i = tid + q * 128, r = i >> 5, c4 = (i & 31) * 4;
+            for (int q = 0; q < 16; ++q) {
+                const int i = ltid + (half * 16 + q) * (PM_LWARPS * 32), r = i >> 5, c4 = (i & 31) * 4;
                 v[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (row0 + r < n_rows) v[q] = __ldcs(reinterpret_cast<const float4 *>(p.z1 + (row0 + r) * 512 + k * 128 + c4));
-            }
-            const int64_t next0 = row0 + (int64_t)gridDim.x * PM_ROWS;   // the block's next tile -> L2
-#pragma unroll
-            for (int q = 0; q < PM_ROWS * 32 / 128; q += 2) {            // (one prefetch per 32-byte sector pair is plenty)
-                const int i = tid + q * 128, r = i >> 5, c4 = (i & 31) * 4;
-                if (next0 + r < n_rows) asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p.z1 + (next0 + r) * 512 + k * 128 + c4));
+                if (tile < n_tiles && row0 + r < n_rows)
+                    v[q] = __ldcs(reinterpret_cast<const float4 *>(p.z1 + (row0 + r) * 512 + k * 128 + c4));
             }
 #pragma unroll
-            for (int q = 0; q < PM_ROWS * 32 / 128; ++q) {
-                const int i = tid + q * 128, r = i >> 5, c4 = (i & 31) * 4;
+            for (int q = 0; q < 16; ++q) {
+                const int i = ltid + (half * 16 + q) * (PM_LWARPS * 32), r = i >> 5, c4 = (i & 31) * 4;
                 uint4 t;
                 t.x = to_tf32(fast_tanh(v[q].x)); t.y = to_tf32(fast_tanh(v[q].y)); t.z = to_tf32(fast_tanh(v[q].z)); t.w = to_tf32(fast_tanh(v[q].w));
                 *reinterpret_cast<uint4 *>(As + r * PM_LD + c4) = t;
             }
         }
-        __syncthreads();
-        float acc[16][4];
+    };
+    if (loader) fill(blockIdx.x, As0);
+    __syncthreads();   // the tables and the first tile
+    int buf = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
+        uint32_t *As = As0 + buf * PM_ROWS * PM_LD;
+        if (loader) {
+            fill(tile + gridDim.x, As0 + (buf ^ 1) * PM_ROWS * PM_LD);
+        } else {
+            const int64_t row0 = tile * PM_ROWS;
+            float acc[16][4];
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
-        // fragments by ldmatrix: a tf32 8 x 4 block is an 8 x 8 b16 matrix (row = 16 bytes), and thread (gid, tig) of
-        // an ldmatrix result holds row gid, 32-bit column tig - exactly the m16n8k8 A (row, k) / B (n, k) fragment order.
-        // lane l supplies the row address of matrix l / 8: A = {rows 0-7 | 8-15} x {k 0-3 | 4-7}, B = two n-tiles x {k 0-3 | 4-7}
-        const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(As + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PM_LD + (lane >> 4) * 4);
-        const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(Ws + ((lane & 7) + (lane >> 4) * 8) * PM_LD + ((lane >> 3) & 1) * 4);
+            for (int nt = 0; nt < 16; ++nt) { acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f; }
+            // fragments by ldmatrix: a tf32 8 x 4 block is an 8 x 8 b16 matrix (row = 16 bytes), and thread (gid, tig) of
+            // an ldmatrix result holds row gid, 32-bit column tig - exactly the m16n8k8 A (row, k) / B (n, k) fragment order.
+            // lane l supplies the row address of matrix l / 8: A = {rows 0-7 | 8-15} x {k 0-3 | 4-7}, B = two n-tiles x {k 0-3 | 4-7}
+            const uint32_t a_addr = (uint32_t)__cvta_generic_to_shared(As + (warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * PM_LD + (lane >> 4) * 4);
+            const uint32_t b_addr = (uint32_t)__cvta_generic_to_shared(Ws + ((lane & 7) + (lane >> 4) * 8) * PM_LD + ((lane >> 3) & 1) * 4);
 #pragma unroll 2
-        for (int ks = 0; ks < 16; ++ks) {
-            uint32_t a0, a1, a2, a3;
-            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
-                         : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_addr + ks * 32));
-#pragma unroll
-            for (int np = 0; np < 8; ++np) {   // two n-tiles per ldmatrix
-                uint32_t b0, b1, b2, b3;
+            for (int ks = 0; ks < 16; ++ks) {
+                uint32_t a0, a1, a2, a3;
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
-                             : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(b_addr + (np * 16 * PM_LD + ks * 8) * 4));
-                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
-                             : "+f"(acc[2 * np][0]), "+f"(acc[2 * np][1]), "+f"(acc[2 * np][2]), "+f"(acc[2 * np][3])
-                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-                asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
-                             : "+f"(acc[2 * np + 1][0]), "+f"(acc[2 * np + 1][1]), "+f"(acc[2 * np + 1][2]), "+f"(acc[2 * np + 1][3])
-                             : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b2), "r"(b3));
+                             : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(a_addr + ks * 32));
+#pragma unroll
+                for (int np = 0; np < 8; ++np) {   // two n-tiles per ldmatrix
+                    uint32_t b0, b1, b2, b3;
+                    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];\n"
+                                 : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(b_addr + (np * 16 * PM_LD + ks * 8) * 4));
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                                 : "+f"(acc[2 * np][0]), "+f"(acc[2 * np][1]), "+f"(acc[2 * np][2]), "+f"(acc[2 * np][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+                    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};\n"
+                                 : "+f"(acc[2 * np + 1][0]), "+f"(acc[2 * np + 1][1]), "+f"(acc[2 * np + 1][2]), "+f"(acc[2 * np + 1][3])
+                                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b2), "r"(b3));
+                }
             }
-        }
-        // epilogue: this thread holds columns nt * 8 + 2 tig (+1) of rows gid (acc[.][0..1]) and gid + 8 (acc[.][2..3])
-        float o_lo[3] = {0.f, 0.f, 0.f}, o_hi[3] = {0.f, 0.f, 0.f};
+            // epilogue: this thread holds columns nt * 8 + 2 tig (+1) of rows gid (acc[.][0..1]) and gid + 8 (acc[.][2..3])
+            float o_lo[3] = {0.f, 0.f, 0.f}, o_hi[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int nt = 0; nt < 16; ++nt) {
+            for (int nt = 0; nt < 16; ++nt) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int col = nt * 8 + 2 * tig + q;
-                const float bb = b2s[col];
-                const float h_lo = fast_tanh(acc[nt][q] + bb), h_hi = fast_tanh(acc[nt][2 + q] + bb);
+                for (int q = 0; q < 2; ++q) {
+                    const int col = nt * 8 + 2 * tig + q;
+                    const float bb = b2s[col];
+                    const float h_lo = fast_tanh(acc[nt][q] + bb), h_hi = fast_tanh(acc[nt][2 + q] + bb);
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const float w = w3s[j * 128 + col];
-                    o_lo[j] += h_lo * w;
-                    o_hi[j] += h_hi * w;
+                    for (int j = 0; j < 3; ++j) {
+                        const float w = w3s[j * 128 + col];
+                        o_lo[j] += h_lo * w;
+                        o_hi[j] += h_hi * w;
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                o_lo[j] += __shfl_xor_sync(0xffffffffu, o_lo[j], 1); o_lo[j] += __shfl_xor_sync(0xffffffffu, o_lo[j], 2);
+                o_hi[j] += __shfl_xor_sync(0xffffffffu, o_hi[j], 1); o_hi[j] += __shfl_xor_sync(0xffffffffu, o_hi[j], 2);
+            }
+            if (tig == 0) {
+                const int64_t r_lo = row0 + warp * 16 + gid, r_hi = r_lo + 8;
+                for (int j = 0; j < nout; ++j) {
+                    if (r_lo < n_rows) p.out9[r_lo * 9 + first + j] = o_lo[j] + b3v[j];
+                    if (r_hi < n_rows) p.out9[r_hi * 9 + first + j] = o_hi[j] + b3v[j];
                 }
             }
         }
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            o_lo[j] += __shfl_xor_sync(0xffffffffu, o_lo[j], 1); o_lo[j] += __shfl_xor_sync(0xffffffffu, o_lo[j], 2);
-            o_hi[j] += __shfl_xor_sync(0xffffffffu, o_hi[j], 1); o_hi[j] += __shfl_xor_sync(0xffffffffu, o_hi[j], 2);
-        }
-        if (tig == 0) {
-            const int64_t r_lo = row0 + warp * 16 + gid, r_hi = r_lo + 8;
-            for (int j = 0; j < nout; ++j) {
-                if (r_lo < n_rows) p.out9[r_lo * 9 + first + j] = o_lo[j] + b3v[j];
-                if (r_hi < n_rows) p.out9[r_hi * 9 + first + j] = o_hi[j] + b3v[j];
-            }
-        }
+        __syncthreads();   // the next tile is in the other buffer; this one may be overwritten
     }
 }
 
@@ -1712,17 +1726,17 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
     if ((((uintptr_t)d_z1) | ((uintptr_t)d_w2)) & 15u) return fail(AT_ERR_ARG, "at_policy_mid_tail: z1 / w2 must be 16-byte aligned");
     CUDA_TRY(cudaSetDevice(device));
     static bool attr_set[64] = {false};
-    const size_t smem = (size_t)(128 + PM_ROWS) * PM_LD * 4 + (128 + 3 * 128) * 4;
+    const size_t smem = (size_t)(128 + 2 * PM_ROWS) * PM_LD * 4 + (128 + 3 * 128) * 4;
     if (device < 64 && !attr_set[device]) {
         CUDA_TRY(cudaFuncSetAttribute(policy_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set[device] = true;
     }
     PolicyMid p = {d_z1, d_w2, d_b2, d_w3, d_b3, d_out9};
     const int64_t n_tiles = (n_rows + PM_ROWS - 1) / PM_ROWS;
-    int gx = 74;                       // 74 x 4 networks = 296 blocks = 2 per SM
+    int gx = 37;                       // 37 x 4 networks = 148 blocks = one per SM
     if (n_tiles < gx) gx = (int)n_tiles;
     cudaStream_t s = (cudaStream_t)stream;
-    policy_mid_kernel<<<dim3(gx, 4), 128, smem, s>>>(p, n_rows);
+    policy_mid_kernel<<<dim3(gx, 4), PM_THREADS, smem, s>>>(p, n_rows);
     CUDA_TRY(cudaGetLastError());
     sample_out9_kernel<<<(int)((n_rows + 255) / 256), 256, 0, s>>>(d_out9, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
                                                                   d_logprobs, lp_stride, d_values, val_stride);
