@@ -200,3 +200,18 @@ def test_policy_mid_tail_matches_the_module_forward():
             os.environ.pop("AT_NO_POLICY_MID", None)
         assert torch.allclose(v, v2, rtol=3e-3, atol=3e-3)
         assert (acts2 == acts).float().mean() > 0.97                       # same uniforms: only near-ties may flip
+
+
+def test_sac_training_script_runs_and_saves_reference_layout(tmp_path):
+    """scripts/train_sac_sac.py (the reference's train_sac_sac.py, batched): two iterations on 512 envs, checkpoints in
+    the reference's SACAgent.state_dict() layout."""
+    import subprocess
+    script = os.path.join(os.path.dirname(HERE), "scripts", "train_sac_sac.py")
+    out = subprocess.run([sys.executable, script, "--num-envs", "512", "--iterations", "2", "--num-steps", "24",
+                          "--start-steps", "8", "--update-every", "3", "--batch-size", "128", "--capacity", "20000",
+                          "--ckpt-dir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "iter 1" in out.stdout and "Saved model for Agent 1" in out.stdout
+    sd = torch.load(str(tmp_path / "sac_agent_0.pt"), map_location="cpu", weights_only=False)
+    assert set(sd) == {"actor", "critic1", "critic2", "critic1_target", "critic2_target", "log_alpha"}
+    assert sd["actor"]["fc1.weight"].shape == (256, 388) and sd["critic1"]["fc1.weight"].shape == (256, 388 + 6)
