@@ -301,3 +301,45 @@ def load_team_checkpoint(path, obs_dim, act_dim=(3, 3, 2), device="cpu"):
         a.load_state_dict(sd)
         agents[name] = a
     return ck["team_config"], agents
+
+
+# ---------------------------------------------------------------------------- 1v1 vs a scripted bot (train_ppo_bot.py)
+class _OneRowCore:
+    """What collect_rollout needs from ``env.core``, for ONE policy-driven tank of a 1v1 ``bot_agent`` env: the wrapper
+    returns both tanks' rows and takes both tanks' action rows (gym_env.py:119, 187; the bot's row is ignored,
+    train_ppo_bot.py:111-113) - this view exposes only row ``index`` of either."""
+
+    def __init__(self, core, index):
+        self.c, self.i = core, index
+        self.num_envs, self.D = core.num_envs, core.D
+        self._acts = torch.zeros((core.num_envs, core.A, 3), dtype=torch.int32, device=core.device)
+
+    def reset(self, mask=None, obs_out=None):
+        rows = self.c.reset(mask).view(self.num_envs, self.c.R, self.D)[:, self.i]
+        if obs_out is None:
+            return rows.clone()
+        obs_out.view(self.num_envs, self.D).copy_(rows)
+        return obs_out
+
+    def step(self, actions, obs_out=None, rewards_out=None, done_out=None):
+        self._acts[:, self.i] = actions.view(self.num_envs, 3)
+        obs, rew, dn = self.c.step(self._acts, done_out=done_out)
+        if obs_out is not None:
+            obs_out.view(self.num_envs, self.D).copy_(obs.view(self.num_envs, self.c.R, self.D)[:, self.i])
+        if rewards_out is not None:
+            rewards_out.view(self.num_envs).copy_(rew[:, self.i])
+        return obs_out, rewards_out, dn
+
+    def step_norm(self, actions, obs_norm_out, obs_out=None, rewards_out=None, done_out=None, epsilon=1e-4):
+        raw = self.c.obs.view(self.num_envs, self.c.R, self.D)
+        self.step(actions, obs_out=obs_out, rewards_out=rewards_out, done_out=done_out)
+        tick_normalize(raw[:, self.i:self.i + 1].contiguous(), epsilon, out=obs_norm_out.view(self.num_envs, 1, self.D))
+        return obs_norm_out, rewards_out, done_out
+
+
+class SingleAgentView:
+    """``MultiAgentEnv(mode='bot_agent', ...)`` as a one-agent env for collect_rollout / RolloutRunner (the training agent
+    is tank ``training_agent_index`` = 1, train_ppo_bot.py:35)."""
+
+    def __init__(self, env, training_agent_index=1):
+        self.env, self.core = env, _OneRowCore(env.core, training_agent_index)

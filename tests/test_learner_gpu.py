@@ -215,3 +215,46 @@ def test_sac_training_script_runs_and_saves_reference_layout(tmp_path):
     sd = torch.load(str(tmp_path / "sac_agent_0.pt"), map_location="cpu", weights_only=False)
     assert set(sd) == {"actor", "critic1", "critic2", "critic1_target", "critic2_target", "log_alpha"}
     assert sd["actor"]["fc1.weight"].shape == (256, 388) and sd["critic1"]["fc1.weight"].shape == (256, 388 + 6)
+
+
+def test_ppo_bot_training_script_runs_and_saves_reference_layout(tmp_path):
+    """scripts/train_ppo_bot.py (the reference's train_ppo_bot.py --bot-type smart, BASELINE config 2, batched): the
+    agent is tank 1 of a bot_agent env, its rollouts replay as one CUDA graph, the checkpoint is the agent's state_dict."""
+    import subprocess
+    from alphatank_b200.learner import PPOAgentBot
+    script = os.path.join(os.path.dirname(HERE), "scripts", "train_ppo_bot.py")
+    out = subprocess.run([sys.executable, script, "--bot-type", "smart", "--num-envs", "1024", "--iterations", "3",
+                          "--num-steps", "16", "--num-epochs", "1", "--ckpt-dir", str(tmp_path)],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "iter 2" in out.stdout
+    sd = torch.load(str(tmp_path / "ppo_agent_vs_smart.pt"), map_location="cpu", weights_only=False)
+    assert list(sd) == list(PPOAgentBot(388).state_dict())
+
+
+def test_single_agent_view_matches_the_plain_env():
+    """SingleAgentView (one policy-driven tank of a bot_agent env): rows, rewards and done flags it hands to the rollout
+    are row 1 of what the env returns for the same actions; step_norm = the tick normaliser on that row."""
+    from alphatank_b200 import MultiAgentEnv
+    from alphatank_b200.learner.ppo import SingleAgentView
+    from alphatank_b200.learner.ppo_utils import tick_normalize
+    dev = torch.device("cuda:0")
+    N = 300
+    a = MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=N, device=dev, seed=3)
+    b = MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=N, device=dev, seed=3)
+    view = SingleAgentView(b).core
+    oa, _ = a.reset()
+    ob = view.reset()
+    assert torch.equal(oa[:, 1], ob)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    norm, rew, dn = torch.empty((N, 1, 388), device=dev), torch.empty((N, 1), device=dev), torch.empty(N, dtype=torch.uint8, device=dev)
+    for t in range(60):
+        act = torch.stack([torch.randint(0, 3, (N,), device=dev, generator=g), torch.randint(0, 3, (N,), device=dev, generator=g),
+                           torch.randint(0, 2, (N,), device=dev, generator=g)], dim=-1).to(torch.int32)
+        full = torch.zeros((N, 2, 3), dtype=torch.int32, device=dev)
+        full[:, 1] = act
+        o, r, d, _, _ = a.step(full)
+        view.step_norm(act.view(N, 1, 3), norm, rewards_out=rew, done_out=dn)
+        row = o.view(N, 2, 388)[:, 1:2]
+        assert torch.equal(rew[:, 0], r[:, 1]) and torch.equal(dn, d)
+        assert torch.equal(norm, tick_normalize(row.contiguous()))
