@@ -1,0 +1,131 @@
+"""GPU (-m gpu): the batched counterparts of the reference's remaining callers of the env step:
+bot_arena.py, train_ppo_ppo.py, train_ppo_cycle.py - each drives the CUDA path through the reference's gym API."""
+import importlib.util
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+pytestmark = pytest.mark.gpu
+
+
+def _script(name):
+    spec = importlib.util.spec_from_file_location("at_script_" + name, os.path.join(REPO, "scripts", name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_masked_reset_after_the_step_equals_the_auto_reset_inside_it():
+    """bot_arena.py / the cycle evaluation read info["winner"] at the terminal tick and reset afterwards (the
+    reference's own order, bot_arena.py:61-70); that must be the same battle stream as the auto-reset inside the step."""
+    from alphatank_b200 import MultiAgentEnv
+    dev = torch.device("cuda:0")
+    N = 1024
+    kw = dict(mode="bot_vs_bot", bot_types=("aggressive", "dodge"), num_envs=N, device=dev, seed=7)
+    a = MultiAgentEnv(auto_reset=True, **kw)
+    b = MultiAgentEnv(auto_reset=False, **kw)
+    oa, _ = a.reset()
+    ob, _ = b.reset()
+    assert torch.equal(oa, ob)
+    ended = 0
+    for t in range(500):
+        oa, ra, da, _, _ = a.step()
+        ob, rb, db, _, _ = b.step()
+        assert torch.equal(da, db) and torch.equal(ra, rb), t
+        ended += int(db.sum())
+        ob = b.reset(mask=db)[0].view(N, -1)
+        assert torch.equal(oa, ob), t
+    assert ended > 100
+
+
+def test_bot_arena_counts_every_match_once():
+    """scripts/bot_arena.py: a stationary bot never fires, so it never wins; every finished match has exactly one
+    outcome; the aggressive bot's hits are its wins (tanks die on the first hit when TERMINATE_TIME is None)."""
+    arena = _script("bot_arena")
+    r = arena.run_bot_matches("aggressive", "stationary", num_envs=2048, ticks=700, seed=3)
+    assert r["episodes"] > 500
+    assert r["bot1_wins"] + r["bot2_wins"] + r["draws"] == r["episodes"]
+    assert r["bot2_wins"] == 0 and r["draws"] == 0 and r["bot2_hits"] == 0
+    assert r["bot1_hits"] == r["bot1_wins"]
+    assert 1.0 < r["mean_episode_ticks"] < 700
+    with pytest.raises(ValueError):                                       # BotFactory.create_bot's error (bot_factory.py:29-31)
+        arena.run_bot_matches("aggressive", "nosuchbot", num_envs=32, ticks=1)
+
+
+def test_terminal_reward_increment_identifies_the_winner():
+    """train_ppo_cycle.py reads a training episode's outcome from the rollout: terminal increment > 25 <=> the agent
+    (tank 1) is the first alive tank at the terminal tick, i.e. info["winner"] == 1 (train_ppo_cycle.py:341)."""
+    from alphatank_b200 import MultiAgentEnv
+    dev = torch.device("cuda:0")
+    N = 4096
+    for bot in ("aggressive", "smart"):
+        env = MultiAgentEnv(mode="bot_agent", type="train", bot_type=bot, num_envs=N, device=dev, seed=5, auto_reset=False)
+        env.reset()
+        prev = torch.zeros(N, device=dev)
+        acts = torch.zeros((N, 2, 3), dtype=torch.int32, device=dev)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        ended = wins = 0
+        for t in range(400):
+            acts[:, 1, 0] = torch.randint(0, 3, (N,), device=dev, generator=g)
+            acts[:, 1, 1] = torch.randint(0, 3, (N,), device=dev, generator=g)
+            acts[:, 1, 2] = torch.randint(0, 2, (N,), device=dev, generator=g)
+            _, rew, done, _, info = env.step(acts)
+            d = done.bool()
+            inc = rew[:, 1] - prev
+            w = info["winner"]
+            assert torch.equal((inc > 25.0)[d], (w == 1)[d]), (bot, t)
+            ended += int(d.sum())
+            wins += int((w == 1)[d].sum())
+            prev = torch.where(d, torch.zeros_like(prev), rew[:, 1])
+            env.reset(mask=done)
+        assert ended > 200 and 0 < wins < ended, (bot, ended, wins)
+        env.close()
+
+
+def test_ppo_cycle_rotates_bots_follows_the_weakness_schedule_and_saves(tmp_path):
+    """scripts/train_ppo_cycle.py: fixed rotation over two bot types, linear weakness schedule applied in place
+    (at_set_weakness), rollouts as CUDA graphs per bot type, evaluation with exact winners, reference checkpoint name."""
+    cyc = _script("train_ppo_cycle")
+    from alphatank_b200.learner import PPOAgentBot
+    N, T, U = 512, 16, 6
+    cfg = cyc.CycleTrainingConfig(bot_types=["aggressive", "random"], rotation_strategy="fixed", switch_every=N * T,
+                                  eval_frequency=3 * N * T, num_steps=T, num_epochs=1, total_timesteps=U * N * T,
+                                  weakness_start=0.2, weakness_end=0.8)
+    assert abs(cfg.get_current_weakness(U * N * T) - 0.8) < 1e-12 and abs(cfg.get_current_weakness(0) - 0.2) < 1e-12
+    lines = []
+    learner, hist, path = cyc.train_cycle(cfg, num_envs=N, updates=U, seed=0, eval_envs=256, eval_ticks=150,
+                                          ckpt_dir=str(tmp_path), log=lines.append)
+    assert [h["bot"] for h in hist] == ["random", "aggressive", "random", "aggressive", "random", "aggressive"]
+    ws = [h["weakness"] for h in hist]
+    assert ws == sorted(ws) and abs(ws[-1] - 0.8) < 1e-12
+    assert "eval" in hist[2] and set(hist[2]["eval"]) == {"aggressive", "random"}
+    assert all(0.0 <= r["win_rate"] <= 1.0 for r in hist[5]["eval"].values())
+    assert os.path.basename(path) == "ppo_agent_cycle.pt"
+    sd = torch.load(path, map_location="cpu", weights_only=False)
+    assert list(sd) == list(PPOAgentBot(388).state_dict())
+    with pytest.raises(ValueError):
+        cyc.CycleTrainingConfig(rotation_strategy="sometimes")
+    with pytest.raises(ValueError):
+        cyc.CycleTrainingConfig(weakness_schedule="cubic")
+    s = cyc.CycleTrainingConfig(weakness_schedule="sigmoid", weakness_start=0.1, weakness_end=0.9, total_timesteps=100)
+    assert abs(s.get_current_weakness(50) - 0.5) < 1e-12
+
+
+def test_ppo_ppo_training_script_runs_and_saves_reference_layout(tmp_path):
+    """scripts/train_ppo_ppo.py (the reference's 1v1 self-play trainer, batched): both tanks policy-driven, one CUDA
+    graph per rollout, checkpoints ppo_agent_<i>.pt = state_dict of a PPOAgentPPO(388)."""
+    from alphatank_b200.learner import PPOAgentPPO
+    script = os.path.join(REPO, "scripts", "train_ppo_ppo.py")
+    out = subprocess.run([sys.executable, script, "--num-envs", "1024", "--iterations", "3", "--num-steps", "16",
+                          "--num-epochs", "1", "--ckpt-dir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "iter 2" in out.stdout and "Saved model for Agent 1" in out.stdout
+    for i in range(2):
+        sd = torch.load(str(tmp_path / ("ppo_agent_%d.pt" % i)), map_location="cpu", weights_only=False)
+        assert list(sd) == list(PPOAgentPPO(388).state_dict())
