@@ -40,7 +40,7 @@ ENV_STATE_DT = np.dtype([("n_bullets", "i4"), ("tick", "i4"), ("training_step", 
                          ("bullets", BULLET_DT, (MAX_BULLETS,))], align=True)
 
 EXPORTS = ("at_create at_destroy at_obs_dim at_obs_rows at_action_rows at_num_walls at_num_envs at_reset at_step at_step_norm "
-           "at_step_host at_get_info at_get_state at_set_state at_synthetic_actions at_bfs_batch at_generate_mazes "
+           "at_step_host at_get_info at_get_terminal_info at_get_state at_set_state at_synthetic_actions at_bfs_batch at_generate_mazes "
            "at_get_luts at_tick_normalize at_sample_heads at_policy_tail at_policy_mid_tail at_debug_block_times at_set_weakness at_launch_count at_last_error at_version").split()
 
 _lib = None
@@ -74,6 +74,7 @@ def lib():
     L.at_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
     L.at_step_norm.argtypes = [vp, vp, vp, vp, C.c_float, vp, vp, vp]
     L.at_get_info.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.at_get_terminal_info.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.at_get_state.argtypes = [vp, i64, i64, vp]
     L.at_set_state.argtypes = [vp, i64, i64, vp]
     L.at_synthetic_actions.argtypes = [vp, i64, vp, vp]

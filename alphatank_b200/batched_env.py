@@ -14,7 +14,9 @@ def _ptr(t):
 
 
 class LazyInfo(dict):
-    """``info`` dict of step(): the device tensors are produced (one small kernel) on first access."""
+    """``info`` dict of step(): the device tensors are produced (one small kernel) on first access.  Like the reference's
+    dict (built inside step(), gym_env.py:93-98, before the caller resets) it describes the episode that just ended
+    for envs whose step returned done - also when the auto-reset has already replaced that state (at_get_terminal_info)."""
 
     def __init__(self, env, keys):
         super().__init__()
@@ -23,7 +25,7 @@ class LazyInfo(dict):
     def _fill(self):
         if not self._done:
             self._done = True
-            full = self._env.get_info()
+            full = self._env.get_info(terminal=True)
             for k in self._keys:
                 dict.__setitem__(self, k, full[k])
 
@@ -154,15 +156,32 @@ class BatchedTankEnv:
         _capi.check(self.L.at_synthetic_actions(self.h, int(tick), _ptr(out), self._stream()), "at_synthetic_actions")
         return out
 
-    def get_info(self):
+    def get_info(self, terminal=False):
+        """winner / hits / be_hits / change_time of the current state; ``terminal=True``: of the latest step as the
+        reference's callers see it - envs that were auto-reset in it report the episode that ended (+ ``"latched"``)."""
         N, n, dev = self.num_envs, self.n_tanks, self.device
         winner = torch.empty((N,), dtype=torch.int32, device=dev)
         hits = torch.empty((N, n), dtype=torch.int32, device=dev)
         be_hits = torch.empty((N, n), dtype=torch.int32, device=dev)
         change = torch.empty((N, n), dtype=torch.int32, device=dev)
-        _capi.check(self.L.at_get_info(self.h, _ptr(winner), _ptr(hits), _ptr(be_hits), _ptr(change), self._stream()),
-                    "at_get_info")
-        return {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change}
+        out = {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change}
+        if terminal:
+            latched = torch.empty((N,), dtype=torch.uint8, device=dev)
+            _capi.check(self.L.at_get_terminal_info(self.h, _ptr(winner), _ptr(hits), _ptr(be_hits), _ptr(change),
+                                                    _ptr(latched), self._stream()), "at_get_terminal_info")
+            out["latched"] = latched
+        else:
+            _capi.check(self.L.at_get_info(self.h, _ptr(winner), _ptr(hits), _ptr(be_hits), _ptr(change), self._stream()),
+                        "at_get_info")
+        return out
+
+    def terminal_winner(self, out):
+        """``info["winner"]`` of the latest step (the finished episode's where the step returned done) into ``out``
+        (int32 [N]) - one small kernel, no allocation: usable inside a captured rollout."""
+        assert out.dtype == torch.int32 and out.is_contiguous() and out.numel() == self.num_envs
+        _capi.check(self.L.at_get_terminal_info(self.h, _ptr(out), None, None, None, None, self._stream()),
+                    "at_get_terminal_info")
+        return out
 
     def get_state(self, first=0, count=None):
         count = self.num_envs - first if count is None else count

@@ -182,7 +182,7 @@ inline int sim_spec_for(const KCfg &k, int cap = 3) {
 // One arena for every SoA column (HBM on the GPU, malloc in the emulator).
 struct ArenaLayout {
     size_t o_cnt, o_rng, o_tick, o_tstep, o_ep, o_zones, o_prev, o_change, o_wlo, o_whi, o_tx, o_ty, o_trew, o_tpack,
-        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_udir, o_bfs, o_tmpl, o_act, o_rw, o_dn, bytes;
+        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_udir, o_bfs, o_tmpl, o_act, o_rw, o_dn, o_ttick, o_twin, o_thit, bytes;
 };
 inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     ArenaLayout L;
@@ -200,6 +200,7 @@ inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     L.o_tmpl = take((4 * 72 + CELLS) * 4);
     L.o_act = take(4 * N * 3 * (k.act_rows ? k.act_rows : 1)); L.o_rw = take(4 * N * (k.rows ? k.rows : 1));
     L.o_dn = take(N);
+    L.o_ttick = take(4 * N); L.o_twin = take(4 * N); L.o_thit = take(4 * N * n);
     L.bytes = bytes;
     return L;
 }
@@ -215,6 +216,8 @@ inline void bind_state(DevState &st, char *b, const ArenaLayout &L, int64_t N) {
     st.bx = (double *)(b + L.o_bx); st.by = (double *)(b + L.o_by); st.bmeta = (uint64_t *)(b + L.o_bm);
     st.trig = (const double *)(b + L.o_trig); st.corn = (const double *)(b + L.o_corn);
     st.pend = (const double *)(b + L.o_pend);
+    st.term_tick = (uint32_t *)(b + L.o_ttick); st.term_winner = (uint32_t *)(b + L.o_twin);
+    st.term_hits = (uint32_t *)(b + L.o_thit);
     st.udelta = (const uint8_t *)(b + L.o_udir);
     st.bfs_tab = nullptr;  // set by the owner for fixed maps (at_sim.h fill_bfs_table)
 }

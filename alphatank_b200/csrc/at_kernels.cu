@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
             if (c.rows == 2) *reinterpret_cast<float2 *>(rewards + e * 2) = make_float2(rw[0], rw[1]);  // one 8-byte store
             else for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
             done[e] = d ? 1 : 0;
-            if (d && c.auto_reset) s.env_reset();
+            if (d && c.auto_reset) { s.latch_terminal_info(); s.env_reset(); }
             s.store();
         } else if (!mask || mask[e]) {
             s.load();
@@ -693,20 +693,25 @@ __global__ void scatter_kernel(const __grid_constant__ KCfg c, const DevState st
     if (q < count) scatter_env(c, st, first + q, in[q]);
 }
 
+// TERMINAL: envs whose episode ended in the latest step and was replaced by the auto-reset report the latched info of
+// that episode (Sim::latch_terminal_info) - what the reference's step() returned before its caller reset.
+template <bool TERMINAL>
 __global__ void info_kernel(const __grid_constant__ KCfg c, const DevState st, int32_t *winner, int32_t *hits,
-                            int32_t *be_hits, int32_t *change_time) {
+                            int32_t *be_hits, int32_t *change_time, uint8_t *latched) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= st.N) return;
+    const bool lt = TERMINAL && st.term_tick[e] == st.tick[e];
+    if (TERMINAL && latched) latched[e] = lt ? 1 : 0;
     int w = -1;
     for (int i = 0; i < c.n_tanks; ++i) {
         int64_t g = (int64_t)i * st.N + e;
         if (w < 0 && (st.tpack[g] & TP_ALIVE)) w = i;
-        uint32_t h = st.thits[g];
+        uint32_t h = lt ? st.term_hits[g] : st.thits[g];
         if (hits) hits[e * c.n_tanks + i] = (int32_t)(h & 0xFFFFu);
         if (be_hits) be_hits[e * c.n_tanks + i] = (int32_t)(h >> 16);
         if (change_time) change_time[e * c.n_tanks + i] = st.change_time[g];
     }
-    if (winner) winner[e] = w;
+    if (winner) winner[e] = lt ? (int)st.term_winner[e] - 1 : w;
 }
 
 __global__ void synthetic_actions_kernel(uint64_t seed, int64_t env_id_base, int64_t n_envs, int rows, uint32_t tick,
@@ -1315,6 +1320,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     }
     cudaMemset(env->arena, 0, L.bytes);
     char *b = (char *)env->arena;
+    cudaMemset(b + L.o_ttick, 0xFF, 4 * (size_t)n_envs);   // no terminal info latched yet (tick starts at 0)
     bind_state(env->st, b, L, n_envs);
     env->d_actions_scratch = (int32_t *)(b + L.o_act);
     env->d_rewards_scratch = (float *)(b + L.o_rw);
@@ -1573,7 +1579,18 @@ int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_h
     if (!env) return fail(AT_ERR_ARG, "at_get_info: null handle");
     CUDA_TRY(cudaSetDevice(env->device));
     const int grid = (int)((env->n_envs + 127) / 128);
-    info_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(env->k, env->st, d_winner, d_hits, d_be_hits, d_change_time);
+    info_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(env->k, env->st, d_winner, d_hits, d_be_hits, d_change_time, nullptr);
+    env->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_get_terminal_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
+                         uint8_t *d_latched, void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_get_terminal_info: null handle");
+    CUDA_TRY(cudaSetDevice(env->device));
+    const int grid = (int)((env->n_envs + 127) / 128);
+    info_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(env->k, env->st, d_winner, d_hits, d_be_hits, d_change_time, d_latched);
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return AT_OK;

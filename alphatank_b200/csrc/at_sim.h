@@ -1435,6 +1435,19 @@ struct SimT {
         }
     }
 
+    // The step's info dict (gym_env.py:93-98 winner; gym_env_multi.py:218-222 hits / be_hits) is read by the
+    // reference's callers BEFORE they reset.  With auto-reset the terminal state is replaced inside the step, so
+    // what the dict needs is latched here; `tick` (never reset, F9) stamps the latch: it is valid until the next step.
+    AT_HD void latch_terminal_info() {
+        int w = -1;
+        for (int i = 0; i < cfg_n(); ++i) {
+            if (w < 0 && t_alive(i)) w = i;
+            st.term_hits[G(i)] = THITS(i);
+        }
+        st.term_winner[e] = (uint32_t)(w + 1);
+        st.term_tick[e] = tick;
+    }
+
     // wrapper step (gym_env.py:73-103, 186-200; gym_env_multi.py:202-223, 307-326).  Returns done.
     AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
         tstep += 1;

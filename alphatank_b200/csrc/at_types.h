@@ -58,6 +58,9 @@ struct DevState {
     uint64_t *wall_lo, *wall_hi;   // [N], only when map == MAZE
     double *tx, *ty, *trew;        // [n][N]
     uint32_t *tpack, *thits;       // [n][N]
+    // info latch of the episode an auto-reset replaced (at_get_terminal_info): valid while term_tick[e] == tick[e]
+    uint32_t *term_tick, *term_winner;  // [N]  (term_winner: first alive tank + 1, 0 = nobody)
+    uint32_t *term_hits;           // [n][N] thits at the terminal tick
     int32_t *tshot;                // [n][N]
     uint32_t *bpack;               // [n][N] bot FSM
     double *bf0, *bf1;             // [n][N] bot doubles (smart: last_x,last_y; dodge: dodge_angle)

@@ -43,8 +43,10 @@ class PPOConfig:                       # defaults: train_multi_ppo.py:25-38
 class RolloutBuffer:
     """[T(+1), N, A, ...] storage on the env's device; the env kernel writes obs / rewards / done into it directly."""
 
-    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device, keep_raw=True):
+    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device, keep_raw=True, keep_winner=False):
         T, N, A, D = num_steps, num_envs, num_agents, obs_dim
+        # keep_winner: info["winner"] of every tick (the finished episode's where dones[t + 1] is set; at_get_terminal_info)
+        self.winner = torch.zeros((T, N), dtype=torch.int32, device=device) if keep_winner else None
         self.T, self.N, self.A, self.D = T, N, A, D
         # env output, un-normalised.  keep_raw=False: only slot 0 exists (the reset observation) - with the "tick"
         # normaliser on a GPU the env step hands over normalised rows and the raw ones are never written
@@ -241,6 +243,8 @@ def collect_rollout(env, learner, buf, first=False):
         else:
             core.step(buf.actions[t], obs_out=buf.raw_obs[t + 1], rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
             learner.normalize(buf.raw_obs[t + 1], update=t + 1 < T, out=buf.obs[t + 1])   # straight into the rollout storage
+        if buf.winner is not None:
+            core.terminal_winner(buf.winner[t])
         if learner.cfg.reward_mode == "delta":
             buf.rewards[t].copy_(buf.env_rewards[t] - prev_cum)
             prev_cum = buf.env_rewards[t] * (1.0 - buf.dones[t + 1].to(torch.float32)).unsqueeze(-1)  # reset -> 0
@@ -329,6 +333,9 @@ class _OneRowCore:
         if rewards_out is not None:
             rewards_out.view(self.num_envs).copy_(rew[:, self.i])
         return obs_out, rewards_out, dn
+
+    def terminal_winner(self, out):
+        return self.c.terminal_winner(out)
 
     def step_norm(self, actions, obs_norm_out, obs_out=None, rewards_out=None, done_out=None, epsilon=1e-4):
         raw = self.c.obs.view(self.num_envs, self.c.R, self.D)

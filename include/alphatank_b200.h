@@ -141,6 +141,15 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
 int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
                 void *stream);
 
+/* The info dict of the LATEST step as the reference's callers see it.  The reference builds info inside step()
+ * (gym_env.py:93-98, gym_env_multi.py:218-222) and its callers reset afterwards (train_ppo_bot.py:121-129,
+ * train_ppo_cycle.py:341-360, bot_arena.py:61-70), so at a terminal tick info describes the episode that just ended.
+ * With auto_reset = 1 that state is replaced inside at_step; the step latches winner / hits / be_hits of the finished
+ * episode first, and this call returns the latched values for exactly the envs whose episode ended in the latest step
+ * (d_latched[e] = 1, uint8[n_envs], may be NULL) and the current values (= at_get_info) for all others. */
+int at_get_terminal_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
+                         uint8_t *d_latched, void *stream);
+
 /* Snapshot / inject `count` envs starting at `first` (host AoS records).  Synchronous. */
 int at_get_state(at_env *env, int64_t first, int64_t count, at_env_state *h_out);
 int at_set_state(at_env *env, int64_t first, int64_t count, const at_env_state *h_in);

@@ -69,6 +69,7 @@ def lib():
         L.ato_get_state.argtypes = [vp, i64, vp]
         L.ato_set_state.argtypes = [vp, i64, vp]
         L.ato_get_info.argtypes = [vp, vp, vp, vp, vp]
+        L.ato_get_terminal_info.argtypes = [vp, vp, vp, vp, vp, vp]
         L.ato_bfs_len_between.restype = i32
         L.ato_bfs_len_between.argtypes = [vp, i64, i32, i32]
         L.ato_bfs_path.restype = i32
@@ -181,6 +182,19 @@ class OracleEnv:
         change = np.zeros((self.n_envs, n), np.int32)
         self.L.ato_get_info(self.h, winner.ctypes.data, hits.ctypes.data, be_hits.ctypes.data, change.ctypes.data)
         return {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change}
+
+    def terminal_info(self):
+        """info of the latest step as the reference's step() returned it: for envs the harness auto-reset in that step
+        the finished episode's winner / hits / be_hits (``latched`` = 1), else the current values."""
+        n = self.n_tanks
+        winner = np.zeros(self.n_envs, np.int32)
+        hits = np.zeros((self.n_envs, n), np.int32)
+        be_hits = np.zeros((self.n_envs, n), np.int32)
+        change = np.zeros((self.n_envs, n), np.int32)
+        latched = np.zeros(self.n_envs, np.uint8)
+        self.L.ato_get_terminal_info(self.h, winner.ctypes.data, hits.ctypes.data, be_hits.ctypes.data, change.ctypes.data,
+                                     latched.ctypes.data)
+        return {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change, "latched": latched}
 
 
 def bfs_path(maze, start, goal):

@@ -204,6 +204,9 @@ typedef struct Env {
     Rng rng;
     int tick, training_step, episode_steps;
     int prev_valid, prev_act[ATO_MAX_TANKS][3], change_time[ATO_MAX_TANKS];
+    /* harness auto-reset only: info of the episode the latest step ended, as step() returned it before the caller's
+     * reset (gym_env.py:93-98 winner, gym_env_multi.py:218-222 hits / be_hits) */
+    int term_valid, term_winner, term_hits[ATO_MAX_TANKS], term_be_hits[ATO_MAX_TANKS];
 } Env;
 
 typedef struct Handle {
@@ -1066,6 +1069,7 @@ static void env_step(Handle *h, int64_t i, const int32_t *actions, float *obs, f
     const int arows = ato_action_rows(h);
     const int32_t *a = actions ? actions + i * arows * 3 : NULL;
     e->training_step += 1;
+    e->term_valid = 0;
     if (!team_layout && a) { /* gym_env.py:77-85 change_time */
         if (e->prev_valid)
             for (int k = 0; k < arows; ++k)
@@ -1093,6 +1097,13 @@ static void env_step(Handle *h, int64_t i, const int32_t *actions, float *obs, f
     }
     done[i] = (uint8_t)d;
     if (d && cfg->auto_reset) {
+        e->term_valid = 1;
+        e->term_winner = -1;
+        for (int k = cfg->n_tanks - 1; k >= 0; --k) {
+            if (e->tanks[k].alive) e->term_winner = k; /* first alive tank, gym_env.py:97 */
+            e->term_hits[k] = e->tanks[k].num_hit;
+            e->term_be_hits[k] = e->tanks[k].num_be_hit;
+        }
         env_reset(h, e);
         write_obs(h, e, obs + i * rows * D);
     }
@@ -1263,6 +1274,23 @@ void ato_get_info(void *hh, int32_t *winner, int32_t *hits, int32_t *be_hits, in
             if (hits) hits[i * n + k] = e->tanks[k].num_hit;
             if (be_hits) be_hits[i * n + k] = e->tanks[k].num_be_hit;
             if (change_time) change_time[i * n + k] = e->change_time[k];
+        }
+    }
+}
+/* info of the latest step: the finished episode's for envs the harness auto-reset in it (latched[i] = 1) */
+void ato_get_terminal_info(void *hh, int32_t *winner, int32_t *hits, int32_t *be_hits, int32_t *change_time,
+                           uint8_t *latched) {
+    Handle *h = (Handle *)hh;
+    const int n = h->cfg.n_tanks;
+    ato_get_info(hh, winner, hits, be_hits, change_time);
+    for (int64_t i = 0; i < h->n_envs; ++i) {
+        const Env *e = &h->envs[i];
+        if (latched) latched[i] = (uint8_t)e->term_valid;
+        if (!e->term_valid) continue;
+        if (winner) winner[i] = e->term_winner;
+        for (int k = 0; k < n; ++k) {
+            if (hits) hits[i * n + k] = e->term_hits[k];
+            if (be_hits) be_hits[i * n + k] = e->term_be_hits[k];
         }
     }
 }

@@ -7,9 +7,9 @@
 The reference opens a window, lets ``BotFactory.create_bot(bot1)`` drive tank 0 and ``create_bot(bot2)`` tank 1 of a
 ``GamingENV(mode="bot_vs_bot")``, both deciding on the pre-tick state (bot_arena.py:51-58), and resets as soon as one
 of the tanks dies (bot_arena.py:61-70).  Here N such matches run at once in ``MultiAgentEnv(mode="bot_vs_bot",
-bot_types=(bot1, bot2))`` with both controllers on the device.  The env is created with ``auto_reset=False`` so that
-the winner can be read at the terminal tick (``info["winner"]`` = first alive tank, gym_env.py:97; -1 = both died in
-the same tick) before the finished matches are reset by a masked ``reset()`` - the reference's own order.
+bot_types=(bot1, bot2))`` with both controllers on the device and finished matches restarted inside the step; the
+winner is ``info["winner"]`` of the terminal tick (first alive tank, gym_env.py:97; -1 = both died in the same tick),
+which the step latches before its auto-reset (``at_get_terminal_info``).
 ``--terminate-time T`` gives the stress variant of BASELINE config 4 (immortal tanks, bullets saturate)."""
 import argparse
 import os
@@ -29,7 +29,7 @@ def run_bot_matches(bot1_type, bot2_type, num_envs=4096, ticks=1000, device="cud
     from alphatank_b200 import MultiAgentEnv
     dev = torch.device(device)
     env = MultiAgentEnv(mode="bot_vs_bot", bot_types=(bot1_type, bot2_type), num_envs=num_envs, device=dev, seed=seed,
-                        auto_reset=False, terminate_time=terminate_time, map=map)
+                        terminate_time=terminate_time, map=map)
     env.reset()
     wins = torch.zeros(3, dtype=torch.int64, device=dev)              # bot1, bot2, nobody
     length = torch.zeros(num_envs, dtype=torch.int64, device=dev)
@@ -41,14 +41,13 @@ def run_bot_matches(bot1_type, bot2_type, num_envs=4096, ticks=1000, device="cud
         _, _, done, _, _ = env.step()
         length += 1
         d = done.bool()
-        gi = env.core.get_info()                                      # = info: state at the terminal tick (not yet reset)
+        gi = env.core.get_info(terminal=True)                         # = info of this step: the finished match's where done
         w = gi["winner"].long()
         idx = torch.where(w < 0, torch.full_like(w, 2), w)
         wins += torch.bincount(idx[d], minlength=3)[:3]
         total_len += length[d].sum()
         hits += gi["hits"].long()[d].sum(0)
         length.masked_fill_(d, 0)
-        env.reset(mask=done)
     torch.cuda.synchronize(dev)
     dt = time.perf_counter() - t0
     w = wins.tolist()

@@ -17,11 +17,10 @@ What is kept from the reference (train_ppo_cycle.py:24-92, 244-256, 258-445):
 * ``run_evaluation`` (:122-206): win rate and mean reward of the agent against every bot type.
 
 What differs because N battles run at once: one env handle, rollout buffer and CUDA graph per bot type (a graph holds
-the handle it was captured on); during training an episode's outcome is read from the rollout itself - the
-terminal tick's reward increment is +50 for the agent's kill and -50 for its death (gaming_env.py:522-541), the shaped
-terms stay below 13 per tick, so ``increment > 25`` <=> ``info["winner"] == 1`` - because the auto-reset inside the
-step has already replaced the terminal state; the evaluation uses ``auto_reset=False`` and reads ``info["winner"]``
-itself.  W&B logging and the video recorder are out of scope."""
+the handle it was captured on); an episode's outcome is ``info["winner"] == 1`` at its terminal tick exactly as in the
+reference (:341, :357) - the step latches the finished episode's info before its auto-reset (``at_get_terminal_info``),
+and the rollout stores it per tick (``RolloutBuffer(keep_winner=True)``).  W&B logging and the video recorder are out
+of scope."""
 import argparse
 import collections
 import math
@@ -106,22 +105,19 @@ def select_next_bot(config, tracker, current_bot, rng):
     return str(rng.choice(config.bot_types, p=[probs[b] for b in config.bot_types]))
 
 
-def rollout_outcomes(buf, last_cum):
-    """(wins, episodes, terminal increments) of the episodes that ended inside a filled rollout buffer.  ``last_cum``:
-    the cumulative rewards returned by the last tick of the previous rollout of the same env ([N, 1])."""
-    cum = buf.env_rewards                                                # [T, N, 1] cumulative per episode
-    prev = torch.cat([last_cum.unsqueeze(0), cum[:-1]], 0)
-    prev = prev * (1.0 - buf.dones[:-1].to(torch.float32)).unsqueeze(-1)  # dones[t]: obs[t] starts an episode
-    inc = (cum - prev).squeeze(-1)                                       # [T, N]
+def rollout_outcomes(buf):
+    """(wins, episodes, won[T, N]) of the episodes that ended inside a filled rollout buffer: the agent (tank 1) won
+    where the terminal tick's ``info["winner"]`` is 1 (train_ppo_cycle.py:341, 357)."""
     ended = buf.dones[1:].bool()
-    won = ended & (inc > 25.0)
+    won = ended & (buf.winner == 1)
     return int(won.sum()), int(ended.sum()), won
 
 
 @torch.no_grad()
 def run_evaluation(learner, bot_types, num_envs, ticks, device, seed=12345, weakness=1.0):
     """train_ppo_cycle.py:122-206: the agent against every bot type; win = ``info["winner"] == 1`` at the terminal
-    tick (:181).  ``num_envs`` battles for ``ticks`` ticks each instead of ``eval_episodes`` sequential episodes."""
+    tick (:181).  ``num_envs`` battles for ``ticks`` ticks each instead of ``eval_episodes`` sequential episodes; the
+    finished battles are reset by the caller after reading info, the reference's own order."""
     from alphatank_b200 import MultiAgentEnv
     from alphatank_b200.learner.ppo import SingleAgentView
     results = {}
@@ -179,9 +175,9 @@ def train_cycle(config, num_envs=4096, updates=None, seed=0, eval_envs=1024, eva
             obs_dim = env.observation_space.shape[0] // env.num_tanks
             if learner is None:
                 learner = PPOLearner(1, obs_dim, tuple(int(x) for x in env.action_space.nvec[:3]), cfg, dev, seed=seed)
-            buf = RolloutBuffer(T, num_envs, 1, obs_dim, dev, keep_raw=False)
+            buf = RolloutBuffer(T, num_envs, 1, obs_dim, dev, keep_raw=False, keep_winner=True)
             slots[bot] = {"env": env, "buf": buf, "runner": RolloutRunner(SingleAgentView(env), learner, buf),
-                          "first": True, "last_cum": torch.zeros((num_envs, 1), dtype=torch.float32, device=dev)}
+                          "first": True}
         return slots[bot]
 
     current_bot = config.bot_types[0]
@@ -201,8 +197,7 @@ def train_cycle(config, num_envs=4096, updates=None, seed=0, eval_envs=1024, eva
         torch.cuda.synchronize(dev)
         t1 = time.perf_counter()
         buf = s["buf"]
-        wins, episodes, won = rollout_outcomes(buf, s["last_cum"])
-        s["last_cum"] = buf.env_rewards[-1].clone()
+        wins, episodes, won = rollout_outcomes(buf)
         s["first"] = False
         # victory bonus, gated by the curriculum (train_ppo_cycle.py:341-350)
         rates = [tracker.get_win_rate(b) for b in config.bot_types]

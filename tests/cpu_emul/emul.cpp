@@ -97,7 +97,7 @@ static void run_t(em_env *env, bool is_step, const int32_t *actions, const uint8
                 const bool d = s.wrapper_step(actions ? actions + e * c.act_rows * 3 : nullptr, rw);
                 for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
                 done[e] = d ? 1 : 0;
-                if (d && c.auto_reset) s.env_reset();
+                if (d && c.auto_reset) { s.latch_terminal_info(); s.env_reset(); }
                 s.store();
                 emit = obs != nullptr;
             } else if (!mask || mask[e]) {
@@ -147,6 +147,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     const ArenaLayout L = arena_layout(env->k, n_envs);
     env->arena.assign(L.bytes, 0);
     bind_state(env->st, env->arena.data(), L, n_envs);
+    memset(env->arena.data() + L.o_ttick, 0xFF, 4 * (size_t)n_envs);   // no terminal info latched yet
     memcpy(env->arena.data() + L.o_trig, env->luts.trig.data(), 722 * 8);
     memcpy(env->arena.data() + L.o_corn, env->luts.corn.data(), 361 * 4 * 8);
     memcpy(env->arena.data() + L.o_pend, env->luts.pend.data(), PEND_LUT * 8);
@@ -213,6 +214,23 @@ void em_get_info(em_env *env, int32_t *winner, int32_t *hits, int32_t *be_hits, 
             if (change_time) change_time[e * c.n_tanks + i] = st.change_time[g];
         }
         if (winner) winner[e] = w;
+    }
+}
+void em_get_terminal_info(em_env *env, int32_t *winner, int32_t *hits, int32_t *be_hits, int32_t *change_time,
+                          uint8_t *latched) {   // = info_kernel<true>
+    const KCfg &c = env->k;
+    const DevState &st = env->st;
+    em_get_info(env, winner, hits, be_hits, change_time);
+    for (int64_t e = 0; e < st.N; ++e) {
+        const bool lt = st.term_tick[e] == st.tick[e];
+        if (latched) latched[e] = lt ? 1 : 0;
+        if (!lt) continue;
+        if (winner) winner[e] = (int)st.term_winner[e] - 1;
+        for (int i = 0; i < c.n_tanks; ++i) {
+            int64_t g = (int64_t)i * st.N + e;
+            if (hits) hits[e * c.n_tanks + i] = (int32_t)(st.term_hits[g] & 0xFFFFu);
+            if (be_hits) be_hits[e * c.n_tanks + i] = (int32_t)(st.term_hits[g] >> 16);
+        }
     }
 }
 int em_bfs(const uint8_t *maze121, int sr, int sc, int gr, int gc, int *next_r, int *next_c) {

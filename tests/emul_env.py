@@ -41,6 +41,7 @@ def lib():
         L.em_get_state.argtypes = [vp, i64, vp]
         L.em_set_state.argtypes = [vp, i64, vp]
         L.em_get_info.argtypes = [vp, vp, vp, vp, vp]
+        L.em_get_terminal_info.argtypes = [vp, vp, vp, vp, vp, vp]
         L.em_bfs.argtypes = [vp, i32, i32, i32, i32, vp, vp]
         L.em_generate_maze.argtypes = [C.c_uint64, i64, vp, vp]
         L.em_jump_axis.restype = C.c_double
@@ -107,6 +108,17 @@ class EmulEnv:
         change = np.zeros((self.n_envs, n), np.int32)
         self.L.em_get_info(self.h, winner.ctypes.data, hits.ctypes.data, be_hits.ctypes.data, change.ctypes.data)
         return {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change}
+
+    def terminal_info(self):
+        n = self.n_tanks
+        winner = np.zeros(self.n_envs, np.int32)
+        hits = np.zeros((self.n_envs, n), np.int32)
+        be_hits = np.zeros((self.n_envs, n), np.int32)
+        change = np.zeros((self.n_envs, n), np.int32)
+        latched = np.zeros(self.n_envs, np.uint8)
+        self.L.em_get_terminal_info(self.h, winner.ctypes.data, hits.ctypes.data, be_hits.ctypes.data, change.ctypes.data,
+                                    latched.ctypes.data)
+        return {"winner": winner, "hits": hits, "be_hits": be_hits, "change_time": change, "latched": latched}
 
 
 def make_emul_env(spec, n_envs, seed, env_id_base=0, auto_reset=False):

@@ -33,3 +33,6 @@ class GpuEnv:
 
     def info(self):
         return {k: v.cpu().numpy() for k, v in self.core.get_info().items()}
+
+    def terminal_info(self):
+        return {k: v.cpu().numpy() for k, v in self.core.get_info(terminal=True).items()}

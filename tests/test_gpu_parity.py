@@ -58,6 +58,11 @@ def test_cuda_matches_oracle_on_batches(name):
             name, t, np.unique(np.nonzero(ra != rb)[0])[:8])
         if not np.array_equal(oa, ob):
             raise AssertionError("%s tick %d obs differ at (env, col) %s" % (name, t, np.argwhere(oa != ob)[:8].tolist()))
+        if da.any() or t == 0:   # info of the step as the reference's callers see it: the finished episode's, latched before the auto-reset
+            ta, tb = a.terminal_info(), b.terminal_info()
+            for f in ta:
+                assert np.array_equal(ta[f], tb[f]), "%s tick %d terminal info %s" % (name, t, f)
+            assert np.array_equal(tb["latched"], db)
         dones += int(da.sum())
     sa, sb = a.get_state(), b.get_state()
     n = a.n_tanks

@@ -38,6 +38,10 @@ def test_masked_reset_after_the_step_equals_the_auto_reset_inside_it():
         oa, ra, da, _, _ = a.step()
         ob, rb, db, _, _ = b.step()
         assert torch.equal(da, db) and torch.equal(ra, rb), t
+        ia, ib = a.core.get_info(terminal=True), b.core.get_info()          # b: not yet reset = the reference's info
+        assert torch.equal(ia["latched"], da)
+        for k in ("winner", "hits", "be_hits", "change_time"):
+            assert torch.equal(ia[k], ib[k]), (t, k)
         ended += int(db.sum())
         ob = b.reset(mask=db)[0].view(N, -1)
         assert torch.equal(oa, ob), t
@@ -58,34 +62,34 @@ def test_bot_arena_counts_every_match_once():
         arena.run_bot_matches("aggressive", "nosuchbot", num_envs=32, ticks=1)
 
 
-def test_terminal_reward_increment_identifies_the_winner():
-    """train_ppo_cycle.py reads a training episode's outcome from the rollout: terminal increment > 25 <=> the agent
-    (tank 1) is the first alive tank at the terminal tick, i.e. info["winner"] == 1 (train_ppo_cycle.py:341)."""
+def test_rollout_buffer_keeps_the_terminal_winner_of_every_tick():
+    """RolloutBuffer(keep_winner=True): the graph-captured rollout stores info["winner"] of every tick; replaying the
+    recorded actions through an env without auto-reset gives the same winners at the terminal ticks."""
     from alphatank_b200 import MultiAgentEnv
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
+    from alphatank_b200.learner.ppo import SingleAgentView
     dev = torch.device("cuda:0")
-    N = 4096
-    for bot in ("aggressive", "smart"):
-        env = MultiAgentEnv(mode="bot_agent", type="train", bot_type=bot, num_envs=N, device=dev, seed=5, auto_reset=False)
-        env.reset()
-        prev = torch.zeros(N, device=dev)
-        acts = torch.zeros((N, 2, 3), dtype=torch.int32, device=dev)
-        g = torch.Generator(device="cuda").manual_seed(1)
-        ended = wins = 0
-        for t in range(400):
-            acts[:, 1, 0] = torch.randint(0, 3, (N,), device=dev, generator=g)
-            acts[:, 1, 1] = torch.randint(0, 3, (N,), device=dev, generator=g)
-            acts[:, 1, 2] = torch.randint(0, 2, (N,), device=dev, generator=g)
-            _, rew, done, _, info = env.step(acts)
+    N, T = 512, 24
+    env = MultiAgentEnv(mode="bot_agent", type="train", bot_type="aggressive", num_envs=N, device=dev, seed=5)
+    ref = MultiAgentEnv(mode="bot_agent", type="train", bot_type="aggressive", num_envs=N, device=dev, seed=5, auto_reset=False)
+    learner = PPOLearner(1, 388, (3, 3, 2), PPOConfig(num_steps=T), dev, seed=0)
+    buf = RolloutBuffer(T, N, 1, 388, dev, keep_raw=False, keep_winner=True)
+    runner = RolloutRunner(SingleAgentView(env), learner, buf)
+    ref.reset()
+    acts = torch.zeros((N, 2, 3), dtype=torch.int32, device=dev)
+    ended = wins = 0
+    for it in range(4):                                   # it 0: eager, it 1: capture + replay, then replays
+        runner.run(first=(it == 0))
+        for t in range(T):
+            acts[:, 1] = buf.actions[t, :, 0]
+            _, _, done, _, info = ref.step(acts)
+            assert torch.equal(done, buf.dones[t + 1]), (it, t)
             d = done.bool()
-            inc = rew[:, 1] - prev
-            w = info["winner"]
-            assert torch.equal((inc > 25.0)[d], (w == 1)[d]), (bot, t)
+            assert torch.equal(info["winner"][d], buf.winner[t][d]), (it, t)
             ended += int(d.sum())
-            wins += int((w == 1)[d].sum())
-            prev = torch.where(d, torch.zeros_like(prev), rew[:, 1])
-            env.reset(mask=done)
-        assert ended > 200 and 0 < wins < ended, (bot, ended, wins)
-        env.close()
+            wins += int((buf.winner[t][d] == 1).sum())
+            ref.reset(mask=done)
+    assert ended > 100 and 0 < wins < ended, (ended, wins)
 
 
 def test_ppo_cycle_rotates_bots_follows_the_weakness_schedule_and_saves(tmp_path):
