@@ -133,3 +133,20 @@ def test_ppo_ppo_training_script_runs_and_saves_reference_layout(tmp_path):
     for i in range(2):
         sd = torch.load(str(tmp_path / ("ppo_agent_%d.pt" % i)), map_location="cpu", weights_only=False)
         assert list(sd) == list(PPOAgentPPO(388).state_dict())
+
+
+def test_sac_ppo_training_script_runs_and_saves_reference_layout(tmp_path):
+    """scripts/train_sac_ppo.py (the reference's PPO-vs-SAC trainer, batched): tank 0 learns by PPO from the on-policy
+    rollout, tank 1 by SAC from the replay buffer; ppo_agent.pt / sac_agent.pt in the reference's layouts."""
+    from alphatank_b200.learner import PPOAgentPPO
+    script = os.path.join(REPO, "scripts", "train_sac_ppo.py")
+    out = subprocess.run([sys.executable, script, "--num-envs", "512", "--iterations", "2", "--ppo-num-steps", "16",
+                          "--ppo-num-epochs", "1", "--sac-update-every", "3", "--sac-batch-size", "128", "--capacity",
+                          "20000", "--ckpt-dir", str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "iter 1" in out.stdout and "Saved models" in out.stdout
+    sd = torch.load(str(tmp_path / "ppo_agent.pt"), map_location="cpu", weights_only=False)
+    assert list(sd) == list(PPOAgentPPO(388).state_dict())
+    sd = torch.load(str(tmp_path / "sac_agent.pt"), map_location="cpu", weights_only=False)
+    assert set(sd) == {"actor", "critic1", "critic2", "critic1_target", "critic2_target", "log_alpha"}
+    assert sd["actor"]["fc1.weight"].shape == (256, 388)
