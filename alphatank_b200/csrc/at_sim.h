@@ -336,6 +336,10 @@ AT_HD int select_bit(M128 m, int k) {
 // config; 2 = 1 + exactly four tanks; 3 = 2 + the 2a_vs_2b tank layout).  SPEC 1 = team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME - the 2v2 / NvM
 // team_vs_bot workloads: the other bots, the 1v1 modes, the maze generator and the arena ordering drop out of the
 // kernel (the generic build is 630 KB of SASS and stalls on instruction fetch).
+#ifndef AT_BULLET_SPLIT
+#define AT_BULLET_SPLIT 0   // 1: bullets_pass runs bullet_geom + bullet_commit instead of bullet_move (experiment)
+#endif
+
 template <int SPEC>
 struct SimT {
     AT_HD int cfg_mode() const { return SPEC >= 1 ? 3 : c.mode; }
@@ -615,6 +619,111 @@ struct SimT {
         return gone;
     }
 
+    // ---- bullet_move in two halves (AT_BULLET_SPLIT, an experiment; default off).  bullet_geom: everything of a move
+    // that depends only on the bullet and on state a pass does not change (tank positions, walls) - new position,
+    // bounce, and per enemy tank the reward class / range / rect-hit bits, computed for EVERY enemy, alive or not.
+    // bullet_commit: what must happen in firing order - the f64 reward additions, the pending-penalty state, the
+    // kill - driven by those bits and filtered by the alive mask as it is at that moment.  Same arithmetic as
+    // bullet_move, so the two forms are interchangeable bit for bit (tests: emulator and kernel against the oracle).
+    struct BRec {
+        double nx, ny;
+        uint64_t m;        // flips / bounces / distance already advanced; cleared / pending as loaded
+        uint64_t ef;       // 6 bits per tank i at [6 i, 6 i + 6): in-range, hi, lo, within-100, within-113 (box), rect hit
+    };
+    static constexpr uint64_t EF_RANGE = 1, EF_HI = 2, EF_LO = 4, EF_N100 = 8, EF_N113 = 16, EF_HIT = 32;
+    AT_HD void bullet_geom(double x, double y, uint64_t m, BRec &R) const {
+        const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u);
+        const bool fx = (m >> BM_FLIPX) & 1u, fy = (m >> BM_FLIPY) & 1u;
+        int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
+        const double cv = cosr(ang), sv = sinr(ang);
+        const double dx = fx ? -cv : cv, dy = fy ? sv : -sv;
+        const double nx = x + dx, ny = y + dy;
+        const int ix = d2i(nx), iy = d2i(ny);
+        double u0, u1;
+        unit_dir(ang, u0, u1);
+        const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
+        uint64_t ef = 0;
+        int idx00;
+        uint32_t sel;
+        rect_cells(ix, iy, 5, 5, idx00, sel);
+        int cell = -1;
+        bool near_tank = false;
+        if (window13(iclo, ichi, idx00) & sel) {
+            const uint32_t ww = window13(wlo, whi, idx00) & sel;
+            cell = ww ? idx00 + ffs32(ww) : -1;
+            near_tank = (window13(tclo, tchi, idx00) & sel) != 0u;
+        }
+        for (uint32_t bits = ((1u << cfg_n()) - 1u) & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // every enemy
+            const int i = ffs32(bits);
+            const double tx = TX(i) - x, ty = TY(i) - y;
+            uint64_t f = 0;
+            if (fabs(tx) < 113.0 && fabs(ty) < 113.0) f |= EF_N113;
+            if (near_tank && rect5_hits_tank(ix, iy, i)) f |= EF_HIT;
+            const double s2 = np_dot2(tx, ty, tx, ty);
+            if (!(fabs(tx) > 301.0 || fabs(ty) > 301.0 || s2 > S300)) {
+                const double q = d0 * tx + d1 * ty;
+                const double q2 = q * q, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
+                bool hi, lo;
+                if (s2 > 0.0 && !(q > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps))) {
+                    hi = q > 0.0 && q2 > a81;
+                    lo = !(q > 0.0 && q2 >= b01);
+                } else {
+                    const double dt = sqrt(s2);
+                    const double dp = np_dot2(d0, d1, tx / dt, ty / dt);
+                    hi = dp > 0.9;
+                    lo = dp < 0.1;
+                }
+                f |= EF_RANGE | (hi ? EF_HI : 0) | (lo ? EF_LO : 0) | (s2 < S100 ? EF_N100 : 0);
+            }
+            ef |= f << (6 * i);
+        }
+        bool nfx = fx, nfy = fy;
+        if (cell >= 0) {
+            const bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
+            if (bxh) nfx = !nfx;
+            if (byh) nfy = !nfy;
+            ++bounces;
+        }
+        ++dist;
+        R.nx = nx; R.ny = ny; R.ef = ef;
+        R.m = (m & ~((1ull << BM_FLIPX) | (1ull << BM_FLIPY) | (7ull << BM_BOUNCES) | (511ull << BM_DIST))) |
+              ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) | ((uint64_t)bounces << BM_BOUNCES) |
+              ((uint64_t)dist << BM_DIST);
+    }
+    AT_HD bool bullet_commit(const BRec &R, double &x, double &y, uint64_t &m, uint32_t &near_tanks) {
+        m = R.m;
+        const int owner = (int)(m & 15u);
+        const int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
+        bool cleared = (m >> BM_CLEARED) & 1u;
+        uint32_t pcnt = (uint32_t)((m >> BM_PEND) & 0xFFFFu);
+        int victim = -1;
+        for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies, list order
+            const int i = ffs32(bits);
+            const uint32_t f = (uint32_t)(R.ef >> (6 * i)) & 63u;
+            if (f & EF_N113) near_tanks |= 1u << i;
+            if ((f & EF_HIT) && victim < 0) victim = i;
+            if (!(f & EF_RANGE)) continue;
+            if (f & EF_HI) TREW(owner) += 0.01;
+            else if (f & EF_LO) { if (!cleared) ++pcnt; }
+            if (f & EF_N100) { pcnt = 0; cleared = true; }
+        }
+        x = R.nx;
+        y = R.ny;
+        bool gone = false;
+        if (victim >= 0) {
+            if (cfg_terminate() == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
+            THITS(owner) += 1u;
+            THITS(victim) += 1u << 16;
+            reward_by_bullets(owner, victim);
+            gone = true;
+        } else if (bounces >= 6 || dist >= 300) {
+            if (!cleared && pcnt > 0) TREW(owner) -= ldg(st.pend + pcnt);
+            gone = true;
+        }
+        m = (m & ~((1ull << BM_CLEARED) | (0xFFFFull << BM_PEND))) | ((uint64_t)cleared << BM_CLEARED) | ((uint64_t)pcnt << BM_PEND);
+        return gone;
+    }
+
     // `for bullet in self.bullets[:]: bullet.move()` (gaming_env.py:71-72, 378-379): firing order, stable
     // compaction in place; also rebuilds the per-owner live counts and ranks (obs uses them).
     AT_HD void bullets_pass() {
@@ -637,6 +746,40 @@ struct SimT {
         iclo = tclo | wlo; ichi = tchi | whi;
         // software pipelining: the next bullet's record is requested before the current one is processed (the
         // columns come from L2/HBM - shared memory leaves the SM almost no L1 - and a move is ~300 instructions)
+#if AT_BULLET_SPLIT == 2
+        // two moves per iteration: their geometry halves are independent instruction streams (ILP for the latency-bound
+        // fp64 chains), the commits follow in firing order
+        auto keep = [&](double x, double y, uint64_t m, uint32_t near_tanks) {
+            const int ow = (int)(m & 15u);
+            for (; near_tanks; near_tanks &= near_tanks - 1) near_set(ffs32(near_tanks), (int)w);
+            uint32_t rank = TLIVE(ow)++;
+            bm.slot_of[(ow * SLOTS_PER_TANK + (int)rank) * BS + tid] = (uint8_t)w;
+            m = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
+            st.bx[G(w)] = x;
+            st.by[G(w)] = y;
+            st.bmeta[G(w)] = m;
+            ++w;
+        };
+        double ax_ = 0.0, ay_ = 0.0, bx_ = 0.0, by_ = 0.0;
+        uint64_t am_ = 0, bm_ = 0;
+        if (n > 0) { ax_ = st.bx[G(0)]; ay_ = st.by[G(0)]; am_ = st.bmeta[G(0)]; }
+        if (n > 1) { bx_ = st.bx[G(1)]; by_ = st.by[G(1)]; bm_ = st.bmeta[G(1)]; }
+        for (uint32_t r = 0; r < n; r += 2) {
+            double xa = ax_, ya = ay_, xb = bx_, yb = by_;
+            uint64_t ma = am_, mb = bm_;
+            const bool has_b = r + 1 < n;
+            if (r + 2 < n) { ax_ = st.bx[G(r + 2)]; ay_ = st.by[G(r + 2)]; am_ = st.bmeta[G(r + 2)]; }
+            if (r + 3 < n) { bx_ = st.bx[G(r + 3)]; by_ = st.by[G(r + 3)]; bm_ = st.bmeta[G(r + 3)]; }
+            BRec RA, RB;
+            bullet_geom(xa, ya, ma, RA);
+            if (has_b) bullet_geom(xb, yb, mb, RB);
+            uint32_t nta = 0, ntb = 0;
+            if (!bullet_commit(RA, xa, ya, ma, nta)) keep(xa, ya, ma, nta);
+            if (has_b && !bullet_commit(RB, xb, yb, mb, ntb)) keep(xb, yb, mb, ntb);
+        }
+        cnt = w;
+        return;
+#endif
         double nx_ = 0.0, ny_ = 0.0;
         uint64_t nm_ = 0;
         if (n > 0) { nx_ = st.bx[G(0)]; ny_ = st.by[G(0)]; nm_ = st.bmeta[G(0)]; }
@@ -645,7 +788,13 @@ struct SimT {
             uint64_t m = nm_;
             if (r + 1 < n) { nx_ = st.bx[G(r + 1)]; ny_ = st.by[G(r + 1)]; nm_ = st.bmeta[G(r + 1)]; }
             uint32_t near_tanks = 0;
+#if AT_BULLET_SPLIT
+            BRec R;
+            bullet_geom(x, y, m, R);
+            if (!bullet_commit(R, x, y, m, near_tanks)) {
+#else
             if (!bullet_move(x, y, m, near_tanks)) {
+#endif
                 const int ow = (int)(m & 15u);
                 for (; near_tanks; near_tanks &= near_tanks - 1) near_set(ffs32(near_tanks), (int)w);
                 uint32_t rank = TLIVE(ow)++;
