@@ -25,10 +25,27 @@ def build():
 _lib = None
 
 
-def lib():
+def build_variant(defines, tag):
+    """The emulator compiled with extra -D switches of at_sim.h (experiment paths kept behind default-off switches)."""
+    out = os.path.join(HERE, "cpu_emul", "libat_emul_%s.so" % tag)
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("at_sim.h", "at_host.h", "at_types.h", "at_rows.h")]
+    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-ffp-contract=off", "-mfma", "-std=c++17", "-shared"] +
+                              ["-D" + d for d in defines] + ["-o", out, SRC, "-lm"])
+    return out
+
+
+def use_library(path=None):
+    """Switch the emulator library the next EmulEnv objects bind (None: back to the default build)."""
+    global _lib
+    _lib = None
+    return lib(path)
+
+
+def lib(path=None):
     global _lib
     if _lib is None:
-        L = C.CDLL(build())
+        L = C.CDLL(path or build())
         vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
         L.em_create.argtypes = [vp, i64, i64, C.c_uint64, C.POINTER(vp)]
         L.em_destroy.argtypes = [vp]

@@ -233,3 +233,29 @@ def test_simulation_specialisations_agree(cap):
                 assert np.array_equal(da, db) and np.array_equal(ra, rb) and np.array_equal(oa, ob), (cap, t)
     finally:
         emul_env.lib().em_set_spec_cap(3)
+
+
+@pytest.mark.parametrize("split", [1, 2])
+def test_bullet_split_switch_is_bit_exact(split):
+    """AT_BULLET_SPLIT (default off; profiles/r04c_step_kernels.md r04g): bullet_move as bullet_geom + bullet_commit,
+    one or two bullets per iteration - the same streams as the oracle on the bench configuration and a 1v1 arena."""
+    path = emul_env.build_variant(["AT_BULLET_SPLIT=%d" % split], "split%d" % split)
+    try:
+        emul_env.use_library(path)
+        for name in ("team_vs_bot", "arena_def_dodge_t200"):
+            spec = SWEEP[name]
+            N, ticks, seed, base = 70, 220, 31, 64
+            a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
+            b = emul_env.make_emul_env(spec, N, seed, base, auto_reset=True)
+            assert np.array_equal(a.reset(), b.reset())
+            ids = np.arange(base, base + N)
+            for t in range(ticks):
+                acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
+                oa, ra, da = a.step(acts, threads=4)
+                ob, rb, db = b.step(acts)
+                assert np.array_equal(da, db) and np.array_equal(ra, rb) and np.array_equal(oa, ob), (name, t)
+            sa, sb = a.get_state(), b.get_state()
+            for f in ("n_bullets", "rng_ctr"):
+                assert np.array_equal(sa[f], sb[f]), f
+    finally:
+        emul_env.use_library(None)
