@@ -78,6 +78,7 @@ class BatchedTankEnv:
         self.done = torch.zeros((N,), dtype=torch.uint8, device=dev)
         self._actions = torch.zeros((N, max(self.A, 1), 3), dtype=torch.int32, device=dev)
         self._h_rewards = self._h_done = None
+        self._prev_cum = None                     # delta_rewards(): the cumulative rewards of the previous step
 
     def close(self):
         if getattr(self, "h", None):
@@ -96,7 +97,25 @@ class BatchedTankEnv:
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         _capi.check(self.L.at_reset(self.h, _ptr(m), _ptr(obs), self._stream()), "at_reset")
+        if self._prev_cum is not None:            # a reset episode starts from zero (gaming_env.py:48-66 zeroes tank.reward)
+            if m is None:
+                self._prev_cum.zero_()
+            else:
+                self._prev_cum.masked_fill_(m.bool().unsqueeze(-1), 0.0)
         return obs
+
+    def delta_rewards(self, rewards, done):
+        """Per-step reward increments from the CUMULATIVE per-episode rewards the reference's wrappers return
+        (gym_env.py:186-187, gym_env_multi.py:307-308; quirk F1): r_t - r_(t-1) inside an episode, r_t on its first
+        step.  Call once per step with that step's outputs; explicit resets are tracked by reset()."""
+        if self._prev_cum is None:
+            self._prev_cum = torch.zeros_like(rewards)
+        out = rewards - self._prev_cum
+        if self.cfg.auto_reset:                   # an env that returned done has been reset inside the step
+            self._prev_cum = rewards * (1.0 - done.to(torch.float32)).unsqueeze(-1)
+        else:
+            self._prev_cum = rewards.clone()
+        return out
 
     def _device_actions(self, actions):
         if self.A == 0:

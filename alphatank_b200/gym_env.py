@@ -37,7 +37,10 @@ class MultiAgentEnv:
 
     def __init__(self, mode="agent", type="train", bot_type="smart", weakness=1.0, *, num_envs=1, device="cuda:0",
                  seed=0, env_id_base=0, auto_reset=True, map=None, terminate_time="config", buff_on=None,
-                 debuff_on=None, bot_types=None):
+                 debuff_on=None, bot_types=None, reward_mode="cumulative"):
+        if reward_mode not in ("cumulative", "delta"):
+            raise ValueError("reward_mode must be 'cumulative' (the reference's per-episode running sum) or 'delta'")
+        self.reward_mode = reward_mode
         if mode not in _1V1_MODES:
             raise ValueError("mode %r is not supported by the batched env (keyboard modes 'bot', 'human_play' and "
                              "'human' need a display); valid: %s" % (mode, sorted(_1V1_MODES)))
@@ -103,6 +106,8 @@ class MultiAgentEnv:
     def step(self, actions=None):
         self.training_step += 1
         obs, rewards, done = self.core.step(actions)
+        if self.reward_mode == "delta":
+            rewards = self.core.delta_rewards(rewards, done)
         return obs, rewards, done, False, LazyInfo(self.core, ("change_time", "winner"))
 
     def step_host(self, h_actions=None):

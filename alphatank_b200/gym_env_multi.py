@@ -25,7 +25,10 @@ class MultiAgentTeamEnv:
     are rejected (keyboard)."""
 
     def __init__(self, game_configs, *, num_envs=1, device="cuda:0", seed=0, env_id_base=0, auto_reset=True, map=None,
-                 terminate_time="config", buff_on=None, debuff_on=None):
+                 terminate_time="config", buff_on=None, debuff_on=None, reward_mode="cumulative"):
+        if reward_mode not in ("cumulative", "delta"):
+            raise ValueError("reward_mode must be 'cumulative' (the reference's per-episode running sum) or 'delta'")
+        self.reward_mode = reward_mode
         self.game_configs = game_configs
         teams, ctrl, bots, ids = [], [], [], {}
         self._agent_names = []
@@ -69,6 +72,8 @@ class MultiAgentTeamEnv:
     def step(self, actions=None):
         self.training_step += 1
         obs, rewards, done = self.core.step(actions)
+        if self.reward_mode == "delta":
+            rewards = self.core.delta_rewards(rewards, done)
         return obs, rewards, done, False, LazyInfo(self.core, ("hits", "be_hits"))
 
     def step_host(self, h_actions=None):

@@ -379,3 +379,37 @@ def test_simulation_specialisations_equal_the_generic_kernel(cap):
         assert np.array_equal(sa[f], sb[f]), f
     for f in ("x", "y", "reward", "angle", "alive", "num_hit", "num_be_hit"):
         assert np.array_equal(sa["tanks"][f][:, :4], sb["tanks"][f][:, :4]), f
+
+
+def test_delta_reward_mode_telescopes_to_the_reference_cumulative_rewards():
+    """reward_mode="delta" (both reward forms): the per-step increments of the reference's cumulative
+    per-episode rewards (quirk F1) - summed over an episode they give the cumulative stream back; explicit masked
+    resets restart the sum."""
+    import torch
+    from alphatank_b200 import MultiAgentEnv, MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    dev = torch.device("cuda:0")
+    N = 2048
+    for make, ar in ((lambda **kw: MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=9, **kw), True),
+                     (lambda **kw: MultiAgentEnv(mode="bot_agent", bot_type="aggressive", num_envs=N, device=dev, seed=9, **kw), False)):
+        a = make(auto_reset=ar)
+        b = make(auto_reset=ar, reward_mode="delta")
+        a.reset(); b.reset()
+        acc = torch.zeros((N, a.core.R), dtype=torch.float64, device=dev)
+        ended = 0
+        for t in range(300):
+            acts = a.core.synthetic_actions(t)
+            _, ra, da, _, _ = a.step(acts)
+            _, rb, db, _, _ = b.step(acts)
+            assert torch.equal(da, db)
+            acc += rb.double()
+            assert torch.allclose(acc, ra.double(), rtol=0, atol=5e-3), t
+            d = da.bool()
+            ended += int(d.sum())
+            acc[d] = 0.0
+            if not ar:                       # the reference's protocol: the caller resets finished envs
+                a.reset(mask=da); b.reset(mask=db)
+        assert ended > 50
+        with pytest.raises(ValueError):
+            make(reward_mode="per_tick")
+        a.close(); b.close()
