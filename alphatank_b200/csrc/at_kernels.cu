@@ -54,7 +54,7 @@ __host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots
     L.off_nearlo = o; o += (size_t)n * BS * 4;
     L.off_nearhi = o; o += n * SLOTS_PER_TANK > 32 ? (size_t)n * BS * 4 : 0;
     L.off_bpack = o; o += (size_t)nb * BS * 4;
-    L.off_tlive = o; o += (size_t)n * BS * 4;
+    L.off_tlive = o; o += (size_t)n * BS;
     L.off_tshot = o; o += (size_t)n * BS * 4;
     o = (o + 15) & ~(size_t)15;
     L.off_tmpl = o; o += fused ? (size_t)(4 * n_walls + CELLS + 4) * 4 : 0;  // +4: shifted so that it shares the rows' 16-byte phase
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     bm.bf0 = (double *)(smem + L.off_bf0); bm.bf1 = (double *)(smem + L.off_bf1);
     bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.nearlo = (uint32_t *)(smem + L.off_nearlo);
     bm.nearhi = (uint32_t *)(smem + L.off_nearhi);
-    bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint32_t *)(smem + L.off_tlive);
+    bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint8_t *)(smem + L.off_tlive);
     bm.tshot = (int32_t *)(smem + L.off_tshot);
     bm.slot_of = (uint8_t *)(smem + L.off_slot);
     uint8_t *udl = (uint8_t *)(smem + L.off_udelta);
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
         fence_async_smem();  // the template is later read by bulk-async copies
     }
     for (int i = 0; i < c.n_tanks; ++i) {  // lanes without an env still walk the emitter: give them inert data
-        bm.tlive[i * BS + tid] = 0u;
+        bm.tlive[i * BS + tid] = 0;
         bm.tpack[i * BS + tid] = 0u;
         bm.tx[i * BS + tid] = 0.0;
         bm.ty[i * BS + tid] = 0.0;
@@ -1371,6 +1371,15 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaFuncSetAttribute(env_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
     cudaFuncSetAttribute(env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
+    if (const char *cv = getenv("AT_SIM_CARVEOUT")) {   // experiment: shared-memory carve-out (percent) of the simulation kernels
+        const int pct = atoi(cv);
+        if (pct > 0 && pct <= 100) {
+            cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(env_kernel<true, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(env_kernel<true, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(env_kernel<true, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+    }
     {   // rows_kernel: the largest group (power of two, <= 4 envs) whose image keeps 12 warps on an SM, else whatever
         // fits at all; the G * 6n (env, slot) pairs must fit the lanes' prefetch registers (<= 3 per lane)
         const char *fz = getenv("AT_FUSED_ROWS"), *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");

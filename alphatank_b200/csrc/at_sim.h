@@ -397,7 +397,7 @@ struct SimT {
         if (cfg_n() * SLOTS_PER_TANK > 32) v |= (uint64_t)bm.nearhi[i * BS + tid] << 32;
         return v;
     }
-    AT_HD uint32_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
+    AT_HD uint8_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
     AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * BS + tid]; }
     // bot FSM columns exist only for bot tanks (bot_ord: ordinal among the bots)
     AT_HD uint32_t &BPACK(int i) const { return bm.bpack[cfg_bot_ord(i) * BS + tid]; }

@@ -78,7 +78,8 @@ struct BlockMem {
     double *trig;                  // [722] copy of st.trig
     double *tx, *ty, *trew;        // [n][BS]
     double *bf0, *bf1;             // [n][BS]
-    uint32_t *tpack, *bpack, *tlive;  // [n][BS]  (tlive: live bullets per owner)
+    uint32_t *tpack, *bpack;       // [n][BS]
+    uint8_t *tlive;                // [n][BS] live bullets per owner (<= 6)
     uint32_t *nearlo, *nearhi;     // [n][BS] bullet slots that may be within 100 px of the tank when it acts (hi: slots >= 32)
     int32_t *tshot;                // [n][BS]
     uint8_t *slot_of;              // [n*6][BS] bullet slot of (owner, per-owner rank), valid for rank < tlive

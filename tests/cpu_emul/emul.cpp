@@ -165,7 +165,7 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     bm.tx = (double *)p; p += n * BS * 8; bm.ty = (double *)p; p += n * BS * 8; bm.trew = (double *)p; p += n * BS * 8;
     bm.bf0 = (double *)p; p += n * BS * 8; bm.bf1 = (double *)p; p += n * BS * 8;
     bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.nearlo = (uint32_t *)p; p += n * BS * 4;
-    bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint32_t *)p; p += n * BS * 4;
+    bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint8_t *)p; p += n * BS * 4;
     bm.tshot = (int32_t *)p; p += n * BS * 4;
     bm.nearhi = (uint32_t *)p; p += n * BS * 4;
     env->tmpl.assign(4 * 72 + CELLS, 0.f);

@@ -19,7 +19,7 @@ one base
 for v in "$@"; do
     cp build/var/lib_$v.so alphatank_b200/libalphatank_b200.so
     one $v
-    timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "oracle_on_batches or full_size or specialisations" > gpurun_out/${TAG}_pytest_$v.log 2>&1
+    [ -n "$SKIP_TESTS" ] || timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "oracle_on_batches or full_size or specialisations" > gpurun_out/${TAG}_pytest_$v.log 2>&1
     tail -2 gpurun_out/${TAG}_pytest_$v.log
 done
 cp /tmp/lib_base.so alphatank_b200/libalphatank_b200.so
