@@ -1,16 +1,15 @@
 // at_kernels.cu - sm_100a kernels and the C ABI (include/alphatank_b200.h) of the batched alphaTank step.
 //
-// One fused kernel per tick (env_kernel<true>), one thread per env in both phases:
-//   phase A  simulation.  Tanks / bot FSMs of the block's 64 envs live in shared memory ([field][tank][thread],
-//            conflict-free); bullets stay in HBM as [slot][env] columns (every warp access is a contiguous run; the
-//            two advection passes, the dodge-reward scans and the obs reads hit L1/L2 after the first touch).
-//            Sequential per-env semantics (firing order, tank order) are trivially exact.  Rewards / done are
-//            written here; done envs are reset in place.
-//   phase B  observation rows.  Each thread emits its env's row values in layout order (uniform control flow, all
-//            lanes busy); the warp transposes 32 envs x 32 columns through a rotated, bank-conflict-free
-//            shared-memory tile into coalesced 128-byte row-chunk stores.  For fixed maps the 281 static wall / maze
-//            columns of every row are not recomputed: they sit once per block in shared memory and each thread
-//            ships them into its rows with one bulk-async (TMA, SASS UBLKCP) copy per row.
+// One tick = env_kernel (the simulation: state in, state / rewards / done out) + rows_kernel (the observation rows,
+// rebuilt from the stored state), the second launched as a programmatic dependent of the first.
+//   env_kernel   Tanks / bot FSMs of the block's 64 envs live in shared memory ([field][tank][thread],
+//                conflict-free); bullets stay in HBM as [slot][env] columns.  Every env has a home lane for its scalar
+//                bookkeeping; the bullets of a warp's 32 envs and the smart bots' line-of-sight queries are pooled
+//                into job lists that all 32 lanes work through (at_sim.h), so lane use does not depend on how many
+//                bullets each env happens to have.  Rewards / done are written here; done envs are reset in place.
+//   rows_kernel  Every warp assembles the R x D rows of a group of envs as an image in shared memory (static wall /
+//                maze columns once per warp, dynamic columns by independent jobs, at_rows.h) and ships the image with
+//                ONE bulk-async (TMA, SASS UBLKCP) copy.
 // The step is HBM-bound integer / fp64 work: no tensor cores anywhere.
 #include <cuda_runtime.h>
 #include <math.h>
@@ -33,46 +32,59 @@ using namespace at;
 // ------------------------------------------------------------------------------------------------ device
 namespace {
 
-constexpr int TILE_FLOATS = 32 * 33;  // per warp: 32 envs x 32 observation columns, row stride 33
 struct SmemLayout {
     int n;
-    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_nearlo, off_nearhi, off_bpack, off_tlive,
-        off_tshot, off_tmpl, off_tile, off_slot, off_udelta, off_losq, total;
+    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_ek, off_tpack, off_nearlo, off_nearhi, off_bpack,
+        off_tshot, off_ealive, off_eevt, off_eord, off_acts, off_res, off_jobs, off_tlive, off_udelta, off_losq, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int n, int n_walls, int n_bots, bool fused = true, int act_rows = 0) {
+// pooled = false: without the columns of the pooled bullet pass (ctrl_kernel)
+__host__ __device__ inline SmemLayout smem_layout(int n, int n_bots, int act_rows, bool pooled = true) {
     const int nb = n_bots > 0 ? n_bots : 1;
     SmemLayout L;
     L.n = n;
     size_t o = 0;
-    L.off_trig = o; o += 722 * 8;
+    L.off_trig = o;
     L.off_tx = o; o += (size_t)n * BS * 8;
     L.off_ty = o; o += (size_t)n * BS * 8;
     L.off_trew = o; o += (size_t)n * BS * 8;
     L.off_bf0 = o; o += (size_t)nb * BS * 8;
     L.off_bf1 = o; o += (size_t)nb * BS * 8;
+    L.off_ek = o; o += pooled ? (size_t)BS * 8 : 0;
     L.off_tpack = o; o += (size_t)n * BS * 4;
     L.off_nearlo = o; o += (size_t)n * BS * 4;
     L.off_nearhi = o; o += n * SLOTS_PER_TANK > 32 ? (size_t)n * BS * 4 : 0;
     L.off_bpack = o; o += (size_t)nb * BS * 4;
-    L.off_tlive = o; o += (size_t)n * BS;
     L.off_tshot = o; o += (size_t)n * BS * 4;
-    o = (o + 15) & ~(size_t)15;
-    L.off_tmpl = o; o += fused ? (size_t)(4 * n_walls + CELLS + 4) * 4 : 0;  // +4: shifted so that it shares the rows' 16-byte phase
-    o = (o + 15) & ~(size_t)15;
-    // fused: the observation tile (the action rows are staged in it before phase B needs it); split: only the staging area
-    L.off_tile = o; o += fused ? (size_t)(BS / 32) * TILE_FLOATS * 4 : (size_t)BS * act_rows * 3 * 4;
-    L.off_slot = o; o += (size_t)n * SLOTS_PER_TANK * BS;
-    L.off_udelta = o; o += 368;
+    L.off_ealive = o; o += pooled ? (size_t)BS * 4 : 0;
+    L.off_eevt = o; o += pooled ? (size_t)BS * 4 : 0;
+    L.off_eord = o; o += pooled ? (size_t)BS * 4 : 0;
+    L.off_acts = o; o += (size_t)BS * act_rows * 3 * 4;      // staging area of the action rows
+    L.off_res = o; o += pooled ? (size_t)n * SLOTS_PER_TANK * BS * 2 : 0;
+    L.off_jobs = o; o += pooled ? (size_t)(BS / 32) * 32 * SLOTS_PER_TANK * n * 2 : 0;
+    L.off_tlive = o; o += (size_t)n * BS;
+    L.off_udelta = o;
     L.off_losq = o; o += (size_t)(BS / 32) * 512;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
+__device__ inline void bind_block_mem(BlockMem &bm, unsigned char *smem, const SmemLayout &L) {
+    bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
+    bm.trew = (double *)(smem + L.off_trew);
+    bm.bf0 = (double *)(smem + L.off_bf0); bm.bf1 = (double *)(smem + L.off_bf1);
+    bm.e_k = (unsigned long long *)(smem + L.off_ek);
+    bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.nearlo = (uint32_t *)(smem + L.off_nearlo);
+    bm.nearhi = (uint32_t *)(smem + L.off_nearhi);
+    bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint8_t *)(smem + L.off_tlive);
+    bm.tshot = (int32_t *)(smem + L.off_tshot);
+    bm.e_alive = (uint32_t *)(smem + L.off_ealive); bm.e_evt = (uint32_t *)(smem + L.off_eevt);
+    bm.e_ord = (uint32_t *)(smem + L.off_eord);
+    bm.res = (uint16_t *)(smem + L.off_res); bm.jobs = (uint16_t *)(smem + L.off_jobs);
+    bm.los_q = (uint8_t *)(smem + L.off_losq);
+    bm.los_r = bm.los_q + (BS / 32) * 256;
+}
 
 #ifndef OBS_EVICT_FIRST
 #define OBS_EVICT_FIRST 1
-#endif
-#ifndef EARLY_TMA
-#define EARLY_TMA 0   // measured: issuing the static-column copies before phase A slows the step by 5 % (r01o)
 #endif
 // Observation rows are write-once streaming data (277 MB per tick at 65536 envs, more than the whole L2): they are
 // stored with an L2 evict-first policy so that they do not push the 53 MB of env state out of the cache.
@@ -102,75 +114,6 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
-// Observation sink of one warp.  Every lane (= env) emits the same (virtual) column at the same time into its own
-// row of a 32 x 33-float shared-memory tile (odd row stride => the 32 lanes hit 32 different banks, and so does a
-// warp reading one tile column).  The emitter announces groups of values with reserve(n); when a group does not
-// fit, the warp flushes the tile: for each env row, lane L stores column j0 + L - one coalesced <= 128-byte run per
-// store instruction.  (A per-thread staging row drained with 16-byte stores was tried: fewer instructions, but the
-// 16-byte row alignment it needs makes every scalar put a 4-way bank conflict and it was slower.)
-// For fixed maps the static wall / maze columns are not emitted at all: virtual columns skip them and each thread
-// ships them with a bulk-async copy from the block's template.
-constexpr int TILE_STRIDE = 33;
-__device__ __forceinline__ float lds_f32(uint32_t saddr) {
-    float v;
-    asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(saddr));
-    return v;
-}
-// columns [0, ncols) of the tile are virtual columns k0 .. of observation row r0 (and continue into row r0 + 1)
-__device__ __noinline__ void tile_flush(const float *tile, float *gbase, int64_t row_len, unsigned emit_mask, int lane,
-                                        int r0, int k0, int ncols, int dyn_len, int head_len, int static_len, int obs_dim) {
-    const uint64_t pol = make_evict_first_policy();
-    __syncwarp();
-    int kk = k0 + lane, r = r0;
-    if (kk >= dyn_len) { kk -= dyn_len; ++r; }
-    const int gcol = r * obs_dim + (kk < head_len ? kk : kk + static_len);
-    if (lane < ncols) {
-        float *dst = gbase + gcol;
-        const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile + lane);
-        if (emit_mask == 0xffffffffu) {      // the usual case: 8 tile reads in flight, then 8 row-chunk stores
-#pragma unroll
-            for (int q0 = 0; q0 < 32; q0 += 8) {
-                float v[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] = lds_f32(src + (uint32_t)((q0 + q) * TILE_STRIDE * 4));
-#pragma unroll
-                for (int q = 0; q < 8; ++q) { stg_stream(dst, v[q], pol); dst += row_len; }
-            }
-        } else {
-#pragma unroll 4
-            for (int rr = 0; rr < 32; ++rr) {
-                if ((emit_mask >> rr) & 1u) stg_stream(dst, lds_f32(src + (uint32_t)(rr * TILE_STRIDE * 4)), pol);
-                dst += row_len;
-            }
-        }
-    }
-    __syncwarp();
-}
-struct TileSink {  // kept in registers: flush takes everything by value
-    float *my;          // tile + lane * TILE_STRIDE
-    float *tile;
-    float *gbase;       // obs row of the warp's lane 0
-    int64_t row_len;    // R * D floats per env
-    unsigned emit_mask; // lanes whose env gets an observation
-    int lane, jj;       // tile columns [0, jj) are filled
-    int r0, k0;         // ... with virtual columns k0.. of observation row r0
-    int dyn_len, head_len, static_len, obs_dim;
-    __device__ __forceinline__ void put(float v) { my[jj++] = v; }
-    __device__ __forceinline__ void flush() {
-        tile_flush(tile, gbase, row_len, emit_mask, lane, r0, k0, jj, dyn_len, head_len, static_len, obs_dim);
-        k0 += jj;
-        if (k0 >= dyn_len) { k0 -= dyn_len; ++r0; }
-        jj = 0;
-    }
-    __device__ __forceinline__ void reserve(int n) {   // n <= 32
-        if (jj + n > 32) flush();
-    }
-    __device__ __forceinline__ void skip_static(const float *, int) {}  // shipped by bulk copies from the template
-    __device__ __forceinline__ void finish() {
-        if (jj) flush();
-    }
-};
-
 // at_step_host: how the host learns that rewards / done have landed in its memory without synchronising the stream
 // (the rows kernel is still running then): the last block to finish posts `epoch` into a mapped host word.
 struct HostSignal {
@@ -180,164 +123,64 @@ struct HostSignal {
     unsigned long long *dbg_times;  // diagnostics (at_debug_block_times): [2 * grid] globaltimer at block start / end
 };
 
-// FUSED = true: simulation + observation rows in one launch (phase B below).  FUSED = false: simulation only; the rows
-// are built from the stored state by rows_kernel, launched behind this kernel as a programmatic dependent.
-template <bool IS_STEP, bool FUSED, int SPEC = 0>
+// at_step_host: the last block to finish posts `epoch` into a mapped host word (block-uniform call)
+__device__ __forceinline__ void signal_host(const HostSignal &sig, int tid) {
+    if (sig.host_flag == nullptr) return;
+    __threadfence_system();   // rewards / done of this block are in host memory before it counts
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int prev = atomicAdd(sig.counter, 1u);
+        if (prev == gridDim.x - 1) {
+            *sig.counter = 0u;
+            __threadfence_system();
+            *sig.host_flag = sig.epoch;
+        }
+    }
+}
+
+// The simulation of one tick (IS_STEP) or a masked reset.  The observation rows are built from the stored state by
+// rows_kernel, launched behind this kernel as a programmatic dependent.
+template <bool IS_STEP, int SPEC = 0>
 __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                  const int32_t *__restrict__ actions,
-                                                 const uint8_t *__restrict__ mask, float *__restrict__ obs,
-                                                 float *__restrict__ rewards, uint8_t *__restrict__ done,
-                                                 const float *__restrict__ g_tmpl, HostSignal sig) {
+                                                 const uint8_t *__restrict__ mask,
+                                                 float *__restrict__ rewards, uint8_t *__restrict__ done, HostSignal sig) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const SmemLayout L = smem_layout(c.n_tanks, c.n_walls, c.n_bots, FUSED, c.act_rows);
-    if (!FUSED) asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // rows_kernel may take freed SM slots
+    const SmemLayout L = smem_layout(c.n_tanks, c.n_bots, c.act_rows);
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");  // rows_kernel may take freed SM slots
     if (sig.dbg_times != nullptr && threadIdx.x == 0) {
         unsigned long long t0;
         asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t0));
         sig.dbg_times[2 * blockIdx.x] = t0;
     }
     BlockMem bm;
-    bm.trig = (double *)(smem + L.off_trig);
-    bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
-    bm.trew = (double *)(smem + L.off_trew);
-    bm.bf0 = (double *)(smem + L.off_bf0); bm.bf1 = (double *)(smem + L.off_bf1);
-    bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.nearlo = (uint32_t *)(smem + L.off_nearlo);
-    bm.nearhi = (uint32_t *)(smem + L.off_nearhi);
-    bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint8_t *)(smem + L.off_tlive);
-    bm.tshot = (int32_t *)(smem + L.off_tshot);
-    bm.slot_of = (uint8_t *)(smem + L.off_slot);
-    uint8_t *udl = (uint8_t *)(smem + L.off_udelta);
-    bm.udelta = udl;
-    bm.los_q = (uint8_t *)(smem + L.off_losq);
-    bm.los_r = bm.los_q + (BS / 32) * 256;
-    float *tmpl = (float *)(smem + L.off_tmpl) + (c.off_walls & 3);  // tmpl[q] and obs column off_walls + q: same phase
-    bm.tmpl = tmpl;
-
+    bind_block_mem(bm, smem, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {   // table copies: every load is issued before the first store (one round trip instead of a dozen)
-        constexpr int TRIG_IT = (722 + BS - 1) / BS, UDL_IT = (361 + BS - 1) / BS;
-        double tv[TRIG_IT];
-        uint8_t uv[UDL_IT];
-#pragma unroll
-        for (int k = 0; k < TRIG_IT; ++k) tv[k] = tid + k * BS < 722 ? __ldg(st.trig + tid + k * BS) : 0.0;
-#pragma unroll
-        for (int k = 0; k < UDL_IT; ++k) uv[k] = tid + k * BS < 361 ? __ldg(st.udelta + tid + k * BS) : (uint8_t)0;
-#pragma unroll
-        for (int k = 0; k < TRIG_IT; ++k) if (tid + k * BS < 722) bm.trig[tid + k * BS] = tv[k];
-#pragma unroll
-        for (int k = 0; k < UDL_IT; ++k) if (tid + k * BS < 361) udl[tid + k * BS] = uv[k];
-    }
-    if (FUSED && c.map != 2) {
-        const int nt = 4 * c.n_walls + CELLS;
-#pragma unroll 8
-        for (int i = tid; i < nt; i += BS) tmpl[i] = __ldg(g_tmpl + i);
-        fence_async_smem();  // the template is later read by bulk-async copies
-    }
-    for (int i = 0; i < c.n_tanks; ++i) {  // lanes without an env still walk the emitter: give them inert data
-        bm.tlive[i * BS + tid] = 0;
-        bm.tpack[i * BS + tid] = 0u;
-        bm.tx[i * BS + tid] = 0.0;
-        bm.ty[i * BS + tid] = 0.0;
-    }
-    __syncthreads();
 
-    const int64_t e = (int64_t)blockIdx.x * BS + tid;
+    const int64_t e_warp0 = (int64_t)blockIdx.x * BS + warp * 32;
+    const int64_t e = e_warp0 + lane;
     const bool valid = e < st.N;
-    // which envs get an observation is known up front (every stepped env; the masked ones of a reset)
-    const bool emit = FUSED && valid && obs != nullptr && c.rows > 0 && (IS_STEP || !mask || mask[e]);
-    const unsigned emit_mask = __ballot_sync(0xffffffffu, emit);
-    const int64_t row_len = (int64_t)c.rows * c.obs_dim;
-    float *gbase = obs + ((int64_t)blockIdx.x * BS + warp * 32) * row_len;
-    const int static_len = c.map != 2 ? 4 * c.n_walls + CELLS : 0;
-
-    // ---------------- static observation columns
-    // Fixed map: the wall rectangles + maze grid of every row (more than half of the observation bytes) do not
-    // depend on the tick; they are copied from the block's template by the bulk-async (TMA) engine.  (Issuing
-    // these copies before phase A, to overlap the HBM writes with the simulation, measured 5 % SLOWER: the write
-    // stream delays phase A's latency-bound state loads - EARLY_TMA.)  When rows are 16-byte phased, each env's thread ships the aligned body of its rows with ONE bulk copy per row and the
-    // few unaligned edge floats with plain stores; otherwise the warp copies them cooperatively.
-    bool bulk_pending = false;
-    auto ship_static = [&]() {
-    if (static_len && emit_mask) {
-            const bool vec = (c.obs_dim % 4 == 0) && ((((uintptr_t)obs) & 15u) == 0);
-            if (vec) {
-                const int head = (4 - (c.off_walls & 3)) & 3;
-                const int nbody = (static_len - head) & ~3;
-                if (emit) {
-                    for (int r = 0; r < c.rows; ++r) {
-                        float *dst = gbase + lane * row_len + (int64_t)r * c.obs_dim + c.off_walls;
-                        bulk_store(dst + head, tmpl + head, (uint32_t)nbody * 4u, make_evict_first_policy());
-                        for (int q = 0; q < head; ++q) dst[q] = tmpl[q];
-                        for (int q = head + nbody; q < static_len; ++q) dst[q] = tmpl[q];
-                    }
-                    bulk_commit();
-                    bulk_pending = true;
-                }
-            } else {
-                for (int rr = 0; rr < 32; ++rr) {
-                    if (!((emit_mask >> rr) & 1u)) continue;
-                    for (int r = 0; r < c.rows; ++r) {
-                        float *dst = gbase + rr * row_len + (int64_t)r * c.obs_dim + c.off_walls;
-                        for (int q = lane; q < static_len; q += 32) dst[q] = tmpl[q];
-                    }
-                }
-            }
-        }
-    };
-#if EARLY_TMA
-    ship_static();
-#endif
-
-    // ---------------- phase A: one thread per env
-    // This env's action rows are staged in the (still unused) observation tile by asynchronous copies: the first
-    // read comes after the first bullet pass, so the copy latency - PCIe latency when at_step_host hands the kernel
-    // a mapped host buffer - is off the critical path.  Each thread copies and later reads only its own rows.
-    const int32_t *my_actions = nullptr;
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
-    bool acts_shared = false;   // true: the warp's rows were copied cooperatively (needs a warp barrier before use)
-    if (IS_STEP && actions && valid_mask) {
-        // (inside this warp's own tile: the other warp of the block may already be flushing its tile)
-        const int row_ints = c.act_rows * 3;
-        int32_t *wstage = (int32_t *)(smem + L.off_tile) + (size_t)warp * (FUSED ? TILE_FLOATS : 32 * row_ints);
-        const int32_t *wsrc = actions + ((int64_t)blockIdx.x * BS + warp * 32) * row_ints;
-#ifndef COOP_ACTS
-#define COOP_ACTS 0   // measured slower (kernel +2 %, host-buffer step +10 %) than per-thread copies (r01t)
-#endif
-        if (COOP_ACTS && valid_mask == 0xffffffffu && ((((uintptr_t)wsrc) & 15u) == 0)) {
-            // full warp: its 32 envs' rows are one contiguous run - 16-byte chunks, lane-strided (full-line requests;
-            // this matters when `actions` is mapped host memory and every request crosses PCIe)
-            const int chunks = 32 * row_ints / 4;   // 32 * 3 * act_rows ints: a multiple of 4
-            for (int q = lane; q < chunks; q += 32)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(wstage + 4 * q)),
-                             "l"(wsrc + 4 * q)
-                             : "memory");
-            acts_shared = true;
-        } else if (valid) {   // partial warp: every thread copies (and later reads) only its own rows
-            for (int q = 0; q < row_ints; ++q)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(wstage + lane * row_ints + q)),
-                             "l"(wsrc + lane * row_ints + q)
-                             : "memory");
+
+    if (IS_STEP) {
+        // This env's action rows are staged in shared memory by asynchronous copies: the first read comes after the
+        // first bullet pass, so the copy latency is off the critical path.  Each thread copies and later reads only
+        // its own rows.
+        const int32_t *my_actions = nullptr;
+        if (actions && valid_mask) {
+            const int row_ints = c.act_rows * 3;
+            int32_t *wstage = (int32_t *)(smem + L.off_acts) + (size_t)warp * 32 * row_ints;
+            const int32_t *wsrc = actions + e_warp0 * row_ints;
+            if (valid)
+                for (int q = 0; q < row_ints; ++q)
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(wstage + lane * row_ints + q)),
+                                 "l"(wsrc + lane * row_ints + q)
+                                 : "memory");
+            my_actions = wstage + lane * row_ints;
         }
-        my_actions = wstage + lane * row_ints;
-    }
-    SimT<SPEC> s(c, st, bm, valid ? e : 0, tid);
-    s.warp_mask = valid_mask;
-    s.acts_shared = acts_shared;
-    if (valid) {
-        if (IS_STEP) {
-            s.load();
-            float rw[MAX_TANKS];
-            const bool d = s.wrapper_step(my_actions, rw);
-            if (c.rows == 2) *reinterpret_cast<float2 *>(rewards + e * 2) = make_float2(rw[0], rw[1]);  // one 8-byte store
-            else for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
-            done[e] = d ? 1 : 0;
-            if (d && c.auto_reset) { s.latch_terminal_info(); s.env_reset(); }
-            s.store();
-        } else if (!mask || mask[e]) {
-            s.load();
-            s.env_reset();
-            s.store();
-        }
+        if (valid_mask) step_lane<DevWarp, SPEC>(c, st, bm, e_warp0, tid, valid, valid_mask, my_actions, rewards, done);
+    } else if (valid && (!mask || mask[e])) {
+        reset_lane(c, st, bm, e, tid);
     }
 
     if (sig.dbg_times != nullptr && tid == 0) {
@@ -345,41 +188,102 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
         asm volatile("mov.u64 %0, %globaltimer;\n" : "=l"(t1));
         sig.dbg_times[2 * blockIdx.x + 1] = t1;
     }
-    if (sig.host_flag != nullptr) {   // (block-uniform)  rewards / done of this block are in host memory before it counts
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            const unsigned int prev = atomicAdd(sig.counter, 1u);
-            if (prev == gridDim.x - 1) {
-                *sig.counter = 0u;
-                __threadfence_system();
-                *sig.host_flag = sig.epoch;
-            }
-        }
-    }
+    signal_host(sig, tid);
+}
 
-    // ---------------- phase B: still one thread per env; the warp transposes through its tile
-    if (!FUSED || emit_mask == 0u) return;   // (no bulk copy is pending either)
-#if !EARLY_TMA
-    ship_static();
+// ---- the split step (at_sim.h: pass_lane / ctrl_lane / fin_lane): bullets_kernel, ctrl_kernel, fin_kernel.
+// Every kernel is launched as a programmatic dependent of its predecessor: the table copies of its prologue overlap
+// the predecessor's tail; griddepcontrol.wait orders everything else behind the predecessor's stores.
+constexpr int PK_WARPS = 4;   // warps per block of bullets_kernel
+#ifndef PK_MIN_BLOCKS
+#define PK_MIN_BLOCKS 7       // blocks per SM the register allocation must allow (28 warps)
 #endif
-    TileSink out;
-    out.tile = (float *)(smem + L.off_tile) + (size_t)warp * TILE_FLOATS;
-    out.my = out.tile + lane * TILE_STRIDE;
-    out.gbase = gbase;
-    out.row_len = row_len;
-    out.emit_mask = emit_mask;
-    out.lane = lane;
-    out.jj = 0;
-    out.r0 = 0;
-    out.k0 = 0;
-    out.static_len = static_len;
-    out.head_len = c.off_walls;
-    out.dyn_len = c.obs_dim - static_len;
-    out.obs_dim = c.obs_dim;
-    s.emit_rows(out);
-    out.finish();
-    if (bulk_pending) bulk_wait_read_all();  // shared memory must outlive the copies' reads
+struct PassSmem {
+    size_t off_tx, off_ty, off_trew, off_ek, off_tpack, off_nearlo, off_nearhi, off_ealive, off_eevt, off_eord,
+        off_res, off_jobs, off_tlive, per_warp, total;
+};
+__host__ __device__ inline PassSmem pass_smem_layout(int n, int WE) {
+    PassSmem L;
+    size_t o = 0;
+    L.off_tx = o; o += (size_t)n * WE * 8;
+    L.off_ty = o; o += (size_t)n * WE * 8;
+    L.off_trew = o; o += (size_t)n * WE * 8;
+    L.off_ek = o; o += (size_t)WE * 8;
+    L.off_tpack = o; o += (size_t)n * WE * 4;
+    L.off_nearlo = o; o += (size_t)n * WE * 4;
+    L.off_nearhi = o; o += n * SLOTS_PER_TANK > 32 ? (size_t)n * WE * 4 : 0;
+    L.off_ealive = o; o += (size_t)WE * 4;
+    L.off_eevt = o; o += (size_t)WE * 4;
+    L.off_eord = o; o += (size_t)WE * 4;
+    L.off_res = o; o += (size_t)n * SLOTS_PER_TANK * WE * 2;
+    L.off_jobs = o; o += (size_t)n * SLOTS_PER_TANK * WE * 2;
+    L.off_tlive = o; o += (size_t)n * WE;
+    L.per_warp = (o + 15) & ~(size_t)15;
+    L.total = L.per_warp * PK_WARPS;
+    return L;
+}
+// One bullet pass over the whole batch: every warp serves WE envs (pass_lane).
+// The second pass of a tick (first == 0) also posts the step's rewards / done.
+template <int WE, int SPEC>
+__global__ void __launch_bounds__(PK_WARPS * 32, PK_MIN_BLOCKS) bullets_kernel(const __grid_constant__ KCfg c, const DevState st, int first,
+                                                                            float *__restrict__ rewards, uint8_t *__restrict__ done,
+                                                                            HostSignal sig) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    const PassSmem L = pass_smem_layout(c.n_tanks, WE);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned char *ws = smem + (size_t)warp * L.per_warp;
+    BlockMem bm;
+    bm.tx = (double *)(ws + L.off_tx); bm.ty = (double *)(ws + L.off_ty); bm.trew = (double *)(ws + L.off_trew);
+    bm.e_k = (unsigned long long *)(ws + L.off_ek);
+    bm.tpack = (uint32_t *)(ws + L.off_tpack); bm.nearlo = (uint32_t *)(ws + L.off_nearlo);
+    bm.nearhi = (uint32_t *)(ws + L.off_nearhi);
+    bm.e_alive = (uint32_t *)(ws + L.off_ealive); bm.e_evt = (uint32_t *)(ws + L.off_eevt);
+    bm.e_ord = (uint32_t *)(ws + L.off_eord);
+    bm.res = (uint16_t *)(ws + L.off_res); bm.jobs = (uint16_t *)(ws + L.off_jobs);
+    bm.tlive = (uint8_t *)(ws + L.off_tlive);
+    bm.bf0 = bm.bf1 = nullptr; bm.bpack = nullptr; bm.tshot = nullptr; bm.los_q = bm.los_r = nullptr;
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    const int64_t e_warp0 = ((int64_t)blockIdx.x * PK_WARPS + warp) * WE;
+    if (e_warp0 < st.N) pass_lane<DevWarp, SPEC, WE>(c, st, bm, e_warp0, lane, first != 0, rewards, done);
+    signal_host(sig, tid);
+}
+
+// The controllers between the two passes (ctrl_lane): one thread per env, the smart bots' line-of-sight queries pooled.
+template <int SPEC>
+__global__ void __launch_bounds__(BS, 7) ctrl_kernel(const __grid_constant__ KCfg c, const DevState st,
+                                                  const int32_t *__restrict__ actions) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    const SmemLayout L = smem_layout(c.n_tanks, c.n_bots, c.act_rows, false);
+    BlockMem bm;
+    bind_block_mem(bm, smem, L);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t e_warp0 = (int64_t)blockIdx.x * BS + warp * 32;
+    const int64_t e = e_warp0 + lane;
+    const bool valid = e < st.N;
+    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
+    const int32_t *my_actions = nullptr;
+    if (actions && valid) {   // action rows: inputs of the step, not written by a predecessor kernel
+        const int row_ints = c.act_rows * 3;
+        int32_t *stage = (int32_t *)(smem + L.off_acts) + (size_t)tid * row_ints;
+        for (int q = 0; q < row_ints; ++q)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(stage + q)),
+                         "l"(actions + e * row_ints + q)
+                         : "memory");
+        my_actions = stage;
+    }
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    ctrl_lane<DevWarp, SPEC>(c, st, bm, e_warp0, tid, valid, valid_mask, my_actions);
+}
+
+// What is left for the envs whose episode ended (fin_lane): terminal info latched, reset in place.
+constexpr int FIN_THREADS = 256;
+__global__ void __launch_bounds__(FIN_THREADS) fin_kernel(const __grid_constant__ KCfg c, const DevState st, const uint8_t *__restrict__ done) {
+    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
+    asm volatile("griddepcontrol.wait;\n" ::: "memory");
+    const int64_t e = (int64_t)blockIdx.x * FIN_THREADS + threadIdx.x;
+    if (e < st.N) fin_lane(c, st, e, done);
 }
 
 // The trainers' per-tick observation normaliser on ONE column of an env's [rows][dim] block (train_multi_ppo.py:89-91
@@ -1183,6 +1087,19 @@ static int fail(int code, const std::string &msg) {
             return fail(AT_ERR_CUDA, std::string(#x) + ": " + cudaGetErrorString(err__));                  \
     } while (0)
 
+// Every entry point runs on the handle's device and leaves the calling thread's current device as it found it.
+struct DeviceGuard {
+    int prev;
+    cudaError_t err;
+    explicit DeviceGuard(int device) : prev(-1), err(cudaSuccess) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device) err = cudaSetDevice(device);
+        else prev = -1;   // nothing to restore
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    cudaError_t status() const { return err; }
+};
+
 struct at_env {
     at_config user_cfg;
     KCfg k;
@@ -1196,9 +1113,12 @@ struct at_env {
     uint8_t *d_done_scratch;
     HostLuts luts;
     const float *d_tmpl;
-    size_t smem_bytes;        // env_kernel<.., true>  (fused rows)
-    size_t smem_bytes_sim;    // env_kernel<.., false> (simulation only)
-    bool split_rows;          // rows by rows_kernel behind the simulation (default); AT_FUSED_ROWS=1: one fused kernel
+    double *d_dyn;            // st.dyn: parameters that may change between steps (at_set_weakness)
+    size_t smem_bytes_sim;    // env_kernel
+    size_t smem_bytes_ctrl;   // ctrl_kernel
+    bool split_step;          // the step runs as bullets / ctrl / bullets / fin kernels (AT_MONOLITH=1: one env_kernel)
+    int pass_we;              // bullets_kernel: envs per warp (32, 16 or 8; AT_PASS_WE)
+    size_t smem_bytes_pass;
     int sim_spec;             // SimT<SPEC> specialisation of the step's simulation kernel (0: generic; AT_NO_SPEC=1 forces it)
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
     int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
@@ -1216,40 +1136,78 @@ struct at_env {
     std::vector<std::pair<const void *, void *>> mapped;  // host buffers seen by at_step_host -> device alias (null: not mapped)
 };
 
+template <class... Args>
+static cudaError_t launch_pdl(void (*fn)(Args...), int grid, int block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, fn, args...);
+}
+
+template <int WE, int SPEC>
+static cudaError_t launch_pass(at_env *env, int first, cudaStream_t s, bool pdl, float *rw, uint8_t *dn, HostSignal sig) {
+    const int per_block = PK_WARPS * WE;
+    const int grid = (int)((env->n_envs + per_block - 1) / per_block);
+    return launch_pdl(bullets_kernel<WE, SPEC>, grid, PK_WARPS * 32, env->smem_bytes_pass, s, pdl, env->k, env->st, first, rw, dn, sig);
+}
+static cudaError_t launch_pass_any(at_env *env, int first, cudaStream_t s, bool pdl, float *rw, uint8_t *dn, HostSignal sig) {
+    const bool s3 = env->sim_spec == 3;
+    switch (env->pass_we) {
+    case 8: return s3 ? launch_pass<8, 3>(env, first, s, pdl, rw, dn, sig) : launch_pass<8, 0>(env, first, s, pdl, rw, dn, sig);
+    case 16: return s3 ? launch_pass<16, 3>(env, first, s, pdl, rw, dn, sig) : launch_pass<16, 0>(env, first, s, pdl, rw, dn, sig);
+    default: return s3 ? launch_pass<32, 3>(env, first, s, pdl, rw, dn, sig) : launch_pass<32, 0>(env, first, s, pdl, rw, dn, sig);
+    }
+}
+// bullets (first pass) -> controllers -> bullets -> results; every kernel but the first a programmatic dependent
+static int launch_split_step(at_env *env, int grid, const int32_t *d_actions, float *d_rewards, uint8_t *d_done,
+                             HostSignal sig, cudaStream_t s) {
+    const bool pdl = env->pdl;
+    const HostSignal none = {nullptr, nullptr, 0u, nullptr};
+    CUDA_TRY(launch_pass_any(env, 1, s, false, nullptr, nullptr, none));
+    switch (env->sim_spec) {
+    case 3: CUDA_TRY(launch_pdl(ctrl_kernel<3>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
+    case 2: CUDA_TRY(launch_pdl(ctrl_kernel<2>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
+    case 1: CUDA_TRY(launch_pdl(ctrl_kernel<1>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
+    default: CUDA_TRY(launch_pdl(ctrl_kernel<0>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
+    }
+    CUDA_TRY(launch_pass_any(env, 0, s, pdl, d_rewards, d_done, sig));
+    if (env->k.auto_reset)
+        CUDA_TRY(launch_pdl(fin_kernel, (int)((env->n_envs + FIN_THREADS - 1) / FIN_THREADS), FIN_THREADS, (size_t)0, s, pdl, env->k,
+                            env->st, (const uint8_t *)d_done));
+    else
+        env->launches -= 1;
+    env->launches += 3;   // (+1 by the caller)
+    return AT_OK;
+}
+
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
-                             float norm_eps = 0.f, bool signal_host = false) {
+                             float norm_eps = 0.f, bool post_to_host = false) {
     const int grid = (int)((env->n_envs + BS - 1) / BS);
     HostSignal sig = {nullptr, nullptr, 0u, env->dbg_times};
-    if (signal_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
+    if (post_to_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
     const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
-    if (d_obs_norm && !env->split_rows) return fail(AT_ERR_ARG, "normalised rows are built by rows_kernel: unset AT_FUSED_ROWS");
-    if (!env->split_rows) {
-        if (is_step)
-            env_kernel<true, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                                    d_done, env->d_tmpl, sig);
-        else
-            env_kernel<false, true><<<grid, BS, env->smem_bytes, s>>>(env->k, env->st, d_actions, d_mask, d_obs, d_rewards,
-                                                                     d_done, env->d_tmpl, sig);
-        env->launches += 1;
-        CUDA_TRY(cudaGetLastError());
-        return AT_OK;
-    }
-    if (is_step && env->sim_spec == 3)
-        env_kernel<true, false, 3><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                        d_done, env->d_tmpl, sig);
+    if (is_step && env->split_step) {
+        int rc = launch_split_step(env, grid, d_actions, d_rewards, d_done, sig, s);
+        if (rc != AT_OK) return rc;
+    } else if (is_step && env->sim_spec == 3)
+        env_kernel<true, 3><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     else if (is_step && env->sim_spec == 2)
-        env_kernel<true, false, 2><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                        d_done, env->d_tmpl, sig);
+        env_kernel<true, 2><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     else if (is_step && env->sim_spec == 1)
-        env_kernel<true, false, 1><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                        d_done, env->d_tmpl, sig);
+        env_kernel<true, 1><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     else if (is_step)
-        env_kernel<true, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                     d_done, env->d_tmpl, sig);
+        env_kernel<true><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     else
-        env_kernel<false, false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, nullptr, d_rewards,
-                                                                      d_done, env->d_tmpl, sig);
+        env_kernel<false><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     if (!rows) return AT_OK;
@@ -1291,7 +1249,8 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         cudaGetLastError();
         return fail(AT_ERR_NOGPU, "at_create: no usable CUDA device (the batched env has no CPU fallback)");
     }
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     if (prop.major < 10)
@@ -1356,38 +1315,58 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         if (cudaEventCreateWithFlags(&env->ev_actions, cudaEventDisableTiming) != cudaSuccess) env->ev_actions = nullptr;
         cudaGetLastError();
     }
+    env->d_dyn = (double *)(b + L.o_dyn);
+    cudaMemcpy(env->d_dyn, &k.weakness, 8, cudaMemcpyHostToDevice);
     env->d_tmpl = (const float *)(b + L.o_tmpl);
     if (k.map != AT_MAP_MAZE) {
         std::vector<float> tm((size_t)4 * k.n_walls + CELLS);
         fill_static_template(k.wall_lo, k.wall_hi, tm.data());
         cudaMemcpy(b + L.o_tmpl, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice);
     }
-    env->smem_bytes = smem_layout(k.n_tanks, k.n_walls, k.n_bots).total;
-    env->smem_bytes_sim = smem_layout(k.n_tanks, k.n_walls, k.n_bots, false, k.act_rows).total;
-    cudaFuncSetAttribute(env_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
-    cudaFuncSetAttribute(env_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes);
-    cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
-    cudaFuncSetAttribute(env_kernel<true, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
-    cudaFuncSetAttribute(env_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
-    cudaFuncSetAttribute(env_kernel<true, false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
-    cudaFuncSetAttribute(env_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->smem_bytes_sim);
-    if (const char *cv = getenv("AT_SIM_CARVEOUT")) {   // experiment: shared-memory carve-out (percent) of the simulation kernels
-        const int pct = atoi(cv);
-        if (pct > 0 && pct <= 100) {
-            cudaFuncSetAttribute(env_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(env_kernel<true, false, 1>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(env_kernel<true, false, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(env_kernel<true, false, 3>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    env->smem_bytes_sim = smem_layout(k.n_tanks, k.n_bots, k.act_rows).total;
+    env->smem_bytes_ctrl = smem_layout(k.n_tanks, k.n_bots, k.act_rows, false).total;
+    {   // The dynamic shared-memory limit is a process-wide attribute of each kernel instantiation: never set it to this
+        // handle's own need (a second handle with a smaller image would lower it under the first one) - raise every
+        // kernel to the device's opt-in maximum once and leave it there.
+        const int lim = (int)prop.sharedMemPerBlockOptin;
+        cudaFuncSetAttribute(env_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(env_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(env_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(env_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(ctrl_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(ctrl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(ctrl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(ctrl_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(bullets_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(bullets_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(bullets_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(bullets_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(bullets_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(bullets_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        if (env->smem_bytes_sim > (size_t)lim) {
+            cudaFree(env->arena);
+            delete env;
+            return fail(AT_ERR_ARG, "at_create: the simulation's working set does not fit shared memory");
         }
     }
     {   // rows_kernel: the largest group (power of two, <= 4 envs) whose image keeps 12 warps on an SM, else whatever
         // fits at all; the G * 6n (env, slot) pairs must fit the lanes' prefetch registers (<= 3 per lane)
-        const char *fz = getenv("AT_FUSED_ROWS"), *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");
-        env->split_rows = !(fz && fz[0] == '1') && k.rows > 0;
+        const char *np = getenv("AT_NO_PDL"), *gg = getenv("AT_ROWS_LGG");
         env->pdl = !(np && np[0] == '1');
         {   // AT_NO_SPEC=1: generic kernel; 2 / 3: stop below that specialisation level
             const char *ns = getenv("AT_NO_SPEC");
             env->sim_spec = sim_spec_for(k, ns && ns[0] >= '1' && ns[0] <= '3' ? ns[0] - '1' : 3);
+        }
+        {   // the split step: fixed maps, every mode but the arena (whose bots decide before the first pass)
+            const char *mo = getenv("AT_MONOLITH"), *we = getenv("AT_PASS_WE");
+            env->split_step = !(mo && mo[0] == '1') && k.map != AT_MAP_MAZE && k.mode != AT_MODE_ARENA;
+            // envs per warp of the bullet kernel: fewer envs per warp = more warps in flight; small batches get the
+            // smallest share so that the pass still spreads over the SMs
+            int w = n_envs >= 32768 ? 16 : 8;
+            if (we && (atoi(we) == 8 || atoi(we) == 16 || atoi(we) == 32)) w = atoi(we);
+            env->pass_we = w;
+            env->smem_bytes_pass = pass_smem_layout(k.n_tanks, w).total;
         }
         const int RD = k.rows * k.obs_dim;
         const char *ww = getenv("AT_ROWS_WARPS");
@@ -1412,13 +1391,14 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->rows_smem_norm = rows_smem_layout(1 << lg, k.n_tanks, RD, W, true).total;
         env->rows_grid_norm = prop.multiProcessorCount;
         env->rows_grid = prop.multiProcessorCount;
-        if (env->split_rows) {
+        if (k.rows > 0) {
             if (env->rows_smem_norm > (size_t)prop.sharedMemPerBlockOptin) {
                 cudaFree(env->arena);
                 delete env;
                 return fail(AT_ERR_ARG, "at_create: an observation image does not fit shared memory");
             }
-            cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)env->rows_smem_norm);
+            // (never this handle's own size: see the note at the simulation kernels above)
+            cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
             int bps = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)env->rows_fn, W * 32, env->rows_smem) != cudaSuccess || bps < 1) {
                 cudaGetLastError();
@@ -1449,7 +1429,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
 
 int at_destroy(at_env *env) {
     if (!env) return AT_OK;
-    cudaSetDevice(env->device);
+    DeviceGuard guard(env->device);
     cudaDeviceSynchronize();
     cudaFree(env->arena);
     if (env->d_sig_counter) cudaFree(env->d_sig_counter);
@@ -1469,7 +1449,8 @@ int64_t at_launch_count(const at_env *env) { return env ? env->launches : AT_ERR
 
 int at_reset(at_env *env, const uint8_t *d_mask, float *d_obs, void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_reset: null handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     return launch_env_kernel(env, false, nullptr, d_mask, d_obs, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -1477,7 +1458,8 @@ int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_reward
     if (!env) return fail(AT_ERR_ARG, "at_step: null handle");
     if (env->k.act_rows > 0 && !d_actions) return fail(AT_ERR_ARG, "at_step: this mode needs an actions array");
     if ((env->k.rows > 0 && !d_rewards) || !d_done) return fail(AT_ERR_ARG, "at_step: rewards / done must not be null");
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream);
 }
 
@@ -1487,7 +1469,8 @@ int at_step_norm(at_env *env, const int32_t *d_actions, float *d_obs, float *d_o
     if (env->k.act_rows > 0 && !d_actions) return fail(AT_ERR_ARG, "at_step_norm: this mode needs an actions array");
     if ((env->k.rows > 0 && !d_rewards) || !d_done) return fail(AT_ERR_ARG, "at_step_norm: rewards / done must not be null");
     if (!d_obs_norm) return fail(AT_ERR_ARG, "at_step_norm: the normalised observation buffer must not be null");
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream, d_obs_norm, epsilon);
 }
 
@@ -1506,7 +1489,8 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
     if ((env->k.rows > 0 && !h_rewards) || !h_done) return fail(AT_ERR_ARG, "at_step_host: rewards / done must not be null");
     if (env->k.act_rows > 0 && !h_actions) return fail(AT_ERR_ARG, "at_step_host: this mode needs an actions array");
     cudaStream_t s = (cudaStream_t)stream;
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     const int64_t N = env->n_envs;
     // Pinned (mapped) host buffers are handed to the kernel as they are: it fetches each env's 24 bytes of actions
     // with asynchronous copies that are hidden behind the first bullet pass and posts rewards / done straight into
@@ -1586,7 +1570,8 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
 int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
                 void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_get_info: null handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     const int grid = (int)((env->n_envs + 127) / 128);
     info_kernel<false><<<grid, 128, 0, (cudaStream_t)stream>>>(env->k, env->st, d_winner, d_hits, d_be_hits, d_change_time, nullptr);
     env->launches += 1;
@@ -1597,7 +1582,8 @@ int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_h
 int at_get_terminal_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
                          uint8_t *d_latched, void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_get_terminal_info: null handle");
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     const int grid = (int)((env->n_envs + 127) / 128);
     info_kernel<true><<<grid, 128, 0, (cudaStream_t)stream>>>(env->k, env->st, d_winner, d_hits, d_be_hits, d_change_time, d_latched);
     env->launches += 1;
@@ -1608,7 +1594,8 @@ int at_get_terminal_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_
 int at_synthetic_actions(at_env *env, int64_t tick, int32_t *d_actions, void *stream) {
     if (!env || !d_actions) return fail(AT_ERR_ARG, "at_synthetic_actions: null argument");
     if (env->k.act_rows == 0) return AT_OK;
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     const int64_t total = env->n_envs * env->k.act_rows;
     synthetic_actions_kernel<<<(int)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         env->k.seed, env->k.env_id_base, env->n_envs, env->k.act_rows, (uint32_t)tick, d_actions);
@@ -1620,7 +1607,8 @@ int at_synthetic_actions(at_env *env, int64_t tick, int32_t *d_actions, void *st
 int at_get_state(at_env *env, int64_t first, int64_t count, at_env_state *h_out) {
     if (!env || !h_out || first < 0 || count <= 0 || first + count > env->n_envs)
         return fail(AT_ERR_ARG, "at_get_state: bad range");
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     PackedEnv *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(PackedEnv) * count));
     gather_kernel<<<(int)((count + 63) / 64), 64>>>(env->k, env->st, first, count, d);
@@ -1641,7 +1629,8 @@ int at_set_state(at_env *env, int64_t first, int64_t count, const at_env_state *
         std::string msg = pack_env(env->k, env->luts, h_in[q], h[(size_t)q]);
         if (!msg.empty()) return fail(AT_ERR_ARG, msg);
     }
-    CUDA_TRY(cudaSetDevice(env->device));
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
     PackedEnv *d = nullptr;
     CUDA_TRY(cudaMalloc(&d, sizeof(PackedEnv) * count));
     cudaError_t err = cudaMemcpy(d, h.data(), sizeof(PackedEnv) * count, cudaMemcpyHostToDevice);
@@ -1657,7 +1646,8 @@ int at_set_state(at_env *env, int64_t first, int64_t count, const at_env_state *
 
 int at_bfs_batch(int device, const uint8_t *d_maze, const int32_t *d_query, int64_t n, int32_t *d_out, void *stream) {
     if (!d_maze || !d_query || !d_out || n <= 0) return fail(AT_ERR_ARG, "at_bfs_batch: bad argument");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     bfs_batch_kernel<<<(int)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d_maze, d_query, n, d_out);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
@@ -1665,7 +1655,8 @@ int at_bfs_batch(int device, const uint8_t *d_maze, const int32_t *d_query, int6
 int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n, uint8_t *d_maze, uint32_t *d_ctr,
                       void *stream) {
     if (!d_maze || n <= 0) return fail(AT_ERR_ARG, "at_generate_mazes: bad argument");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     maze_kernel<<<(int)((n + 63) / 64), 64, 0, (cudaStream_t)stream>>>(seed, env_id_base, n, d_maze, d_ctr);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
@@ -1673,8 +1664,14 @@ int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n,
 
 int at_set_weakness(at_env *env, double weakness) {
     if (!env || !(weakness >= 0.0 && weakness <= 1.0)) return fail(AT_ERR_ARG, "at_set_weakness: null handle or weakness outside [0, 1]");
+    // The kernels read the weakness from device memory (DevState::dyn), not from the by-value kernel config, so the
+    // change also reaches steps that replay a captured CUDA graph.  Synchronous copy: it has landed when the call
+    // returns, i.e. before any step enqueued afterwards.
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
+    CUDA_TRY(cudaMemcpy(env->d_dyn, &weakness, 8, cudaMemcpyHostToDevice));
     env->user_cfg.weakness = weakness;
-    env->k.weakness = weakness;   // the kernel config travels by value with every launch
+    env->k.weakness = weakness;
     return AT_OK;
 }
 
@@ -1682,7 +1679,8 @@ int at_tick_normalize(int device, const float *d_obs, int64_t n_envs, int rows, 
                       void *stream) {
     if (!d_obs || !d_out || n_envs <= 0 || rows <= 0 || rows > AT_MAX_TANKS || dim <= 0)
         return fail(AT_ERR_ARG, "at_tick_normalize: bad argument");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     const bool vec = dim % 4 == 0 && ((((uintptr_t)d_obs) | ((uintptr_t)d_out)) & 15u) == 0;
     const int64_t threads = n_envs * (vec ? dim / 4 : dim);
     const int un = !vec || rows > 4 ? 1 : (rows <= 2 ? 4 : 2);   // tick_normalize_kernel: UN chunks per thread
@@ -1714,7 +1712,8 @@ int at_sample_heads(int device, const float *const *d_logits, const int *dims, i
         total += dims[k];
     }
     if (total > 8) return fail(AT_ERR_ARG, "at_sample_heads: more than 8 logits per row");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     sample_heads_kernel<<<(int)((n_rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(h, n_rows, seed, d_counter, stream_id,
                                                                                    d_actions, act_stride, d_logprobs, lp_stride);
     CUDA_TRY(cudaGetLastError());
@@ -1734,7 +1733,8 @@ int at_policy_tail(int device, const float *const *d_z2, const float *d_w3, cons
     if (((uintptr_t)d_w3) & 15u) return fail(AT_ERR_ARG, "at_policy_tail: the output-layer matrix must be 16-byte aligned");
     p.w3 = d_w3;
     p.b3 = d_b3;
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     int64_t blocks = (n_rows * 16 + 255) / 256;
     if (blocks > 148 * 16) blocks = 148 * 16;
     policy_tail_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(p, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
@@ -1750,7 +1750,8 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
     if (!d_z1 || !d_w2 || !d_b2 || !d_w3 || !d_b3 || !d_out9 || n_rows <= 0 || !d_actions || !d_logprobs || !d_values)
         return fail(AT_ERR_ARG, "at_policy_mid_tail: bad argument");
     if ((((uintptr_t)d_z1) | ((uintptr_t)d_w2)) & 15u) return fail(AT_ERR_ARG, "at_policy_mid_tail: z1 / w2 must be 16-byte aligned");
-    CUDA_TRY(cudaSetDevice(device));
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
     static bool attr_set[64] = {false};
     const size_t smem = (size_t)(128 + 2 * PM_ROWS) * PM_LD * 4 + (128 + 3 * 128) * 4;
     if (device < 64 && !attr_set[device]) {

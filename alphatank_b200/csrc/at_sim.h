@@ -1,7 +1,12 @@
-// at_sim.h - per-thread (= per-env) simulation of one alphaTank tick, and the per-lane observation row
-// builders.  Written as __host__ __device__ code: the CUDA kernels in at_kernels.cu run it with one thread
-// per env; tests/cpu_emul compiles the same header with g++ to check the formulation against the oracle in
-// a GPU-less container (test infrastructure only - the product has no CPU path).
+// at_sim.h - simulation of one alphaTank tick.  Every env has a home lane (one thread per env) that owns its scalar
+// bookkeeping; the heavy, order-free parts of a tick are POOLED over the warp: the live bullets of the warp's 32 envs
+// (and the smart bots' line-of-sight queries) form job lists that all 32 lanes work through together, whatever the
+// per-env counts are (bullets_pass_pooled, pool_los), and only what the reference's sequential semantics really order
+// - the f64 reward additions, kills, list compaction - is committed per env in firing order.
+// Written as __host__ __device__ code against a warp policy (at_warp.h): the CUDA kernels in at_kernels.cu run it
+// on the warp intrinsics; tests/cpu_emul compiles the same header with g++ and runs it on a 32-fiber SIMT emulator
+// to check the formulation against the oracle in a GPU-less container (test infrastructure only - the product has
+// no CPU path).
 //
 // This is NOT a transliteration of the reference's Python: walls are a 121-bit mask probed by cell, angles
 // are integers indexing host-built libm tables, bullets carry a packed 64-bit record, BFS is a bit-parallel
@@ -16,6 +21,7 @@
 #include <string.h>
 
 #include "at_types.h"
+#include "at_warp.h"
 
 namespace at {
 
@@ -303,6 +309,13 @@ AT_HD int popc64(uint64_t v) {
     return __builtin_popcountll(v);
 #endif
 }
+AT_HD int popc32(uint32_t v) {
+#ifdef __CUDA_ARCH__
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
 AT_HD int ctz64(uint64_t v) {  // index of the lowest set bit (v != 0)
 #ifdef __CUDA_ARCH__
     return __ffsll((long long)v) - 1;
@@ -336,11 +349,9 @@ AT_HD int select_bit(M128 m, int k) {
 // config; 2 = 1 + exactly four tanks; 3 = 2 + the 2a_vs_2b tank layout).  SPEC 1 = team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME - the 2v2 / NvM
 // team_vs_bot workloads: the other bots, the 1v1 modes, the maze generator and the arena ordering drop out of the
 // kernel (the generic build is 630 KB of SASS and stalls on instruction fetch).
-#ifndef AT_BULLET_SPLIT
-#define AT_BULLET_SPLIT 0   // 1: bullets_pass runs bullet_geom + bullet_commit instead of bullet_move (experiment)
-#endif
-
-template <int SPEC>
+// CS = stride of the working-set columns (envs per block, or per warp in the bullet kernel); WE = envs per warp: the
+// lanes 0 .. WE-1 of a warp are home lanes, the others only serve pooled jobs.
+template <int SPEC, int CS = BS, int WE = 32>
 struct SimT {
     AT_HD int cfg_mode() const { return SPEC >= 1 ? 3 : c.mode; }
     AT_HD int cfg_bot_type(int i) const { return SPEC >= 1 ? 0 : c.bot_type[i]; }
@@ -368,41 +379,40 @@ struct SimT {
     int tid;    // slot in the block working set
     uint32_t cnt, rng, tick, tstep, epstep, zones;
     uint64_t wlo, whi, nlo, nhi;
-    uint64_t tclo, tchi;   // cells under any alive tank's 30x24 rect (rebuilt per bullet pass; superset after kills)
-    uint64_t iclo, ichi;   // wall | tank cells: a 5x5 rect inside one uninteresting cell needs no further test
     uint32_t alive_bits;   // bit i: tank i alive (mirror of TPACK)
-    uint32_t warp_mask;    // lanes of this warp that run the simulation (device: for the pooled stages)
-    bool acts_shared;      // device: action rows staged cooperatively by the whole (full) warp
+    uint32_t warp_mask;    // lanes of this warp that own an env (the pooled stages of the controllers run on these)
+    int ew0;               // SoA index of the env of this warp's lane 0 (pooled jobs address other lanes' envs)
+    bool valid;            // this lane owns an env (lanes past the end of the batch still serve pooled jobs)
 
     AT_HD SimT(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e((int)e_), n32((int)st_.N), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0), nlo(0), nhi(0), tclo(0), tchi(0), iclo(0), ichi(0), alive_bits(0), warp_mask(0xffffffffu), acts_shared(false) {}
+          whi(0), nlo(0), nhi(0), alive_bits(0), warp_mask(0xffffffffu), ew0((int)e_ - (tid_ & 31)), valid(true) {}
 
-    AT_HD double &TX(int i) const { return bm.tx[i * BS + tid]; }
-    AT_HD double &TY(int i) const { return bm.ty[i * BS + tid]; }
-    AT_HD double &TREW(int i) const { return bm.trew[i * BS + tid]; }
-    AT_HD uint32_t &TPACK(int i) const { return bm.tpack[i * BS + tid]; }
+    AT_HD double &TX(int i) const { return bm.tx[i * CS + tid]; }
+    AT_HD double &TY(int i) const { return bm.ty[i * CS + tid]; }
+    AT_HD double &TREW(int i) const { return bm.trew[i * CS + tid]; }
+    AT_HD uint32_t &TPACK(int i) const { return bm.tpack[i * CS + tid]; }
     AT_HD uint32_t &THITS(int i) const { return st.thits[G(i)]; }  // touched on hits / resets only: stays in HBM
     // bullets (slot indices) that may lie within 100 px of tank i when it acts this tick (dodge_reward candidates)
     AT_HD void near_clear(int i) const {
-        bm.nearlo[i * BS + tid] = 0u;
-        if (cfg_n() * SLOTS_PER_TANK > 32) bm.nearhi[i * BS + tid] = 0u;
+        bm.nearlo[i * CS + tid] = 0u;
+        if (cfg_n() * SLOTS_PER_TANK > 32) bm.nearhi[i * CS + tid] = 0u;
     }
     AT_HD void near_set(int i, int slot) const {
-        if (slot < 32) bm.nearlo[i * BS + tid] |= 1u << slot;
-        else bm.nearhi[i * BS + tid] |= 1u << (slot - 32);
+        if (slot < 32) bm.nearlo[i * CS + tid] |= 1u << slot;
+        else bm.nearhi[i * CS + tid] |= 1u << (slot - 32);
     }
     AT_HD uint64_t near_get(int i) const {
-        uint64_t v = bm.nearlo[i * BS + tid];
-        if (cfg_n() * SLOTS_PER_TANK > 32) v |= (uint64_t)bm.nearhi[i * BS + tid] << 32;
+        uint64_t v = bm.nearlo[i * CS + tid];
+        if (cfg_n() * SLOTS_PER_TANK > 32) v |= (uint64_t)bm.nearhi[i * CS + tid] << 32;
         return v;
     }
-    AT_HD uint8_t &TLIVE(int i) const { return bm.tlive[i * BS + tid]; }
-    AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * BS + tid]; }
+    AT_HD uint8_t &TLIVE(int i) const { return bm.tlive[i * CS + tid]; }
+    AT_HD int32_t &TSHOT(int i) const { return bm.tshot[i * CS + tid]; }
     // bot FSM columns exist only for bot tanks (bot_ord: ordinal among the bots)
-    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[cfg_bot_ord(i) * BS + tid]; }
-    AT_HD double &BF0(int i) const { return bm.bf0[cfg_bot_ord(i) * BS + tid]; }
-    AT_HD double &BF1(int i) const { return bm.bf1[cfg_bot_ord(i) * BS + tid]; }
+    AT_HD uint32_t &BPACK(int i) const { return bm.bpack[cfg_bot_ord(i) * CS + tid]; }
+    AT_HD double &BF0(int i) const { return bm.bf0[cfg_bot_ord(i) * CS + tid]; }
+    AT_HD double &BF1(int i) const { return bm.bf1[cfg_bot_ord(i) * CS + tid]; }
     AT_HD int G(int slot) const { return slot * n32 + e; }
 
     AT_HD int t_angle(int i) const { return (int)(TPACK(i) & 511u); }
@@ -417,20 +427,20 @@ struct SimT {
     }
     // bullet_dir / np.linalg.norm(bullet_dir) of the firing direction (cos a, -sin a): one ulp offset per component
     AT_HD void unit_dir(int a, double &u0, double &u1) const {
-        const uint32_t dl = bm.udelta[a];
-        u0 = bits_d(d_bits(bm.trig[2 * a]) + (uint64_t)(int64_t)((int)(dl & 3u) - 1));
-        u1 = bits_d(d_bits(-bm.trig[2 * a + 1]) + (uint64_t)(int64_t)((int)((dl >> 2) & 3u) - 1));
+        const uint32_t dl = ldg(st.udelta + a);
+        u0 = bits_d(d_bits(cosr(a)) + (uint64_t)(int64_t)((int)(dl & 3u) - 1));
+        u1 = bits_d(d_bits(-sinr(a)) + (uint64_t)(int64_t)((int)((dl >> 2) & 3u) - 1));
     }
-    AT_HD double cosr(int a) const { return bm.trig[2 * a]; }
-    AT_HD double sinr(int a) const { return bm.trig[2 * a + 1]; }
+    // The 6 KB of direction tables are read through L1 (one copy per SM) rather than staged per block in shared
+    // memory (seven copies per SM that would come out of the same 256 KB and shrink the L1 the other tables live in).
+    AT_HD double cosr(int a) const { return ldg(st.trig + 2 * a); }
+    AT_HD double sinr(int a) const { return ldg(st.trig + 2 * a + 1); }
 
-    // the kernel stages the action rows with asynchronous copies at launch; they must have landed before the
-    // first read.  Full warps copy their rows cooperatively (acts_shared): wait, then a warp barrier - control flow
-    // is uniform up to both call sites.  Partial warps copy thread by thread.
+    // the kernel stages this env's action rows with asynchronous copies at launch (each thread copies and reads only
+    // its own rows); they must have landed before the first read
     AT_HD void acts_ready() const {
 #ifdef __CUDA_ARCH__
         asm volatile("cp.async.wait_all;\n" ::: "memory");
-        if (acts_shared) __syncwarp();
 #endif
     }
     AT_HD uint32_t rng_u32() { return rng_word(c.seed, c.env_id_base + e, 0, rng++); }
@@ -441,7 +451,6 @@ struct SimT {
     }
 
     AT_HD bool wall_at(int idx) const { return ((idx < 64 ? wlo >> idx : whi >> (idx - 64)) & 1ull) != 0; }
-    AT_HD bool tank_cell_at(int idx) const { return ((idx < 64 ? tclo >> idx : tchi >> (idx - 64)) & 1ull) != 0; }
     AT_HD bool near_at(int idx) const { return ((idx < 64 ? nlo >> idx : nhi >> (idx - 64)) & 1ull) != 0; }
 
     // The <= 2 x 2 cells under a w x h rect (w, h <= 70) at integer (ix, iy): index of the top-left cell and a
@@ -505,8 +514,23 @@ struct SimT {
 
     static constexpr int AT_MODE_AGENT_ = 0, AT_MODE_BOT_AGENT_ = 1, AT_MODE_ARENA_ = 2, AT_MODE_TEAM_ = 3;
 
-    // One Bullet.move().  Returns true when the bullet leaves the list.
-    AT_HD bool bullet_move(double &x, double &y, uint64_t &m, uint32_t &near_tanks) {
+    // One Bullet.move() (sprite.py:59-105) of a bullet of the env in block slot q, as a PURE function of the record,
+    // the env's tank columns and the alive mask: everything the move decides, nothing committed.  The commits - f64
+    // reward additions, the kill, the compaction - are applied by the caller in firing order (bullet_move for one env
+    // at a time, bullets_pass_pooled for the warp's bullets at once).
+    struct BOut {
+        double nx, ny;
+        uint64_t m;        // the record after the move (flips, bounces, distance, cleared, pending count)
+        uint32_t near;     // alive enemies whose 113-px box holds the bullet (dodge_reward candidates)
+        int n_hi;          // BULLET_TOWARD_REWARD additions to the owner (one per enemy the bullet flies at)
+        int victim;        // first alive enemy (list order) whose rect the moved bullet overlaps, or -1
+        bool expired;      // no victim, and bounces >= 6 or distance >= 300: leaves the list (settle_penalty)
+    };
+    AT_HD bool rect5_hits_tank_q(int ix, int iy, int i, int q) const {  // vs Rect(x - 15, y - 12, 30, 24) (F11)
+        int Tx = d2i(bm.tx[i * CS + q] - 15), Ty = d2i(bm.ty[i * CS + q] - 12);
+        return ix < Tx + 30 && iy < Ty + 24 && ix + 5 > Tx && iy + 5 > Ty;
+    }
+    AT_HD void bullet_eval(int q, double x, double y, uint64_t m, uint32_t alive, BOut &o) const {
         const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u);
         const bool fx = (m >> BM_FLIPX) & 1u, fy = (m >> BM_FLIPY) & 1u;
         int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
@@ -516,6 +540,8 @@ struct SimT {
         double dx = fx ? -cv : cv, dy = fy ? sv : -sv;
         const double nx = x + dx, ny = y + dy;
         const int ix = d2i(nx), iy = d2i(ny);
+        uint32_t near_tanks = 0, gate = 0;
+        int n_hi = 0;
         // update_reward_logic on the pre-move position (sprite.py:27-57).  Same decisions as the reference's
         // norm / divide / dot sequence, reached cheaply: the unit direction comes from a table, distances are
         // compared through their squares (exact, see S300 / S100), and the cosine is first evaluated with fast
@@ -524,67 +550,81 @@ struct SimT {
             double u0, u1;
             unit_dir(ang, u0, u1);
             const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
-            // one enemy: s2 = |t|^2 and q = d . t are taken by reference so that the caller decides when they are computed
-            auto enemy = [&](int i, double tx, double ty, double s2, double q) {
+            // one enemy: s2 = |t|^2 and q = d . t are passed in so that the caller decides when they are computed
+            auto enemy = [&](double tx, double ty, double s2, double qd) {
                 // cos > 0.9 <=> q > 0 and q^2 > 0.81 s2 ; cos < 0.1 <=> q <= 0 or q^2 < 0.01 s2   (q = d . t)
-                const double q2 = q * q, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
+                const double q2 = qd * qd, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
                 bool hi, lo;
-                if (s2 > 0.0 && !(q > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps))) {
-                    hi = q > 0.0 && q2 > a81;
-                    lo = !(q > 0.0 && q2 >= b01);
+                if (s2 > 0.0 && !(qd > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps))) {
+                    hi = qd > 0.0 && q2 > a81;
+                    lo = !(qd > 0.0 && q2 >= b01);
                 } else {  // within 1e-9 of a threshold, or dist == 0 (NaN: both comparisons false): reference sequence
                     const double dt = sqrt(s2);
                     const double dp = np_dot2(d0, d1, tx / dt, ty / dt);
                     hi = dp > 0.9;
                     lo = dp < 0.1;
                 }
-                if (hi) TREW(owner) += 0.01;
+                if (hi) ++n_hi;
                 else if (lo) { if (!cleared) ++pcnt; }
                 if (s2 < S100) { pcnt = 0; cleared = true; }          // dist < DISTANCE_CANCEL_THRESHOLD
             };
-            if (SPEC == 3) {   // exactly two enemies (tanks 2, 3 or 0, 1): their geometry is computed side by side
+            // per enemy also: the dodge_reward candidate box (the tank moves <= 10 px and this bullet <= 1 px per axis
+            // before that test) and the gate of the rect test below (the moved 5x5 rect can only overlap
+            // Rect(x-15, y-12, 30, 24) when the pre-move centre distance is < 22 / 19 px per axis)
+            if (SPEC == 3) {   // exactly two enemies (tanks 2, 3 or 0, 1): side by side and predicated, no divergence
                 const int e0 = (owner & 2) ^ 2;
-                double txv[2], tyv[2], s2v[2], qv[2];
-#pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    txv[j] = TX(e0 + j) - x; tyv[j] = TY(e0 + j) - y;
-                    s2v[j] = np_dot2(txv[j], tyv[j], txv[j], tyv[j]);
-                    qv[j] = d0 * txv[j] + d1 * tyv[j];
-                }
+                bool use[2], hi[2], lo[2], in100[2];
 #pragma unroll
                 for (int j = 0; j < 2; ++j) {
                     const int i = e0 + j;
-                    if (!((alive_bits >> i) & 1u)) continue;
-                    if (fabs(txv[j]) < 113.0 && fabs(tyv[j]) < 113.0) near_tanks |= 1u << i;
-                    if (fabs(txv[j]) > 301.0 || fabs(tyv[j]) > 301.0 || s2v[j] > S300) continue;
-                    enemy(i, txv[j], tyv[j], s2v[j], qv[j]);
+                    const double tx = bm.tx[i * CS + q] - x, ty = bm.ty[i * CS + q] - y;
+                    const double s2 = np_dot2(tx, ty, tx, ty);
+                    const double qd = d0 * tx + d1 * ty;
+                    const double atx = fabs(tx), aty = fabs(ty);
+                    const bool al = (alive >> i) & 1u;
+                    if (al && atx < 113.0 && aty < 113.0) near_tanks |= 1u << i;
+                    if (al && atx < 24.0 && aty < 21.0) gate |= 1u << i;
+                    use[j] = al && !(atx > 301.0 || aty > 301.0 || s2 > S300);
+                    const double q2 = qd * qd, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
+                    hi[j] = qd > 0.0 && q2 > a81;
+                    lo[j] = !(qd > 0.0 && q2 >= b01);
+                    in100[j] = s2 < S100;
+                    if (use[j] && (!(s2 > 0.0) || (qd > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps)))) {
+                        const double dt = sqrt(s2);   // within 1e-9 of a threshold, or dist == 0: the reference's sequence
+                        const double dp = np_dot2(d0, d1, tx / dt, ty / dt);
+                        hi[j] = dp > 0.9;
+                        lo[j] = dp < 0.1;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {   // the bullet's own state, enemy after enemy
+                    n_hi += (use[j] && hi[j]) ? 1 : 0;
+                    pcnt += (use[j] && !hi[j] && lo[j] && !cleared) ? 1u : 0u;
+                    if (use[j] && in100[j]) { pcnt = 0; cleared = true; }
                 }
             } else {
-                for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies
+                for (uint32_t bits = alive & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies
                     const int i = ffs32(bits);
-                    const double tx = TX(i) - x, ty = TY(i) - y;
-                    // dodge_reward candidate: the tank moves <= 10 px and this bullet <= 1 px per axis before that test
-                    if (fabs(tx) < 113.0 && fabs(ty) < 113.0) near_tanks |= 1u << i;
-                    if (fabs(tx) > 301.0 || fabs(ty) > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
+                    const double tx = bm.tx[i * CS + q] - x, ty = bm.ty[i * CS + q] - y;
+                    const double atx = fabs(tx), aty = fabs(ty);
+                    if (atx < 113.0 && aty < 113.0) near_tanks |= 1u << i;
+                    if (atx < 24.0 && aty < 21.0) gate |= 1u << i;
+                    if (atx > 301.0 || aty > 301.0) continue;  // norm >= max(|tx|, |ty|) > 300
                     const double s2 = np_dot2(tx, ty, tx, ty);
                     if (s2 > S300) continue;                              // dist > BULLET_MAX_DISTANCE
-                    enemy(i, tx, ty, s2, d0 * tx + d1 * ty);
+                    enemy(tx, ty, s2, d0 * tx + d1 * ty);
                 }
             }
         }
         bool nfx = fx, nfy = fy;
-        // the <= 4 cells under the 5x5 rect, branch-free: first wall in list order + "is any tank rect here?"
-        int cell = -1;
-        bool near_tank = false;
+        // the <= 4 cells under the 5x5 rect, branch-free: first wall in list order
+        int cell;
         {
             int idx00;
             uint32_t sel;
             rect_cells(ix, iy, 5, 5, idx00, sel);
-            if (window13(iclo, ichi, idx00) & sel) {  // some cell holds a wall or lies under a tank rect
-                const uint32_t ww = window13(wlo, whi, idx00) & sel;
-                cell = ww ? idx00 + ffs32(ww) : -1;
-                near_tank = (window13(tclo, tchi, idx00) & sel) != 0u;
-            }
+            const uint32_t ww = window13(wlo, whi, idx00) & sel;
+            cell = ww ? idx00 + ffs32(ww) : -1;
         }
         if (cell >= 0) {  // sprite.py:66-82 (F12)
             bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
@@ -592,213 +632,61 @@ struct SimT {
             if (byh) nfy = !nfy;
             ++bounces;
         }
-        x = nx;
-        y = ny;
         ++dist;
-        // single exit: the warp reconverges before the record is packed / stored by the caller
         int victim = -1;
-        if (near_tank)
-            for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // sprite.py:88-100
-                const int i = ffs32(bits);
-                if (rect5_hits_tank(ix, iy, i)) { victim = i; break; }
-            }
-        bool gone = false;
-        if (victim >= 0) {
-            if (cfg_terminate() == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
-            THITS(owner) += 1u;
-            THITS(victim) += 1u << 16;
-            reward_by_bullets(owner, victim);
-            gone = true;
-        } else if (bounces >= 6 || dist >= 300) {  // sprite.py:102-111
-            if (!cleared && pcnt > 0) TREW(owner) -= ldg(st.pend + pcnt);
-            gone = true;
+        for (; gate; gate &= gate - 1) {  // sprite.py:88-100
+            const int i = ffs32(gate);
+            if (rect5_hits_tank_q(ix, iy, i, q)) { victim = i; break; }
         }
-        m = (uint64_t)owner | ((uint64_t)ang << BM_ANGLE) | ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) |
-            ((uint64_t)bounces << BM_BOUNCES) | ((uint64_t)cleared << BM_CLEARED) | ((uint64_t)dist << BM_DIST) |
-            ((uint64_t)pcnt << BM_PEND);
-        return gone;
+        o.nx = nx; o.ny = ny; o.near = near_tanks; o.n_hi = n_hi; o.victim = victim;
+        o.expired = victim < 0 && (bounces >= 6 || dist >= 300);  // sprite.py:102-111
+        o.m = (uint64_t)owner | ((uint64_t)ang << BM_ANGLE) | ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) |
+              ((uint64_t)bounces << BM_BOUNCES) | ((uint64_t)cleared << BM_CLEARED) | ((uint64_t)dist << BM_DIST) |
+              ((uint64_t)pcnt << BM_PEND);
     }
-
-    // ---- bullet_move in two halves (AT_BULLET_SPLIT, an experiment; default off).  bullet_geom: everything of a move
-    // that depends only on the bullet and on state a pass does not change (tank positions, walls) - new position,
-    // bounce, and per enemy tank the reward class / range / rect-hit bits, computed for EVERY enemy, alive or not.
-    // bullet_commit: what must happen in firing order - the f64 reward additions, the pending-penalty state, the
-    // kill - driven by those bits and filtered by the alive mask as it is at that moment.  Same arithmetic as
-    // bullet_move, so the two forms are interchangeable bit for bit (tests: emulator and kernel against the oracle).
-    struct BRec {
-        double nx, ny;
-        uint64_t m;        // flips / bounces / distance already advanced; cleared / pending as loaded
-        uint64_t ef;       // 6 bits per tank i at [6 i, 6 i + 6): in-range, hi, lo, within-100, within-113 (box), rect hit
-    };
-    static constexpr uint64_t EF_RANGE = 1, EF_HI = 2, EF_LO = 4, EF_N100 = 8, EF_N113 = 16, EF_HIT = 32;
-    AT_HD void bullet_geom(double x, double y, uint64_t m, BRec &R) const {
-        const int owner = (int)(m & 15u), ang = (int)((m >> BM_ANGLE) & 511u);
-        const bool fx = (m >> BM_FLIPX) & 1u, fy = (m >> BM_FLIPY) & 1u;
-        int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
-        const double cv = cosr(ang), sv = sinr(ang);
-        const double dx = fx ? -cv : cv, dy = fy ? sv : -sv;
-        const double nx = x + dx, ny = y + dy;
-        const int ix = d2i(nx), iy = d2i(ny);
-        double u0, u1;
-        unit_dir(ang, u0, u1);
-        const double d0 = fx ? -u0 : u0, d1 = fy ? -u1 : u1;
-        uint64_t ef = 0;
-        int idx00;
-        uint32_t sel;
-        rect_cells(ix, iy, 5, 5, idx00, sel);
-        int cell = -1;
-        bool near_tank = false;
-        if (window13(iclo, ichi, idx00) & sel) {
-            const uint32_t ww = window13(wlo, whi, idx00) & sel;
-            cell = ww ? idx00 + ffs32(ww) : -1;
-            near_tank = (window13(tclo, tchi, idx00) & sel) != 0u;
-        }
-        for (uint32_t bits = ((1u << cfg_n()) - 1u) & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // every enemy
-            const int i = ffs32(bits);
-            const double tx = TX(i) - x, ty = TY(i) - y;
-            uint64_t f = 0;
-            if (fabs(tx) < 113.0 && fabs(ty) < 113.0) f |= EF_N113;
-            if (near_tank && rect5_hits_tank(ix, iy, i)) f |= EF_HIT;
-            const double s2 = np_dot2(tx, ty, tx, ty);
-            if (!(fabs(tx) > 301.0 || fabs(ty) > 301.0 || s2 > S300)) {
-                const double q = d0 * tx + d1 * ty;
-                const double q2 = q * q, a81 = 0.81 * s2, b01 = 0.01 * s2, eps = 1e-9 * s2;
-                bool hi, lo;
-                if (s2 > 0.0 && !(q > 0.0 && (fabs(q2 - a81) <= eps || fabs(q2 - b01) <= eps))) {
-                    hi = q > 0.0 && q2 > a81;
-                    lo = !(q > 0.0 && q2 >= b01);
-                } else {
-                    const double dt = sqrt(s2);
-                    const double dp = np_dot2(d0, d1, tx / dt, ty / dt);
-                    hi = dp > 0.9;
-                    lo = dp < 0.1;
-                }
-                f |= EF_RANGE | (hi ? EF_HI : 0) | (lo ? EF_LO : 0) | (s2 < S100 ? EF_N100 : 0);
-            }
-            ef |= f << (6 * i);
-        }
-        bool nfx = fx, nfy = fy;
-        if (cell >= 0) {
-            const bool bxh = rect5_hits_cell(ix, d2i(y), cell), byh = rect5_hits_cell(d2i(x), iy, cell);
-            if (bxh) nfx = !nfx;
-            if (byh) nfy = !nfy;
-            ++bounces;
-        }
-        ++dist;
-        R.nx = nx; R.ny = ny; R.ef = ef;
-        R.m = (m & ~((1ull << BM_FLIPX) | (1ull << BM_FLIPY) | (7ull << BM_BOUNCES) | (511ull << BM_DIST))) |
-              ((uint64_t)nfx << BM_FLIPX) | ((uint64_t)nfy << BM_FLIPY) | ((uint64_t)bounces << BM_BOUNCES) |
-              ((uint64_t)dist << BM_DIST);
+    // what a hit commits (sprite.py:88-100): the kill, the hit counters, the rewards
+    AT_HD void commit_hit(int owner, int victim) {
+        if (cfg_terminate() == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
+        THITS(owner) += 1u;
+        THITS(victim) += 1u << 16;
+        reward_by_bullets(owner, victim);
     }
-    AT_HD bool bullet_commit(const BRec &R, double &x, double &y, uint64_t &m, uint32_t &near_tanks) {
-        m = R.m;
+    // settle_penalty (sprite.py:107-111) of an expired bullet with record m
+    AT_HD void commit_expiry(uint64_t m) {
+        const uint32_t pcnt = (uint32_t)((m >> BM_PEND) & 0xFFFFu);
+        if (!((m >> BM_CLEARED) & 1u) && pcnt > 0) TREW((int)(m & 15u)) -= ldg(st.pend + pcnt);
+    }
+    // One Bullet.move() of this lane's env, committed.  Returns true when the bullet leaves the list.
+    AT_HD bool bullet_move(double &x, double &y, uint64_t &m, uint32_t &near_tanks) {
+        BOut o;
+        bullet_eval(tid, x, y, m, alive_bits, o);
         const int owner = (int)(m & 15u);
-        const int bounces = (int)((m >> BM_BOUNCES) & 7u), dist = (int)((m >> BM_DIST) & 511u);
-        bool cleared = (m >> BM_CLEARED) & 1u;
-        uint32_t pcnt = (uint32_t)((m >> BM_PEND) & 0xFFFFu);
-        int victim = -1;
-        for (uint32_t bits = alive_bits & ~cfg_team_members(owner); bits; bits &= bits - 1) {  // alive enemies, list order
-            const int i = ffs32(bits);
-            const uint32_t f = (uint32_t)(R.ef >> (6 * i)) & 63u;
-            if (f & EF_N113) near_tanks |= 1u << i;
-            if ((f & EF_HIT) && victim < 0) victim = i;
-            if (!(f & EF_RANGE)) continue;
-            if (f & EF_HI) TREW(owner) += 0.01;
-            else if (f & EF_LO) { if (!cleared) ++pcnt; }
-            if (f & EF_N100) { pcnt = 0; cleared = true; }
-        }
-        x = R.nx;
-        y = R.ny;
-        bool gone = false;
-        if (victim >= 0) {
-            if (cfg_terminate() == 0) { TPACK(victim) &= ~TP_ALIVE; alive_bits &= ~(1u << victim); }
-            THITS(owner) += 1u;
-            THITS(victim) += 1u << 16;
-            reward_by_bullets(owner, victim);
-            gone = true;
-        } else if (bounces >= 6 || dist >= 300) {
-            if (!cleared && pcnt > 0) TREW(owner) -= ldg(st.pend + pcnt);
-            gone = true;
-        }
-        m = (m & ~((1ull << BM_CLEARED) | (0xFFFFull << BM_PEND))) | ((uint64_t)cleared << BM_CLEARED) | ((uint64_t)pcnt << BM_PEND);
-        return gone;
+        for (int k = 0; k < o.n_hi; ++k) TREW(owner) += 0.01;
+        near_tanks |= o.near;
+        x = o.nx; y = o.ny; m = o.m;
+        if (o.victim >= 0) { commit_hit(owner, o.victim); return true; }
+        if (o.expired) { commit_expiry(m); return true; }
+        return false;
     }
 
-    // `for bullet in self.bullets[:]: bullet.move()` (gaming_env.py:71-72, 378-379): firing order, stable
-    // compaction in place; also rebuilds the per-owner live counts and ranks (obs uses them).
-    AT_HD void bullets_pass() {
+    // `for bullet in self.bullets[:]: bullet.move()` (gaming_env.py:71-72, 378-379) of this lane's env from list
+    // position r0 on: firing order, stable compaction in place (w = next free position); keeps the per-owner live
+    // counts and ranks (the observation rows use them).
+    AT_HD void bullets_serial(uint32_t r0, uint32_t w) {
         const uint32_t n = cnt;
-        uint32_t w = 0;
-        for (int i = 0; i < cfg_n(); ++i) { TLIVE(i) = 0; near_clear(i); }
-        tclo = 0; tchi = 0;
-        if (n > 0)
-            for (uint32_t bits = alive_bits; bits; bits &= bits - 1) {  // cells under Rect(x-15, y-12, 30, 24)
-                const int i = ffs32(bits);
-                const int Tx = d2i(TX(i) - 15), Ty = d2i(TY(i) - 12);
-                const int c0 = imax(fdiv70(Tx), 0), c1 = imin(fdiv70(Tx + 29), 10);
-                const int r0 = imax(fdiv70(Ty), 0), r1 = imin(fdiv70(Ty + 23), 10);
-                for (int r = r0; r <= r1; ++r)
-                    for (int cc = c0; cc <= c1; ++cc) {
-                        const int idx = r * 11 + cc;
-                        if (idx < 64) tclo |= 1ull << idx; else tchi |= 1ull << (idx - 64);
-                    }
-            }
-        iclo = tclo | wlo; ichi = tchi | whi;
-        // software pipelining: the next bullet's record is requested before the current one is processed (the
-        // columns come from L2/HBM - shared memory leaves the SM almost no L1 - and a move is ~300 instructions)
-#if AT_BULLET_SPLIT == 2
-        // two moves per iteration: their geometry halves are independent instruction streams (ILP for the latency-bound
-        // fp64 chains), the commits follow in firing order
-        auto keep = [&](double x, double y, uint64_t m, uint32_t near_tanks) {
-            const int ow = (int)(m & 15u);
-            for (; near_tanks; near_tanks &= near_tanks - 1) near_set(ffs32(near_tanks), (int)w);
-            uint32_t rank = TLIVE(ow)++;
-            bm.slot_of[(ow * SLOTS_PER_TANK + (int)rank) * BS + tid] = (uint8_t)w;
-            m = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
-            st.bx[G(w)] = x;
-            st.by[G(w)] = y;
-            st.bmeta[G(w)] = m;
-            ++w;
-        };
-        double ax_ = 0.0, ay_ = 0.0, bx_ = 0.0, by_ = 0.0;
-        uint64_t am_ = 0, bm_ = 0;
-        if (n > 0) { ax_ = st.bx[G(0)]; ay_ = st.by[G(0)]; am_ = st.bmeta[G(0)]; }
-        if (n > 1) { bx_ = st.bx[G(1)]; by_ = st.by[G(1)]; bm_ = st.bmeta[G(1)]; }
-        for (uint32_t r = 0; r < n; r += 2) {
-            double xa = ax_, ya = ay_, xb = bx_, yb = by_;
-            uint64_t ma = am_, mb = bm_;
-            const bool has_b = r + 1 < n;
-            if (r + 2 < n) { ax_ = st.bx[G(r + 2)]; ay_ = st.by[G(r + 2)]; am_ = st.bmeta[G(r + 2)]; }
-            if (r + 3 < n) { bx_ = st.bx[G(r + 3)]; by_ = st.by[G(r + 3)]; bm_ = st.bmeta[G(r + 3)]; }
-            BRec RA, RB;
-            bullet_geom(xa, ya, ma, RA);
-            if (has_b) bullet_geom(xb, yb, mb, RB);
-            uint32_t nta = 0, ntb = 0;
-            if (!bullet_commit(RA, xa, ya, ma, nta)) keep(xa, ya, ma, nta);
-            if (has_b && !bullet_commit(RB, xb, yb, mb, ntb)) keep(xb, yb, mb, ntb);
-        }
-        cnt = w;
-        return;
-#endif
+        // software pipelining: the next bullet's record is requested before the current one is processed
         double nx_ = 0.0, ny_ = 0.0;
         uint64_t nm_ = 0;
-        if (n > 0) { nx_ = st.bx[G(0)]; ny_ = st.by[G(0)]; nm_ = st.bmeta[G(0)]; }
-        for (uint32_t r = 0; r < n; ++r) {
+        if (r0 < n) { nx_ = st.bx[G(r0)]; ny_ = st.by[G(r0)]; nm_ = st.bmeta[G(r0)]; }
+        for (uint32_t r = r0; r < n; ++r) {
             double x = nx_, y = ny_;
             uint64_t m = nm_;
             if (r + 1 < n) { nx_ = st.bx[G(r + 1)]; ny_ = st.by[G(r + 1)]; nm_ = st.bmeta[G(r + 1)]; }
             uint32_t near_tanks = 0;
-#if AT_BULLET_SPLIT
-            BRec R;
-            bullet_geom(x, y, m, R);
-            if (!bullet_commit(R, x, y, m, near_tanks)) {
-#else
             if (!bullet_move(x, y, m, near_tanks)) {
-#endif
                 const int ow = (int)(m & 15u);
                 for (; near_tanks; near_tanks &= near_tanks - 1) near_set(ffs32(near_tanks), (int)w);
                 uint32_t rank = TLIVE(ow)++;
-                bm.slot_of[(ow * SLOTS_PER_TANK + (int)rank) * BS + tid] = (uint8_t)w;
                 m = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
                 st.bx[G(w)] = x;
                 st.by[G(w)] = y;
@@ -807,6 +695,141 @@ struct SimT {
             }
         }
         cnt = w;
+    }
+    AT_HD void bullets_pass() {   // one env per lane, nothing pooled (per-env mazes; the reference form of the pass)
+        for (int i = 0; i < cfg_n(); ++i) { TLIVE(i) = 0; near_clear(i); }
+        bullets_serial(0, 0);
+    }
+
+    // The pass over the warp's bullets at once.  The live records of the 32 envs form one job list (by list position,
+    // then env); the lanes take 32 jobs per round, evaluate them (bullet_eval on the pass-start alive masks) and commit
+    // what does not depend on the order: the moved record in place, the dodge candidates, the per-owner count of
+    // toward-rewards.  What the order does matter for is left to the env's home lane afterwards:
+    //   * an owner that lost a bullet in this pass (expired or hit) gets its reward additions replayed bullet by bullet
+    //     (r + 0.01 - penalty + 0.01 is not r - penalty + 0.02 in f64); every other owner's additions are k equal
+    //     constants, whose order is immaterial;
+    //   * removed bullets are squeezed out of the list (records behind them move down, ranks / candidate bits follow);
+    //   * a HIT changes the alive mask, so every bullet behind the first hit of an env is not committed by the pool at
+    //     all and is re-run by the home lane with the sequential bullets_serial() - hits are rare (~0.5 % of env-passes).
+    // Fixed maps only (the job lanes test walls with their own registers' map).
+    template <class WP>
+    AT_HD void bullets_pass_pooled() {
+        if (cfg_maze()) {
+            if (valid) bullets_pass();
+            return;
+        }
+        constexpr uint32_t FULL = 0xffffffffu;
+        const int lane = tid & 31, wbase = tid & ~31, n = cfg_n();
+        const bool home = WE == 32 || lane < WE;
+        const uint32_t my_cnt = (valid && home) ? cnt : 0u;
+        if (home) {
+            bm.e_alive[tid] = alive_bits;
+            bm.e_evt[tid] = 0xFFu;
+            bm.e_ord[tid] = 0u;
+            bm.e_k[tid] = 0ull;
+            for (int i = 0; i < n; ++i) near_clear(i);
+        }
+        // job list, position-major (all first bullets, then all second ones, ...): the lanes of a round then read
+        // neighbouring envs of one [slot][env] column - the same few sectors - and bullets of one env (whose commits
+        // meet at the env's counters) are spread over different rounds
+        uint16_t *jobs = bm.jobs + (size_t)(tid >> 5) * (WE * SLOTS_PER_TANK * c.n_tanks);
+        uint32_t total = 0;
+        for (uint32_t k = 0;; ++k) {
+            const uint32_t have = WP::ballot(FULL, my_cnt > k);
+            if (have == 0u) break;
+            if (my_cnt > k) jobs[total + popc32(have & ((1u << lane) - 1u))] = (uint16_t)(lane | (k << 5));
+            total += popc32(have);
+        }
+        WP::sync(FULL);
+        // the records of the next round are requested before this round is evaluated
+        uint32_t jq_n = 0;
+        int g_n = 0;
+        double x_n = 0.0, y_n = 0.0;
+        uint64_t m_n = 0;
+        if ((uint32_t)lane < total) {
+            jq_n = jobs[lane];
+            g_n = (int)(jq_n >> 5) * n32 + ew0 + (int)(jq_n & 31u);
+            x_n = st.bx[g_n]; y_n = st.by[g_n]; m_n = st.bmeta[g_n];
+        }
+        for (uint32_t base = 0; base < total; base += 32) {
+            const bool act = base + lane < total;
+            const uint32_t jq = jq_n;
+            const int g = g_n;
+            const double x = x_n, y = y_n;
+            const uint64_t m = m_n;
+            if (base + 32 + lane < total) {
+                jq_n = jobs[base + 32 + lane];
+                g_n = (int)(jq_n >> 5) * n32 + ew0 + (int)(jq_n & 31u);
+                x_n = st.bx[g_n]; y_n = st.by[g_n]; m_n = st.bmeta[g_n];
+            }
+            const int q = wbase + (int)(jq & 31u);
+            const uint32_t slot = jq >> 5;
+            BOut o;
+            o.victim = -1; o.expired = false; o.n_hi = 0; o.near = 0; o.nx = 0.0; o.ny = 0.0; o.m = 0;
+            if (act) {
+                bullet_eval(q, x, y, m, bm.e_alive[q], o);
+                if (o.victim >= 0) WP::atomic_min(&bm.e_evt[q], slot);
+            }
+            WP::sync(FULL);
+            if (act && slot <= bm.e_evt[q]) {   // not behind a hit: the evaluation stands
+                const int owner = (int)(m & 15u);
+                const bool removed = o.victim >= 0 || o.expired;
+                st.bx[g] = o.nx; st.by[g] = o.ny; st.bmeta[g] = o.m | (m & (7ull << BM_RANK));
+                bm.res[slot * CS + q] = (uint16_t)((uint32_t)o.n_hi | (o.expired ? 8u : 0u) | (o.victim >= 0 ? 16u : 0u) |
+                                                   ((uint32_t)(o.victim & 7) << 5) | ((uint32_t)owner << 8));
+                if (o.n_hi) WP::atomic_add64(&bm.e_k[q], (unsigned long long)o.n_hi << (8 * owner));
+                if (removed) {
+                    WP::atomic_or(&bm.e_ord[q], 1u << owner);
+                } else if (SPEC == 3) {   // two enemies, 24 slots
+                    const int e0 = (owner & 2) ^ 2;
+                    if ((o.near >> e0) & 1u) WP::atomic_or(&bm.nearlo[e0 * CS + q], 1u << slot);
+                    if ((o.near >> (e0 + 1)) & 1u) WP::atomic_or(&bm.nearlo[(e0 + 1) * CS + q], 1u << slot);
+                } else {
+                    for (uint32_t nb = o.near; nb; nb &= nb - 1) {
+                        const int i = ffs32(nb);
+                        if (slot < 32) WP::atomic_or(&bm.nearlo[i * CS + q], 1u << slot);
+                        else WP::atomic_or(&bm.nearhi[i * CS + q], 1u << (slot - 32));
+                    }
+                }
+            }
+        }
+        WP::sync(FULL);
+        if (!valid) return;
+        // ---- the env's home lane: what the order matters for
+        const uint32_t evt = bm.e_evt[tid], ord = bm.e_ord[tid];
+        {
+            const unsigned long long K = bm.e_k[tid];
+            for (int i = 0; i < n; ++i) {
+                if ((ord >> i) & 1u) continue;
+                // k equal additions: one exact fma when they stay inside a binade, else the literal loop (jump_axis)
+                const int k = (int)((uint32_t)(K >> (8 * i)) & 255u);
+                if (k) TREW(i) = jump_axis(TREW(i), 0.01, k);
+            }
+        }
+        if (ord == 0u) return;   // nothing left the list: positions, ranks and the live counts stand
+        uint64_t old_near[MAX_TANKS];
+        for (int i = 0; i < n; ++i) { old_near[i] = near_get(i); near_clear(i); TLIVE(i) = 0; }
+        const uint32_t nproc = evt == 0xFFu ? cnt : evt + 1u;
+        uint32_t w = 0;
+        for (uint32_t r = 0; r < nproc; ++r) {
+            const uint32_t rr = bm.res[r * CS + tid];
+            const int owner = (int)((rr >> 8) & 7u);
+            if ((ord >> owner) & 1u)
+                for (uint32_t k = rr & 7u; k > 0; --k) TREW(owner) += 0.01;
+            if (rr & 16u) { commit_hit(owner, (int)((rr >> 5) & 7u)); continue; }
+            if (rr & 8u) { commit_expiry(st.bmeta[G(r)]); continue; }
+            const uint32_t rank = TLIVE(owner)++;
+            if (w != r) {   // a removed bullet precedes: the record moves down and its rank may have changed
+                const uint64_t m = st.bmeta[G(r)];
+                st.bx[G(w)] = st.bx[G(r)];
+                st.by[G(w)] = st.by[G(r)];
+                st.bmeta[G(w)] = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
+            }
+            for (int i = 0; i < n; ++i)
+                if ((old_near[i] >> r) & 1ull) near_set(i, (int)w);
+            ++w;
+        }
+        bullets_serial(nproc, w);   // the bullets behind a hit (nothing when there was none)
     }
 
     // ---------------------------------------------------------------- tanks (env/sprite.py:326-357, 528-657)
@@ -1010,29 +1033,29 @@ struct SimT {
         int q, bx0, bx1, by0, by1, bounces, dist, plan_in, result;  // result: -1 running, 0 / 1 finished
         bool stat_x, stat_y, accepted;
     };
-    AT_HD int los_ex(const Los &L, int i) const { return d2i(bm.tx[i * BS + L.q] - 15); }
-    AT_HD int los_ey(const Los &L, int i) const { return d2i(bm.ty[i * BS + L.q] - 12); }
+    AT_HD int los_ex(const Los &L, int i) const { return d2i(bm.tx[i * CS + L.q] - 15); }
+    AT_HD int los_ey(const Los &L, int i) const { return d2i(bm.ty[i * CS + L.q] - 12); }
     AT_HD void los_init(Los &L, int q, int me) const {
-        const uint32_t pk = bm.tpack[me * BS + q];
+        const uint32_t pk = bm.tpack[me * CS + q];
         const int a = (int)(pk & 511u);
         const double cv = cosr(a), sv = sinr(a);
         L.q = q;
-        L.x = bm.tx[me * BS + q] + 10 * cv;
-        L.y = bm.ty[me * BS + q] - 10 * sv;
+        L.x = bm.tx[me * CS + q] + 10 * cv;
+        L.y = bm.ty[me * CS + q] - 10 * sv;
         L.dx = cv;
         L.dy = -sv;
         L.enemies = 0;
         L.bx0 = 1 << 20; L.bx1 = -(1 << 20); L.by0 = 1 << 20; L.by1 = -(1 << 20);  // union of the enemy rect origins
         bool reachable = false;
         for (int i = 0; i < cfg_n(); ++i)
-            if (cfg_team(i) != cfg_team(me) && (bm.tpack[i * BS + q] & TP_ALIVE)) {
+            if (cfg_team(i) != cfg_team(me) && (bm.tpack[i * CS + q] & TP_ALIVE)) {
                 L.enemies |= 1u << i;
                 const int exi = los_ex(L, i), eyi = los_ey(L, i);
                 L.bx0 = imin(L.bx0, exi); L.bx1 = imax(L.bx1, exi); L.by0 = imin(L.by0, eyi); L.by1 = imax(L.by1, eyi);
                 // Exact cull.  Every tested position lies within 301 unit sub-steps (a polyline, so <= 301 px) of the
                 // muzzle, and its 5x5 rect can only overlap the enemy's Rect(x-15, y-12, 30, 24) when it is less than
                 // 20 px / 17 px from the enemy's centre: the muzzle must be within 301 px of that box (1 px of slack).
-                const double gx = fabs(bm.tx[i * BS + q] - L.x), gy = fabs(bm.ty[i * BS + q] - L.y);
+                const double gx = fabs(bm.tx[i * CS + q] - L.x), gy = fabs(bm.ty[i * CS + q] - L.y);
                 const double ux = fmax(gx - 21.0, 0.0), uy = fmax(gy - 18.0, 0.0);
                 reachable = reachable || (ux * ux + uy * uy < 303.0 * 303.0);
             }
@@ -1265,8 +1288,8 @@ struct SimT {
     // iterations), so instead of every thread marching its own bots while its neighbours idle, the (env, bot) jobs
     // of the 32 envs go into a shared-memory queue and idle lanes keep dequeuing - one los_iter per lockstep round.
     // `need` has bit j set when bot tank j of this env needs an answer; returns the answers in the same bits.
+    template <class WP>
     AT_HD uint32_t pool_los(uint32_t need) {
-#ifdef __CUDA_ARCH__
         const int lane = tid & 31, wbase = tid & ~31;
         const unsigned wm = warp_mask;
         uint8_t *queue = bm.los_q + (tid >> 5) * 256;
@@ -1275,25 +1298,25 @@ struct SimT {
         for (uint32_t hb = cfg_los_hoist(); hb; hb &= hb - 1) {
             const int j = ffs32(hb);
             const bool mine = (need >> j) & 1u;
-            const unsigned m = __ballot_sync(wm, mine);
-            if (mine) queue[total + __popc(m & ((1u << lane) - 1u))] = (uint8_t)(lane | (j << 5));
-            total += __popc(m);
+            const unsigned m = WP::ballot(wm, mine);
+            if (mine) queue[total + popc32(m & ((1u << lane) - 1u))] = (uint8_t)(lane | (j << 5));
+            total += popc32(m);
         }
-        __syncwarp(wm);  // queue and the other envs' tank columns (shared memory) are visible
+        WP::sync(wm);  // queue and the other envs' tank columns (shared memory) are visible
         int next = 0, myjob = 0;
         bool active = false;
         Los L;
         L.result = 0;
         for (;;) {
-            const unsigned idle = __ballot_sync(wm, !active);
-            const int pos = next + __popc(idle & ((1u << lane) - 1u));
+            const unsigned idle = WP::ballot(wm, !active);
+            const int pos = next + popc32(idle & ((1u << lane) - 1u));
             if (!active && pos < total) {
                 myjob = queue[pos];
                 los_init(L, wbase + (myjob & 31), myjob >> 5);
                 active = true;
             }
-            next = imin(next + __popc(idle), total);
-            if (__ballot_sync(wm, active) == 0u) break;
+            next = imin(next + popc32(idle), total);
+            if (WP::ballot(wm, active) == 0u) break;
             if (active) {  // phase-aligned: everybody plans now, then everybody takes plain sub-steps
                 if (L.plan_in <= 0) los_plan(L);
                 bool fin = false;
@@ -1305,21 +1328,13 @@ struct SimT {
                 }
             }
         }
-        __syncwarp(wm);
+        WP::sync(wm);
         uint32_t out = 0;
         for (uint32_t hb = need; hb; hb &= hb - 1) {
             const int j = ffs32(hb);
             out |= (uint32_t)res[lane | (j << 5)] << j;
         }
         return out;
-#else
-        uint32_t out = 0;
-        for (uint32_t hb = need; hb; hb &= hb - 1) {
-            const int j = ffs32(hb);
-            if (line_of_sight(j)) out |= 1u << j;
-        }
-        return out;
-#endif
     }
     AT_HD void random_action(int me, int act[3]) {  // simple_bots.py:32-46
         uint32_t p = BPACK(me);
@@ -1530,6 +1545,7 @@ struct SimT {
     //   stage 0  arena only: both bots decide on the pre-tick state (bot_arena.py:51-52)
     //   stage 1  bullets pass 1      stage 2  controllers in the reference's order      stage 3  bullets pass 2
     // stage 0 (arena: bots decide on the pre-tick state) or stage 2 (controllers in the reference's order)
+    template <class WP>
     AT_HD void controllers(int stage, const int32_t *a, int (&acts)[MAX_TANKS][3], uint32_t &pre_done, uint32_t &los_bits) {
         const bool arena = cfg_mode() == AT_MODE_ARENA_, team = cfg_mode() == AT_MODE_TEAM_, botagent = cfg_mode() == AT_MODE_BOT_AGENT_;
         // acting order: team mode = agent tanks in config order, then bot tanks in config order
@@ -1547,10 +1563,11 @@ struct SimT {
                         if (smart_pre(j)) need |= 1u << j;
                     }
                     pre_done = cfg_los_hoist();
-                    los_bits = pool_los(need);
+                    los_bits = pool_los<WP>(need);
                 }
                 bot_action(i, acts[i], (pre_done >> i) & 1u, (los_bits >> i) & 1u);
-                if (botagent && !(rng_unit53() < c.weakness)) { acts[i][0] = 1; acts[i][1] = 1; acts[i][2] = 0; }
+                // (the weakness lives in device memory: at_set_weakness changes it under a captured CUDA graph too)
+                if (botagent && !(rng_unit53() < ldg(st.dyn))) { acts[i][0] = 1; acts[i][1] = 1; acts[i][2] = 0; }
             }
             if (stage == 0) continue;
             if (!is_bot) {
@@ -1563,24 +1580,28 @@ struct SimT {
             apply_action(i, acts[i][0], acts[i][1], acts[i][2], swapped ? 0 : 2, swapped ? 2 : 0, swapped ? 1 : 0);
         }
     }
+    // Called by every lane of the warp (lanes without an env serve the pooled bullet jobs and skip the rest).
+    template <class WP>
     AT_HD void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
         int acts[MAX_TANKS][3];
         tick += 1;
         if (cfg_mode() != AT_MODE_TEAM_) epstep += 1;
         uint32_t pre_done = 0, los_bits = 0;
-        if (SPEC >= 1) {   // straight-line: pass, controllers, pass (measured: the rolled stage loop costs 10 %)
-            bullets_pass();
-            controllers(2, a, acts, pre_done, los_bits);
-            bullets_pass();
+        if (SPEC >= 1) {   // pass, controllers, pass - rolled, so that the pooled pass exists once in the instruction stream
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                bullets_pass_pooled<WP>();
+                if (pass == 0 && valid) controllers<WP>(2, a, acts, pre_done, los_bits);
+            }
             return;
         }
         const bool arena = cfg_mode() == AT_MODE_ARENA_;
         for (int stage = arena ? 0 : 1; stage < 4; ++stage) {
             if (stage & 1) {
-                bullets_pass();
+                bullets_pass_pooled<WP>();
                 continue;
             }
-            controllers(stage, a, acts, pre_done, los_bits);
+            if (valid) controllers<WP>(stage, a, acts, pre_done, los_bits);
         }
     }
 
@@ -1598,9 +1619,10 @@ struct SimT {
     }
 
     // wrapper step (gym_env.py:73-103, 186-200; gym_env_multi.py:202-223, 307-326).  Returns done.
-    AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
+    // the part of the wrapper step in front of the engine's tick
+    AT_HD void wrapper_pre(const int32_t *a) {
         tstep += 1;
-        if (!cfg_team_layout() && a) {  // change_time, gym_env.py:77-85
+        if (valid && !cfg_team_layout() && a) {  // change_time, gym_env.py:77-85
             acts_ready();
             uint32_t pv = st.prev_act[e];
             uint32_t nv = 1u;
@@ -1611,7 +1633,9 @@ struct SimT {
             }
             st.prev_act[e] = nv;
         }
-        game_step(a);
+    }
+    // ... and the part behind it: the step's rewards and done flag
+    AT_HD bool wrapper_post(float *rewards_row) {
         for (int r = 0; r < cfg_rows(); ++r)
             rewards_row[r] = (float)TREW(cfg_team_layout() ? cfg_agent_tank(r) : r);
         bool done;
@@ -1634,143 +1658,135 @@ struct SimT {
         }
         return done;
     }
-
-    // ---------------------------------------------------------------- observation rows
-    // gym_env.py:105-183 (1v1 layout) / gym_env_multi.py:225-304 (team layout), one value after the other in
-    // layout order, exactly like the reference builds its list.  Runs one thread per env; values go to a sink
-    // (`reserve(n)` announces a group of <= n puts, `skip_static` jumps over the template columns).  Control flow
-    // is uniform across the warp (slot loops run over all 6 n slots with a predicate), so all 32 lanes emit column j
-    // together and the GPU sink can transpose 32 envs x 32 columns through shared memory (at_kernels.cu: TileSink).
-    // record of observation slot f of agent tank t's row (f / 6 = position in the owner order: t first, then the
-    // other tanks).  The loaded values are not touched here, so the loads stay in flight until they are used.
-    AT_HD void fetch_slot(int t, int f, int nslots, bool &has, uint64_t &m, double &x, double &y) const {
-        has = false; m = 0; x = 0.0; y = 0.0;
-        if (f >= nslots) return;
-        const int o = f / SLOTS_PER_TANK, k = f - o * SLOTS_PER_TANK;
-        const int owner = o == 0 ? t : (o <= t ? o - 1 : o);
-        if ((uint32_t)k < TLIVE(owner)) {
-            const int slot = bm.slot_of[(owner * SLOTS_PER_TANK + k) * BS + tid];
-            has = true;
-            m = st.bmeta[G(slot)];
-            x = st.bx[G(slot)];
-            y = st.by[G(slot)];
-        }
+    template <class WP>
+    AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
+        wrapper_pre(a);
+        game_step<WP>(a);
+        if (!valid) return false;
+        return wrapper_post(rewards_row);
     }
-    template <class Sink>
-    AT_HD void emit_tank_common(Sink &out, int i) const {
-        const double x = TX(i), y = TY(i);
-        const int a = t_angle(i);
-        const double sp = (double)t_speed(i);
-        const double *co = st.corn + 4 * a;
-        const double c0 = ldg(co), c1 = ldg(co + 1), c2 = ldg(co + 2), c3 = ldg(co + 3);
-        out.put((float)(x + c0)); out.put((float)(y + c1)); out.put((float)(x + c2)); out.put((float)(y + c3));
-        out.put((float)(x - c0)); out.put((float)(y - c1)); out.put((float)(x - c2)); out.put((float)(y - c3));
-        out.put((float)(sp * cosr(a)));
-        out.put((float)(sp * sinr(a)));
-        out.put((TPACK(i) & TP_HW) ? 1.0f : 0.0f);
-    }
-    template <class Sink>
-    AT_HD void emit_rows(Sink &out) const {
-        const bool team = cfg_team_layout();
+    // the step's results of this lane's env: rewards / done out; returns done
+    AT_HD bool post_results(float *rewards, uint8_t *done) {
+        float rw[MAX_TANKS];
+        const bool d = wrapper_post(rw);
+        if (cfg_rows() == 2) {
 #ifdef __CUDA_ARCH__
-        for (int i = 0; i < cfg_n(); ++i)  // corner-offset LUT entries (one 32-byte sector each) -> L1
-            asm volatile("prefetch.global.L1 [%0];\n" ::"l"(st.corn + 4 * t_angle(i)));
+            *reinterpret_cast<float2 *>(rewards + (int64_t)e * 2) = make_float2(rw[0], rw[1]);  // one 8-byte store
+#else
+            rewards[(int64_t)e * 2] = rw[0]; rewards[(int64_t)e * 2 + 1] = rw[1];
 #endif
-        for (int r = 0; r < cfg_rows(); ++r) {
-            const int t = team ? cfg_agent_tank(r) : r;
-            const double ax = TX(t), ay = TY(t);
-            out.reserve(15);
-            out.put((float)ax); out.put((float)ay);
-            emit_tank_common(out, t);
-            if (team) out.put(1.0f);
-            out.put(t_alive(t) ? 1.0f : 0.0f);
-            // bullet slots: own 6 first, then every other tank's in tank order (zeros beyond an owner's live
-            // ones).  One rolled loop over the n*6 slots (small code: the kernel is instruction-cache bound) with
-            // the records requested two iterations ahead, so their L2 latency overlaps the emission.
-            {
-                const int nslots = cfg_n() * SLOTS_PER_TANK;
-                uint64_t m0, m1;
-                double x0, y0, x1, y1;
-                bool h0, h1;
-                auto emit_slot = [&](int f, bool has, uint64_t m, double bxv, double byv) {
-                    double x = 0.0, y = 0.0, dx = 0.0, dy = 0.0;
-                    if (has) {
-                        x = bxv;
-                        y = byv;
-                        const int ang = (int)((m >> BM_ANGLE) & 511u);
-                        const double cv = cosr(ang), sv = sinr(ang);
-                        dx = ((m >> BM_FLIPX) & 1u) ? -cv : cv;
-                        dy = ((m >> BM_FLIPY) & 1u) ? sv : -sv;
-                    }
-                    out.reserve(8);
-                    out.put((float)x); out.put((float)y); out.put((float)dx); out.put((float)dy);
-                    if (f >= SLOTS_PER_TANK) {
-                        const double rx = x - ax, ry = y - ay;
-                        out.put(has ? (float)rx : 0.0f);
-                        out.put(has ? (float)ry : 0.0f);
-                        out.put(has ? (float)sqrt(rx * rx + ry * ry) : 0.0f);
-                        if (team) out.put(has && cfg_team((int)(m & 15u)) == cfg_team(t) ? 1.0f : 0.0f);
-                    }
-                };
-                // two register sets used alternately (a register move of an in-flight load would wait for it)
-                fetch_slot(t, 0, nslots, h0, m0, x0, y0);
-                fetch_slot(t, 1, nslots, h1, m1, x1, y1);
-#pragma unroll 1
-                for (int f = 0; f < nslots; f += 2) {
-                    emit_slot(f, h0, m0, x0, y0);
-                    fetch_slot(t, f + 2, nslots, h0, m0, x0, y0);
-                    emit_slot(f + 1, h1, m1, x1, y1);
-                    fetch_slot(t, f + 3, nslots, h1, m1, x1, y1);
-                }
-            }
-            for (int i = 0; i < cfg_n(); ++i) {
-                if (i == t) continue;
-                const double x = TX(i), y = TY(i);
-                const double rx = x - ax, ry = y - ay;
-                out.reserve(18);
-                out.put((float)x); out.put((float)y); out.put((float)rx); out.put((float)ry);
-                out.put((float)sqrt(rx * rx + ry * ry));
-                emit_tank_common(out, i);
-                if (team) out.put(cfg_team(i) == cfg_team(t) ? 1.0f : 0.0f);
-                out.put(t_alive(i) ? 1.0f : 0.0f);
-            }
-            if (!cfg_maze()) {  // fixed map: the sink fills these columns from the block's template
-                out.skip_static(bm.tmpl, 4 * c.n_walls + CELLS);
-            } else {
-                const M128 wm = {wlo, whi};
-                for (int k = 0; k < c.n_walls; ++k) {  // k-th wall in row-major order (uniform trip count)
-                    const int cell = select_bit(wm, k);
-                    const float X = (float)((cell % 11) * 70), Y = (float)((cell / 11) * 70);
-                    out.reserve(4);
-                    out.put(X); out.put(Y); out.put(X + 70.0f); out.put(Y + 70.0f);
-                }
-                for (int cell = 0; cell < CELLS; ++cell) { out.reserve(1); out.put(wall_at(cell) ? 1.0f : 0.0f); }
-            }
-            for (int v = 0; v < c.n_zone_vals; ++v) {  // zone corners, buff first (gym_env.py:168-173)
-                const int k = (v >> 1) + (c.buff_on ? 0 : 2);
-                const int cell = (int)((zones >> (7 * k)) & 127u);
-                out.reserve(1);
-                out.put((float)(((v & 1) ? cell / 11 : cell % 11) * 70));
-            }
-            out.reserve(2);
-            out.put((TPACK(t) & TP_INBUFF) ? 1.0f : 0.0f);
-            out.put((TPACK(t) & TP_INDEBUFF) ? 1.0f : 0.0f);
+        } else {
+            for (int r = 0; r < cfg_rows(); ++r) rewards[(int64_t)e * c.rows + r] = rw[r];
         }
+        done[e] = d ? 1 : 0;
+        return d;
+    }
+    // ... and terminal info latched, auto-reset
+    AT_HD void finish_step(float *rewards, uint8_t *done) {
+        if (post_results(rewards, done) && c.auto_reset) { latch_terminal_info(); env_reset(); }
     }
 
     // ---------------------------------------------------------------- HBM <-> working set
     AT_HD void load() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
         zones = st.zones[e];
+        const uint32_t live = st.tlive[e];
         if (cfg_maze()) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; set_near(); }
         else { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
-        for (int i = 0; i < cfg_n(); ++i) {
-            TX(i) = st.tx[G(i)]; TY(i) = st.ty[G(i)]; TREW(i) = st.trew[G(i)];
-            TPACK(i) = st.tpack[G(i)]; TSHOT(i) = st.tshot[G(i)];
-            if (cfg_ctrl(i) == 1) { BPACK(i) = st.bpack[G(i)]; BF0(i) = st.bf0[G(i)]; BF1(i) = st.bf1[G(i)]; }
-            if (TPACK(i) & TP_ALIVE) alive_bits |= 1u << i;
+        // Four tanks at a time through registers: every load of a batch is issued before the first shared-memory
+        // store (the compiler cannot tell that the working-set columns and the SoA columns never alias, and a
+        // load / store / load / store sequence would be one L2 round trip per column - 40 of them in a row).
+        const int n = cfg_n();
+        for (int i0 = 0; i0 < n; i0 += 4) {
+            double x[4], y[4], rw[4], f0[4], f1[4];
+            uint32_t tp[4], bp[4];
+            int32_t ts[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                x[k] = y[k] = rw[k] = f0[k] = f1[k] = 0.0; tp[k] = bp[k] = 0u; ts[k] = 0;
+                if (i < n) {
+                    x[k] = st.tx[G(i)]; y[k] = st.ty[G(i)]; rw[k] = st.trew[G(i)];
+                    tp[k] = st.tpack[G(i)]; ts[k] = st.tshot[G(i)];
+                    if (cfg_ctrl(i) == 1) { bp[k] = st.bpack[G(i)]; f0[k] = st.bf0[G(i)]; f1[k] = st.bf1[G(i)]; }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                if (i < n) {
+                    TX(i) = x[k]; TY(i) = y[k]; TREW(i) = rw[k]; TPACK(i) = tp[k]; TSHOT(i) = ts[k];
+                    TLIVE(i) = (uint8_t)((live >> (4 * i)) & 15u);
+                    if (cfg_ctrl(i) == 1) { BPACK(i) = bp[k]; BF0(i) = f0[k]; BF1(i) = f1[k]; }
+                    if (tp[k] & TP_ALIVE) alive_bits |= 1u << i;
+                }
+            }
         }
     }
+    // the bullet kernel's view of the env: list length, tank positions / alive flags / rewards
+    AT_HD void load_pass(bool first) {
+        cnt = st.cnt[e];
+        const uint32_t live = st.tlive[e];
+        if (!first) tstep = st.tstep[e];
+        // (the engine bumps episode_steps before the first pass; the controllers' kernel stores the increment)
+        epstep = st.epstep[e] + ((first && cfg_mode() != AT_MODE_TEAM_) ? 1u : 0u);
+        const int n = cfg_n();
+        for (int i0 = 0; i0 < n; i0 += 4) {   // (batched through registers: see load())
+            double x[4], y[4], rw[4];
+            uint32_t tp[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                x[k] = y[k] = rw[k] = 0.0; tp[k] = 0u;
+                if (i < n) { x[k] = st.tx[G(i)]; y[k] = st.ty[G(i)]; rw[k] = st.trew[G(i)]; tp[k] = st.tpack[G(i)]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                if (i < n) {
+                    TX(i) = x[k]; TY(i) = y[k]; TREW(i) = rw[k]; TPACK(i) = tp[k];
+                    TLIVE(i) = (uint8_t)((live >> (4 * i)) & 15u);
+                    if (tp[k] & TP_ALIVE) alive_bits |= 1u << i;
+                }
+            }
+        }
+    }
+    AT_HD void store_pass(bool first) {
+        st.cnt[e] = cnt;
+        if (!first) st.tstep[e] = tstep;
+        uint32_t live = 0;
+        for (int i = 0; i < cfg_n(); ++i) {
+            st.trew[G(i)] = TREW(i); st.tpack[G(i)] = TPACK(i);
+            live |= (uint32_t)TLIVE(i) << (4 * i);
+            if (first) {
+                st.nearlo[G(i)] = bm.nearlo[i * CS + tid];
+                if (cfg_n() * SLOTS_PER_TANK > 32) st.nearhi[G(i)] = bm.nearhi[i * CS + tid];
+            }
+        }
+        st.tlive[e] = live;
+    }
+    // what the first bullet pass leaves for the controllers: the dodge_reward candidates
+    AT_HD void load_handover() {
+        const int n = cfg_n();
+        const bool wide = n * SLOTS_PER_TANK > 32;
+        for (int i0 = 0; i0 < n; i0 += 4) {   // (batched through registers: see load())
+            uint32_t lo[4], hi[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                lo[k] = hi[k] = 0u;
+                if (i0 + k < n) { lo[k] = st.nearlo[G(i0 + k)]; if (wide) hi[k] = st.nearhi[G(i0 + k)]; }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = i0 + k;
+                if (i < n) {
+                    bm.nearlo[i * CS + tid] = lo[k];
+                    if (wide) bm.nearhi[i * CS + tid] = hi[k];
+                }
+            }
+        }
+    }
+    AT_HD void load_fixed_map() { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
     AT_HD void set_near() { M128 nm = near_wall_mask(wlo, whi); nlo = nm.lo; nhi = nm.hi; }
     AT_HD void load_scalars_only() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
@@ -1782,14 +1798,99 @@ struct SimT {
         st.cnt[e] = cnt; st.rng_ctr[e] = rng; st.tick[e] = tick; st.tstep[e] = tstep; st.epstep[e] = epstep;
         st.zones[e] = zones;
         if (cfg_maze()) { st.wall_lo[e] = wlo; st.wall_hi[e] = whi; }
+        uint32_t live = 0;
         for (int i = 0; i < cfg_n(); ++i) {
             st.tx[G(i)] = TX(i); st.ty[G(i)] = TY(i); st.trew[G(i)] = TREW(i);
             st.tpack[G(i)] = TPACK(i); st.tshot[G(i)] = TSHOT(i);
+            live |= (uint32_t)TLIVE(i) << (4 * i);
             if (cfg_ctrl(i) == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
         }
+        st.tlive[e] = live;
     }
 };
 typedef SimT<0> Sim;   // the generic build (emulator, reset kernel, every config without a specialisation)
+
+// One lane's part of a step of the warp's 32 envs: the body of env_kernel<true, SPEC> (and of the emulator's fibers).
+// e_warp0 = SoA index of the env of lane 0; lanes with valid == false own no env (ragged tail of the batch).
+template <class WP, int SPEC>
+AT_HD void step_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int tid, bool valid,
+                     uint32_t valid_mask, const int32_t *my_actions, float *rewards, uint8_t *done) {
+    const int64_t e = e_warp0 + (tid & 31);
+    SimT<SPEC> s(c, st, bm, e, tid);
+    s.valid = valid;
+    s.warp_mask = valid_mask;
+    if (valid) s.load();
+    else s.load_fixed_map();   // a lane without an env still serves pooled jobs, which test walls with the lane's own map
+    s.wrapper_pre(my_actions);
+    s.template game_step<WP>(my_actions);
+    if (!valid) return;
+    s.finish_step(rewards, done);
+    s.store();
+}
+
+// ---- the same step as three kernels (fixed maps, every mode but the arena): the bullet pass on its own (pass_lane,
+// twice per tick; the second one also posts rewards / done), the controllers between the passes (ctrl_lane), the
+// reset of the envs whose episode ended (fin_lane).  The pass owns no
+// per-env registers worth mentioning, so its kernel gives every warp only WE < 32 envs - the pooled jobs keep all 32
+// lanes busy anyway - and the GPU holds 32 / WE times as many warps to hide the fp64 latencies behind.
+// What one kernel hands to the next travels through the SoA state; on top of the monolithic kernel's columns: the
+// per-owner live counts and the dodge candidates of the first pass (DevState::tlive / nearlo / nearhi).
+template <class WP, int SPEC, int WE>
+AT_HD void pass_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int lane, bool first,
+                     float *rewards, uint8_t *done) {
+    const int64_t e = e_warp0 + lane;
+    SimT<SPEC, WE, WE> s(c, st, bm, e < st.N ? e : e_warp0, lane);
+    s.ew0 = (int)e_warp0;
+    s.valid = lane < WE && e < st.N;
+    s.load_fixed_map();
+    if (s.valid) s.load_pass(first);
+    s.template bullets_pass_pooled<WP>();
+    if (!s.valid) return;
+    if (!first) s.post_results(rewards, done);   // the tick is over: rewards / done (a done env is reset by fin_lane)
+    s.store_pass(first);
+}
+template <class WP, int SPEC>
+AT_HD void ctrl_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int tid, bool valid,
+                     uint32_t valid_mask, const int32_t *my_actions) {
+    if (!valid) return;   // (the pooled line-of-sight stage runs on the lanes of valid_mask)
+    SimT<SPEC> s(c, st, bm, e_warp0 + (tid & 31), tid);
+    s.warp_mask = valid_mask;
+    s.load();
+    s.load_handover();
+    s.wrapper_pre(my_actions);
+    s.tick += 1;
+    if (s.cfg_mode() != SimT<SPEC>::AT_MODE_TEAM_) s.epstep += 1;
+    int acts[MAX_TANKS][3];
+    uint32_t pre_done = 0, los_bits = 0;
+    s.template controllers<WP>(2, my_actions, acts, pre_done, los_bits);
+    s.store();
+}
+// what is left of the step for an env whose episode ended: terminal info latched, reset in place.  Rare (~0.5 % of
+// env-steps), so the env's working set is a private one (columns of stride 1 on the lane's stack), not shared memory.
+AT_HD void fin_lane(const KCfg &c, const DevState &st, int64_t e, const uint8_t *done) {
+    if (!done[e] || !c.auto_reset) return;
+    double tx[MAX_TANKS], ty[MAX_TANKS], trew[MAX_TANKS], bf0[MAX_TANKS], bf1[MAX_TANKS];
+    uint32_t tpack[MAX_TANKS], bpack[MAX_TANKS], nearlo[MAX_TANKS], nearhi[MAX_TANKS];
+    int32_t tshot[MAX_TANKS];
+    uint8_t tlive[MAX_TANKS];
+    BlockMem bm;
+    memset(&bm, 0, sizeof bm);
+    bm.tx = tx; bm.ty = ty; bm.trew = trew; bm.bf0 = bf0; bm.bf1 = bf1; bm.tpack = tpack; bm.bpack = bpack;
+    bm.nearlo = nearlo; bm.nearhi = nearhi; bm.tshot = tshot; bm.tlive = tlive;
+    SimT<0, 1, 32> s(c, st, bm, e, 0);
+    s.ew0 = (int)e;
+    s.load();
+    s.latch_terminal_info();
+    s.env_reset();
+    s.store();
+}
+// One lane's part of a (masked) reset: the generic build, nothing pooled.
+AT_HD void reset_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e, int tid) {
+    Sim s(c, st, bm, e, tid);
+    s.load();
+    s.env_reset();
+    s.store();
+}
 
 // wall rectangles (row-major = reference list order) + maze grid columns of a fixed map
 AT_HD void fill_static_template(uint64_t wall_lo, uint64_t wall_hi, float *tmpl) {

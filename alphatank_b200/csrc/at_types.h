@@ -71,21 +71,29 @@ struct DevState {
     const double *pend;            // [PEND_LUT] k-fold accumulation of BULLET_AWAY_PENALTY
     const uint8_t *udelta;         // [361] ulp offsets of the numpy-normalised bullet direction from (cos a, -sin a)
     const uint16_t *bfs_tab;       // [121*121] all-pairs bfs_first_step of a FIXED map: len | dir << 8 (null for mazes)
+    uint32_t *tlive;               // [N] live bullets per owner, 4 bits each (kept by shoot / the bullet passes)
+    // hand-over between the kernels of a split step (pass_lane -> ctrl_lane, at_sim.h)
+    uint32_t *nearlo, *nearhi;     // [n][N] dodge_reward candidates of the first bullet pass (bullet slots; hi: slots >= 32)
+    const double *dyn;             // [1] parameters a caller may change between steps (at_set_weakness): read from memory,
+                                   //     so a captured CUDA graph sees the new value.  dyn[0] = bot weakness
 };
 
 // per-block working set of the tanks / bots (shared memory on the GPU)
 struct BlockMem {
-    double *trig;                  // [722] copy of st.trig
     double *tx, *ty, *trew;        // [n][BS]
     double *bf0, *bf1;             // [n][BS]
     uint32_t *tpack, *bpack;       // [n][BS]
     uint8_t *tlive;                // [n][BS] live bullets per owner (<= 6)
     uint32_t *nearlo, *nearhi;     // [n][BS] bullet slots that may be within 100 px of the tank when it acts (hi: slots >= 32)
     int32_t *tshot;                // [n][BS]
-    uint8_t *slot_of;              // [n*6][BS] bullet slot of (owner, per-owner rank), valid for rank < tlive
-    const float *tmpl;             // [4W + 121] wall + maze observation columns of a fixed map
-    const uint8_t *udelta;         // [361] copy of st.udelta
     uint8_t *los_q, *los_r;        // [warps][256] pooled line-of-sight job queue / answers
+    // pooled bullet pass (Sim::bullets_pass_pooled): per env [BS] ...
+    uint32_t *e_alive;             // alive mask at the start of the pass
+    uint32_t *e_evt;               // list position of the first bullet that hit a tank in this pass (0xFF: none)
+    uint32_t *e_ord;               // owners that lost a bullet in this pass (their reward additions are replayed in order)
+    unsigned long long *e_k;       // toward-reward additions per owner, 8 bits each
+    uint16_t *res;                 // [6n][BS] per bullet: n_hi[0:3) expired 3 hit 4 victim[5:8) owner[8:11)
+    uint16_t *jobs;                // [warps][32 * 48] job list of the warp: env lane | list position << 5
 };
 
 }  // namespace at

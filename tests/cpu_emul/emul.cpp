@@ -1,13 +1,15 @@
 // emul.cpp - TEST-ONLY host emulation of the CUDA env kernel (alphatank_b200/csrc/at_kernels.cu).
 //
 // This GPU-less build container cannot run the kernels, so this file compiles the kernels' own per-thread
-// code (at_sim.h, __host__ __device__) with g++ and drives it the way env_kernel does: blocks of 64 envs,
-// phase A one "thread" per env over a block working set, phase B 32 "lanes" per observation row through a
-// staging buffer.  It lets the CPU test-suite compare the CUDA-side FORMULATION (cell bitmasks, integer-angle
-// tables, packed bullets, bit-parallel BFS, counter penalties, row builders) with the oracle before any GPU
+// code (at_sim.h, __host__ __device__) with g++ and drives it the way env_kernel does: blocks of 64 envs = two
+// warps, every warp 32 fibers of a small SIMT emulator (simt.h) that run step_lane<> - the kernel body - in
+// lockstep at the warp collectives, so the pooled stages (bullet jobs, line-of-sight queue) execute here exactly as
+// written; the observation rows come from the job functions of rows_kernel (at_rows.h).  It lets the CPU
+// test-suite compare the CUDA-side FORMULATION (cell bitmasks, integer-angle tables, packed bullets, pooled bullet
+// pass with in-order commits, bit-parallel BFS, counter penalties, row jobs) with the oracle before any GPU
 // time is spent.  It is not part of the product, is never loaded by alphatank_b200/, and is not a fallback:
-// the product fails loudly without a GPU.  What it cannot cover (warp sync, bulk-async stores, HBM layout
-// races) is covered by the -m gpu tests.
+// the product fails loudly without a GPU.  What it cannot cover (real memory ordering, bulk-async stores) is
+// covered by the -m gpu tests.
 #include <stdlib.h>
 #include <string.h>
 
@@ -17,6 +19,7 @@
 #include "../../alphatank_b200/csrc/at_host.h"
 #include "../../alphatank_b200/csrc/at_sim.h"
 #include "../../alphatank_b200/csrc/at_rows.h"
+#include "simt.h"
 
 using namespace at;
 
@@ -28,23 +31,19 @@ struct em_env {
     std::vector<char> arena;
     std::vector<char> block;  // one block's working set
     std::vector<float> tmpl;
-    std::vector<uint8_t> slot_of;
     BlockMem bm;
+    BlockMem pbm;             // one warp's working set of bullets_kernel (columns of stride WE)
+    std::vector<char> pblock;
+    simt::Warp warp;
 };
 static thread_local std::string g_err;
-
-struct DirectSink {  // the emulator writes column j of the env's observation row directly
-    float *row;
-    int j;
-    void reserve(int) {}
-    void put(float v) { row[j++] = v; }
-    void skip_static(const float *tmpl, int n) { for (int k = 0; k < n; ++k) row[j++] = tmpl[k]; }
-};
 
 template <int A, int B, int C>
 struct ShapeTag { static constexpr int nt = A, nr = B, tm = C; };
 // rows_kernel's formulation (at_rows.h): the rows of env e rebuilt from the STORED state by independent jobs
-static int g_rows_mode = 0;  // 0: Sim::emit_rows (the fused kernel's phase B), 1: the jobs of rows_kernel
+static int g_lane_order = 0;  // simt lane order between collectives: 0 forward, 1 reverse, 2 shuffled
+static int g_monolith = 0;    // 1: every step as one env_kernel (step_lane) even where the library would split it
+static int g_pass_we = 16;    // envs per warp of bullets_kernel
 static void rows_from_state(em_env *env, int64_t e, float *img) {
     const KCfg &c = env->k;
     const DevState &st = env->st;
@@ -79,43 +78,90 @@ static void rows_from_state(em_env *env, int64_t e, float *img) {
     else jobs(ShapeTag<0, 0, -1>{});
 }
 
+// bullets_kernel: every warp serves WE envs
+template <int SPEC, int WE>
+static void run_pass(em_env *env, bool first, float *rewards, uint8_t *done) {
+    const KCfg &c = env->k;
+    const DevState &st = env->st;
+    const int n = c.n_tanks;
+    BlockMem &bm = env->pbm;
+    char *p = env->pblock.data();
+    bm.tx = (double *)p; p += n * WE * 8; bm.ty = (double *)p; p += n * WE * 8; bm.trew = (double *)p; p += n * WE * 8;
+    bm.e_k = (unsigned long long *)p; p += WE * 8;
+    bm.tpack = (uint32_t *)p; p += n * WE * 4; bm.nearlo = (uint32_t *)p; p += n * WE * 4; bm.nearhi = (uint32_t *)p; p += n * WE * 4;
+    bm.e_alive = (uint32_t *)p; p += WE * 4; bm.e_evt = (uint32_t *)p; p += WE * 4;
+    bm.e_ord = (uint32_t *)p; p += WE * 4;
+    bm.res = (uint16_t *)p; p += n * SLOTS_PER_TANK * WE * 2; bm.jobs = (uint16_t *)p; p += n * SLOTS_PER_TANK * WE * 2;
+    bm.tlive = (uint8_t *)p; p += n * WE;
+    bm.bf0 = bm.bf1 = nullptr; bm.bpack = nullptr; bm.tshot = nullptr; bm.los_q = bm.los_r = nullptr;
+    for (int64_t e_warp0 = 0; e_warp0 < st.N; e_warp0 += WE)
+        simt::run_warp(env->warp, 0xffffffffu, [&](int lane) { pass_lane<simt::FiberWarp, SPEC, WE>(c, st, bm, e_warp0, lane, first, rewards, done); });
+}
+template <int SPEC>
+static void run_pass_we(em_env *env, bool first, float *rewards, uint8_t *done) {
+    if (g_pass_we == 8) run_pass<SPEC, 8>(env, first, rewards, done);
+    else if (g_pass_we == 32) run_pass<SPEC, 32>(env, first, rewards, done);
+    else run_pass<SPEC, 16>(env, first, rewards, done);
+}
+// the split step: bullets_kernel, ctrl_kernel, bullets_kernel, fin_kernel - each over the whole batch
+template <int SPEC>
+static void run_split(em_env *env, const int32_t *actions, float *rewards, uint8_t *done) {
+    const KCfg &c = env->k;
+    const DevState &st = env->st;
+    if (SPEC == 3) run_pass_we<3>(env, true, nullptr, nullptr); else run_pass_we<0>(env, true, nullptr, nullptr);
+    for (int64_t b0 = 0; b0 < env->n_envs; b0 += BS)
+        for (int wp = 0; wp < BS / 32; ++wp) {
+            const int64_t e_warp0 = b0 + wp * 32;
+            uint32_t valid_mask = 0;
+            for (int l = 0; l < 32; ++l)
+                if (e_warp0 + l < st.N) valid_mask |= 1u << l;
+            if (!valid_mask) continue;
+            simt::run_warp(env->warp, valid_mask, [&](int lane) {
+                const int64_t e = e_warp0 + lane;
+                ctrl_lane<simt::FiberWarp, SPEC>(c, st, env->bm, e_warp0, wp * 32 + lane, true, valid_mask,
+                                                 actions ? actions + e * c.act_rows * 3 : nullptr);
+            });
+        }
+    if (SPEC == 3) run_pass_we<3>(env, false, rewards, done); else run_pass_we<0>(env, false, rewards, done);
+    for (int64_t e = 0; e < st.N; ++e) fin_lane(c, st, e, done);
+}
+
 template <int SPEC>
 static void run_t(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
                 uint8_t *done) {
     const KCfg &c = env->k;
     const DevState &st = env->st;
     const int64_t row_len = (int64_t)c.rows * c.obs_dim;
-    for (int64_t b0 = 0; b0 < env->n_envs; b0 += BS) {
-        for (int tid = 0; tid < BS; ++tid) {
-            const int64_t e = b0 + tid;
-            if (e >= st.N) continue;
-            SimT<SPEC> s(c, st, env->bm, e, tid);
-            bool emit = false;
+    env->warp.order_mode = g_lane_order;
+    const bool split = is_step && !g_monolith && c.map != AT_MAP_MAZE && c.mode != AT_MODE_ARENA;   // as at_create decides
+    if (split) run_split<SPEC>(env, actions, rewards, done);
+    for (int64_t b0 = 0; b0 < env->n_envs && !split; b0 += BS) {
+        for (int wp = 0; wp < BS / 32; ++wp) {
+            const int64_t e_warp0 = b0 + wp * 32;
+            uint32_t valid_mask = 0;
+            for (int l = 0; l < 32; ++l)
+                if (e_warp0 + l < st.N) valid_mask |= 1u << l;
+            if (!valid_mask) continue;
             if (is_step) {
-                s.load();
-                float rw[MAX_TANKS];
-                const bool d = s.wrapper_step(actions ? actions + e * c.act_rows * 3 : nullptr, rw);
-                for (int r = 0; r < c.rows; ++r) rewards[e * c.rows + r] = rw[r];
-                done[e] = d ? 1 : 0;
-                if (d && c.auto_reset) { s.latch_terminal_info(); s.env_reset(); }
-                s.store();
-                emit = obs != nullptr;
-            } else if (!mask || mask[e]) {
-                s.load();
-                s.env_reset();
-                s.store();
-                emit = obs != nullptr;
-            }
-            if (emit && c.rows > 0) {
-                if (g_rows_mode) {
-                    for (int64_t q = 0; q < row_len; ++q) obs[e * row_len + q] = -12345.0f;  // every column must be written
-                    rows_from_state(env, e, obs + e * row_len);
-                } else {
-                    DirectSink out{obs + e * row_len, 0};
-                    s.emit_rows(out);
+                simt::run_warp(env->warp, 0xffffffffu, [&](int lane) {
+                    const int64_t e = e_warp0 + lane;
+                    const bool valid = e < st.N;
+                    step_lane<simt::FiberWarp, SPEC>(c, st, env->bm, e_warp0, wp * 32 + lane, valid, valid_mask,
+                                                     (actions && valid) ? actions + e * c.act_rows * 3 : nullptr, rewards, done);
+                });
+            } else {
+                for (int l = 0; l < 32; ++l) {
+                    const int64_t e = e_warp0 + l;
+                    if (e < st.N && (!mask || mask[e])) reset_lane(c, st, env->bm, e, wp * 32 + l);
                 }
             }
         }
+    }
+    if (obs == nullptr || c.rows == 0) return;
+    for (int64_t e = 0; e < st.N; ++e) {   // rows_kernel: every stepped env; the masked ones of a reset
+        if (!is_step && mask && !mask[e]) continue;
+        for (int64_t q = 0; q < row_len; ++q) obs[e * row_len + q] = -12345.0f;  // every column must be written
+        rows_from_state(env, e, obs + e * row_len);
     }
 }
 
@@ -157,29 +203,41 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->st.bfs_tab = (const uint16_t *)(env->arena.data() + L.o_bfs);
     }
     const int n = env->k.n_tanks;
-    env->block.assign((size_t)n * BS * (5 * 8 + 6 * 4) + 722 * 8, 0);
+    env->block.assign((size_t)n * BS * (5 * 8 + 6 * 4) + 722 * 8 + (size_t)BS * (8 + 4 * 4) + (size_t)n * SLOTS_PER_TANK * BS * 2 +
+                      (size_t)(BS / 32) * 32 * SLOTS_PER_TANK * n * 2 + (size_t)(BS / 32) * 512 + 64, 0);
     char *p = env->block.data();
     BlockMem &bm = env->bm;
-    bm.trig = (double *)p; p += 722 * 8;
-    memcpy(bm.trig, env->luts.trig.data(), 722 * 8);
     bm.tx = (double *)p; p += n * BS * 8; bm.ty = (double *)p; p += n * BS * 8; bm.trew = (double *)p; p += n * BS * 8;
     bm.bf0 = (double *)p; p += n * BS * 8; bm.bf1 = (double *)p; p += n * BS * 8;
+    bm.e_k = (unsigned long long *)p; p += BS * 8;
     bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.nearlo = (uint32_t *)p; p += n * BS * 4;
     bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint8_t *)p; p += n * BS * 4;
     bm.tshot = (int32_t *)p; p += n * BS * 4;
     bm.nearhi = (uint32_t *)p; p += n * BS * 4;
+    bm.e_alive = (uint32_t *)p; p += BS * 4; bm.e_evt = (uint32_t *)p; p += BS * 4;
+    bm.e_ord = (uint32_t *)p; p += BS * 4;
+    bm.res = (uint16_t *)p; p += (size_t)n * SLOTS_PER_TANK * BS * 2;
+    bm.jobs = (uint16_t *)p; p += (size_t)(BS / 32) * 32 * SLOTS_PER_TANK * n * 2;
+    bm.los_q = (uint8_t *)p; p += (BS / 32) * 256;
+    bm.los_r = (uint8_t *)p; p += (BS / 32) * 256;
+    env->pblock.assign((size_t)n * 32 * (3 * 8 + 3 * 4 + 1) + 32 * (8 + 16) + (size_t)n * SLOTS_PER_TANK * 32 * 4 + 64, 0);
     env->tmpl.assign(4 * 72 + CELLS, 0.f);
     if (env->k.map != AT_MAP_MAZE) fill_static_template(env->k.wall_lo, env->k.wall_hi, env->tmpl.data());
-    env->slot_of.assign((size_t)n * SLOTS_PER_TANK * BS, 0);
-    bm.tmpl = env->tmpl.data();
-    bm.slot_of = env->slot_of.data();
-    bm.udelta = env->luts.udelta.data();
+    *(double *)(env->arena.data() + L.o_dyn) = env->k.weakness;
     run(env, false, nullptr, nullptr, nullptr, nullptr, nullptr);  // the constructor's own reset
     *out = env;
     return AT_OK;
 }
 void em_destroy(em_env *env) { delete env; }
-void em_set_rows_mode(int m) { g_rows_mode = m; }
+void em_set_lane_order(int m) { g_lane_order = m; }
+void em_set_monolith(int m) { g_monolith = m; }
+void em_set_pass_we(int w) { g_pass_we = w; }
+int em_set_weakness(em_env *env, double w) {
+    *(double *)env->st.dyn = w;
+    env->k.weakness = w;
+    return AT_OK;
+}
+uint64_t em_collectives(em_env *env) { return env->warp.collectives; }
 void em_set_spec_cap(int cap) { g_spec_cap = cap; }
 int em_obs_dim(em_env *env) { return env->k.obs_dim; }
 int em_obs_rows(em_env *env) { return env->k.rows; }

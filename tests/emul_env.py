@@ -15,7 +15,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "alphatank_b200", "csrc")
 
 
 def build():
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("at_sim.h", "at_host.h", "at_types.h", "at_rows.h")]
+    deps = [SRC, os.path.join(HERE, "cpu_emul", "simt.h")] + [os.path.join(CSRC, f) for f in ("at_sim.h", "at_host.h", "at_types.h", "at_rows.h", "at_warp.h")]
     if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-ffp-contract=off", "-mfma", "-std=c++17", "-shared", "-o", LIB,
                                SRC, "-lm"])
@@ -25,34 +25,22 @@ def build():
 _lib = None
 
 
-def build_variant(defines, tag):
-    """The emulator compiled with extra -D switches of at_sim.h (experiment paths kept behind default-off switches)."""
-    out = os.path.join(HERE, "cpu_emul", "libat_emul_%s.so" % tag)
-    deps = [SRC] + [os.path.join(CSRC, f) for f in ("at_sim.h", "at_host.h", "at_types.h", "at_rows.h")]
-    if not os.path.exists(out) or os.path.getmtime(out) < max(os.path.getmtime(d) for d in deps):
-        subprocess.check_call(["g++", "-O2", "-fPIC", "-ffp-contract=off", "-mfma", "-std=c++17", "-shared"] +
-                              ["-D" + d for d in defines] + ["-o", out, SRC, "-lm"])
-    return out
-
-
-def use_library(path=None):
-    """Switch the emulator library the next EmulEnv objects bind (None: back to the default build)."""
-    global _lib
-    _lib = None
-    return lib(path)
-
-
-def lib(path=None):
+def lib():
     global _lib
     if _lib is None:
-        L = C.CDLL(path or build())
+        L = C.CDLL(build())
         vp, i32, i64 = C.c_void_p, C.c_int32, C.c_int64
         L.em_create.argtypes = [vp, i64, i64, C.c_uint64, C.POINTER(vp)]
         L.em_destroy.argtypes = [vp]
         for f in ("em_obs_dim", "em_obs_rows", "em_action_rows"):
             getattr(L, f).argtypes = [vp]
         L.em_reset.argtypes = [vp, vp, vp]
-        L.em_set_rows_mode.argtypes = [i32]
+        L.em_set_lane_order.argtypes = [i32]
+        L.em_set_monolith.argtypes = [i32]
+        L.em_set_pass_we.argtypes = [i32]
+        L.em_set_weakness.argtypes = [vp, C.c_double]
+        L.em_collectives.argtypes = [vp]
+        L.em_collectives.restype = C.c_uint64
         L.em_set_spec_cap.argtypes = [i32]
         L.em_step.argtypes = [vp, vp, vp, vp, vp]
         L.em_get_state.argtypes = [vp, i64, vp]

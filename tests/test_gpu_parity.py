@@ -286,17 +286,15 @@ def test_set_weakness_hot_swap_equals_construction_and_oracle():
     ("team_vs_bot_maze", {"AT_ROWS_LGG": "2"}),
     ("team_8_mixed", {}), ("team_three_teams_nodebuff", {}), ("botagent_smart_maze", {}), ("agent_nobuff_battlefield", {}),
 ])
-def test_split_rows_kernel_equals_fused_rows(name, knobs):
-    """Default path = simulation kernel + rows_kernel (rows rebuilt from the stored state, one bulk copy per group of
-    envs); AT_FUSED_ROWS=1 = the single fused kernel.  Same bits in every observation column on a ragged batch
-    (1003 envs: the last group is partial), through auto-resets, and after a masked reset."""
+def test_rows_kernel_launch_shapes_agree_with_the_oracle(name, knobs):
+    """rows_kernel (rows rebuilt from the stored state, one bulk copy per group of envs) under its launch knobs -
+    envs per group, plain instead of programmatic dependent launch, blocks per SM, warps per block - against the
+    oracle: the same bits in every observation column on a ragged batch (1003 envs: the last group is partial),
+    through auto-resets, and after a masked reset."""
     spec = SWEEP[name]
     N, seed, base = 1003, 31, 900
-    old = {k: os.environ.get(k) for k in ("AT_FUSED_ROWS", "AT_ROWS_LGG", "AT_NO_PDL", "AT_ROWS_BPS", "AT_ROWS_WARPS")}
+    old = {k: os.environ.get(k) for k in ("AT_ROWS_LGG", "AT_NO_PDL", "AT_ROWS_BPS", "AT_ROWS_WARPS")}
     try:
-        os.environ["AT_FUSED_ROWS"] = "1"
-        a = _gpu(spec, N, seed, base, auto_reset=True)
-        os.environ["AT_FUSED_ROWS"] = "0"
         os.environ.update(knobs)
         b = _gpu(spec, N, seed, base, auto_reset=True)
     finally:
@@ -305,11 +303,12 @@ def test_split_rows_kernel_equals_fused_rows(name, knobs):
                 os.environ.pop(k, None)
             else:
                 os.environ[k] = v
+    a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
     assert np.array_equal(a.reset(), b.reset())
     ids = np.arange(base, base + N)
     for t in range(120):
         acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
-        oa, ra, da = a.step(acts)
+        oa, ra, da = a.step(acts, threads=4)
         ob, rb, db = b.step(acts)
         assert np.array_equal(da, db) and np.array_equal(ra, rb)
         if not np.array_equal(oa, ob):

@@ -91,30 +91,6 @@ def test_kernel_logic_matches_oracle_on_batches(name):
     assert dones > 0 or spec["mode"] == "agent"
 
 
-@pytest.mark.parametrize("name", sorted(SWEEP))
-def test_rows_kernel_jobs_match_oracle_on_batches(name):
-    """The split path's row builder (csrc/at_rows.h: rows rebuilt from the STORED state by independent jobs, the
-    per-thread code of rows_kernel) against the oracle: every observation column bit-exact, none left unwritten."""
-    spec = SWEEP[name]
-    N, ticks, seed, base = 70, 200, 77, 500
-    a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
-    emul_env.lib().em_set_rows_mode(1)
-    try:
-        b = emul_env.make_emul_env(spec, N, seed, base, auto_reset=True)
-        assert np.array_equal(a.reset(), b.reset())
-        ids = np.arange(base, base + N)
-        for t in range(ticks):
-            acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
-            oa, ra, da = a.step(acts, threads=4)
-            ob, rb, db = b.step(acts)
-            assert np.array_equal(da, db) and np.array_equal(ra, rb)
-            if not np.array_equal(oa, ob):
-                bad = np.argwhere(oa != ob)
-                raise AssertionError("%s tick %d obs differ at (env, col) %s" % (name, t, bad[:8].tolist()))
-    finally:
-        emul_env.lib().em_set_rows_mode(0)
-
-
 def test_bfs_bitparallel_matches_reference_pairs():
     z = np.load(os.path.join(parity.GOLDEN, "bfs.npz"))
     grids, cases = z["grids"], z["cases"]
@@ -235,14 +211,18 @@ def test_simulation_specialisations_agree(cap):
         emul_env.lib().em_set_spec_cap(3)
 
 
-@pytest.mark.parametrize("split", [1, 2])
-def test_bullet_split_switch_is_bit_exact(split):
-    """AT_BULLET_SPLIT (default off; profiles/r04c_step_kernels.md r04g): bullet_move as bullet_geom + bullet_commit,
-    one or two bullets per iteration - the same streams as the oracle on the bench configuration and a 1v1 arena."""
-    path = emul_env.build_variant(["AT_BULLET_SPLIT=%d" % split], "split%d" % split)
+@pytest.mark.parametrize("order", [1, 2])
+def test_pooled_stages_do_not_depend_on_the_lane_order(order):
+    """The pooled stages (Sim::bullets_pass_pooled, pool_los) run here on the SIMT emulator (tests/cpu_emul/simt.h):
+    32 fibers per warp that meet at the warp collectives.  Between two collectives the emulator runs the lanes one
+    after the other - in reverse (1) or freshly shuffled (2) order here instead of lane order - so a lane that read
+    another lane's shared-memory write without a barrier in between would diverge from the oracle.  Bullet-heavy
+    configs: the bench layout, the immortal arena (a hit every few ticks: F6 bonus + the serial tail behind a hit)
+    and the 8-tank mix (48 slots: 64-bit candidate masks)."""
+    L = emul_env.lib()
+    L.em_set_lane_order(order)
     try:
-        emul_env.use_library(path)
-        for name in ("team_vs_bot", "arena_def_dodge_t200"):
+        for name in ("team_vs_bot", "arena_def_dodge_t200", "team_8_mixed"):
             spec = SWEEP[name]
             N, ticks, seed, base = 70, 220, 31, 64
             a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
@@ -257,5 +237,6 @@ def test_bullet_split_switch_is_bit_exact(split):
             sa, sb = a.get_state(), b.get_state()
             for f in ("n_bullets", "rng_ctr"):
                 assert np.array_equal(sa[f], sb[f]), f
+            assert L.em_collectives(b.h) > 0
     finally:
-        emul_env.use_library(None)
+        L.em_set_lane_order(0)

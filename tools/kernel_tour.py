@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Small tour of every kernel the library launches: the step in its split / fused / normalised / host-buffer forms on
+"""Small tour of every kernel the library launches: the step in its plain / normalised / host-buffer forms on
 four env kinds (partial last block, per-env mazes), masked resets, the info kernels, state snapshots, and the
 learner-side kernels - with torch's caching allocator off, so every buffer is its own cudaMalloc.  (Written for
 compute-sanitizer; that tool is closed on this GPU pool, so the tour only checks that every launch succeeds.)
@@ -55,9 +55,6 @@ tour("team harder, battlefield", MultiAgentTeamEnv(team_vs_bot_harder_configs, n
 tour("1v1 bot_agent smart, maze", MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=100, device=dev, seed=3, map="maze"))
 tour("arena defensive vs dodge", MultiAgentEnv(mode="bot_vs_bot", bot_types=("defensive", "dodge"), num_envs=65, device=dev, seed=4,
                                                terminate_time=16))
-os.environ["AT_FUSED_ROWS"] = "1"
-tour("team 2v2, fused rows", MultiAgentTeamEnv(team_vs_bot_configs, num_envs=100, device=dev, seed=5), norm_ok=False)
-os.environ.pop("AT_FUSED_ROWS")
 
 # learner-side kernels: tick normaliser, sampling, policy tail / mid kernels through one small rollout
 from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, collect_rollout  # noqa: E402
