@@ -78,7 +78,7 @@ class BatchedTankEnv:
         self.done = torch.zeros((N,), dtype=torch.uint8, device=dev)
         self._actions = torch.zeros((N, max(self.A, 1), 3), dtype=torch.int32, device=dev)
         self._h_rewards = self._h_done = None
-        self._prev_cum = None                     # delta_rewards(): the cumulative rewards of the previous step
+        self._tank_cols = None                    # scratch of tank_columns()
 
     def close(self):
         if getattr(self, "h", None):
@@ -97,25 +97,29 @@ class BatchedTankEnv:
         if mask is not None:
             m = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
         _capi.check(self.L.at_reset(self.h, _ptr(m), _ptr(obs), self._stream()), "at_reset")
-        if self._prev_cum is not None:            # a reset episode starts from zero (gaming_env.py:48-66 zeroes tank.reward)
-            if m is None:
-                self._prev_cum.zero_()
-            else:
-                self._prev_cum.masked_fill_(m.bool().unsqueeze(-1), 0.0)
         return obs
 
-    def delta_rewards(self, rewards, done):
-        """Per-step reward increments from the CUMULATIVE per-episode rewards the reference's wrappers return
-        (gym_env.py:186-187, gym_env_multi.py:307-308; quirk F1): r_t - r_(t-1) inside an episode, r_t on its first
-        step.  Call once per step with that step's outputs; explicit resets are tracked by reset()."""
-        if self._prev_cum is None:
-            self._prev_cum = torch.zeros_like(rewards)
-        out = rewards - self._prev_cum
-        if self.cfg.auto_reset:                   # an env that returned done has been reset inside the step
-            self._prev_cum = rewards * (1.0 - done.to(torch.float32)).unsqueeze(-1)
-        else:
-            self._prev_cum = rewards.clone()
-        return out
+    def set_reward_mode(self, mode):
+        """'cumulative': the reference's per-episode running sums (gym_env.py:186-187, gym_env_multi.py:307-308; quirk
+        F1).  'delta': per-step increments - r_t - r_(t-1) inside an episode, r_t on its first step - computed inside
+        the step kernel (at_set_reward_mode); a reset episode starts from zero (gaming_env.py:48-66 zeroes
+        tank.reward)."""
+        _capi.check(self.L.at_set_reward_mode(self.h, {"cumulative": 0, "delta": 1}[mode]), "at_set_reward_mode")
+
+    def observe(self, obs_out=None):
+        """The observation rows of the current state (env._get_observation(), gym_env.py:105-183) - nothing stepped."""
+        obs = self.obs if obs_out is None else obs_out
+        _capi.check(self.L.at_observe(self.h, _ptr(obs), self._stream()), "at_observe")
+        return obs
+
+    def tank_columns(self, tank):
+        """float64 [7, N] on the device: alive, x, y, angle, reward, num_hit, num_be_hit of tank ``tank`` - one small
+        kernel on the current stream, nothing goes through the host."""
+        if self._tank_cols is None:
+            self._tank_cols = torch.empty((7, self.num_envs), dtype=torch.float64, device=self.device)
+        _capi.check(self.L.at_get_tank_columns(self.h, int(tank), _ptr(self._tank_cols), self._stream()),
+                    "at_get_tank_columns")
+        return self._tank_cols
 
     def _device_actions(self, actions):
         if self.A == 0:
@@ -224,20 +228,22 @@ class BatchedTankEnv:
 
 
 class TankView:
-    """``env.game_env.tanks[i]`` stand-in: per-tank state columns as torch tensors over the batch
-    (the reference's callers read ``tanks[i].alive``, inference.py:115-116)."""
+    """``env.game_env.tanks[i]`` stand-in: per-tank state columns as torch tensors over the batch, on the env's device
+    (the reference's callers read ``tanks[i].alive`` every tick, inference.py:115-116).  Every read is one small
+    column kernel (at_get_tank_columns) - no host round trip, no full-state snapshot."""
+
+    _COLS = {"alive": 0, "x": 1, "y": 2, "angle": 3, "reward": 4, "num_hit": 5, "num_be_hit": 6}
 
     def __init__(self, owner, index):
         self._o, self._i = owner, index
 
     def _col(self, name):
-        st = self._o.core.get_state()
-        return torch.as_tensor(st["tanks"][name][:, self._i].copy())
+        return self._o.core.tank_columns(self._i)[self._COLS[name]].clone()
 
-    alive = property(lambda s: s._col("alive").bool())
+    alive = property(lambda s: s._col("alive") != 0)
     x = property(lambda s: s._col("x"))
     y = property(lambda s: s._col("y"))
-    angle = property(lambda s: s._col("angle"))
+    angle = property(lambda s: s._col("angle").to(torch.int32))
     reward = property(lambda s: s._col("reward"))
-    num_hit = property(lambda s: s._col("num_hit"))
-    num_be_hit = property(lambda s: s._col("num_be_hit"))
+    num_hit = property(lambda s: s._col("num_hit").to(torch.int32))
+    num_be_hit = property(lambda s: s._col("num_be_hit").to(torch.int32))

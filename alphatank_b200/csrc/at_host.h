@@ -182,7 +182,7 @@ inline int sim_spec_for(const KCfg &k, int cap = 3) {
 // One arena for every SoA column (HBM on the GPU, malloc in the emulator).
 struct ArenaLayout {
     size_t o_cnt, o_rng, o_tick, o_tstep, o_ep, o_zones, o_prev, o_change, o_wlo, o_whi, o_tx, o_ty, o_trew, o_tpack,
-        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_udir, o_bfs, o_tmpl, o_act, o_rw, o_dn, o_ttick, o_twin, o_thit, o_dyn, o_tlive, o_nearlo, o_nearhi, bytes;
+        o_thits, o_tshot, o_bpack, o_bf0, o_bf1, o_bx, o_by, o_bm, o_trig, o_corn, o_pend, o_udir, o_bfs, o_tmpl, o_act, o_rw, o_dn, o_ttick, o_twin, o_thit, o_dyn, o_prevrw, o_atab, bytes;
 };
 inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     ArenaLayout L;
@@ -202,7 +202,8 @@ inline ArenaLayout arena_layout(const KCfg &k, int64_t N) {
     L.o_dn = take(N);
     L.o_ttick = take(4 * N); L.o_twin = take(4 * N); L.o_thit = take(4 * N * n);
     L.o_dyn = take(64);
-    L.o_tlive = take(4 * N); L.o_nearlo = take(4 * N * n); L.o_nearhi = take(4 * N * n);
+    L.o_atab = take(361 * 5 * 8);
+    L.o_prevrw = take(4 * N * (k.rows ? k.rows : 1));
     L.bytes = bytes;
     return L;
 }
@@ -222,7 +223,8 @@ inline void bind_state(DevState &st, char *b, const ArenaLayout &L, int64_t N) {
     st.term_hits = (uint32_t *)(b + L.o_thit);
     st.udelta = (const uint8_t *)(b + L.o_udir);
     st.bfs_tab = nullptr;  // set by the owner for fixed maps (at_sim.h fill_bfs_table)
-    st.tlive = (uint32_t *)(b + L.o_tlive); st.nearlo = (uint32_t *)(b + L.o_nearlo); st.nearhi = (uint32_t *)(b + L.o_nearhi);
+    st.prev_rew = (float *)(b + L.o_prevrw);
+    st.atab = (const double *)(b + L.o_atab);   // the owner fills it (at_sim.h fill_atan_table)
     st.dyn = (const double *)(b + L.o_dyn);   // the owner writes dyn[0] = weakness
 }
 
@@ -253,13 +255,10 @@ AT_HD void scatter_env(const KCfg &c, const DevState &st, int64_t e, const Packe
         st.tpack[g] = p.tpack[i]; st.thits[g] = p.thits[i]; st.bpack[g] = p.bpack[i]; st.tshot[g] = p.tshot[i];
         st.change_time[g] = p.change_time[i];
     }
-    uint32_t live = 0;
     for (uint32_t s = 0; s < p.cnt; ++s) {
         int64_t g = (int64_t)s * st.N + e;
         st.bx[g] = p.bx[s]; st.by[g] = p.by[s]; st.bmeta[g] = p.bmeta[s];
-        live += 1u << (4 * (int)(p.bmeta[s] & 15u));
     }
-    st.tlive[e] = live;
 }
 
 inline void unpack_env(const KCfg &k, const HostLuts &l, const PackedEnv &p, at_env_state &o) {

@@ -2,11 +2,11 @@
 //
 // One tick = env_kernel (the simulation: state in, state / rewards / done out) + rows_kernel (the observation rows,
 // rebuilt from the stored state), the second launched as a programmatic dependent of the first.
-//   env_kernel   Tanks / bot FSMs of the block's 64 envs live in shared memory ([field][tank][thread],
-//                conflict-free); bullets stay in HBM as [slot][env] columns.  Every env has a home lane for its scalar
-//                bookkeeping; the bullets of a warp's 32 envs and the smart bots' line-of-sight queries are pooled
-//                into job lists that all 32 lanes work through (at_sim.h), so lane use does not depend on how many
-//                bullets each env happens to have.  Rewards / done are written here; done envs are reset in place.
+//   env_kernel   One thread per env.  Tanks / bot FSMs of the block's 64 envs live in shared memory
+//                ([field][tank][thread], conflict-free); bullets stay in HBM as [slot][env] columns (every warp access
+//                is a contiguous run).  Sequential per-env semantics (firing order, tank order) are exact by
+//                construction; the smart bots' line-of-sight queries of a warp are pooled (at_sim.h).  Rewards / done
+//                are written here; done envs are reset in place.
 //   rows_kernel  Every warp assembles the R x D rows of a group of envs as an image in shared memory (static wall /
 //                maze columns once per warp, dynamic columns by independent jobs, at_rows.h) and ships the image with
 //                ONE bulk-async (TMA, SASS UBLKCP) copy.
@@ -34,51 +34,42 @@ namespace {
 
 struct SmemLayout {
     int n;
-    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_ek, off_tpack, off_nearlo, off_nearhi, off_bpack,
-        off_tshot, off_ealive, off_eevt, off_eord, off_acts, off_res, off_jobs, off_tlive, off_udelta, off_losq, total;
+    size_t off_trig, off_tx, off_ty, off_trew, off_bf0, off_bf1, off_tpack, off_nearlo, off_nearhi, off_bpack, off_tshot,
+        off_acts, off_tlive, off_udelta, off_losq, total;
 };
-// pooled = false: without the columns of the pooled bullet pass (ctrl_kernel)
-__host__ __device__ inline SmemLayout smem_layout(int n, int n_bots, int act_rows, bool pooled = true) {
+__host__ __device__ inline SmemLayout smem_layout(int n, int n_bots, int act_rows) {
     const int nb = n_bots > 0 ? n_bots : 1;
     SmemLayout L;
     L.n = n;
     size_t o = 0;
-    L.off_trig = o;
+    L.off_trig = o; o += 722 * 8;
     L.off_tx = o; o += (size_t)n * BS * 8;
     L.off_ty = o; o += (size_t)n * BS * 8;
     L.off_trew = o; o += (size_t)n * BS * 8;
     L.off_bf0 = o; o += (size_t)nb * BS * 8;
     L.off_bf1 = o; o += (size_t)nb * BS * 8;
-    L.off_ek = o; o += pooled ? (size_t)BS * 8 : 0;
     L.off_tpack = o; o += (size_t)n * BS * 4;
     L.off_nearlo = o; o += (size_t)n * BS * 4;
     L.off_nearhi = o; o += n * SLOTS_PER_TANK > 32 ? (size_t)n * BS * 4 : 0;
     L.off_bpack = o; o += (size_t)nb * BS * 4;
     L.off_tshot = o; o += (size_t)n * BS * 4;
-    L.off_ealive = o; o += pooled ? (size_t)BS * 4 : 0;
-    L.off_eevt = o; o += pooled ? (size_t)BS * 4 : 0;
-    L.off_eord = o; o += pooled ? (size_t)BS * 4 : 0;
     L.off_acts = o; o += (size_t)BS * act_rows * 3 * 4;      // staging area of the action rows
-    L.off_res = o; o += pooled ? (size_t)n * SLOTS_PER_TANK * BS * 2 : 0;
-    L.off_jobs = o; o += pooled ? (size_t)(BS / 32) * 32 * SLOTS_PER_TANK * n * 2 : 0;
     L.off_tlive = o; o += (size_t)n * BS;
-    L.off_udelta = o;
+    L.off_udelta = o; o += 368;
     L.off_losq = o; o += (size_t)(BS / 32) * 512;
     L.total = (o + 15) & ~(size_t)15;
     return L;
 }
 __device__ inline void bind_block_mem(BlockMem &bm, unsigned char *smem, const SmemLayout &L) {
+    bm.trig = (double *)(smem + L.off_trig);
     bm.tx = (double *)(smem + L.off_tx); bm.ty = (double *)(smem + L.off_ty);
     bm.trew = (double *)(smem + L.off_trew);
     bm.bf0 = (double *)(smem + L.off_bf0); bm.bf1 = (double *)(smem + L.off_bf1);
-    bm.e_k = (unsigned long long *)(smem + L.off_ek);
     bm.tpack = (uint32_t *)(smem + L.off_tpack); bm.nearlo = (uint32_t *)(smem + L.off_nearlo);
     bm.nearhi = (uint32_t *)(smem + L.off_nearhi);
     bm.bpack = (uint32_t *)(smem + L.off_bpack); bm.tlive = (uint8_t *)(smem + L.off_tlive);
     bm.tshot = (int32_t *)(smem + L.off_tshot);
-    bm.e_alive = (uint32_t *)(smem + L.off_ealive); bm.e_evt = (uint32_t *)(smem + L.off_eevt);
-    bm.e_ord = (uint32_t *)(smem + L.off_eord);
-    bm.res = (uint16_t *)(smem + L.off_res); bm.jobs = (uint16_t *)(smem + L.off_jobs);
+    bm.udelta = (uint8_t *)(smem + L.off_udelta);
     bm.los_q = (uint8_t *)(smem + L.off_losq);
     bm.los_r = bm.los_q + (BS / 32) * 256;
 }
@@ -156,6 +147,21 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     BlockMem bm;
     bind_block_mem(bm, smem, L);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {   // table copies: every load is issued before the first store (one round trip instead of a dozen)
+        uint8_t *udl = (uint8_t *)(smem + L.off_udelta);
+        constexpr int TRIG_IT = (722 + BS - 1) / BS, UDL_IT = (361 + BS - 1) / BS;
+        double tv[TRIG_IT];
+        uint8_t uv[UDL_IT];
+#pragma unroll
+        for (int k = 0; k < TRIG_IT; ++k) tv[k] = tid + k * BS < 722 ? __ldg(st.trig + tid + k * BS) : 0.0;
+#pragma unroll
+        for (int k = 0; k < UDL_IT; ++k) uv[k] = tid + k * BS < 361 ? __ldg(st.udelta + tid + k * BS) : (uint8_t)0;
+#pragma unroll
+        for (int k = 0; k < TRIG_IT; ++k) if (tid + k * BS < 722) bm.trig[tid + k * BS] = tv[k];
+#pragma unroll
+        for (int k = 0; k < UDL_IT; ++k) if (tid + k * BS < 361) udl[tid + k * BS] = uv[k];
+    }
+    __syncthreads();
 
     const int64_t e_warp0 = (int64_t)blockIdx.x * BS + warp * 32;
     const int64_t e = e_warp0 + lane;
@@ -178,7 +184,7 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
                                  : "memory");
             my_actions = wstage + lane * row_ints;
         }
-        if (valid_mask) step_lane<DevWarp, SPEC>(c, st, bm, e_warp0, tid, valid, valid_mask, my_actions, rewards, done);
+        if (valid) step_lane<DevWarp, SPEC>(c, st, bm, e_warp0, tid, valid_mask, my_actions, rewards, done);
     } else if (valid && (!mask || mask[e])) {
         reset_lane(c, st, bm, e, tid);
     }
@@ -189,101 +195,6 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
         sig.dbg_times[2 * blockIdx.x + 1] = t1;
     }
     signal_host(sig, tid);
-}
-
-// ---- the split step (at_sim.h: pass_lane / ctrl_lane / fin_lane): bullets_kernel, ctrl_kernel, fin_kernel.
-// Every kernel is launched as a programmatic dependent of its predecessor: the table copies of its prologue overlap
-// the predecessor's tail; griddepcontrol.wait orders everything else behind the predecessor's stores.
-constexpr int PK_WARPS = 4;   // warps per block of bullets_kernel
-#ifndef PK_MIN_BLOCKS
-#define PK_MIN_BLOCKS 7       // blocks per SM the register allocation must allow (28 warps)
-#endif
-struct PassSmem {
-    size_t off_tx, off_ty, off_trew, off_ek, off_tpack, off_nearlo, off_nearhi, off_ealive, off_eevt, off_eord,
-        off_res, off_jobs, off_tlive, per_warp, total;
-};
-__host__ __device__ inline PassSmem pass_smem_layout(int n, int WE) {
-    PassSmem L;
-    size_t o = 0;
-    L.off_tx = o; o += (size_t)n * WE * 8;
-    L.off_ty = o; o += (size_t)n * WE * 8;
-    L.off_trew = o; o += (size_t)n * WE * 8;
-    L.off_ek = o; o += (size_t)WE * 8;
-    L.off_tpack = o; o += (size_t)n * WE * 4;
-    L.off_nearlo = o; o += (size_t)n * WE * 4;
-    L.off_nearhi = o; o += n * SLOTS_PER_TANK > 32 ? (size_t)n * WE * 4 : 0;
-    L.off_ealive = o; o += (size_t)WE * 4;
-    L.off_eevt = o; o += (size_t)WE * 4;
-    L.off_eord = o; o += (size_t)WE * 4;
-    L.off_res = o; o += (size_t)n * SLOTS_PER_TANK * WE * 2;
-    L.off_jobs = o; o += (size_t)n * SLOTS_PER_TANK * WE * 2;
-    L.off_tlive = o; o += (size_t)n * WE;
-    L.per_warp = (o + 15) & ~(size_t)15;
-    L.total = L.per_warp * PK_WARPS;
-    return L;
-}
-// One bullet pass over the whole batch: every warp serves WE envs (pass_lane).
-// The second pass of a tick (first == 0) also posts the step's rewards / done.
-template <int WE, int SPEC>
-__global__ void __launch_bounds__(PK_WARPS * 32, PK_MIN_BLOCKS) bullets_kernel(const __grid_constant__ KCfg c, const DevState st, int first,
-                                                                            float *__restrict__ rewards, uint8_t *__restrict__ done,
-                                                                            HostSignal sig) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    const PassSmem L = pass_smem_layout(c.n_tanks, WE);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    unsigned char *ws = smem + (size_t)warp * L.per_warp;
-    BlockMem bm;
-    bm.tx = (double *)(ws + L.off_tx); bm.ty = (double *)(ws + L.off_ty); bm.trew = (double *)(ws + L.off_trew);
-    bm.e_k = (unsigned long long *)(ws + L.off_ek);
-    bm.tpack = (uint32_t *)(ws + L.off_tpack); bm.nearlo = (uint32_t *)(ws + L.off_nearlo);
-    bm.nearhi = (uint32_t *)(ws + L.off_nearhi);
-    bm.e_alive = (uint32_t *)(ws + L.off_ealive); bm.e_evt = (uint32_t *)(ws + L.off_eevt);
-    bm.e_ord = (uint32_t *)(ws + L.off_eord);
-    bm.res = (uint16_t *)(ws + L.off_res); bm.jobs = (uint16_t *)(ws + L.off_jobs);
-    bm.tlive = (uint8_t *)(ws + L.off_tlive);
-    bm.bf0 = bm.bf1 = nullptr; bm.bpack = nullptr; bm.tshot = nullptr; bm.los_q = bm.los_r = nullptr;
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    const int64_t e_warp0 = ((int64_t)blockIdx.x * PK_WARPS + warp) * WE;
-    if (e_warp0 < st.N) pass_lane<DevWarp, SPEC, WE>(c, st, bm, e_warp0, lane, first != 0, rewards, done);
-    signal_host(sig, tid);
-}
-
-// The controllers between the two passes (ctrl_lane): one thread per env, the smart bots' line-of-sight queries pooled.
-template <int SPEC>
-__global__ void __launch_bounds__(BS, 7) ctrl_kernel(const __grid_constant__ KCfg c, const DevState st,
-                                                  const int32_t *__restrict__ actions) {
-    extern __shared__ __align__(16) unsigned char smem[];
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    const SmemLayout L = smem_layout(c.n_tanks, c.n_bots, c.act_rows, false);
-    BlockMem bm;
-    bind_block_mem(bm, smem, L);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t e_warp0 = (int64_t)blockIdx.x * BS + warp * 32;
-    const int64_t e = e_warp0 + lane;
-    const bool valid = e < st.N;
-    const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
-    const int32_t *my_actions = nullptr;
-    if (actions && valid) {   // action rows: inputs of the step, not written by a predecessor kernel
-        const int row_ints = c.act_rows * 3;
-        int32_t *stage = (int32_t *)(smem + L.off_acts) + (size_t)tid * row_ints;
-        for (int q = 0; q < row_ints; ++q)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(stage + q)),
-                         "l"(actions + e * row_ints + q)
-                         : "memory");
-        my_actions = stage;
-    }
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    ctrl_lane<DevWarp, SPEC>(c, st, bm, e_warp0, tid, valid, valid_mask, my_actions);
-}
-
-// What is left for the envs whose episode ended (fin_lane): terminal info latched, reset in place.
-constexpr int FIN_THREADS = 256;
-__global__ void __launch_bounds__(FIN_THREADS) fin_kernel(const __grid_constant__ KCfg c, const DevState st, const uint8_t *__restrict__ done) {
-    asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
-    asm volatile("griddepcontrol.wait;\n" ::: "memory");
-    const int64_t e = (int64_t)blockIdx.x * FIN_THREADS + threadIdx.x;
-    if (e < st.N) fin_lane(c, st, e, done);
 }
 
 // The trainers' per-tick observation normaliser on ONE column of an env's [rows][dim] block (train_multi_ppo.py:89-91
@@ -616,6 +527,25 @@ __global__ void info_kernel(const __grid_constant__ KCfg c, const DevState st, i
         if (change_time) change_time[e * c.n_tanks + i] = st.change_time[g];
     }
     if (winner) winner[e] = lt ? (int)st.term_winner[e] - 1 : w;
+}
+
+__global__ void prev_rew_kernel(const DevState st, int row, int tank) {   // at_set_reward_mode: start of the increments
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < st.N) st.prev_rew[(int64_t)row * st.N + e] = (float)st.trew[(int64_t)tank * st.N + e];
+}
+// per-tank columns for env.game_env.tanks[i].<attr> readers: out[c][e], c = alive, x, y, angle, reward, num_hit, num_be_hit
+__global__ void tank_columns_kernel(const DevState st, int tank, double *__restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= st.N) return;
+    const int64_t g = (int64_t)tank * st.N + e;
+    const uint32_t pk = st.tpack[g], th = st.thits[g];
+    out[e] = (pk & TP_ALIVE) ? 1.0 : 0.0;
+    out[st.N + e] = st.tx[g];
+    out[2 * st.N + e] = st.ty[g];
+    out[3 * st.N + e] = (double)(pk & 511u);
+    out[4 * st.N + e] = st.trew[g];
+    out[5 * st.N + e] = (double)(th & 0xFFFFu);
+    out[6 * st.N + e] = (double)(th >> 16);
 }
 
 __global__ void synthetic_actions_kernel(uint64_t seed, int64_t env_id_base, int64_t n_envs, int rows, uint32_t tick,
@@ -1115,10 +1045,6 @@ struct at_env {
     const float *d_tmpl;
     double *d_dyn;            // st.dyn: parameters that may change between steps (at_set_weakness)
     size_t smem_bytes_sim;    // env_kernel
-    size_t smem_bytes_ctrl;   // ctrl_kernel
-    bool split_step;          // the step runs as bullets / ctrl / bullets / fin kernels (AT_MONOLITH=1: one env_kernel)
-    int pass_we;              // bullets_kernel: envs per warp (32, 16 or 8; AT_PASS_WE)
-    size_t smem_bytes_pass;
     int sim_spec;             // SimT<SPEC> specialisation of the step's simulation kernel (0: generic; AT_NO_SPEC=1 forces it)
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
     int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
@@ -1152,42 +1078,8 @@ static cudaError_t launch_pdl(void (*fn)(Args...), int grid, int block, size_t s
     return cudaLaunchKernelEx(&cfg, fn, args...);
 }
 
-template <int WE, int SPEC>
-static cudaError_t launch_pass(at_env *env, int first, cudaStream_t s, bool pdl, float *rw, uint8_t *dn, HostSignal sig) {
-    const int per_block = PK_WARPS * WE;
-    const int grid = (int)((env->n_envs + per_block - 1) / per_block);
-    return launch_pdl(bullets_kernel<WE, SPEC>, grid, PK_WARPS * 32, env->smem_bytes_pass, s, pdl, env->k, env->st, first, rw, dn, sig);
-}
-static cudaError_t launch_pass_any(at_env *env, int first, cudaStream_t s, bool pdl, float *rw, uint8_t *dn, HostSignal sig) {
-    const bool s3 = env->sim_spec == 3;
-    switch (env->pass_we) {
-    case 8: return s3 ? launch_pass<8, 3>(env, first, s, pdl, rw, dn, sig) : launch_pass<8, 0>(env, first, s, pdl, rw, dn, sig);
-    case 16: return s3 ? launch_pass<16, 3>(env, first, s, pdl, rw, dn, sig) : launch_pass<16, 0>(env, first, s, pdl, rw, dn, sig);
-    default: return s3 ? launch_pass<32, 3>(env, first, s, pdl, rw, dn, sig) : launch_pass<32, 0>(env, first, s, pdl, rw, dn, sig);
-    }
-}
-// bullets (first pass) -> controllers -> bullets -> results; every kernel but the first a programmatic dependent
-static int launch_split_step(at_env *env, int grid, const int32_t *d_actions, float *d_rewards, uint8_t *d_done,
-                             HostSignal sig, cudaStream_t s) {
-    const bool pdl = env->pdl;
-    const HostSignal none = {nullptr, nullptr, 0u, nullptr};
-    CUDA_TRY(launch_pass_any(env, 1, s, false, nullptr, nullptr, none));
-    switch (env->sim_spec) {
-    case 3: CUDA_TRY(launch_pdl(ctrl_kernel<3>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
-    case 2: CUDA_TRY(launch_pdl(ctrl_kernel<2>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
-    case 1: CUDA_TRY(launch_pdl(ctrl_kernel<1>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
-    default: CUDA_TRY(launch_pdl(ctrl_kernel<0>, grid, BS, env->smem_bytes_ctrl, s, pdl, env->k, env->st, d_actions)); break;
-    }
-    CUDA_TRY(launch_pass_any(env, 0, s, pdl, d_rewards, d_done, sig));
-    if (env->k.auto_reset)
-        CUDA_TRY(launch_pdl(fin_kernel, (int)((env->n_envs + FIN_THREADS - 1) / FIN_THREADS), FIN_THREADS, (size_t)0, s, pdl, env->k,
-                            env->st, (const uint8_t *)d_done));
-    else
-        env->launches -= 1;
-    env->launches += 3;   // (+1 by the caller)
-    return AT_OK;
-}
-
+static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, cudaStream_t s, float *d_obs_norm, float norm_eps,
+                              bool pdl);
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
                              float norm_eps = 0.f, bool post_to_host = false) {
@@ -1195,10 +1087,7 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     HostSignal sig = {nullptr, nullptr, 0u, env->dbg_times};
     if (post_to_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
     const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
-    if (is_step && env->split_step) {
-        int rc = launch_split_step(env, grid, d_actions, d_rewards, d_done, sig, s);
-        if (rc != AT_OK) return rc;
-    } else if (is_step && env->sim_spec == 3)
+    if (is_step && env->sim_spec == 3)
         env_kernel<true, 3><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     else if (is_step && env->sim_spec == 2)
         env_kernel<true, 2><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
@@ -1211,6 +1100,12 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     if (!rows) return AT_OK;
+    return launch_rows_kernel(env, d_mask, d_obs, s, d_obs_norm, norm_eps, env->pdl);
+}
+
+// rows_kernel: the observation rows (raw and / or tick-normalised) of the stored state
+static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, cudaStream_t s, float *d_obs_norm, float norm_eps,
+                              bool pdl) {
     const int G = 1 << env->rows_lgG;
     const int n_groups = (int)((env->n_envs + G - 1) / G);
     cudaLaunchConfig_t cfg;
@@ -1225,7 +1120,7 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = env->pdl ? 1 : 0;
+    cfg.numAttrs = pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups,
                                 (float *)d_obs_norm, norm_eps));
     env->launches += 1;
@@ -1315,6 +1210,11 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         if (cudaEventCreateWithFlags(&env->ev_actions, cudaEventDisableTiming) != cudaSuccess) env->ev_actions = nullptr;
         cudaGetLastError();
     }
+    {
+        std::vector<double> at((size_t)361 * ATAB_STRIDE);
+        fill_atan_table(at.data());
+        cudaMemcpy(b + L.o_atab, at.data(), at.size() * 8, cudaMemcpyHostToDevice);
+    }
     env->d_dyn = (double *)(b + L.o_dyn);
     cudaMemcpy(env->d_dyn, &k.weakness, 8, cudaMemcpyHostToDevice);
     env->d_tmpl = (const float *)(b + L.o_tmpl);
@@ -1324,7 +1224,6 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         cudaMemcpy(b + L.o_tmpl, tm.data(), tm.size() * 4, cudaMemcpyHostToDevice);
     }
     env->smem_bytes_sim = smem_layout(k.n_tanks, k.n_bots, k.act_rows).total;
-    env->smem_bytes_ctrl = smem_layout(k.n_tanks, k.n_bots, k.act_rows, false).total;
     {   // The dynamic shared-memory limit is a process-wide attribute of each kernel instantiation: never set it to this
         // handle's own need (a second handle with a smaller image would lower it under the first one) - raise every
         // kernel to the device's opt-in maximum once and leave it there.
@@ -1334,16 +1233,6 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         cudaFuncSetAttribute(env_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(env_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(ctrl_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(ctrl_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(ctrl_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(ctrl_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(bullets_kernel<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(bullets_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(bullets_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(bullets_kernel<8, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(bullets_kernel<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-        cudaFuncSetAttribute(bullets_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         if (env->smem_bytes_sim > (size_t)lim) {
             cudaFree(env->arena);
             delete env;
@@ -1357,16 +1246,6 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         {   // AT_NO_SPEC=1: generic kernel; 2 / 3: stop below that specialisation level
             const char *ns = getenv("AT_NO_SPEC");
             env->sim_spec = sim_spec_for(k, ns && ns[0] >= '1' && ns[0] <= '3' ? ns[0] - '1' : 3);
-        }
-        {   // the split step: fixed maps, every mode but the arena (whose bots decide before the first pass)
-            const char *mo = getenv("AT_MONOLITH"), *we = getenv("AT_PASS_WE");
-            env->split_step = !(mo && mo[0] == '1') && k.map != AT_MAP_MAZE && k.mode != AT_MODE_ARENA;
-            // envs per warp of the bullet kernel: fewer envs per warp = more warps in flight; small batches get the
-            // smallest share so that the pass still spreads over the SMs
-            int w = n_envs >= 32768 ? 16 : 8;
-            if (we && (atoi(we) == 8 || atoi(we) == 16 || atoi(we) == 32)) w = atoi(we);
-            env->pass_we = w;
-            env->smem_bytes_pass = pass_smem_layout(k.n_tanks, w).total;
         }
         const int RD = k.rows * k.obs_dim;
         const char *ww = getenv("AT_ROWS_WARPS");
@@ -1564,6 +1443,48 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
         CUDA_TRY(cudaMemcpyAsync(h_rewards, env->d_rewards_scratch, (size_t)N * env->k.rows * 4, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaMemcpyAsync(h_done, env->d_done_scratch, (size_t)N, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return AT_OK;
+}
+
+int at_observe(at_env *env, float *d_obs, void *stream) {
+    if (!env || !d_obs) return fail(AT_ERR_ARG, "at_observe: null handle or buffer");
+    if (env->k.rows == 0) return AT_OK;
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
+    return launch_rows_kernel(env, nullptr, d_obs, (cudaStream_t)stream, nullptr, 0.f, false);
+}
+
+int at_set_reward_mode(at_env *env, int mode) {
+    if (!env || (mode != AT_REWARD_CUMULATIVE && mode != AT_REWARD_DELTA))
+        return fail(AT_ERR_ARG, "at_set_reward_mode: null handle or unknown mode");
+    if (mode == AT_REWARD_DELTA && !env->k.reward_delta) {   // the increments start from the values as they are now
+        DeviceGuard guard(env->device);
+        CUDA_TRY(guard.status());
+        const int n = env->k.n_tanks;
+        for (int r = 0; r < env->k.rows; ++r) {   // prev_rew[r] = (float)trew[tank of row r]: one small kernel per row
+            const int t = env->k.team_layout ? env->k.agent_tank[r] : r;
+            (void)n;
+            prev_rew_kernel<<<(int)((env->n_envs + 255) / 256), 256>>>(env->st, r, t);
+        }
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    env->k.reward_delta = mode == AT_REWARD_DELTA;
+    return AT_OK;
+}
+
+int at_forget_host_buffers(at_env *env) {
+    if (!env) return fail(AT_ERR_ARG, "at_forget_host_buffers: null handle");
+    env->mapped.clear();
+    return AT_OK;
+}
+
+int at_get_tank_columns(at_env *env, int tank, double *d_out, void *stream) {
+    if (!env || !d_out || tank < 0 || tank >= env->k.n_tanks) return fail(AT_ERR_ARG, "at_get_tank_columns: bad argument");
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
+    tank_columns_kernel<<<(int)((env->n_envs + 255) / 256), 256, 0, (cudaStream_t)stream>>>(env->st, tank, d_out);
+    env->launches += 1;
+    CUDA_TRY(cudaGetLastError());
     return AT_OK;
 }
 

@@ -1,8 +1,5 @@
-// at_sim.h - simulation of one alphaTank tick.  Every env has a home lane (one thread per env) that owns its scalar
-// bookkeeping; the heavy, order-free parts of a tick are POOLED over the warp: the live bullets of the warp's 32 envs
-// (and the smart bots' line-of-sight queries) form job lists that all 32 lanes work through together, whatever the
-// per-env counts are (bullets_pass_pooled, pool_los), and only what the reference's sequential semantics really order
-// - the f64 reward additions, kills, list compaction - is committed per env in firing order.
+// at_sim.h - simulation of one alphaTank tick, one thread (lane) per env; the smart bots' line-of-sight queries of a
+// warp's 32 envs are pooled into a job queue that all lanes work through together (pool_los).
 // Written as __host__ __device__ code against a warp policy (at_warp.h): the CUDA kernels in at_kernels.cu run it
 // on the warp intrinsics; tests/cpu_emul compiles the same header with g++ and runs it on a 32-fiber SIMT emulator
 // to check the formulation against the oracle in a GPU-less container (test infrastructure only - the product has
@@ -144,10 +141,96 @@ AT_HD double fast_rsqrt(double s) {
 #endif
 }
 
+// ---- correctly rounded atan2 near integer-degree bearings (the slow path of Sim::angle_diff_to).
+// A bearing feeds integer-degree thresholds.  Bearings that are integers up to rounding are NOT measure-zero here:
+// two tanks spawn in the same cell and one drives off along its (integer) heading, so the other sees it at exactly
+// heading + 180 and |bearing - own angle| sits on a threshold up to the last bits of atan2.  The device atan2 is
+// only good to 2 ulp, so such decisions are re-taken on the correctly rounded value: from theta0 = the device's
+// atan2, one Newton step delta = (y cos theta0 - x sin theta0) / (x cos theta0 + y sin theta0), with sin / cos of
+// theta0 = phi_K + d built by angle addition from a host table of 106-bit sin / cos of the K-degree angles phi_K
+// (d < 1e-10, so first / second order terms in plain doubles suffice), and theta0 + delta rounded once.
+// (Python's math.atan2 is glibc's: correctly rounded for 99.6 % of such inputs, measured against mpmath in
+// tests/test_kernel_logic_cpu.py; the remaining inputs are where a libm-dependent reference has no single right
+// answer - DESIGN.md "Transcendentals".)
+struct DD {
+    double hi, lo;
+};
+AT_HD DD dd_two_sum(double a, double b) {
+    const double s = a + b, bb = s - a;
+    return {s, (a - (s - bb)) + (b - bb)};
+}
+AT_HD DD dd_fast_two_sum(double a, double b) {  // |a| >= |b|
+    const double s = a + b;
+    return {s, b - (s - a)};
+}
+AT_HD DD dd_add(DD a, DD b) {
+    DD s = dd_two_sum(a.hi, b.hi);
+    const DD t = dd_two_sum(a.lo, b.lo);
+    s.lo += t.hi;
+    s = dd_fast_two_sum(s.hi, s.lo);
+    s.lo += t.lo;
+    return dd_fast_two_sum(s.hi, s.lo);
+}
+AT_HD DD dd_neg(DD a) { return {-a.hi, -a.lo}; }
+AT_HD DD dd_mul(DD a, DD b) {
+    const double p = a.hi * b.hi;
+    double e = fma_rn(a.hi, b.hi, -p);
+    e = fma_rn(a.hi, b.lo, e);
+    e = fma_rn(a.lo, b.hi, e);
+    return dd_fast_two_sum(p, e);
+}
+AT_HD DD dd_mul_d(DD a, double b) {
+    const double p = a.hi * b;
+    double e = fma_rn(a.hi, b, -p);
+    e = fma_rn(a.lo, b, e);
+    return dd_fast_two_sum(p, e);
+}
+AT_HD DD dd_div_d(DD a, double d) {  // d: a small exact integer
+    const double q1 = a.hi / d;
+    const double p = q1 * d;
+    const double r = ((a.hi - p) - fma_rn(q1, d, -p)) + a.lo;   // a - q1 d
+    return dd_fast_two_sum(q1, r / d);
+}
+// host side: 106-bit sin / cos of a double by Taylor sums (|t| <= pi; the table of the K-degree angles below)
+inline void dd_sincos_host(double t, DD &sn, DD &cs) {
+    const DD x = {t, 0.0};
+    const DD x2 = dd_mul(x, x);
+    DD ts = x, tc = {1.0, 0.0};
+    sn = ts; cs = tc;
+    for (int k = 1; k <= 34; ++k) {
+        tc = dd_neg(dd_div_d(dd_mul(tc, x2), (double)((2 * k - 1) * (2 * k))));
+        ts = dd_neg(dd_div_d(dd_mul(ts, x2), (double)((2 * k) * (2 * k + 1))));
+        cs = dd_add(cs, tc);
+        sn = dd_add(sn, ts);
+    }
+}
+constexpr int ATAB_STRIDE = 5;      // per K = -180 .. 180: phi_K, sin hi / lo, cos hi / lo
+inline void fill_atan_table(double *tab) {
+    for (int K = -180; K <= 180; ++K) {
+        const double phi = (double)K * (3.141592653589793 / 180.0);
+        DD sn, cs;
+        dd_sincos_host(phi, sn, cs);
+        double *r = tab + (K + 180) * ATAB_STRIDE;
+        r[0] = phi; r[1] = sn.hi; r[2] = sn.lo; r[3] = cs.hi; r[4] = cs.lo;
+    }
+}
+// th0 = an atan2(y, x) good to a few ulp whose value in degrees is within 1e-9 of the integer K: the correctly
+// rounded atan2(y, x)
+AT_HD double atan2_refine(double y, double x, double th0, int K, const double *tab) {
+    const double *r = tab + (K + 180) * ATAB_STRIDE;
+    const double d = th0 - ldg(r);                       // exact: both within 1e-10 of each other
+    const DD S = {ldg(r + 1), ldg(r + 2)}, Cc = {ldg(r + 3), ldg(r + 4)};
+    const double h = 0.5 * d * d;
+    const DD sn = dd_add(S, dd_two_sum(Cc.hi * d, fma_rn(Cc.hi, d, -(Cc.hi * d)) + Cc.lo * d - S.hi * h));   // S + C d - S d^2 / 2
+    const DD cs = dd_add(Cc, dd_two_sum(-(S.hi * d), -fma_rn(S.hi, d, -(S.hi * d)) - S.lo * d - Cc.hi * h)); // C - S d - C d^2 / 2
+    const DD num = dd_add(dd_mul_d(cs, y), dd_neg(dd_mul_d(sn, x)));   // y cos - x sin  (= |v| sin(theta - th0))
+    const double den = x * cs.hi + y * sn.hi;                            // x cos + y sin  (= |v| cos(theta - th0))
+    return dd_two_sum(th0, num.hi / den).hi;
+}
+
 // atan2 with the lattice cases pinned to the correctly rounded doubles glibc returns (axis-aligned and
-// diagonal bearings are NOT measure-zero here: tanks spawn on cell centres).  Elsewhere the device atan2
-// (<= 2 ulp) feeds integer-degree thresholds, where a last-bit difference cannot change the decision
-// unless the bearing is within ~1e-13 deg of an integer (DESIGN.md "Transcendentals").
+// diagonal bearings: tanks spawn on cell centres).  Elsewhere the device atan2 (<= 2 ulp); Sim::angle_diff_to
+// re-takes the decisions that could depend on those last bits with atan2_cr.
 AT_HD double at_atan2(double y, double x) {
     double ax = fabs(x), ay = fabs(y);
     if (ay == 0.0) {
@@ -349,10 +432,9 @@ AT_HD int select_bit(M128 m, int k) {
 // config; 2 = 1 + exactly four tanks; 3 = 2 + the 2a_vs_2b tank layout).  SPEC 1 = team mode, every scripted tank a smart bot, fixed map, no TERMINATE_TIME - the 2v2 / NvM
 // team_vs_bot workloads: the other bots, the 1v1 modes, the maze generator and the arena ordering drop out of the
 // kernel (the generic build is 630 KB of SASS and stalls on instruction fetch).
-// CS = stride of the working-set columns (envs per block, or per warp in the bullet kernel); WE = envs per warp: the
-// lanes 0 .. WE-1 of a warp are home lanes, the others only serve pooled jobs.
-template <int SPEC, int CS = BS, int WE = 32>
+template <int SPEC>
 struct SimT {
+    static constexpr int CS = BS;   // stride of the block's working-set columns
     AT_HD int cfg_mode() const { return SPEC >= 1 ? 3 : c.mode; }
     AT_HD int cfg_bot_type(int i) const { return SPEC >= 1 ? 0 : c.bot_type[i]; }
     AT_HD bool cfg_maze() const { return SPEC >= 1 ? false : c.map == 2; }
@@ -381,12 +463,10 @@ struct SimT {
     uint64_t wlo, whi, nlo, nhi;
     uint32_t alive_bits;   // bit i: tank i alive (mirror of TPACK)
     uint32_t warp_mask;    // lanes of this warp that own an env (the pooled stages of the controllers run on these)
-    int ew0;               // SoA index of the env of this warp's lane 0 (pooled jobs address other lanes' envs)
-    bool valid;            // this lane owns an env (lanes past the end of the batch still serve pooled jobs)
 
     AT_HD SimT(const KCfg &c_, const DevState &st_, const BlockMem &bm_, int64_t e_, int tid_)
         : c(c_), st(st_), bm(bm_), e((int)e_), n32((int)st_.N), tid(tid_), cnt(0), rng(0), tick(0), tstep(0), epstep(0), zones(0), wlo(0),
-          whi(0), nlo(0), nhi(0), alive_bits(0), warp_mask(0xffffffffu), ew0((int)e_ - (tid_ & 31)), valid(true) {}
+          whi(0), nlo(0), nhi(0), alive_bits(0), warp_mask(0xffffffffu) {}
 
     AT_HD double &TX(int i) const { return bm.tx[i * CS + tid]; }
     AT_HD double &TY(int i) const { return bm.ty[i * CS + tid]; }
@@ -427,14 +507,12 @@ struct SimT {
     }
     // bullet_dir / np.linalg.norm(bullet_dir) of the firing direction (cos a, -sin a): one ulp offset per component
     AT_HD void unit_dir(int a, double &u0, double &u1) const {
-        const uint32_t dl = ldg(st.udelta + a);
-        u0 = bits_d(d_bits(cosr(a)) + (uint64_t)(int64_t)((int)(dl & 3u) - 1));
-        u1 = bits_d(d_bits(-sinr(a)) + (uint64_t)(int64_t)((int)((dl >> 2) & 3u) - 1));
+        const uint32_t dl = bm.udelta[a];
+        u0 = bits_d(d_bits(bm.trig[2 * a]) + (uint64_t)(int64_t)((int)(dl & 3u) - 1));
+        u1 = bits_d(d_bits(-bm.trig[2 * a + 1]) + (uint64_t)(int64_t)((int)((dl >> 2) & 3u) - 1));
     }
-    // The 6 KB of direction tables are read through L1 (one copy per SM) rather than staged per block in shared
-    // memory (seven copies per SM that would come out of the same 256 KB and shrink the L1 the other tables live in).
-    AT_HD double cosr(int a) const { return ldg(st.trig + 2 * a); }
-    AT_HD double sinr(int a) const { return ldg(st.trig + 2 * a + 1); }
+    AT_HD double cosr(int a) const { return bm.trig[2 * a]; }
+    AT_HD double sinr(int a) const { return bm.trig[2 * a + 1]; }
 
     // the kernel stages this env's action rows with asynchronous copies at launch (each thread copies and reads only
     // its own rows); they must have landed before the first read
@@ -517,7 +595,7 @@ struct SimT {
     // One Bullet.move() (sprite.py:59-105) of a bullet of the env in block slot q, as a PURE function of the record,
     // the env's tank columns and the alive mask: everything the move decides, nothing committed.  The commits - f64
     // reward additions, the kill, the compaction - are applied by the caller in firing order (bullet_move for one env
-    // at a time, bullets_pass_pooled for the warp's bullets at once).
+    // at a time).
     struct BOut {
         double nx, ny;
         uint64_t m;        // the record after the move (flips, bounces, distance, cleared, pending count)
@@ -696,140 +774,9 @@ struct SimT {
         }
         cnt = w;
     }
-    AT_HD void bullets_pass() {   // one env per lane, nothing pooled (per-env mazes; the reference form of the pass)
+    AT_HD void bullets_pass() {
         for (int i = 0; i < cfg_n(); ++i) { TLIVE(i) = 0; near_clear(i); }
         bullets_serial(0, 0);
-    }
-
-    // The pass over the warp's bullets at once.  The live records of the 32 envs form one job list (by list position,
-    // then env); the lanes take 32 jobs per round, evaluate them (bullet_eval on the pass-start alive masks) and commit
-    // what does not depend on the order: the moved record in place, the dodge candidates, the per-owner count of
-    // toward-rewards.  What the order does matter for is left to the env's home lane afterwards:
-    //   * an owner that lost a bullet in this pass (expired or hit) gets its reward additions replayed bullet by bullet
-    //     (r + 0.01 - penalty + 0.01 is not r - penalty + 0.02 in f64); every other owner's additions are k equal
-    //     constants, whose order is immaterial;
-    //   * removed bullets are squeezed out of the list (records behind them move down, ranks / candidate bits follow);
-    //   * a HIT changes the alive mask, so every bullet behind the first hit of an env is not committed by the pool at
-    //     all and is re-run by the home lane with the sequential bullets_serial() - hits are rare (~0.5 % of env-passes).
-    // Fixed maps only (the job lanes test walls with their own registers' map).
-    template <class WP>
-    AT_HD void bullets_pass_pooled() {
-        if (cfg_maze()) {
-            if (valid) bullets_pass();
-            return;
-        }
-        constexpr uint32_t FULL = 0xffffffffu;
-        const int lane = tid & 31, wbase = tid & ~31, n = cfg_n();
-        const bool home = WE == 32 || lane < WE;
-        const uint32_t my_cnt = (valid && home) ? cnt : 0u;
-        if (home) {
-            bm.e_alive[tid] = alive_bits;
-            bm.e_evt[tid] = 0xFFu;
-            bm.e_ord[tid] = 0u;
-            bm.e_k[tid] = 0ull;
-            for (int i = 0; i < n; ++i) near_clear(i);
-        }
-        // job list, position-major (all first bullets, then all second ones, ...): the lanes of a round then read
-        // neighbouring envs of one [slot][env] column - the same few sectors - and bullets of one env (whose commits
-        // meet at the env's counters) are spread over different rounds
-        uint16_t *jobs = bm.jobs + (size_t)(tid >> 5) * (WE * SLOTS_PER_TANK * c.n_tanks);
-        uint32_t total = 0;
-        for (uint32_t k = 0;; ++k) {
-            const uint32_t have = WP::ballot(FULL, my_cnt > k);
-            if (have == 0u) break;
-            if (my_cnt > k) jobs[total + popc32(have & ((1u << lane) - 1u))] = (uint16_t)(lane | (k << 5));
-            total += popc32(have);
-        }
-        WP::sync(FULL);
-        // the records of the next round are requested before this round is evaluated
-        uint32_t jq_n = 0;
-        int g_n = 0;
-        double x_n = 0.0, y_n = 0.0;
-        uint64_t m_n = 0;
-        if ((uint32_t)lane < total) {
-            jq_n = jobs[lane];
-            g_n = (int)(jq_n >> 5) * n32 + ew0 + (int)(jq_n & 31u);
-            x_n = st.bx[g_n]; y_n = st.by[g_n]; m_n = st.bmeta[g_n];
-        }
-        for (uint32_t base = 0; base < total; base += 32) {
-            const bool act = base + lane < total;
-            const uint32_t jq = jq_n;
-            const int g = g_n;
-            const double x = x_n, y = y_n;
-            const uint64_t m = m_n;
-            if (base + 32 + lane < total) {
-                jq_n = jobs[base + 32 + lane];
-                g_n = (int)(jq_n >> 5) * n32 + ew0 + (int)(jq_n & 31u);
-                x_n = st.bx[g_n]; y_n = st.by[g_n]; m_n = st.bmeta[g_n];
-            }
-            const int q = wbase + (int)(jq & 31u);
-            const uint32_t slot = jq >> 5;
-            BOut o;
-            o.victim = -1; o.expired = false; o.n_hi = 0; o.near = 0; o.nx = 0.0; o.ny = 0.0; o.m = 0;
-            if (act) {
-                bullet_eval(q, x, y, m, bm.e_alive[q], o);
-                if (o.victim >= 0) WP::atomic_min(&bm.e_evt[q], slot);
-            }
-            WP::sync(FULL);
-            if (act && slot <= bm.e_evt[q]) {   // not behind a hit: the evaluation stands
-                const int owner = (int)(m & 15u);
-                const bool removed = o.victim >= 0 || o.expired;
-                st.bx[g] = o.nx; st.by[g] = o.ny; st.bmeta[g] = o.m | (m & (7ull << BM_RANK));
-                bm.res[slot * CS + q] = (uint16_t)((uint32_t)o.n_hi | (o.expired ? 8u : 0u) | (o.victim >= 0 ? 16u : 0u) |
-                                                   ((uint32_t)(o.victim & 7) << 5) | ((uint32_t)owner << 8));
-                if (o.n_hi) WP::atomic_add64(&bm.e_k[q], (unsigned long long)o.n_hi << (8 * owner));
-                if (removed) {
-                    WP::atomic_or(&bm.e_ord[q], 1u << owner);
-                } else if (SPEC == 3) {   // two enemies, 24 slots
-                    const int e0 = (owner & 2) ^ 2;
-                    if ((o.near >> e0) & 1u) WP::atomic_or(&bm.nearlo[e0 * CS + q], 1u << slot);
-                    if ((o.near >> (e0 + 1)) & 1u) WP::atomic_or(&bm.nearlo[(e0 + 1) * CS + q], 1u << slot);
-                } else {
-                    for (uint32_t nb = o.near; nb; nb &= nb - 1) {
-                        const int i = ffs32(nb);
-                        if (slot < 32) WP::atomic_or(&bm.nearlo[i * CS + q], 1u << slot);
-                        else WP::atomic_or(&bm.nearhi[i * CS + q], 1u << (slot - 32));
-                    }
-                }
-            }
-        }
-        WP::sync(FULL);
-        if (!valid) return;
-        // ---- the env's home lane: what the order matters for
-        const uint32_t evt = bm.e_evt[tid], ord = bm.e_ord[tid];
-        {
-            const unsigned long long K = bm.e_k[tid];
-            for (int i = 0; i < n; ++i) {
-                if ((ord >> i) & 1u) continue;
-                // k equal additions: one exact fma when they stay inside a binade, else the literal loop (jump_axis)
-                const int k = (int)((uint32_t)(K >> (8 * i)) & 255u);
-                if (k) TREW(i) = jump_axis(TREW(i), 0.01, k);
-            }
-        }
-        if (ord == 0u) return;   // nothing left the list: positions, ranks and the live counts stand
-        uint64_t old_near[MAX_TANKS];
-        for (int i = 0; i < n; ++i) { old_near[i] = near_get(i); near_clear(i); TLIVE(i) = 0; }
-        const uint32_t nproc = evt == 0xFFu ? cnt : evt + 1u;
-        uint32_t w = 0;
-        for (uint32_t r = 0; r < nproc; ++r) {
-            const uint32_t rr = bm.res[r * CS + tid];
-            const int owner = (int)((rr >> 8) & 7u);
-            if ((ord >> owner) & 1u)
-                for (uint32_t k = rr & 7u; k > 0; --k) TREW(owner) += 0.01;
-            if (rr & 16u) { commit_hit(owner, (int)((rr >> 5) & 7u)); continue; }
-            if (rr & 8u) { commit_expiry(st.bmeta[G(r)]); continue; }
-            const uint32_t rank = TLIVE(owner)++;
-            if (w != r) {   // a removed bullet precedes: the record moves down and its rank may have changed
-                const uint64_t m = st.bmeta[G(r)];
-                st.bx[G(w)] = st.bx[G(r)];
-                st.by[G(w)] = st.by[G(r)];
-                st.bmeta[G(w)] = (m & ~(7ull << BM_RANK)) | ((uint64_t)rank << BM_RANK);
-            }
-            for (int i = 0; i < n; ++i)
-                if ((old_near[i] >> r) & 1ull) near_set(i, (int)w);
-            ++w;
-        }
-        bullets_serial(nproc, w);   // the bullets behind a hit (nothing when there was none)
     }
 
     // ---------------------------------------------------------------- tanks (env/sprite.py:326-357, 528-657)
@@ -1017,7 +964,17 @@ struct SimT {
     }
     AT_HD double angle_diff_to(int me, double tx, double ty) const {
         double dx = tx - TX(me), dy = ty - TY(me);
-        double ta = py_fmod360(py_degrees(at_atan2(-dy, dx)));
+        double th = at_atan2(-dy, dx);
+#if defined(__CUDA_ARCH__) && !defined(AT_NO_ATAN2_CR)
+        // every caller compares the difference with integer thresholds (and the tank's angle is an integer): when the
+        // bearing is within 1e-9 degrees of an integer the last bits of atan2 decide, and the decision is taken on the
+        // correctly rounded value (atan2_refine; pinned lattice cases are exact already)
+        {
+            const double t = py_degrees(th), k = rint(t);
+            if (fabs(t - k) < 1e-9 && dx != 0.0 && dy != 0.0 && fabs(dx) != fabs(dy)) th = atan2_refine(-dy, dx, th, (int)k, st.atab);
+        }
+#endif
+        double ta = py_fmod360(py_degrees(th));
         int cur = t_angle(me) % 360;
         return py_fmod360(ta - cur + 180) - 180;
     }
@@ -1534,6 +1491,8 @@ struct SimT {
             zones |= (uint32_t)select_bit(freec, j) << (14 * z + 7);
         }
         epstep = 0;
+        if (c.reward_delta)
+            for (int r = 0; r < cfg_rows(); ++r) st.prev_rew[r * n32 + e] = 0.0f;
         st.prev_act[e] = 0u;
         for (int k = 0; k < cfg_n(); ++k) st.change_time[G(k)] = 0;
     }
@@ -1580,28 +1539,25 @@ struct SimT {
             apply_action(i, acts[i][0], acts[i][1], acts[i][2], swapped ? 0 : 2, swapped ? 2 : 0, swapped ? 1 : 0);
         }
     }
-    // Called by every lane of the warp (lanes without an env serve the pooled bullet jobs and skip the rest).
     template <class WP>
     AT_HD void game_step(const int32_t *a /* [act_rows][3] of this env, or null */) {
         int acts[MAX_TANKS][3];
         tick += 1;
         if (cfg_mode() != AT_MODE_TEAM_) epstep += 1;
         uint32_t pre_done = 0, los_bits = 0;
-        if (SPEC >= 1) {   // pass, controllers, pass - rolled, so that the pooled pass exists once in the instruction stream
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass) {
-                bullets_pass_pooled<WP>();
-                if (pass == 0 && valid) controllers<WP>(2, a, acts, pre_done, los_bits);
-            }
+        if (SPEC >= 1) {   // straight-line: pass, controllers, pass (measured: the rolled stage loop costs 10 %)
+            bullets_pass();
+            controllers<WP>(2, a, acts, pre_done, los_bits);
+            bullets_pass();
             return;
         }
         const bool arena = cfg_mode() == AT_MODE_ARENA_;
         for (int stage = arena ? 0 : 1; stage < 4; ++stage) {
             if (stage & 1) {
-                bullets_pass_pooled<WP>();
+                bullets_pass();
                 continue;
             }
-            if (valid) controllers<WP>(stage, a, acts, pre_done, los_bits);
+            controllers<WP>(stage, a, acts, pre_done, los_bits);
         }
     }
 
@@ -1622,7 +1578,7 @@ struct SimT {
     // the part of the wrapper step in front of the engine's tick
     AT_HD void wrapper_pre(const int32_t *a) {
         tstep += 1;
-        if (valid && !cfg_team_layout() && a) {  // change_time, gym_env.py:77-85
+        if (!cfg_team_layout() && a) {  // change_time, gym_env.py:77-85
             acts_ready();
             uint32_t pv = st.prev_act[e];
             uint32_t nv = 1u;
@@ -1662,13 +1618,18 @@ struct SimT {
     AT_HD bool wrapper_step(const int32_t *a, float *rewards_row) {
         wrapper_pre(a);
         game_step<WP>(a);
-        if (!valid) return false;
         return wrapper_post(rewards_row);
     }
-    // the step's results of this lane's env: rewards / done out; returns done
-    AT_HD bool post_results(float *rewards, uint8_t *done) {
+    // the step's results of this lane's env: rewards / done out, terminal info latched, auto-reset
+    AT_HD void finish_step(float *rewards, uint8_t *done) {
         float rw[MAX_TANKS];
         const bool d = wrapper_post(rw);
+        if (c.reward_delta)   // AT_REWARD_DELTA: the increment since the value the previous step returned
+            for (int r = 0; r < cfg_rows(); ++r) {
+                const float cum = rw[r];
+                rw[r] = cum - st.prev_rew[r * n32 + e];
+                st.prev_rew[r * n32 + e] = (d && c.auto_reset) ? 0.0f : cum;
+            }
         if (cfg_rows() == 2) {
 #ifdef __CUDA_ARCH__
             *reinterpret_cast<float2 *>(rewards + (int64_t)e * 2) = make_float2(rw[0], rw[1]);  // one 8-byte store
@@ -1679,18 +1640,13 @@ struct SimT {
             for (int r = 0; r < cfg_rows(); ++r) rewards[(int64_t)e * c.rows + r] = rw[r];
         }
         done[e] = d ? 1 : 0;
-        return d;
-    }
-    // ... and terminal info latched, auto-reset
-    AT_HD void finish_step(float *rewards, uint8_t *done) {
-        if (post_results(rewards, done) && c.auto_reset) { latch_terminal_info(); env_reset(); }
+        if (d && c.auto_reset) { latch_terminal_info(); env_reset(); }
     }
 
     // ---------------------------------------------------------------- HBM <-> working set
     AT_HD void load() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
         zones = st.zones[e];
-        const uint32_t live = st.tlive[e];
         if (cfg_maze()) { wlo = st.wall_lo[e]; whi = st.wall_hi[e]; set_near(); }
         else { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
         // Four tanks at a time through registers: every load of a batch is issued before the first shared-memory
@@ -1716,77 +1672,12 @@ struct SimT {
                 const int i = i0 + k;
                 if (i < n) {
                     TX(i) = x[k]; TY(i) = y[k]; TREW(i) = rw[k]; TPACK(i) = tp[k]; TSHOT(i) = ts[k];
-                    TLIVE(i) = (uint8_t)((live >> (4 * i)) & 15u);
                     if (cfg_ctrl(i) == 1) { BPACK(i) = bp[k]; BF0(i) = f0[k]; BF1(i) = f1[k]; }
                     if (tp[k] & TP_ALIVE) alive_bits |= 1u << i;
                 }
             }
         }
     }
-    // the bullet kernel's view of the env: list length, tank positions / alive flags / rewards
-    AT_HD void load_pass(bool first) {
-        cnt = st.cnt[e];
-        const uint32_t live = st.tlive[e];
-        if (!first) tstep = st.tstep[e];
-        // (the engine bumps episode_steps before the first pass; the controllers' kernel stores the increment)
-        epstep = st.epstep[e] + ((first && cfg_mode() != AT_MODE_TEAM_) ? 1u : 0u);
-        const int n = cfg_n();
-        for (int i0 = 0; i0 < n; i0 += 4) {   // (batched through registers: see load())
-            double x[4], y[4], rw[4];
-            uint32_t tp[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = i0 + k;
-                x[k] = y[k] = rw[k] = 0.0; tp[k] = 0u;
-                if (i < n) { x[k] = st.tx[G(i)]; y[k] = st.ty[G(i)]; rw[k] = st.trew[G(i)]; tp[k] = st.tpack[G(i)]; }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = i0 + k;
-                if (i < n) {
-                    TX(i) = x[k]; TY(i) = y[k]; TREW(i) = rw[k]; TPACK(i) = tp[k];
-                    TLIVE(i) = (uint8_t)((live >> (4 * i)) & 15u);
-                    if (tp[k] & TP_ALIVE) alive_bits |= 1u << i;
-                }
-            }
-        }
-    }
-    AT_HD void store_pass(bool first) {
-        st.cnt[e] = cnt;
-        if (!first) st.tstep[e] = tstep;
-        uint32_t live = 0;
-        for (int i = 0; i < cfg_n(); ++i) {
-            st.trew[G(i)] = TREW(i); st.tpack[G(i)] = TPACK(i);
-            live |= (uint32_t)TLIVE(i) << (4 * i);
-            if (first) {
-                st.nearlo[G(i)] = bm.nearlo[i * CS + tid];
-                if (cfg_n() * SLOTS_PER_TANK > 32) st.nearhi[G(i)] = bm.nearhi[i * CS + tid];
-            }
-        }
-        st.tlive[e] = live;
-    }
-    // what the first bullet pass leaves for the controllers: the dodge_reward candidates
-    AT_HD void load_handover() {
-        const int n = cfg_n();
-        const bool wide = n * SLOTS_PER_TANK > 32;
-        for (int i0 = 0; i0 < n; i0 += 4) {   // (batched through registers: see load())
-            uint32_t lo[4], hi[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                lo[k] = hi[k] = 0u;
-                if (i0 + k < n) { lo[k] = st.nearlo[G(i0 + k)]; if (wide) hi[k] = st.nearhi[G(i0 + k)]; }
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = i0 + k;
-                if (i < n) {
-                    bm.nearlo[i * CS + tid] = lo[k];
-                    if (wide) bm.nearhi[i * CS + tid] = hi[k];
-                }
-            }
-        }
-    }
-    AT_HD void load_fixed_map() { wlo = c.wall_lo; whi = c.wall_hi; nlo = c.near_lo; nhi = c.near_hi; }
     AT_HD void set_near() { M128 nm = near_wall_mask(wlo, whi); nlo = nm.lo; nhi = nm.hi; }
     AT_HD void load_scalars_only() {
         cnt = st.cnt[e]; rng = st.rng_ctr[e]; tick = st.tick[e]; tstep = st.tstep[e]; epstep = st.epstep[e];
@@ -1798,93 +1689,29 @@ struct SimT {
         st.cnt[e] = cnt; st.rng_ctr[e] = rng; st.tick[e] = tick; st.tstep[e] = tstep; st.epstep[e] = epstep;
         st.zones[e] = zones;
         if (cfg_maze()) { st.wall_lo[e] = wlo; st.wall_hi[e] = whi; }
-        uint32_t live = 0;
         for (int i = 0; i < cfg_n(); ++i) {
             st.tx[G(i)] = TX(i); st.ty[G(i)] = TY(i); st.trew[G(i)] = TREW(i);
             st.tpack[G(i)] = TPACK(i); st.tshot[G(i)] = TSHOT(i);
-            live |= (uint32_t)TLIVE(i) << (4 * i);
             if (cfg_ctrl(i) == 1) { st.bpack[G(i)] = BPACK(i); st.bf0[G(i)] = BF0(i); st.bf1[G(i)] = BF1(i); }
         }
-        st.tlive[e] = live;
     }
 };
 typedef SimT<0> Sim;   // the generic build (emulator, reset kernel, every config without a specialisation)
 
-// One lane's part of a step of the warp's 32 envs: the body of env_kernel<true, SPEC> (and of the emulator's fibers).
-// e_warp0 = SoA index of the env of lane 0; lanes with valid == false own no env (ragged tail of the batch).
+// One lane's part of a step: the body of env_kernel<true, SPEC> (and of the emulator's fibers).  e_warp0 = SoA index of
+// the env of lane 0; valid_mask = lanes of the warp that own an env (the pooled line-of-sight stage runs on these).
 template <class WP, int SPEC>
-AT_HD void step_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int tid, bool valid,
-                     uint32_t valid_mask, const int32_t *my_actions, float *rewards, uint8_t *done) {
-    const int64_t e = e_warp0 + (tid & 31);
-    SimT<SPEC> s(c, st, bm, e, tid);
-    s.valid = valid;
-    s.warp_mask = valid_mask;
-    if (valid) s.load();
-    else s.load_fixed_map();   // a lane without an env still serves pooled jobs, which test walls with the lane's own map
-    s.wrapper_pre(my_actions);
-    s.template game_step<WP>(my_actions);
-    if (!valid) return;
-    s.finish_step(rewards, done);
-    s.store();
-}
-
-// ---- the same step as three kernels (fixed maps, every mode but the arena): the bullet pass on its own (pass_lane,
-// twice per tick; the second one also posts rewards / done), the controllers between the passes (ctrl_lane), the
-// reset of the envs whose episode ended (fin_lane).  The pass owns no
-// per-env registers worth mentioning, so its kernel gives every warp only WE < 32 envs - the pooled jobs keep all 32
-// lanes busy anyway - and the GPU holds 32 / WE times as many warps to hide the fp64 latencies behind.
-// What one kernel hands to the next travels through the SoA state; on top of the monolithic kernel's columns: the
-// per-owner live counts and the dodge candidates of the first pass (DevState::tlive / nearlo / nearhi).
-template <class WP, int SPEC, int WE>
-AT_HD void pass_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int lane, bool first,
-                     float *rewards, uint8_t *done) {
-    const int64_t e = e_warp0 + lane;
-    SimT<SPEC, WE, WE> s(c, st, bm, e < st.N ? e : e_warp0, lane);
-    s.ew0 = (int)e_warp0;
-    s.valid = lane < WE && e < st.N;
-    s.load_fixed_map();
-    if (s.valid) s.load_pass(first);
-    s.template bullets_pass_pooled<WP>();
-    if (!s.valid) return;
-    if (!first) s.post_results(rewards, done);   // the tick is over: rewards / done (a done env is reset by fin_lane)
-    s.store_pass(first);
-}
-template <class WP, int SPEC>
-AT_HD void ctrl_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int tid, bool valid,
-                     uint32_t valid_mask, const int32_t *my_actions) {
-    if (!valid) return;   // (the pooled line-of-sight stage runs on the lanes of valid_mask)
+AT_HD void step_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e_warp0, int tid, uint32_t valid_mask,
+                     const int32_t *my_actions, float *rewards, uint8_t *done) {
     SimT<SPEC> s(c, st, bm, e_warp0 + (tid & 31), tid);
     s.warp_mask = valid_mask;
     s.load();
-    s.load_handover();
     s.wrapper_pre(my_actions);
-    s.tick += 1;
-    if (s.cfg_mode() != SimT<SPEC>::AT_MODE_TEAM_) s.epstep += 1;
-    int acts[MAX_TANKS][3];
-    uint32_t pre_done = 0, los_bits = 0;
-    s.template controllers<WP>(2, my_actions, acts, pre_done, los_bits);
+    s.template game_step<WP>(my_actions);
+    s.finish_step(rewards, done);
     s.store();
 }
-// what is left of the step for an env whose episode ended: terminal info latched, reset in place.  Rare (~0.5 % of
-// env-steps), so the env's working set is a private one (columns of stride 1 on the lane's stack), not shared memory.
-AT_HD void fin_lane(const KCfg &c, const DevState &st, int64_t e, const uint8_t *done) {
-    if (!done[e] || !c.auto_reset) return;
-    double tx[MAX_TANKS], ty[MAX_TANKS], trew[MAX_TANKS], bf0[MAX_TANKS], bf1[MAX_TANKS];
-    uint32_t tpack[MAX_TANKS], bpack[MAX_TANKS], nearlo[MAX_TANKS], nearhi[MAX_TANKS];
-    int32_t tshot[MAX_TANKS];
-    uint8_t tlive[MAX_TANKS];
-    BlockMem bm;
-    memset(&bm, 0, sizeof bm);
-    bm.tx = tx; bm.ty = ty; bm.trew = trew; bm.bf0 = bf0; bm.bf1 = bf1; bm.tpack = tpack; bm.bpack = bpack;
-    bm.nearlo = nearlo; bm.nearhi = nearhi; bm.tshot = tshot; bm.tlive = tlive;
-    SimT<0, 1, 32> s(c, st, bm, e, 0);
-    s.ew0 = (int)e;
-    s.load();
-    s.latch_terminal_info();
-    s.env_reset();
-    s.store();
-}
-// One lane's part of a (masked) reset: the generic build, nothing pooled.
+// One lane's part of a (masked) reset: the generic build.
 AT_HD void reset_lane(const KCfg &c, const DevState &st, const BlockMem &bm, int64_t e, int tid) {
     Sim s(c, st, bm, e, tid);
     s.load();

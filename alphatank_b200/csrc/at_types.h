@@ -44,6 +44,7 @@ struct KCfg {
     // observation row layout (floats)
     int32_t self_len, off_ob, off_eb, eb_stride, off_et, et_len, off_walls, off_maze, off_zones, off_flags;
     int32_t row_bulk_ok;  // D*4 % 16 == 0: rows can leave shared memory as one bulk-async copy
+    int32_t reward_delta; // at_set_reward_mode: rewards out = increment since the previous step (st.prev_rew)
     double weakness;
     uint64_t seed;
     int64_t env_id_base;
@@ -71,29 +72,23 @@ struct DevState {
     const double *pend;            // [PEND_LUT] k-fold accumulation of BULLET_AWAY_PENALTY
     const uint8_t *udelta;         // [361] ulp offsets of the numpy-normalised bullet direction from (cos a, -sin a)
     const uint16_t *bfs_tab;       // [121*121] all-pairs bfs_first_step of a FIXED map: len | dir << 8 (null for mazes)
-    uint32_t *tlive;               // [N] live bullets per owner, 4 bits each (kept by shoot / the bullet passes)
-    // hand-over between the kernels of a split step (pass_lane -> ctrl_lane, at_sim.h)
-    uint32_t *nearlo, *nearhi;     // [n][N] dodge_reward candidates of the first bullet pass (bullet slots; hi: slots >= 32)
+    float *prev_rew;               // [rows][N] rewards returned by the previous step (AT_REWARD_DELTA only)
+    const double *atab;            // [361][5] K-degree angles with 106-bit sin / cos (at_sim.h atan2_refine)
     const double *dyn;             // [1] parameters a caller may change between steps (at_set_weakness): read from memory,
                                    //     so a captured CUDA graph sees the new value.  dyn[0] = bot weakness
 };
 
 // per-block working set of the tanks / bots (shared memory on the GPU)
 struct BlockMem {
+    double *trig;                  // [722] copy of st.trig
     double *tx, *ty, *trew;        // [n][BS]
     double *bf0, *bf1;             // [n][BS]
     uint32_t *tpack, *bpack;       // [n][BS]
     uint8_t *tlive;                // [n][BS] live bullets per owner (<= 6)
     uint32_t *nearlo, *nearhi;     // [n][BS] bullet slots that may be within 100 px of the tank when it acts (hi: slots >= 32)
     int32_t *tshot;                // [n][BS]
+    const uint8_t *udelta;         // [361] copy of st.udelta
     uint8_t *los_q, *los_r;        // [warps][256] pooled line-of-sight job queue / answers
-    // pooled bullet pass (Sim::bullets_pass_pooled): per env [BS] ...
-    uint32_t *e_alive;             // alive mask at the start of the pass
-    uint32_t *e_evt;               // list position of the first bullet that hit a tank in this pass (0xFF: none)
-    uint32_t *e_ord;               // owners that lost a bullet in this pass (their reward additions are replayed in order)
-    unsigned long long *e_k;       // toward-reward additions per owner, 8 bits each
-    uint16_t *res;                 // [6n][BS] per bullet: n_hi[0:3) expired 3 hit 4 victim[5:8) owner[8:11)
-    uint16_t *jobs;                // [warps][32 * 48] job list of the warp: env lane | list position << 5
 };
 
 }  // namespace at

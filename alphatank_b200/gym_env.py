@@ -44,9 +44,6 @@ class MultiAgentEnv:
         if mode not in _1V1_MODES:
             raise ValueError("mode %r is not supported by the batched env (keyboard modes 'bot', 'human_play' and "
                              "'human' need a display); valid: %s" % (mode, sorted(_1V1_MODES)))
-        if type != "train" and mode == "bot_agent":
-            raise ValueError("bot_agent with type != 'train' reads actions[0] (gaming_env.py:176-177); pass "
-                             "type='train' and put the agent's action in row 1")
         self.mode, self.type, self.bot_type, self.weakness = mode, type, bot_type, float(weakness)
         self._kw = dict(num_envs=num_envs, device=device, seed=seed, env_id_base=env_id_base, auto_reset=auto_reset,
                         map=map, terminate_time=terminate_time, buff_on=buff_on, debuff_on=debuff_on,
@@ -75,6 +72,10 @@ class MultiAgentEnv:
         if old is not None:
             old.close()
         self.core = BatchedTankEnv(cfg, kw["num_envs"], kw["device"], kw["seed"], kw["env_id_base"])
+        if self.reward_mode == "delta":
+            self.core.set_reward_mode("delta")          # per-step increments, computed by the step kernel
+        # gaming_env.py:176-177: outside training ('inference') the bot_agent branch reads the agent's action from row 0
+        self._agent_row0 = kind == "bot_agent" and self.type != "train"
         self.num_envs = self.core.num_envs
         self.num_tanks = 2
         self.num_agents = 2 if kind == "agent" else (1 if kind == "bot_agent" else 0)
@@ -103,15 +104,25 @@ class MultiAgentEnv:
         info = {"Tank:%d-%s" % (i, t): 0 for i, t in enumerate(("TeamA", "TeamB"))}   # gym_env.py:70
         return obs.view(self.num_envs, self.num_tanks, self.core.D), info
 
+    def _agent_rows(self, actions):
+        """bot_agent with type != 'train' (inference.py): callers pass the agent's action as row 0 - [N, 1, 3] or
+        [N, 2, 3] with row 1 unused.  The engine's agent tank is tank 1, so the row is handed to it as row 1; row 0
+        keeps the caller's values, whose repeats change_time[0] counts (gym_env.py:77-85)."""
+        import torch
+        a = torch.as_tensor(actions).reshape(self.num_envs, -1, 3)
+        return torch.stack((a[:, 0], a[:, 0]), dim=1).contiguous()
+
     def step(self, actions=None):
         self.training_step += 1
+        if self._agent_row0:
+            actions = self._agent_rows(actions)
         obs, rewards, done = self.core.step(actions)
-        if self.reward_mode == "delta":
-            rewards = self.core.delta_rewards(rewards, done)
         return obs, rewards, done, False, LazyInfo(self.core, ("change_time", "winner"))
 
     def step_host(self, h_actions=None):
         self.training_step += 1
+        if self._agent_row0:
+            h_actions = self._agent_rows(h_actions).to("cpu", dtype=__import__("torch").int32)
         return self.core.step_host(h_actions)
 
     def render(self, mode="human"):

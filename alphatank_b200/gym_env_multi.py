@@ -49,6 +49,8 @@ class MultiAgentTeamEnv:
                                 debuff_on=config_basic.DEBUFF_ON if debuff_on is None else debuff_on,
                                 auto_reset=auto_reset)
         self.core = BatchedTankEnv(cfg, num_envs, device, seed, env_id_base)
+        if self.reward_mode == "delta":
+            self.core.set_reward_mode("delta")          # per-step increments, computed by the step kernel
         self.training_step = 0
         self.num_envs = self.core.num_envs
         self.num_tanks = len(teams)
@@ -72,8 +74,6 @@ class MultiAgentTeamEnv:
     def step(self, actions=None):
         self.training_step += 1
         obs, rewards, done = self.core.step(actions)
-        if self.reward_mode == "delta":
-            rewards = self.core.delta_rewards(rewards, done)
         return obs, rewards, done, False, LazyInfo(self.core, ("hits", "be_hits"))
 
     def step_host(self, h_actions=None):

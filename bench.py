@@ -3,12 +3,14 @@
 
 Workload (BASELINE.json configs[2]): 2v2 ``team_vs_bot_configs`` (Tank1,2 agents vs Tank3,4 on-device smart
 bots), octagon map, 65536 envs per GPU, synthetic uniform random actions (ATRNG stream), auto-reset.
-One "step" = one tick of every env = ONE fused kernel launch per GPU.  Envs shard across GPUs by env id with
-no data-path collective (weak scaling: per-GPU work fixed).
+One "step" = one tick of every env = the simulation kernel + the rows kernel per GPU.  Envs shard across GPUs by
+env id with no data-path collective (weak scaling: per-GPU work fixed).  The line also carries the other BASELINE
+configurations (`configs`), the per-kernel rooflines, the end-to-end figure through host buffers and - under
+torchrun - config 5 on every GPU and the PPO gradient all-reduce (`ppo_allreduce`).
 
     python bench.py --gpus 1 --steps 200 --warmup 10
     python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 --steps 200 --warmup 10
-    python bench.py --impl reference --steps 20 --warmup 3      # CPU arm: oracle port on all host threads
+    python bench.py --impl reference --steps 20 --warmup 3      # CPU arm: the reference's own env on all host cores
 
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the definition of every key.
 """
@@ -38,6 +40,7 @@ def parse():
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--ref-envs", type=int, default=8192, help="envs per step of the CPU reference arm (bounded sample)")
     p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-configs", action="store_true", help="skip the sub-records of the other BASELINE configurations")
     p.add_argument("--burn-in", type=int, default=600,
                    help="untimed ticks before the warm-up steps: episodes (mean ~190 ticks) desynchronise, so the timed "
                         "steps see the steady-state mix of episode phases instead of 65536 freshly reset battles")
@@ -125,25 +128,36 @@ class ClockSampler:
                 "samples": len(s)}
 
 
-def kernel_split(E, D, step_ms, sim_ms, peak):
+def kernel_split(E, D, step_ms, sim_ms, rows_ms, peak):
     """Per-kernel view of the step.  SURVEY 8d's 7039 B/env-step = 2 S_state + 3 A + 4 R + 1 (simulation kernel: state
-    in and out, actions, rewards, done) + 4 R D (rows kernel: the observation rows)."""
+    in and out, actions, rewards, done) + 4 R D (rows kernel: the observation rows).  Both kernels are timed directly
+    (CUDA events around back-to-back launches of that kernel alone); they overlap slightly inside a step (programmatic
+    dependent launch), so sim + rows may exceed the step."""
     sim_b = (ALG_BYTES_PER_ENV_STEP - 4 * N_AGENTS * D) * E
     rows_b = 4 * N_AGENTS * D * E
-    rows_ms = max(step_ms - sim_ms, 1e-6)
     return {
-        "env_kernel<true,false>": {"ms": sim_ms, "alg_bytes": sim_b, "achieved_gbs": sim_b / sim_ms / 1e6,
-                                   "frac": sim_b / sim_ms / 1e6 / peak, "share_of_step": sim_ms / step_ms,
-                                   "note": "timed alone (at_step without an observation buffer); latency-bound "
-                                           "fp64 / integer simulation, see DESIGN.md"},
+        "env_kernel": {"ms": sim_ms, "alg_bytes": sim_b, "achieved_gbs": sim_b / sim_ms / 1e6,
+                       "frac": sim_b / sim_ms / 1e6 / peak, "share_of_step": sim_ms / (sim_ms + rows_ms),
+                       "note": "at_step without an observation buffer launches only the simulation kernel; "
+                               "latency-bound fp64 / integer work, see DESIGN.md"},
         "rows_kernel": {"ms": rows_ms, "alg_bytes": rows_b, "achieved_gbs": rows_b / rows_ms / 1e6,
-                        "frac": rows_b / rows_ms / 1e6 / peak, "share_of_step": rows_ms / step_ms,
-                        "note": "step minus simulation (the two overlap slightly: programmatic dependent launch)"},
+                        "frac": rows_b / rows_ms / 1e6 / peak, "share_of_step": rows_ms / (sim_ms + rows_ms),
+                        "note": "at_observe launches only rows_kernel (timed directly, state resident)"},
     }
 
 
-def cpu_arm(n_envs, steps, warmup, seed, threads, burn_in=0):
-    """Times the oracle port (oracle/tank_oracle.c) on host threads: the reference's algorithm on the CPU."""
+def workload_config(E, world, burn_in, D=528):
+    """The `config` object of the JSON line - the same for both arms (the reference arm runs a bounded sample of it)."""
+    return {"workload": WORKLOAD, "envs_per_gpu": E, "total_envs": E * world, "agents_per_env": N_AGENTS,
+            "burn_in_ticks": burn_in, "tanks_per_env": 4, "obs_dim": D,
+            "parallelism": "env-id sharding x%d, no step-path collective" % world,
+            "timing": "per-step footprint (SoA state ~%d MB + %d MB of observations written) exceeds the 126 MB L2; "
+                      "no flush between steps needed" % (804 * E // 2**20, D * 4 * N_AGENTS * E // 2**20)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms
+def cpu_port(n_envs, steps, warmup, seed, threads, burn_in=0):
+    """Times the oracle port (oracle/tank_oracle.c) on host threads: the reference's algorithm restated in C."""
     import numpy as np
     from oracle import oracle as O
     from oracle.atrng import synthetic_actions
@@ -164,28 +178,141 @@ def cpu_arm(n_envs, steps, warmup, seed, threads, burn_in=0):
     return n_envs * N_AGENTS * steps / dt, dt
 
 
+REF_TICKS_PER_STEP = 25     # reference arm: one "step" = every pool worker advances its env by this many ticks
+
+
+def cpu_reference(pool_ticks, pool_warmup, single_ticks, single_warmup, procs):
+    """The UNMODIFIED reference env (oracle/_ref, see oracle/ref_runner.py) on this box's host cores, BASELINE.md
+    section 3: one process / one env, and a pool of `procs` independent envs.  Returns a cpu_baseline dict in
+    agent-steps/s, or None when oracle/_ref was not built (the reference only exists in the build container)."""
+    from oracle import ref_runner as R
+    if not R.available():
+        return None
+    single = R.time_single(3, ticks=single_ticks, warmup=single_warmup, repeats=1) if single_ticks else None
+    pool, wall = R.time_pool(3, procs, ticks=pool_ticks, warmup=pool_warmup)
+    return {"value": pool * N_AGENTS, "unit": UNIT, "cores": procs, "kind": "reference",
+            "single_core": single * N_AGENTS if single else None, "pool": pool * N_AGENTS,
+            "pygame": R.pygame_kind(), "aiming_reward": "enabled (reference default)",
+            "sample": "the reference's own env/ + configs/ (oracle/_ref, headless, virtual clock, GIF decoding skipped): "
+                      "MultiAgentTeamEnv(team_vs_bot_configs), uniform random agent actions, reset on done; "
+                      "%d processes x 1 env x %d ticks after %d warm-up ticks (%.1f s)%s" % (
+                          procs, pool_ticks, pool_warmup, wall,
+                          "; single core: 1 env x %d ticks after %d" % (single_ticks, single_warmup) if single_ticks else "")}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps = args.steps if args.steps is not None else 20
     warmup = args.warmup if args.warmup is not None else 3
-    threads = os.cpu_count() or 1
-    value, dt = cpu_arm(args.ref_envs, steps, warmup, args.seed, threads, burn_in=args.burn_in)
-    sample = "%d envs x %d ticks per run after %d untimed burn-in ticks (oracle C port of the reference env step, pthreads over envs)" % (
-        args.ref_envs, steps, args.burn_in)
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
-        "warmup": warmup, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_step": args.ref_envs, "agents_per_env": N_AGENTS,
-                   "note": "the reference itself is single-env interpreted Python needing pygame (not installable on "
-                           "the box); this arm times its C restatement (oracle/) on all host threads"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    procs = os.cpu_count() or 1
+    cb = cpu_reference(steps * REF_TICKS_PER_STEP, warmup * REF_TICKS_PER_STEP, 300, 60, procs)
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    line = {"impl": "reference", "metric": METRIC, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.envs_per_gpu, max(world, 1), args.burn_in), "gpu_launches": 0}
+    if cb is None:       # no oracle/_ref on this box: the C restatement of the reference's algorithm stands in
+        value, dt = cpu_port(args.ref_envs, steps, warmup, args.seed, procs, burn_in=args.burn_in)
+        cb = {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+              "sample": "%d envs x %d ticks per run after %d untimed burn-in ticks (oracle C port of the reference env "
+                        "step, pthreads over envs); oracle/_ref is not present on this box" % (args.ref_envs, steps, args.burn_in)}
+        line["ms_per_step"] = 1e3 * dt / steps
+    else:
+        # one step = REF_TICKS_PER_STEP ticks of each of the pool's `procs` envs
+        line["ms_per_step"] = 1e3 * procs * REF_TICKS_PER_STEP * N_AGENTS / cb["value"]
+        v, dt = cpu_port(2048, 8, 2, args.seed, procs)
+        cb["port"] = {"value": v, "unit": UNIT, "cores": procs,
+                      "sample": "oracle C port (oracle/tank_oracle.c), 2048 envs x 8 ticks, pthreads over envs, %.1f s" % dt}
+    line["value"] = cb["value"]
+    line["cpu_baseline"] = cb
+    line["e2e"] = {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def timed_loop(torch, dist, dev, world, fn, n):
+    """n calls of fn between barriers, timed with CUDA events on the launching stream; max over ranks (ms)."""
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    stream = torch.cuda.current_stream(dev)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(n):
+        fn(i)
+    ev1.record(stream)
+    barrier()
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms.item())
+
+
+def sub_config(torch, dist, dev, world, peak, name, make, agents, alg_bytes, note, steps=100, burn=300):
+    """One of the other BASELINE.json configurations: ms per tick, agent-steps/s and roofline fraction (device-timed,
+    inputs resident, the same protocol as the headline: burn-in, then `steps` back-to-back ticks)."""
+    env = make()
+    core = env.core
+    env.reset()
+    acts = None
+    if core.A:
+        acts = torch.empty((32, core.num_envs, core.A, 3), dtype=torch.int32, device=dev)
+        for t in range(32):
+            core.synthetic_actions(t, acts[t])
+    for t in range(burn):
+        core.step(acts[t % 32] if acts is not None else None)
+    ms = timed_loop(torch, dist, dev, world, lambda i: core.step(acts[i % 32] if acts is not None else None), steps) / steps
+    n = core.num_envs
+    rec = {"workload": name, "envs_per_gpu": n, "ms_per_tick": ms, "env_steps_per_sec": n * world / ms * 1e3,
+           "agent_steps_per_sec": n * world * agents / ms * 1e3, "agents_per_env": agents,
+           "alg_bytes_per_env_step": alg_bytes, "achieved_gbs": alg_bytes * n / ms / 1e6,
+           "frac": alg_bytes * n / ms / 1e6 / peak, "obs": "%d x %d" % (core.R, core.D), "note": note}
+    env.close()
+    del env
+    torch.cuda.empty_cache()
+    return rec
+
+
+def ppo_allreduce_record(torch, dist, dev, world, rank, seed, E):
+    """The one collective of the workload (train_multi_ppo.py:133-182 data parallel): the all-reduce of a policy's
+    flattened gradient, once per optimiser step.  Timed alone (NCCL, CUDA events, max over ranks) on a tensor of the
+    gradient's size, and as a share of a real PPO update on config 5's per-GPU batch (short rollout, one epoch)."""
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
+    torch.backends.cuda.matmul.allow_tf32 = True
+    T, epochs, mbs = 8, 1, 8
+    env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=E, device=dev, seed=seed, env_id_base=rank * E)
+    A = len(env.get_observation_order())
+    D = env.observation_space.shape[0] // A
+    cfg = PPOConfig(num_steps=T, num_epochs=epochs, num_minibatches=mbs)
+    learner = PPOLearner(A, D, (3, 3, 2), cfg, dev, seed=seed)
+    buf = RolloutBuffer(T, E, A, D, dev, keep_raw=False)
+    runner = RolloutRunner(env, learner, buf, use_graph=False)
+    runner.run(first=True)
+    ms_roll = timed_loop(torch, dist, dev, world, lambda i: runner.run(first=False), 2) / 2
+    learner.update(buf)                                    # warm-up (allocator, NCCL channels)
+    ms_upd = timed_loop(torch, dist, dev, world, lambda i: learner.update(buf), 1)
+    n_par = sum(p.numel() for p in learner.agents[0].parameters())
+    flat = torch.zeros(n_par, dtype=torch.float32, device=dev)
+    for _ in range(5):
+        dist.all_reduce(flat)
+    reps = 50
+    ms_ar = timed_loop(torch, dist, dev, world, lambda i: dist.all_reduce(flat), reps) / reps
+    n_ar = A * epochs * mbs
+    rec = {"collective": "NCCL all-reduce(sum) of one policy's flattened fp32 gradient, once per optimiser step",
+           "bytes_per_allreduce": 4 * n_par, "params_per_policy": n_par, "policies": A,
+           "us_per_allreduce": ms_ar * 1e3, "algbw_gbs": 4 * n_par / ms_ar / 1e6,
+           "allreduces_per_update": n_ar, "update_ms": ms_upd, "share_of_update": n_ar * ms_ar / ms_upd,
+           "update": "%d envs/GPU x %d ticks x %d agents, %d epoch, %d minibatches" % (E, T, A, epochs, mbs),
+           "rollout_agent_steps_per_sec": E * world * T * A / ms_roll * 1e3,
+           "rollout_note": "policies in the loop (tick-normalised rows, sampling on device), issued kernel by kernel"}
+    env.close()
+    return rec
 
 
 def run_ours(args):
@@ -202,7 +329,7 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__ as ge
     ge.build_cuda()
-    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200 import MultiAgentEnv, MultiAgentTeamEnv
     from alphatank_b200.configs.config_teams import team_vs_bot_configs
 
     E = args.envs_per_gpu
@@ -216,25 +343,8 @@ def run_ours(args):
     for t in range(ring):
         core.synthetic_actions(t, acts[t])
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
     def timed(fn, n):
-        stream = torch.cuda.current_stream(dev)
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record(stream)
-        for i in range(n):
-            fn(i)
-        ev1.record(stream)
-        barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item())
+        return timed_loop(torch, dist, dev, world, fn, n)
 
     for t in range(args.burn_in):              # state preparation (like generating the synthetic inputs): not a step
         core.step(acts[t % ring])
@@ -246,8 +356,8 @@ def run_ours(args):
     launches = core.launch_count() - l0
     total_envs = E * world
 
-    # per-kernel split of the step: the simulation kernel alone (at_step without an observation buffer launches only
-    # env_kernel<true, false>); the rest of the step is rows_kernel
+    # per-kernel split of the step, each kernel timed directly: the simulation kernel alone (at_step without an
+    # observation buffer launches only env_kernel) and the rows kernel alone (at_observe launches only rows_kernel)
     import ctypes as C
     from alphatank_b200 import _capi
     sim_steps = max(min(steps, 100), 10)
@@ -258,6 +368,7 @@ def run_ours(args):
                                    C.c_void_p(core.done.data_ptr()),
                                    C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "at_step")
     ms_sim = timed(sim_only, sim_steps) / sim_steps
+    ms_rows = timed(lambda i: core.observe(), sim_steps) / sim_steps
     value = total_envs * N_AGENTS * steps / (ms * 1e-3)
 
     # end to end through the reference-facing API with HOST action / reward / done buffers
@@ -267,32 +378,60 @@ def run_ours(args):
         env.step_host(h_acts[t % len(h_acts)])
     ms_e2e = timed(lambda i: env.step_host(h_acts[i % len(h_acts)]), e2e_steps)
     e2e_value = total_envs * N_AGENTS * e2e_steps / (ms_e2e * 1e-3)
+    D = core.D
+    env.close()
+    del env, core
+    torch.cuda.empty_cache()
+
+    peak, peak_src = measured_peak()
+    # ---- the other BASELINE.json configurations (parity-test cases; reported beside the headline, not as `value`)
+    subs = {}
+    mk5 = lambda: MultiAgentTeamEnv(team_vs_bot_configs, num_envs=131072, device=dev, seed=args.seed, env_id_base=rank * 131072)  # noqa: E731
+    if not args.no_configs:
+        if world == 1:
+            subs["c1_1v1_agents_random_actions"] = sub_config(
+                torch, dist, dev, world, peak, "config 1 batched: MultiAgentEnv() 1v1, both tanks random actions, 65536 envs",
+                lambda: MultiAgentEnv(mode="agent", num_envs=65536, device=dev, seed=args.seed), 2, 4511, "A = 2")
+            subs["c2_1v1_vs_smart_bot_4096"] = sub_config(
+                torch, dist, dev, world, peak, "config 2: MultiAgentEnv(mode='bot_agent', bot_type='smart'), 4096 envs "
+                "(train_ppo_bot.py --bot-type smart), random agent actions",
+                lambda: MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=4096, device=dev, seed=args.seed), 1, 4556,
+                "A = 1; 64 blocks on 148 SMs: bounded by the latency of one tick, not by throughput")
+            subs["c4_arena_defensive_vs_dodge_262144"] = sub_config(
+                torch, dist, dev, world, peak, "config 4: bot arena defensive vs dodge, TERMINATE_TIME 4096 (immortal tanks, "
+                "bullets saturate), 262144 envs, bot-driven",
+                lambda: MultiAgentEnv(mode="bot_vs_bot", bot_types=("defensive", "dodge"), num_envs=262144, device=dev,
+                                      terminate_time=4096, seed=args.seed), 2, 4601,
+                "no policy-controlled tank: agent-steps counts the 2 scripted tanks; S_state = 744 B")
+        subs["c5_2v2_131072_per_gpu"] = sub_config(
+            torch, dist, dev, world, peak, "config 5: 2v2 team_vs_bot at 131072 envs per GPU (1M envs on 8 GPUs)", mk5, 2,
+            ALG_BYTES_PER_ENV_STEP, "value is the whole job over %d GPU(s)" % world)
+    ppo = None
+    if world > 1 and not args.no_configs:
+        ppo = ppo_allreduce_record(torch, dist, dev, world, rank, args.seed, 131072)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peak, peak_src = measured_peak()
     alg_bytes = ALG_BYTES_PER_ENV_STEP * E
     kernel_s = ms * 1e-3 / steps
     achieved = alg_bytes / kernel_s / 1e9
     traffic = ncu_traffic()
+    cfg = workload_config(E, world, args.burn_in, D)
+    cfg["env_steps_per_sec"] = value / N_AGENTS
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "envs_per_gpu": E, "total_envs": total_envs, "agents_per_env": N_AGENTS,
-                   "burn_in_ticks": args.burn_in, "tanks_per_env": 4, "obs_dim": core.D, "parallelism": "env-id sharding x%d, no step-path collective"
-                   % world, "timing": "per-step footprint (SoA state ~%d MB + %d MB of observations written) exceeds the "
-                   "126 MB L2; no flush between steps needed" % (804 * E // 2**20, core.D * 4 * N_AGENTS * E // 2**20),
-                   "env_steps_per_sec": value / N_AGENTS},
+        "data": "synthetic", "config": cfg,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic["dram_bytes_per_launch"] if traffic else None,
-                     "kernel": "one step = env_kernel<true,false> (simulation) + rows_kernel (observation rows)",
+                     "traffic_source": {k: traffic.get(k) for k in ("captured_at_commit", "capture", "kernels")} if traffic else None,
+                     "kernel": "one step = env_kernel (simulation) + rows_kernel (observation rows)",
                      "alg_bytes_per_launch": alg_bytes,
                      "alg_bytes_per_env_step": ALG_BYTES_PER_ENV_STEP, "peak_source": peak_src,
                      "kernel_ms": kernel_s * 1e3,
-                     "kernels": kernel_split(E, core.D, kernel_s * 1e3, ms_sim, peak)},
+                     "kernels": kernel_split(E, D, kernel_s * 1e3, ms_sim, ms_rows, peak)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N_AGENTS * 3 * 4,
                 "d2h_bytes_per_step": E * N_AGENTS * 4 + E, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                 "note": "MultiAgentTeamEnv.step_host: pinned host actions in (DMA copy beside the previous step's rows "
@@ -300,17 +439,25 @@ def run_ours(args):
                         "call returns when they have landed); observations stay in HBM for the policy"},
         "gpu_launches": launches * world,
         "clocks": clk.summary(),
+        "configs": subs,
     }
+    if ppo is not None:
+        line["ppo_allreduce"] = ppo
     if world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        n_ref, t_ref = 4096, 8
-        v, dt = cpu_arm(n_ref, t_ref, 2, args.seed, threads)
-        while dt < 8.0 and t_ref < 4096:     # grow the sample to about 10-20 s of CPU work
+        procs = os.cpu_count() or 1
+        cb = cpu_reference(250, 50, 250, 50, procs)
+        n_ref, t_ref = 2048, 8
+        v, dt = cpu_port(n_ref, t_ref, 2, args.seed, procs)
+        while dt < 4.0 and t_ref < 4096:     # grow the sample to a few seconds of CPU work
             t_ref *= 2
-            v, dt = cpu_arm(n_ref, t_ref, 2, args.seed, threads)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": "%d envs x %d ticks of the same workload, oracle C port, %.1f s" % (
-                                    n_ref, t_ref, dt)}
+            v, dt = cpu_port(n_ref, t_ref, 2, args.seed, procs)
+        port = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
+                "sample": "%d envs x %d ticks of the same workload, oracle C port (oracle/tank_oracle.c), %.1f s" % (n_ref, t_ref, dt)}
+        if cb is None:
+            cb = port
+        else:
+            cb["port"] = port
+        line["cpu_baseline"] = cb
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

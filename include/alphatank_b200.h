@@ -125,15 +125,30 @@ int64_t at_num_envs(const at_env *env);
  * non-zero (d_mask NULL = all).  Writes the reset observation rows of those envs into d_obs (if non-NULL). */
 int at_reset(at_env *env, const uint8_t *d_mask, float *d_obs, void *stream);
 
-/* Replaces env.step(actions) (gym_env.py:73-103, gym_env_multi.py:202-223): one fused kernel does bullets
+/* Replaces env.step(actions) (gym_env.py:73-103, gym_env_multi.py:202-223): the simulation kernel does bullets
  * pass 1, controllers (agents from d_actions, bots on device), bullets pass 2, rewards (cumulative, F1),
- * done / TERMINATE_TIME bookkeeping, optional auto-reset and the observation rows. */
+ * done / TERMINATE_TIME bookkeeping and the optional auto-reset; the rows kernel behind it the observation rows. */
 int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_rewards, uint8_t *d_done, void *stream);
 
 /* Same call with HOST action / reward / done buffers (pinned memory recommended): copies actions in,
- * steps, copies rewards+done out and synchronises the stream.  Observations stay in HBM (d_obs). */
+ * steps, copies rewards+done out and synchronises the stream.  Observations stay in HBM (d_obs).
+ * The call remembers which host buffers are pinned + mapped (the query is a driver call); a caller that frees
+ * such a buffer and may get the same address back for pageable memory calls at_forget_host_buffers first. */
 int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
                  void *stream);
+int at_forget_host_buffers(at_env *env);
+
+/* Replaces env._get_observation() (gym_env.py:105-183, gym_env_multi.py:225-304) on the CURRENT state: the
+ * observation rows of every env into d_obs, nothing stepped.  (at_step / at_reset already return them.) */
+int at_observe(at_env *env, float *d_obs, void *stream);
+
+/* What at_step / at_step_norm / at_step_host write into the rewards array.  AT_REWARD_CUMULATIVE (default): the
+ * reference's per-episode running sums (gym_env.py:186-187, gym_env_multi.py:307-308; tank.reward is only zeroed by
+ * reset - quirk F1).  AT_REWARD_DELTA: the increment since the previous step's value (the first step of an episode
+ * returns its value as it is) - what a learner that sums rewards itself needs; computed inside the step from the
+ * previous value kept per env, same float32 arithmetic as subtracting consecutive cumulative outputs. */
+enum at_reward_mode { AT_REWARD_CUMULATIVE = 0, AT_REWARD_DELTA = 1 };
+int at_set_reward_mode(at_env *env, int mode);
 
 /* info dict of step(): winner int32[n_envs] (gym_env.py:97, -1 = nobody alive), hits / be_hits
  * int32[n_envs][n_tanks] (gym_env_multi.py:220-222), change_time int32[n_envs][n_tanks] (gym_env.py:77-83).
@@ -149,6 +164,12 @@ int at_get_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_h
  * (d_latched[e] = 1, uint8[n_envs], may be NULL) and the current values (= at_get_info) for all others. */
 int at_get_terminal_info(at_env *env, int32_t *d_winner, int32_t *d_hits, int32_t *d_be_hits, int32_t *d_change_time,
                          uint8_t *d_latched, void *stream);
+
+/* Per-tank state columns over the batch, for callers that read env.game_env.tanks[i].<attr> (inference.py:115-116
+ * reads .alive every tick): d_out double[AT_TANK_COLS][n_envs] = alive, x, y, angle, reward, num_hit, num_be_hit of
+ * tank `tank`.  One small kernel on the caller's stream; nothing is copied to the host. */
+#define AT_TANK_COLS 7
+int at_get_tank_columns(at_env *env, int tank, double *d_out, void *stream);
 
 /* Snapshot / inject `count` envs starting at `first` (host AoS records).  Synchronous. */
 int at_get_state(at_env *env, int64_t first, int64_t count, at_env_state *h_out);

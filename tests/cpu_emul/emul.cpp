@@ -3,11 +3,10 @@
 // This GPU-less build container cannot run the kernels, so this file compiles the kernels' own per-thread
 // code (at_sim.h, __host__ __device__) with g++ and drives it the way env_kernel does: blocks of 64 envs = two
 // warps, every warp 32 fibers of a small SIMT emulator (simt.h) that run step_lane<> - the kernel body - in
-// lockstep at the warp collectives, so the pooled stages (bullet jobs, line-of-sight queue) execute here exactly as
-// written; the observation rows come from the job functions of rows_kernel (at_rows.h).  It lets the CPU
-// test-suite compare the CUDA-side FORMULATION (cell bitmasks, integer-angle tables, packed bullets, pooled bullet
-// pass with in-order commits, bit-parallel BFS, counter penalties, row jobs) with the oracle before any GPU
-// time is spent.  It is not part of the product, is never loaded by alphatank_b200/, and is not a fallback:
+// lockstep at the warp collectives, so the pooled line-of-sight stage executes here exactly as written; the
+// observation rows come from the job functions of rows_kernel (at_rows.h).  It lets the CPU test-suite compare
+// the CUDA-side FORMULATION (cell bitmasks, integer-angle tables, packed bullets, pooled line of sight,
+// bit-parallel BFS, counter penalties, row jobs) with the oracle before any GPU time is spent.  It is not part of the product, is never loaded by alphatank_b200/, and is not a fallback:
 // the product fails loudly without a GPU.  What it cannot cover (real memory ordering, bulk-async stores) is
 // covered by the -m gpu tests.
 #include <stdlib.h>
@@ -32,8 +31,6 @@ struct em_env {
     std::vector<char> block;  // one block's working set
     std::vector<float> tmpl;
     BlockMem bm;
-    BlockMem pbm;             // one warp's working set of bullets_kernel (columns of stride WE)
-    std::vector<char> pblock;
     simt::Warp warp;
 };
 static thread_local std::string g_err;
@@ -42,8 +39,6 @@ template <int A, int B, int C>
 struct ShapeTag { static constexpr int nt = A, nr = B, tm = C; };
 // rows_kernel's formulation (at_rows.h): the rows of env e rebuilt from the STORED state by independent jobs
 static int g_lane_order = 0;  // simt lane order between collectives: 0 forward, 1 reverse, 2 shuffled
-static int g_monolith = 0;    // 1: every step as one env_kernel (step_lane) even where the library would split it
-static int g_pass_we = 16;    // envs per warp of bullets_kernel
 static void rows_from_state(em_env *env, int64_t e, float *img) {
     const KCfg &c = env->k;
     const DevState &st = env->st;
@@ -78,54 +73,6 @@ static void rows_from_state(em_env *env, int64_t e, float *img) {
     else jobs(ShapeTag<0, 0, -1>{});
 }
 
-// bullets_kernel: every warp serves WE envs
-template <int SPEC, int WE>
-static void run_pass(em_env *env, bool first, float *rewards, uint8_t *done) {
-    const KCfg &c = env->k;
-    const DevState &st = env->st;
-    const int n = c.n_tanks;
-    BlockMem &bm = env->pbm;
-    char *p = env->pblock.data();
-    bm.tx = (double *)p; p += n * WE * 8; bm.ty = (double *)p; p += n * WE * 8; bm.trew = (double *)p; p += n * WE * 8;
-    bm.e_k = (unsigned long long *)p; p += WE * 8;
-    bm.tpack = (uint32_t *)p; p += n * WE * 4; bm.nearlo = (uint32_t *)p; p += n * WE * 4; bm.nearhi = (uint32_t *)p; p += n * WE * 4;
-    bm.e_alive = (uint32_t *)p; p += WE * 4; bm.e_evt = (uint32_t *)p; p += WE * 4;
-    bm.e_ord = (uint32_t *)p; p += WE * 4;
-    bm.res = (uint16_t *)p; p += n * SLOTS_PER_TANK * WE * 2; bm.jobs = (uint16_t *)p; p += n * SLOTS_PER_TANK * WE * 2;
-    bm.tlive = (uint8_t *)p; p += n * WE;
-    bm.bf0 = bm.bf1 = nullptr; bm.bpack = nullptr; bm.tshot = nullptr; bm.los_q = bm.los_r = nullptr;
-    for (int64_t e_warp0 = 0; e_warp0 < st.N; e_warp0 += WE)
-        simt::run_warp(env->warp, 0xffffffffu, [&](int lane) { pass_lane<simt::FiberWarp, SPEC, WE>(c, st, bm, e_warp0, lane, first, rewards, done); });
-}
-template <int SPEC>
-static void run_pass_we(em_env *env, bool first, float *rewards, uint8_t *done) {
-    if (g_pass_we == 8) run_pass<SPEC, 8>(env, first, rewards, done);
-    else if (g_pass_we == 32) run_pass<SPEC, 32>(env, first, rewards, done);
-    else run_pass<SPEC, 16>(env, first, rewards, done);
-}
-// the split step: bullets_kernel, ctrl_kernel, bullets_kernel, fin_kernel - each over the whole batch
-template <int SPEC>
-static void run_split(em_env *env, const int32_t *actions, float *rewards, uint8_t *done) {
-    const KCfg &c = env->k;
-    const DevState &st = env->st;
-    if (SPEC == 3) run_pass_we<3>(env, true, nullptr, nullptr); else run_pass_we<0>(env, true, nullptr, nullptr);
-    for (int64_t b0 = 0; b0 < env->n_envs; b0 += BS)
-        for (int wp = 0; wp < BS / 32; ++wp) {
-            const int64_t e_warp0 = b0 + wp * 32;
-            uint32_t valid_mask = 0;
-            for (int l = 0; l < 32; ++l)
-                if (e_warp0 + l < st.N) valid_mask |= 1u << l;
-            if (!valid_mask) continue;
-            simt::run_warp(env->warp, valid_mask, [&](int lane) {
-                const int64_t e = e_warp0 + lane;
-                ctrl_lane<simt::FiberWarp, SPEC>(c, st, env->bm, e_warp0, wp * 32 + lane, true, valid_mask,
-                                                 actions ? actions + e * c.act_rows * 3 : nullptr);
-            });
-        }
-    if (SPEC == 3) run_pass_we<3>(env, false, rewards, done); else run_pass_we<0>(env, false, rewards, done);
-    for (int64_t e = 0; e < st.N; ++e) fin_lane(c, st, e, done);
-}
-
 template <int SPEC>
 static void run_t(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
                 uint8_t *done) {
@@ -133,9 +80,7 @@ static void run_t(em_env *env, bool is_step, const int32_t *actions, const uint8
     const DevState &st = env->st;
     const int64_t row_len = (int64_t)c.rows * c.obs_dim;
     env->warp.order_mode = g_lane_order;
-    const bool split = is_step && !g_monolith && c.map != AT_MAP_MAZE && c.mode != AT_MODE_ARENA;   // as at_create decides
-    if (split) run_split<SPEC>(env, actions, rewards, done);
-    for (int64_t b0 = 0; b0 < env->n_envs && !split; b0 += BS) {
+    for (int64_t b0 = 0; b0 < env->n_envs; b0 += BS) {
         for (int wp = 0; wp < BS / 32; ++wp) {
             const int64_t e_warp0 = b0 + wp * 32;
             uint32_t valid_mask = 0;
@@ -143,11 +88,10 @@ static void run_t(em_env *env, bool is_step, const int32_t *actions, const uint8
                 if (e_warp0 + l < st.N) valid_mask |= 1u << l;
             if (!valid_mask) continue;
             if (is_step) {
-                simt::run_warp(env->warp, 0xffffffffu, [&](int lane) {
+                simt::run_warp(env->warp, valid_mask, [&](int lane) {
                     const int64_t e = e_warp0 + lane;
-                    const bool valid = e < st.N;
-                    step_lane<simt::FiberWarp, SPEC>(c, st, env->bm, e_warp0, wp * 32 + lane, valid, valid_mask,
-                                                     (actions && valid) ? actions + e * c.act_rows * 3 : nullptr, rewards, done);
+                    step_lane<simt::FiberWarp, SPEC>(c, st, env->bm, e_warp0, wp * 32 + lane, valid_mask,
+                                                     actions ? actions + e * c.act_rows * 3 : nullptr, rewards, done);
                 });
             } else {
                 for (int l = 0; l < 32; ++l) {
@@ -203,35 +147,31 @@ int em_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         env->st.bfs_tab = (const uint16_t *)(env->arena.data() + L.o_bfs);
     }
     const int n = env->k.n_tanks;
-    env->block.assign((size_t)n * BS * (5 * 8 + 6 * 4) + 722 * 8 + (size_t)BS * (8 + 4 * 4) + (size_t)n * SLOTS_PER_TANK * BS * 2 +
-                      (size_t)(BS / 32) * 32 * SLOTS_PER_TANK * n * 2 + (size_t)(BS / 32) * 512 + 64, 0);
+    env->block.assign((size_t)n * BS * (5 * 8 + 6 * 4) + 722 * 8 + (size_t)(BS / 32) * 512 + 64, 0);
     char *p = env->block.data();
     BlockMem &bm = env->bm;
+    bm.trig = (double *)p; p += 722 * 8;
+    memcpy(bm.trig, env->luts.trig.data(), 722 * 8);
     bm.tx = (double *)p; p += n * BS * 8; bm.ty = (double *)p; p += n * BS * 8; bm.trew = (double *)p; p += n * BS * 8;
     bm.bf0 = (double *)p; p += n * BS * 8; bm.bf1 = (double *)p; p += n * BS * 8;
-    bm.e_k = (unsigned long long *)p; p += BS * 8;
     bm.tpack = (uint32_t *)p; p += n * BS * 4; bm.nearlo = (uint32_t *)p; p += n * BS * 4;
     bm.bpack = (uint32_t *)p; p += n * BS * 4; bm.tlive = (uint8_t *)p; p += n * BS * 4;
     bm.tshot = (int32_t *)p; p += n * BS * 4;
     bm.nearhi = (uint32_t *)p; p += n * BS * 4;
-    bm.e_alive = (uint32_t *)p; p += BS * 4; bm.e_evt = (uint32_t *)p; p += BS * 4;
-    bm.e_ord = (uint32_t *)p; p += BS * 4;
-    bm.res = (uint16_t *)p; p += (size_t)n * SLOTS_PER_TANK * BS * 2;
-    bm.jobs = (uint16_t *)p; p += (size_t)(BS / 32) * 32 * SLOTS_PER_TANK * n * 2;
     bm.los_q = (uint8_t *)p; p += (BS / 32) * 256;
     bm.los_r = (uint8_t *)p; p += (BS / 32) * 256;
-    env->pblock.assign((size_t)n * 32 * (3 * 8 + 3 * 4 + 1) + 32 * (8 + 16) + (size_t)n * SLOTS_PER_TANK * 32 * 4 + 64, 0);
+    bm.udelta = env->luts.udelta.data();
     env->tmpl.assign(4 * 72 + CELLS, 0.f);
     if (env->k.map != AT_MAP_MAZE) fill_static_template(env->k.wall_lo, env->k.wall_hi, env->tmpl.data());
     *(double *)(env->arena.data() + L.o_dyn) = env->k.weakness;
+    fill_atan_table((double *)(env->arena.data() + L.o_atab));
     run(env, false, nullptr, nullptr, nullptr, nullptr, nullptr);  // the constructor's own reset
     *out = env;
     return AT_OK;
 }
 void em_destroy(em_env *env) { delete env; }
 void em_set_lane_order(int m) { g_lane_order = m; }
-void em_set_monolith(int m) { g_monolith = m; }
-void em_set_pass_we(int w) { g_pass_we = w; }
+
 int em_set_weakness(em_env *env, double w) {
     *(double *)env->st.dyn = w;
     env->k.weakness = w;
@@ -298,6 +238,16 @@ int em_bfs(const uint8_t *maze121, int sr, int sc, int gr, int gc, int *next_r, 
     return bfs_first_step(lo, hi, sr, sc, gr, gc, next_r, next_c);
 }
 double em_jump_axis(double x, double d, int m) { return jump_axis(x, d, m); }
+// atan2_refine on a starting value that is `ulps` units off the host's atan2 (the device's is good to 2 ulp)
+double em_atan2_refine(double y, double x, int ulps) {
+    static std::vector<double> tab;
+    if (tab.empty()) { tab.resize(361 * ATAB_STRIDE); fill_atan_table(tab.data()); }
+    double th0 = atan2(y, x);
+    for (int i = 0; i < (ulps < 0 ? -ulps : ulps); ++i) th0 = nextafter(th0, ulps < 0 ? -10.0 : 10.0);
+    const double t = th0 * (180.0 / 3.141592653589793), k = rint(t);
+    if (!(fabs(t - k) < 1e-9)) return NAN;      // not a case the kernel refines
+    return atan2_refine(y, x, th0, (int)k, tab.data());
+}
 void em_generate_maze(uint64_t seed, int64_t env_id, uint32_t *ctr, uint8_t *maze121) {
     const MazeOut mz = generate_maze_mask(seed, env_id, *ctr);
     const uint64_t lo = mz.lo, hi = mz.hi;

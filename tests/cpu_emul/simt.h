@@ -153,18 +153,9 @@ inline void run_warp(Warp &w, uint32_t active, const std::function<void(int)> &b
 
 // the warp policy (interface of at::DevWarp, alphatank_b200/csrc/at_warp.h)
 struct FiberWarp {
-    static constexpr bool kDevice = false;
-    static int lane() { return current()->cur; }
     static void sync(uint32_t mask) { collective(OP_SYNC, mask, 0, 0); }
     static uint32_t ballot(uint32_t mask, bool pred) { return collective(OP_BALLOT, mask, pred ? 1u : 0u, 0); }
     static uint32_t shfl(uint32_t mask, uint32_t v, int src) { return collective(OP_SHFL, mask, v, src); }
-    static uint32_t shfl_up(uint32_t mask, uint32_t v, int d) { return collective(OP_SHFL_UP, mask, v, d); }
-    static uint32_t atomic_or(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o | v; return o; }
-    static uint32_t atomic_min(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = v < o ? v : o; return o; }
-    static uint32_t atomic_add(uint32_t *p, uint32_t v) { uint32_t o = *p; *p = o + v; return o; }
-    static unsigned long long atomic_add64(unsigned long long *p, unsigned long long v) {
-        unsigned long long o = *p; *p = o + v; return o;
-    }
 };
 
 }  // namespace simt

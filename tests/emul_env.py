@@ -36,8 +36,6 @@ def lib():
             getattr(L, f).argtypes = [vp]
         L.em_reset.argtypes = [vp, vp, vp]
         L.em_set_lane_order.argtypes = [i32]
-        L.em_set_monolith.argtypes = [i32]
-        L.em_set_pass_we.argtypes = [i32]
         L.em_set_weakness.argtypes = [vp, C.c_double]
         L.em_collectives.argtypes = [vp]
         L.em_collectives.restype = C.c_uint64
@@ -51,6 +49,8 @@ def lib():
         L.em_generate_maze.argtypes = [C.c_uint64, i64, vp, vp]
         L.em_jump_axis.restype = C.c_double
         L.em_jump_axis.argtypes = [C.c_double, C.c_double, i32]
+        L.em_atan2_refine.restype = C.c_double
+        L.em_atan2_refine.argtypes = [C.c_double, C.c_double, i32]
         L.em_last_error.restype = C.c_char_p
         _lib = L
     return _lib

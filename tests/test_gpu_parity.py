@@ -412,3 +412,118 @@ def test_delta_reward_mode_telescopes_to_the_reference_cumulative_rewards():
         with pytest.raises(ValueError):
             make(reward_mode="per_tick")
         a.close(); b.close()
+
+
+def test_kernel_delta_rewards_equal_the_difference_of_consecutive_cumulative_rewards():
+    """AT_REWARD_DELTA is computed inside the step (csrc/at_sim.h finish_step) from the previous value kept per env: the
+    same float32 numbers as subtracting consecutive cumulative outputs on the caller's side, zero-based after a reset."""
+    import torch
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    dev = torch.device("cuda:0")
+    N = 1500
+    a = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=4)
+    b = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=4, reward_mode="delta")
+    a.reset(); b.reset()
+    prev = torch.zeros((N, 2), dtype=torch.float32, device=dev)
+    for t in range(260):
+        acts = a.core.synthetic_actions(t)
+        _, ra, da, _, _ = a.step(acts)
+        _, rb, db, _, _ = b.step(acts)
+        assert torch.equal(rb, ra - prev), t
+        prev = ra * (1.0 - da.to(torch.float32)).unsqueeze(-1)
+    b.core.set_reward_mode("cumulative")          # and back: the same stream as the cumulative handle again
+    acts = a.core.synthetic_actions(260)
+    _, ra, _, _, _ = a.step(acts)
+    _, rb, _, _, _ = b.step(acts)
+    assert torch.equal(ra, rb)
+
+
+def test_observe_and_tank_columns_read_the_current_state():
+    """at_observe = env._get_observation() on the current state (the rows the last step returned); the TankView
+    properties (env.game_env.tanks[i].alive ..., inference.py:115-116) come from one column kernel and agree with the
+    full-state snapshot."""
+    import torch
+    from alphatank_b200 import MultiAgentEnv
+    env = MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=777, device="cuda:0", seed=2)
+    env.reset()
+    for t in range(90):
+        obs, _, _, _, _ = env.step(env.core.synthetic_actions(t))
+    last = obs.clone()
+    again = env.core.observe(torch.empty_like(env.core.obs))
+    assert torch.equal(last.view(-1), again.view(-1))
+    st = env.core.get_state()
+    for i in range(2):
+        tv = env.game_env.tanks[i]
+        assert np.array_equal(tv.alive.cpu().numpy(), st["tanks"]["alive"][:, i] != 0)
+        assert np.array_equal(tv.x.cpu().numpy(), st["tanks"]["x"][:, i])
+        assert np.array_equal(tv.angle.cpu().numpy(), st["tanks"]["angle"][:, i])
+        assert np.array_equal(tv.reward.cpu().numpy(), st["tanks"]["reward"][:, i])
+        assert np.array_equal(tv.num_be_hit.cpu().numpy(), st["tanks"]["num_be_hit"][:, i])
+    assert tv.alive.is_cuda
+
+
+def test_bot_agent_outside_training_reads_the_agent_action_from_row_0():
+    """gaming_env.py:176-177 (F15): MultiAgentEnv(mode='bot_agent', type != 'train') - the inference scripts - takes the
+    agent's action from actions[0].  Same trajectories as a training-type env fed the same action in row 1."""
+    import torch
+    from alphatank_b200 import MultiAgentEnv
+    N = 600
+    a = MultiAgentEnv(mode="bot_agent", type="train", bot_type="aggressive", num_envs=N, device="cuda:0", seed=8)
+    b = MultiAgentEnv(mode="bot_agent", type="inference", bot_type="aggressive", num_envs=N, device="cuda:0", seed=8)
+    a.reset(); b.reset()
+    for t in range(150):
+        acts = a.core.synthetic_actions(t).clone()
+        oa, ra, da, _, _ = a.step(acts)
+        ob, rb, db, _, _ = b.step(acts[:, 1:2])          # one row per env, as inference.py passes it
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(da, db), t
+
+
+def test_handles_with_different_shared_memory_needs_coexist():
+    """The dynamic shared-memory limit of a kernel is process-wide: a second handle with a smaller working set
+    (octagon: 40 walls) must not lower it under a first one that needs more (battlefield: 61 walls)."""
+    big = _gpu(SWEEP["team_harder_battlefield"], 300, 5, 0, auto_reset=True)
+    small = _gpu(SWEEP["team_vs_bot"], 300, 5, 0, auto_reset=True)
+    ora = parity.make_oracle_env(SWEEP["team_harder_battlefield"], 300, 5, 0, auto_reset=True)
+    assert np.array_equal(big.reset(), ora.reset())
+    small.reset()
+    ids = np.arange(300)
+    for t in range(20):
+        acts = synthetic_actions(5, ids, t, big.A)
+        ob, rb, db = big.step(acts)
+        small.step(synthetic_actions(5, ids, t, small.A))
+        oo, ro, do = ora.step(acts, threads=4)
+        assert np.array_equal(ob, oo) and np.array_equal(rb, ro) and np.array_equal(db, do), t
+
+
+def test_set_weakness_reaches_a_captured_cuda_graph():
+    """at_set_weakness writes device memory the kernels read (DevState::dyn), so a step captured in a CUDA graph - the
+    rollout runner's case - follows the curriculum: after set_weakness(0) the replayed graph's bot never acts again."""
+    import torch
+    from alphatank_b200 import MultiAgentEnv
+    N = 512
+    env = MultiAgentEnv(mode="bot_agent", bot_type="aggressive", weakness=1.0, num_envs=N, device="cuda:0", seed=6,
+                        auto_reset=False)
+    env.reset()
+    acts = torch.ones((N, 2, 3), dtype=torch.int32, device="cuda:0")     # the agent idles
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            env.core.step(acts)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            env.core.step(acts)
+    torch.cuda.synchronize()
+    for _ in range(40):
+        g.replay()
+    torch.cuda.synchronize()
+    moved = env.core.get_state()["tanks"]
+    assert (moved["speed"][:, 0] != 0).any() or (moved["num_hit"][:, 0] > 0).any()   # weakness 1: the bot acts
+    env.set_weakness(0.0)
+    before = env.core.get_state()["tanks"]
+    for _ in range(60):
+        g.replay()
+    torch.cuda.synchronize()
+    after = env.core.get_state()["tanks"]
+    assert np.array_equal(before["x"][:, 0], after["x"][:, 0]) and np.array_equal(before["angle"][:, 0], after["angle"][:, 0])
+    assert (after["speed"][:, 0] == 0).all()

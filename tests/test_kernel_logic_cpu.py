@@ -213,17 +213,16 @@ def test_simulation_specialisations_agree(cap):
 
 @pytest.mark.parametrize("order", [1, 2])
 def test_pooled_stages_do_not_depend_on_the_lane_order(order):
-    """The pooled stages (Sim::bullets_pass_pooled, pool_los) run here on the SIMT emulator (tests/cpu_emul/simt.h):
-    32 fibers per warp that meet at the warp collectives.  Between two collectives the emulator runs the lanes one
-    after the other - in reverse (1) or freshly shuffled (2) order here instead of lane order - so a lane that read
-    another lane's shared-memory write without a barrier in between would diverge from the oracle.  Bullet-heavy
-    configs: the bench layout, the immortal arena (a hit every few ticks: F6 bonus + the serial tail behind a hit)
-    and the 8-tank mix (48 slots: 64-bit candidate masks)."""
+    """The pooled line-of-sight stage (Sim::pool_los) runs here on the SIMT emulator (tests/cpu_emul/simt.h): 32
+    fibers per warp that meet at the warp collectives.  Between two collectives the emulator runs the lanes one after
+    the other - in reverse (1) or freshly shuffled (2) order here instead of lane order - so a lane that read another
+    lane's shared-memory write without a barrier in between would diverge from the oracle.  Smart-bot configs: the
+    bench layout, a 1v1 arena of two smart bots, the 6-tank battlefield mix."""
     L = emul_env.lib()
     L.em_set_lane_order(order)
     try:
-        for name in ("team_vs_bot", "arena_def_dodge_t200", "team_8_mixed"):
-            spec = SWEEP[name]
+        for name in ("team_vs_bot", "arena_smart_smart", "team_harder_battlefield"):
+            spec = SWEEP[name] if name in SWEEP else _spec("arena", [("A", "bot", "smart"), ("B", "bot", "smart")])
             N, ticks, seed, base = 70, 220, 31, 64
             a = parity.make_oracle_env(spec, N, seed, base, auto_reset=True)
             b = emul_env.make_emul_env(spec, N, seed, base, auto_reset=True)
@@ -240,3 +239,40 @@ def test_pooled_stages_do_not_depend_on_the_lane_order(order):
             assert L.em_collectives(b.h) > 0
     finally:
         L.em_set_lane_order(0)
+
+
+def test_atan2_refine_is_correctly_rounded():
+    """atan2_refine (csrc/at_sim.h: one Newton step on a few-ulp atan2, sin / cos by angle addition from a table of
+    106-bit values at the integer-degree angles) against mpmath at 200 bits, on the inputs it exists for - bearings that
+    are integers up to rounding (a tank that left a shared spawn cell along its heading, seen from that cell) - starting
+    from values up to 3 ulp off.  The same run reports how often glibc's atan2 (= Python's = the oracle's) is itself
+    correctly rounded there: that rate bounds how often a knife-edge bot decision on the GPU can differ from the
+    reference, whose own answer depends on the libm it runs on."""
+    mpmath = pytest.importorskip("mpmath")
+    import math
+    mpmath.mp.prec = 200
+    L = emul_env.lib()
+    cases = []
+    for a in range(0, 361):
+        r = math.radians(a)
+        c, s = math.cos(r), math.sin(r)
+        for k in (1, 2, 3, 5, 8, 13, 21, 29):
+            for sp in (10, -10, 1):
+                x, y = 105.0, 595.0
+                for _ in range(k):
+                    x, y = x + sp * c, y - sp * s
+                dx, dy = x - 105.0, y - 595.0
+                if dx != 0.0 and dy != 0.0 and abs(dx) != abs(dy):   # (axis / diagonal cases are pinned constants)
+                    cases += [(-dy, dx), (dy, -dx)]
+    bad = bad_libm = refined = 0
+    for y, x in cases:
+        want = float(mpmath.atan2(mpmath.mpf(y), mpmath.mpf(x)))
+        bad_libm += math.atan2(y, x) != want
+        for ulps in (0, 2, -3):
+            got = L.em_atan2_refine(y, x, ulps)
+            if got == got:     # NaN: the bearing is not within 1e-9 degrees of an integer (never refined)
+                refined += 1
+                bad += got != want
+    assert refined > 0.9 * 3 * len(cases)
+    assert bad == 0, "%d of %d not correctly rounded" % (bad, refined)
+    assert bad_libm < 0.02 * len(cases)      # glibc 2.39: ~0.4 %

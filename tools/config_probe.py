@@ -38,6 +38,8 @@ def run(name, env, agents, steps=200, burn=400):
     env.close() if hasattr(env, "close") else None
 
 
+run("2v2 team_vs_bot, 256 envs (smoke size)", MultiAgentTeamEnv(team_vs_bot_configs, num_envs=256, device=dev), 2)
+run("2v2 team_vs_bot, 4096 envs", MultiAgentTeamEnv(team_vs_bot_configs, num_envs=4096, device=dev), 2)
 run("config 2: 1v1 bot_agent vs smart bot", MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=4096, device=dev), 1)
 run("config 2 at 65 536 envs", MultiAgentEnv(mode="bot_agent", bot_type="smart", num_envs=65536, device=dev), 1)
 run("config 1 batched: 1v1 agent mode", MultiAgentEnv(mode="agent", num_envs=65536, device=dev), 2)
