@@ -241,7 +241,7 @@ __device__ __forceinline__ void tick_norm_column(const float (&v)[RMAX], int row
 // the simulation's tail; griddepcontrol.wait orders everything else behind the simulation's stores.
 constexpr int RK_MAX_WARPS = 16;   // warps per block: a launch parameter (blockDim.x / 32)
 struct RowsSmem {   // per warp, after the block's trig table
-    size_t off_img, off_nimg, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, per_warp, total;
+    size_t off_img, off_nimg, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, off_jl, per_warp, total;
 };
 __host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats, int warps, bool norm) {
     RowsSmem L;
@@ -260,6 +260,8 @@ __host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_float
     L.off_zn = o; o += (size_t)G * 4;
     L.off_emit = o; o += (size_t)G * 4;
     L.off_occ = o; o += (size_t)G * S;     // which bullet positions of the image hold a bullet
+    o = (o + 1) & ~(size_t)1;
+    L.off_jl = o; o += (size_t)G * S * 2;  // the group's position jobs, compacted
     L.per_warp = (o + 127) & ~(size_t)127;
     L.total = 722 * 8 + 64 + L.per_warp * warps;   // (722 * 8 + 64 is a multiple of 128)
     return L;
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     uint64_t *wl = (uint64_t *)(ws + L.off_wlo), *wh = (uint64_t *)(ws + L.off_whi);
     int *em_s = (int *)(ws + L.off_emit);
     uint8_t *occ = (uint8_t *)(ws + L.off_occ);
+    uint16_t *jl = (uint16_t *)(ws + L.off_jl);
     const int N = (int)st.N;   // (at_create guarantees 6 n N < 2^31: 32-bit column indices)
 
     // ---- prologue: nothing here depends on the simulation kernel's stores
@@ -398,24 +401,43 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         // the previous copy must be done reading the image
         if (lane == 0) bulk_wait_read_all();
         const bool all_emit = __all_sync(0xffffffffu, my_em);   // (also the warp barrier between phase 1 and 2)
-        // ---- phase 2: 32 jobs per pass (2v2, 4 envs: three passes of position jobs, one of tank jobs).  Position jobs
-        // are rank-major - a pass holds two ranks of every owner - and a position that holds no bullet now and held
-        // none when the image was last filled is skipped (it is still zero): the pass of ranks 4, 5 mostly has no work.
-        for (int j = lane; j < jobs; j += 32) {
-            const int g = j & (G - 1);
-            if (j < jobs_pos) {
-                const int jp = j >> lgG;
-                const int k = jp / n, o = jp - k * n;
-                const int q = (o * SLOTS_PER_TANK + k) * G + g;
-                const uint64_t m = rm[q];
-                const bool has = m != ROWS_EMPTY;
-                if (!inplace) {   // (an image that is normalised in place is rebuilt in full)
-                    if (!has && !occ[q]) continue;
+        // ---- phase 2: 32 jobs per pass.  Position jobs first: a position that holds no bullet now and held none when
+        // the image was last filled needs no work (it is still zero) - about 60 % of them - so the positions that do are
+        // compacted into a list (ballot + prefix) and the lanes work through that list densely instead of visiting every
+        // position with two lanes in three idle.  (An image that is normalised in place is rebuilt in full.)
+        int npos = jobs_pos;
+        if (!inplace) {
+            npos = 0;
+            for (int j0 = 0; j0 < jobs_pos; j0 += 32) {
+                const int j = j0 + lane;
+                bool need = false;
+                if (j < jobs_pos) {
+                    const int jp = j >> lgG;
+                    const int k = jp / n, o = jp - k * n;
+                    const int q = (o * SLOTS_PER_TANK + k) * G + (j & (G - 1));
+                    const bool has = rm[q] != ROWS_EMPTY;
+                    need = has || occ[q];
                     occ[q] = has ? 1 : 0;
                 }
-                rows_position_job<NT, NR, TEAM>(c, trig, o, k, m, rx[q], ry[q], tx + g, ty + g, G, img + g * RD, g + 4 * (o >> 1));
-                if (has) rm[q] = ROWS_EMPTY;   // the table is empty again for the next group
-            } else if (j < jobs_pos + jobs_tank) {   // the rows' own blocks first, then the other-tank blocks
+                const unsigned nb = __ballot_sync(0xffffffffu, need);
+                if (need) jl[npos + __popc(nb & ((1u << lane) - 1u))] = (uint16_t)j;
+                npos += __popc(nb);
+            }
+            __syncwarp();
+        }
+        for (int i = lane; i < npos; i += 32) {
+            const int j = inplace ? i : (int)jl[i];
+            const int g = j & (G - 1);
+            const int jp = j >> lgG;
+            const int k = jp / n, o = jp - k * n;
+            const int q = (o * SLOTS_PER_TANK + k) * G + g;
+            const uint64_t m = rm[q];
+            rows_position_job<NT, NR, TEAM>(c, trig, o, k, m, rx[q], ry[q], tx + g, ty + g, G, img + g * RD, g + 4 * (o >> 1));
+            if (m != ROWS_EMPTY) rm[q] = ROWS_EMPTY;   // the table is empty again for the next group
+        }
+        for (int j = jobs_pos + lane; j < jobs; j += 32) {
+            const int g = j & (G - 1);
+            if (j < jobs_pos + jobs_tank) {   // the rows' own blocks first, then the other-tank blocks
                 const int j2 = (j - jobs_pos) >> lgG;
                 int r, i;
                 if (j2 < nrows) {

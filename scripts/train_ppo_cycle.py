@@ -12,12 +12,14 @@ What is kept from the reference (train_ppo_cycle.py:24-92, 244-256, 258-445):
 * the env is ``MultiAgentEnv(mode='bot_agent', type='train', bot_type=...)``, the agent is tank 1, the opponent is
   switched by ``set_bot_type`` (:305) and its weakness follows the schedule (``set_weakness`` -> ``at_set_weakness``,
   in place);
-* GAE + clipped surrogate with the reference's per-tick observation normaliser; the checkpoint is the agent's
+* GAE + clipped surrogate; observations go through ONE persistent ``RunningMeanStd`` updated with every batch of
+  rows the agent sees (:279, :319-320; the fresh-normaliser-per-tick quirk belongs to train_ppo_bot.py /
+  train_multi_ppo.py, not to this trainer), evaluation keeps its own (:102, :155); the checkpoint is the agent's
   ``state_dict()`` at ``checkpoints/single_ppo_cycle/ppo_agent_cycle.pt`` (:438-441), loadable by ``inference.py``;
 * ``run_evaluation`` (:122-206): win rate and mean reward of the agent against every bot type.
 
-What differs because N battles run at once: one env handle, rollout buffer and CUDA graph per bot type (a graph holds
-the handle it was captured on); an episode's outcome is ``info["winner"] == 1`` at its terminal tick exactly as in the
+What differs because N battles run at once: one env handle and rollout buffer per bot type (the running normaliser
+keeps host-side state, so these rollouts are issued kernel by kernel, not as a CUDA graph); an episode's outcome is ``info["winner"] == 1`` at its terminal tick exactly as in the
 reference (:341, :357) - the step latches the finished episode's info before its auto-reset (``at_get_terminal_info``),
 and the rollout stores it per tick (``RolloutBuffer(keep_winner=True)``).  W&B logging and the video recorder are out
 of scope."""
@@ -114,12 +116,15 @@ def rollout_outcomes(buf):
 
 
 @torch.no_grad()
-def run_evaluation(learner, bot_types, num_envs, ticks, device, seed=12345, weakness=1.0):
+def run_evaluation(learner, bot_types, num_envs, ticks, device, seed=12345, weakness=1.0, eval_norm=None):
     """train_ppo_cycle.py:122-206: the agent against every bot type; win = ``info["winner"] == 1`` at the terminal
     tick (:181).  ``num_envs`` battles for ``ticks`` ticks each instead of ``eval_episodes`` sequential episodes; the
-    finished battles are reset by the caller after reading info, the reference's own order."""
+    finished battles are reset by the caller after reading info, the reference's own order.  Observations go through
+    the evaluator's OWN running normaliser (:102, :155), not the trainer's: pass one ``RunningMeanStd`` as
+    ``eval_norm`` to keep it across evaluations like the reference's evaluator object does."""
     from alphatank_b200 import MultiAgentEnv
     from alphatank_b200.learner.ppo import SingleAgentView
+    from alphatank_b200.learner.ppo_utils import RunningMeanStd
     results = {}
     for bot in bot_types:
         env = MultiAgentEnv(mode="bot_agent", type="train", bot_type=bot, weakness=weakness, num_envs=num_envs,
@@ -130,10 +135,13 @@ def run_evaluation(learner, bot_types, num_envs, ticks, device, seed=12345, weak
         rew = torch.zeros((num_envs,), dtype=torch.float32, device=device)
         done = torch.zeros((num_envs,), dtype=torch.uint8, device=device)
         view.reset(obs_out=raw)
+        if eval_norm is None:
+            eval_norm = RunningMeanStd((D,), device=device)
         wins = episodes = 0
         reward_sum = 0.0
         for _ in range(ticks):
-            acts, _, _ = learner.act(learner.normalize(raw))
+            eval_norm.update(raw)
+            acts, _, _ = learner.act(eval_norm.normalize(raw).view(num_envs, 1, D))
             view.step(acts, obs_out=raw, rewards_out=rew, done_out=done)
             d = done.bool()
             if bool(d.any()):
@@ -162,8 +170,9 @@ def train_cycle(config, num_envs=4096, updates=None, seed=0, eval_envs=1024, eva
     eval_updates = max(1, config.eval_frequency // (T * num_envs)) if config.eval_frequency else 0
     cfg = PPOConfig(learning_rate=config.learning_rate, gamma=config.gamma, gae_lambda=config.gae_lambda,
                     clip_coef=config.clip_coef, ent_coef=config.ent_coef, vf_coef=config.vf_coef,
-                    max_grad_norm=config.max_grad_norm, num_steps=T, num_epochs=config.num_epochs)
-    learner = tracker = None
+                    max_grad_norm=config.max_grad_norm, num_steps=T, num_epochs=config.num_epochs,
+                    obs_norm="running")       # train_ppo_cycle.py:279, 319-320: one persistent RunningMeanStd
+    learner = tracker = eval_norm = None
     slots = {}                                                           # bot type -> env, buffer, runner, state
 
     def slot(bot):
@@ -175,7 +184,7 @@ def train_cycle(config, num_envs=4096, updates=None, seed=0, eval_envs=1024, eva
             obs_dim = env.observation_space.shape[0] // env.num_tanks
             if learner is None:
                 learner = PPOLearner(1, obs_dim, tuple(int(x) for x in env.action_space.nvec[:3]), cfg, dev, seed=seed)
-            buf = RolloutBuffer(T, num_envs, 1, obs_dim, dev, keep_raw=False, keep_winner=True)
+            buf = RolloutBuffer(T, num_envs, 1, obs_dim, dev, keep_raw=True, keep_winner=True)   # (the running normaliser reads the raw rows)
             slots[bot] = {"env": env, "buf": buf, "runner": RolloutRunner(SingleAgentView(env), learner, buf),
                           "first": True}
         return slots[bot]
@@ -219,7 +228,10 @@ def train_cycle(config, num_envs=4096, updates=None, seed=0, eval_envs=1024, eva
                                           rec["agent_steps_per_s"] / 1e6, t2 - t1, stats["policy_loss"],
                                           stats["value_loss"], stats["entropy"]))
         if eval_updates and update % eval_updates == 0:
-            ev = run_evaluation(learner, config.bot_types, eval_envs, eval_ticks, dev)
+            if eval_norm is None:
+                from alphatank_b200.learner.ppo_utils import RunningMeanStd
+                eval_norm = RunningMeanStd((learner.D,), device=dev)
+            ev = run_evaluation(learner, config.bot_types, eval_envs, eval_ticks, dev, eval_norm=eval_norm)
             rec["eval"] = ev
             log("  eval: " + "  ".join("%s %.2f (%d ep)" % (b, r["win_rate"], r["episodes"]) for b, r in ev.items()))
     os.makedirs(ckpt_dir, exist_ok=True)
