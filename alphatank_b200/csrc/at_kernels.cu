@@ -26,6 +26,7 @@
 #include "at_host.h"
 #include "at_sim.h"
 #include "at_rows.h"
+#include "at_policy_tc.cuh"
 
 using namespace at;
 
@@ -1710,6 +1711,29 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
     CUDA_TRY(cudaGetLastError());
     sample_out9_kernel<<<(int)((n_rows + 255) / 256), 256, 0, s>>>(d_out9, n_rows, seed, d_counter, stream_id, d_actions, act_stride,
                                                                   d_logprobs, lp_stride, d_values, val_stride);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t n_rows, int dim, const float *d_w1, const float *d_b1,
+                    float *d_z1, void *stream) {
+    if (!d_x || !d_w1 || !d_b1 || !d_z1 || n_rows <= 0 || dim <= 0 || dim % 4 != 0 || x_row_stride % 4 != 0 || x_row_stride < dim)
+        return fail(AT_ERR_ARG, "at_policy_first: bad argument (dim and the row stride must be multiples of 4 floats)");
+    if ((((uintptr_t)d_x) | ((uintptr_t)d_w1) | ((uintptr_t)d_z1) | ((uintptr_t)d_b1)) & 15u)
+        return fail(AT_ERR_ARG, "at_policy_first: buffers must be 16-byte aligned");
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
+    CUtensorMap mx, mw;
+    if (!at_tc::make_map_2d(&mx, d_x, (uint64_t)n_rows, (uint64_t)dim, (uint64_t)x_row_stride * 4, at_tc::TM) ||
+        !at_tc::make_map_2d(&mw, d_w1, (uint64_t)at_tc::TN, (uint64_t)dim, (uint64_t)dim * 4, 256))
+        return fail(AT_ERR_CUDA, "at_policy_first: cuTensorMapEncodeTiled is not available or rejected the tensors");
+    static bool attr_set = false;
+    if (!attr_set) {
+        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_first_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = (int)((n_rows + at_tc::TM - 1) / at_tc::TM), kc = (dim + at_tc::KC - 1) / at_tc::KC;
+    at_tc::policy_first_kernel<<<grid, 128, at_tc::SMEM_BYTES, (cudaStream_t)stream>>>(mx, mw, d_b1, d_z1, (int)n_rows, kc);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
 }

@@ -229,6 +229,14 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
                        int32_t *d_actions, int64_t act_stride, float *d_logprobs, int64_t lp_stride, float *d_values,
                        int64_t val_stride, void *stream);
 
+/* The first layers of one policy's four MLPs (models/ppo_utils.py:31-45: critic + three heads share the input) as one
+ * contraction on the tcgen05 tensor cores: d_z1 float[n_rows][512] = x . W1^T + b1, x = n_rows rows of `dim` floats
+ * x_row_stride floats apart (so a column slice of the [N][A][D] observation tensor can be passed as it is), d_w1 =
+ * float[512][dim], d_b1 = float[512].  TMA operand loads, TF32 multiply with fp32 accumulation in tensor memory - the
+ * precision of the cuBLAS TF32 GEMM it replaces.  dim and x_row_stride must be multiples of 4. */
+int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t n_rows, int dim, const float *d_w1,
+                    const float *d_b1, float *d_z1, void *stream);
+
 /* Diagnostics: while d_times (device, uint64[2 * ceil(n_envs / 64)]) is set, every block of the simulation kernel
  * stamps %globaltimer (ns) at its start and end into it; NULL switches the stamps off.  Used to study how the blocks'
  * finishing times spread (profiles/). */

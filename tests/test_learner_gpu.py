@@ -258,3 +258,34 @@ def test_single_agent_view_matches_the_plain_env():
         row = o.view(N, 2, 388)[:, 1:2]
         assert torch.equal(rew[:, 0], r[:, 1]) and torch.equal(dn, d)
         assert torch.equal(norm, tick_normalize(row.contiguous()))
+
+
+@pytest.mark.parametrize("n_rows", [128, 1000, 40000])
+def test_policy_first_layers_on_tcgen05_match_the_fp32_reference(n_rows):
+    """at_policy_first (csrc/at_policy_tc.cuh: TMA operand loads, tcgen05.mma.kind::tf32, accumulators in tensor memory)
+    against the plain PyTorch fp32 reference of the same op, x . W1^T + b1 for the four first layers of a policy:
+    TF32 multiplies (10-bit mantissa) with fp32 accumulation over K = 528 -> tolerance 2e-3 of the row scale, the same
+    bar as the cuBLAS TF32 GEMM it replaces.  x is a column slice of an [N, A, D] tensor (strided rows), N ragged."""
+    import ctypes as C
+    from alphatank_b200 import _capi
+    from alphatank_b200.learner.ppo_utils import PPOAgentPPO
+    torch.manual_seed(0)
+    dev = torch.device("cuda:0")
+    D, A = 528, 2
+    agent = PPOAgentPPO(D).to(dev)
+    nets = [agent.critic] + list(agent.actor)
+    w1 = torch.cat([m[0].weight for m in nets], dim=0).contiguous()
+    b1 = torch.cat([m[0].bias for m in nets], dim=0).contiguous()
+    obs = torch.randn((n_rows, A, D), device=dev) * 3.0
+    obs[:, :, 100:200] = 0.0                       # runs of empty bullet columns, like real rows
+    for i in range(A):
+        x = obs[:, i]
+        z = torch.full((n_rows, 512), float("nan"), device=dev)
+        _capi.check(_capi.lib().at_policy_first(0, C.c_void_p(x.data_ptr()), x.stride(0), n_rows, D, C.c_void_p(w1.data_ptr()),
+                                                C.c_void_p(b1.data_ptr()), C.c_void_p(z.data_ptr()),
+                                                C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)), "at_policy_first")
+        torch.backends.cuda.matmul.allow_tf32 = False
+        ref = torch.addmm(b1, x.double(), w1.double().t().to(torch.float64)).float() if False else (x.double() @ w1.double().t() + b1.double()).float()
+        assert torch.isfinite(z).all()
+        scale = (x.abs().double() @ w1.abs().double().t()).float() + 1.0
+        assert ((z - ref).abs() / scale).max().item() < 2e-3
