@@ -113,6 +113,7 @@ struct HostSignal {
     volatile uint32_t *host_flag;   // mapped host memory; nullptr: no signalling
     uint32_t epoch;
     unsigned long long *dbg_times;  // diagnostics (at_debug_block_times): [2 * grid] globaltimer at block start / end
+    int epw;                        // envs per warp (1 .. 32, lanes 0 .. epw - 1 own one): see sim_envs_per_warp
 };
 
 // at_step_host: the last block to finish posts `epoch` into a mapped host word (block-uniform call)
@@ -164,9 +165,11 @@ __global__ void __launch_bounds__(BS, 7) env_kernel(const __grid_constant__ KCfg
     }
     __syncthreads();
 
-    const int64_t e_warp0 = (int64_t)blockIdx.x * BS + warp * 32;
+    // Small batches leave most SMs' warp slots empty, and a warp's tick lasts as long as the UNION of its lanes' paths:
+    // with fewer envs per warp (the other lanes idle) the same envs spread over more warps with shorter paths.
+    const int64_t e_warp0 = ((int64_t)blockIdx.x * (BS / 32) + warp) * sig.epw;
     const int64_t e = e_warp0 + lane;
-    const bool valid = e < st.N;
+    const bool valid = lane < sig.epw && e < st.N;
     const unsigned valid_mask = __ballot_sync(0xffffffffu, valid);
 
     if (IS_STEP) {
@@ -1068,6 +1071,7 @@ struct at_env {
     const float *d_tmpl;
     double *d_dyn;            // st.dyn: parameters that may change between steps (at_set_weakness)
     size_t smem_bytes_sim;    // env_kernel
+    int sim_epw;              // envs per warp of the simulation kernel (sim_envs_per_warp; AT_SIM_EPW overrides)
     int sim_spec;             // SimT<SPEC> specialisation of the step's simulation kernel (0: generic; AT_NO_SPEC=1 forces it)
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
     int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
@@ -1106,8 +1110,10 @@ static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, 
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
                              float norm_eps = 0.f, bool post_to_host = false) {
-    const int grid = (int)((env->n_envs + BS - 1) / BS);
-    HostSignal sig = {nullptr, nullptr, 0u, env->dbg_times};
+    const int epw = env->dbg_times ? 32 : env->sim_epw;   // (the block stamps are sized for full warps)
+    const int per_block = (BS / 32) * epw;
+    const int grid = (int)((env->n_envs + per_block - 1) / per_block);
+    HostSignal sig = {nullptr, nullptr, 0u, env->dbg_times, epw};
     if (post_to_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
     const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
     if (is_step && env->sim_spec == 3)
@@ -1269,6 +1275,16 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         {   // AT_NO_SPEC=1: generic kernel; 2 / 3: stop below that specialisation level
             const char *ns = getenv("AT_NO_SPEC");
             env->sim_spec = sim_spec_for(k, ns && ns[0] >= '1' && ns[0] <= '3' ? ns[0] - '1' : 3);
+        }
+        {   // envs per warp: spread a small batch until every warp scheduler (4 per SM) has one warp - measured on a
+            // B200 (profiles/r06_small_batches.md): 256 envs 0.104 -> 0.059 ms, 4096 envs 0.112 -> 0.092 ms per tick;
+            // past one warp per scheduler the spread costs more (the warps contend) than the shorter paths save
+            const char *ep = getenv("AT_SIM_EPW");
+            const int64_t slots = (int64_t)prop.multiProcessorCount * 4;
+            int epw = 1;
+            while (epw < 32 && (n_envs + epw - 1) / epw > slots) epw *= 2;
+            if (ep && atoi(ep) >= 1 && atoi(ep) <= 32) epw = atoi(ep);
+            env->sim_epw = epw;
         }
         const int RD = k.rows * k.obs_dim;
         const char *ww = getenv("AT_ROWS_WARPS");
