@@ -42,9 +42,17 @@ ENV_STATE_DT = np.dtype([("n_bullets", "i4"), ("tick", "i4"), ("training_step", 
 EXPORTS = ("at_create at_destroy at_obs_dim at_obs_rows at_action_rows at_num_walls at_num_envs at_reset at_step at_step_norm "
            "at_step_host at_get_info at_get_terminal_info at_get_state at_set_state at_synthetic_actions at_bfs_batch at_generate_mazes "
            "at_get_luts at_tick_normalize at_sample_heads at_policy_tail at_policy_mid_tail at_debug_block_times at_set_weakness at_launch_count at_last_error at_version "
-           "at_observe at_set_reward_mode at_get_tank_columns at_forget_host_buffers at_policy_first").split()
+           "at_observe at_set_reward_mode at_get_tank_columns at_forget_host_buffers at_policy_first at_policy_forward at_obs_static_range").split()
 
 _lib = None
+
+
+class AtPolicy(C.Structure):
+    """include/alphatank_b200.h: at_policy (one policy's operands and outputs for at_policy_forward)."""
+    _fields_ = [("x", C.c_void_p), ("x_row_stride", C.c_int64),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p), ("w3", C.c_void_p), ("b3", C.c_void_p),
+                ("actions", C.c_void_p), ("act_stride", C.c_int64), ("logprobs", C.c_void_p), ("lp_stride", C.c_int64),
+                ("values", C.c_void_p), ("val_stride", C.c_int64), ("out9", C.c_void_p), ("stream_id", C.c_uint32)]
 
 
 class NativeLibraryMissing(RuntimeError):
@@ -88,6 +96,8 @@ def lib():
     L.at_get_tank_columns.argtypes = [vp, i32, vp, vp]
     L.at_forget_host_buffers.argtypes = [vp]
     L.at_policy_first.argtypes = [i32, vp, i64, i64, i32, vp, vp, vp, vp]
+    L.at_policy_forward.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, vp]
+    L.at_obs_static_range.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.at_tick_normalize.argtypes = [i32, vp, i64, i32, i32, C.c_float, vp, vp]
     L.at_debug_block_times.argtypes = [vp, vp]
     L.at_policy_mid_tail.argtypes = [i32, vp, vp, vp, vp, vp, vp, i64, C.c_uint64, vp, C.c_uint32, vp, i64, vp, i64, vp, i64, vp]

@@ -174,6 +174,13 @@ class BatchedTankEnv:
                                         C.c_void_p(self._h_done.data_ptr()), self._stream()), "at_step_host")
         return self.obs, self._h_rewards, self._h_done
 
+    def static_obs_range(self):
+        """(lo, hi): observation columns [lo, hi) of every row never change while this env lives (the wall / maze
+        block of a fixed map); lo == hi for per-env mazes."""
+        lo, hi = C.c_int32(0), C.c_int32(0)
+        _capi.check(self.L.at_obs_static_range(self.h, C.byref(lo), C.byref(hi)), "at_obs_static_range")
+        return int(lo.value), int(hi.value)
+
     def synthetic_actions(self, tick, out=None):
         out = self._actions if out is None else out
         _capi.check(self.L.at_synthetic_actions(self.h, int(tick), _ptr(out), self._stream()), "at_synthetic_actions")

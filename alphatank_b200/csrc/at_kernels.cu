@@ -1754,6 +1754,66 @@ int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t 
     return AT_OK;
 }
 
+int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
+                      const int64_t *d_counter, void *stream) {
+    if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % 4 != 0 || dim > 1024)
+        return fail(AT_ERR_ARG, "at_policy_forward: 1 or 2 policies, dim a multiple of 4 up to 1024");
+    const int k_chunks = (dim + at_tc::KC - 1) / at_tc::KC;
+    const uint32_t all = k_chunks >= 32 ? 0xFFFFFFFFu : ((1u << k_chunks) - 1u);
+    if (chunk_mask == 0) chunk_mask = all;
+    if (chunk_mask & ~all) return fail(AT_ERR_ARG, "at_policy_forward: chunk_mask names columns past dim");
+    DeviceGuard guard(device);
+    CUDA_TRY(guard.status());
+    at_tc::PolicyFwd P;
+    memset(&P, 0, sizeof P);
+    CUtensorMap maps[6];
+    for (int i = 0; i < 2; ++i) {
+        const at_policy &q = pol[i < n_policies ? i : 0];
+        if (!q.x || !q.w1 || !q.b1 || !q.w2 || !q.b2 || !q.w3 || !q.b3 || !q.actions || !q.logprobs || !q.values ||
+            q.x_row_stride % 4 != 0 || q.x_row_stride < dim)
+            return fail(AT_ERR_ARG, "at_policy_forward: null buffer or a row stride that is not a multiple of 4 floats");
+        if ((((uintptr_t)q.x) | ((uintptr_t)q.w1) | ((uintptr_t)q.w2)) & 15u)
+            return fail(AT_ERR_ARG, "at_policy_forward: x / w1 / w2 must be 16-byte aligned");
+        if (!at_tc::make_map_2d(&maps[i], q.x, (uint64_t)n_rows, (uint64_t)dim, (uint64_t)q.x_row_stride * 4, at_tc::TM) ||
+            !at_tc::make_map_2d(&maps[2 + i], q.w1, 512, (uint64_t)dim, (uint64_t)dim * 4, 256) ||
+            !at_tc::make_map_2d(&maps[4 + i], q.w2, 512, 128, 128 * 4, 128))
+            return fail(AT_ERR_CUDA, "at_policy_forward: cuTensorMapEncodeTiled is not available or rejected the tensors");
+        at_tc::PolicyIO &io = P.io[i];
+        io.b1 = q.b1; io.b2 = q.b2; io.w3 = q.w3; io.b3 = q.b3;
+        io.actions = q.actions; io.logprobs = q.logprobs; io.values = q.values; io.out9 = q.out9;
+        io.act_stride = q.act_stride; io.lp_stride = q.lp_stride; io.val_stride = q.val_stride;
+        io.stream_id = q.stream_id;
+    }
+    P.n_rows = n_rows;
+    P.tiles_per_policy = (int)((n_rows + at_tc::TM - 1) / at_tc::TM);
+    P.n_policies = n_policies;
+    P.chunk_mask = chunk_mask;
+    P.seed = seed;
+    P.counter = d_counter;
+    static bool attr_set[64] = {false};
+    static int sms[64] = {0};
+    if (device < 0 || device >= 64) return fail(AT_ERR_ARG, "at_policy_forward: device index out of range");
+    if (!attr_set[device]) {
+        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::F_SMEM_BYTES));
+        CUDA_TRY(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
+        attr_set[device] = true;
+    }
+    const int n_tiles = P.tiles_per_policy * n_policies;
+    const int grid = n_tiles < sms[device] ? n_tiles : sms[device];
+    at_tc::policy_forward_kernel<<<grid, at_tc::F_THREADS, at_tc::F_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                                                     maps[4], maps[5], P);
+    CUDA_TRY(cudaGetLastError());
+    return AT_OK;
+}
+
+int at_obs_static_range(const at_env *env, int32_t *lo, int32_t *hi) {
+    if (!env || !lo || !hi) return fail(AT_ERR_ARG, "at_obs_static_range: null argument");
+    // walls + maze columns of a fixed map never change (gym_env_multi.py:283-292); per-env mazes do
+    *lo = env->k.off_walls;
+    *hi = env->k.map == AT_MAP_MAZE ? env->k.off_walls : env->k.off_zones;
+    return AT_OK;
+}
+
 int at_debug_block_times(at_env *env, unsigned long long *d_times) {
     if (!env) return fail(AT_ERR_ARG, "at_debug_block_times: null handle");
     env->dbg_times = d_times;   // [2 * ceil(n_envs / 64)] device words, or NULL to switch the stamps off

@@ -20,7 +20,7 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from .ppo_utils import PPOAgentPPO, RunningMeanStd, tick_normalize
+from .ppo_utils import FusedPolicies, PPOAgentPPO, RunningMeanStd, tick_normalize
 
 
 @dataclasses.dataclass
@@ -107,6 +107,39 @@ class PPOLearner:
         self.optimizers = [torch.optim.Adam(a.parameters(), lr=self.cfg.learning_rate, eps=self.cfg.adam_eps)
                            for a in self.agents]
         self.running = [RunningMeanStd((obs_dim,), device=self.device) for _ in range(num_agents)]
+        self._fused = None            # FusedPolicies per pair of agents (cuda: at_policy_forward), False: not available
+        self._static = None
+
+    # ---- the tcgen05 inference path (csrc/at_policy_tc.cuh)
+    def fused_policies(self):
+        """The agents packed for at_policy_forward (two per launch), or None where that path does not apply (CPU, another
+        architecture than the reference's, AT_NO_POLICY_TC=1: the per-layer kernels of sample_cuda take over)."""
+        if self._fused is None:
+            self._fused = False
+            if self.device.type == "cuda" and not os.environ.get("AT_NO_POLICY_TC") and \
+                    torch.cuda.get_device_capability(self.device)[0] == 10:
+                try:
+                    self._fused = [FusedPolicies(self.agents[i:i + 2], self.D, self.device) for i in range(0, self.A, 2)]
+                except ValueError:
+                    self._fused = False
+                if self._fused and self._static is not None:
+                    self.set_static_columns(*self._static)
+        return self._fused or None
+
+    def set_static_columns(self, lo, hi, y):
+        """Observation columns [lo, hi) hold y[i, lo:hi] in every row agent i will ever see (BatchedTankEnv.
+        static_obs_range + one normalised row): the fused inference path folds them into the first layers' bias.
+        Only meaningful for stateless normalisers ("tick" / "none")."""
+        self._static = (int(lo), int(hi), y.detach().clone())
+        if self._fused:
+            for k, f in enumerate(self._fused):
+                f.set_static(int(lo), int(hi), self._static[2][2 * k:2 * k + 2])
+
+    def refresh_inference(self):
+        """Re-pack the inference weights after the parameters changed (update() and load_state_dict callers)."""
+        if self._fused:
+            for f in self._fused:
+                f.refresh()
 
     # ---- acting
     def normalize(self, raw_obs, update=True, out=None):
@@ -128,20 +161,33 @@ class PPOLearner:
         return x
 
     @torch.no_grad()
-    def act(self, obs_nad):
-        """obs [N, A, D] -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]."""
+    def act(self, obs_nad, out=None):
+        """obs [N, A, D] -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A] (written into ``out`` = the
+        three tensors when given, e.g. a rollout buffer's slots)."""
         if obs_nad.is_cuda:   # one sampling kernel per policy, written in place (at_sample_heads)
             n, heads = obs_nad.shape[0], len(self.agents[0].actor)
-            acts = torch.empty((n, self.A, heads), dtype=torch.int32, device=obs_nad.device)
-            lps = torch.empty((n, self.A, heads), dtype=torch.float32, device=obs_nad.device)
+            if out is not None:
+                acts, lps, vals = out
+            else:
+                acts = torch.empty((n, self.A, heads), dtype=torch.int32, device=obs_nad.device)
+                lps = torch.empty((n, self.A, heads), dtype=torch.float32, device=obs_nad.device)
+                vals = torch.empty((n, self.A), dtype=torch.float32, device=obs_nad.device)
             if getattr(self, "_sample_ctr", None) is None:
                 self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
             self._sample_ctr.add_(1)
-            vals = torch.empty((n, self.A), dtype=torch.float32, device=obs_nad.device)
+            fused = self.fused_policies()
+            if fused is not None and self.cfg.obs_norm == "running" and fused[0].chunk_mask:
+                raise RuntimeError("static-column folding needs a stateless observation normaliser")
+            if fused is not None:   # the whole forward + sampling of two policies per launch (tcgen05, at_policy_forward)
+                for k, f in enumerate(fused):
+                    f.forward(obs_nad[:, 2 * k:2 * k + 2], acts[:, 2 * k:2 * k + 2], lps[:, 2 * k:2 * k + 2], vals[:, 2 * k:2 * k + 2],
+                              self._sample_ctr, self.seed, 2 * k + self.A * _rank())
+                return acts, lps, vals
             for i, agent in enumerate(self.agents):
                 agent.sample_cuda(obs_nad[:, i], acts[:, i], lps[:, i], self._sample_ctr, self.seed, i + self.A * _rank(),
                                   values_out=vals[:, i])
             return acts, lps, vals
+        assert out is None or not obs_nad.is_cuda
         acts, lps, vals = [], [], []
         for i, agent in enumerate(self.agents):
             a, lp, v = agent.sample(obs_nad[:, i])
@@ -204,6 +250,7 @@ class PPOLearner:
                     opt.step()
                     last = {"policy_loss": pg.detach(), "value_loss": v_loss.detach(), "entropy": ent.detach()}
             stats.append({k: float(v) for k, v in last.items()})
+        self.refresh_inference()
         return stats
 
 
@@ -232,11 +279,18 @@ def collect_rollout(env, learner, buf, first=False):
     prev_cum = getattr(buf, "_prev_cum", None)
     if prev_cum is None or first:
         prev_cum = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.obs.device)
+    if first and buf.obs.is_cuda and learner.cfg.obs_norm in ("tick", "none") and hasattr(core, "static_obs_range"):
+        lo, hi = core.static_obs_range()        # fixed maps: the wall / maze block is the same in every row for ever
+        if hi > lo:
+            learner.set_static_columns(lo, hi, buf.obs[0][0])
     for t in range(T):
-        a, lp, v = learner.act(buf.obs[t])
-        buf.actions[t].copy_(a)
-        buf.logprobs[t].copy_(lp)
-        buf.values[t].copy_(v)
+        if buf.obs.is_cuda:
+            learner.act(buf.obs[t], out=(buf.actions[t], buf.logprobs[t], buf.values[t]))
+        else:
+            a, lp, v = learner.act(buf.obs[t])
+            buf.actions[t].copy_(a)
+            buf.logprobs[t].copy_(lp)
+            buf.values[t].copy_(v)
         if fused:
             core.step_norm(buf.actions[t], buf.obs[t + 1], obs_out=buf.raw_obs[t + 1] if buf.keep_raw else None,
                            rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])

@@ -189,5 +189,104 @@ class PPOAgentPPO(nn.Module):
         return action, logprobs, entropy, self.critic(x)
 
 
+def _round_tf32_(w):
+    """Round an fp32 tensor to the nearest TF32 value in place (10-bit mantissa): the tensor core truncates its fp32
+    operands, rounding the weights once on the host keeps their error unbiased."""
+    bits = w.view(torch.int32)
+    bits.add_(0x1000).bitwise_and_(~0x1FFF)
+    return w
+
+
+class FusedPolicies:
+    """The inference side of up to two PPOAgentPPO policies on the tcgen05 tensor cores (csrc/at_policy_tc.cuh through
+    at_policy_forward): one kernel launch samples actions / log-probabilities / values for all of them.  The weights
+    are packed once into static tensors (``refresh()`` after every optimiser step re-packs them in place, so a
+    captured CUDA graph keeps reading the right storage).
+
+    ``static``: (lo, hi, y) - observation columns [lo, hi) are the same for every row the policies will ever see and
+    hold the values y[i, lo:hi] for agent i (the wall / maze block of a fixed map after the stateless per-tick
+    normaliser).  K chunks of 32 columns that lie inside that range are dropped from the first layers' contraction and
+    their contribution W1[:, chunk] . y is folded into the bias."""
+
+    def __init__(self, agents, obs_dim, device):
+        assert 1 <= len(agents) <= 2
+        self.agents, self.D, self.device = list(agents), int(obs_dim), torch.device(device)
+        for a in self.agents:
+            nets = [a.critic] + list(a.actor)
+            if [int(m[4].out_features) for m in nets] != [1, 3, 3, 2] or any(m[0].out_features != 128 or m[2].out_features != 128 for m in nets):
+                raise ValueError("at_policy_forward serves the reference architecture only (128 hidden units, heads 3 / 3 / 2)")
+        if self.D % 4 != 0 or self.D > 1024:
+            raise ValueError("at_policy_forward needs an observation width that is a multiple of 4, up to 1024")
+        n = len(self.agents)
+        f = dict(dtype=torch.float32, device=self.device)
+        self.w1 = torch.empty((n, 512, self.D), **f)
+        self.b1 = torch.empty((n, 512), **f)
+        self.w2 = torch.empty((n, 4, 128, 128), **f)
+        self.b2 = torch.empty((n, 4, 128), **f)
+        self.w3 = torch.empty((n, 9, 128), **f)
+        self.b3 = torch.empty((n, 9), **f)
+        self.chunk_mask = 0          # 0 = every chunk
+        self._fold_cols = None
+        self._fold_y = None
+        self.refresh()
+
+    def set_static(self, lo, hi, y):
+        """y: [n_agents, D] the constant columns' values as the policies see them (only [lo, hi) is read)."""
+        k_chunks = (self.D + 31) // 32
+        keep = [c for c in range(k_chunks) if not (lo <= 32 * c and min(32 * c + 32, self.D) <= hi)]
+        if len(keep) == k_chunks:
+            self.chunk_mask, self._fold_cols, self._fold_y = 0, None, None
+        else:
+            drop = [c for c in range(k_chunks) if c not in keep]
+            cols = torch.cat([torch.arange(32 * c, min(32 * c + 32, self.D)) for c in drop]).to(self.device)
+            self.chunk_mask = sum(1 << c for c in keep)
+            self._fold_cols = cols
+            self._fold_y = y.to(self.device, torch.float32)[:, cols].contiguous()
+        self.refresh()
+
+    @torch.no_grad()
+    def refresh(self):
+        for i, a in enumerate(self.agents):
+            nets = [a.critic] + list(a.actor)
+            w1 = torch.cat([m[0].weight for m in nets], dim=0)
+            b1 = torch.cat([m[0].bias for m in nets], dim=0)
+            if self._fold_cols is not None:      # fp32 fold of the dropped columns (exact weights, before the TF32 rounding)
+                b1 = b1 + w1[:, self._fold_cols] @ self._fold_y[i]
+            self.w1[i].copy_(w1)
+            self.b1[i].copy_(b1)
+            self.w2[i].copy_(torch.stack([m[2].weight for m in nets]))
+            self.b2[i].copy_(torch.stack([m[2].bias for m in nets]))
+            self.w3[i].copy_(torch.cat([m[4].weight for m in nets], dim=0))
+            self.b3[i].copy_(torch.cat([m[4].bias for m in nets], dim=0))
+        _round_tf32_(self.w1)
+        _round_tf32_(self.w2)
+
+    def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None):
+        """obs [N, A, D] (A = the number of packed policies) -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]
+        written in place; ``counter``: device int64 [1] the caller advances once per tick; ``out9``: optional
+        [A, N, 9] (value + 8 logits per row)."""
+        import ctypes as C
+
+        from .. import _capi
+        n, A = obs_nad.shape[0], len(self.agents)
+        assert obs_nad.shape[1] == A and obs_nad.shape[2] == self.D and obs_nad.stride(2) == 1 and obs_nad.dtype == torch.float32
+        assert actions_out.dtype == torch.int32 and actions_out.stride(-1) == 1 and logprobs_out.stride(-1) == 1
+        pols = (_capi.AtPolicy * A)()
+        for i in range(A):
+            x, a, lp, v = obs_nad[:, i], actions_out[:, i], logprobs_out[:, i], values_out[:, i]
+            q = pols[i]
+            q.x, q.x_row_stride = x.data_ptr(), x.stride(0)
+            q.w1, q.b1, q.w2, q.b2 = self.w1[i].data_ptr(), self.b1[i].data_ptr(), self.w2[i].data_ptr(), self.b2[i].data_ptr()
+            q.w3, q.b3 = self.w3[i].data_ptr(), self.b3[i].data_ptr()
+            q.actions, q.act_stride = a.data_ptr(), a.stride(0)
+            q.logprobs, q.lp_stride = lp.data_ptr(), lp.stride(0)
+            q.values, q.val_stride = v.data_ptr(), v.stride(0)
+            q.out9 = out9[i].data_ptr() if out9 is not None else None
+            q.stream_id = int(stream_base) + i
+        _capi.check(_capi.lib().at_policy_forward(
+            obs_nad.device.index, pols, A, n, self.D, int(self.chunk_mask), int(seed), C.c_void_p(counter.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream(obs_nad.device).cuda_stream)), "at_policy_forward")
+
+
 class PPOAgentBot(PPOAgentPPO):
     """models/ppo_utils.py:64-94 (identical architecture; the 1v1-vs-bot trainers use this name)."""

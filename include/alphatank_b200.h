@@ -237,6 +237,35 @@ int at_policy_mid_tail(int device, const float *d_z1, const float *d_w2, const f
 int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t n_rows, int dim, const float *d_w1,
                     const float *d_b1, float *d_z1, void *stream);
 
+/* A policy's whole inference pass in one kernel on the tcgen05 tensor cores (models/ppo_utils.py:31-62 - critic + three
+ * action heads, D -> 128 -> 128 -> {1, 3, 3, 2} - as train_multi_ppo.py:96-116 calls get_action_and_value per tank):
+ * TMA-loaded observation tiles -> first layers (TF32 multiply, fp32 accumulate in tensor memory) -> tanh -> second
+ * layers -> tanh -> output layers -> log-softmax -> Gumbel-max draw (the Philox stream of at_sample_heads).  Neither the
+ * [N, 512] activations nor the logits go to HBM.  One launch serves 1 or 2 policies of n_rows rows each.
+ *   x            n_rows rows of `dim` floats, x_row_stride floats apart (a column slice of [N][A][D] as it is)
+ *   w1 / b1      float[512][dim] / float[512]: the four first layers side by side (critic, head 0, 1, 2)
+ *   w2 / b2      float[4][128][128] / float[4][128];   w3 / b3: float[9][128] / float[9] (value; 3 + 3 + 2 logits)
+ *   out9         optional float[n_rows][9]: value and the 8 logits
+ * chunk_mask: bit c set = columns 32 c .. 32 c + 31 take part in the first layers' contraction (0 = all).  Columns that
+ * are constant for the handle's lifetime (at_obs_static_range) may be left out when their contribution W1[:, cols] . x
+ * is added to b1 by the caller - 2v2 rows: 9 of 17 chunks remain.  Precision: TF32 operands (x truncated, the hidden
+ * activations rounded to nearest), fp32 accumulation, tanh.approx (relative error 2^-11). */
+typedef struct at_policy {
+    const float *x; int64_t x_row_stride;
+    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    int32_t *actions; int64_t act_stride;
+    float *logprobs; int64_t lp_stride;
+    float *values; int64_t val_stride;
+    float *out9;
+    uint32_t stream_id;
+} at_policy;
+int at_policy_forward(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
+                      uint64_t seed, const int64_t *d_counter, void *stream);
+
+/* Observation columns [lo, hi) of every row that never change while the handle lives (the wall rectangles and the maze
+ * block of a fixed map, gym_env_multi.py:283-292); lo == hi for per-env mazes. */
+int at_obs_static_range(const at_env *env, int32_t *lo, int32_t *hi);
+
 /* Diagnostics: while d_times (device, uint64[2 * ceil(n_envs / 64)]) is set, every block of the simulation kernel
  * stamps %globaltimer (ns) at its start and end into it; NULL switches the stamps off.  Used to study how the blocks'
  * finishing times spread (profiles/). */

@@ -1,6 +1,7 @@
 """GPU (-m gpu): the PPO rollout / update loop on the CUDA env step and the checkpoint file
 (row 2).  The rollout writes env outputs straight into the rollout storage; replaying its recorded actions through
 a second env handle must reproduce every stored observation / reward / done bit for bit."""
+import copy
 import os
 import sys
 
@@ -289,3 +290,148 @@ def test_policy_first_layers_on_tcgen05_match_the_fp32_reference(n_rows):
         assert torch.isfinite(z).all()
         scale = (x.abs().double() @ w1.abs().double().t()).float() + 1.0
         assert ((z - ref).abs() / scale).max().item() < 2e-3
+
+
+def _scaled_agents(A, D, dev, seed=0):
+    """Policies whose logits / values are O(1) (the reference's init gives ~0.01 logits: too small to test against)."""
+    from alphatank_b200.learner.ppo_utils import PPOAgentPPO
+    torch.manual_seed(seed)
+    agents = [PPOAgentPPO(D).to(dev) for _ in range(A)]
+    with torch.no_grad():
+        for a in agents:
+            for net in [a.critic] + list(a.actor):
+                net[0].weight.normal_(0, 1.0 / 23.0); net[0].bias.normal_(0, 0.3)
+                net[2].weight.normal_(0, 1.5 / 11.3); net[2].bias.normal_(0, 0.3)
+                net[4].weight.normal_(0, 2.0 / 11.3); net[4].bias.normal_(0, 0.3)
+    return agents
+
+
+def _fp64_out9(agent, x):
+    a64 = copy.deepcopy(agent).double()
+    x = x.double()
+    return torch.cat([a64.critic(x)] + [h(x) for h in a64.actor], dim=-1)
+
+
+@pytest.mark.parametrize("n_rows", [128, 1000, 40000])
+def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows):
+    """at_policy_forward (csrc/at_policy_tc.cuh: the whole inference pass of two policies in one tcgen05 kernel) against
+    the fp64 forward of the same modules.  Precision of the path: TF32 operands (10-bit mantissa) in both hidden layers,
+    fp32 accumulation, tanh.approx (2^-11) - tolerance 1e-2 on values / logits that are O(1) (measured: ~2e-3);
+    the chosen action's log-probability must be the log-softmax of the kernel's own logits to 1e-5."""
+    from alphatank_b200.learner.ppo_utils import FusedPolicies
+    dev = torch.device("cuda:0")
+    D, A = 528, 2
+    agents = _scaled_agents(A, D, dev)
+    torch.manual_seed(1)
+    obs = torch.randn((n_rows, A, D), device=dev)
+    obs[:, :, 100:180] = 0.0
+    fp = FusedPolicies(agents, D, dev)
+    acts = torch.full((n_rows, A, 3), -1, dtype=torch.int32, device=dev)
+    lps = torch.full((n_rows, A, 3), float("nan"), device=dev)
+    vals = torch.full((n_rows, A), float("nan"), device=dev)
+    out9 = torch.full((A, n_rows, 9), float("nan"), device=dev)
+    ctr = torch.ones(1, dtype=torch.int64, device=dev)
+    fp.forward(obs, acts, lps, vals, ctr, seed=7, out9=out9)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out9).all() and torch.isfinite(lps).all() and torch.isfinite(vals).all()
+    for i in range(A):
+        ref = _fp64_out9(agents[i], obs[:, i]).float()
+        err = (out9[i] - ref).abs().max().item()
+        assert ref.abs().mean().item() > 0.2      # the comparison means something
+        assert err < 1e-2, err
+        assert torch.equal(vals[:, i], out9[i][:, 0])
+        for h, (lo, d) in enumerate(((1, 3), (4, 3), (7, 2))):
+            lp_all = torch.log_softmax(out9[i][:, lo:lo + d], dim=-1)
+            a = acts[:, i, h].long()
+            assert int(a.min()) >= 0 and int(a.max()) < d
+            assert (lp_all.gather(-1, a.unsqueeze(-1)).squeeze(-1) - lps[:, i, h]).abs().max().item() < 1e-5
+
+
+def test_policy_forward_draws_follow_the_softmax():
+    """Identical rows -> identical logits; the Gumbel-max draws over 200 000 rows must reproduce softmax(logits) per head
+    (4 sigma of the binomial), and a second tick (counter advanced) must draw differently."""
+    from alphatank_b200.learner.ppo_utils import FusedPolicies
+    dev = torch.device("cuda:0")
+    D, n = 528, 200_000
+    agents = _scaled_agents(1, D, dev, seed=3)
+    torch.manual_seed(2)
+    obs = torch.randn((1, 1, D), device=dev).expand(n, 1, D).contiguous()
+    fp = FusedPolicies(agents, D, dev)
+    out9 = torch.zeros((1, n, 9), device=dev)
+    draws = []
+    for tick in (1, 2):
+        acts = torch.zeros((n, 1, 3), dtype=torch.int32, device=dev)
+        lps, vals = torch.zeros((n, 1, 3), device=dev), torch.zeros((n, 1), device=dev)
+        fp.forward(obs, acts, lps, vals, torch.full((1,), tick, dtype=torch.int64, device=dev), seed=11, out9=out9)
+        draws.append(acts.clone())
+        assert (out9[0] - out9[0][0:1]).abs().max().item() == 0.0
+        for h, (lo, d) in enumerate(((1, 3), (4, 3), (7, 2))):
+            p = torch.softmax(out9[0][0, lo:lo + d].double(), dim=-1)
+            freq = torch.bincount(acts[:, 0, h].long(), minlength=d).double() / n
+            assert ((freq - p).abs() < 4 * (p * (1 - p) / n).sqrt() + 1e-4).all(), (h, freq, p)
+    assert (draws[0] != draws[1]).any()
+
+
+def test_policy_forward_folds_constant_columns_into_the_bias():
+    """Columns that are the same in every row (the wall / maze block of a fixed map) dropped from the contraction and
+    folded into the first layers' bias: 9 of 17 K chunks remain for the 2v2 rows, same result to TF32 accuracy."""
+    from alphatank_b200.learner.ppo_utils import FusedPolicies
+    dev = torch.device("cuda:0")
+    D, A, n = 528, 2, 3000
+    agents = _scaled_agents(A, D, dev, seed=5)
+    torch.manual_seed(4)
+    obs = torch.randn((n, A, D), device=dev)
+    const = torch.randn((A, D), device=dev)
+    obs[:, :, 237:518] = const[:, 237:518]
+    res = []
+    for fold in (False, True):
+        fp = FusedPolicies(agents, D, dev)
+        if fold:
+            fp.set_static(237, 518, const)
+            assert fp.chunk_mask == 0x100FF
+        out9 = torch.zeros((A, n, 9), device=dev)
+        acts = torch.zeros((n, A, 3), dtype=torch.int32, device=dev)
+        fp.forward(obs, acts, torch.zeros((n, A, 3), device=dev), torch.zeros((n, A), device=dev),
+                   torch.ones(1, dtype=torch.int64, device=dev), seed=1, out9=out9)
+        res.append(out9)
+    for i in range(A):
+        ref = _fp64_out9(agents[i], obs[:, i]).float()
+        assert (res[1][i] - ref).abs().max().item() < 1e-2
+        assert (res[0][i] - ref).abs().max().item() < 1e-2
+
+
+def test_rollout_on_the_fused_policies_matches_the_per_layer_path():
+    """collect_rollout with the tcgen05 inference path (static columns folded) against the same rollout on the per-layer
+    kernels (AT_NO_POLICY_TC): the first tick's values agree to TF32 accuracy and the rollout is self-consistent
+    (stored log-probabilities are the policies' own, to 5e-3, when re-evaluated in fp32 on the stored observations)."""
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, collect_rollout
+    dev = torch.device("cuda:0")
+    N, T = 2048, 6
+    vals = []
+    for no_tc in ("", "1"):
+        if no_tc:
+            os.environ["AT_NO_POLICY_TC"] = "1"
+        try:
+            env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=3)
+            A = len(env.get_observation_order())
+            D = env.observation_space.shape[0] // A
+            learner = PPOLearner(A, D, (3, 3, 2), PPOConfig(num_steps=T), dev, seed=0)
+            buf = RolloutBuffer(T, N, A, D, dev, keep_raw=False)
+            collect_rollout(env, learner, buf, first=True)
+            torch.cuda.synchronize()
+            if not no_tc:
+                assert learner.fused_policies() is not None and learner.fused_policies()[0].chunk_mask == 0x100FF
+                for i, agent in enumerate(learner.agents):
+                    x = buf.obs[:T, :, i].reshape(T * N, D)
+                    _, lp, _, v = agent.get_action_and_value(x, buf.actions[:, :, i].reshape(T * N, 3))
+                    assert (lp - buf.logprobs[:, :, i].reshape(T * N, 3)).abs().max().item() < 5e-3
+                    assert (v.squeeze(-1) - buf.values[:T, :, i].reshape(T * N)).abs().max().item() < 5e-3
+            else:
+                assert learner.fused_policies() is None
+            vals.append(buf.values[0].clone())
+            env.close()
+        finally:
+            os.environ.pop("AT_NO_POLICY_TC", None)
+    assert (vals[0] - vals[1]).abs().max().item() < 5e-3
