@@ -285,37 +285,50 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_c
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // Order of the tensor-core work of a CTA with local tiles 0 .. m - 1 (the producer fills the ring in the same order):
+    //   L1(0, h0) L1(0, h1)   then per tile i:   L2(i, n0) L2(i, n1) L2(i, n2) L1(i + 1, h0) L2(i, n3) L1(i + 1, h1)
+    // - the next tile's first layers fill the tensor core while the epilogue works down the current tile's networks.
+    const int m_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer
             uint32_t g = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            auto slot = [&](uint32_t bytes) -> unsigned char * {
+                const uint32_t s = g % F_STAGES;
+                if (g >= F_STAGES) mbar_wait(empty + s, ((g / F_STAGES) - 1) & 1);
+                mbar_expect_tx(full + s, bytes);
+                return smem + (size_t)s * F_STAGE_BYTES;
+            };
+            auto l1 = [&](int i, int h) {
+                const int tile = blockIdx.x + i * gridDim.x;
                 const int p = tile / P.tiles_per_policy, row0 = (tile - p * P.tiles_per_policy) * TM;
-                const CUtensorMap *mx = p ? &map_x1 : &map_x0, *mw1 = p ? &map_w1_1 : &map_w1_0, *mw2 = p ? &map_w2_1 : &map_w2_0;
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t m = P.chunk_mask;
-                    while (m) {
-                        const int c = __ffs(m) - 1;
-                        m &= m - 1;
-                        const uint32_t s = g % F_STAGES;
-                        if (g >= F_STAGES) mbar_wait(empty + s, ((g / F_STAGES) - 1) & 1);
-                        unsigned char *sa = smem + (size_t)s * F_STAGE_BYTES;
-                        mbar_expect_tx(full + s, F_STAGE_BYTES);
-                        tma_load_2d(sa, mx, full + s, c * KC, row0);
-                        tma_load_2d(sa + FA_BYTES, mw1, full + s, c * KC, h * 256);
-                        ++g;
-                    }
+                const CUtensorMap *mx = p ? &map_x1 : &map_x0, *mw1 = p ? &map_w1_1 : &map_w1_0;
+                uint32_t m = P.chunk_mask;
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    unsigned char *sa = slot(F_STAGE_BYTES);
+                    tma_load_2d(sa, mx, full + g % F_STAGES, c * KC, row0);
+                    tma_load_2d(sa + FA_BYTES, mw1, full + g % F_STAGES, c * KC, h * 256);
+                    ++g;
                 }
-                for (int net = 0; net < 4; ++net)
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t s = g % F_STAGES;
-                        if (g >= F_STAGES) mbar_wait(empty + s, ((g / F_STAGES) - 1) & 1);
-                        unsigned char *sb = smem + (size_t)s * F_STAGE_BYTES + FA_BYTES;
-                        mbar_expect_tx(full + s, FB_BYTES);
-                        tma_load_2d(sb, mw2, full + s, (2 * half) * KC, net * 128);
-                        tma_load_2d(sb + FA_BYTES, mw2, full + s, (2 * half + 1) * KC, net * 128);
-                        ++g;
-                    }
+            };
+            auto l2 = [&](int i, int net) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const CUtensorMap *mw2 = tile / P.tiles_per_policy ? &map_w2_1 : &map_w2_0;
+                for (int half = 0; half < 2; ++half) {
+                    unsigned char *sb = slot(FB_BYTES) + FA_BYTES;
+                    tma_load_2d(sb, mw2, full + g % F_STAGES, (2 * half) * KC, net * 128);
+                    tma_load_2d(sb + FA_BYTES, mw2, full + g % F_STAGES, (2 * half + 1) * KC, net * 128);
+                    ++g;
+                }
+            };
+            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
+            for (int i = 0; i < m_tiles; ++i) {
+                l2(i, 0); l2(i, 1); l2(i, 2);
+                if (i + 1 < m_tiles) l1(i + 1, 0);
+                l2(i, 3);
+                if (i + 1 < m_tiles) l1(i + 1, 1);
             }
         }
     } else if (warp == 1) {
@@ -324,46 +337,50 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_c
             constexpr uint32_t idesc1 = umma_idesc_tf32(TM, 256), idesc2 = umma_idesc_tf32(TM, 128);
             const uint32_t h1a = smem_u32(h1);
             uint32_t g = 0;
-            int it = 0;
-            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                for (int h = 0; h < 2; ++h) {
-                    if (it > 0) {
-                        mbar_wait(acc_free + h, (uint32_t)((it - 1) & 1));
-                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    }
-                    for (int ci = 0; ci < n_chunks; ++ci) {
-                        const uint32_t s = g % F_STAGES;
-                        mbar_wait(full + s, (g / F_STAGES) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                        const uint32_t a0 = smem_u32(smem + (size_t)s * F_STAGE_BYTES), b0 = a0 + FA_BYTES;
+            auto l1 = [&](int i, int h) {
+                if (i > 0) {   // the epilogue has read the previous tile's results out of this half
+                    mbar_wait(acc_free + h, (uint32_t)((i - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                }
+                for (int ci = 0; ci < n_chunks; ++ci) {
+                    const uint32_t s = g % F_STAGES;
+                    mbar_wait(full + s, (g / F_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a0 = smem_u32(smem + (size_t)s * F_STAGE_BYTES), b0 = a0 + FA_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < KC / 8; ++kk)
+                        umma_tf32(tmem_base + h * 256, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
+                                  (ci > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(empty + s);
+                    ++g;
+                }
+                umma_commit(acc1_full + h);
+            };
+            auto l2 = [&](int i, int net) {
+                mbar_wait(h1_ready, (uint32_t)((4 * i + net) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t s = g % F_STAGES;
+                    mbar_wait(full + s, (g / F_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t b0 = smem_u32(smem + (size_t)s * F_STAGE_BYTES) + FA_BYTES;
+#pragma unroll
+                    for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
                         for (int kk = 0; kk < KC / 8; ++kk)
-                            umma_tf32(tmem_base + h * 256, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
-                                      (ci > 0 || kk > 0) ? 1u : 0u);
-                        umma_commit(empty + s);
-                        ++g;
-                    }
-                    umma_commit(acc1_full + h);
+                            umma_tf32(tmem_base + net * 128, umma_desc_sw128(h1a + (2 * half + cc) * FA_BYTES + kk * 32),
+                                      umma_desc_sw128(b0 + cc * FA_BYTES + kk * 32), idesc2, (half > 0 || cc > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(empty + s);
+                    ++g;
                 }
-                for (int net = 0; net < 4; ++net) {
-                    mbar_wait(h1_ready, (uint32_t)((4 * it + net) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    for (int half = 0; half < 2; ++half) {
-                        const uint32_t s = g % F_STAGES;
-                        mbar_wait(full + s, (g / F_STAGES) & 1);
-                        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                        const uint32_t b0 = smem_u32(smem + (size_t)s * F_STAGE_BYTES) + FA_BYTES;
-#pragma unroll
-                        for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                            for (int kk = 0; kk < KC / 8; ++kk)
-                                umma_tf32(tmem_base + net * 128, umma_desc_sw128(h1a + (2 * half + cc) * FA_BYTES + kk * 32),
-                                          umma_desc_sw128(b0 + cc * FA_BYTES + kk * 32), idesc2, (half > 0 || cc > 0 || kk > 0) ? 1u : 0u);
-                        umma_commit(empty + s);
-                        ++g;
-                    }
-                    umma_commit(l2_done);
-                }
+                umma_commit(l2_done);
+            };
+            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
+            for (int i = 0; i < m_tiles; ++i) {
+                l2(i, 0); l2(i, 1); l2(i, 2);
+                if (i + 1 < m_tiles) l1(i + 1, 0);
+                l2(i, 3);
+                if (i + 1 < m_tiles) l1(i + 1, 1);
             }
         }
     } else {
