@@ -156,6 +156,17 @@ class BatchedTankEnv:
                                         _ptr(dn), self._stream()), "at_step_norm")
         return obs_norm_out, rew, dn
 
+    def step_norm16(self, actions, obs_norm_out, obs_out=None, rewards_out=None, done_out=None, epsilon=1e-4):
+        """``step_norm`` with the normalised rows as fp16 (``obs_norm_out``: torch.float16, N * R * D elements): the same
+        fp32 values rounded to nearest - half the observation bytes, and what the tcgen05 policy kernel contracts."""
+        a = self._device_actions(actions)
+        rew = self.rewards if rewards_out is None else rewards_out
+        dn = self.done if done_out is None else done_out
+        assert obs_norm_out.dtype == torch.float16 and obs_norm_out.is_contiguous() and obs_norm_out.numel() == self.num_envs * self.R * self.D
+        _capi.check(self.L.at_step_norm16(self.h, _ptr(a), _ptr(obs_out), _ptr(obs_norm_out), float(epsilon), _ptr(rew),
+                                          _ptr(dn), self._stream()), "at_step_norm16")
+        return obs_norm_out, rew, dn
+
     def step_host(self, h_actions):
         """End-to-end variant: actions come from (pinned) HOST memory, rewards and done are returned in pinned
         host memory, observations stay in HBM.  Returns as soon as rewards / done have landed in host memory (the simulation

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "../../include/alphatank_b200.h"
+#include <cuda_fp16.h>
 #include "at_host.h"
 #include "at_sim.h"
 #include "at_rows.h"
@@ -247,12 +248,12 @@ constexpr int RK_MAX_WARPS = 16;   // warps per block: a launch parameter (block
 struct RowsSmem {   // per warp, after the block's trig table
     size_t off_img, off_nimg, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, off_jl, per_warp, total;
 };
-__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats, int warps, bool norm) {
+__host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_floats, int warps, int nimg_elem /* 0 | 4 | 2 bytes */) {
     RowsSmem L;
     size_t o = 0;
     const size_t S = (size_t)n * SLOTS_PER_TANK;
     L.off_img = o; o += ((size_t)G * row_floats * 4 + 127) & ~(size_t)127;
-    L.off_nimg = o; o += norm ? (((size_t)G * row_floats * 4 + 127) & ~(size_t)127) : 0;   // the normalised copy of the image
+    L.off_nimg = o; o += ((size_t)G * row_floats * nimg_elem + 127) & ~(size_t)127;   // the normalised copy of the image (fp32 / fp16)
     L.off_rx = o; o += (size_t)G * S * 8;
     L.off_ry = o; o += (size_t)G * S * 8;
     L.off_rm = o; o += (size_t)G * S * 8;
@@ -277,19 +278,22 @@ template <int NT, int NR, int TEAM, bool MAZE, int PP>
 __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                           const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                           const float *__restrict__ g_tmpl, int lgG, int n_groups,
-                                                          float *__restrict__ obs_norm, float norm_eps) {
+                                                          float *__restrict__ obs_norm, float norm_eps, int norm_half) {
     extern __shared__ __align__(128) unsigned char smem[];
     typedef RowsShape<NT, NR, TEAM> SH;
     // obs_norm: also emit (norm2: a second, normalised image) or only emit (inplace: obs == nullptr; the image is built
     // in full every group and normalised in place) the tick-normalised rows
-    const bool norm = obs_norm != nullptr, norm2 = norm && obs != nullptr, inplace = norm && obs == nullptr;
+    // norm_half: the normalised rows leave as fp16 (always through a second image: the raw one stays incremental)
+    const bool norm = obs_norm != nullptr, half_out = norm && norm_half != 0, norm2 = norm && (obs != nullptr || half_out),
+               inplace = norm && !norm2;
     const TickNormK nk(SH::rows(c), norm_eps);
     const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, nrows = SH::rows(c), RD = nrows * c.obs_dim;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-    const RowsSmem L = rows_smem_layout(G, n, RD, nwarps, norm2);
+    const RowsSmem L = rows_smem_layout(G, n, RD, nwarps, norm2 ? (half_out ? 2 : 4) : 0);
     double *trig = (double *)smem;
     unsigned char *ws = smem + 722 * 8 + 64 + (size_t)warp * L.per_warp;
     float *img = (float *)(ws + L.off_img), *nimg = norm2 ? (float *)(ws + L.off_nimg) : img;
+    __half *nimg16 = (__half *)(ws + L.off_nimg);
     double *rx = (double *)(ws + L.off_rx), *ry = (double *)(ws + L.off_ry);
     uint64_t *rm = (uint64_t *)(ws + L.off_rm);
     double *tx = (double *)(ws + L.off_tx), *ty = (double *)(ws + L.off_ty);
@@ -305,6 +309,8 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     for (int p = lane; p < G * S; p += 32) { rm[p] = ROWS_EMPTY; occ[p] = 0; }
     for (int i = lane; i < G * RD / 4; i += 32) reinterpret_cast<float4 *>(img)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int i = ((G * RD) & ~3) + lane; i < G * RD; i += 32) img[i] = 0.f;
+    if (half_out)   // the fp16 image starts out as zeros too (the static columns are filled in below)
+        for (int i = lane; i < (G * RD + 1) / 2; i += 32) reinterpret_cast<uint32_t *>(nimg16)[i] = 0u;
     __syncwarp();
     constexpr int RMAX = NR ? NR : MAX_TANKS;
     if (!MAZE) {
@@ -321,13 +327,14 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
             }
             for (int gr = 0; gr < G * nrows; ++gr) {   // gr = env * rows + row
                 if (!inplace) img[gr * c.obs_dim + c.off_walls + q] = v;
-                if (norm) nimg[gr * c.obs_dim + c.off_walls + q] = vn;
+                if (half_out) nimg16[gr * c.obs_dim + c.off_walls + q] = __float2half_rn(vn);
+                else if (norm) nimg[gr * c.obs_dim + c.off_walls + q] = vn;
             }
         }
     }
     // columns the normaliser visits per group: [0, off_walls) and [dyn2, D) (everything for per-env maps)
     const int dyn2 = MAZE ? c.off_walls : c.off_zones, ndyn = c.off_walls + (c.obs_dim - dyn2);
-    const bool bulk_ok = (((size_t)RD * 4) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0) && ((((uintptr_t)obs_norm) & 15u) == 0);
+    const bool bulk_ok = (((size_t)RD * (half_out ? 2 : 4)) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0) && ((((uintptr_t)obs_norm) & 15u) == 0);
     const uint64_t pol = make_evict_first_policy();
     __syncthreads();   // the trig table (the only block-wide barrier)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
@@ -381,6 +388,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     const int gs = gridDim.x * nwarps, g0 = blockIdx.x * nwarps + warp;
     const int jobs_pos = G * S, jobs_tank = G * nrows * n, jobs = jobs_pos + jobs_tank + (MAZE ? G * CELLS : 0);
 
+    uint32_t nz_prev = 0xFFFFFFFFu;   // batches of the normalised image that may hold non-zero values (warp-uniform)
     // one group: `use` = counts of group grp + 1 (loaded one iteration ago), `fill` = receives those of grp + 2
     auto group = [&](int grp, const uint32_t *use_cnt, const uint32_t *use_em, uint32_t *fill_cnt, uint32_t *fill_em) {
         // ---- phase 1: this group's prefetched columns -> the warp's tables
@@ -460,13 +468,15 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         }
         if (norm) {   // the tick normaliser over the dynamic columns: raw image -> normalised image (or in place)
             __syncwarp();
+            uint32_t nz_now = 0;   // bit (g * 16 + batch): the batch of 32 columns holds a non-zero value in this group
             for (int g = 0; g < G; ++g)
-                for (int j0 = 0; j0 < ndyn; j0 += 32) {
+                for (int j0 = 0, jb = 0; j0 < ndyn; j0 += 32, ++jb) {
                     const int j = j0 + lane;
                     const bool in = j < ndyn;
                     const int col = j < c.off_walls ? j : j - c.off_walls + dyn2;
                     const float *src = img + g * RD + col;
                     float *dn = nimg + g * RD + col;
+                    __half *dh = nimg16 + g * RD + col;
                     float vv[RMAX];
                     bool zero = true;
 #pragma unroll
@@ -474,35 +484,47 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
                         vv[a] = in && a < nrows ? src[a * c.obs_dim] : 0.f;
                         zero = zero && vv[a] == 0.f;
                     }
+                    const uint32_t bit = (G <= 2 && jb < 16) ? 1u << (g * 16 + jb) : 0u;
                     if (__all_sync(0xffffffffu, zero)) {   // 32 all-zero columns (empty bullet positions) normalise to zero
-                        if (norm2 && in)
-                            for (int a = 0; a < nrows; ++a) dn[a * c.obs_dim] = 0.f;
+                        if (norm2 && in && !(bit && !(nz_prev & bit))) {   // (... and are zero already if the last group left them so)
+                            if (half_out) for (int a = 0; a < nrows; ++a) dh[a * c.obs_dim] = __float2half_rn(0.f);
+                            else for (int a = 0; a < nrows; ++a) dn[a * c.obs_dim] = 0.f;
+                        }
                         continue;
                     }
+                    nz_now |= bit;
                     float mean, inv;
                     tick_norm_column<RMAX>(vv, nrows, nk, mean, inv);
                     if (in) {
 #pragma unroll
                         for (int a = 0; a < RMAX; ++a)
-                            if (a < nrows) dn[a * c.obs_dim] = (vv[a] - mean) * inv;
+                            if (a < nrows) {
+                                const float y = (vv[a] - mean) * inv;
+                                if (half_out) dh[a * c.obs_dim] = __float2half_rn(y);
+                                else dn[a * c.obs_dim] = y;
+                            }
                     }
                 }
+            nz_prev = (G <= 2) ? nz_now : 0xFFFFFFFFu;
         }
         fence_async_smem();   // the images are read by the async proxy
         __syncwarp();
         // ---- phase 3: ship the image(s)
         float *dst = obs + (int64_t)grp * G * RD, *dstn = obs_norm + (int64_t)grp * G * RD;
+        __half *dsth = reinterpret_cast<__half *>(obs_norm) + (int64_t)grp * G * RD;
         if (all_emit && bulk_ok) {
             if (lane == 0) {
                 if (obs) bulk_store(dst, img, (uint32_t)(G * RD * 4), pol);
-                if (norm) bulk_store(dstn, nimg, (uint32_t)(G * RD * 4), pol);   // (nimg == img when in place)
+                if (half_out) bulk_store(reinterpret_cast<float *>(dsth), reinterpret_cast<const float *>(nimg16), (uint32_t)(G * RD * 2), pol);
+                else if (norm) bulk_store(dstn, nimg, (uint32_t)(G * RD * 4), pol);   // (nimg == img when in place)
                 bulk_commit();
             }
         } else {   // masked reset / ragged tail / rows that are not 16-byte multiples: coalesced plain stores
             for (int g = 0; g < G; ++g) {
                 if (!em_s[g]) continue;
                 if (obs) for (int q = lane; q < RD; q += 32) stg_stream(dst + g * RD + q, img[g * RD + q], pol);
-                if (norm) for (int q = lane; q < RD; q += 32) stg_stream(dstn + g * RD + q, nimg[g * RD + q], pol);
+                if (half_out) for (int q = lane; q < RD; q += 32) dsth[g * RD + q] = nimg16[g * RD + q];
+                else if (norm) for (int q = lane; q < RD; q += 32) stg_stream(dstn + g * RD + q, nimg[g * RD + q], pol);
             }
             __syncwarp();   // the tables (em_s) are rewritten by the next group's phase 1
         }
@@ -521,7 +543,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     }
     if (lane == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
 }
-typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int, float *, float);
+typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int, float *, float, int);
 
 __global__ void gather_kernel(const __grid_constant__ KCfg c, const DevState st, int64_t first, int64_t count,
                               PackedEnv *out) {
@@ -1078,6 +1100,8 @@ struct at_env {
     rows_kernel_fn rows_fn;   // the instantiation for this config's shape
     size_t rows_smem, rows_smem_norm;   // (norm: with the second, normalised image)
     int rows_grid_norm;
+    int rows_warps_h, rows_grid_h;        // fp16 normalised rows (at_step_norm16): warps per block, grid
+    size_t rows_smem_h;
     int64_t launches;
     unsigned int *d_sig_counter;          // at_step_host: finished-block counter of the simulation kernel
     volatile uint32_t *h_sig_flag;        // ... and the mapped host word its last block posts the epoch to
@@ -1106,10 +1130,10 @@ static cudaError_t launch_pdl(void (*fn)(Args...), int grid, int block, size_t s
 }
 
 static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, cudaStream_t s, float *d_obs_norm, float norm_eps,
-                              bool pdl);
+                              bool pdl, bool norm_half = false);
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
-                             float norm_eps = 0.f, bool post_to_host = false) {
+                             float norm_eps = 0.f, bool post_to_host = false, bool norm_half = false) {
     const int epw = env->dbg_times ? 32 : env->sim_epw;   // (the block stamps are sized for full warps)
     const int per_block = (BS / 32) * epw;
     const int grid = (int)((env->n_envs + per_block - 1) / per_block);
@@ -1129,21 +1153,23 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     if (!rows) return AT_OK;
-    return launch_rows_kernel(env, d_mask, d_obs, s, d_obs_norm, norm_eps, env->pdl);
+    return launch_rows_kernel(env, d_mask, d_obs, s, d_obs_norm, norm_eps, env->pdl, norm_half);
 }
 
 // rows_kernel: the observation rows (raw and / or tick-normalised) of the stored state
 static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, cudaStream_t s, float *d_obs_norm, float norm_eps,
-                              bool pdl) {
+                              bool pdl, bool norm_half) {
     const int G = 1 << env->rows_lgG;
     const int n_groups = (int)((env->n_envs + G - 1) / G);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    const int want = (n_groups + env->rows_warps - 1) / env->rows_warps;
-    const int rgrid = (d_obs_norm && d_obs) ? env->rows_grid_norm : env->rows_grid;
+    norm_half = norm_half && d_obs_norm;
+    const int warps = norm_half ? env->rows_warps_h : env->rows_warps;
+    const int want = (n_groups + warps - 1) / warps;
+    const int rgrid = norm_half ? env->rows_grid_h : ((d_obs_norm && d_obs) ? env->rows_grid_norm : env->rows_grid);
     cfg.gridDim = dim3((unsigned)(want < rgrid ? want : rgrid));
-    cfg.blockDim = dim3(env->rows_warps * 32);
-    cfg.dynamicSmemBytes = (d_obs_norm && d_obs) ? env->rows_smem_norm : env->rows_smem;
+    cfg.blockDim = dim3(warps * 32);
+    cfg.dynamicSmemBytes = norm_half ? env->rows_smem_h : ((d_obs_norm && d_obs) ? env->rows_smem_norm : env->rows_smem);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1151,7 +1177,7 @@ static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups,
-                                (float *)d_obs_norm, norm_eps));
+                                (float *)d_obs_norm, norm_eps, norm_half ? 1 : 0));
     env->launches += 1;
     return AT_OK;
 }
@@ -1295,7 +1321,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         int lg = gg ? atoi(gg) : 1;
         if (lg < 0) lg = 0;
         if (lg > 3) lg = 3;
-        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD, W, true).total > (size_t)prop.sharedMemPerBlockOptin ||
+        while (lg > 0 && (rows_smem_layout(1 << lg, k.n_tanks, RD, W, 4).total > (size_t)prop.sharedMemPerBlockOptin ||
                           (1 << lg) * k.n_tanks * SLOTS_PER_TANK > 96 || (1 << lg) * k.n_tanks > 32))
             --lg;
         const int pairs = (1 << lg) * k.n_tanks * SLOTS_PER_TANK;
@@ -1305,8 +1331,8 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         else if (pairs <= 64 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) env->rows_fn = rows_kernel<2, 2, 0, false, 2>;
         else env->rows_fn = rows_kernel<0, 0, -1, false, 3>;
         env->rows_lgG = lg;
-        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD, W, false).total;
-        env->rows_smem_norm = rows_smem_layout(1 << lg, k.n_tanks, RD, W, true).total;
+        env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD, W, 0).total;
+        env->rows_smem_norm = rows_smem_layout(1 << lg, k.n_tanks, RD, W, 4).total;
         env->rows_grid_norm = prop.multiProcessorCount;
         env->rows_grid = prop.multiProcessorCount;
         if (k.rows > 0) {
@@ -1331,6 +1357,27 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
                 bpn = 1;
             }
             env->rows_grid_norm = prop.multiProcessorCount * bpn;
+            // fp16 normalised rows: raw fp32 image + fp16 image per warp; the warps per block that put most warps on an SM
+            int best_w = 1, best_tot = 0, best_b = 1;
+            for (int w = RK_MAX_WARPS; w >= 1; --w) {
+                const size_t sm = rows_smem_layout(1 << lg, k.n_tanks, RD, w, 2).total;
+                if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
+                int b = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, (const void *)env->rows_fn, w * 32, sm) != cudaSuccess) { cudaGetLastError(); b = 0; }
+                if (b * w > best_tot) { best_tot = b * w; best_w = w; best_b = b; }
+            }
+            const char *wh = getenv("AT_ROWS_WARPS_H");
+            if (wh && atoi(wh) >= 1 && atoi(wh) <= RK_MAX_WARPS) {
+                best_w = atoi(wh);
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&best_b, (const void *)env->rows_fn, best_w * 32,
+                                                                  rows_smem_layout(1 << lg, k.n_tanks, RD, best_w, 2).total) != cudaSuccess || best_b < 1) {
+                    cudaGetLastError();
+                    best_b = 1;
+                }
+            }
+            env->rows_warps_h = best_w;
+            env->rows_smem_h = rows_smem_layout(1 << lg, k.n_tanks, RD, best_w, 2).total;
+            env->rows_grid_h = prop.multiProcessorCount * (best_b < 1 ? 1 : best_b);
         }
     }
     // GamingENV.__init__ -> self.reset() (gaming_env.py:43): the constructor's own reset consumes draws
@@ -1390,6 +1437,18 @@ int at_step_norm(at_env *env, const int32_t *d_actions, float *d_obs, float *d_o
     DeviceGuard guard(env->device);
     CUDA_TRY(guard.status());
     return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream, d_obs_norm, epsilon);
+}
+
+int at_step_norm16(at_env *env, const int32_t *d_actions, float *d_obs, uint16_t *d_obs_norm16, float epsilon, float *d_rewards,
+                   uint8_t *d_done, void *stream) {
+    if (!env) return fail(AT_ERR_ARG, "at_step_norm16: null handle");
+    if (env->k.act_rows > 0 && !d_actions) return fail(AT_ERR_ARG, "at_step_norm16: this mode needs an actions array");
+    if ((env->k.rows > 0 && !d_rewards) || !d_done) return fail(AT_ERR_ARG, "at_step_norm16: rewards / done must not be null");
+    if (!d_obs_norm16) return fail(AT_ERR_ARG, "at_step_norm16: the normalised observation buffer must not be null");
+    DeviceGuard guard(env->device);
+    CUDA_TRY(guard.status());
+    return launch_env_kernel(env, true, d_actions, nullptr, d_obs, d_rewards, d_done, (cudaStream_t)stream, (float *)d_obs_norm16, epsilon,
+                             false, true);
 }
 
 // device-visible alias of a host buffer (pinned + mapped memory under unified addressing), or nullptr
@@ -1754,11 +1813,11 @@ int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t 
     return AT_OK;
 }
 
-int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
-                      const int64_t *d_counter, void *stream) {
-    if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % 4 != 0 || dim > 1024)
-        return fail(AT_ERR_ARG, "at_policy_forward: 1 or 2 policies, dim a multiple of 4 up to 1024");
-    const int k_chunks = (dim + at_tc::KC - 1) / at_tc::KC;
+static int policy_forward_impl(bool half, int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
+                               uint64_t seed, const int64_t *d_counter, void *stream) {
+    if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % 8 != 0 || dim > (half ? 2048 : 1024))
+        return fail(AT_ERR_ARG, "at_policy_forward: 1 or 2 policies, dim a multiple of 8 up to 1024 (fp16: 2048)");
+    const int kc = half ? at_tc::H_KC : at_tc::KC, k_chunks = (dim + kc - 1) / kc;
     const uint32_t all = k_chunks >= 32 ? 0xFFFFFFFFu : ((1u << k_chunks) - 1u);
     if (chunk_mask == 0) chunk_mask = all;
     if (chunk_mask & ~all) return fail(AT_ERR_ARG, "at_policy_forward: chunk_mask names columns past dim");
@@ -1770,13 +1829,17 @@ int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t 
     for (int i = 0; i < 2; ++i) {
         const at_policy &q = pol[i < n_policies ? i : 0];
         if (!q.x || !q.w1 || !q.b1 || !q.w2 || !q.b2 || !q.w3 || !q.b3 || !q.actions || !q.logprobs || !q.values ||
-            q.x_row_stride % 4 != 0 || q.x_row_stride < dim)
+            q.x_row_stride % 8 != 0 || q.x_row_stride < dim)
             return fail(AT_ERR_ARG, "at_policy_forward: null buffer or a row stride that is not a multiple of 4 floats");
         if ((((uintptr_t)q.x) | ((uintptr_t)q.w1) | ((uintptr_t)q.w2)) & 15u)
             return fail(AT_ERR_ARG, "at_policy_forward: x / w1 / w2 must be 16-byte aligned");
-        if (!at_tc::make_map_2d(&maps[i], q.x, (uint64_t)n_rows, (uint64_t)dim, (uint64_t)q.x_row_stride * 4, at_tc::TM) ||
-            !at_tc::make_map_2d(&maps[2 + i], q.w1, 512, (uint64_t)dim, (uint64_t)dim * 4, 256) ||
-            !at_tc::make_map_2d(&maps[4 + i], q.w2, 512, 128, 128 * 4, 128))
+        const bool ok = half ? (at_tc::make_map_2d_f16(&maps[i], q.x, (uint64_t)n_rows, (uint64_t)dim, (uint64_t)q.x_row_stride * 2, at_tc::TM) &&
+                                at_tc::make_map_2d_f16(&maps[2 + i], q.w1, 512, (uint64_t)dim, (uint64_t)dim * 2, 256) &&
+                                at_tc::make_map_2d_f16(&maps[4 + i], q.w2, 512, 128, 128 * 2, 128))
+                             : (at_tc::make_map_2d(&maps[i], q.x, (uint64_t)n_rows, (uint64_t)dim, (uint64_t)q.x_row_stride * 4, at_tc::TM) &&
+                                at_tc::make_map_2d(&maps[2 + i], q.w1, 512, (uint64_t)dim, (uint64_t)dim * 4, 256) &&
+                                at_tc::make_map_2d(&maps[4 + i], q.w2, 512, 128, 128 * 4, 128));
+        if (!ok)
             return fail(AT_ERR_CUDA, "at_policy_forward: cuTensorMapEncodeTiled is not available or rejected the tensors");
         at_tc::PolicyIO &io = P.io[i];
         io.b1 = q.b1; io.b2 = q.b2; io.w3 = q.w3; io.b3 = q.b3;
@@ -1795,15 +1858,30 @@ int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t 
     if (device < 0 || device >= 64) return fail(AT_ERR_ARG, "at_policy_forward: device index out of range");
     if (!attr_set[device]) {
         CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::F_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::H_SMEM_BYTES));
         CUDA_TRY(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
         attr_set[device] = true;
     }
     const int n_tiles = P.tiles_per_policy * n_policies;
     const int grid = n_tiles < sms[device] ? n_tiles : sms[device];
-    at_tc::policy_forward_kernel<<<grid, at_tc::F_THREADS, at_tc::F_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
-                                                                                                     maps[4], maps[5], P);
+    if (half)
+        at_tc::policy_forward16_kernel<<<grid, at_tc::H_THREADS, at_tc::H_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                                                           maps[4], maps[5], P);
+    else
+        at_tc::policy_forward_kernel<<<grid, at_tc::F_THREADS, at_tc::F_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                                                         maps[4], maps[5], P);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;
+}
+
+int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
+                      const int64_t *d_counter, void *stream) {
+    return policy_forward_impl(false, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, stream);
+}
+
+int at_policy_forward16(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
+                        const int64_t *d_counter, void *stream) {
+    return policy_forward_impl(true, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, stream);
 }
 
 int at_obs_static_range(const at_env *env, int32_t *lo, int32_t *hi) {

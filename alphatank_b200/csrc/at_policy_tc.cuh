@@ -510,4 +510,305 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_c
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 
+// ====================================================================================================================
+// policy_forward16_kernel - the same pass on fp16 operands (at_step_norm16's rows, weights rounded to fp16 by the
+// caller; fp32 accumulation): tcgen05.mma.kind::f16 runs at twice the TF32 rate and every operand byte counts half,
+// which matters because the first layers are bound by what an SM can pull from L2 (~107 GB/s measured: each 128-row
+// tile streams all of W1).  fp16 has TF32's 10 mantissa bits; the normalised rows, the weights and tanh's output are
+// far inside its range.  Differences to the TF32 kernel: K chunks of 64 columns (one 128-byte swizzle row), W2 of a
+// network is ONE ring slot, the activations of two networks are in flight (two h1 buffers), and eight epilogue warps -
+// two per TMEM lane quarter, each thread one row and HALF the columns of a network (= one K chunk of the second layer);
+// the two halves of a row's output dot products meet in shared memory.
+constexpr int H_KC = 64;                                  // fp16 columns per chunk
+constexpr int H_STAGES = 3;
+constexpr uint32_t HA_BYTES = TM * H_KC * 2;              // 16 KB: x chunk
+constexpr uint32_t HB_BYTES = 256 * H_KC * 2;             // 32 KB: W1 chunk of one half, or a whole W2 (two chunks)
+constexpr uint32_t H_STAGE_BYTES = HA_BYTES + HB_BYTES;
+constexpr uint32_t HH1_BYTES = 2 * HA_BYTES;              // 32 KB: one network's activations (two K chunks)
+constexpr int H_EPI_WARPS = 8, H_THREADS = 64 + H_EPI_WARPS * 32;
+constexpr size_t H_SMEM_BYTES = 1024 + (size_t)H_STAGES * H_STAGE_BYTES + 2 * HH1_BYTES + F_TABLE_FLOATS * 4 + 128 * 3 * 4 + 24 * 8 + 16;
+
+// instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (format 0), K-major, N / 8 at bit 17, M / 16 at bit 24
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+                 "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;\n" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
+__global__ void __launch_bounds__(H_THREADS, 1)
+policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
+                        const __grid_constant__ CUtensorMap map_w1_0, const __grid_constant__ CUtensorMap map_w1_1,
+                        const __grid_constant__ CUtensorMap map_w2_0, const __grid_constant__ CUtensorMap map_w2_1,
+                        const __grid_constant__ PolicyFwd P) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *h1 = smem + (size_t)H_STAGES * H_STAGE_BYTES;            // two buffers of HH1_BYTES
+    float *tab = (float *)(h1 + 2 * HH1_BYTES);
+    float *b1s = tab, *b2s = tab + 512, *w3s = tab + 1024, *b3s = tab + 1024 + 9 * 128;
+    float *part = tab + F_TABLE_FLOATS;                                      // [3][128]: the upper column half's partial outputs
+    uint64_t *bars = (uint64_t *)(part + 3 * 128);
+    uint64_t *full = bars, *empty = bars + H_STAGES, *acc1_full = bars + 2 * H_STAGES, *acc_free = acc1_full + 2,
+             *h1_ready = acc_free + 2, *l2_done = h1_ready + 2;
+    uint32_t *tmem_slot = (uint32_t *)(l2_done + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = P.tiles_per_policy * P.n_policies;
+    const int n_chunks = __popc(P.chunk_mask);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < H_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        for (int h = 0; h < 2; ++h) {
+            mbar_init(acc1_full + h, 1); mbar_init(acc_free + h, H_EPI_WARPS * 32);
+            mbar_init(h1_ready + h, H_EPI_WARPS * 32); mbar_init(l2_done + h, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    }
+    if (warp == 1) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    const int m_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    // tensor-core order (the producer fills the ring in the same order), local tiles 0 .. m - 1, networks j = 4 i + net:
+    //   L1(0, h0) L1(0, h1)   then per tile i:   L2(i, n0) L2(i, n1) L2(i, n2) L1(i + 1, h0) L2(i, n3) L1(i + 1, h1)
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t g = 0;
+            auto slot = [&](uint32_t bytes) -> unsigned char * {
+                const uint32_t s = g % H_STAGES;
+                if (g >= H_STAGES) mbar_wait(empty + s, ((g / H_STAGES) - 1) & 1);
+                mbar_expect_tx(full + s, bytes);
+                return smem + (size_t)s * H_STAGE_BYTES;
+            };
+            auto l1 = [&](int i, int h) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const int p = tile / P.tiles_per_policy, row0 = (tile - p * P.tiles_per_policy) * TM;
+                const CUtensorMap *mx = p ? &map_x1 : &map_x0, *mw1 = p ? &map_w1_1 : &map_w1_0;
+                uint32_t m = P.chunk_mask;
+                while (m) {
+                    const int c = __ffs(m) - 1;
+                    m &= m - 1;
+                    unsigned char *sa = slot(H_STAGE_BYTES);
+                    tma_load_2d(sa, mx, full + g % H_STAGES, c * H_KC, row0);
+                    tma_load_2d(sa + HA_BYTES, mw1, full + g % H_STAGES, c * H_KC, h * 256);
+                    ++g;
+                }
+            };
+            auto l2 = [&](int i, int net) {
+                const int tile = blockIdx.x + i * gridDim.x;
+                const CUtensorMap *mw2 = tile / P.tiles_per_policy ? &map_w2_1 : &map_w2_0;
+                unsigned char *sb = slot(HB_BYTES) + HA_BYTES;
+                tma_load_2d(sb, mw2, full + g % H_STAGES, 0, net * 128);
+                tma_load_2d(sb + HA_BYTES, mw2, full + g % H_STAGES, H_KC, net * 128);
+                ++g;
+            };
+            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
+            for (int i = 0; i < m_tiles; ++i) {
+                l2(i, 0); l2(i, 1); l2(i, 2);
+                if (i + 1 < m_tiles) l1(i + 1, 0);
+                l2(i, 3);
+                if (i + 1 < m_tiles) l1(i + 1, 1);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = umma_idesc_f16(TM, 256), idesc2 = umma_idesc_f16(TM, 128);
+            uint32_t g = 0;
+            auto l1 = [&](int i, int h) {
+                if (i > 0) {
+                    mbar_wait(acc_free + h, (uint32_t)((i - 1) & 1));
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                }
+                for (int ci = 0; ci < n_chunks; ++ci) {
+                    const uint32_t s = g % H_STAGES;
+                    mbar_wait(full + s, (g / H_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                    const uint32_t a0 = smem_u32(smem + (size_t)s * H_STAGE_BYTES), b0 = a0 + HA_BYTES;
+#pragma unroll
+                    for (int kk = 0; kk < H_KC / 16; ++kk)   // 16 halves = 32 bytes per instruction along K
+                        umma_f16(tmem_base + h * 256, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
+                                 (ci > 0 || kk > 0) ? 1u : 0u);
+                    umma_commit(empty + s);
+                    ++g;
+                }
+                umma_commit(acc1_full + h);
+            };
+            auto l2 = [&](int i, int net) {
+                const int j = 4 * i + net, b = j & 1;
+                mbar_wait(h1_ready + b, (uint32_t)((j >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t s = g % H_STAGES;
+                mbar_wait(full + s, (g / H_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t a0 = smem_u32(h1 + (size_t)b * HH1_BYTES), b0 = smem_u32(smem + (size_t)s * H_STAGE_BYTES) + HA_BYTES;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc)
+#pragma unroll
+                    for (int kk = 0; kk < H_KC / 16; ++kk)
+                        umma_f16(tmem_base + net * 128, umma_desc_sw128(a0 + cc * HA_BYTES + kk * 32),
+                                 umma_desc_sw128(b0 + cc * HA_BYTES + kk * 32), idesc2, (cc > 0 || kk > 0) ? 1u : 0u);
+                umma_commit(empty + s);
+                ++g;
+                umma_commit(l2_done + b);
+            };
+            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
+            for (int i = 0; i < m_tiles; ++i) {
+                l2(i, 0); l2(i, 1); l2(i, 2);
+                if (i + 1 < m_tiles) l1(i + 1, 0);
+                l2(i, 3);
+                if (i + 1 < m_tiles) l1(i + 1, 1);
+            }
+        }
+    } else {
+        // ===== epilogue: thread = (row, column half); TMEM lane quarter = warp % 4
+        const int q = warp & 3, ch = (warp - 2) >> 2, r = q * 32 + lane;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint64_t ctr = P.counter ? (uint64_t)*P.counter : 0ull;
+        int cur_p = -1, it = 0;
+        // first-layer columns [64 ch, 64 ch + 64) of `net` -> + bias -> tanh -> fp16 -> K chunk `ch` of the second layer's
+        // A operand (128-byte swizzle: the 16-byte unit u of row r lives at unit u ^ (r & 7))
+        auto conv = [&](int j, int net) {
+            unsigned char *dst = h1 + (size_t)(j & 1) * HH1_BYTES + (size_t)ch * HA_BYTES + (size_t)r * 128;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + (uint32_t)(net * 128 + ch * 64 + c * 32), v);
+                const float *bb = b1s + net * 128 + ch * 64 + c * 32;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {   // 8 columns = one 16-byte unit
+                    uint4 w;
+                    w.x = pack_half2(tanh_approx(__uint_as_float(v[8 * u]) + bb[8 * u]), tanh_approx(__uint_as_float(v[8 * u + 1]) + bb[8 * u + 1]));
+                    w.y = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 2]) + bb[8 * u + 2]), tanh_approx(__uint_as_float(v[8 * u + 3]) + bb[8 * u + 3]));
+                    w.z = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 4]) + bb[8 * u + 4]), tanh_approx(__uint_as_float(v[8 * u + 5]) + bb[8 * u + 5]));
+                    w.w = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 6]) + bb[8 * u + 6]), tanh_approx(__uint_as_float(v[8 * u + 7]) + bb[8 * u + 7]));
+                    *reinterpret_cast<uint4 *>(dst + (((c * 4 + u) ^ (r & 7)) << 4)) = w;
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(h1_ready + (j & 1));
+        };
+        // second-layer columns of `net` -> its output (value, or one head's draw); the two column halves meet in `part`
+        auto readout = [&](int j, int net, const PolicyIO &io, int64_t row, bool in) {
+            mbar_wait(l2_done + (j & 1), (uint32_t)((j >> 1) & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            const int first = net == 0 ? 0 : (net == 1 ? 1 : (net == 2 ? 4 : 7)), nout = net == 0 ? 1 : (net == 3 ? 2 : 3);
+            float o[3] = {0.f, 0.f, 0.f};
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(lane_addr + (uint32_t)(net * 128 + ch * 64 + c * 32), v);
+                const float *bb = b2s + net * 128 + ch * 64 + c * 32, *ww = w3s + first * 128 + ch * 64 + c * 32;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const float hv = tanh_approx(__uint_as_float(v[i]) + bb[i]);
+                    o[0] = fmaf(hv, ww[i], o[0]);
+                    if (nout > 1) o[1] = fmaf(hv, ww[128 + i], o[1]);
+                    if (nout > 2) o[2] = fmaf(hv, ww[256 + i], o[2]);
+                }
+            }
+            if (ch == 1) { part[r] = o[0]; part[128 + r] = o[1]; part[256 + r] = o[2]; }
+            asm volatile("bar.sync 2, 256;\n" ::: "memory");
+            if (ch == 0) { o[0] += part[r]; o[1] += part[128 + r]; o[2] += part[256 + r]; }
+            asm volatile("bar.sync 3, 256;\n" ::: "memory");   // `part` may be rewritten
+            if (ch != 0 || !in) return;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) o[k] += b3s[first + (k < nout ? k : 0)];
+            if (io.out9)
+                for (int k = 0; k < nout; ++k) io.out9[row * 9 + first + k] = o[k];
+            if (net == 0) { io.values[row * io.val_stride] = o[0]; return; }
+            const int draw = net == 1 ? 0 : (net == 2 ? 3 : 6);
+            uint32_t u[8];
+#pragma unroll
+            for (int b = 0; b < 2; ++b) {
+                uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)b << 31), cc = (uint32_t)ctr,
+                         c3 = (uint32_t)(ctr >> 32) ^ (io.stream_id * 0x9E3779B9u);
+                at::philox4x32_10(c0, c1, cc, c3, (uint32_t)(P.seed & 0xFFFFFFFFu), (uint32_t)(P.seed >> 32));
+                u[4 * b] = c0; u[4 * b + 1] = c1; u[4 * b + 2] = cc; u[4 * b + 3] = c3;
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < nout) mx = fmaxf(mx, o[k]);
+            float se = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k < nout) se += expf(o[k] - mx);
+            const float lse = mx + logf(se);
+            int best = 0;
+            float best_s = -INFINITY, best_lp = 0.f;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k < nout) {
+                    const float lp = o[k] - lse;
+                    const float un = ((float)u[(draw + k) & 7] + 0.5f) * 2.3283064365386963e-10f;
+                    const float gm = -logf(fmaxf(-logf(fminf(un, 0.99999994f)), 1e-20f));
+                    if (lp + gm > best_s) { best_s = lp + gm; best = k; best_lp = lp; }
+                }
+            }
+            io.actions[row * io.act_stride + (net - 1)] = best;
+            io.logprobs[row * io.lp_stride + (net - 1)] = best_lp;
+        };
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int p = tile / P.tiles_per_policy;
+            const int64_t row = (int64_t)(tile - p * P.tiles_per_policy) * TM + r;
+            const bool in = row < P.n_rows;
+            const PolicyIO &io = P.io[p];
+            if (p != cur_p) {
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                const int t = threadIdx.x - 64;
+                for (int i = t; i < 512; i += 256) { b1s[i] = __ldg(io.b1 + i); b2s[i] = __ldg(io.b2 + i); }
+                for (int i = t; i < 9 * 128; i += 256) w3s[i] = __ldg(io.w3 + i);
+                if (t < 12) b3s[t] = t < 9 ? __ldg(io.b3 + t) : 0.f;
+                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                cur_p = p;
+            }
+            const int j0 = 4 * it;
+            // conv(j) writes h1 buffer j & 1, free once readout(j - 2) has seen the second layer of j - 2 finish
+            mbar_wait(acc1_full + 0, (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            conv(j0, 0);
+            conv(j0 + 1, 1);
+            readout(j0, 0, io, row, in);
+            mbar_wait(acc1_full + 1, (uint32_t)(it & 1));
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            conv(j0 + 2, 2);
+            readout(j0 + 1, 1, io, row, in);
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(acc_free + 0);
+            conv(j0 + 3, 3);
+            readout(j0 + 2, 2, io, row, in);
+            readout(j0 + 3, 3, io, row, in);
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(acc_free + 1);
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
+}
+
+// a [rows][cols] fp16 matrix with `row_stride_bytes` between rows, read in boxes of box_rows x 64 columns
+inline bool make_map_2d_f16(CUtensorMap *map, const void *base, uint64_t rows, uint64_t cols, uint64_t row_stride_bytes, uint32_t box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows}, strides[1] = {row_stride_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)H_KC, box_rows}, estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace at_tc

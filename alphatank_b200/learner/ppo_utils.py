@@ -208,20 +208,24 @@ class FusedPolicies:
     normaliser).  K chunks of 32 columns that lie inside that range are dropped from the first layers' contraction and
     their contribution W1[:, chunk] . y is folded into the bias."""
 
-    def __init__(self, agents, obs_dim, device):
+    def __init__(self, agents, obs_dim, device, half=False):
         assert 1 <= len(agents) <= 2
         self.agents, self.D, self.device = list(agents), int(obs_dim), torch.device(device)
+        # half: fp16 observations (at_step_norm16) and fp16 weights on tcgen05.mma.kind::f16 (at_policy_forward16) instead
+        # of fp32 observations / TF32 (at_policy_forward); K chunks are 64 columns wide there
+        self.half, self.kc = bool(half), 64 if half else 32
         for a in self.agents:
             nets = [a.critic] + list(a.actor)
             if [int(m[4].out_features) for m in nets] != [1, 3, 3, 2] or any(m[0].out_features != 128 or m[2].out_features != 128 for m in nets):
                 raise ValueError("at_policy_forward serves the reference architecture only (128 hidden units, heads 3 / 3 / 2)")
-        if self.D % 4 != 0 or self.D > 1024:
-            raise ValueError("at_policy_forward needs an observation width that is a multiple of 4, up to 1024")
+        if self.D % 8 != 0 or self.D > 1024:
+            raise ValueError("at_policy_forward needs an observation width that is a multiple of 8, up to 1024")
         n = len(self.agents)
         f = dict(dtype=torch.float32, device=self.device)
-        self.w1 = torch.empty((n, 512, self.D), **f)
+        wt = torch.float16 if self.half else torch.float32
+        self.w1 = torch.empty((n, 512, self.D), dtype=wt, device=self.device)
         self.b1 = torch.empty((n, 512), **f)
-        self.w2 = torch.empty((n, 4, 128, 128), **f)
+        self.w2 = torch.empty((n, 4, 128, 128), dtype=wt, device=self.device)
         self.b2 = torch.empty((n, 4, 128), **f)
         self.w3 = torch.empty((n, 9, 128), **f)
         self.b3 = torch.empty((n, 9), **f)
@@ -232,13 +236,14 @@ class FusedPolicies:
 
     def set_static(self, lo, hi, y):
         """y: [n_agents, D] the constant columns' values as the policies see them (only [lo, hi) is read)."""
-        k_chunks = (self.D + 31) // 32
-        keep = [c for c in range(k_chunks) if not (lo <= 32 * c and min(32 * c + 32, self.D) <= hi)]
+        kc = self.kc
+        k_chunks = (self.D + kc - 1) // kc
+        keep = [c for c in range(k_chunks) if not (lo <= kc * c and min(kc * c + kc, self.D) <= hi)]
         if len(keep) == k_chunks:
             self.chunk_mask, self._fold_cols, self._fold_y = 0, None, None
         else:
             drop = [c for c in range(k_chunks) if c not in keep]
-            cols = torch.cat([torch.arange(32 * c, min(32 * c + 32, self.D)) for c in drop]).to(self.device)
+            cols = torch.cat([torch.arange(kc * c, min(kc * c + kc, self.D)) for c in drop]).to(self.device)
             self.chunk_mask = sum(1 << c for c in keep)
             self._fold_cols = cols
             self._fold_y = y.to(self.device, torch.float32)[:, cols].contiguous()
@@ -258,8 +263,9 @@ class FusedPolicies:
             self.b2[i].copy_(torch.stack([m[2].bias for m in nets]))
             self.w3[i].copy_(torch.cat([m[4].weight for m in nets], dim=0))
             self.b3[i].copy_(torch.cat([m[4].bias for m in nets], dim=0))
-        _round_tf32_(self.w1)
-        _round_tf32_(self.w2)
+        if not self.half:         # (copy_ into the fp16 tensors has rounded to nearest already)
+            _round_tf32_(self.w1)
+            _round_tf32_(self.w2)
 
     def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None):
         """obs [N, A, D] (A = the number of packed policies) -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]
@@ -269,7 +275,8 @@ class FusedPolicies:
 
         from .. import _capi
         n, A = obs_nad.shape[0], len(self.agents)
-        assert obs_nad.shape[1] == A and obs_nad.shape[2] == self.D and obs_nad.stride(2) == 1 and obs_nad.dtype == torch.float32
+        assert obs_nad.shape[1] == A and obs_nad.shape[2] == self.D and obs_nad.stride(2) == 1
+        assert obs_nad.dtype == (torch.float16 if self.half else torch.float32)
         assert actions_out.dtype == torch.int32 and actions_out.stride(-1) == 1 and logprobs_out.stride(-1) == 1
         pols = (_capi.AtPolicy * A)()
         for i in range(A):
@@ -283,9 +290,9 @@ class FusedPolicies:
             q.values, q.val_stride = v.data_ptr(), v.stride(0)
             q.out9 = out9[i].data_ptr() if out9 is not None else None
             q.stream_id = int(stream_base) + i
-        _capi.check(_capi.lib().at_policy_forward(
-            obs_nad.device.index, pols, A, n, self.D, int(self.chunk_mask), int(seed), C.c_void_p(counter.data_ptr()),
-            C.c_void_p(torch.cuda.current_stream(obs_nad.device).cuda_stream)), "at_policy_forward")
+        fn = _capi.lib().at_policy_forward16 if self.half else _capi.lib().at_policy_forward
+        _capi.check(fn(obs_nad.device.index, pols, A, n, self.D, int(self.chunk_mask), int(seed), C.c_void_p(counter.data_ptr()),
+                       C.c_void_p(torch.cuda.current_stream(obs_nad.device).cuda_stream)), "at_policy_forward")
 
 
 class PPOAgentBot(PPOAgentPPO):

@@ -195,6 +195,12 @@ int at_generate_mazes(int device, uint64_t seed, int64_t env_id_base, int64_t n,
 int at_step_norm(at_env *env, const int32_t *d_actions, float *d_obs, float *d_obs_norm, float epsilon, float *d_rewards,
                  uint8_t *d_done, void *stream);
 
+/* at_step_norm with the normalised rows written as IEEE fp16 (round to nearest of the same fp32 values): half the
+ * observation traffic of a rollout, and the operand type of at_policy_forward16's tensor-core contraction.
+ * d_obs_norm16: uint16[N][R * D] fp16 bits; d_obs (raw fp32 rows) may be NULL. */
+int at_step_norm16(at_env *env, const int32_t *d_actions, float *d_obs, uint16_t *d_obs_norm16, float epsilon,
+                   float *d_rewards, uint8_t *d_done, void *stream);
+
 /* The trainers' per-tick observation normaliser (train_multi_ppo.py:89-91: a fresh RunningMeanStd((A, D)) from
  * models/ppo_utils.py:6-29 is updated with, and applied to, each env's own [rows][dim] block) in one pass over
  * d_obs float[n_envs][rows][dim] -> d_out (may alias d_obs).  epsilon = RunningMeanStd's 1e-4. */
@@ -251,8 +257,9 @@ int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t 
  * is added to b1 by the caller - 2v2 rows: 9 of 17 chunks remain.  Precision: TF32 operands (x truncated, the hidden
  * activations rounded to nearest), fp32 accumulation, tanh.approx (relative error 2^-11). */
 typedef struct at_policy {
-    const float *x; int64_t x_row_stride;
-    const float *w1, *b1, *w2, *b2, *w3, *b3;
+    const void *x; int64_t x_row_stride;      /* float (at_policy_forward) or fp16 bits (at_policy_forward16); stride in elements */
+    const void *w1; const float *b1;          /* w1 / w2 in x's type, everything else float */
+    const void *w2; const float *b2, *w3, *b3;
     int32_t *actions; int64_t act_stride;
     float *logprobs; int64_t lp_stride;
     float *values; int64_t val_stride;
@@ -261,6 +268,12 @@ typedef struct at_policy {
 } at_policy;
 int at_policy_forward(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                       uint64_t seed, const int64_t *d_counter, void *stream);
+
+/* The same pass on fp16 operands - x = at_step_norm16's rows, w1 / w2 rounded to fp16 by the caller, fp32 accumulation,
+ * biases / output layers / outputs in fp32: tcgen05.mma.kind::f16 at twice the TF32 rate and half the operand bytes
+ * (fp16 carries TF32's 10 mantissa bits).  chunk_mask counts chunks of 64 columns here (2v2 rows: 5 of 9 remain). */
+int at_policy_forward16(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
+                        uint64_t seed, const int64_t *d_counter, void *stream);
 
 /* Observation columns [lo, hi) of every row that never change while the handle lives (the wall rectangles and the maze
  * block of a fixed map, gym_env_multi.py:283-292); lo == hi for per-env mazes. */

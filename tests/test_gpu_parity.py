@@ -326,14 +326,17 @@ def test_step_norm_equals_step_then_tick_normalize(name):
     from alphatank_b200.learner.ppo_utils import tick_normalize_cuda
     spec = SWEEP[name]
     N, seed, base = 1003, 12, 40
-    a, b, c = (_gpu(spec, N, seed, base, auto_reset=True) for _ in range(3))
-    for e in (a, b, c):
+    a, b, c, d, e2 = (_gpu(spec, N, seed, base, auto_reset=True) for _ in range(5))
+    for e in (a, b, c, d, e2):
         e.reset()
     ids = np.arange(base, base + N)
     R, D = a.R, a.D
     norm_b = torch.full((N, R * D), -7.0, device="cuda:0")
     norm_c = torch.full((N, R * D), -7.0, device="cuda:0")
     raw_b = torch.full((N, R * D), -7.0, device="cuda:0")
+    half_d = torch.full((N, R * D), -7.0, device="cuda:0", dtype=torch.float16)     # at_step_norm16: fp16 rows ...
+    half_e = torch.full((N, R * D), -7.0, device="cuda:0", dtype=torch.float16)     # ... with the raw rows beside them
+    raw_e = torch.full((N, R * D), -7.0, device="cuda:0")
     for t in range(100):
         acts = synthetic_actions(seed, ids, t, a.A) if a.A else None
         ta = None if acts is None else torch.as_tensor(np.ascontiguousarray(acts, dtype=np.int32))
@@ -346,6 +349,13 @@ def test_step_norm_equals_step_then_tick_normalize(name):
             if not torch.equal(got, want):
                 bad = (got != want).nonzero()[:6].tolist()
                 raise AssertionError("%s tick %d normalised rows differ at (env, col) %s" % (name, t, bad))
+        _, rd, dd = d.core.step_norm16(ta, half_d)
+        _, re_, de = e2.core.step_norm16(ta, half_e, obs_out=raw_e)
+        assert torch.equal(raw_e, oa) and torch.equal(ra, rd) and torch.equal(da, dd) and torch.equal(ra, re_) and torch.equal(da, de)
+        for got in (half_d, half_e):     # the same fp32 values, rounded to nearest fp16
+            if not torch.equal(got, want.half()):
+                bad = (got != want.half()).nonzero()[:6].tolist()
+                raise AssertionError("%s tick %d fp16 normalised rows differ at (env, col) %s" % (name, t, bad))
 
 
 @pytest.mark.parametrize("cap", ["1", "2", "3"])

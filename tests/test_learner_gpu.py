@@ -312,12 +312,15 @@ def _fp64_out9(agent, x):
     return torch.cat([a64.critic(x)] + [h(x) for h in a64.actor], dim=-1)
 
 
+@pytest.mark.parametrize("half", [False, True], ids=["tf32", "fp16"])
 @pytest.mark.parametrize("n_rows", [128, 1000, 40000])
-def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows):
+def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows, half):
     """at_policy_forward (csrc/at_policy_tc.cuh: the whole inference pass of two policies in one tcgen05 kernel) against
     the fp64 forward of the same modules.  Precision of the path: TF32 operands (10-bit mantissa) in both hidden layers,
     fp32 accumulation, tanh.approx (2^-11) - tolerance 1e-2 on values / logits that are O(1) (measured: ~2e-3);
-    the chosen action's log-probability must be the log-softmax of the kernel's own logits to 1e-5."""
+    the chosen action's log-probability must be the log-softmax of the kernel's own logits to 1e-5.
+    fp16: at_policy_forward16 on fp16 rows / weights (the same 10 mantissa bits), against the fp64 forward of the
+    fp16-rounded rows."""
     from alphatank_b200.learner.ppo_utils import FusedPolicies
     dev = torch.device("cuda:0")
     D, A = 528, 2
@@ -325,7 +328,9 @@ def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows):
     torch.manual_seed(1)
     obs = torch.randn((n_rows, A, D), device=dev)
     obs[:, :, 100:180] = 0.0
-    fp = FusedPolicies(agents, D, dev)
+    if half:
+        obs = obs.half()
+    fp = FusedPolicies(agents, D, dev, half=half)
     acts = torch.full((n_rows, A, 3), -1, dtype=torch.int32, device=dev)
     lps = torch.full((n_rows, A, 3), float("nan"), device=dev)
     vals = torch.full((n_rows, A), float("nan"), device=dev)
@@ -337,6 +342,7 @@ def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows):
     for i in range(A):
         ref = _fp64_out9(agents[i], obs[:, i]).float()
         err = (out9[i] - ref).abs().max().item()
+        print("max |out9 - fp64| = %.2e (%s, %d rows)" % (err, "fp16" if half else "tf32", n_rows))
         assert ref.abs().mean().item() > 0.2      # the comparison means something
         assert err < 1e-2, err
         assert torch.equal(vals[:, i], out9[i][:, 0])
@@ -372,7 +378,8 @@ def test_policy_forward_draws_follow_the_softmax():
     assert (draws[0] != draws[1]).any()
 
 
-def test_policy_forward_folds_constant_columns_into_the_bias():
+@pytest.mark.parametrize("half", [False, True], ids=["tf32", "fp16"])
+def test_policy_forward_folds_constant_columns_into_the_bias(half):
     """Columns that are the same in every row (the wall / maze block of a fixed map) dropped from the contraction and
     folded into the first layers' bias: 9 of 17 K chunks remain for the 2v2 rows, same result to TF32 accuracy."""
     from alphatank_b200.learner.ppo_utils import FusedPolicies
@@ -383,12 +390,14 @@ def test_policy_forward_folds_constant_columns_into_the_bias():
     obs = torch.randn((n, A, D), device=dev)
     const = torch.randn((A, D), device=dev)
     obs[:, :, 237:518] = const[:, 237:518]
+    if half:
+        obs, const = obs.half(), const.half()
     res = []
     for fold in (False, True):
-        fp = FusedPolicies(agents, D, dev)
+        fp = FusedPolicies(agents, D, dev, half=half)
         if fold:
             fp.set_static(237, 518, const)
-            assert fp.chunk_mask == 0x100FF
+            assert fp.chunk_mask == (0x10F if half else 0x100FF)
         out9 = torch.zeros((A, n, 9), device=dev)
         acts = torch.zeros((n, A, 3), dtype=torch.int32, device=dev)
         fp.forward(obs, acts, torch.zeros((n, A, 3), device=dev), torch.zeros((n, A), device=dev),
