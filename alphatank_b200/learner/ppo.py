@@ -43,7 +43,7 @@ class PPOConfig:                       # defaults: train_multi_ppo.py:25-38
 class RolloutBuffer:
     """[T(+1), N, A, ...] storage on the env's device; the env kernel writes obs / rewards / done into it directly."""
 
-    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device, keep_raw=True, keep_winner=False):
+    def __init__(self, num_steps, num_envs, num_agents, obs_dim, device, keep_raw=True, keep_winner=False, obs_dtype=torch.float32):
         T, N, A, D = num_steps, num_envs, num_agents, obs_dim
         # keep_winner: info["winner"] of every tick (the finished episode's where dones[t + 1] is set; at_get_terminal_info)
         self.winner = torch.zeros((T, N), dtype=torch.int32, device=device) if keep_winner else None
@@ -52,7 +52,9 @@ class RolloutBuffer:
         # normaliser on a GPU the env step hands over normalised rows and the raw ones are never written
         self.keep_raw = keep_raw
         self.raw_obs = torch.zeros(((T + 1) if keep_raw else 1, N, A * D), dtype=torch.float32, device=device)
-        self.obs = torch.zeros((T + 1, N, A, D), dtype=torch.float32, device=device)        # what the policy saw (+ the bootstrap obs)
+        # what the policy saw (+ the bootstrap obs).  torch.float16: the env writes the normalised rows as fp16
+        # (at_step_norm16) and the policies contract them on tcgen05.mma.kind::f16 - half the rollout's observation bytes
+        self.obs = torch.zeros((T + 1, N, A, D), dtype=obs_dtype, device=device)
         self.actions = torch.zeros((T, N, A, 3), dtype=torch.int32, device=device)
         self.logprobs = torch.zeros((T, N, A, 3), dtype=torch.float32, device=device)
         self.env_rewards = torch.zeros((T, N, A), dtype=torch.float32, device=device)       # cumulative, as returned
@@ -111,15 +113,16 @@ class PPOLearner:
         self._static = None
 
     # ---- the tcgen05 inference path (csrc/at_policy_tc.cuh)
-    def fused_policies(self):
-        """The agents packed for at_policy_forward (two per launch), or None where that path does not apply (CPU, another
-        architecture than the reference's, AT_NO_POLICY_TC=1: the per-layer kernels of sample_cuda take over)."""
-        if self._fused is None:
+    def fused_policies(self, half=False):
+        """The agents packed for at_policy_forward / at_policy_forward16 (two per launch), or None where that path does
+        not apply (CPU, another architecture than the reference's, AT_NO_POLICY_TC=1: the per-layer kernels of
+        sample_cuda take over).  ``half``: for fp16 observations."""
+        if self._fused is None or (self._fused and self._fused[0].half != bool(half)):
             self._fused = False
             if self.device.type == "cuda" and not os.environ.get("AT_NO_POLICY_TC") and \
                     torch.cuda.get_device_capability(self.device)[0] == 10:
                 try:
-                    self._fused = [FusedPolicies(self.agents[i:i + 2], self.D, self.device) for i in range(0, self.A, 2)]
+                    self._fused = [FusedPolicies(self.agents[i:i + 2], self.D, self.device, half=half) for i in range(0, self.A, 2)]
                 except ValueError:
                     self._fused = False
                 if self._fused and self._static is not None:
@@ -175,7 +178,10 @@ class PPOLearner:
             if getattr(self, "_sample_ctr", None) is None:
                 self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
             self._sample_ctr.add_(1)
-            fused = self.fused_policies()
+            half = obs_nad.dtype == torch.float16
+            fused = self.fused_policies(half)
+            if fused is None and half:
+                raise RuntimeError("fp16 observations need the tcgen05 inference path (at_policy_forward16)")
             if fused is not None and self.cfg.obs_norm == "running" and fused[0].chunk_mask:
                 raise RuntimeError("static-column folding needs a stateless observation normaliser")
             if fused is not None:   # the whole forward + sampling of two policies per launch (tcgen05, at_policy_forward)
@@ -198,7 +204,7 @@ class PPOLearner:
 
     @torch.no_grad()
     def values(self, obs_nad):
-        return torch.stack([agent.get_value(obs_nad[:, i]).squeeze(-1) for i, agent in enumerate(self.agents)], dim=1)
+        return torch.stack([agent.get_value(obs_nad[:, i].float()).squeeze(-1) for i, agent in enumerate(self.agents)], dim=1)
 
     # ---- learning
     def update(self, buf, generator=None):
@@ -230,7 +236,7 @@ class PPOLearner:
                 perm = torch.randperm(B, device=b_obs.device, generator=generator) if c.num_minibatches > 1 else None
                 for k in range(0, B, mb):
                     idx = perm[k:k + mb] if perm is not None else slice(None)
-                    _, new_lp, entropy, new_v = agent.get_action_and_value(b_obs[idx], b_act[idx])
+                    _, new_lp, entropy, new_v = agent.get_action_and_value(b_obs[idx].float(), b_act[idx])
                     ratio = torch.exp((new_lp - b_lp[idx]).clamp(-10, 10))
                     pg = torch.max(-b_adv[idx] * ratio, -b_adv[idx] * torch.clamp(ratio, 1 - c.clip_coef, 1 + c.clip_coef)).mean()
                     v_loss = 0.5 * ((new_v.squeeze(-1) - b_ret[idx]) ** 2).mean()
@@ -263,10 +269,15 @@ def collect_rollout(env, learner, buf, first=False):
     # GPU + "tick" normaliser: the env step returns the normalised rows itself (at_step_norm: normalised in shared
     # memory by rows_kernel), so the 277 MB of raw rows per tick are neither written nor read back
     fused = learner.cfg.obs_norm == "tick" and buf.obs.is_cuda
+    half = buf.obs.dtype == torch.float16
     assert fused or buf.keep_raw, "keep_raw=False needs the fused normalised step (cuda + obs_norm='tick')"
+    assert fused or not half, "fp16 observations come from the fused normalised step (cuda + obs_norm='tick')"
     if first:
         core.reset(obs_out=buf.raw_obs[0])
-        learner.normalize(buf.raw_obs[0], out=buf.obs[0])
+        if half:
+            buf.obs[0].copy_(learner.normalize(buf.raw_obs[0]))       # (rounds to nearest, like at_step_norm16)
+        else:
+            learner.normalize(buf.raw_obs[0], out=buf.obs[0])
         buf.dones[0].zero_()
     else:                                     # continue: the previous rollout's last observation / done flag
         if buf.keep_raw:
@@ -292,8 +303,9 @@ def collect_rollout(env, learner, buf, first=False):
             buf.logprobs[t].copy_(lp)
             buf.values[t].copy_(v)
         if fused:
-            core.step_norm(buf.actions[t], buf.obs[t + 1], obs_out=buf.raw_obs[t + 1] if buf.keep_raw else None,
-                           rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
+            (core.step_norm16 if half else core.step_norm)(
+                buf.actions[t], buf.obs[t + 1], obs_out=buf.raw_obs[t + 1] if buf.keep_raw else None,
+                rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
         else:
             core.step(buf.actions[t], obs_out=buf.raw_obs[t + 1], rewards_out=buf.env_rewards[t], done_out=buf.dones[t + 1])
             learner.normalize(buf.raw_obs[t + 1], update=t + 1 < T, out=buf.obs[t + 1])   # straight into the rollout storage

@@ -409,6 +409,44 @@ def test_policy_forward_folds_constant_columns_into_the_bias(half):
         assert (res[0][i] - ref).abs().max().item() < 1e-2
 
 
+def test_rollout_and_update_on_fp16_observations():
+    """RolloutBuffer(obs_dtype=float16): at_step_norm16 rows + at_policy_forward16 in collect_rollout, replayed as a CUDA
+    graph, then a PPO update on the stored fp16 rows.  The stored rows are the fp32 normalised rows rounded to nearest,
+    the stored log-probabilities / values are the policies' own (fp32 modules on the stored rows) to 5e-3, and the
+    update moves the parameters and re-packs the inference weights."""
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
+    from alphatank_b200.learner.ppo_utils import tick_normalize
+    dev = torch.device("cuda:0")
+    N, T = 2048, 6
+    env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=N, device=dev, seed=5)
+    A = len(env.get_observation_order())
+    D = env.observation_space.shape[0] // A
+    learner = PPOLearner(A, D, (3, 3, 2), PPOConfig(num_steps=T, num_epochs=1, num_minibatches=2), dev, seed=0)
+    buf = RolloutBuffer(T, N, A, D, dev, keep_raw=True, obs_dtype=torch.float16)
+    runner = RolloutRunner(env, learner, buf)
+    for k in range(3):                       # first: eager; second: capture + replay; third: replay
+        runner.run(first=(k == 0))
+        torch.cuda.synchronize()
+        fp = learner.fused_policies(half=True)
+        assert fp is not None and fp[0].half and fp[0].chunk_mask == 0x10F
+        want = tick_normalize(buf.raw_obs.view(T + 1, N, A, D).reshape((T + 1) * N, A, D).contiguous()).half()
+        assert torch.equal(buf.obs.view((T + 1) * N, A, D), want)
+        for i, agent in enumerate(learner.agents):
+            x = buf.obs[:T, :, i].reshape(T * N, D).float()
+            _, lp, _, v = agent.get_action_and_value(x, buf.actions[:, :, i].reshape(T * N, 3))
+            assert (lp - buf.logprobs[:, :, i].reshape(T * N, 3)).abs().max().item() < 5e-3
+            assert (v.squeeze(-1) - buf.values[:T, :, i].reshape(T * N)).abs().max().item() < 5e-3
+    before = [p.detach().clone() for p in learner.agents[0].parameters()]
+    b1_before = fp[0].b1.clone()
+    stats = learner.update(buf)
+    assert all(torch.isfinite(torch.tensor(list(s.values()))).all() for s in stats)
+    assert any((a != b).any() for a, b in zip(before, learner.agents[0].parameters()))
+    assert (fp[0].b1 != b1_before).any()
+    env.close()
+
+
 def test_rollout_on_the_fused_policies_matches_the_per_layer_path():
     """collect_rollout with the tcgen05 inference path (static columns folded) against the same rollout on the per-layer
     kernels (AT_NO_POLICY_TC): the first tick's values agree to TF32 accuracy and the rollout is self-consistent

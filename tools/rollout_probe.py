@@ -18,6 +18,7 @@ def main():
     p.add_argument("--iters", type=int, default=6)
     p.add_argument("--list", action="store_true")
     p.add_argument("--no-graph", action="store_true")
+    p.add_argument("--half", action="store_true", help="fp16 observations (at_step_norm16 + at_policy_forward16)")
     a = p.parse_args()
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
@@ -30,7 +31,7 @@ def main():
     A = len(names)
     D = env.observation_space.shape[0] // A
     learner = PPOLearner(A, D, (3, 3, 2), PPOConfig(num_steps=a.num_steps), dev, seed=0)
-    buf = RolloutBuffer(a.num_steps, a.num_envs, A, D, dev, keep_raw=False)
+    buf = RolloutBuffer(a.num_steps, a.num_envs, A, D, dev, keep_raw=False, obs_dtype=torch.float16 if a.half else torch.float32)
     runner = RolloutRunner(env, learner, buf, use_graph=not a.no_graph)
     runner.run(first=True)
     for _ in range(12):          # into the steady-state mix of episode phases
@@ -41,8 +42,8 @@ def main():
         runner.run()
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / a.iters
-    print("rollout: %.3f ms per tick, %.1f M agent-steps/s (env + policies, T=%d, %d envs)" % (
-        1e3 * dt / a.num_steps, a.num_envs * a.num_steps * A / dt / 1e6, a.num_steps, a.num_envs), flush=True)
+    print("rollout (%s observations): %.3f ms per tick, %.1f M agent-steps/s (env + policies, T=%d, %d envs)" % (
+        "fp16" if a.half else "fp32", 1e3 * dt / a.num_steps, a.num_envs * a.num_steps * A / dt / 1e6, a.num_steps, a.num_envs), flush=True)
     if a.list:
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CUDA]) as prof:
