@@ -1813,6 +1813,8 @@ int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t 
     return AT_OK;
 }
 
+static unsigned long long *g_policy_dbg = nullptr;   // at_policy_debug_stamps
+
 static int policy_forward_impl(bool half, int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                                uint64_t seed, const int64_t *d_counter, void *stream) {
     if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % 8 != 0 || dim > (half ? 2048 : 1024))
@@ -1853,6 +1855,7 @@ static int policy_forward_impl(bool half, int device, const at_policy *pol, int 
     P.chunk_mask = chunk_mask;
     P.seed = seed;
     P.counter = d_counter;
+    P.dbg = g_policy_dbg;
     static bool attr_set[64] = {false};
     static int sms[64] = {0};
     if (device < 0 || device >= 64) return fail(AT_ERR_ARG, "at_policy_forward: device index out of range");
@@ -1882,6 +1885,11 @@ int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t 
 int at_policy_forward16(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
                         const int64_t *d_counter, void *stream) {
     return policy_forward_impl(true, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, stream);
+}
+
+int at_policy_debug_stamps(unsigned long long *d_stamps) {
+    g_policy_dbg = d_stamps;   // device uint64[2][512] or NULL: block 0 of at_policy_forward16 records (event, SM clock) pairs
+    return AT_OK;
 }
 
 int at_obs_static_range(const at_env *env, int32_t *lo, int32_t *hi) {

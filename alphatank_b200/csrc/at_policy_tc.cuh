@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(128, 1) policy_first_kernel(const __grid_const
                                                                const float *__restrict__ b1, float *__restrict__ z1, int n_rows,
                                                                int k_chunks) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);   // swizzle atoms: 1024-byte aligned
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned (offset arithmetic keeps the shared address space)
     unsigned char *stage_a[STAGES], *stage_b[STAGES];
     for (int s = 0; s < STAGES; ++s) { stage_a[s] = smem + (size_t)s * STAGE_BYTES; stage_b[s] = stage_a[s] + A_BYTES; }
     uint64_t *bars = (uint64_t *)(smem + (size_t)STAGES * STAGE_BYTES);
@@ -235,6 +235,7 @@ struct PolicyFwd {
     uint32_t chunk_mask;     // K chunks (32 columns each) of the first layers to contract
     uint64_t seed;
     const int64_t *counter;
+    unsigned long long *dbg;   // diagnostics: [2][512] (event id, clock) pairs of block 0, or nullptr
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
@@ -256,7 +257,7 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_c
                       const __grid_constant__ CUtensorMap map_w2_0, const __grid_constant__ CUtensorMap map_w2_1,
                       const __grid_constant__ PolicyFwd P) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned (offset arithmetic keeps the shared address space)
     unsigned char *h1 = smem + (size_t)F_STAGES * F_STAGE_BYTES;
     float *tab = (float *)(h1 + H1_BYTES);
     float *b1s = tab, *b2s = tab + 512, *w3s = tab + 1024, *b3s = tab + 1024 + 9 * 128;
@@ -526,7 +527,7 @@ constexpr uint32_t HB_BYTES = 256 * H_KC * 2;             // 32 KB: W1 chunk of 
 constexpr uint32_t H_STAGE_BYTES = HA_BYTES + HB_BYTES;
 constexpr uint32_t HH1_BYTES = 2 * HA_BYTES;              // 32 KB: one network's activations (two K chunks)
 constexpr int H_EPI_WARPS = 8, H_THREADS = 64 + H_EPI_WARPS * 32;
-constexpr size_t H_SMEM_BYTES = 1024 + (size_t)H_STAGES * H_STAGE_BYTES + 2 * HH1_BYTES + F_TABLE_FLOATS * 4 + 128 * 3 * 4 + 24 * 8 + 16;
+constexpr size_t H_SMEM_BYTES = 1024 + (size_t)H_STAGES * H_STAGE_BYTES + 2 * HH1_BYTES + F_TABLE_FLOATS * 4 + 2 * 128 * 3 * 4 + 24 * 8 + 16;
 
 // instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (format 0), K-major, N / 8 at bit 17, M / 16 at bit 24
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
@@ -549,24 +550,28 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                         const __grid_constant__ CUtensorMap map_w2_0, const __grid_constant__ CUtensorMap map_w2_1,
                         const __grid_constant__ PolicyFwd P) {
     extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = (unsigned char *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned (offset arithmetic keeps the shared address space)
     unsigned char *h1 = smem + (size_t)H_STAGES * H_STAGE_BYTES;            // two buffers of HH1_BYTES
     float *tab = (float *)(h1 + 2 * HH1_BYTES);
     float *b1s = tab, *b2s = tab + 512, *w3s = tab + 1024, *b3s = tab + 1024 + 9 * 128;
-    float *part = tab + F_TABLE_FLOATS;                                      // [3][128]: the upper column half's partial outputs
-    uint64_t *bars = (uint64_t *)(part + 3 * 128);
-    uint64_t *full = bars, *empty = bars + H_STAGES, *acc1_full = bars + 2 * H_STAGES, *acc_free = acc1_full + 2,
-             *h1_ready = acc_free + 2, *l2_done = h1_ready + 2;
-    uint32_t *tmem_slot = (uint32_t *)(l2_done + 2);
+    float *part = tab + F_TABLE_FLOATS;                                      // [2][3][128]: one column half's partial outputs
+    uint64_t *bars = (uint64_t *)(part + 2 * 3 * 128);
+    // tensor memory: X = columns 0-255, the first layers of the current pair of networks; Y[b] = columns 256 + 128 b, the
+    // second layer of network j (b = j & 1).  X is free again as soon as its two networks are converted, so the next
+    // pair's first layers run while the epilogue reads the previous pair's outputs out of Y.
+    uint64_t *full = bars, *empty = bars + H_STAGES, *acc1_full = bars + 2 * H_STAGES, *x_free = acc1_full + 1,
+             *h1_ready = x_free + 1, *l2_done = h1_ready + 2, *y_free = l2_done + 2;
+    uint32_t *tmem_slot = (uint32_t *)(y_free + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = P.tiles_per_policy * P.n_policies;
     const int n_chunks = __popc(P.chunk_mask);
     if (threadIdx.x == 0) {
         for (int s = 0; s < H_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
+        mbar_init(acc1_full, 1);
+        mbar_init(x_free, H_EPI_WARPS * 32);
         for (int h = 0; h < 2; ++h) {
-            mbar_init(acc1_full + h, 1); mbar_init(acc_free + h, H_EPI_WARPS * 32);
-            mbar_init(h1_ready + h, H_EPI_WARPS * 32); mbar_init(l2_done + h, 1);
+            mbar_init(h1_ready + h, H_EPI_WARPS * 32); mbar_init(l2_done + h, 1); mbar_init(y_free + h, H_EPI_WARPS * 32);
         }
         asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
@@ -580,9 +585,18 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const int m_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // diagnostics (at_policy_debug_stamps): block 0 records (event id, SM clock) pairs per role - 0: MMA issuer, 1: epilogue
+    int n_stamp = 0;
+    auto stamp = [&](int role, int id) {
+        if (P.dbg != nullptr && blockIdx.x == 0 && n_stamp < 255) {
+            P.dbg[role * 512 + 2 * n_stamp] = (unsigned long long)id;
+            P.dbg[role * 512 + 2 * n_stamp + 1] = (unsigned long long)clock64();
+            ++n_stamp;
+        }
+    };
 
     // tensor-core order (the producer fills the ring in the same order), local tiles 0 .. m - 1, networks j = 4 i + net:
-    //   L1(0, h0) L1(0, h1)   then per tile i:   L2(i, n0) L2(i, n1) L2(i, n2) L1(i + 1, h0) L2(i, n3) L1(i + 1, h1)
+    //   per tile i:   L1(i, h0) L2(i, n0) L2(i, n1) L1(i, h1) L2(i, n2) L2(i, n3)
     if (warp == 0) {
         if (lane == 0) {
             uint32_t g = 0;
@@ -614,12 +628,9 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                 tma_load_2d(sb + HA_BYTES, mw2, full + g % H_STAGES, H_KC, net * 128);
                 ++g;
             };
-            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
             for (int i = 0; i < m_tiles; ++i) {
-                l2(i, 0); l2(i, 1); l2(i, 2);
-                if (i + 1 < m_tiles) l1(i + 1, 0);
-                l2(i, 3);
-                if (i + 1 < m_tiles) l1(i + 1, 1);
+                l1(i, 0); l2(i, 0); l2(i, 1);
+                l1(i, 1); l2(i, 2); l2(i, 3);
             }
         }
     } else if (warp == 1) {
@@ -627,8 +638,10 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
             constexpr uint32_t idesc1 = umma_idesc_f16(TM, 256), idesc2 = umma_idesc_f16(TM, 128);
             uint32_t g = 0;
             auto l1 = [&](int i, int h) {
-                if (i > 0) {
-                    mbar_wait(acc_free + h, (uint32_t)((i - 1) & 1));
+                const int u = 2 * i + h;
+                stamp(0, 100 + h);
+                if (u > 0) {   // the previous pair of networks has been converted out of X
+                    mbar_wait(x_free, (uint32_t)((u - 1) & 1));
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 }
                 for (int ci = 0; ci < n_chunks; ++ci) {
@@ -638,16 +651,19 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                     const uint32_t a0 = smem_u32(smem + (size_t)s * H_STAGE_BYTES), b0 = a0 + HA_BYTES;
 #pragma unroll
                     for (int kk = 0; kk < H_KC / 16; ++kk)   // 16 halves = 32 bytes per instruction along K
-                        umma_f16(tmem_base + h * 256, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
+                        umma_f16(tmem_base, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
                                  (ci > 0 || kk > 0) ? 1u : 0u);
                     umma_commit(empty + s);
                     ++g;
                 }
-                umma_commit(acc1_full + h);
+                umma_commit(acc1_full);
+                stamp(0, 110 + h);
             };
             auto l2 = [&](int i, int net) {
                 const int j = 4 * i + net, b = j & 1;
+                stamp(0, 200 + net);
                 mbar_wait(h1_ready + b, (uint32_t)((j >> 1) & 1));
+                if (j >= 2) mbar_wait(y_free + b, (uint32_t)(((j >> 1) - 1) & 1));   // network j - 2 has been read out of Y[b]
                 asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                 const uint32_t s = g % H_STAGES;
                 mbar_wait(full + s, (g / H_STAGES) & 1);
@@ -657,18 +673,16 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                 for (int cc = 0; cc < 2; ++cc)
 #pragma unroll
                     for (int kk = 0; kk < H_KC / 16; ++kk)
-                        umma_f16(tmem_base + net * 128, umma_desc_sw128(a0 + cc * HA_BYTES + kk * 32),
+                        umma_f16(tmem_base + 256 + b * 128, umma_desc_sw128(a0 + cc * HA_BYTES + kk * 32),
                                  umma_desc_sw128(b0 + cc * HA_BYTES + kk * 32), idesc2, (cc > 0 || kk > 0) ? 1u : 0u);
                 umma_commit(empty + s);
                 ++g;
                 umma_commit(l2_done + b);
+                stamp(0, 210 + net);
             };
-            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
             for (int i = 0; i < m_tiles; ++i) {
-                l2(i, 0); l2(i, 1); l2(i, 2);
-                if (i + 1 < m_tiles) l1(i + 1, 0);
-                l2(i, 3);
-                if (i + 1 < m_tiles) l1(i + 1, 1);
+                l1(i, 0); l2(i, 0); l2(i, 1);
+                l1(i, 1); l2(i, 2); l2(i, 3);
             }
         }
     } else {
@@ -684,7 +698,7 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)(net * 128 + ch * 64 + c * 32), v);
+                tmem_ld32(lane_addr + (uint32_t)((net & 1) * 128 + ch * 64 + c * 32), v);
                 const float *bb = b1s + net * 128 + ch * 64 + c * 32;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {   // 8 columns = one 16-byte unit
@@ -700,16 +714,20 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(h1_ready + (j & 1));
         };
-        // second-layer columns of `net` -> its output (value, or one head's draw); the two column halves meet in `part`
-        auto readout = [&](int j, int net, const PolicyIO &io, int64_t row, bool in) {
+        // second-layer columns of `net` -> its <= 3 outputs.  The two column halves of a row meet in `part` (two buffers,
+        // one barrier per network); the outputs of networks 0-2 are completed by the lower column half's threads, those of
+        // network 3 by the upper half's, and each group samples its heads once per tile (`finish`).
+        float lg[9];
+        auto readout = [&](int j, int net) {
             mbar_wait(l2_done + (j & 1), (uint32_t)((j >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+            if (threadIdx.x == 64) stamp(1, 400 + net);
             const int first = net == 0 ? 0 : (net == 1 ? 1 : (net == 2 ? 4 : 7)), nout = net == 0 ? 1 : (net == 3 ? 2 : 3);
             float o[3] = {0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)(net * 128 + ch * 64 + c * 32), v);
+                tmem_ld32(lane_addr + (uint32_t)(256 + (j & 1) * 128 + ch * 64 + c * 32), v);
                 const float *bb = b2s + net * 128 + ch * 64 + c * 32, *ww = w3s + first * 128 + ch * 64 + c * 32;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
@@ -719,47 +737,63 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                     if (nout > 2) o[2] = fmaf(hv, ww[256 + i], o[2]);
                 }
             }
-            if (ch == 1) { part[r] = o[0]; part[128 + r] = o[1]; part[256 + r] = o[2]; }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            mbar_arrive(y_free + (j & 1));   // (this thread's part of Y[b] is in registers)
+            float *pb = part + (j & 1) * 384;
+            const int sender = net == 3 ? 0 : 1;
+            if (ch == sender) { pb[r] = o[0]; pb[128 + r] = o[1]; pb[256 + r] = o[2]; }
             asm volatile("bar.sync 2, 256;\n" ::: "memory");
-            if (ch == 0) { o[0] += part[r]; o[1] += part[128 + r]; o[2] += part[256 + r]; }
-            asm volatile("bar.sync 3, 256;\n" ::: "memory");   // `part` may be rewritten
-            if (ch != 0 || !in) return;
+            if (ch != sender) {
 #pragma unroll
-            for (int k = 0; k < 3; ++k) o[k] += b3s[first + (k < nout ? k : 0)];
-            if (io.out9)
-                for (int k = 0; k < nout; ++k) io.out9[row * 9 + first + k] = o[k];
-            if (net == 0) { io.values[row * io.val_stride] = o[0]; return; }
-            const int draw = net == 1 ? 0 : (net == 2 ? 3 : 6);
-            uint32_t u[8];
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)b << 31), cc = (uint32_t)ctr,
-                         c3 = (uint32_t)(ctr >> 32) ^ (io.stream_id * 0x9E3779B9u);
-                at::philox4x32_10(c0, c1, cc, c3, (uint32_t)(P.seed & 0xFFFFFFFFu), (uint32_t)(P.seed >> 32));
-                u[4 * b] = c0; u[4 * b + 1] = c1; u[4 * b + 2] = cc; u[4 * b + 3] = c3;
+                for (int q3 = 0; q3 < 3; ++q3)
+                    if (q3 < nout) lg[first + q3] = o[q3] + pb[q3 * 128 + r] + b3s[first + q3];
             }
+        };
+        // one head's draw from its logits (the Philox stream of sample_out9_kernel: head k uses u[draw .. draw + d))
+        auto draw_head = [&](const PolicyIO &io, int64_t row, int head, const float *l, int d, const uint32_t *u, int draw) {
             float mx = -INFINITY;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (k < nout) mx = fmaxf(mx, o[k]);
+            for (int q3 = 0; q3 < 3; ++q3)
+                if (q3 < d) mx = fmaxf(mx, l[q3]);
             float se = 0.f;
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (k < nout) se += expf(o[k] - mx);
-            const float lse = mx + logf(se);
+            for (int q3 = 0; q3 < 3; ++q3)
+                if (q3 < d) se += __expf(l[q3] - mx);
+            const float lse = mx + __logf(se);   // (hardware ex2 / lg2: ~1e-7 absolute on the log-probabilities)
             int best = 0;
             float best_s = -INFINITY, best_lp = 0.f;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k < nout) {
-                    const float lp = o[k] - lse;
-                    const float un = ((float)u[(draw + k) & 7] + 0.5f) * 2.3283064365386963e-10f;
-                    const float gm = -logf(fmaxf(-logf(fminf(un, 0.99999994f)), 1e-20f));
-                    if (lp + gm > best_s) { best_s = lp + gm; best = k; best_lp = lp; }
+            for (int q3 = 0; q3 < 3; ++q3) {
+                if (q3 < d) {
+                    const float lp = l[q3] - lse;
+                    const float un = ((float)u[(draw + q3) & 7] + 0.5f) * 2.3283064365386963e-10f;
+                    const float gm = -__logf(fmaxf(-__logf(fminf(un, 0.99999994f)), 1e-20f));
+                    if (lp + gm > best_s) { best_s = lp + gm; best = q3; best_lp = lp; }
                 }
             }
-            io.actions[row * io.act_stride + (net - 1)] = best;
-            io.logprobs[row * io.lp_stride + (net - 1)] = best_lp;
+            io.actions[row * io.act_stride + head] = best;
+            io.logprobs[row * io.lp_stride + head] = best_lp;
+        };
+        auto finish = [&](const PolicyIO &io, int64_t row) {
+            uint32_t u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+            for (int bk = 0; bk < 2; ++bk) {
+                if (ch == 1 && bk == 0) continue;   // head 2 draws from the second block only
+                uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)bk << 31), cc = (uint32_t)ctr,
+                         c3 = (uint32_t)(ctr >> 32) ^ (io.stream_id * 0x9E3779B9u);
+                at::philox4x32_10(c0, c1, cc, c3, (uint32_t)(P.seed & 0xFFFFFFFFu), (uint32_t)(P.seed >> 32));
+                u[4 * bk] = c0; u[4 * bk + 1] = c1; u[4 * bk + 2] = cc; u[4 * bk + 3] = c3;
+            }
+            if (ch == 0) {
+                io.values[row * io.val_stride] = lg[0];
+                if (io.out9)
+                    for (int q3 = 0; q3 < 7; ++q3) io.out9[row * 9 + q3] = lg[q3];
+                draw_head(io, row, 0, lg + 1, 3, u, 0);
+                draw_head(io, row, 1, lg + 4, 3, u, 3);
+            } else {
+                if (io.out9) { io.out9[row * 9 + 7] = lg[7]; io.out9[row * 9 + 8] = lg[8]; }
+                draw_head(io, row, 2, lg + 7, 2, u, 6);
+            }
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int p = tile / P.tiles_per_policy;
@@ -777,22 +811,23 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
             }
             const int j0 = 4 * it;
             // conv(j) writes h1 buffer j & 1, free once readout(j - 2) has seen the second layer of j - 2 finish
-            mbar_wait(acc1_full + 0, (uint32_t)(it & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            conv(j0, 0);
-            conv(j0 + 1, 1);
-            readout(j0, 0, io, row, in);
-            mbar_wait(acc1_full + 1, (uint32_t)(it & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            conv(j0 + 2, 2);
-            readout(j0 + 1, 1, io, row, in);
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            mbar_arrive(acc_free + 0);
-            conv(j0 + 3, 3);
-            readout(j0 + 2, 2, io, row, in);
-            readout(j0 + 3, 3, io, row, in);
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            mbar_arrive(acc_free + 1);
+            for (int h = 0; h < 2; ++h) {
+                if (threadIdx.x == 64) stamp(1, 300 + h);
+                mbar_wait(acc1_full, (uint32_t)h);   // unit 2 it + h
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                if (threadIdx.x == 64) stamp(1, 310 + h);
+                conv(j0 + 2 * h, 2 * h);
+                conv(j0 + 2 * h + 1, 2 * h + 1);
+                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+                mbar_arrive(x_free);
+                if (threadIdx.x == 64) stamp(1, 320 + h);
+                readout(j0 + 2 * h, 2 * h);
+                if (threadIdx.x == 64) stamp(1, 330 + h);
+                readout(j0 + 2 * h + 1, 2 * h + 1);
+                if (threadIdx.x == 64) stamp(1, 340 + h);
+            }
+            if (in) finish(io, row);
+            if (threadIdx.x == 64) stamp(1, 350);
         }
     }
     __syncwarp();

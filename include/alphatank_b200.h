@@ -275,6 +275,10 @@ int at_policy_forward(int device, const at_policy *policies, int n_policies, int
 int at_policy_forward16(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                         uint64_t seed, const int64_t *d_counter, void *stream);
 
+/* Diagnostics: while d_stamps (device, uint64[2][512]) is set, block 0 of at_policy_forward16 records (event id, SM
+ * clock) pairs of its MMA-issuing thread ([0]) and of one epilogue thread ([1]); NULL switches them off (profiles/). */
+int at_policy_debug_stamps(unsigned long long *d_stamps);
+
 /* Observation columns [lo, hi) of every row that never change while the handle lives (the wall rectangles and the maze
  * block of a fixed map, gym_env_multi.py:283-292); lo == hi for per-env mazes. */
 int at_obs_static_range(const at_env *env, int32_t *lo, int32_t *hi);
