@@ -315,6 +315,39 @@ def ppo_allreduce_record(torch, dist, dev, world, rank, seed, E):
     return rec
 
 
+def policy_rollout_record(torch, dist, dev, world, rank, seed, E):
+    """the PPO rollout with the policies in the loop (train_multi_ppo.py:86-131 batched) - per tick one
+    simulation kernel, one rows kernel that hands over tick-normalised rows, ONE tcgen05 kernel for both policies'
+    forward passes and draws (at_policy_forward / at_policy_forward16) - replayed as a CUDA graph.  Two variants: fp32
+    rows + TF32 contraction, fp16 rows + fp16 contraction (fp32 accumulation in both)."""
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs.config_teams import team_vs_bot_configs
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
+    T, out = 16, {}
+    for name, dt in (("fp32_rows_tf32", torch.float32), ("fp16_rows_fp16", torch.float16)):
+        env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=E, device=dev, seed=seed, env_id_base=rank * E)
+        A = len(env.get_observation_order())
+        D = env.observation_space.shape[0] // A
+        learner = PPOLearner(A, D, (3, 3, 2), PPOConfig(num_steps=T), dev, seed=seed)
+        buf = RolloutBuffer(T, E, A, D, dev, keep_raw=False, obs_dtype=dt)
+        runner = RolloutRunner(env, learner, buf)
+        runner.run(first=True)
+        for _ in range(12):      # capture + into the steady-state mix of episode phases
+            runner.run()
+        reps = 4
+        ms = timed_loop(torch, dist, dev, world, lambda i: runner.run(), reps) / reps
+        fused = learner.fused_policies(dt == torch.float16)
+        out[name] = {"ms_per_tick": ms / T, "agent_steps_per_sec": E * world * T * A / ms * 1e3,
+                     "policy_kernel": ("at_policy_forward16" if dt == torch.float16 else "at_policy_forward") if fused else "per-layer kernels",
+                     "k_chunks_contracted": bin(fused[0].chunk_mask).count("1") if fused and fused[0].chunk_mask else None}
+        env.close()
+        del buf, runner, learner
+        torch.cuda.empty_cache()
+    out["note"] = ("%d envs/GPU x %d ticks per rollout, 2 policies (models/ppo_utils.py:31-62), CUDA-graph replay; static wall / maze "
+                   "columns folded into the first layers' bias" % (E, T))
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -406,6 +439,9 @@ def run_ours(args):
         subs["c5_2v2_131072_per_gpu"] = sub_config(
             torch, dist, dev, world, peak, "config 5: 2v2 team_vs_bot at 131072 envs per GPU (1M envs on 8 GPUs)", mk5, 2,
             ALG_BYTES_PER_ENV_STEP, "value is the whole job over %d GPU(s)" % world)
+    rollout = None
+    if not args.no_configs:
+        rollout = policy_rollout_record(torch, dist, dev, world, rank, args.seed, E)
     ppo = None
     if world > 1 and not args.no_configs:
         ppo = ppo_allreduce_record(torch, dist, dev, world, rank, args.seed, 131072)
@@ -441,6 +477,8 @@ def run_ours(args):
         "clocks": clk.summary(),
         "configs": subs,
     }
+    if rollout is not None:
+        line["policy_rollout"] = rollout
     if ppo is not None:
         line["ppo_allreduce"] = ppo
     if world == 1 and not args.no_cpu_baseline:
