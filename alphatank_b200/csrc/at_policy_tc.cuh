@@ -83,6 +83,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {  
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {   // ... the caller waits (tmem_ld_wait)
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+        "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
+
 // z1[n_rows][512] = x . W1^T + b1.  map_x: the [n_rows][D] fp32 rows (row stride arbitrary, a multiple of 16 bytes),
 // map_w: W1 [512][D]; both encoded with a {32, 128} / {32, 256} box and the 128-byte swizzle.
 __global__ void __launch_bounds__(128, 1) policy_first_kernel(const __grid_constant__ CUtensorMap map_x,
@@ -517,17 +529,18 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_c
 // which matters because the first layers are bound by what an SM can pull from L2 (~107 GB/s measured: each 128-row
 // tile streams all of W1).  fp16 has TF32's 10 mantissa bits; the normalised rows, the weights and tanh's output are
 // far inside its range.  Differences to the TF32 kernel: K chunks of 64 columns (one 128-byte swizzle row), W2 of a
-// network is ONE ring slot, the activations of two networks are in flight (two h1 buffers), and eight epilogue warps -
-// two per TMEM lane quarter, each thread one row and HALF the columns of a network (= one K chunk of the second layer);
-// the two halves of a row's output dot products meet in shared memory.
+// network is ONE ring slot, the activations of two networks are in flight (two h1 buffers), and sixteen epilogue warps -
+// four per TMEM lane quarter, each thread one row and a QUARTER of a network's columns (the epilogue is a latency chain of
+// tcgen05.ld -> bias -> MUFU.TANH -> store: four warps per scheduler keep the MUFU pipe fed); the four quarters of a
+// row's output dot products meet in shared memory.
 constexpr int H_KC = 64;                                  // fp16 columns per chunk
 constexpr int H_STAGES = 3;
 constexpr uint32_t HA_BYTES = TM * H_KC * 2;              // 16 KB: x chunk
 constexpr uint32_t HB_BYTES = 256 * H_KC * 2;             // 32 KB: W1 chunk of one half, or a whole W2 (two chunks)
 constexpr uint32_t H_STAGE_BYTES = HA_BYTES + HB_BYTES;
 constexpr uint32_t HH1_BYTES = 2 * HA_BYTES;              // 32 KB: one network's activations (two K chunks)
-constexpr int H_EPI_WARPS = 8, H_THREADS = 64 + H_EPI_WARPS * 32;
-constexpr size_t H_SMEM_BYTES = 1024 + (size_t)H_STAGES * H_STAGE_BYTES + 2 * HH1_BYTES + F_TABLE_FLOATS * 4 + 2 * 128 * 3 * 4 + 24 * 8 + 16;
+constexpr int H_EPI_WARPS = 16, H_THREADS = 64 + H_EPI_WARPS * 32;
+constexpr size_t H_SMEM_BYTES = 1024 + (size_t)H_STAGES * H_STAGE_BYTES + 2 * HH1_BYTES + F_TABLE_FLOATS * 4 + 2 * 3 * 384 * 4 + 24 * 8 + 16;
 
 // instruction descriptor, kind::f16: D = F32 (bit 4), A = B = F16 (format 0), K-major, N / 8 at bit 17, M / 16 at bit 24
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
@@ -554,8 +567,8 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
     unsigned char *h1 = smem + (size_t)H_STAGES * H_STAGE_BYTES;            // two buffers of HH1_BYTES
     float *tab = (float *)(h1 + 2 * HH1_BYTES);
     float *b1s = tab, *b2s = tab + 512, *w3s = tab + 1024, *b3s = tab + 1024 + 9 * 128;
-    float *part = tab + F_TABLE_FLOATS;                                      // [2][3][128]: one column half's partial outputs
-    uint64_t *bars = (uint64_t *)(part + 2 * 3 * 128);
+    float *part = tab + F_TABLE_FLOATS;                                      // [2 buffers][3 senders][3][128]: partial outputs
+    uint64_t *bars = (uint64_t *)(part + 2 * 3 * 384);
     // tensor memory: X = columns 0-255, the first layers of the current pair of networks; Y[b] = columns 256 + 128 b, the
     // second layer of network j (b = j & 1).  X is free again as soon as its two networks are converted, so the next
     // pair's first layers run while the epilogue reads the previous pair's outputs out of Y.
@@ -686,67 +699,69 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
             }
         }
     } else {
-        // ===== epilogue: thread = (row, column half); TMEM lane quarter = warp % 4
-        const int q = warp & 3, ch = (warp - 2) >> 2, r = q * 32 + lane;
+        // ===== epilogue: thread = (row, column quarter); TMEM lane quarter = warp % 4, 32 of a network's 128 columns each
+        const int q = warp & 3, cq = (warp - 2) >> 2, r = q * 32 + lane;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
         const uint64_t ctr = P.counter ? (uint64_t)*P.counter : 0ull;
         int cur_p = -1, it = 0;
-        // first-layer columns [64 ch, 64 ch + 64) of `net` -> + bias -> tanh -> fp16 -> K chunk `ch` of the second layer's
-        // A operand (128-byte swizzle: the 16-byte unit u of row r lives at unit u ^ (r & 7))
+        // first-layer columns [32 cq, 32 cq + 32) of `net` -> + bias -> tanh -> fp16 -> half of K chunk cq / 2 of the second
+        // layer's A operand (128-byte swizzle: the 16-byte unit u of row r lives at unit u ^ (r & 7))
         auto conv = [&](int j, int net) {
-            unsigned char *dst = h1 + (size_t)(j & 1) * HH1_BYTES + (size_t)ch * HA_BYTES + (size_t)r * 128;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)((net & 1) * 128 + ch * 64 + c * 32), v);
-                const float *bb = b1s + net * 128 + ch * 64 + c * 32;
+            unsigned char *dst = h1 + (size_t)(j & 1) * HH1_BYTES + (size_t)(cq >> 1) * HA_BYTES + (size_t)r * 128;
+            uint32_t v[32];
+            tmem_ld32(lane_addr + (uint32_t)((net & 1) * 128 + cq * 32), v);
+            const float *bb = b1s + net * 128 + cq * 32;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {   // 8 columns = one 16-byte unit
-                    uint4 w;
-                    w.x = pack_half2(tanh_approx(__uint_as_float(v[8 * u]) + bb[8 * u]), tanh_approx(__uint_as_float(v[8 * u + 1]) + bb[8 * u + 1]));
-                    w.y = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 2]) + bb[8 * u + 2]), tanh_approx(__uint_as_float(v[8 * u + 3]) + bb[8 * u + 3]));
-                    w.z = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 4]) + bb[8 * u + 4]), tanh_approx(__uint_as_float(v[8 * u + 5]) + bb[8 * u + 5]));
-                    w.w = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 6]) + bb[8 * u + 6]), tanh_approx(__uint_as_float(v[8 * u + 7]) + bb[8 * u + 7]));
-                    *reinterpret_cast<uint4 *>(dst + (((c * 4 + u) ^ (r & 7)) << 4)) = w;
-                }
+            for (int u = 0; u < 4; ++u) {   // 8 columns = one 16-byte unit
+                uint4 w;
+                w.x = pack_half2(tanh_approx(__uint_as_float(v[8 * u]) + bb[8 * u]), tanh_approx(__uint_as_float(v[8 * u + 1]) + bb[8 * u + 1]));
+                w.y = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 2]) + bb[8 * u + 2]), tanh_approx(__uint_as_float(v[8 * u + 3]) + bb[8 * u + 3]));
+                w.z = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 4]) + bb[8 * u + 4]), tanh_approx(__uint_as_float(v[8 * u + 5]) + bb[8 * u + 5]));
+                w.w = pack_half2(tanh_approx(__uint_as_float(v[8 * u + 6]) + bb[8 * u + 6]), tanh_approx(__uint_as_float(v[8 * u + 7]) + bb[8 * u + 7]));
+                *reinterpret_cast<uint4 *>(dst + ((((cq & 1) * 4 + u) ^ (r & 7)) << 4)) = w;
             }
             asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(h1_ready + (j & 1));
         };
-        // second-layer columns of `net` -> its <= 3 outputs.  The two column halves of a row meet in `part` (two buffers,
-        // one barrier per network); the outputs of networks 0-2 are completed by the lower column half's threads, those of
-        // network 3 by the upper half's, and each group samples its heads once per tile (`finish`).
-        float lg[9];
+        // second-layer columns of `net` -> its <= 3 outputs.  The four column quarters of a row meet in `part` (two buffers,
+        // one barrier per network): network 0 (value) and 1 (head 0) are completed by quarter 0's threads, network 2 (head
+        // 1) by quarter 1's, network 3 (head 2) by quarter 2's, and each group samples its head once per tile (`finish`).
+        float lg[4] = {0.f, 0.f, 0.f, 0.f};   // quarter 0: value + head 0; quarter 1 / 2: the head's logits
         auto readout = [&](int j, int net) {
             mbar_wait(l2_done + (j & 1), (uint32_t)((j >> 1) & 1));
             asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
             if (threadIdx.x == 64) stamp(1, 400 + net);
             const int first = net == 0 ? 0 : (net == 1 ? 1 : (net == 2 ? 4 : 7)), nout = net == 0 ? 1 : (net == 3 ? 2 : 3);
             float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)(256 + (j & 1) * 128 + ch * 64 + c * 32), v);
-                const float *bb = b2s + net * 128 + ch * 64 + c * 32, *ww = w3s + first * 128 + ch * 64 + c * 32;
+            uint32_t v[32];
+            tmem_ld32(lane_addr + (uint32_t)(256 + (j & 1) * 128 + cq * 32), v);
+            const float *bb = b2s + net * 128 + cq * 32, *ww = w3s + first * 128 + cq * 32;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const float hv = tanh_approx(__uint_as_float(v[i]) + bb[i]);
-                    o[0] = fmaf(hv, ww[i], o[0]);
-                    if (nout > 1) o[1] = fmaf(hv, ww[128 + i], o[1]);
-                    if (nout > 2) o[2] = fmaf(hv, ww[256 + i], o[2]);
-                }
+            for (int i = 0; i < 32; ++i) {
+                const float hv = tanh_approx(__uint_as_float(v[i]) + bb[i]);
+                o[0] = fmaf(hv, ww[i], o[0]);
+                if (nout > 1) o[1] = fmaf(hv, ww[128 + i], o[1]);
+                if (nout > 2) o[2] = fmaf(hv, ww[256 + i], o[2]);
             }
             asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
             mbar_arrive(y_free + (j & 1));   // (this thread's part of Y[b] is in registers)
-            float *pb = part + (j & 1) * 384;
-            const int sender = net == 3 ? 0 : 1;
-            if (ch == sender) { pb[r] = o[0]; pb[128 + r] = o[1]; pb[256 + r] = o[2]; }
-            asm volatile("bar.sync 2, 256;\n" ::: "memory");
-            if (ch != sender) {
+            float *pb = part + (j & 1) * (3 * 384);
+            const int recv = net <= 1 ? 0 : net - 1;
+            if (cq != recv) {
+                float *ps = pb + (cq < recv ? cq : cq - 1) * 384;
+                ps[r] = o[0]; ps[128 + r] = o[1]; ps[256 + r] = o[2];
+            }
+            asm volatile("bar.sync 2, 512;\n" ::: "memory");
+            if (cq == recv) {
 #pragma unroll
                 for (int q3 = 0; q3 < 3; ++q3)
-                    if (q3 < nout) lg[first + q3] = o[q3] + pb[q3 * 128 + r] + b3s[first + q3];
+                    if (q3 < nout) {
+                        const float t = o[q3] + pb[q3 * 128 + r] + pb[384 + q3 * 128 + r] + pb[768 + q3 * 128 + r] + b3s[first + q3];
+                        if (net == 0) lg[0] = t;
+                        else if (net == 1) lg[1 + q3] = t;
+                        else lg[q3] = t;
+                    }
             }
         };
         // one head's draw from its logits (the Philox stream of sample_out9_kernel: head k uses u[draw .. draw + d))
@@ -775,24 +790,28 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
             io.logprobs[row * io.lp_stride + head] = best_lp;
         };
         auto finish = [&](const PolicyIO &io, int64_t row) {
+            if (cq == 3) return;
             uint32_t u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
             for (int bk = 0; bk < 2; ++bk) {
-                if (ch == 1 && bk == 0) continue;   // head 2 draws from the second block only
+                if ((cq == 0 && bk == 1) || (cq == 2 && bk == 0)) continue;   // head 0: block 0, head 1: both, head 2: block 1
                 uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)bk << 31), cc = (uint32_t)ctr,
                          c3 = (uint32_t)(ctr >> 32) ^ (io.stream_id * 0x9E3779B9u);
                 at::philox4x32_10(c0, c1, cc, c3, (uint32_t)(P.seed & 0xFFFFFFFFu), (uint32_t)(P.seed >> 32));
                 u[4 * bk] = c0; u[4 * bk + 1] = c1; u[4 * bk + 2] = cc; u[4 * bk + 3] = c3;
             }
-            if (ch == 0) {
+            if (cq == 0) {
                 io.values[row * io.val_stride] = lg[0];
                 if (io.out9)
-                    for (int q3 = 0; q3 < 7; ++q3) io.out9[row * 9 + q3] = lg[q3];
+                    for (int q3 = 0; q3 < 4; ++q3) io.out9[row * 9 + q3] = lg[q3];
                 draw_head(io, row, 0, lg + 1, 3, u, 0);
-                draw_head(io, row, 1, lg + 4, 3, u, 3);
+            } else if (cq == 1) {
+                if (io.out9)
+                    for (int q3 = 0; q3 < 3; ++q3) io.out9[row * 9 + 4 + q3] = lg[q3];
+                draw_head(io, row, 1, lg, 3, u, 3);
             } else {
-                if (io.out9) { io.out9[row * 9 + 7] = lg[7]; io.out9[row * 9 + 8] = lg[8]; }
-                draw_head(io, row, 2, lg + 7, 2, u, 6);
+                if (io.out9) { io.out9[row * 9 + 7] = lg[0]; io.out9[row * 9 + 8] = lg[1]; }
+                draw_head(io, row, 2, lg, 2, u, 6);
             }
         };
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
@@ -801,12 +820,12 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
             const bool in = row < P.n_rows;
             const PolicyIO &io = P.io[p];
             if (p != cur_p) {
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                asm volatile("bar.sync 1, 512;\n" ::: "memory");
                 const int t = threadIdx.x - 64;
-                for (int i = t; i < 512; i += 256) { b1s[i] = __ldg(io.b1 + i); b2s[i] = __ldg(io.b2 + i); }
-                for (int i = t; i < 9 * 128; i += 256) w3s[i] = __ldg(io.w3 + i);
+                for (int i = t; i < 512; i += 512) { b1s[i] = __ldg(io.b1 + i); b2s[i] = __ldg(io.b2 + i); }
+                for (int i = t; i < 9 * 128; i += 512) w3s[i] = __ldg(io.w3 + i);
                 if (t < 12) b3s[t] = t < 9 ? __ldg(io.b3 + t) : 0.f;
-                asm volatile("bar.sync 1, 256;\n" ::: "memory");
+                asm volatile("bar.sync 1, 512;\n" ::: "memory");
                 cur_p = p;
             }
             const int j0 = 4 * it;
