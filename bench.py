@@ -323,7 +323,7 @@ def policy_rollout_record(torch, dist, dev, world, rank, seed, E):
     from alphatank_b200 import MultiAgentTeamEnv
     from alphatank_b200.configs.config_teams import team_vs_bot_configs
     from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
-    T, out = 16, {}
+    T, out = 32, {}     # PPOConfig.num_steps default
     for name, dt in (("fp32_rows_tf32", torch.float32), ("fp16_rows_fp16", torch.float16)):
         env = MultiAgentTeamEnv(team_vs_bot_configs, num_envs=E, device=dev, seed=seed, env_id_base=rank * E)
         A = len(env.get_observation_order())
