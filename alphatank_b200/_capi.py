@@ -42,7 +42,7 @@ ENV_STATE_DT = np.dtype([("n_bullets", "i4"), ("tick", "i4"), ("training_step", 
 EXPORTS = ("at_create at_destroy at_obs_dim at_obs_rows at_action_rows at_num_walls at_num_envs at_reset at_step at_step_norm "
            "at_step_host at_get_info at_get_terminal_info at_get_state at_set_state at_synthetic_actions at_bfs_batch at_generate_mazes "
            "at_get_luts at_tick_normalize at_sample_heads at_policy_tail at_policy_mid_tail at_debug_block_times at_set_weakness at_launch_count at_last_error at_version "
-           "at_observe at_set_reward_mode at_get_tank_columns at_forget_host_buffers at_policy_first at_policy_forward at_obs_static_range at_step_norm16 at_policy_forward16 at_policy_debug_stamps").split()
+           "at_observe at_set_reward_mode at_get_tank_columns at_forget_host_buffers at_policy_first at_policy_forward at_obs_static_range at_step_norm16 at_policy_forward16 at_policy_debug_stamps at_set_rows_mode").split()
 
 _lib = None
 
@@ -100,6 +100,7 @@ def lib():
     L.at_policy_forward.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, vp]
     L.at_policy_forward16.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, vp]
     L.at_policy_debug_stamps.argtypes = [vp]
+    L.at_set_rows_mode.argtypes = [vp, i32]
     L.at_obs_static_range.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
     L.at_tick_normalize.argtypes = [i32, vp, i64, i32, i32, C.c_float, vp, vp]
     L.at_debug_block_times.argtypes = [vp, vp]

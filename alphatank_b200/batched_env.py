@@ -185,6 +185,11 @@ class BatchedTankEnv:
                                         C.c_void_p(self._h_done.data_ptr()), self._stream()), "at_step_host")
         return self.obs, self._h_rewards, self._h_done
 
+    def set_rows_mode(self, persistent_buffers):
+        """persistent_buffers=True: step calls stop rewriting the columns that never change on a fixed map (the caller's
+        output buffers were written in full once before and are reused - at_set_rows_mode)."""
+        _capi.check(self.L.at_set_rows_mode(self.h, 1 if persistent_buffers else 0), "at_set_rows_mode")
+
     def static_obs_range(self):
         """(lo, hi): observation columns [lo, hi) of every row never change while this env lives (the wall / maze
         block of a fixed map); lo == hi for per-env mazes."""

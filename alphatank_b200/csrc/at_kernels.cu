@@ -287,8 +287,9 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     typedef RowsShape<NT, NR, TEAM> SH;
     // obs_norm: also emit (norm2: a second, normalised image) or only emit (inplace: obs == nullptr; the image is built
     // in full every group and normalised in place) the tick-normalised rows
-    // norm_half: the normalised rows leave as fp16 (always through a second image: the raw one stays incremental)
-    const bool norm = obs_norm != nullptr, half_out = norm && norm_half != 0, norm2 = norm && (obs != nullptr || half_out),
+    // norm_half bit 0: the normalised rows leave as fp16 (always through a second image: the raw one stays incremental);
+    // bit 1: persistent output buffers - the columns that never change on a fixed map are not written again
+    const bool norm = obs_norm != nullptr, half_out = norm && (norm_half & 1) != 0, norm2 = norm && (obs != nullptr || half_out),
                inplace = norm && !norm2;
     const TickNormK nk(SH::rows(c), norm_eps);
     const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, nrows = SH::rows(c), RD = nrows * c.obs_dim;
@@ -340,6 +341,11 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     const int dyn2 = MAZE ? c.off_walls : c.off_zones, ndyn = c.off_walls + (c.obs_dim - dyn2);
     const bool bulk_ok = (((size_t)RD * (half_out ? 2 : 4)) % 16 == 0) && ((((uintptr_t)obs) & 15u) == 0) && ((((uintptr_t)obs_norm) & 15u) == 0);
     const uint64_t pol = make_evict_first_policy();
+    // persistent-buffer mode: the dynamic runs of a row, widened to 16-byte multiples for fp32 (4 floats) and fp16 (8 halves)
+    const int cA4 = (c.off_walls + 3) & ~3, cB4 = dyn2 & ~3, cA8 = (c.off_walls + 7) & ~7, cB8 = dyn2 & ~7;
+    const bool need4 = obs != nullptr || (norm && !half_out), need8 = half_out;   // fp32 / fp16 images to ship
+    const bool skip_static = (norm_half & 2) != 0 && !MAZE && (!need4 || ((c.obs_dim & 3) == 0 && cA4 < cB4)) &&
+                             (!need8 || ((c.obs_dim & 7) == 0 && cA8 < cB8));
     __syncthreads();   // the trig table (the only block-wide barrier)
     asm volatile("griddepcontrol.wait;\n" ::: "memory");
 
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         load_b(grp + gs, use_cnt, use_em);
         load_a(grp + 2 * gs, fill_cnt, fill_em);
         // the previous copy must be done reading the image
-        if (lane == 0) bulk_wait_read_all();
+        bulk_wait_read_all();   // (every lane: in persistent-buffer mode several lanes issue copies)
         const bool all_emit = __all_sync(0xffffffffu, my_em);   // (also the warp barrier between phase 1 and 2)
         // ---- phase 2: 32 jobs per pass.  Position jobs first: a position that holds no bullet now and held none when
         // the image was last filled needs no work (it is still zero) - about 60 % of them - so the positions that do are
@@ -565,7 +571,28 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         // ---- phase 3: ship the image(s)
         float *dst = obs + (int64_t)grp * G * RD, *dstn = obs_norm + (int64_t)grp * G * RD;
         __half *dsth = reinterpret_cast<__half *>(obs_norm) + (int64_t)grp * G * RD;
-        if (all_emit && bulk_ok) {
+        if (all_emit && bulk_ok && skip_static) {
+            // persistent buffers: per row the two dynamic runs [0, cA) and [cB, D) only (16-byte multiples; the few static
+            // columns inside them are rewritten with their own values), one bulk copy per lane and run
+            const int n_pieces = 2 * G * nrows;
+            bool issued = false;
+            for (int pc = lane; pc < n_pieces; pc += 32) {
+                const int gr = pc >> 1, second = pc & 1;
+                if (obs) {
+                    const int off = gr * c.obs_dim + (second ? cB4 : 0), len = second ? c.obs_dim - cB4 : cA4;
+                    bulk_store(dst + off, img + off, (uint32_t)(len * 4), pol);
+                }
+                if (half_out) {
+                    const int off = gr * c.obs_dim + (second ? cB8 : 0), len = second ? c.obs_dim - cB8 : cA8;
+                    bulk_store(reinterpret_cast<float *>(dsth + off), reinterpret_cast<const float *>(nimg16 + off), (uint32_t)(len * 2), pol);
+                } else if (norm) {
+                    const int off = gr * c.obs_dim + (second ? cB4 : 0), len = second ? c.obs_dim - cB4 : cA4;
+                    bulk_store(dstn + off, nimg + off, (uint32_t)(len * 4), pol);
+                }
+                issued = true;
+            }
+            if (issued) bulk_commit();
+        } else if (all_emit && bulk_ok) {
             if (lane == 0) {
                 if (obs) bulk_store(dst, img, (uint32_t)(G * RD * 4), pol);
                 if (half_out) bulk_store(reinterpret_cast<float *>(dsth), reinterpret_cast<const float *>(nimg16), (uint32_t)(G * RD * 2), pol);
@@ -594,7 +621,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         group(grp, x_cnt, x_em, y_cnt, y_em);
         grp += gs;
     }
-    if (lane == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
+    bulk_wait_read_all();   // shared memory must outlive the copies' reads
 }
 typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int, float *, float, int);
 
@@ -1153,6 +1180,7 @@ struct at_env {
     rows_kernel_fn rows_fn;   // the instantiation for this config's shape
     size_t rows_smem, rows_smem_norm;   // (norm: with the second, normalised image)
     int rows_grid_norm;
+    bool rows_skip_static;                // at_set_rows_mode: the steps' output buffers are persistent (static columns not rewritten)
     int rows_warps_h, rows_grid_h;        // fp16 normalised rows (at_step_norm16): warps per block, grid
     size_t rows_smem_h;
     int64_t launches;
@@ -1183,7 +1211,7 @@ static cudaError_t launch_pdl(void (*fn)(Args...), int grid, int block, size_t s
 }
 
 static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, cudaStream_t s, float *d_obs_norm, float norm_eps,
-                              bool pdl, bool norm_half = false);
+                              bool pdl, bool norm_half = false, bool allow_skip = false);
 static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions, const uint8_t *d_mask,
                              float *d_obs, float *d_rewards, uint8_t *d_done, cudaStream_t s, float *d_obs_norm = nullptr,
                              float norm_eps = 0.f, bool post_to_host = false, bool norm_half = false) {
@@ -1206,12 +1234,12 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     env->launches += 1;
     CUDA_TRY(cudaGetLastError());
     if (!rows) return AT_OK;
-    return launch_rows_kernel(env, d_mask, d_obs, s, d_obs_norm, norm_eps, env->pdl, norm_half);
+    return launch_rows_kernel(env, d_mask, d_obs, s, d_obs_norm, norm_eps, env->pdl, norm_half, is_step && d_mask == nullptr);
 }
 
 // rows_kernel: the observation rows (raw and / or tick-normalised) of the stored state
 static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, cudaStream_t s, float *d_obs_norm, float norm_eps,
-                              bool pdl, bool norm_half) {
+                              bool pdl, bool norm_half, bool allow_skip) {
     const int G = 1 << env->rows_lgG;
     const int n_groups = (int)((env->n_envs + G - 1) / G);
     cudaLaunchConfig_t cfg;
@@ -1230,7 +1258,7 @@ static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, 
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups,
-                                (float *)d_obs_norm, norm_eps, norm_half ? 1 : 0));
+                                (float *)d_obs_norm, norm_eps, (norm_half ? 1 : 0) | (allow_skip && env->rows_skip_static ? 2 : 0)));
     env->launches += 1;
     return AT_OK;
 }
@@ -1299,6 +1327,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     }
 
     env->dbg_times = nullptr;
+    env->rows_skip_static = false;
     env->d_sig_counter = nullptr; env->h_sig_flag = nullptr; env->h_sig_flag_dev = nullptr; env->sig_epoch = 0;
     {
         void *hp = nullptr, *dp = nullptr;
@@ -1938,6 +1967,12 @@ int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t 
 int at_policy_forward16(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
                         const int64_t *d_counter, void *stream) {
     return policy_forward_impl(true, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, stream);
+}
+
+int at_set_rows_mode(at_env *env, int persistent_buffers) {
+    if (!env) return fail(AT_ERR_ARG, "at_set_rows_mode: null handle");
+    env->rows_skip_static = persistent_buffers != 0;
+    return AT_OK;
 }
 
 int at_policy_debug_stamps(unsigned long long *d_stamps) {

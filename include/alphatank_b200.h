@@ -275,6 +275,15 @@ int at_policy_forward(int device, const at_policy *policies, int n_policies, int
 int at_policy_forward16(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                         uint64_t seed, const int64_t *d_counter, void *stream);
 
+/* Persistent output buffers.  With persistent_buffers != 0 the STEP calls (at_step, at_step_norm, at_step_norm16,
+ * at_step_host) write only the columns of a row that can change - [0, off_walls) and [off_zones, D), widened to 16-byte
+ * multiples - and leave the wall / maze block of a fixed map (at_obs_static_range: 281 of 528 columns of the 2v2 rows)
+ * as it is.  The caller guarantees that every buffer it passes was written in full once before by this handle (at_reset,
+ * at_observe, or a step call made before the switch): a ring of rollout slots, the env's own persistent buffer.
+ * Resets and at_observe always write whole rows; per-env mazes and row lengths that are not 16-byte multiples ignore
+ * the switch.  (The reference rebuilds the wall block of every observation, gym_env_multi.py:283-292.) */
+int at_set_rows_mode(at_env *env, int persistent_buffers);
+
 /* Diagnostics: while d_stamps (device, uint64[2][512]) is set, block 0 of at_policy_forward16 records (event id, SM
  * clock) pairs of its MMA-issuing thread ([0]) and of one epilogue thread ([1]); NULL switches them off (profiles/). */
 int at_policy_debug_stamps(unsigned long long *d_stamps);

@@ -358,6 +358,52 @@ def test_step_norm_equals_step_then_tick_normalize(name):
                 raise AssertionError("%s tick %d fp16 normalised rows differ at (env, col) %s" % (name, t, bad))
 
 
+@pytest.mark.parametrize("name", ["team_vs_bot", "team_harder_battlefield", "agent_t96", "team_8_mixed", "agent_maze"])
+def test_persistent_buffer_mode_writes_the_same_rows(name):
+    """at_set_rows_mode(1): the step calls ship only the dynamic runs of every row (two bulk copies per row instead of one
+    per group) into buffers that were written in full once - raw fp32 rows, normalised fp32 rows (second image and in
+    place) and normalised fp16 rows must equal the whole-row writes of handles without the switch, on a ragged batch,
+    through auto-resets, with two alternating output buffers.  (Per-env mazes ignore the switch.)"""
+    import torch
+    spec = SWEEP[name]
+    N, seed, base = 1003, 21, 7
+    envs = [[_gpu(spec, N, seed, base, auto_reset=True) for _ in range(3)] for _ in range(2)]   # [full | persistent][kind]
+    for e in envs[0] + envs[1]:
+        e.reset()
+    ids = np.arange(base, base + N)
+    R, D, A = envs[0][0].R, envs[0][0].D, envs[0][0].A
+    dev = "cuda:0"
+    mk = lambda dt=torch.float32: [[torch.full((N, R * D), -7.0, device=dev, dtype=dt) for _ in range(2)] for _ in range(2)]
+    raw, n2, ni, h = mk(), mk(), mk(), mk(torch.float16)
+    for t in range(90):
+        acts = synthetic_actions(seed, ids, t, A) if A else None
+        ta = None if acts is None else torch.as_tensor(np.ascontiguousarray(acts, dtype=np.int32))
+        b = t & 1
+        if t == 2:                      # both buffers of every kind have been written in full once
+            for e in envs[1]:
+                e.core.set_rows_mode(True)
+        for m in range(2):
+            envs[m][0].core.step_norm(ta, n2[m][b], obs_out=raw[m][b])
+            envs[m][1].core.step_norm(ta, ni[m][b])
+            envs[m][2].core.step_norm16(ta, h[m][b])
+        for x, what in ((raw, "raw"), (n2, "norm (second image)"), (ni, "norm (in place)"), (h, "fp16")):
+            if not torch.equal(x[0][b], x[1][b]):
+                bad = (x[0][b] != x[1][b]).nonzero()[:6].tolist()
+                raise AssertionError("%s tick %d: %s rows differ at (env, col) %s" % (name, t, what, bad))
+    # the switch really skips the static block: a buffer that was never written keeps its filler there (fixed maps only)
+    lo, hi = envs[1][0].core.static_obs_range()
+    fresh = torch.full((N, R * D), -7.0, device=dev)
+    ta = None if not A else torch.as_tensor(np.ascontiguousarray(synthetic_actions(seed, ids, 90, A), dtype=np.int32))
+    envs[1][0].core.step(ta, obs_out=fresh)
+    rows = fresh.view(N, R, D)
+    if hi > lo and D % 4 == 0:
+        a4, b4 = (lo + 3) & ~3, hi & ~3
+        whole = (N // 8) * 8              # (the ragged last group takes the plain-store path and writes whole rows)
+        assert (rows[:whole, :, a4:b4] == -7.0).all() and (rows[:, :, :lo] != -7.0).any() and (rows[:, :, b4:] != -7.0).any()
+    else:
+        assert (rows != -7.0).all() or name == "agent_maze"
+
+
 @pytest.mark.parametrize("cap", ["1", "2", "3"])
 def test_simulation_specialisations_equal_the_generic_kernel(cap):
     """env_kernel<true, false, SPEC>: the simulation kernel compiled for a config class (SimT<SPEC>: team mode + smart

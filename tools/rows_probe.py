@@ -41,8 +41,15 @@ variants = [
 ]
 for t in range(400):
     core.step(acts[t % 64])
+for name, fn in variants[1:]:     # every buffer written in full once
+    fn(0); fn(1)
 base = None
+variants = variants + [("PERSISTENT BUFFERS (at_set_rows_mode)", None)] + [(n, f) for n, f in variants[1:]]
 for name, fn in variants:
+    if fn is None:
+        core.set_rows_mode(True)
+        print(name, flush=True)
+        continue
     for t in range(20):
         fn(t)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
