@@ -278,7 +278,9 @@ __host__ __device__ inline RowsSmem rows_smem_layout(int G, int n, int row_float
 
 // NT / NR / TEAM: compile-time shape (0 / 0 / -1: from the config); MAZE: per-env maps; PP: (env, slot) pairs a lane
 // prefetches per group (G * 6n <= 32 PP)
-template <int NT, int NR, int TEAM, bool MAZE, int PP>
+// NORMK: 0 = raw rows only, 1 = can also emit tick-normalised fp32 rows, 2 = tick-normalised fp16 rows (+ raw): every
+// build carries only its own code (the raw-rows kernel lost 15 % when the normalisers shared its body).
+template <int NT, int NR, int TEAM, bool MAZE, int PP, int NORMK>
 __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_constant__ KCfg c, const DevState st,
                                                           const uint8_t *__restrict__ mask, float *__restrict__ obs,
                                                           const float *__restrict__ g_tmpl, int lgG, int n_groups,
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     // in full every group and normalised in place) the tick-normalised rows
     // norm_half bit 0: the normalised rows leave as fp16 (always through a second image: the raw one stays incremental);
     // bit 1: persistent output buffers - the columns that never change on a fixed map are not written again
-    const bool norm = obs_norm != nullptr, half_out = norm && (norm_half & 1) != 0, norm2 = norm && (obs != nullptr || half_out),
+    const bool norm = NORMK != 0 && obs_norm != nullptr, half_out = NORMK == 2 && norm, norm2 = norm && (obs != nullptr || half_out),
                inplace = norm && !norm2;
     const TickNormK nk(SH::rows(c), norm_eps);
     const int G = 1 << lgG, n = SH::n(c), S = n * SLOTS_PER_TANK, nrows = SH::rows(c), RD = nrows * c.obs_dim;
@@ -421,7 +423,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         load_b(grp + gs, use_cnt, use_em);
         load_a(grp + 2 * gs, fill_cnt, fill_em);
         // the previous copy must be done reading the image
-        bulk_wait_read_all();   // (every lane: in persistent-buffer mode several lanes issue copies)
+        if (skip_static || lane == 0) bulk_wait_read_all();   // (persistent-buffer mode: several lanes issue copies)
         const bool all_emit = __all_sync(0xffffffffu, my_em);   // (also the warp barrier between phase 1 and 2)
         // ---- phase 2: 32 jobs per pass.  Position jobs first: a position that holds no bullet now and held none when
         // the image was last filled needs no work (it is still zero) - about 60 % of them - so the positions that do are
@@ -621,7 +623,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         group(grp, x_cnt, x_em, y_cnt, y_em);
         grp += gs;
     }
-    bulk_wait_read_all();   // shared memory must outlive the copies' reads
+    if (skip_static || lane == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
 }
 typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int, float *, float, int);
 
@@ -1177,9 +1179,9 @@ struct at_env {
     int sim_spec;             // SimT<SPEC> specialisation of the step's simulation kernel (0: generic; AT_NO_SPEC=1 forces it)
     bool pdl;                 // rows_kernel is launched as a programmatic dependent (AT_NO_PDL=1: plain launch)
     int rows_lgG, rows_grid, rows_warps;  // rows_kernel: log2(envs per group), persistent grid, warps per block
-    rows_kernel_fn rows_fn;   // the instantiation for this config's shape
+    rows_kernel_fn rows_fn, rows_fn_norm, rows_fn_half;   // this config's shape: raw rows only / + normalised fp32 / + normalised fp16
     size_t rows_smem, rows_smem_norm;   // (norm: with the second, normalised image)
-    int rows_grid_norm;
+    int rows_grid_norm, rows_grid_inplace;   // (in place: normalised fp32 rows only, one image)
     bool rows_skip_static;                // at_set_rows_mode: the steps' output buffers are persistent (static columns not rewritten)
     int rows_warps_h, rows_grid_h;        // fp16 normalised rows (at_step_norm16): warps per block, grid
     size_t rows_smem_h;
@@ -1247,7 +1249,7 @@ static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, 
     norm_half = norm_half && d_obs_norm;
     const int warps = norm_half ? env->rows_warps_h : env->rows_warps;
     const int want = (n_groups + warps - 1) / warps;
-    const int rgrid = norm_half ? env->rows_grid_h : ((d_obs_norm && d_obs) ? env->rows_grid_norm : env->rows_grid);
+    const int rgrid = norm_half ? env->rows_grid_h : ((d_obs_norm && d_obs) ? env->rows_grid_norm : (d_obs_norm ? env->rows_grid_inplace : env->rows_grid));
     cfg.gridDim = dim3((unsigned)(want < rgrid ? want : rgrid));
     cfg.blockDim = dim3(warps * 32);
     cfg.dynamicSmemBytes = norm_half ? env->rows_smem_h : ((d_obs_norm && d_obs) ? env->rows_smem_norm : env->rows_smem);
@@ -1257,7 +1259,7 @@ static int launch_rows_kernel(at_env *env, const uint8_t *d_mask, float *d_obs, 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = pdl ? 1 : 0;
-    CUDA_TRY(cudaLaunchKernelEx(&cfg, env->rows_fn, env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups,
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, norm_half ? env->rows_fn_half : (d_obs_norm ? env->rows_fn_norm : env->rows_fn), env->k, env->st, d_mask, (float *)d_obs, env->d_tmpl, env->rows_lgG, n_groups,
                                 (float *)d_obs_norm, norm_eps, (norm_half ? 1 : 0) | (allow_skip && env->rows_skip_static ? 2 : 0)));
     env->launches += 1;
     return AT_OK;
@@ -1407,15 +1409,19 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
                           (1 << lg) * k.n_tanks * SLOTS_PER_TANK > 96 || (1 << lg) * k.n_tanks > 32))
             --lg;
         const int pairs = (1 << lg) * k.n_tanks * SLOTS_PER_TANK;
-        if (k.map == AT_MAP_MAZE) env->rows_fn = rows_kernel<0, 0, -1, true, 3>;
-        else if (pairs <= 64 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) env->rows_fn = rows_kernel<4, 2, 1, false, 2>;
-        else if (pairs <= 96 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) env->rows_fn = rows_kernel<4, 2, 1, false, 3>;
-        else if (pairs <= 64 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) env->rows_fn = rows_kernel<2, 2, 0, false, 2>;
-        else env->rows_fn = rows_kernel<0, 0, -1, false, 3>;
+#define AT_ROWS_PICK(...) do { env->rows_fn = rows_kernel<__VA_ARGS__, 0>; env->rows_fn_norm = rows_kernel<__VA_ARGS__, 1>; \
+                               env->rows_fn_half = rows_kernel<__VA_ARGS__, 2>; } while (0)
+        if (k.map == AT_MAP_MAZE) AT_ROWS_PICK(0, 0, -1, true, 3);
+        else if (pairs <= 64 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) AT_ROWS_PICK(4, 2, 1, false, 2);
+        else if (pairs <= 96 && k.n_tanks == 4 && k.rows == 2 && k.team_layout) AT_ROWS_PICK(4, 2, 1, false, 3);
+        else if (pairs <= 64 && k.n_tanks == 2 && k.rows == 2 && !k.team_layout) AT_ROWS_PICK(2, 2, 0, false, 2);
+        else AT_ROWS_PICK(0, 0, -1, false, 3);
+#undef AT_ROWS_PICK
         env->rows_lgG = lg;
         env->rows_smem = rows_smem_layout(1 << lg, k.n_tanks, RD, W, 0).total;
         env->rows_smem_norm = rows_smem_layout(1 << lg, k.n_tanks, RD, W, 4).total;
         env->rows_grid_norm = prop.multiProcessorCount;
+        env->rows_grid_inplace = prop.multiProcessorCount;
         env->rows_grid = prop.multiProcessorCount;
         if (k.rows > 0) {
             if (env->rows_smem_norm > (size_t)prop.sharedMemPerBlockOptin) {
@@ -1425,6 +1431,8 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
             }
             // (never this handle's own size: see the note at the simulation kernels above)
             cudaFuncSetAttribute((const void *)env->rows_fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+            cudaFuncSetAttribute((const void *)env->rows_fn_norm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
+            cudaFuncSetAttribute((const void *)env->rows_fn_half, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prop.sharedMemPerBlockOptin);
             int bps = 1;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, (const void *)env->rows_fn, W * 32, env->rows_smem) != cudaSuccess || bps < 1) {
                 cudaGetLastError();
@@ -1434,24 +1442,30 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
             if (bp && atoi(bp) > 0 && atoi(bp) < bps) bps = atoi(bp);
             env->rows_grid = prop.multiProcessorCount * bps;
             int bpn = 1;
-            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpn, (const void *)env->rows_fn, W * 32, env->rows_smem_norm) != cudaSuccess || bpn < 1) {
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpn, (const void *)env->rows_fn_norm, W * 32, env->rows_smem_norm) != cudaSuccess || bpn < 1) {
                 cudaGetLastError();
                 bpn = 1;
             }
             env->rows_grid_norm = prop.multiProcessorCount * bpn;
+            int bpi = 1;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bpi, (const void *)env->rows_fn_norm, W * 32, env->rows_smem) != cudaSuccess || bpi < 1) {
+                cudaGetLastError();
+                bpi = 1;
+            }
+            env->rows_grid_inplace = prop.multiProcessorCount * bpi;
             // fp16 normalised rows: raw fp32 image + fp16 image per warp; the warps per block that put most warps on an SM
             int best_w = 1, best_tot = 0, best_b = 1;
             for (int w = RK_MAX_WARPS; w >= 1; --w) {
                 const size_t sm = rows_smem_layout(1 << lg, k.n_tanks, RD, w, 2).total;
                 if (sm > (size_t)prop.sharedMemPerBlockOptin) continue;
                 int b = 0;
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, (const void *)env->rows_fn, w * 32, sm) != cudaSuccess) { cudaGetLastError(); b = 0; }
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, (const void *)env->rows_fn_half, w * 32, sm) != cudaSuccess) { cudaGetLastError(); b = 0; }
                 if (b * w > best_tot) { best_tot = b * w; best_w = w; best_b = b; }
             }
             const char *wh = getenv("AT_ROWS_WARPS_H");
             if (wh && atoi(wh) >= 1 && atoi(wh) <= RK_MAX_WARPS) {
                 best_w = atoi(wh);
-                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&best_b, (const void *)env->rows_fn, best_w * 32,
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&best_b, (const void *)env->rows_fn_half, best_w * 32,
                                                                   rows_smem_layout(1 << lg, k.n_tanks, RD, best_w, 2).total) != cudaSuccess || best_b < 1) {
                     cudaGetLastError();
                     best_b = 1;
@@ -1899,8 +1913,8 @@ static unsigned long long *g_policy_dbg = nullptr;   // at_policy_debug_stamps
 
 static int policy_forward_impl(bool half, int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                                uint64_t seed, const int64_t *d_counter, void *stream) {
-    if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % 8 != 0 || dim > (half ? 2048 : 1024))
-        return fail(AT_ERR_ARG, "at_policy_forward: 1 or 2 policies, dim a multiple of 8 up to 1024 (fp16: 2048)");
+    if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % (half ? 8 : 4) != 0 || dim > (half ? 2048 : 1024))
+        return fail(AT_ERR_ARG, "at_policy_forward: 1 or 2 policies, dim a multiple of 4 up to 1024 (fp16: of 8 up to 2048)");
     const int kc = half ? at_tc::H_KC : at_tc::KC, k_chunks = (dim + kc - 1) / kc;
     const uint32_t all = k_chunks >= 32 ? 0xFFFFFFFFu : ((1u << k_chunks) - 1u);
     if (chunk_mask == 0) chunk_mask = all;
@@ -1913,7 +1927,7 @@ static int policy_forward_impl(bool half, int device, const at_policy *pol, int 
     for (int i = 0; i < 2; ++i) {
         const at_policy &q = pol[i < n_policies ? i : 0];
         if (!q.x || !q.w1 || !q.b1 || !q.w2 || !q.b2 || !q.w3 || !q.b3 || !q.actions || !q.logprobs || !q.values ||
-            q.x_row_stride % 8 != 0 || q.x_row_stride < dim)
+            q.x_row_stride % (half ? 8 : 4) != 0 || q.x_row_stride < dim)
             return fail(AT_ERR_ARG, "at_policy_forward: null buffer or a row stride that is not a multiple of 4 floats");
         if ((((uintptr_t)q.x) | ((uintptr_t)q.w1) | ((uintptr_t)q.w2)) & 15u)
             return fail(AT_ERR_ARG, "at_policy_forward: x / w1 / w2 must be 16-byte aligned");

@@ -218,8 +218,8 @@ class FusedPolicies:
             nets = [a.critic] + list(a.actor)
             if [int(m[4].out_features) for m in nets] != [1, 3, 3, 2] or any(m[0].out_features != 128 or m[2].out_features != 128 for m in nets):
                 raise ValueError("at_policy_forward serves the reference architecture only (128 hidden units, heads 3 / 3 / 2)")
-        if self.D % 8 != 0 or self.D > 1024:
-            raise ValueError("at_policy_forward needs an observation width that is a multiple of 8, up to 1024")
+        if self.D % (8 if self.half else 4) != 0 or self.D > 1024:     # (TMA: 16-byte row pitch)
+            raise ValueError("at_policy_forward needs an observation width that is a multiple of 4 (fp16: 8), up to 1024")
         n = len(self.agents)
         f = dict(dtype=torch.float32, device=self.device)
         wt = torch.float16 if self.half else torch.float32

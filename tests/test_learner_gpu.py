@@ -353,6 +353,27 @@ def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows, half):
             assert (lp_all.gather(-1, a.unsqueeze(-1)).squeeze(-1) - lps[:, i, h]).abs().max().item() < 1e-5
 
 
+def test_policy_forward_on_the_1v1_rows_single_policy():
+    """One policy, D = 388 (the 1v1 rows of train_ppo_bot.py; not a multiple of 8: TF32 kernel only), ragged row count,
+    rows taken from a [N, 2, D] tensor with stride 2 D."""
+    from alphatank_b200.learner.ppo_utils import FusedPolicies
+    dev = torch.device("cuda:0")
+    D, n = 388, 777
+    agents = _scaled_agents(1, D, dev, seed=8)
+    torch.manual_seed(9)
+    both = torch.randn((n, 2, D), device=dev)
+    obs = both[:, 1:2]
+    fp = FusedPolicies(agents, D, dev)
+    with pytest.raises(ValueError):
+        FusedPolicies(agents, D, dev, half=True)
+    acts = torch.zeros((n, 1, 3), dtype=torch.int32, device=dev)
+    lps, vals, out9 = torch.zeros((n, 1, 3), device=dev), torch.zeros((n, 1), device=dev), torch.zeros((1, n, 9), device=dev)
+    fp.forward(obs, acts, lps, vals, torch.ones(1, dtype=torch.int64, device=dev), seed=3, out9=out9)
+    ref = _fp64_out9(agents[0], obs[:, 0]).float()
+    assert (out9[0] - ref).abs().max().item() < 1e-2
+    assert torch.equal(vals[:, 0], out9[0][:, 0])
+
+
 def test_policy_forward_draws_follow_the_softmax():
     """Identical rows -> identical logits; the Gumbel-max draws over 200 000 rows must reproduce softmax(logits) per head
     (4 sigma of the binomial), and a second tick (counter advanced) must draw differently."""
