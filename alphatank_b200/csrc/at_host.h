@@ -176,6 +176,12 @@ inline int sim_spec_for(const KCfg &k, int cap = 3) {
     if (spec == 2 && k.ctrl[0] == AT_CTRL_AGENT && k.ctrl[1] == AT_CTRL_AGENT && k.ctrl[2] == AT_CTRL_BOT &&
         k.ctrl[3] == AT_CTRL_BOT && k.team[0] == k.team[1] && k.team[2] == k.team[3] && k.team[0] != k.team[2])
         spec = 3;
+    // the 1v1 wrappers on a fixed map: agent mode (4), bot_agent against the smart bot (5); any cap below 3 = generic
+    if (k.n_tanks == 2 && k.map != AT_MAP_MAZE && !k.team_layout) {
+        if (k.mode == AT_MODE_AGENT && k.ctrl[0] == AT_CTRL_AGENT && k.ctrl[1] == AT_CTRL_AGENT) return cap >= 3 ? 4 : 0;
+        if (k.mode == AT_MODE_BOT_AGENT && k.ctrl[0] == AT_CTRL_BOT && k.bot_type[0] == AT_BOT_SMART && k.ctrl[1] == AT_CTRL_AGENT)
+            return cap >= 3 ? 5 : 0;
+    }
     return spec < cap ? spec : cap;
 }
 

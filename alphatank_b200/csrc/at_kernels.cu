@@ -1223,7 +1223,11 @@ static int launch_env_kernel(at_env *env, bool is_step, const int32_t *d_actions
     HostSignal sig = {nullptr, nullptr, 0u, env->dbg_times, epw};
     if (post_to_host) { sig.counter = env->d_sig_counter; sig.host_flag = env->h_sig_flag_dev; sig.epoch = ++env->sig_epoch; }
     const bool rows = (d_obs != nullptr || d_obs_norm != nullptr) && env->k.rows > 0;
-    if (is_step && env->sim_spec == 3)
+    if (is_step && env->sim_spec == 5)
+        env_kernel<true, 5><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
+    else if (is_step && env->sim_spec == 4)
+        env_kernel<true, 4><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
+    else if (is_step && env->sim_spec == 3)
         env_kernel<true, 3><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
     else if (is_step && env->sim_spec == 2)
         env_kernel<true, 2><<<grid, BS, env->smem_bytes_sim, s>>>(env->k, env->st, d_actions, d_mask, d_rewards, d_done, sig);
@@ -1371,6 +1375,8 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
         cudaFuncSetAttribute(env_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(env_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(env_kernel<true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(env_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+        cudaFuncSetAttribute(env_kernel<true, 5>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         cudaFuncSetAttribute(env_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
         if (env->smem_bytes_sim > (size_t)lim) {
             cudaFree(env->arena);

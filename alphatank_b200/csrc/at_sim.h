@@ -435,16 +435,20 @@ AT_HD int select_bit(M128 m, int k) {
 template <int SPEC>
 struct SimT {
     static constexpr int CS = BS;   // stride of the block's working-set columns
-    AT_HD int cfg_mode() const { return SPEC >= 1 ? 3 : c.mode; }
-    AT_HD int cfg_bot_type(int i) const { return SPEC >= 1 ? 0 : c.bot_type[i]; }
+    // SPEC 4 / 5: the 1v1 wrappers on a fixed map - 4 = agent mode (two policy-driven tanks: every bot drops out),
+    // 5 = bot_agent against the smart bot (train_ppo_bot.py --bot-type smart, BASELINE config 2); TERMINATE_TIME stays a
+    // run-time value there
+    static constexpr bool kTeam = SPEC >= 1 && SPEC <= 3, kOne = SPEC >= 4;
+    AT_HD int cfg_mode() const { return kTeam ? 3 : (SPEC == 4 ? 0 : (SPEC == 5 ? 1 : c.mode)); }
+    AT_HD int cfg_bot_type(int i) const { return (kTeam || SPEC == 5) ? 0 : c.bot_type[i]; }
     AT_HD bool cfg_maze() const { return SPEC >= 1 ? false : c.map == 2; }
-    AT_HD bool cfg_team_layout() const { return SPEC >= 1 ? true : c.team_layout != 0; }
-    AT_HD int cfg_terminate() const { return SPEC >= 1 ? 0 : c.terminate_time; }
-    AT_HD int cfg_n() const { return SPEC >= 2 ? 4 : c.n_tanks; }   // SPEC 2 = SPEC 1 with exactly four tanks
+    AT_HD bool cfg_team_layout() const { return kTeam ? true : (kOne ? false : c.team_layout != 0); }
+    AT_HD int cfg_terminate() const { return kTeam ? 0 : c.terminate_time; }
+    AT_HD int cfg_n() const { return (SPEC == 2 || SPEC == 3) ? 4 : (kOne ? 2 : c.n_tanks); }   // SPEC 2 = SPEC 1 with exactly four tanks
     // SPEC 3 = SPEC 2 with the 2a_vs_2b layout: tanks 0, 1 = one team's agents, tanks 2, 3 = the other team's smart bots
     AT_HD int cfg_team(int i) const { return SPEC == 3 ? (i >> 1) : c.team[i]; }
     AT_HD uint32_t cfg_team_members(int i) const { return SPEC == 3 ? (i < 2 ? 3u : 12u) : c.team_members[i]; }
-    AT_HD int cfg_ctrl(int i) const { return SPEC == 3 ? (i >> 1) : c.ctrl[i]; }
+    AT_HD int cfg_ctrl(int i) const { return SPEC == 3 ? (i >> 1) : (SPEC == 4 ? 0 : (SPEC == 5 ? (i == 0 ? 1 : 0) : c.ctrl[i])); }
     AT_HD int cfg_agent_tank(int k) const { return SPEC == 3 ? k : c.agent_tank[k]; }
     AT_HD int cfg_bot_tank(int k) const { return SPEC == 3 ? 2 + k : c.bot_tank[k]; }
     AT_HD int cfg_bot_ord(int i) const { return SPEC == 3 ? (i >= 2 ? i - 2 : 0) : c.bot_ord[i]; }
@@ -739,7 +743,11 @@ struct SimT {
         BOut o;
         bullet_eval(tid, x, y, m, alive_bits, o);
         const int owner = (int)(m & 15u);
-        for (int k = 0; k < o.n_hi; ++k) TREW(owner) += 0.01;
+        if (o.n_hi) {   // the same additions in the same order, through a register instead of a shared-memory round trip each
+            double t = TREW(owner);
+            for (int k = 0; k < o.n_hi; ++k) t += 0.01;
+            TREW(owner) = t;
+        }
         near_tanks |= o.near;
         x = o.nx; y = o.ny; m = o.m;
         if (o.victim >= 0) { commit_hit(owner, o.victim); return true; }
@@ -834,11 +842,13 @@ struct SimT {
         const double mx = TX(i), my = TY(i);
         // only the candidates flagged by the bullet pass / shoot() are visited, in slot order (= list order);
         // every other enemy bullet is provably >= 100 px away and would hit `continue` (sprite.py:508)
-        for (bool first = true; cand; cand &= cand - 1, first = false) {
-            const int r = ctz64(cand);
-            uint64_t m = pm;
-            double bxv = px, byv = py;
-            if (!first) { m = st.bmeta[G(r)]; bxv = st.bx[G(r)]; byv = st.by[G(r)]; }
+        // (the next candidate's record is requested before the current one is processed: one L2 round trip in flight
+        // behind the arithmetic instead of one exposed per candidate)
+        uint64_t m = pm, nm = 0;
+        double bxv = px, byv = py, nbx = 0.0, nby = 0.0;
+        for (; cand; cand &= cand - 1, m = nm, bxv = nbx, byv = nby) {
+            const uint64_t rest = cand & (cand - 1);
+            if (rest) { const int r2 = ctz64(rest); nm = st.bmeta[G(r2)]; nbx = st.bx[G(r2)]; nby = st.by[G(r2)]; }
             if (cfg_team((int)(m & 15u)) == myteam) continue;
             const double ex_ = mx - bxv;
             if (fabs(ex_) >= 101.0) continue;                          // distance >= 100 for sure

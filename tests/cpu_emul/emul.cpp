@@ -114,7 +114,9 @@ static int g_spec_cap = 3;
 static void run(em_env *env, bool is_step, const int32_t *actions, const uint8_t *mask, float *obs, float *rewards,
                 uint8_t *done) {
     const int spec = is_step ? sim_spec_for(env->k, g_spec_cap) : 0;
-    if (spec == 3) run_t<3>(env, is_step, actions, mask, obs, rewards, done);
+    if (spec == 5) run_t<5>(env, is_step, actions, mask, obs, rewards, done);
+    else if (spec == 4) run_t<4>(env, is_step, actions, mask, obs, rewards, done);
+    else if (spec == 3) run_t<3>(env, is_step, actions, mask, obs, rewards, done);
     else if (spec == 2) run_t<2>(env, is_step, actions, mask, obs, rewards, done);
     else if (spec == 1) run_t<1>(env, is_step, actions, mask, obs, rewards, done);
     else run_t<0>(env, is_step, actions, mask, obs, rewards, done);

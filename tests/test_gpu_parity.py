@@ -436,6 +436,37 @@ def test_simulation_specialisations_equal_the_generic_kernel(cap):
         assert np.array_equal(sa["tanks"][f][:, :4], sb["tanks"][f][:, :4]), f
 
 
+@pytest.mark.parametrize("name", ["agent_t96", "agent_nobuff_battlefield", "botagent_smart_weak", "botagent_smart_battlefield_t128"])
+def test_1v1_specialisations_equal_the_generic_kernel(name):
+    """SimT<4> (1v1 agent mode) and SimT<5> (1v1 bot_agent against the smart bot) on fixed maps against the generic
+    kernel (AT_NO_SPEC=1): same rewards, done flags, rows and state through auto-resets and TERMINATE_TIME."""
+    spec = SWEEP[name]
+    N, seed, base = 1500, 23, 64
+    old = os.environ.get("AT_NO_SPEC")
+    try:
+        os.environ.pop("AT_NO_SPEC", None)
+        a = _gpu(spec, N, seed, base, auto_reset=True)
+        os.environ["AT_NO_SPEC"] = "1"
+        b = _gpu(spec, N, seed, base, auto_reset=True)
+    finally:
+        if old is None:
+            os.environ.pop("AT_NO_SPEC", None)
+        else:
+            os.environ["AT_NO_SPEC"] = old
+    assert np.array_equal(a.reset(), b.reset())
+    ids = np.arange(base, base + N)
+    for t in range(300):
+        acts = synthetic_actions(seed, ids, t, a.A)
+        oa, ra, da = a.step(acts)
+        ob, rb, db = b.step(acts)
+        assert np.array_equal(da, db) and np.array_equal(ra, rb) and np.array_equal(oa, ob), "tick %d" % t
+    sa, sb = a.get_state(), b.get_state()
+    for f in ("n_bullets", "tick", "training_step", "episode_steps", "rng_ctr", "zones"):
+        assert np.array_equal(sa[f], sb[f]), f
+    for f in ("x", "y", "reward", "angle", "alive", "num_hit", "num_be_hit"):
+        assert np.array_equal(sa["tanks"][f][:, :2], sb["tanks"][f][:, :2]), f
+
+
 def test_delta_reward_mode_telescopes_to_the_reference_cumulative_rewards():
     """reward_mode="delta" (both reward forms): the per-step increments of the reference's cumulative
     per-episode rewards (quirk F1) - summed over an episode they give the cumulative stream back; explicit masked

@@ -37,6 +37,8 @@ SWEEP = {
     "agent_t96": _spec("agent", [("A", "agent", None), ("B", "agent", None)], tt=96),
     "botagent_smart_maze": _spec("bot_agent", [("A", "bot", "smart"), ("B", "agent", None)], "maze"),
     "botagent_dodge_weak": _spec("bot_agent", [("A", "bot", "dodge"), ("B", "agent", None)], weakness=0.6),
+    "botagent_smart_weak": _spec("bot_agent", [("A", "bot", "smart"), ("B", "agent", None)], weakness=0.8),            # SPEC 5
+    "botagent_smart_battlefield_t128": _spec("bot_agent", [("A", "bot", "smart"), ("B", "agent", None)], "battlefield", tt=128),
     "arena_def_dodge_t200": _spec("arena", [("A", "bot", "defensive"), ("B", "bot", "dodge")], tt=200),
     "arena_random_aggr_maze": _spec("arena", [("A", "bot", "random"), ("B", "bot", "aggressive")], "maze"),
     "team_vs_bot": _spec("team", T["team_vs_bot_configs"]),
@@ -193,7 +195,8 @@ def test_simulation_specialisations_agree(cap):
     every level, so each specialisation and the generic build run the same 2a_vs_2b batch."""
     specs = [SWEEP["team_vs_bot"],
              _spec("team", [("A", "agent", None), ("B", "bot", "smart"), ("B", "bot", "smart"), ("A", "agent", None)]),   # SPEC 2
-             _spec("team", [("A", "agent", None), ("B", "bot", "smart"), ("C", "bot", "smart")], "battlefield")]        # SPEC 1
+             _spec("team", [("A", "agent", None), ("B", "bot", "smart"), ("C", "bot", "smart")], "battlefield"),        # SPEC 1
+             SWEEP["agent_t96"], SWEEP["botagent_smart_weak"]]          # SPEC 4 / 5 (any cap below 3: the generic build)
     emul_env.lib().em_set_spec_cap(cap)
     try:
         for spec in specs:
