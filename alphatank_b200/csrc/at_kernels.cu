@@ -248,6 +248,9 @@ __device__ __forceinline__ void tick_norm_column(const float (&v)[RMAX], int row
 // loop is bounded by the HBM write stream.
 // Launched as a programmatic dependent of env_kernel<.., false>: the prologue (tables, static columns) overlaps
 // the simulation's tail; griddepcontrol.wait orders everything else behind the simulation's stores.
+#ifndef AT_ROWS_SINGLE_BODY
+#define AT_ROWS_SINGLE_BODY 1
+#endif
 constexpr int RK_MAX_WARPS = 16;   // warps per block: a launch parameter (blockDim.x / 32)
 struct RowsSmem {   // per warp, after the block's trig table
     size_t off_img, off_nimg, off_rx, off_ry, off_rm, off_tx, off_ty, off_wlo, off_whi, off_tp, off_zn, off_emit, off_occ, off_jl, per_warp, total;
@@ -615,6 +618,16 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
     load_a(g0, x_cnt, x_em);
     load_a(g0 + gs, y_cnt, y_em);
     load_b(g0, x_cnt, x_em);
+#if AT_ROWS_SINGLE_BODY
+    // one copy of the group body: y = counts of the next group, x = being filled, handed over at the end of the
+    // iteration (the moves wait for loads that were issued a whole group of work earlier)
+#pragma unroll 1
+    for (int grp = g0; grp < n_groups; grp += gs) {
+        group(grp, y_cnt, y_em, x_cnt, x_em);
+#pragma unroll
+        for (int pp = 0; pp < PP; ++pp) { y_cnt[pp] = x_cnt[pp]; y_em[pp] = x_em[pp]; }
+    }
+#else
     for (int grp = g0;;) {   // x / y alternate between "counts of the next group" and "being filled"
         if (grp >= n_groups) break;
         group(grp, y_cnt, y_em, x_cnt, x_em);
@@ -623,6 +636,7 @@ __global__ void __launch_bounds__(RK_MAX_WARPS * 32) rows_kernel(const __grid_co
         group(grp, x_cnt, x_em, y_cnt, y_em);
         grp += gs;
     }
+#endif
     if (skip_static || lane == 0) bulk_wait_read_all();   // shared memory must outlive the copies' reads
 }
 typedef void (*rows_kernel_fn)(const KCfg, const DevState, const uint8_t *, float *, const float *, int, int, float *, float, int);
