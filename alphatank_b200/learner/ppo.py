@@ -111,6 +111,7 @@ class PPOLearner:
         self.running = [RunningMeanStd((obs_dim,), device=self.device) for _ in range(num_agents)]
         self._fused = None            # FusedPolicies per pair of agents (cuda: at_policy_forward), False: not available
         self._static = None
+        self._static_keys = set()
 
     # ---- the tcgen05 inference path (csrc/at_policy_tc.cuh)
     def fused_policies(self, half=False):
@@ -126,14 +127,26 @@ class PPOLearner:
                 except ValueError:
                     self._fused = False
                 if self._fused and self._static is not None:
-                    self.set_static_columns(*self._static)
+                    for k, f in enumerate(self._fused):
+                        f.set_static(self._static[0], self._static[1], self._static[2][2 * k:2 * k + 2])
         return self._fused or None
 
-    def set_static_columns(self, lo, hi, y):
-        """Observation columns [lo, hi) hold y[i, lo:hi] in every row agent i will ever see (BatchedTankEnv.
-        static_obs_range + one normalised row): the fused inference path folds them into the first layers' bias.
-        Only meaningful for stateless normalisers ("tick" / "none")."""
-        self._static = (int(lo), int(hi), y.detach().clone())
+    def set_static_columns(self, lo, hi, y, key=None):
+        """Observation columns [lo, hi) hold y[i, lo:hi] in every row agent i sees FROM ONE ENV (BatchedTankEnv.
+        static_obs_range + one normalised row): act(fold=key) on that env's rows folds them into the first layers' bias.
+        Only meaningful for stateless normalisers ("tick" / "none").  ``key`` names the env the values belong to
+        (collect_rollout uses id(env.core)): rows of any other env are contracted in full."""
+        lo, hi = int(lo), int(hi)
+        if key is not None and self._static is not None and self._static_keys:
+            # a second env on the same learner (cycle trainer: one handle per bot type): its rows may use the fold only if
+            # they carry the same static values - the first env's fold may be baked into a captured graph
+            same = (lo, hi) == self._static[:2] and torch.equal(y[:, lo:hi].to(self._static[2].device, self._static[2].dtype),
+                                                                self._static[2][:, lo:hi])
+            if same:
+                self._static_keys.add(key)
+            return
+        self._static_keys = set() if key is None else {key}
+        self._static = (lo, hi, y.detach().clone())
         if self._fused:
             for k, f in enumerate(self._fused):
                 f.set_static(int(lo), int(hi), self._static[2][2 * k:2 * k + 2])
@@ -164,9 +177,10 @@ class PPOLearner:
         return x
 
     @torch.no_grad()
-    def act(self, obs_nad, out=None):
+    def act(self, obs_nad, out=None, fold=None):
         """obs [N, A, D] -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A] (written into ``out`` = the
-        three tensors when given, e.g. a rollout buffer's slots)."""
+        three tensors when given, e.g. a rollout buffer's slots).  ``fold``: the key given to set_static_columns when the
+        rows come from that env (its static columns are then folded into the bias); None: contract every column."""
         if obs_nad.is_cuda:   # one sampling kernel per policy, written in place (at_sample_heads)
             n, heads = obs_nad.shape[0], len(self.agents[0].actor)
             if out is not None:
@@ -182,12 +196,11 @@ class PPOLearner:
             fused = self.fused_policies(half)
             if fused is None and half:
                 raise RuntimeError("fp16 observations need the tcgen05 inference path (at_policy_forward16)")
-            if fused is not None and self.cfg.obs_norm == "running" and fused[0].chunk_mask:
-                raise RuntimeError("static-column folding needs a stateless observation normaliser")
+            do_fold = fold is not None and fold in self._static_keys and self.cfg.obs_norm in ("tick", "none")
             if fused is not None:   # the whole forward + sampling of two policies per launch (tcgen05, at_policy_forward)
                 for k, f in enumerate(fused):
                     f.forward(obs_nad[:, 2 * k:2 * k + 2], acts[:, 2 * k:2 * k + 2], lps[:, 2 * k:2 * k + 2], vals[:, 2 * k:2 * k + 2],
-                              self._sample_ctr, self.seed, 2 * k + self.A * _rank())
+                              self._sample_ctr, self.seed, 2 * k + self.A * _rank(), fold=do_fold)
                 return acts, lps, vals
             for i, agent in enumerate(self.agents):
                 agent.sample_cuda(obs_nad[:, i], acts[:, i], lps[:, i], self._sample_ctr, self.seed, i + self.A * _rank(),
@@ -290,13 +303,14 @@ def collect_rollout(env, learner, buf, first=False):
     prev_cum = getattr(buf, "_prev_cum", None)
     if prev_cum is None or first:
         prev_cum = torch.zeros((buf.N, buf.A), dtype=torch.float32, device=buf.obs.device)
+    key = id(core)
     if first and buf.obs.is_cuda and learner.cfg.obs_norm in ("tick", "none") and hasattr(core, "static_obs_range"):
         lo, hi = core.static_obs_range()        # fixed maps: the wall / maze block is the same in every row for ever
         if hi > lo:
-            learner.set_static_columns(lo, hi, buf.obs[0][0])
+            learner.set_static_columns(lo, hi, buf.obs[0][0], key=key)
     for t in range(T):
         if buf.obs.is_cuda:
-            learner.act(buf.obs[t], out=(buf.actions[t], buf.logprobs[t], buf.values[t]))
+            learner.act(buf.obs[t], out=(buf.actions[t], buf.logprobs[t], buf.values[t]), fold=key)
         else:
             a, lp, v = learner.act(buf.obs[t])
             buf.actions[t].copy_(a)

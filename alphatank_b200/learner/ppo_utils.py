@@ -225,6 +225,7 @@ class FusedPolicies:
         wt = torch.float16 if self.half else torch.float32
         self.w1 = torch.empty((n, 512, self.D), dtype=wt, device=self.device)
         self.b1 = torch.empty((n, 512), **f)
+        self.b1_fold = torch.empty((n, 512), **f)        # b1 + W1[:, dropped chunks] . y (forward(fold=True))
         self.w2 = torch.empty((n, 4, 128, 128), dtype=wt, device=self.device)
         self.b2 = torch.empty((n, 4, 128), **f)
         self.w3 = torch.empty((n, 9, 128), **f)
@@ -255,10 +256,11 @@ class FusedPolicies:
             nets = [a.critic] + list(a.actor)
             w1 = torch.cat([m[0].weight for m in nets], dim=0)
             b1 = torch.cat([m[0].bias for m in nets], dim=0)
-            if self._fold_cols is not None:      # fp32 fold of the dropped columns (exact weights, before the TF32 rounding)
-                b1 = b1 + w1[:, self._fold_cols] @ self._fold_y[i]
             self.w1[i].copy_(w1)
             self.b1[i].copy_(b1)
+            if self._fold_cols is not None:      # fp32 fold of the dropped columns (exact weights, before the TF32 rounding)
+                b1 = b1 + w1[:, self._fold_cols] @ self._fold_y[i]
+            self.b1_fold[i].copy_(b1)
             self.w2[i].copy_(torch.stack([m[2].weight for m in nets]))
             self.b2[i].copy_(torch.stack([m[2].bias for m in nets]))
             self.w3[i].copy_(torch.cat([m[4].weight for m in nets], dim=0))
@@ -267,10 +269,12 @@ class FusedPolicies:
             _round_tf32_(self.w1)
             _round_tf32_(self.w2)
 
-    def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None):
+    def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None, fold=None):
         """obs [N, A, D] (A = the number of packed policies) -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]
         written in place; ``counter``: device int64 [1] the caller advances once per tick; ``out9``: optional
-        [A, N, 9] (value + 8 logits per row)."""
+        [A, N, 9] (value + 8 logits per row).  ``fold``: contract only the K chunks kept by set_static() (the rows MUST hold
+        the static values given there); default: whenever set_static() dropped chunks."""
+        fold = bool(self.chunk_mask) if fold is None else (bool(fold) and bool(self.chunk_mask))
         import ctypes as C
 
         from .. import _capi
@@ -283,7 +287,8 @@ class FusedPolicies:
             x, a, lp, v = obs_nad[:, i], actions_out[:, i], logprobs_out[:, i], values_out[:, i]
             q = pols[i]
             q.x, q.x_row_stride = x.data_ptr(), x.stride(0)
-            q.w1, q.b1, q.w2, q.b2 = self.w1[i].data_ptr(), self.b1[i].data_ptr(), self.w2[i].data_ptr(), self.b2[i].data_ptr()
+            q.w1, q.b1 = self.w1[i].data_ptr(), (self.b1_fold if fold else self.b1)[i].data_ptr()
+            q.w2, q.b2 = self.w2[i].data_ptr(), self.b2[i].data_ptr()
             q.w3, q.b3 = self.w3[i].data_ptr(), self.b3[i].data_ptr()
             q.actions, q.act_stride = a.data_ptr(), a.stride(0)
             q.logprobs, q.lp_stride = lp.data_ptr(), lp.stride(0)
@@ -291,7 +296,7 @@ class FusedPolicies:
             q.out9 = out9[i].data_ptr() if out9 is not None else None
             q.stream_id = int(stream_base) + i
         fn = _capi.lib().at_policy_forward16 if self.half else _capi.lib().at_policy_forward
-        _capi.check(fn(obs_nad.device.index, pols, A, n, self.D, int(self.chunk_mask), int(seed), C.c_void_p(counter.data_ptr()),
+        _capi.check(fn(obs_nad.device.index, pols, A, n, self.D, int(self.chunk_mask) if fold else 0, int(seed), C.c_void_p(counter.data_ptr()),
                        C.c_void_p(torch.cuda.current_stream(obs_nad.device).cuda_stream)), "at_policy_forward")
 
 
