@@ -1956,7 +1956,7 @@ static int policy_forward_impl(bool half, int device, const at_policy *pol, int 
                                 at_tc::make_map_2d_f16(&maps[4 + i], q.w2, 512, 128, 128 * 2, 128))
                              : (at_tc::make_map_2d(&maps[i], q.x, (uint64_t)n_rows, (uint64_t)dim, (uint64_t)q.x_row_stride * 4, at_tc::TM) &&
                                 at_tc::make_map_2d(&maps[2 + i], q.w1, 512, (uint64_t)dim, (uint64_t)dim * 4, 256) &&
-                                at_tc::make_map_2d(&maps[4 + i], q.w2, 512, 128, 128 * 4, 128));
+                                at_tc::make_map_2d_f16(&maps[4 + i], q.w2, 512, 128, 128 * 2, 128));   // (W2 is fp16 in both)
         if (!ok)
             return fail(AT_ERR_CUDA, "at_policy_forward: cuTensorMapEncodeTiled is not available or rejected the tensors");
         at_tc::PolicyIO &io = P.io[i];
@@ -1976,18 +1976,18 @@ static int policy_forward_impl(bool half, int device, const at_policy *pol, int 
     static int sms[64] = {0};
     if (device < 0 || device >= 64) return fail(AT_ERR_ARG, "at_policy_forward: device index out of range");
     if (!attr_set[device]) {
-        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::F_SMEM_BYTES));
-        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::H_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::H_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(at_tc::policy_forward_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)at_tc::H_SMEM_BYTES));
         CUDA_TRY(cudaDeviceGetAttribute(&sms[device], cudaDevAttrMultiProcessorCount, device));
         attr_set[device] = true;
     }
     const int n_tiles = P.tiles_per_policy * n_policies;
     const int grid = n_tiles < sms[device] ? n_tiles : sms[device];
     if (half)
-        at_tc::policy_forward16_kernel<<<grid, at_tc::H_THREADS, at_tc::H_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+        at_tc::policy_forward_kernel<true><<<grid, at_tc::H_THREADS, at_tc::H_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
                                                                                                            maps[4], maps[5], P);
     else
-        at_tc::policy_forward_kernel<<<grid, at_tc::F_THREADS, at_tc::F_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+        at_tc::policy_forward_kernel<false><<<grid, at_tc::H_THREADS, at_tc::H_SMEM_BYTES, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
                                                                                                          maps[4], maps[5], P);
     CUDA_TRY(cudaGetLastError());
     return AT_OK;

@@ -206,33 +206,29 @@ inline bool make_map_2d(CUtensorMap *map, const void *base, uint64_t rows, uint6
 
 
 // ====================================================================================================================
-// policy_forward_kernel - a policy's whole inference pass in ONE kernel (models/ppo_utils.py:31-62, the four MLPs
+// policy_forward_kernel<HALF_IN> - a policy's whole inference pass in ONE kernel (models/ppo_utils.py:31-62, the four MLPs
 // D -> 128 -> 128 -> {1, 3, 3, 2} of train_multi_ppo.py:96-116's `get_action_and_value`): TMA-loaded observation tiles ->
-// first layers on tcgen05.mma (TF32, fp32 accumulators in tensor memory) -> tanh -> second layers on tcgen05.mma ->
-// tanh -> output layers -> log-softmax -> Gumbel-max draw.  Neither the [N, 512] activations nor the logits go to HBM.
+// first layers on tcgen05.mma (fp32 accumulators in tensor memory) -> tanh -> second layers on tcgen05.mma -> tanh ->
+// output layers -> log-softmax -> Gumbel-max draw.  Neither the [N, 512] activations nor the logits go to HBM.
+//   HALF_IN = true   fp16 rows (at_step_norm16) and fp16 W1: kind::f16, K chunks of 64 columns
+//   HALF_IN = false  fp32 rows (at_step_norm) and fp32 W1: kind::tf32 (the tensor core reads the upper 19 bits), K chunks of 32
+// Either way a chunk is one 128-byte swizzle row per matrix row, the hidden activations and W2 are fp16 (tanh's output
+// lies in [-1, 1]; fp16 carries TF32's 10 mantissa bits) and everything is accumulated in fp32.
 //
 // A CTA (one per SM, persistent over 128-row tiles) has three roles:
-//   warp 0, one lane   TMA producer: a three-slot ring of {x chunk [128 x 32], W1 chunk [256 x 32]} for the first layers
-//                      (two passes over K per tile: networks 0-1 into TMEM columns 0-255, networks 2-3 into 256-511),
-//                      then W2 of each network through the same ring (two slots of two [128 x 32] chunks);
-//   warp 1, one lane   MMA issuer: first layers (M 128, N 256, K 8 per instruction), and for every network, once its
-//                      tanh'd activations are in shared memory, the second layer (M 128, N 128) into the network's own
-//                      128 TMEM columns (their first-layer values have been read out by then);
-//   warps 2-5          epilogue, thread = row: tcgen05.ld the first-layer columns of a network, + bias, tanh, store them
-//                      as the second layer's A operand in the 128-byte-swizzle layout the tensor core reads; later
-//                      tcgen05.ld the second-layer columns, + bias, tanh, dot with the <= 3 output rows, sample.
-// While the tensor core runs a tile's second half the epilogue converts the first, and so on down the chain (barriers:
-// acc1_full[half], h1_ready, l2_done, acc_free[half]); K chunks that only hold columns which are constant for the
-// handle's lifetime (the wall / maze block of a fixed map: 281 of 528 columns) can be left out by the caller, their
-// contribution folded into the bias (`chunk_mask`, at_policy_forward).
-constexpr int F_STAGES = 3;
-constexpr uint32_t FA_BYTES = TM * KC * 4;              // 16 KB: x chunk
-constexpr uint32_t FB_BYTES = 256 * KC * 4;             // 32 KB: W1 chunk of one half (or two W2 chunks)
-constexpr uint32_t F_STAGE_BYTES = FA_BYTES + FB_BYTES;
-constexpr uint32_t H1_BYTES = 4 * FA_BYTES;             // 64 KB: one network's activations, four K chunks
+//   warp 0, one lane   TMA producer: a three-slot ring of {x chunk [128 rows], W1 chunk [256 rows]} (48 KB) for the first
+//                      layers of a PAIR of networks, and W2 of each network as one slot;
+//   warp 1, one lane   MMA issuer: the pair's first layers (M 128, N 256) into tensor-memory columns 0-255 (X); for every
+//                      network, once its activations are in shared memory, the second layer (M 128, N 128) into
+//                      Y[j & 1] = columns 256 + 128 (j & 1).  X is free as soon as its two networks are converted, so the
+//                      next pair's first layers run while the previous pair is read out of Y;
+//   warps 2-17         epilogue, thread = (row, quarter of a network's columns): tcgen05.ld, + bias, tanh.approx, fp16,
+//                      16-byte stores into the second layer's A operand in the 128-byte-swizzle layout the tensor core
+//                      reads; later tcgen05.ld of the second layer, + bias, tanh, dot with the <= 3 output rows; the four
+//                      quarters of a row meet in shared memory; the heads are sampled once per tile.
+// K chunks that only hold columns which are constant for the handle's lifetime (the wall / maze block of a fixed map: 281 of
+// 528 columns) can be left out by the caller, their contribution folded into the bias (`chunk_mask`, at_policy_forward).
 constexpr int F_TABLE_FLOATS = 512 + 512 + 9 * 128 + 12;
-constexpr size_t F_SMEM_BYTES = 1024 + (size_t)F_STAGES * F_STAGE_BYTES + H1_BYTES + F_TABLE_FLOATS * 4 + 16 * 8 + 16;
-constexpr int F_THREADS = 192;
 
 struct PolicyIO {            // one policy's tables and outputs
     const float *b1, *b2, *w3, *b3;   // [512] (folded), [4][128], [9][128], [9]
@@ -263,276 +259,9 @@ __device__ __forceinline__ float round_tf32(float v) {
     asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
     return __uint_as_float(r);
 }
-__global__ void __launch_bounds__(F_THREADS, 1)
-policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
-                      const __grid_constant__ CUtensorMap map_w1_0, const __grid_constant__ CUtensorMap map_w1_1,
-                      const __grid_constant__ CUtensorMap map_w2_0, const __grid_constant__ CUtensorMap map_w2_1,
-                      const __grid_constant__ PolicyFwd P) {
-    extern __shared__ unsigned char smem_raw[];
-    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // swizzle atoms: 1024-byte aligned (offset arithmetic keeps the shared address space)
-    unsigned char *h1 = smem + (size_t)F_STAGES * F_STAGE_BYTES;
-    float *tab = (float *)(h1 + H1_BYTES);
-    float *b1s = tab, *b2s = tab + 512, *w3s = tab + 1024, *b3s = tab + 1024 + 9 * 128;
-    uint64_t *bars = (uint64_t *)(tab + F_TABLE_FLOATS);
-    uint64_t *full = bars, *empty = bars + F_STAGES, *acc1_full = bars + 2 * F_STAGES, *acc_free = acc1_full + 2,
-             *h1_ready = acc_free + 2, *l2_done = h1_ready + 1;
-    uint32_t *tmem_slot = (uint32_t *)(l2_done + 1);
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n_tiles = P.tiles_per_policy * P.n_policies;
-    const int n_chunks = __popc(P.chunk_mask);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < F_STAGES; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-        for (int h = 0; h < 2; ++h) { mbar_init(acc1_full + h, 1); mbar_init(acc_free + h, 128); }
-        mbar_init(h1_ready, 128);
-        mbar_init(l2_done, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    }
-    if (warp == 1) {
-        __syncwarp();
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const uint32_t tmem_base = *tmem_slot;
-
-    // Order of the tensor-core work of a CTA with local tiles 0 .. m - 1 (the producer fills the ring in the same order):
-    //   L1(0, h0) L1(0, h1)   then per tile i:   L2(i, n0) L2(i, n1) L2(i, n2) L1(i + 1, h0) L2(i, n3) L1(i + 1, h1)
-    // - the next tile's first layers fill the tensor core while the epilogue works down the current tile's networks.
-    const int m_tiles = blockIdx.x < n_tiles ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer
-            uint32_t g = 0;
-            auto slot = [&](uint32_t bytes) -> unsigned char * {
-                const uint32_t s = g % F_STAGES;
-                if (g >= F_STAGES) mbar_wait(empty + s, ((g / F_STAGES) - 1) & 1);
-                mbar_expect_tx(full + s, bytes);
-                return smem + (size_t)s * F_STAGE_BYTES;
-            };
-            auto l1 = [&](int i, int h) {
-                const int tile = blockIdx.x + i * gridDim.x;
-                const int p = tile / P.tiles_per_policy, row0 = (tile - p * P.tiles_per_policy) * TM;
-                const CUtensorMap *mx = p ? &map_x1 : &map_x0, *mw1 = p ? &map_w1_1 : &map_w1_0;
-                uint32_t m = P.chunk_mask;
-                while (m) {
-                    const int c = __ffs(m) - 1;
-                    m &= m - 1;
-                    unsigned char *sa = slot(F_STAGE_BYTES);
-                    tma_load_2d(sa, mx, full + g % F_STAGES, c * KC, row0);
-                    tma_load_2d(sa + FA_BYTES, mw1, full + g % F_STAGES, c * KC, h * 256);
-                    ++g;
-                }
-            };
-            auto l2 = [&](int i, int net) {
-                const int tile = blockIdx.x + i * gridDim.x;
-                const CUtensorMap *mw2 = tile / P.tiles_per_policy ? &map_w2_1 : &map_w2_0;
-                for (int half = 0; half < 2; ++half) {
-                    unsigned char *sb = slot(FB_BYTES) + FA_BYTES;
-                    tma_load_2d(sb, mw2, full + g % F_STAGES, (2 * half) * KC, net * 128);
-                    tma_load_2d(sb + FA_BYTES, mw2, full + g % F_STAGES, (2 * half + 1) * KC, net * 128);
-                    ++g;
-                }
-            };
-            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
-            for (int i = 0; i < m_tiles; ++i) {
-                l2(i, 0); l2(i, 1); l2(i, 2);
-                if (i + 1 < m_tiles) l1(i + 1, 0);
-                l2(i, 3);
-                if (i + 1 < m_tiles) l1(i + 1, 1);
-            }
-        }
-    } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer
-            constexpr uint32_t idesc1 = umma_idesc_tf32(TM, 256), idesc2 = umma_idesc_tf32(TM, 128);
-            const uint32_t h1a = smem_u32(h1);
-            uint32_t g = 0;
-            auto l1 = [&](int i, int h) {
-                if (i > 0) {   // the epilogue has read the previous tile's results out of this half
-                    mbar_wait(acc_free + h, (uint32_t)((i - 1) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                }
-                for (int ci = 0; ci < n_chunks; ++ci) {
-                    const uint32_t s = g % F_STAGES;
-                    mbar_wait(full + s, (g / F_STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint32_t a0 = smem_u32(smem + (size_t)s * F_STAGE_BYTES), b0 = a0 + FA_BYTES;
-#pragma unroll
-                    for (int kk = 0; kk < KC / 8; ++kk)
-                        umma_tf32(tmem_base + h * 256, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
-                                  (ci > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(empty + s);
-                    ++g;
-                }
-                umma_commit(acc1_full + h);
-            };
-            auto l2 = [&](int i, int net) {
-                mbar_wait(h1_ready, (uint32_t)((4 * i + net) & 1));
-                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                for (int half = 0; half < 2; ++half) {
-                    const uint32_t s = g % F_STAGES;
-                    mbar_wait(full + s, (g / F_STAGES) & 1);
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                    const uint32_t b0 = smem_u32(smem + (size_t)s * F_STAGE_BYTES) + FA_BYTES;
-#pragma unroll
-                    for (int cc = 0; cc < 2; ++cc)
-#pragma unroll
-                        for (int kk = 0; kk < KC / 8; ++kk)
-                            umma_tf32(tmem_base + net * 128, umma_desc_sw128(h1a + (2 * half + cc) * FA_BYTES + kk * 32),
-                                      umma_desc_sw128(b0 + cc * FA_BYTES + kk * 32), idesc2, (half > 0 || cc > 0 || kk > 0) ? 1u : 0u);
-                    umma_commit(empty + s);
-                    ++g;
-                }
-                umma_commit(l2_done);
-            };
-            if (m_tiles > 0) { l1(0, 0); l1(0, 1); }
-            for (int i = 0; i < m_tiles; ++i) {
-                l2(i, 0); l2(i, 1); l2(i, 2);
-                if (i + 1 < m_tiles) l1(i + 1, 0);
-                l2(i, 3);
-                if (i + 1 < m_tiles) l1(i + 1, 1);
-            }
-        }
-    } else {
-        // ===== epilogue: thread = row (TMEM lane quarter = warp % 4)
-        const int q = warp & 3, r = q * 32 + lane;
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-        const uint64_t ctr = P.counter ? (uint64_t)*P.counter : 0ull;
-        int cur_p = -1, it = 0;
-        // a network's second-layer columns -> its output (value, or one head's draw)
-        auto readout = [&](int net, const PolicyIO &io, int64_t row, bool in) {
-            const int first = net == 0 ? 0 : (net == 1 ? 1 : (net == 2 ? 4 : 7)), nout = net == 0 ? 1 : (net == 3 ? 2 : 3);
-            float o[3] = {0.f, 0.f, 0.f};
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t v[32];
-                tmem_ld32(lane_addr + (uint32_t)(net * 128 + c * 32), v);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int col = net * 128 + c * 32 + i;
-                    const float hv = tanh_approx(__uint_as_float(v[i]) + b2s[col]);
-                    o[0] = fmaf(hv, w3s[first * 128 + c * 32 + i], o[0]);   // (explicit: the TU is compiled with -fmad=false)
-                    if (nout > 1) o[1] = fmaf(hv, w3s[(first + 1) * 128 + c * 32 + i], o[1]);
-                    if (nout > 2) o[2] = fmaf(hv, w3s[(first + 2) * 128 + c * 32 + i], o[2]);
-                }
-            }
-#pragma unroll
-            for (int j = 0; j < 3; ++j) o[j] += b3s[first + (j < nout ? j : 0)];
-            if (!in) return;
-            if (io.out9)
-                for (int j = 0; j < nout; ++j) io.out9[row * 9 + first + j] = o[j];
-            if (net == 0) { io.values[row * io.val_stride] = o[0]; return; }
-            // the draws of sample_out9_kernel: head k uses u[draw .. draw + d) of the row's two Philox blocks
-            const int draw = net == 1 ? 0 : (net == 2 ? 3 : 6);
-            uint32_t u[8];
-#pragma unroll
-            for (int b = 0; b < 2; ++b) {
-                uint32_t c0 = (uint32_t)row, c1 = (uint32_t)((uint64_t)row >> 32) | ((uint32_t)b << 31), cc = (uint32_t)ctr,
-                         c3 = (uint32_t)(ctr >> 32) ^ (io.stream_id * 0x9E3779B9u);
-                at::philox4x32_10(c0, c1, cc, c3, (uint32_t)(P.seed & 0xFFFFFFFFu), (uint32_t)(P.seed >> 32));
-                u[4 * b] = c0; u[4 * b + 1] = c1; u[4 * b + 2] = cc; u[4 * b + 3] = c3;
-            }
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                if (j < nout) mx = fmaxf(mx, o[j]);
-            float se = 0.f;
-#pragma unroll
-            for (int j = 0; j < 3; ++j)
-                if (j < nout) se += expf(o[j] - mx);
-            const float lse = mx + logf(se);
-            int best = 0;
-            float best_s = -INFINITY, best_lp = 0.f;
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                if (j < nout) {
-                    const float lp = o[j] - lse;
-                    const float un = ((float)u[(draw + j) & 7] + 0.5f) * 2.3283064365386963e-10f;
-                    const float gm = -logf(fmaxf(-logf(fminf(un, 0.99999994f)), 1e-20f));
-                    if (lp + gm > best_s) { best_s = lp + gm; best = j; best_lp = lp; }
-                }
-            }
-            io.actions[row * io.act_stride + (net - 1)] = best;
-            io.logprobs[row * io.lp_stride + (net - 1)] = best_lp;
-        };
-        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int p = tile / P.tiles_per_policy;
-            const int64_t row = (int64_t)(tile - p * P.tiles_per_policy) * TM + r;
-            const bool in = row < P.n_rows;
-            const PolicyIO &io = P.io[p];
-            if (p != cur_p) {   // this policy's tables (a CTA's tiles are in policy order: at most one switch)
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                const int t = threadIdx.x - 64;
-                for (int i = t; i < 512; i += 128) { b1s[i] = __ldg(io.b1 + i); b2s[i] = __ldg(io.b2 + i); }
-                for (int i = t; i < 9 * 128; i += 128) w3s[i] = __ldg(io.w3 + i);
-                if (t < 12) b3s[t] = t < 9 ? __ldg(io.b3 + t) : 0.f;
-                asm volatile("bar.sync 1, 128;\n" ::: "memory");
-                cur_p = p;
-            }
-            for (int net = 0; net < 4; ++net) {
-                const int j = 4 * it + net;
-                if ((net & 1) == 0) {
-                    mbar_wait(acc1_full + (net >> 1), (uint32_t)(it & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                }
-                if (net > 0) {   // the second layer of the previous network has finished: h1 is free, its results are ready
-                    mbar_wait(l2_done, (uint32_t)((j - 1) & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-                }
-                // first-layer columns of `net` -> + bias -> tanh -> the second layer's A operand (128-byte swizzle:
-                // 16-byte unit u of row r lives at unit u ^ (r & 7))
-#pragma unroll 1
-                for (int c = 0; c < 4; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(lane_addr + (uint32_t)(net * 128 + c * 32), v);
-                    unsigned char *dst = h1 + (size_t)c * FA_BYTES + (size_t)r * 128;
-#pragma unroll
-                    for (int u4 = 0; u4 < 8; ++u4) {
-                        float4 w;
-                        w.x = round_tf32(tanh_approx(__uint_as_float(v[4 * u4]) + b1s[net * 128 + c * 32 + 4 * u4]));
-                        w.y = round_tf32(tanh_approx(__uint_as_float(v[4 * u4 + 1]) + b1s[net * 128 + c * 32 + 4 * u4 + 1]));
-                        w.z = round_tf32(tanh_approx(__uint_as_float(v[4 * u4 + 2]) + b1s[net * 128 + c * 32 + 4 * u4 + 2]));
-                        w.w = round_tf32(tanh_approx(__uint_as_float(v[4 * u4 + 3]) + b1s[net * 128 + c * 32 + 4 * u4 + 3]));
-                        *reinterpret_cast<float4 *>(dst + ((u4 ^ (r & 7)) << 4)) = w;
-                    }
-                }
-                asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> the tensor core's reads
-                asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                mbar_arrive(h1_ready);
-                if (net > 0) {
-                    readout(net - 1, io, row, in);
-                    if (net == 2) {   // networks 0 and 1 are done with columns 0-255
-                        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-                        mbar_arrive(acc_free + 0);
-                    }
-                }
-            }
-            mbar_wait(l2_done, (uint32_t)((4 * it + 3) & 1));
-            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-            readout(3, io, row, in);
-            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-            mbar_arrive(acc_free + 1);
-        }
-    }
-    __syncwarp();
-    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
-    __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
-}
-
-// ====================================================================================================================
-// policy_forward16_kernel - the same pass on fp16 operands (at_step_norm16's rows, weights rounded to fp16 by the
-// caller; fp32 accumulation): tcgen05.mma.kind::f16 runs at twice the TF32 rate and every operand byte counts half,
-// which matters because the first layers are bound by what an SM can pull from L2 (~107 GB/s measured: each 128-row
-// tile streams all of W1).  fp16 has TF32's 10 mantissa bits; the normalised rows, the weights and tanh's output are
-// far inside its range.  Differences to the TF32 kernel: K chunks of 64 columns (one 128-byte swizzle row), W2 of a
-// network is ONE ring slot, the activations of two networks are in flight (two h1 buffers), and sixteen epilogue warps -
-// four per TMEM lane quarter, each thread one row and a QUARTER of a network's columns (the epilogue is a latency chain of
-// tcgen05.ld -> bias -> MUFU.TANH -> store: four warps per scheduler keep the MUFU pipe fed); the four quarters of a
-// row's output dot products meet in shared memory.
+// Why fp16 where the caller can provide it: tcgen05.mma.kind::f16 runs at twice the TF32 rate and every operand byte counts
+// half, which matters because the first layers are bound by what an SM can pull from L2 (~130 GB/s measured: each 128-row
+// tile streams all of W1).
 constexpr int H_KC = 64;                                  // fp16 columns per chunk
 constexpr int H_STAGES = 3;
 constexpr uint32_t HA_BYTES = TM * H_KC * 2;              // 16 KB: x chunk
@@ -557,8 +286,9 @@ __device__ __forceinline__ uint32_t pack_half2(float lo, float hi) {
     return r;
 }
 
+template <bool HALF_IN>
 __global__ void __launch_bounds__(H_THREADS, 1)
-policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
+policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_constant__ CUtensorMap map_x1,
                         const __grid_constant__ CUtensorMap map_w1_0, const __grid_constant__ CUtensorMap map_w1_1,
                         const __grid_constant__ CUtensorMap map_w2_0, const __grid_constant__ CUtensorMap map_w2_1,
                         const __grid_constant__ PolicyFwd P) {
@@ -628,8 +358,8 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                     const int c = __ffs(m) - 1;
                     m &= m - 1;
                     unsigned char *sa = slot(H_STAGE_BYTES);
-                    tma_load_2d(sa, mx, full + g % H_STAGES, c * H_KC, row0);
-                    tma_load_2d(sa + HA_BYTES, mw1, full + g % H_STAGES, c * H_KC, h * 256);
+                    tma_load_2d(sa, mx, full + g % H_STAGES, c * (HALF_IN ? H_KC : KC), row0);
+                    tma_load_2d(sa + HA_BYTES, mw1, full + g % H_STAGES, c * (HALF_IN ? H_KC : KC), h * 256);
                     ++g;
                 }
             };
@@ -648,7 +378,7 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc1 = umma_idesc_f16(TM, 256), idesc2 = umma_idesc_f16(TM, 128);
+            constexpr uint32_t idesc1 = HALF_IN ? umma_idesc_f16(TM, 256) : umma_idesc_tf32(TM, 256), idesc2 = umma_idesc_f16(TM, 128);
             uint32_t g = 0;
             auto l1 = [&](int i, int h) {
                 const int u = 2 * i + h;
@@ -663,9 +393,10 @@ policy_forward16_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid
                     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
                     const uint32_t a0 = smem_u32(smem + (size_t)s * H_STAGE_BYTES), b0 = a0 + HA_BYTES;
 #pragma unroll
-                    for (int kk = 0; kk < H_KC / 16; ++kk)   // 16 halves = 32 bytes per instruction along K
-                        umma_f16(tmem_base, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1,
-                                 (ci > 0 || kk > 0) ? 1u : 0u);
+                    for (int kk = 0; kk < 4; ++kk) {   // 16 halves / 8 floats = 32 bytes per instruction along K
+                        if (HALF_IN) umma_f16(tmem_base, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1, (ci > 0 || kk > 0) ? 1u : 0u);
+                        else umma_tf32(tmem_base, umma_desc_sw128(a0 + kk * 32), umma_desc_sw128(b0 + kk * 32), idesc1, (ci > 0 || kk > 0) ? 1u : 0u);
+                    }
                     umma_commit(empty + s);
                     ++g;
                 }

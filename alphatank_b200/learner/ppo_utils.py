@@ -226,7 +226,7 @@ class FusedPolicies:
         self.w1 = torch.empty((n, 512, self.D), dtype=wt, device=self.device)
         self.b1 = torch.empty((n, 512), **f)
         self.b1_fold = torch.empty((n, 512), **f)        # b1 + W1[:, dropped chunks] . y (forward(fold=True))
-        self.w2 = torch.empty((n, 4, 128, 128), dtype=wt, device=self.device)
+        self.w2 = torch.empty((n, 4, 128, 128), dtype=torch.float16, device=self.device)   # (fp16 in both kernels)
         self.b2 = torch.empty((n, 4, 128), **f)
         self.w3 = torch.empty((n, 9, 128), **f)
         self.b3 = torch.empty((n, 9), **f)
@@ -267,7 +267,6 @@ class FusedPolicies:
             self.b3[i].copy_(torch.cat([m[4].bias for m in nets], dim=0))
         if not self.half:         # (copy_ into the fp16 tensors has rounded to nearest already)
             _round_tf32_(self.w1)
-            _round_tf32_(self.w2)
 
     def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None, fold=None):
         """obs [N, A, D] (A = the number of packed policies) -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]

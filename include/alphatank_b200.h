@@ -245,20 +245,22 @@ int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t 
 
 /* A policy's whole inference pass in one kernel on the tcgen05 tensor cores (models/ppo_utils.py:31-62 - critic + three
  * action heads, D -> 128 -> 128 -> {1, 3, 3, 2} - as train_multi_ppo.py:96-116 calls get_action_and_value per tank):
- * TMA-loaded observation tiles -> first layers (TF32 multiply, fp32 accumulate in tensor memory) -> tanh -> second
- * layers -> tanh -> output layers -> log-softmax -> Gumbel-max draw (the Philox stream of at_sample_heads).  Neither the
- * [N, 512] activations nor the logits go to HBM.  One launch serves 1 or 2 policies of n_rows rows each.
- *   x            n_rows rows of `dim` floats, x_row_stride floats apart (a column slice of [N][A][D] as it is)
- *   w1 / b1      float[512][dim] / float[512]: the four first layers side by side (critic, head 0, 1, 2)
- *   w2 / b2      float[4][128][128] / float[4][128];   w3 / b3: float[9][128] / float[9] (value; 3 + 3 + 2 logits)
+ * TMA-loaded observation tiles -> first layers (fp32 accumulators in tensor memory) -> tanh -> second layers -> tanh ->
+ * output layers -> log-softmax -> Gumbel-max draw (the Philox stream of at_sample_heads).  Neither the [N, 512]
+ * activations nor the logits go to HBM.  One launch serves 1 or 2 policies of n_rows rows each.
+ *   x            n_rows rows of `dim` elements, x_row_stride elements apart (a column slice of [N][A][D] as it is):
+ *                float (at_policy_forward: TF32 contraction) or fp16 bits (at_policy_forward16)
+ *   w1 / b1      [512][dim] in x's type / float[512]: the four first layers side by side (critic, head 0, 1, 2)
+ *   w2 / b2      fp16 bits [4][128][128] in BOTH entry points / float[4][128];   w3 / b3: float[9][128] / float[9]
  *   out9         optional float[n_rows][9]: value and the 8 logits
- * chunk_mask: bit c set = columns 32 c .. 32 c + 31 take part in the first layers' contraction (0 = all).  Columns that
- * are constant for the handle's lifetime (at_obs_static_range) may be left out when their contribution W1[:, cols] . x
- * is added to b1 by the caller - 2v2 rows: 9 of 17 chunks remain.  Precision: TF32 operands (x truncated, the hidden
+ * chunk_mask: bit c set = K chunk c takes part in the first layers' contraction (0 = all); a chunk is 32 columns for
+ * float rows, 64 for fp16 rows.  Columns that are constant for the handle's lifetime (at_obs_static_range) may be left
+ * out when their contribution W1[:, cols] . x is added to b1 by the caller - 2v2 rows: 9 of 17 (5 of 9) chunks remain.
+ * Precision: 10-bit mantissas on both operands of both hidden layers (TF32 reads of the float rows, fp16 hidden
  * activations rounded to nearest), fp32 accumulation, tanh.approx (relative error 2^-11). */
 typedef struct at_policy {
     const void *x; int64_t x_row_stride;      /* float (at_policy_forward) or fp16 bits (at_policy_forward16); stride in elements */
-    const void *w1; const float *b1;          /* w1 / w2 in x's type, everything else float */
+    const void *w1; const float *b1;          /* w1 in x's type, w2 fp16 bits, everything else float */
     const void *w2; const float *b2, *w3, *b3;
     int32_t *actions; int64_t act_stride;
     float *logprobs; int64_t lp_stride;
@@ -269,9 +271,8 @@ typedef struct at_policy {
 int at_policy_forward(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                       uint64_t seed, const int64_t *d_counter, void *stream);
 
-/* The same pass on fp16 operands - x = at_step_norm16's rows, w1 / w2 rounded to fp16 by the caller, fp32 accumulation,
- * biases / output layers / outputs in fp32: tcgen05.mma.kind::f16 at twice the TF32 rate and half the operand bytes
- * (fp16 carries TF32's 10 mantissa bits).  chunk_mask counts chunks of 64 columns here (2v2 rows: 5 of 9 remain). */
+/* The same pass on fp16 rows - x = at_step_norm16's rows, w1 rounded to fp16 by the caller: tcgen05.mma.kind::f16 at
+ * twice the TF32 rate and half the operand bytes.  chunk_mask counts chunks of 64 columns here. */
 int at_policy_forward16(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
                         uint64_t seed, const int64_t *d_counter, void *stream);
 

@@ -32,6 +32,8 @@ def main():
     p.add_argument("--reward-mode", default="cumulative", choices=["cumulative", "delta"])
     p.add_argument("--obs-norm", default="tick", choices=["tick", "running", "none"])
     p.add_argument("--no-graph", action="store_true", help="issue the rollout kernel by kernel instead of one CUDA graph")
+    p.add_argument("--obs-fp16", action="store_true",
+                   help="keep the tick-normalised rows as fp16 (at_step_norm16 + the fp16 tensor-core policy kernel; needs --obs-norm tick)")
     p.add_argument("--seed", type=int, default=0)
     p.add_argument("--ckpt-dir", default="checkpoints/team_ppo")
     a = p.parse_args()
@@ -57,7 +59,8 @@ def main():
     cfg = PPOConfig(num_steps=a.num_steps, num_epochs=a.num_epochs, num_minibatches=a.num_minibatches,
                     reward_mode=a.reward_mode, obs_norm=a.obs_norm)
     learner = PPOLearner(A, D, tuple(int(x) for x in env.action_space.nvec[:3]), cfg, dev, seed=a.seed)
-    buf = RolloutBuffer(a.num_steps, a.num_envs, A, D, dev, keep_raw=a.obs_norm != "tick")
+    buf = RolloutBuffer(a.num_steps, a.num_envs, A, D, dev, keep_raw=a.obs_norm != "tick",
+                        obs_dtype=torch.float16 if (a.obs_fp16 and a.obs_norm == "tick") else torch.float32)
     runner = RolloutRunner(env, learner, buf, use_graph=not a.no_graph)
     for it in range(a.iterations):
         torch.cuda.synchronize(dev)

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Timeline of block 0 of at_policy_forward16 (at_policy_debug_stamps): what the MMA-issuing thread and one epilogue
+"""Timeline of block 0 of the policy kernel (fp16 rows) (at_policy_debug_stamps): what the MMA-issuing thread and one epilogue
 thread wait for, in SM clocks relative to the first stamp.  Development tooling."""
 import ctypes as C
 import os
