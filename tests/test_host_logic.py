@@ -37,6 +37,29 @@ def test_struct_layouts_match_the_header():
     assert _capi.ENV_STATE_DT.itemsize == O.ENV_DT.itemsize     # oracle and product exchange the same snapshot record
 
 
+def test_policy_struct_layout_and_argument_checks():
+    """at_policy (include/alphatank_b200.h) as the ctypes mirror lays it out, and the argument checks of the policy entry
+    points, which come before any CUDA call (so they can be exercised without a GPU)."""
+    P = _capi.AtPolicy
+    assert C.sizeof(P) == 16 * 8                       # 15 pointer / int64 fields + uint32 stream_id, padded (LP64)
+    hdr = open(os.path.join(REPO, "include", "alphatank_b200.h")).read()
+    body = re.sub(r"/\*.*?\*/", "", hdr[hdr.index("typedef struct at_policy {"):hdr.index("} at_policy;")], flags=re.S)
+    names = re.findall(r"[\*\s](\w+)\s*[;,]", body)
+    assert names == [n for n, _ in P._fields_], names
+    L = _capi.lib()
+    for fn in (L.at_policy_forward, L.at_policy_forward16):
+        assert fn(0, None, 1, 128, 528, 0, 0, None, None) == _capi.AT_ERR_ARG            # no policies
+        pol = (P * 1)()
+        assert fn(0, pol, 3, 128, 528, 0, 0, None, None) == _capi.AT_ERR_ARG             # more than two
+        assert fn(0, pol, 1, 0, 528, 0, 0, None, None) == _capi.AT_ERR_ARG               # no rows
+        assert fn(0, pol, 1, 128, 530, 0, 0, None, None) == _capi.AT_ERR_ARG             # row length not a multiple of 4 / 8
+        assert fn(0, pol, 1, 128, 528, 1 << 20, 0, None, None) == _capi.AT_ERR_ARG       # chunk past the last column
+    assert L.at_policy_forward16(0, (P * 1)(), 1, 128, 388, 0, 0, None, None) == _capi.AT_ERR_ARG   # 388 % 8 != 0: fp32 rows only
+    assert b"at_policy_forward" in L.at_last_error()
+    assert L.at_obs_static_range(None, None, None) == _capi.AT_ERR_ARG
+    assert L.at_set_rows_mode(None, 1) == _capi.AT_ERR_ARG
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
