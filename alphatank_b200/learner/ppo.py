@@ -216,6 +216,28 @@ class PPOLearner:
         return (torch.stack(acts, dim=1).to(torch.int32), torch.stack(lps, dim=1), torch.stack(vals, dim=1))
 
     @torch.no_grad()
+    def values_into(self, obs_nad, out, fold=None):
+        """values(obs) written into ``out`` [N, A] - on the tcgen05 path one launch of the policy kernel (its draws go to
+        scratch tensors and the tick counter is not advanced) instead of a cast of the rows and six GEMMs per policy."""
+        fused = self.fused_policies(obs_nad.dtype == torch.float16) if obs_nad.is_cuda else None
+        if fused is None:
+            out.copy_(self.values(obs_nad))
+            return out
+        n = obs_nad.shape[0]
+        sc = getattr(self, "_value_scratch", None)
+        if sc is None or sc[0].shape[0] != n:
+            sc = (torch.empty((n, self.A, 3), dtype=torch.int32, device=obs_nad.device),
+                  torch.empty((n, self.A, 3), dtype=torch.float32, device=obs_nad.device))
+            self._value_scratch = sc
+        if getattr(self, "_sample_ctr", None) is None:
+            self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
+        do_fold = fold is not None and fold in self._static_keys and self.cfg.obs_norm in ("tick", "none")
+        for k, f in enumerate(fused):
+            f.forward(obs_nad[:, 2 * k:2 * k + 2], sc[0][:, 2 * k:2 * k + 2], sc[1][:, 2 * k:2 * k + 2], out[:, 2 * k:2 * k + 2],
+                      self._sample_ctr, self.seed, 2 * k + self.A * _rank(), fold=do_fold)
+        return out
+
+    @torch.no_grad()
     def values(self, obs_nad):
         return torch.stack([agent.get_value(obs_nad[:, i].float()).squeeze(-1) for i, agent in enumerate(self.agents)], dim=1)
 
@@ -332,7 +354,7 @@ def collect_rollout(env, learner, buf, first=False):
             buf.rewards[t].copy_(buf.env_rewards[t])
     buf._prev_cum = prev_cum
     buf._prev_live = prev_cum
-    buf.values[T].copy_(learner.values(buf.obs[T]))
+    learner.values_into(buf.obs[T], buf.values[T], fold=key)
     return buf
 
 
