@@ -244,6 +244,8 @@ AT_HD double at_atan2(double y, double x) {
 // Out-of-line copies for the generic build (SimT<0>): it serves every bot type, and with these three helpers inlined at
 // every call site its SASS is 800 KB (at_atan2 60 KB, Philox 54 KB, py_fmod360 42 KB) - instruction fetch, not arithmetic.
 AT_HDN double at_atan2_ni(double y, double x) { return at_atan2(y, x); }
+AT_HDN double cos_ni(double v) { return cos(v); }   // (the dodge bot's non-integer angles: fp64 libm bodies, ~4 KB each)
+AT_HDN double sin_ni(double v) { return sin(v); }
 AT_HDN double py_fmod360_ni(double v) { return py_fmod360(v); }
 AT_HDN uint32_t rng_word_ni(uint64_t seed, int64_t env_id, uint32_t stream, uint32_t ctr) { return rng_word(seed, env_id, stream, ctr); }
 
@@ -419,7 +421,7 @@ AT_HD int ffs32(uint32_t v) {  // index of the lowest set bit (v != 0)
 #endif
 }
 // index of the k-th (0-based) set bit of a 128-bit mask
-AT_HD int select_bit(M128 m, int k) {
+AT_HDN int select_bit(M128 m, int k) {   // (out of line: only resets call it, eight times)
     uint64_t w = m.lo;
     int base = 0;
     int pl = popc64(m.lo);
@@ -1390,7 +1392,7 @@ struct SimT {
     AT_HD bool dodge_hits_wall(int me, double angle) const {  // simple_bots.py:309-329
         double rad = py_radians(angle);
         double wcd = GRID * 1.5;
-        double fx = TX(me) + cos(rad) * wcd, fy = TY(me) - sin(rad) * wcd;
+        double fx = TX(me) + cos_ni(rad) * wcd, fy = TY(me) - sin_ni(rad) * wcd;
         return first_wall(d2i(fx - 15), d2i(fy - 12), 30, 24) >= 0;
     }
     AT_HD double dodge_calc_angle(int me, double thx, double thy) {  // simple_bots.py:359-402
@@ -1405,7 +1407,7 @@ struct SimT {
                 for (int k = 0; k < 3; ++k) {
                     double var = -45.0 + (-30.0 - -45.0) * rng_unit53();  // random.uniform(-45, -30)
                     double theta = py_radians(base[bi] + var);
-                    double cs = cos(theta), sn = sin(theta);
+                    double cs = cos_ni(theta), sn = sin_ni(theta);
                     double r0 = fma_rn(cs, v0, (-sn) * v1), r1 = fma_rn(sn, v0, cs * v1);
                     double fa = fmod360_(py_degrees(atan2_(-r1, r0)));
                     if (!dodge_hits_wall(me, fa)) return fa;
