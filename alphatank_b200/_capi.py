@@ -97,8 +97,8 @@ def lib():
     L.at_get_tank_columns.argtypes = [vp, i32, vp, vp]
     L.at_forget_host_buffers.argtypes = [vp]
     L.at_policy_first.argtypes = [i32, vp, i64, i64, i32, vp, vp, vp, vp]
-    L.at_policy_forward.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, vp]
-    L.at_policy_forward16.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, vp]
+    L.at_policy_forward.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, i32, vp]
+    L.at_policy_forward16.argtypes = [i32, C.POINTER(AtPolicy), i32, i64, i32, C.c_uint32, u64, vp, i32, vp]
     L.at_policy_debug_stamps.argtypes = [vp]
     L.at_set_rows_mode.argtypes = [vp, i32]
     L.at_obs_static_range.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]

@@ -1932,7 +1932,7 @@ int at_policy_first(int device, const float *d_x, int64_t x_row_stride, int64_t 
 static unsigned long long *g_policy_dbg = nullptr;   // at_policy_debug_stamps
 
 static int policy_forward_impl(bool half, int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
-                               uint64_t seed, const int64_t *d_counter, void *stream) {
+                               uint64_t seed, int64_t *d_counter, int advance_counter, void *stream) {
     if (!pol || n_policies < 1 || n_policies > 2 || n_rows <= 0 || n_rows > (int64_t)1 << 30 || dim <= 0 || dim % (half ? 8 : 4) != 0 || dim > (half ? 2048 : 1024))
         return fail(AT_ERR_ARG, "at_policy_forward: 1 or 2 policies, dim a multiple of 4 up to 1024 (fp16: of 8 up to 2048)");
     const int kc = half ? at_tc::H_KC : at_tc::KC, k_chunks = (dim + kc - 1) / kc;
@@ -1970,7 +1970,8 @@ static int policy_forward_impl(bool half, int device, const at_policy *pol, int 
     P.n_policies = n_policies;
     P.chunk_mask = chunk_mask;
     P.seed = seed;
-    P.counter = d_counter;
+    P.counter = (long long *)d_counter;
+    P.advance = advance_counter;
     P.dbg = g_policy_dbg;
     static bool attr_set[64] = {false};
     static int sms[64] = {0};
@@ -1994,13 +1995,13 @@ static int policy_forward_impl(bool half, int device, const at_policy *pol, int 
 }
 
 int at_policy_forward(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
-                      const int64_t *d_counter, void *stream) {
-    return policy_forward_impl(false, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, stream);
+                      int64_t *d_counter, int advance_counter, void *stream) {
+    return policy_forward_impl(false, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, advance_counter, stream);
 }
 
 int at_policy_forward16(int device, const at_policy *pol, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask, uint64_t seed,
-                        const int64_t *d_counter, void *stream) {
-    return policy_forward_impl(true, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, stream);
+                        int64_t *d_counter, int advance_counter, void *stream) {
+    return policy_forward_impl(true, device, pol, n_policies, n_rows, dim, chunk_mask, seed, d_counter, advance_counter, stream);
 }
 
 int at_set_rows_mode(at_env *env, int persistent_buffers) {

@@ -242,7 +242,8 @@ struct PolicyFwd {
     int tiles_per_policy, n_policies;
     uint32_t chunk_mask;     // K chunks (32 columns each) of the first layers to contract
     uint64_t seed;
-    const int64_t *counter;
+    long long *counter;        // [0] the tick counter the draws are keyed by; [1] finished-CTA count (advance != 0)
+    int advance;               // the last CTA to finish adds 1 to counter[0] (every CTA has read it by then)
     unsigned long long *dbg;   // diagnostics: [2][512] (event id, clock) pairs of block 0, or nullptr
 };
 
@@ -583,6 +584,13 @@ policy_forward_kernel(const __grid_constant__ CUtensorMap map_x0, const __grid_c
     __syncwarp();
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
+    if (threadIdx.x == 0 && P.advance && P.counter) {   // the tick counter moves on once the whole grid has used it
+        __threadfence();
+        if (atomicAdd(reinterpret_cast<unsigned long long *>(P.counter + 1), 1ull) == (unsigned long long)(gridDim.x - 1)) {
+            P.counter[1] = 0;
+            P.counter[0] += 1;
+        }
+    }
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "r"(512u) : "memory");
 }
 

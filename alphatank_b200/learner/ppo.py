@@ -189,9 +189,8 @@ class PPOLearner:
                 acts = torch.empty((n, self.A, heads), dtype=torch.int32, device=obs_nad.device)
                 lps = torch.empty((n, self.A, heads), dtype=torch.float32, device=obs_nad.device)
                 vals = torch.empty((n, self.A), dtype=torch.float32, device=obs_nad.device)
-            if getattr(self, "_sample_ctr", None) is None:
-                self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
-            self._sample_ctr.add_(1)
+            if getattr(self, "_sample_ctr", None) is None:     # (tick counter, the policy kernel's finished-CTA count)
+                self._sample_ctr = torch.zeros(2, dtype=torch.int64, device=obs_nad.device)
             half = obs_nad.dtype == torch.float16
             fused = self.fused_policies(half)
             if fused is None and half:
@@ -200,8 +199,10 @@ class PPOLearner:
             if fused is not None:   # the whole forward + sampling of two policies per launch (tcgen05, at_policy_forward)
                 for k, f in enumerate(fused):
                     f.forward(obs_nad[:, 2 * k:2 * k + 2], acts[:, 2 * k:2 * k + 2], lps[:, 2 * k:2 * k + 2], vals[:, 2 * k:2 * k + 2],
-                              self._sample_ctr, self.seed, 2 * k + self.A * _rank(), fold=do_fold)
+                              self._sample_ctr, self.seed, 2 * k + self.A * _rank(), fold=do_fold,
+                              advance=k == len(fused) - 1)     # the tick's last launch moves the counter on
                 return acts, lps, vals
+            self._sample_ctr[:1].add_(1)
             for i, agent in enumerate(self.agents):
                 agent.sample_cuda(obs_nad[:, i], acts[:, i], lps[:, i], self._sample_ctr, self.seed, i + self.A * _rank(),
                                   values_out=vals[:, i])
@@ -230,7 +231,7 @@ class PPOLearner:
                   torch.empty((n, self.A, 3), dtype=torch.float32, device=obs_nad.device))
             self._value_scratch = sc
         if getattr(self, "_sample_ctr", None) is None:
-            self._sample_ctr = torch.zeros(1, dtype=torch.int64, device=obs_nad.device)
+            self._sample_ctr = torch.zeros(2, dtype=torch.int64, device=obs_nad.device)
         do_fold = fold is not None and fold in self._static_keys and self.cfg.obs_norm in ("tick", "none")
         for k, f in enumerate(fused):
             f.forward(obs_nad[:, 2 * k:2 * k + 2], sc[0][:, 2 * k:2 * k + 2], sc[1][:, 2 * k:2 * k + 2], out[:, 2 * k:2 * k + 2],

@@ -268,9 +268,10 @@ class FusedPolicies:
         if not self.half:         # (copy_ into the fp16 tensors has rounded to nearest already)
             _round_tf32_(self.w1)
 
-    def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None, fold=None):
+    def forward(self, obs_nad, actions_out, logprobs_out, values_out, counter, seed=0, stream_base=0, out9=None, fold=None, advance=False):
         """obs [N, A, D] (A = the number of packed policies) -> actions int32 [N, A, 3], logprobs [N, A, 3], values [N, A]
-        written in place; ``counter``: device int64 [1] the caller advances once per tick; ``out9``: optional
+        written in place; ``counter``: device int64 [2] = (tick counter, 0); ``advance``: the kernel moves the tick counter on
+        when it is done (else the caller does, once per tick); ``out9``: optional
         [A, N, 9] (value + 8 logits per row).  ``fold``: contract only the K chunks kept by set_static() (the rows MUST hold
         the static values given there); default: whenever set_static() dropped chunks."""
         fold = bool(self.chunk_mask) if fold is None else (bool(fold) and bool(self.chunk_mask))
@@ -295,8 +296,9 @@ class FusedPolicies:
             q.out9 = out9[i].data_ptr() if out9 is not None else None
             q.stream_id = int(stream_base) + i
         fn = _capi.lib().at_policy_forward16 if self.half else _capi.lib().at_policy_forward
+        assert counter.dtype == torch.int64 and counter.numel() >= 2
         _capi.check(fn(obs_nad.device.index, pols, A, n, self.D, int(self.chunk_mask) if fold else 0, int(seed), C.c_void_p(counter.data_ptr()),
-                       C.c_void_p(torch.cuda.current_stream(obs_nad.device).cuda_stream)), "at_policy_forward")
+                       1 if advance else 0, C.c_void_p(torch.cuda.current_stream(obs_nad.device).cuda_stream)), "at_policy_forward")
 
 
 class PPOAgentBot(PPOAgentPPO):

@@ -268,13 +268,16 @@ typedef struct at_policy {
     float *out9;
     uint32_t stream_id;
 } at_policy;
+/* d_counter: device int64[2] - [0] is the tick counter the draws are keyed by (seed, row, counter, stream_id), [1] must be
+ * 0 (the kernel's finished-CTA count).  advance_counter != 0: the last CTA to finish adds 1 to d_counter[0], so a captured
+ * rollout needs no separate kernel to move it on; 0: the caller advances it (or not: a pass whose draws are discarded). */
 int at_policy_forward(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
-                      uint64_t seed, const int64_t *d_counter, void *stream);
+                      uint64_t seed, int64_t *d_counter, int advance_counter, void *stream);
 
 /* The same pass on fp16 rows - x = at_step_norm16's rows, w1 rounded to fp16 by the caller: tcgen05.mma.kind::f16 at
  * twice the TF32 rate and half the operand bytes.  chunk_mask counts chunks of 64 columns here. */
 int at_policy_forward16(int device, const at_policy *policies, int n_policies, int64_t n_rows, int dim, uint32_t chunk_mask,
-                        uint64_t seed, const int64_t *d_counter, void *stream);
+                        uint64_t seed, int64_t *d_counter, int advance_counter, void *stream);
 
 /* Persistent output buffers.  With persistent_buffers != 0 the STEP calls (at_step, at_step_norm, at_step_norm16,
  * at_step_host) write only the columns of a row that can change - [0, off_walls) and [off_zones, D), widened to 16-byte

@@ -48,13 +48,13 @@ def test_policy_struct_layout_and_argument_checks():
     assert names == [n for n, _ in P._fields_], names
     L = _capi.lib()
     for fn in (L.at_policy_forward, L.at_policy_forward16):
-        assert fn(0, None, 1, 128, 528, 0, 0, None, None) == _capi.AT_ERR_ARG            # no policies
+        assert fn(0, None, 1, 128, 528, 0, 0, None, 0, None) == _capi.AT_ERR_ARG            # no policies
         pol = (P * 1)()
-        assert fn(0, pol, 3, 128, 528, 0, 0, None, None) == _capi.AT_ERR_ARG             # more than two
-        assert fn(0, pol, 1, 0, 528, 0, 0, None, None) == _capi.AT_ERR_ARG               # no rows
-        assert fn(0, pol, 1, 128, 530, 0, 0, None, None) == _capi.AT_ERR_ARG             # row length not a multiple of 4 / 8
-        assert fn(0, pol, 1, 128, 528, 1 << 20, 0, None, None) == _capi.AT_ERR_ARG       # chunk past the last column
-    assert L.at_policy_forward16(0, (P * 1)(), 1, 128, 388, 0, 0, None, None) == _capi.AT_ERR_ARG   # 388 % 8 != 0: fp32 rows only
+        assert fn(0, pol, 3, 128, 528, 0, 0, None, 0, None) == _capi.AT_ERR_ARG             # more than two
+        assert fn(0, pol, 1, 0, 528, 0, 0, None, 0, None) == _capi.AT_ERR_ARG               # no rows
+        assert fn(0, pol, 1, 128, 530, 0, 0, None, 0, None) == _capi.AT_ERR_ARG             # row length not a multiple of 4 / 8
+        assert fn(0, pol, 1, 128, 528, 1 << 20, 0, None, 0, None) == _capi.AT_ERR_ARG       # chunk past the last column
+    assert L.at_policy_forward16(0, (P * 1)(), 1, 128, 388, 0, 0, None, 0, None) == _capi.AT_ERR_ARG   # 388 % 8 != 0: fp32 rows only
     assert b"at_policy_forward" in L.at_last_error()
     assert L.at_obs_static_range(None, None, None) == _capi.AT_ERR_ARG
     assert L.at_set_rows_mode(None, 1) == _capi.AT_ERR_ARG

@@ -134,7 +134,7 @@ def test_sample_heads_kernel_is_a_categorical_sampler():
     x = torch.randn(1, 24, device=dev).expand(N, 24).contiguous()          # the same observation in every row
     acts = torch.full((N, 2, 3), -1, dtype=torch.int32, device=dev)
     lps = torch.zeros((N, 2, 3), dtype=torch.float32, device=dev)
-    ctr = torch.ones(1, dtype=torch.int64, device=dev)
+    ctr = torch.tensor([1, 0], dtype=torch.int64, device=dev)
     v = agent.sample_cuda(x, acts[:, 1], lps[:, 1], ctr, seed=5, stream_id=0)       # reference shape: at_policy_tail
     assert (acts[:, 0] == -1).all() and v.shape == (N, 1)                  # strided output: the other agent's columns untouched
     logits, value = agent.fused_logits_and_value(x)
@@ -335,7 +335,7 @@ def test_policy_forward_on_tcgen05_matches_the_fp64_module(n_rows, half):
     lps = torch.full((n_rows, A, 3), float("nan"), device=dev)
     vals = torch.full((n_rows, A), float("nan"), device=dev)
     out9 = torch.full((A, n_rows, 9), float("nan"), device=dev)
-    ctr = torch.ones(1, dtype=torch.int64, device=dev)
+    ctr = torch.tensor([1, 0], dtype=torch.int64, device=dev)
     fp.forward(obs, acts, lps, vals, ctr, seed=7, out9=out9)
     torch.cuda.synchronize()
     assert torch.isfinite(out9).all() and torch.isfinite(lps).all() and torch.isfinite(vals).all()
@@ -368,7 +368,7 @@ def test_policy_forward_on_the_1v1_rows_single_policy():
         FusedPolicies(agents, D, dev, half=True)
     acts = torch.zeros((n, 1, 3), dtype=torch.int32, device=dev)
     lps, vals, out9 = torch.zeros((n, 1, 3), device=dev), torch.zeros((n, 1), device=dev), torch.zeros((1, n, 9), device=dev)
-    fp.forward(obs, acts, lps, vals, torch.ones(1, dtype=torch.int64, device=dev), seed=3, out9=out9)
+    fp.forward(obs, acts, lps, vals, torch.tensor([1, 0], dtype=torch.int64, device=dev), seed=3, out9=out9)
     ref = _fp64_out9(agents[0], obs[:, 0]).float()
     assert (out9[0] - ref).abs().max().item() < 1e-2
     assert torch.equal(vals[:, 0], out9[0][:, 0])
@@ -389,7 +389,7 @@ def test_policy_forward_draws_follow_the_softmax():
     for tick in (1, 2):
         acts = torch.zeros((n, 1, 3), dtype=torch.int32, device=dev)
         lps, vals = torch.zeros((n, 1, 3), device=dev), torch.zeros((n, 1), device=dev)
-        fp.forward(obs, acts, lps, vals, torch.full((1,), tick, dtype=torch.int64, device=dev), seed=11, out9=out9)
+        fp.forward(obs, acts, lps, vals, torch.tensor([tick, 0], dtype=torch.int64, device=dev), seed=11, out9=out9)
         draws.append(acts.clone())
         assert (out9[0] - out9[0][0:1]).abs().max().item() == 0.0
         for h, (lo, d) in enumerate(((1, 3), (4, 3), (7, 2))):
@@ -422,7 +422,7 @@ def test_policy_forward_folds_constant_columns_into_the_bias(half):
         out9 = torch.zeros((A, n, 9), device=dev)
         acts = torch.zeros((n, A, 3), dtype=torch.int32, device=dev)
         fp.forward(obs, acts, torch.zeros((n, A, 3), device=dev), torch.zeros((n, A), device=dev),
-                   torch.ones(1, dtype=torch.int64, device=dev), seed=1, out9=out9)
+                   torch.tensor([1, 0], dtype=torch.int64, device=dev), seed=1, out9=out9)
         res.append(out9)
     for i in range(A):
         ref = _fp64_out9(agents[i], obs[:, i]).float()

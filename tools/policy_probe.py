@@ -17,7 +17,7 @@ agents = [PPOAgentPPO(D).to(dev) for _ in range(A)]
 obs = [torch.randn((N, A, D), device=dev) for _ in range(3)]       # rotate: 3 x 277 MB > L2
 acts = torch.zeros((N, A, 3), dtype=torch.int32, device=dev)
 lps, vals = torch.zeros((N, A, 3), device=dev), torch.zeros((N, A), device=dev)
-ctr = torch.ones(1, dtype=torch.int64, device=dev)
+ctr = torch.tensor([1, 0], dtype=torch.int64, device=dev)
 for half, fold in ((False, False), (False, True), (True, False), (True, True)):
     fp = FusedPolicies(agents, D, dev, half=half)
     if half and obs[0].dtype != torch.float16:

@@ -18,7 +18,7 @@ agents = [PPOAgentPPO(D).to(dev) for _ in range(A)]
 obs = torch.randn((N, A, D), device=dev).half()
 acts = torch.zeros((N, A, 3), dtype=torch.int32, device=dev)
 lps, vals = torch.zeros((N, A, 3), device=dev), torch.zeros((N, A), device=dev)
-ctr = torch.ones(1, dtype=torch.int64, device=dev)
+ctr = torch.tensor([1, 0], dtype=torch.int64, device=dev)
 fp = FusedPolicies(agents, D, dev, half=True)
 fp.set_static(237, 518, obs[0])
 for _ in range(3):
