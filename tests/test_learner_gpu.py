@@ -503,3 +503,41 @@ def test_rollout_on_the_fused_policies_matches_the_per_layer_path():
         finally:
             os.environ.pop("AT_NO_POLICY_TC", None)
     assert (vals[0] - vals[1]).abs().max().item() < 5e-3
+
+
+@pytest.mark.parametrize("n_agents, half", [(4, True), (3, False), (3, True)])
+def test_rollout_with_more_than_two_policies(n_agents, half):
+    """A = 4 (`team_configs`: two launches of the policy kernel per tick, the second one advances the tick counter) and
+    A = 3 (a pair and a single policy): the stored log-probabilities / values are the policies' own on the stored rows, the
+    draws differ from tick to tick, and the rollout replays as a CUDA graph."""
+    from alphatank_b200 import MultiAgentTeamEnv
+    from alphatank_b200.configs import config_teams
+    from alphatank_b200.learner import PPOConfig, PPOLearner, RolloutBuffer, RolloutRunner
+    dev = torch.device("cuda:0")
+    cfg = dict(config_teams.team_configs)
+    if n_agents == 3:
+        cfg["Tank4"] = dict(cfg["Tank4"], mode="bot", bot_type="smart")
+    N, T = 1024, 5
+    env = MultiAgentTeamEnv(cfg, num_envs=N, device=dev, seed=2)
+    A = len(env.get_observation_order())
+    D = env.observation_space.shape[0] // A
+    assert A == n_agents
+    learner = PPOLearner(A, D, (3, 3, 2), PPOConfig(num_steps=T), dev, seed=0)
+    buf = RolloutBuffer(T, N, A, D, dev, keep_raw=False, obs_dtype=torch.float16 if half else torch.float32)
+    runner = RolloutRunner(env, learner, buf)
+    ctr = []
+    for k in range(3):
+        runner.run(first=(k == 0))
+        torch.cuda.synchronize()
+        fused = learner.fused_policies(half)
+        assert fused is not None and len(fused) == (A + 1) // 2
+        ctr.append(int(learner._sample_ctr[0]))
+        assert int(learner._sample_ctr[1]) == 0
+        for i, agent in enumerate(learner.agents):
+            x = buf.obs[:T, :, i].reshape(T * N, D).float()
+            _, lp, _, v = agent.get_action_and_value(x, buf.actions[:, :, i].reshape(T * N, 3))
+            assert (lp - buf.logprobs[:, :, i].reshape(T * N, 3)).abs().max().item() < 5e-3
+            assert (v.squeeze(-1) - buf.values[:T, :, i].reshape(T * N)).abs().max().item() < 5e-3
+        assert (buf.actions[0] != buf.actions[1]).any() and (buf.actions[:, :, 0] != buf.actions[:, :, A - 1]).any()
+    assert ctr == [T, 2 * T, 3 * T]          # one advance per tick, eager and replayed alike
+    env.close()
