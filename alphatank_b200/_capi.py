@@ -42,7 +42,7 @@ ENV_STATE_DT = np.dtype([("n_bullets", "i4"), ("tick", "i4"), ("training_step", 
 EXPORTS = ("at_create at_destroy at_obs_dim at_obs_rows at_action_rows at_num_walls at_num_envs at_reset at_step at_step_norm "
            "at_step_host at_get_info at_get_terminal_info at_get_state at_set_state at_synthetic_actions at_bfs_batch at_generate_mazes "
            "at_get_luts at_tick_normalize at_sample_heads at_policy_tail at_policy_mid_tail at_debug_block_times at_set_weakness at_launch_count at_last_error at_version "
-           "at_observe at_set_reward_mode at_get_tank_columns at_forget_host_buffers at_policy_first at_policy_forward at_obs_static_range at_step_norm16 at_policy_forward16 at_policy_debug_stamps at_set_rows_mode").split()
+           "at_observe at_set_reward_mode at_get_tank_columns at_forget_host_buffers at_policy_first at_policy_forward at_obs_static_range at_step_norm16 at_policy_forward16 at_policy_debug_stamps at_set_rows_mode at_step_host_u8").split()
 
 _lib = None
 
@@ -81,6 +81,7 @@ def lib():
     L.at_reset.argtypes = [vp, vp, vp, vp]
     L.at_step.argtypes = [vp, vp, vp, vp, vp, vp]
     L.at_step_host.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.at_step_host_u8.argtypes = [vp, vp, vp, vp, vp, vp]
     L.at_step_norm.argtypes = [vp, vp, vp, vp, C.c_float, vp, vp, vp]
     L.at_step_norm16.argtypes = [vp, vp, vp, vp, C.c_float, vp, vp, vp]
     L.at_get_info.argtypes = [vp, vp, vp, vp, vp, vp]

@@ -175,14 +175,17 @@ class BatchedTankEnv:
         if self._h_rewards is None:
             self._h_rewards = torch.zeros((self.num_envs, self.R), dtype=torch.float32).pin_memory()
             self._h_done = torch.zeros((self.num_envs,), dtype=torch.uint8).pin_memory()
-        ap = None
+        ap, fn = None, self.L.at_step_host
         if self.A:
-            if not (isinstance(h_actions, torch.Tensor) and h_actions.dtype == torch.int32 and h_actions.is_contiguous()
-                    and h_actions.device.type == "cpu"):
+            if isinstance(h_actions, torch.Tensor) and h_actions.dtype == torch.uint8 and h_actions.is_contiguous() \
+                    and h_actions.device.type == "cpu":
+                fn = self.L.at_step_host_u8          # one byte per action: a quarter of the PCIe traffic
+            elif not (isinstance(h_actions, torch.Tensor) and h_actions.dtype == torch.int32 and h_actions.is_contiguous()
+                      and h_actions.device.type == "cpu"):
                 h_actions = torch.as_tensor(np.asarray(h_actions), dtype=torch.int32).contiguous()
             ap = C.c_void_p(h_actions.data_ptr())
-        _capi.check(self.L.at_step_host(self.h, ap, _ptr(self.obs), C.c_void_p(self._h_rewards.data_ptr()),
-                                        C.c_void_p(self._h_done.data_ptr()), self._stream()), "at_step_host")
+        _capi.check(fn(self.h, ap, _ptr(self.obs), C.c_void_p(self._h_rewards.data_ptr()),
+                       C.c_void_p(self._h_done.data_ptr()), self._stream()), "at_step_host")
         return self.obs, self._h_rewards, self._h_done
 
     def set_rows_mode(self, persistent_buffers):

@@ -1183,6 +1183,7 @@ struct at_env {
     void *arena;  // one allocation, carved into the SoA columns (at_host.h arena_layout)
     size_t arena_bytes;
     int32_t *d_actions_scratch;
+    uint8_t *d_actions_u8;    // at_step_host_u8: the packed actions as they arrive (allocated on first use)
     float *d_rewards_scratch;
     uint8_t *d_done_scratch;
     HostLuts luts;
@@ -1333,6 +1334,7 @@ int at_create(const at_config *cfg, int64_t n_envs, int64_t env_id_base, uint64_
     cudaMemset(b + L.o_ttick, 0xFF, 4 * (size_t)n_envs);   // no terminal info latched yet (tick starts at 0)
     bind_state(env->st, b, L, n_envs);
     env->d_actions_scratch = (int32_t *)(b + L.o_act);
+    env->d_actions_u8 = nullptr;
     env->d_rewards_scratch = (float *)(b + L.o_rw);
     env->d_done_scratch = (uint8_t *)(b + L.o_dn);
     cudaMemcpy(b + L.o_trig, env->luts.trig.data(), 722 * 8, cudaMemcpyHostToDevice);
@@ -1513,6 +1515,7 @@ int at_destroy(at_env *env) {
     DeviceGuard guard(env->device);
     cudaDeviceSynchronize();
     cudaFree(env->arena);
+    if (env->d_actions_u8) cudaFree(env->d_actions_u8);
     if (env->d_sig_counter) cudaFree(env->d_sig_counter);
     if (env->h_sig_flag) cudaFreeHost((void *)env->h_sig_flag);
     if (env->copy_stream) cudaStreamDestroy(env->copy_stream);
@@ -1576,8 +1579,14 @@ static void *mapped_alias(const void *h) {
     return nullptr;
 }
 
-int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
-                 void *stream) {
+// u8 -> i32 expansion of packed host actions (at_step_host_u8): runs on the copy stream right behind the DMA copy
+__global__ void expand_actions_kernel(const uint8_t *__restrict__ src, int32_t *__restrict__ dst, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (int32_t)src[i];
+}
+
+static int step_host_impl(at_env *env, const void *h_actions, int action_bytes, float *d_obs, float *h_rewards, uint8_t *h_done,
+                          void *stream) {
     if (!env) return fail(AT_ERR_ARG, "at_step_host: null handle");
     if ((env->k.rows > 0 && !h_rewards) || !h_done) return fail(AT_ERR_ARG, "at_step_host: rewards / done must not be null");
     if (env->k.act_rows > 0 && !h_actions) return fail(AT_ERR_ARG, "at_step_host: this mode needs an actions array");
@@ -1604,7 +1613,8 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
         }
     }
     static const bool allow_direct = !getenv("AT_STEP_HOST_COPY");  // diagnostic switch: force the copy path
-    const bool direct = allow_direct && (env->k.act_rows == 0 || dev[0]) && (env->k.rows == 0 || dev[1]) && dev[2];
+    const bool direct = allow_direct && (env->k.act_rows == 0 || dev[0]) && (env->k.rows == 0 || dev[1]) && dev[2] &&
+                        (action_bytes == 4 || env->k.act_rows == 0 || (env->copy_stream && env->ev_actions));   // (packed actions always go by DMA)
     if (direct) {
         // The call returns as soon as rewards / done are in host memory: the simulation kernel's last block posts the
         // step's epoch into a mapped host word and the host spins on it - no driver synchronisation, and the rows
@@ -1617,9 +1627,16 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
         // Rewards / done: posted writes from the kernel straight into the mapped host buffers.
         static const bool dma = !getenv("AT_STEP_HOST_MAPPED_ACTIONS");   // diagnostic switch: the kernel fetches them
         const int32_t *acts = (const int32_t *)dev[0];
-        if (dma && env->k.act_rows > 0 && env->copy_stream && env->ev_actions) {
-            CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)N * env->k.act_rows * 3 * 4,
-                                     cudaMemcpyHostToDevice, env->copy_stream));
+        const int64_t n_act = N * env->k.act_rows * 3;
+        if (action_bytes == 1 && env->k.act_rows > 0 && !env->d_actions_u8) CUDA_TRY(cudaMalloc((void **)&env->d_actions_u8, (size_t)n_act));
+        if ((dma || action_bytes == 1) && env->k.act_rows > 0 && env->copy_stream && env->ev_actions) {
+            if (action_bytes == 1) {   // a quarter of the bytes across PCIe, widened on the device
+                CUDA_TRY(cudaMemcpyAsync(env->d_actions_u8, h_actions, (size_t)n_act, cudaMemcpyHostToDevice, env->copy_stream));
+                expand_actions_kernel<<<(int)((n_act + 255) / 256), 256, 0, env->copy_stream>>>(env->d_actions_u8, env->d_actions_scratch, n_act);
+                env->launches += 1;
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)n_act * 4, cudaMemcpyHostToDevice, env->copy_stream));
+            }
             CUDA_TRY(cudaEventRecord(env->ev_actions, env->copy_stream));
             CUDA_TRY(cudaStreamWaitEvent(s, env->ev_actions, 0));
             acts = env->d_actions_scratch;
@@ -1647,9 +1664,17 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
         __sync_synchronize();
         return AT_OK;
     }
-    if (env->k.act_rows > 0)
-        CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)N * env->k.act_rows * 3 * 4,
-                                 cudaMemcpyHostToDevice, s));
+    if (env->k.act_rows > 0) {
+        const int64_t n_act = N * env->k.act_rows * 3;
+        if (action_bytes == 1) {
+            if (!env->d_actions_u8) CUDA_TRY(cudaMalloc((void **)&env->d_actions_u8, (size_t)n_act));
+            CUDA_TRY(cudaMemcpyAsync(env->d_actions_u8, h_actions, (size_t)n_act, cudaMemcpyHostToDevice, s));
+            expand_actions_kernel<<<(int)((n_act + 255) / 256), 256, 0, s>>>(env->d_actions_u8, env->d_actions_scratch, n_act);
+            env->launches += 1;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(env->d_actions_scratch, h_actions, (size_t)n_act * 4, cudaMemcpyHostToDevice, s));
+        }
+    }
     int rc = launch_env_kernel(env, true, env->d_actions_scratch, nullptr, d_obs, env->d_rewards_scratch,
                                env->d_done_scratch, s);
     if (rc != AT_OK) return rc;
@@ -1658,6 +1683,14 @@ int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_r
     CUDA_TRY(cudaMemcpyAsync(h_done, env->d_done_scratch, (size_t)N, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return AT_OK;
+}
+
+int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done, void *stream) {
+    return step_host_impl(env, h_actions, 4, d_obs, h_rewards, h_done, stream);
+}
+
+int at_step_host_u8(at_env *env, const uint8_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done, void *stream) {
+    return step_host_impl(env, h_actions, 1, d_obs, h_rewards, h_done, stream);
 }
 
 int at_observe(at_env *env, float *d_obs, void *stream) {

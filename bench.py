@@ -413,7 +413,8 @@ def run_ours(args):
     value = total_envs * N_AGENTS * steps / (ms * 1e-3)
 
     # end to end through the reference-facing API with HOST action / reward / done buffers
-    h_acts = [acts[t % ring].cpu().pin_memory() for t in range(min(ring, 16))]
+    # actions cross PCIe one byte each (values 0 .. 2; at_step_host_u8 widens them on the device)
+    h_acts = [acts[t % ring].to(torch.uint8).cpu().pin_memory() for t in range(min(ring, 16))]
     e2e_steps = max(min(steps, 100), 10)
     for t in range(3):
         env.step_host(h_acts[t % len(h_acts)])
@@ -480,9 +481,9 @@ def run_ours(args):
                          "ms_per_step": ms_persist, "obs_bytes_written_per_env_step": 4 * 2 * ((240) + (528 - 516)),
                          "note": "at_set_rows_mode(1): static wall / maze columns of the caller's reused buffer not rewritten "
                                  "(2016 instead of 4224 observation bytes per env-step; measured: no faster - the rows kernel is bound by instruction issue, not by its write stream); labelled extra, the headline writes whole rows"}},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N_AGENTS * 3 * 4,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": E * N_AGENTS * 3,
                 "d2h_bytes_per_step": E * N_AGENTS * 4 + E, "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
-                "note": "MultiAgentTeamEnv.step_host: pinned host actions in (DMA copy beside the previous step's rows "
+                "note": "MultiAgentTeamEnv.step_host: pinned host actions in (uint8, DMA copy beside the previous step's rows "
                         "kernel), rewards+done posted into pinned host memory and read by the host every step (the "
                         "call returns when they have landed); observations stay in HBM for the policy"},
         "gpu_launches": launches * world,

@@ -136,6 +136,9 @@ int at_step(at_env *env, const int32_t *d_actions, float *d_obs, float *d_reward
  * such a buffer and may get the same address back for pageable memory calls at_forget_host_buffers first. */
 int at_step_host(at_env *env, const int32_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done,
                  void *stream);
+/* at_step_host with the actions packed one byte each (values 0 .. 2: gym_env.py:26 MultiDiscrete([3, 3, 2])): a quarter of
+ * the bytes across PCIe, widened to int32 on the device right behind the copy. */
+int at_step_host_u8(at_env *env, const uint8_t *h_actions, float *d_obs, float *h_rewards, uint8_t *h_done, void *stream);
 int at_forget_host_buffers(at_env *env);
 
 /* Replaces env._get_observation() (gym_env.py:105-183, gym_env_multi.py:225-304) on the CURRENT state: the

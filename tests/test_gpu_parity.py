@@ -195,13 +195,18 @@ def test_full_size_arena_stress_bullet_saturation():
     assert np.array_equal(so["n_bullets"], st["n_bullets"][:64])
 
 
-def test_step_host_equals_step_and_non_default_stream():
+@pytest.mark.parametrize("dtype, pinned", [(torch.int32, True), (torch.uint8, True), (torch.uint8, False)])
+def test_step_host_equals_step_and_non_default_stream(dtype, pinned):
+    """at_step_host (int32 host actions) and at_step_host_u8 (one byte per action, widened on the device; pinned = the
+    DMA + mapped-results path, pageable = the copy path) against at_step, on a non-default stream."""
     spec = SWEEP["team_vs_bot"]
     a = _gpu(spec, 512, 5, 0, auto_reset=True)
     b = _gpu(spec, 512, 5, 0, auto_reset=True)
     a.reset(); b.reset()
     s = torch.cuda.Stream()
-    h = torch.zeros((512, a.A, 3), dtype=torch.int32).pin_memory()
+    h = torch.zeros((512, a.A, 3), dtype=dtype)
+    if pinned:
+        h = h.pin_memory()
     for t in range(60):
         acts = synthetic_actions(5, np.arange(512), t, a.A)
         h.copy_(torch.as_tensor(acts))
