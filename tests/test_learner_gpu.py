@@ -115,7 +115,7 @@ def test_tick_normalize_kernel_matches_reference_formula():
         # the formula in float64, and what an fp32 evaluation of it can differ by: mean = bm A / (eps + A) is rounded to fp32
         # (half an ulp of |mean|) before x - mean, which cancels when the rows of a column are close - a few ulps of |mean|
         # times 1 / sqrt(var), on top of the ordinary 2e-5.  (Compared with torch's own fp32 CPU evaluation on every column,
-        # one GPU box out of seven reported a 3.2e-4 difference once - the size of exactly this effect - and the other six none.)
+        # one GPU box out of seven reported a 3.2e-4 difference once - the size of this effect; not reproduced, cause unknown.)
         x64 = x.double().cpu()
         A = shape[1]
         bm = x64.mean(dim=1, keepdim=True)
